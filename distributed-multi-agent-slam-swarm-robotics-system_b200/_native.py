@@ -1,0 +1,119 @@
+"""ctypes binding of the C ABI in ``include/occgrid_b200.h`` (liboccgrid_b200.so).
+
+The shared library is built in-tree by :func:`build` (``nvcc -gencode
+arch=compute_100a,code=sm_100a``); there is NO fallback: if it is missing or a CUDA device is
+absent, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, 'csrc')
+LIB_PATH = os.path.join(PKG_DIR, 'liboccgrid_b200.so')
+SOURCES = ['occgrid_integrate.cu', 'occgrid_tiled.cu', 'mapmerge.cu']
+HEADERS = ['common.cuh', 'beam_expand.cuh', 'sincos_dd.cuh', os.path.join('..', '..', 'include', 'occgrid_b200.h')]
+
+STRATEGY = {'auto': -1, 'global_atomic': 0, 'tiled': 1}
+COUNTER_NAMES = ('packets', 'accepted', 'dropped', 'bad_pose', 'beams', 'hits', 'updates', 'slowpath',
+                 'owned_updates', 'records')
+N_COUNTERS = 16
+
+
+class OccGridError(RuntimeError):
+    pass
+
+
+class Geom(C.Structure):
+    """struct occgrid_geom"""
+    _fields_ = [('ox', C.c_double), ('oy', C.c_double), ('res', C.c_double),
+                ('size_x', C.c_int32), ('size_y', C.c_int32),
+                ('win_x0', C.c_int32), ('win_y0', C.c_int32),
+                ('win_w', C.c_int32), ('win_h', C.c_int32)]
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA translation unit for sm_100a into liboccgrid_b200.so (in-tree)."""
+    if not force and not _stale():
+        return LIB_PATH
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    cmd = ['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+           '-Xcompiler', '-fPIC', '-shared', '-o', LIB_PATH] + srcs
+    if verbose:
+        cmd.insert(1, '-Xptxas=-v')
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise OccGridError('nvcc failed:\n' + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the library (never builds implicitly on a GPU box: the .so travels with the repo)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OccGridError(f'{LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                           '(needs nvcc).  There is no CPU fallback.')
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32, u32, sz = C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_size_t
+    gp = C.POINTER(Geom)
+    L.occgrid_abi_version.restype = i32
+    L.occgrid_last_error.restype = C.c_char_p
+    L.occgrid_workspace_bytes.restype = sz
+    L.occgrid_workspace_bytes.argtypes = [gp, i64, i32]
+    L.occgrid_workspace_reset.restype = i32
+    L.occgrid_workspace_reset.argtypes = [vp, sz, vp]
+    L.occgrid_integrate_packets.restype = i32
+    L.occgrid_integrate_packets.argtypes = [gp, vp, i64, i32, i32, vp, vp, vp, i32, vp, vp, sz, vp, i32, vp]
+    L.occgrid_update_rays.restype = i32
+    L.occgrid_update_rays.argtypes = [gp, vp, vp, i64, vp, vp, sz, vp, i32, vp]
+    L.occgrid_scatter_probe.restype = i32
+    L.occgrid_scatter_probe.argtypes = [i32, vp, i64, i64, u32, vp]
+    _bind_merge(L)
+    _lib = L
+    return L
+
+
+def _bind_merge(L):
+    """mapmerge_* entry points (bound when present in the library)."""
+    vp, i64, i32, sz, dbl = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_double
+    if not hasattr(L, 'mapmerge_extract_transform'):
+        return
+    L.mapmerge_extract_transform.restype = i32
+    L.mapmerge_extract_transform.argtypes = [vp, i32, i32, dbl, dbl, dbl, vp, vp, i64, vp, vp, sz, vp]
+    L.mapmerge_bounds.restype = i32
+    L.mapmerge_bounds.argtypes = [vp, i64, vp, vp]
+    L.mapmerge_voxel_downsample.restype = i32
+    L.mapmerge_voxel_downsample.argtypes = [vp, i64, vp, dbl, vp, i64, vp, vp, sz, vp]
+    L.mapmerge_voxel_workspace_bytes.restype = sz
+    L.mapmerge_voxel_workspace_bytes.argtypes = [i64, i64]
+    L.mapmerge_rasterise.restype = i32
+    L.mapmerge_rasterise.argtypes = [vp, i64, dbl, dbl, dbl, i32, i32, vp, vp]
+    L.mapmerge_fuse_max.restype = i32
+    L.mapmerge_fuse_max.argtypes = [vp, vp, i64, vp]
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().occgrid_last_error().decode('utf-8', 'replace')
+        raise OccGridError(f'{what} failed (rc={rc}): {msg}')
+
+
+def last_error():
+    return lib().occgrid_last_error().decode('utf-8', 'replace')

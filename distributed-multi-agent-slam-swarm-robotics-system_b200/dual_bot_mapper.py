@@ -1,0 +1,393 @@
+"""Drop-in surface of the reference's ``server_nodes/dual_bot_mapper.py`` hot path.
+
+Same names, argument meaning and cell conventions as the reference (cited per item, paths
+relative to the reference root), with the grid resident in B200 HBM and every update executed
+by the hand-written sm_100a kernels behind ``include/occgrid_b200.h``:
+
+* ``OccupancyGrid(size, resolution, origin_x, origin_y)``  — :110-179.  ``.grid`` reads back as
+  ``np.int8 (size, size)`` indexed ``[gy, gx]`` with -1 / 0 / 100 (:92-94, :119, :150).
+* ``update_ray(robot_x, robot_y, hit_x, hit_y, hit_valid)``    — :136-156 (a batch of one).
+* ``update_packets(...)`` — NEW batched entry equal to running the per-packet loop body
+  (:826-903) over the records in buffer order.
+* ``PoseGraphSLAM`` — :244-338, host-side and sequential as in the reference; it only feeds the
+  per-packet drift table (:855-857, :908-914) to the device path.
+
+PyTorch owns the device buffers and streams; there is no CPU fallback — without the CUDA
+library or a CUDA device the compute entry points raise.
+"""
+from __future__ import annotations
+
+import math
+import struct
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import Geom, OccGridError
+
+# -- protocol (:41-54) ---------------------------------------------------------
+PACKET_FMT = '<4sBfffiIffffB'
+PACKET_SIZE = struct.calcsize(PACKET_FMT)
+PACKET_FMT_V1 = '<4sBfffiIffff'
+PACKET_SIZE_V1 = struct.calcsize(PACKET_FMT_V1)
+ZONE_FMT = '<4sffff'
+ZONE_SIZE = struct.calcsize(ZONE_FMT)
+TARGET_FMT = '<4sff'
+TARGET_SIZE = struct.calcsize(TARGET_FMT)
+
+# -- trust filter (:57-58) and sensor angles (:61-66) --------------------------
+MAX_DIST_M = 1.20
+MIN_DIST_M = 0.05
+SENSOR_ANGLES_RAD = {'front': 0.0, 'left': math.pi / 2, 'back': math.pi, 'right': -math.pi / 2}
+
+# -- landmark types (:69-74) ---------------------------------------------------
+LM_NONE, LM_CORNER_L, LM_CORNER_R, LM_CORRIDOR, LM_DEAD_END, LM_OPEN = range(6)
+
+# -- occupancy grid (:87-94) ---------------------------------------------------
+GRID_RESOLUTION = 0.05
+GRID_SIZE = 200
+GRID_ORIGIN_X = -5.0
+GRID_ORIGIN_Y = -5.0
+CELL_UNKNOWN = -1
+CELL_FREE = 0
+CELL_OCCUPIED = 100
+
+# -- SLAM constants (:97-99) ---------------------------------------------------
+CLOSURE_RADIUS = 0.60
+MIN_POSES_BETWEEN = 30
+CLOSURE_CORRECTION = 0.5
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise OccGridError('no CUDA device: the occupancy-grid engine has no CPU fallback')
+    dev = torch.device(device)
+    if dev.type != 'cuda':
+        raise OccGridError(f'device must be a CUDA device, got {device!r}')
+    return dev
+
+
+def normalise_datagrams(datagrams):
+    """Host batcher rule of the ingest loop (:828-838): 42-byte datagrams are v2, 41-byte ones
+    v1 (landmark := LM_NONE), any other size is skipped.  Returns (uint8 [m, 42], kept indices)."""
+    keep = [i for i, p in enumerate(datagrams) if len(p) in (PACKET_SIZE, PACKET_SIZE_V1)]
+    arr = np.zeros((len(keep), PACKET_SIZE), np.uint8)
+    for j, i in enumerate(keep):
+        p = datagrams[i]
+        arr[j, :len(p)] = np.frombuffer(bytes(p), np.uint8)
+    return arr, np.asarray(keep, np.int64)
+
+
+class OccupancyGrid:
+    """2D occupancy grid for mapping (reference :110-179), resident on one B200.
+
+    Extra keyword arguments (no reference counterpart):
+      device        CUDA device (default current)
+      window        (x0, y0, w, h): this object holds only that window of the global
+                    ``size`` x ``size`` grid (one spatial tile of a multi-GPU map)
+      strategy      'auto' | 'tiled' | 'global_atomic' — kernel family; results are identical
+      max_batch     largest number of records a single ``update_packets`` call may carry
+                    (sizes the device workspace once; grown on demand)
+    """
+
+    def __init__(self, size=GRID_SIZE, resolution=GRID_RESOLUTION,
+                 origin_x=GRID_ORIGIN_X, origin_y=GRID_ORIGIN_Y, *,
+                 device='cuda', window=None, strategy='auto', max_batch=1 << 16):
+        self.size = int(size)
+        self.res = float(resolution)
+        self.ox = float(origin_x)
+        self.oy = float(origin_y)
+        self.device = _require_cuda(device)
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        self.window = tuple(int(v) for v in window) if window is not None else (0, 0, self.size, self.size)
+        x0, y0, w, h = self.window
+        self._geom = Geom(self.ox, self.oy, self.res, self.size, self.size, x0, y0, w, h)
+        self._strategy = _native.STRATEGY[strategy]
+        self._lib = _native.lib()
+        with torch.cuda.device(self.device):
+            self.grid_tensor = torch.full((h, w), CELL_UNKNOWN, dtype=torch.int8, device=self.device)
+            self._counters = torch.zeros(_native.N_COUNTERS, dtype=torch.int64, device=self.device)
+        self._ws = None
+        self._ws_ray = None
+        self._ws_capacity = 0
+        self._host_cache = None
+        self._pinned = None
+        self._ensure_workspace(int(max_batch))
+
+    # ---- workspace -----------------------------------------------------------------------
+    def _ensure_workspace(self, n_packets):
+        if self._ws is not None and n_packets <= self._ws_capacity:
+            return
+        cap = max(n_packets, 1)
+        nbytes = self._lib.occgrid_workspace_bytes(self._geom, cap, self._strategy)
+        if nbytes == 0:
+            raise OccGridError('occgrid_workspace_bytes: ' + _native.last_error())
+        with torch.cuda.device(self.device):
+            self._ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        self._ws_capacity = cap
+
+    def _ray_workspace(self):
+        if self._ws_ray is None:
+            nbytes = self._lib.occgrid_workspace_bytes(self._geom, 0, _native.STRATEGY['global_atomic'])
+            if self._strategy == _native.STRATEGY['global_atomic']:
+                self._ws_ray = self._ws
+            else:
+                with torch.cuda.device(self.device):
+                    self._ws_ray = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        return self._ws_ray
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ---- reference surface ---------------------------------------------------------------
+    @property
+    def grid(self):
+        """Host view of the grid, ``np.int8 [gy, gx]`` (:119).  Synchronises and copies; the
+        copy is cached until the next update.  Readers in the reference index it directly
+        (renderer :512, frontiers :189-193)."""
+        if self._host_cache is None:
+            self._host_cache = self.grid_tensor.cpu().numpy()
+        return self._host_cache
+
+    def world_to_grid(self, wx, wy):
+        """:121-125 — true division then int() truncation toward zero."""
+        gx = int((wx - self.ox) / self.res)
+        gy = int((wy - self.oy) / self.res)
+        return gx, gy
+
+    def grid_to_world(self, gx, gy):
+        """:127-131 — cell centre."""
+        wx = self.ox + (gx + 0.5) * self.res
+        wy = self.oy + (gy + 0.5) * self.res
+        return wx, wy
+
+    def in_bounds(self, gx, gy):
+        """:133-134"""
+        return 0 <= gx < self.size and 0 <= gy < self.size
+
+    def _bresenham(self, x0, y0, x1, y1):
+        """:158-179 — host helper kept for API parity (the device walks the same line)."""
+        cells = []
+        dx, dy = abs(x1 - x0), abs(y1 - y0)
+        sx = 1 if x0 < x1 else -1
+        sy = 1 if y0 < y1 else -1
+        err = dx - dy
+        x, y = x0, y0
+        while True:
+            cells.append((x, y))
+            if x == x1 and y == y1:
+                return cells
+            e2 = 2 * err
+            if e2 > -dy:
+                err -= dy
+                x += sx
+            if e2 < dx:
+                err += dx
+                y += sy
+
+    def update_ray(self, robot_x, robot_y, hit_x, hit_y, hit_valid):
+        """:136-156.  One ray = a batch of one through the same kernels."""
+        rays = np.array([[robot_x, robot_y, hit_x, hit_y]], dtype=np.float64)
+        self.update_rays(rays, np.array([1 if hit_valid else 0], dtype=np.uint8))
+
+    # ---- batched entries -----------------------------------------------------------------
+    def update_rays(self, rays, hit_valid):
+        """Batched ``update_ray``: rays float64 [n, 4] = (robot_x, robot_y, hit_x, hit_y), applied
+        in index order with the reference's last-writer-wins (:148-156)."""
+        with torch.cuda.device(self.device):
+            r = torch.as_tensor(rays, dtype=torch.float64).reshape(-1, 4)
+            h = torch.as_tensor(hit_valid).to(torch.uint8).reshape(-1)
+            if r.shape[0] != h.shape[0]:
+                raise ValueError('rays and hit_valid differ in length')
+            r = r.to(self.device, non_blocking=True).contiguous()
+            h = h.to(self.device, non_blocking=True).contiguous()
+            ws = self._ray_workspace()
+            rc = self._lib.occgrid_update_rays(self._geom, r.data_ptr(), h.data_ptr(), r.shape[0],
+                                               self.grid_tensor.data_ptr(), ws.data_ptr(), ws.numel(),
+                                               self._counters.data_ptr(), self._strategy, self._stream())
+            _native.check(rc, 'occgrid_update_rays')
+        self._host_cache = None
+
+    def _agent_table(self, separation, agent_offsets):
+        if agent_offsets is None:
+            # reference rule: ids {1, 2}; only agent 2 is shifted, along x (:842, :851-852)
+            tab = np.array([[0.0, 0.0], [0.0, 0.0], [float(separation), 0.0]], np.float64)
+        else:
+            tab = np.ascontiguousarray(agent_offsets, np.float64).reshape(-1, 2)
+        return torch.from_numpy(tab).to(self.device)
+
+    def stage_packets(self, packets):
+        """Host -> device staging of a record buffer.  Accepts bytes/bytearray/memoryview,
+        numpy or torch uint8 ([n, stride] or flat, stride inferred as 42 for flat input), or a
+        list of datagrams (normalised with the ingest rule, :828-838).  Returns
+        (uint8 cuda tensor [n, stride], kept_indices or None)."""
+        kept = None
+        if isinstance(packets, (list, tuple)):
+            packets, kept = normalise_datagrams(packets)
+        if isinstance(packets, (bytes, bytearray, memoryview)):
+            packets = np.frombuffer(packets, np.uint8)
+        if isinstance(packets, np.ndarray):
+            packets = torch.from_numpy(np.ascontiguousarray(packets, np.uint8))
+        if not isinstance(packets, torch.Tensor) or packets.dtype != torch.uint8:
+            raise TypeError('packets must be bytes, a uint8 array/tensor or a list of datagrams')
+        if packets.dim() == 1:
+            if packets.numel() % PACKET_SIZE:
+                raise ValueError('flat packet buffer length is not a multiple of 42')
+            packets = packets.reshape(-1, PACKET_SIZE)
+        if packets.device.type != 'cuda':
+            n = packets.numel()
+            if self._pinned is None or self._pinned.numel() < n:
+                self._pinned = torch.empty(max(n, 1 << 16), dtype=torch.uint8).pin_memory()
+            stage = self._pinned[:n].view(packets.shape)
+            stage.copy_(packets)
+            packets = stage.to(self.device, non_blocking=True)
+        return packets.contiguous(), kept
+
+    def update_packets(self, packets, separation=0.0, drift=None, agent_offsets=None,
+                       agent_idx=None, rec_len=PACKET_SIZE):
+        """Integrate a batch of QuasarPackets: equal to running the reference loop body
+        (:826-903) over the records in buffer order.
+
+        separation     ``--separation`` (:716): x offset of agent 2 (:851-852)
+        drift          None or float64 [n, 2]: SLAM drift in force for each record (:855-857)
+        agent_offsets  EXTENSION: float64 [A+1, 2] start offsets; ids 1..A accepted
+        agent_idx      EXTENSION: int32 [n] agent index replacing the uint8 wire id
+        """
+        with torch.cuda.device(self.device):
+            pk, kept = self.stage_packets(packets)
+            n, stride = pk.shape
+            if n == 0:
+                return
+            self._ensure_workspace(n)
+            tab = self._agent_table(separation, agent_offsets)
+            d_ptr = None
+            if drift is not None:
+                d = torch.as_tensor(drift, dtype=torch.float64)
+                if kept is not None and d.shape[0] != n:
+                    d = d[torch.from_numpy(kept)]
+                d = d.reshape(n, 2).to(self.device, non_blocking=True).contiguous()
+                d_ptr = d.data_ptr()
+            a_ptr = None
+            if agent_idx is not None:
+                a = torch.as_tensor(agent_idx, dtype=torch.int32).reshape(n).to(self.device, non_blocking=True).contiguous()
+                a_ptr = a.data_ptr()
+            rc = self._lib.occgrid_integrate_packets(
+                self._geom, pk.data_ptr(), n, stride, rec_len, a_ptr, d_ptr, tab.data_ptr(), tab.shape[0] - 1,
+                self.grid_tensor.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                self._counters.data_ptr(), self._strategy, self._stream())
+            _native.check(rc, 'occgrid_integrate_packets')
+        self._host_cache = None
+
+    # ---- bookkeeping ---------------------------------------------------------------------
+    def counters(self, reset=False):
+        """Device-side statistics (see the OCCGRID_C_* enum)."""
+        vals = self._counters.cpu().tolist()
+        if reset:
+            self._counters.zero_()
+        return {k: int(v) for k, v in zip(_native.COUNTER_NAMES, vals)}
+
+    def clear(self):
+        self.grid_tensor.fill_(CELL_UNKNOWN)
+        self._host_cache = None
+
+
+class PoseNode:
+    """:244-258"""
+    __slots__ = ('x', 'y', 'yaw', 'agent_id', 'landmark_type', 'timestamp', 'index',
+                 'corrected_x', 'corrected_y')
+
+    def __init__(self, x, y, yaw, agent_id, landmark_type, timestamp, index):
+        self.x, self.y, self.yaw = x, y, yaw
+        self.agent_id, self.landmark_type = agent_id, landmark_type
+        self.timestamp, self.index = timestamp, index
+        self.corrected_x, self.corrected_y = x, y
+
+
+class PoseGraphSLAM:
+    """Landmark loop closure (:261-338).  Sequential host logic, as in the reference: the hot
+    path only consumes its output as the per-packet drift table."""
+
+    def __init__(self, verbose=False):
+        self.nodes = []
+        self.landmarks = []
+        self.closures = []
+        self.last_closure_idx = {1: -MIN_POSES_BETWEEN, 2: -MIN_POSES_BETWEEN}
+        self.verbose = verbose
+
+    def add_pose(self, x, y, yaw, agent_id, landmark_type, timestamp):
+        idx = len(self.nodes)
+        node = PoseNode(x, y, yaw, agent_id, landmark_type, timestamp, idx)
+        self.nodes.append(node)
+        if landmark_type == LM_NONE:
+            return False, 0.0, 0.0
+        result = self._check_closure(node)
+        self.landmarks.append((x, y, landmark_type, idx))
+        return result
+
+    def _check_closure(self, node):
+        recent = node.index - self.last_closure_idx.get(node.agent_id, -999) < MIN_POSES_BETWEEN
+        for lm_x, lm_y, lm_type, lm_idx in self.landmarks:
+            if lm_type != node.landmark_type or node.index - lm_idx < MIN_POSES_BETWEEN or recent:
+                continue
+            dist = math.sqrt((node.x - lm_x) ** 2 + (node.y - lm_y) ** 2)
+            if dist < CLOSURE_RADIUS:
+                corr_dx = (lm_x - node.x) * CLOSURE_CORRECTION
+                corr_dy = (lm_y - node.y) * CLOSURE_CORRECTION
+                self.closures.append((lm_idx, node.index, corr_dx, corr_dy))
+                self.last_closure_idx[node.agent_id] = node.index
+                if self.verbose:
+                    print(f'[SLAM] LOOP CLOSURE! Agent {node.agent_id} | Dist: {dist:.2f}m | '
+                          f'Correction: ({corr_dx:.3f}, {corr_dy:.3f})')
+                return True, corr_dx, corr_dy
+        return False, 0.0, 0.0
+
+    def get_correction_for_agent(self, agent_id):
+        tx = ty = 0.0
+        for _, node_idx, cdx, cdy in self.closures:
+            if self.nodes[node_idx].agent_id == agent_id:
+                tx += cdx
+                ty += cdy
+        return tx, ty
+
+
+def slam_drift_table(datagrams, separation=0.0, slam=None, timestamps=None):
+    """Run the sequential part of the ingest loop (:826-857, :908-914) on the host and return
+    the drift (cdx, cdy) in force for every datagram, float64 [n, 2] — the input
+    ``OccupancyGrid.update_packets(drift=...)`` needs to reproduce a SLAM-corrected session."""
+    slam = slam if slam is not None else PoseGraphSLAM()
+    drift = {1: (0.0, 0.0), 2: (0.0, 0.0)}
+    out = np.zeros((len(datagrams), 2), np.float64)
+    for k, data in enumerate(datagrams):
+        lm = LM_NONE
+        if len(data) == PACKET_SIZE:
+            magic, agent_id, rx, ry, ryaw, _, _, _, _, _, _, lm = struct.unpack(PACKET_FMT, data)
+        elif len(data) == PACKET_SIZE_V1:
+            magic, agent_id, rx, ry, ryaw = struct.unpack(PACKET_FMT_V1, data)[:5]
+        else:
+            continue
+        if magic != b'QSRL' or agent_id not in (1, 2):
+            continue
+        if agent_id == 2:
+            rx += separation
+        cdx, cdy = drift[agent_id]
+        out[k] = (cdx, cdy)
+        rx += cdx
+        ry += cdy
+        if not (math.isfinite(rx) and math.isfinite(ry) and math.isfinite(ryaw)):
+            continue
+        closure, ndx, ndy = slam.add_pose(rx, ry, ryaw, agent_id, lm,
+                                          timestamps[k] if timestamps is not None else float(k))
+        if closure:
+            drift[agent_id] = (drift[agent_id][0] + ndx, drift[agent_id][1] + ndy)
+    return out, slam
+
+
+def replay_session(datagrams, grid=None, separation=0.0, use_slam=True, **grid_kwargs):
+    """Headless restatement of ``main()``'s ingest loop for a recorded session: host SLAM
+    chain -> drift table -> one batched device integration.  Returns (grid, slam)."""
+    grid = grid if grid is not None else OccupancyGrid(**grid_kwargs)
+    drift, slam = (slam_drift_table(datagrams, separation) if use_slam else (None, None))
+    grid.update_packets(list(datagrams), separation=separation, drift=drift)
+    return grid, slam

@@ -1,0 +1,148 @@
+/*
+ * occgrid_b200 — C ABI of the B200-native occupancy-grid integration and map-fusion engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of
+ * deevinandu/Distributed-Multi-Agent-SLAM-Swarm-Robotics-System:
+ *
+ *   QuasarPacket batch -> pose correction -> 4 beams -> integer Bresenham -> int8 grid scatter
+ *       (server_nodes/dual_bot_mapper.py:41-46, 826-903, 110-179)
+ *   agent grids -> occupied-cell extraction -> rigid transform -> voxel fuse -> rasterise
+ *       (server_nodes/map_merger.py:35-127)
+ *
+ * The reference is pure Python and has no FFI of its own; the entry points below are what a
+ * ctypes binding in dual_bot_mapper.py / map_merger.py would call (INTEGRATION.md shows the
+ * stub).  Conventions:
+ *   - plain pointers and sizes only; every `d_` pointer is DEVICE memory owned by the caller
+ *     (torch in our Python host layer); the library allocates nothing and keeps no global
+ *     state except a thread-local last-error string;
+ *   - every call is asynchronous on the given CUDA stream (`stream` is a cudaStream_t passed
+ *     as void*; NULL = the legacy default stream);
+ *   - return value 0 = ok, <0 = error (see occgrid_last_error()).  Malformed packets are
+ *     counted and skipped, never fatal (dual_bot_mapper.py:838-843 `continue`s);
+ *   - one host thread per stream (the reference path is single-threaded: :797, map_merger.py:132).
+ */
+#ifndef OCCGRID_B200_H
+#define OCCGRID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCCGRID_ABI_VERSION 1
+
+/* Cell values — dual_bot_mapper.py:92-94 (same convention as nav_msgs/OccupancyGrid.data). */
+#define OCCGRID_CELL_UNKNOWN  (-1)
+#define OCCGRID_CELL_FREE       0
+#define OCCGRID_CELL_OCCUPIED 100
+
+/* Wire format — dual_bot_mapper.py:41-46; firmware struct AgentFirmware_Bot1.ino:172-185.
+ * '<4sBfffiIffffB': magic@0 'QSRL', agent_id u8@4, x f32@5, y f32@9, yaw f32@13,
+ * encoder i32@17, v2v u32@21, front/left/back/right f32@25/29/33/37 (metres), landmark u8@41. */
+#define OCCGRID_PACKET_SIZE    42
+#define OCCGRID_PACKET_SIZE_V1 41
+
+/* Error codes */
+#define OCCGRID_OK             0
+#define OCCGRID_E_ARG        (-1)   /* bad argument (null pointer, size, alignment)            */
+#define OCCGRID_E_WORKSPACE  (-2)   /* workspace too small for this call                        */
+#define OCCGRID_E_CUDA       (-3)   /* a CUDA runtime call failed; see occgrid_last_error()      */
+#define OCCGRID_E_RANGE      (-4)   /* geometry outside supported range (ray longer than limit)  */
+
+/* Integration strategies (both hand-written sm_100a kernels; results are identical). */
+#define OCCGRID_STRATEGY_AUTO          (-1)
+#define OCCGRID_STRATEGY_GLOBAL_ATOMIC   0  /* per-cell atomicMax on a global order-stamp plane     */
+#define OCCGRID_STRATEGY_TILED           1  /* beams binned by tile; order stamps resolved in smem  */
+
+/* Grid geometry.  Mirrors OccupancyGrid.__init__ (dual_bot_mapper.py:113-119) plus a window:
+ * `d_grid` holds rows [win_y0, win_y0+win_h) x columns [win_x0, win_x0+win_w) of the global
+ * size_y x size_x grid, row-major ([gy][gx], :150), row stride win_w.  The reference case
+ * is win = whole grid; a spatial tile of a multi-GPU map uses a proper sub-window.  Cells
+ * are clipped one by one (:149,:155), never geometrically. */
+typedef struct occgrid_geom {
+    double  ox, oy;          /* world coordinates of the lower-left corner of cell (0,0) */
+    double  res;             /* metres per cell                                          */
+    int32_t size_x, size_y;  /* global grid extent in cells                              */
+    int32_t win_x0, win_y0;  /* window origin in global cells                            */
+    int32_t win_w, win_h;    /* window extent in cells                                   */
+} occgrid_geom;
+
+/* Counter slots (uint64 each, device memory, accumulated with atomics; caller zeroes). */
+enum {
+    OCCGRID_C_PACKETS = 0,   /* records seen                                              */
+    OCCGRID_C_ACCEPTED,      /* passed magic/agent filter and pose is finite               */
+    OCCGRID_C_DROPPED,       /* bad magic or agent id outside 1..n_agents (:840-843)       */
+    OCCGRID_C_BAD_POSE,      /* NaN/Inf pose: skipped (the reference would crash, :123)     */
+    OCCGRID_C_BEAMS,         /* beams expanded (4 per accepted packet)                     */
+    OCCGRID_C_HITS,          /* beams with MIN_DIST < d <= MAX_DIST (:888)                 */
+    OCCGRID_C_UPDATES,       /* beam-cell updates = sum of max(|dx|,|dy|)+1   */
+    OCCGRID_C_SLOWPATH,      /* beams re-evaluated with double-double sin/cos               */
+    OCCGRID_C_OWNED_UPDATES, /* updates of beams whose start cell lies in this window       */
+    OCCGRID_C_RECORDS,       /* (tile, beam) records binned by the tiled strategy           */
+    OCCGRID_N_COUNTERS = 16
+};
+
+int         occgrid_abi_version(void);
+const char* occgrid_last_error(void);
+
+/* Bytes of device workspace occgrid_integrate_packets / occgrid_update_rays need for up to
+ * `max_packets` records per call under `strategy`.  0 on error. */
+size_t occgrid_workspace_bytes(const occgrid_geom* geom, int64_t max_packets, int strategy);
+
+/* Zero the workspace (once after allocation, and after any failed call). */
+int occgrid_workspace_reset(void* d_workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Batched replacement of the per-packet loop body, dual_bot_mapper.py:826-903:
+ * for each record in buffer order: decode (:828-838), filter (:840-843), pose correction
+ * (:851-857), and for front,left,back,right (:882-886): hit test (:888), endpoint
+ * (:890-891 | :900-902), OccupancyGrid.update_ray (:136-156) with last-writer-wins in
+ * record order, then sensor order.
+ *
+ *   d_packets    n records `stride` bytes apart (stride >= rec_len); 16-byte aligned base
+ *   rec_len      42 (v2) or 41 (v1, no landmark byte) — the landmark is not read on this path
+ *   d_agent_idx  NULL, or int32[n]: out-of-band agent index replacing the wire byte
+ *                (extension for > 255 agents)
+ *   d_drift      NULL, or double[n][2]: SLAM drift (cdx, cdy) in force when record k arrived
+ *                (:855-857; produced sequentially by PoseGraphSLAM on the host, :908-914)
+ *   d_agent_off  double[n_agents+1][2]: start offset of agent a at [a]; ids 1..n_agents are
+ *                accepted.  Reference mode: n_agents = 2, {(0,0),(0,0),(separation,0)} (:851-852)
+ *   d_grid       int8 window (see occgrid_geom), updated in place
+ *   d_counters   NULL or uint64[OCCGRID_N_COUNTERS]
+ */
+int occgrid_integrate_packets(const occgrid_geom* geom,
+                              const uint8_t* d_packets, int64_t n, int stride, int rec_len,
+                              const int32_t* d_agent_idx, const double* d_drift,
+                              const double* d_agent_off, int n_agents,
+                              int8_t* d_grid,
+                              void* d_workspace, size_t workspace_bytes,
+                              uint64_t* d_counters, int strategy, void* stream);
+
+/*
+ * Batched OccupancyGrid.update_ray (dual_bot_mapper.py:136-156) on explicit world-space rays:
+ * d_rays = double[n][4] (robot_x, robot_y, hit_x, hit_y), d_hit = uint8[n] (hit_valid),
+ * applied in index order with last-writer-wins.
+ */
+int occgrid_update_rays(const occgrid_geom* geom,
+                        const double* d_rays, const uint8_t* d_hit, int64_t n,
+                        int8_t* d_grid,
+                        void* d_workspace, size_t workspace_bytes,
+                        uint64_t* d_counters, int strategy, void* stream);
+
+/*
+ * Scatter-roofline microkernels: `n_ops` operations to uniformly random cells.
+ *   kind 0: atomicMax(u32) on a global plane of `plane_cells` words   (red.global.max.u32)
+ *   kind 1: plain 1-byte stores to a global plane of `plane_cells` bytes
+ *   kind 2: atomicMax(u32) on a per-CTA shared-memory tile of `plane_cells` words
+ *   kind 3: plain 4-byte stores to a per-CTA shared-memory tile
+ * Used by bench.py to put a measured ceiling beside the integrate kernels.
+ */
+int occgrid_scatter_probe(int kind, void* d_plane, int64_t plane_cells, int64_t n_ops,
+                          uint32_t seed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCCGRID_B200_H */

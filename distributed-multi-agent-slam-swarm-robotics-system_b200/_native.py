@@ -85,6 +85,9 @@ def lib():
     L.occgrid_update_rays.argtypes = [gp, vp, vp, i64, vp, vp, sz, vp, i32, vp]
     L.occgrid_scatter_probe.restype = i32
     L.occgrid_scatter_probe.argtypes = [i32, vp, i64, i64, u32, vp]
+    L.occgrid_profile_begin.restype = i32
+    L.occgrid_profile_end.restype = i32
+    L.occgrid_profile_end.argtypes = [vp, vp, i32]
     _bind_merge(L)
     _lib = L
     return L
@@ -107,6 +110,24 @@ def _bind_merge(L):
     L.mapmerge_rasterise.argtypes = [vp, i64, dbl, dbl, dbl, i32, i32, vp, vp]
     L.mapmerge_fuse_max.restype = i32
     L.mapmerge_fuse_max.argtypes = [vp, vp, i64, vp]
+
+
+KERNEL_NAMES = ('integrate_global', 'resolve', 'update_rays', 'tile_count', 'tile_scan', 'tile_scatter',
+                'tile_raycast', 'tile_resolve', 'merge_extract', 'merge_bounds', 'merge_voxel', 'merge_raster',
+                'merge_fuse', 'probe')
+
+
+def profile_begin():
+    check(lib().occgrid_profile_begin(), 'occgrid_profile_begin')
+
+
+def profile_end():
+    """-> {kernel name: (total ms, launches)} for kernels launched since profile_begin()."""
+    n = len(KERNEL_NAMES)
+    ms = (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    check(lib().occgrid_profile_end(ms, cnt, n), 'occgrid_profile_end')
+    return {KERNEL_NAMES[i]: (ms[i], cnt[i]) for i in range(n) if cnt[i]}
 
 
 def check(rc, what):

@@ -28,6 +28,21 @@ inline Geom to_geom(const occgrid_geom* g) {
 
 int validate_geom(const occgrid_geom* g);
 
+// Optional per-kernel timing (occgrid_profile_begin/_end): when enabled, every launch of one
+// of our kernels is bracketed by cudaEventRecord on its stream, so bench.py can report the
+// dominant kernel's own duration and the exact number of launches.
+enum KernelId { K_INTEGRATE_GLOBAL = 0, K_RESOLVE, K_UPDATE_RAYS, K_TILE_COUNT, K_TILE_SCAN, K_TILE_SCATTER,
+                K_TILE_RAYCAST, K_TILE_RESOLVE, K_MERGE_EXTRACT, K_MERGE_BOUNDS, K_MERGE_VOXEL, K_MERGE_RASTER,
+                K_MERGE_FUSE, K_PROBE, K_N_KERNELS };
+bool profile_enabled();
+void profile_mark(int kernel_id, cudaStream_t st, bool begin);
+
+struct ProfileScope {
+    int id; cudaStream_t st; bool on;
+    ProfileScope(int id_, cudaStream_t st_) : id(id_), st(st_), on(profile_enabled()) { if (on) profile_mark(id, st, true); }
+    ~ProfileScope() { if (on) profile_mark(id, st, false); }
+};
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Block-wide accumulation of the first N uint64 counter slots: per-thread values -> warp

@@ -12,7 +12,9 @@
 // four beams, issuing one red.global.max.u32 per cell on a window-sized stamp plane; a
 // streaming resolve pass folds the stamps into the int8 grid and re-zeroes the plane.
 // Strategy TILED lives in occgrid_tiled.cu.
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -33,6 +35,25 @@ bool cuda_ok(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return true;
     set_last_error("CUDA error %s (%d) in %s", cudaGetErrorString(e), (int)e, what);
     return false;
+}
+
+// ---- per-kernel profiling hook -----------------------------------------------------------
+struct ProfileState {
+    std::mutex mu;
+    bool on = false;
+    std::vector<cudaEvent_t> ev[K_N_KERNELS];   // begin/end pairs
+};
+static ProfileState g_prof;
+
+bool profile_enabled() { return g_prof.on; }
+
+void profile_mark(int id, cudaStream_t st, bool begin) {
+    (void)begin;
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    g_prof.ev[id].push_back(e);
 }
 
 int validate_geom(const occgrid_geom* g) {
@@ -221,6 +242,7 @@ static int launch_resolve(const occgrid_geom* geom, unsigned int* stamps, int8_t
     if (want < 1) want = 1;
     const size_t cap = (size_t)sm_count() * 8;
     const int blocks = (int)(want < cap ? want : cap);
+    ProfileScope ps(K_RESOLVE, st);
     k_resolve<<<blocks, kThreads, 0, st>>>(stamps, grid, n_cells, vec_ok);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
@@ -241,8 +263,11 @@ int integrate_packets_global(const occgrid_geom* geom, const uint8_t* d_packets,
     unsigned int* stamps = reinterpret_cast<unsigned int*>(d_ws);
     const Geom g = to_geom(geom);
     const long long blocks = (n + kThreads - 1) / kThreads;
-    k_integrate_global<<<(unsigned int)blocks, kThreads, 0, st>>>(g, d_packets, n, stride, d_agent_idx, d_drift,
-                                                                 d_agent_off, n_agents, stamps, d_counters);
+    {
+        ProfileScope ps(K_INTEGRATE_GLOBAL, st);
+        k_integrate_global<<<(unsigned int)blocks, kThreads, 0, st>>>(g, d_packets, n, stride, d_agent_idx, d_drift,
+                                                                     d_agent_off, n_agents, stamps, d_counters);
+    }
     OCC_CUDA_TRY(cudaGetLastError());
     return launch_resolve(geom, stamps, d_grid, st);
 }
@@ -389,9 +414,42 @@ int occgrid_update_rays(const occgrid_geom* geom, const double* d_rays, const ui
     unsigned int* stamps = reinterpret_cast<unsigned int*>(d_workspace);
     cudaStream_t st = (cudaStream_t)stream;
     const long long blocks = (n + kThreads - 1) / kThreads;
-    k_update_rays_global<<<(unsigned int)blocks, kThreads, 0, st>>>(to_geom(geom), d_rays, d_hit, n, stamps, d_counters);
+    {
+        ProfileScope ps(K_UPDATE_RAYS, st);
+        k_update_rays_global<<<(unsigned int)blocks, kThreads, 0, st>>>(to_geom(geom), d_rays, d_hit, n, stamps, d_counters);
+    }
     OCC_CUDA_TRY(cudaGetLastError());
     return launch_resolve(geom, stamps, d_grid, st);
+}
+
+int occgrid_profile_begin(void) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    for (auto& v : g_prof.ev) { for (auto e : v) cudaEventDestroy(e); v.clear(); }
+    g_prof.on = true;
+    return OCCGRID_OK;
+}
+
+int occgrid_profile_end(double* ms_by_kernel, int64_t* launches_by_kernel, int n_slots) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    g_prof.on = false;
+    int rc = OCCGRID_OK;
+    for (int k = 0; k < K_N_KERNELS; ++k) {
+        double ms = 0.0;
+        auto& v = g_prof.ev[k];
+        for (size_t i = 0; i + 1 < v.size(); i += 2) {
+            float t = 0.f;
+            if (cudaEventSynchronize(v[i + 1]) != cudaSuccess || cudaEventElapsedTime(&t, v[i], v[i + 1]) != cudaSuccess) rc = OCCGRID_E_CUDA;
+            ms += t;
+        }
+        if (k < n_slots) {
+            if (ms_by_kernel) ms_by_kernel[k] = ms;
+            if (launches_by_kernel) launches_by_kernel[k] = (int64_t)(v.size() / 2);
+        }
+        for (auto e : v) cudaEventDestroy(e);
+        v.clear();
+    }
+    if (rc != OCCGRID_OK) set_last_error("profile_end: event query failed");
+    return rc;
 }
 
 int occgrid_scatter_probe(int kind, void* d_plane, int64_t plane_cells, int64_t n_ops, uint32_t seed, void* stream) {

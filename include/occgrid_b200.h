@@ -142,6 +142,20 @@ int occgrid_update_rays(const occgrid_geom* geom,
 int occgrid_scatter_probe(int kind, void* d_plane, int64_t plane_cells, int64_t n_ops,
                           uint32_t seed, void* stream);
 
+/*
+ * Measurement hook (bench.py): between _begin and _end every kernel this library launches is
+ * bracketed by CUDA events on its stream.  _end synchronises those events and returns, per
+ * kernel id (OCCGRID_K_*), the summed device time in ms and the number of launches.
+ */
+enum {
+    OCCGRID_K_INTEGRATE_GLOBAL = 0, OCCGRID_K_RESOLVE, OCCGRID_K_UPDATE_RAYS, OCCGRID_K_TILE_COUNT,
+    OCCGRID_K_TILE_SCAN, OCCGRID_K_TILE_SCATTER, OCCGRID_K_TILE_RAYCAST, OCCGRID_K_TILE_RESOLVE,
+    OCCGRID_K_MERGE_EXTRACT, OCCGRID_K_MERGE_BOUNDS, OCCGRID_K_MERGE_VOXEL, OCCGRID_K_MERGE_RASTER,
+    OCCGRID_K_MERGE_FUSE, OCCGRID_K_PROBE, OCCGRID_K_N_KERNELS
+};
+int occgrid_profile_begin(void);
+int occgrid_profile_end(double* ms_by_kernel, int64_t* launches_by_kernel, int n_slots);
+
 #ifdef __cplusplus
 }
 #endif

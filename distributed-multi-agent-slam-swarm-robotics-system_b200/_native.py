@@ -94,21 +94,22 @@ def lib():
 
 
 def _bind_merge(L):
-    """mapmerge_* entry points (bound when present in the library)."""
-    vp, i64, i32, sz, dbl = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_double
-    if not hasattr(L, 'mapmerge_extract_transform'):
-        return
-    L.mapmerge_extract_transform.restype = i32
-    L.mapmerge_extract_transform.argtypes = [vp, i32, i32, dbl, dbl, dbl, vp, vp, i64, vp, vp, sz, vp]
-    L.mapmerge_bounds.restype = i32
-    L.mapmerge_bounds.argtypes = [vp, i64, vp, vp]
-    L.mapmerge_voxel_downsample.restype = i32
-    L.mapmerge_voxel_downsample.argtypes = [vp, i64, vp, dbl, vp, i64, vp, vp, sz, vp]
+    """mapmerge_* entry points (include/occgrid_b200.h)."""
+    vp, i64, i32, sz, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t, C.c_double
+    L.mapmerge_extract_workspace_bytes.restype = sz
+    L.mapmerge_extract_workspace_bytes.argtypes = [i64]
+    L.mapmerge_extract_transform.restype = C.c_int
+    L.mapmerge_extract_transform.argtypes = [vp, i32, i32, dbl, dbl, dbl, vp, vp, vp, i64, vp, vp, vp, vp, sz, vp]
+    L.mapmerge_bounds_workspace_bytes.restype = sz
+    L.mapmerge_bounds.restype = C.c_int
+    L.mapmerge_bounds.argtypes = [vp, vp, vp, vp, vp, sz, vp]
     L.mapmerge_voxel_workspace_bytes.restype = sz
     L.mapmerge_voxel_workspace_bytes.argtypes = [i64, i64]
-    L.mapmerge_rasterise.restype = i32
-    L.mapmerge_rasterise.argtypes = [vp, i64, dbl, dbl, dbl, i32, i32, vp, vp]
-    L.mapmerge_fuse_max.restype = i32
+    L.mapmerge_voxel_downsample.restype = C.c_int
+    L.mapmerge_voxel_downsample.argtypes = [vp, vp, vp, i64, dbl, vp, i64, vp, vp, vp, vp, vp, sz, vp]
+    L.mapmerge_rasterise.restype = C.c_int
+    L.mapmerge_rasterise.argtypes = [vp, vp, vp, dbl, vp, i32, i32, vp, vp]
+    L.mapmerge_fuse_max.restype = C.c_int
     L.mapmerge_fuse_max.argtypes = [vp, vp, i64, vp]
 
 

@@ -1,0 +1,562 @@
+// Map-fusion kernels and their C ABI (include/occgrid_b200.h, mapmerge_* entry points).
+//
+// Reference path replaced: MapMerger.grid_to_pcd / map_callback / publish_global_map,
+// server_nodes/map_merger.py:35-127, with the three Open3D calls on it written out
+// (PointCloud::Transform :58, operator+= :59, VoxelDownSample :60) and the rigid transform
+// supplied by the caller in place of ICP (:45-56).
+//
+// Data layout: a point cloud is two fp64 device arrays (x[], y[]; z == 0 on this path) plus a
+// device-resident int64 count, so a whole merge sequence runs stream-ordered without host
+// round trips.  All arithmetic that decides a cell or voxel index is fp64 with individually
+// rounded operations, in the order the reference evaluates it.
+//
+// Determinism: Open3D's voxel filter emits voxels in hash-map order (unspecified).  We fix the
+// canonical order "ascending (iy, ix)" and sum the points of a voxel in ascending point index,
+// so results are bit-reproducible and equal to the oracle (oracle/merge_oracle.py).
+#include "common.cuh"
+
+namespace occ {
+
+constexpr int kMT = 256;              // threads per CTA
+constexpr int kCellsPerThread = 16;   // one 16-byte load of int8 cells
+constexpr int kChunk = kMT * kCellsPerThread;
+
+// Status word bits (device int32, sticky; checked by the host wrapper at its next sync).
+enum { ST_POINT_OVERFLOW = 1, ST_LATTICE_OVERFLOW = 2 };
+
+struct Xform { double m[16]; int identity; };
+
+// ---- block-level exclusive scan of one unsigned value per thread --------------------------
+__device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, unsigned int* s_warp /* >= 32 */,
+                                                             unsigned int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned int w = (lane < (int)(blockDim.x >> 5)) ? s_warp[lane] : 0u;
+        unsigned int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        s_warp[lane] = winc - w;          // exclusive warp offsets
+        if (lane == 31) s_warp[32] = winc;   // block total
+    }
+    __syncthreads();
+    unsigned int res = s_warp[warp] + inc - v;
+    *total = s_warp[32];
+    __syncthreads();
+    return res;
+}
+
+// ---- a10: occupied-cell extraction (data > 50, map_merger.py:72) --------------------------
+
+__device__ __forceinline__ unsigned int occupied_mask16(const int8_t* __restrict__ grid, long long base, long long n) {
+    unsigned int mask = 0;
+    if (base + 16 <= n && ((reinterpret_cast<uintptr_t>(grid + base) & 15) == 0)) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(grid + base));
+        const int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if ((int8_t)((w[i] >> (8 * b)) & 0xff) > 50) mask |= 1u << (4 * i + b);
+    } else {
+        for (int i = 0; i < 16 && base + i < n; ++i)
+            if (grid[base + i] > 50) mask |= 1u << i;
+    }
+    return mask;
+}
+
+__global__ void __launch_bounds__(kMT)
+k_extract_count(const int8_t* __restrict__ grid, long long n_cells, unsigned int* __restrict__ block_counts) {
+    __shared__ unsigned int s_warp[33];
+    const long long base = ((long long)blockIdx.x * kMT + threadIdx.x) * kCellsPerThread;
+    unsigned int c = base < n_cells ? __popc(occupied_mask16(grid, base, n_cells)) : 0u;
+    unsigned int total;
+    block_exclusive_scan(c, s_warp, &total);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+}
+
+// Single-CTA exclusive scan of the per-block counts; also reserves the output range
+// [old_count, old_count + total) in the destination cloud.
+__global__ void __launch_bounds__(1024)
+k_extract_reserve(unsigned int* __restrict__ block_counts, int n_blocks, long long* __restrict__ d_count,
+                  long long capacity, long long* __restrict__ ws_base, int* __restrict__ status,
+                  long long* __restrict__ d_last_appended) {
+    __shared__ unsigned int s_warp[33];
+    __shared__ unsigned int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int start = 0; start < n_blocks; start += blockDim.x) {
+        const int i = start + threadIdx.x;
+        const unsigned int v = i < n_blocks ? block_counts[i] : 0u;
+        unsigned int total;
+        const unsigned int ex = block_exclusive_scan(v, s_warp, &total);
+        if (i < n_blocks) block_counts[i] = s_carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const long long base = *d_count;
+        long long total = s_carry;
+        if (base + total > capacity) { atomicOr(status, ST_POINT_OVERFLOW); total = 0; }
+        ws_base[0] = base;
+        ws_base[1] = total;
+        *d_count = base + total;
+        if (d_last_appended) *d_last_appended = total;
+    }
+}
+
+// grid_to_pcd (:76-77) fused with PointCloud::Transform (:58).
+__global__ void __launch_bounds__(kMT)
+k_extract_write(const int8_t* __restrict__ grid, long long n_cells, int width, double res, double origin_x,
+                double origin_y, Xform T, const unsigned int* __restrict__ block_offsets,
+                const long long* __restrict__ ws_base, double* __restrict__ px, double* __restrict__ py) {
+    __shared__ unsigned int s_warp[33];
+    if (ws_base[1] == 0) return;
+    const long long base = ((long long)blockIdx.x * kMT + threadIdx.x) * kCellsPerThread;
+    const unsigned int mask = base < n_cells ? occupied_mask16(grid, base, n_cells) : 0u;
+    unsigned int total;
+    unsigned int off = block_exclusive_scan(__popc(mask), s_warp, &total);
+    long long dst = ws_base[0] + block_offsets[blockIdx.x] + off;
+    unsigned int m = mask;
+    while (m) {
+        const int i = __ffs(m) - 1;
+        m &= m - 1;
+        const long long c = base + i;
+        const long long row = c / width, col = c - row * width;
+        double x = OCC_DADD(OCC_DMUL((double)col, res), origin_x);       // :77
+        double y = OCC_DADD(OCC_DMUL((double)row, res), origin_y);       // :76
+        if (!T.identity) {
+            const double w = OCC_DADD(OCC_DADD(OCC_DMUL(T.m[12], x), OCC_DMUL(T.m[13], y)), T.m[15]);
+            const double tx = OCC_DADD(OCC_DADD(OCC_DMUL(T.m[0], x), OCC_DMUL(T.m[1], y)), T.m[3]);
+            const double ty = OCC_DADD(OCC_DADD(OCC_DMUL(T.m[4], x), OCC_DMUL(T.m[5], y)), T.m[7]);
+            x = OCC_DDIV(tx, w);
+            y = OCC_DDIV(ty, w);
+        }
+        px[dst] = x;
+        py[dst] = y;
+        ++dst;
+    }
+}
+
+// ---- bounds (GetMinBound/GetMaxBound; publish_global_map :95-98) ---------------------------
+
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__global__ void __launch_bounds__(kMT)
+k_bounds_partial(const double* __restrict__ px, const double* __restrict__ py, const long long* __restrict__ d_count,
+                 double* __restrict__ partial /* gridDim.x * 4 */) {
+    __shared__ double s[4][kMT / 32];
+    const long long n = *d_count;
+    double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
+        const double x = px[i], y = py[i];
+        mnx = fmin(mnx, x); mxx = fmax(mxx, x);
+        mny = fmin(mny, y); mxy = fmax(mxy, y);
+    }
+    mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s[0][warp] = mnx; s[1][warp] = mny; s[2][warp] = mxx; s[3][warp] = mxy; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kMT / 32; ++w) {
+            mnx = fmin(mnx, s[0][w]); mny = fmin(mny, s[1][w]); mxx = fmax(mxx, s[2][w]); mxy = fmax(mxy, s[3][w]);
+        }
+        partial[blockIdx.x * 4 + 0] = mnx; partial[blockIdx.x * 4 + 1] = mny;
+        partial[blockIdx.x * 4 + 2] = mxx; partial[blockIdx.x * 4 + 3] = mxy;
+    }
+}
+
+__global__ void __launch_bounds__(kMT)
+k_bounds_final(const double* __restrict__ partial, int n_partial, double* __restrict__ bounds) {
+    __shared__ double s[4][kMT / 32];
+    double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (int i = threadIdx.x; i < n_partial; i += kMT) {
+        mnx = fmin(mnx, partial[i * 4 + 0]); mny = fmin(mny, partial[i * 4 + 1]);
+        mxx = fmax(mxx, partial[i * 4 + 2]); mxy = fmax(mxy, partial[i * 4 + 3]);
+    }
+    mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s[0][warp] = mnx; s[1][warp] = mny; s[2][warp] = mxx; s[3][warp] = mxy; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kMT / 32; ++w) {
+            mnx = fmin(mnx, s[0][w]); mny = fmin(mny, s[1][w]); mxx = fmax(mxx, s[2][w]); mxy = fmax(mxy, s[3][w]);
+        }
+        bounds[0] = mnx; bounds[1] = mny; bounds[2] = mxx; bounds[3] = mxy;
+    }
+}
+
+// ---- a11: VoxelDownSample -------------------------------------------------------------------
+
+struct VoxelHeader {          // lives at the start of the voxel workspace
+    double mbx, mby;          // voxel_min_bound = min_bound - 0.5 * voxel
+    long long nx, ny, cells;  // lattice extent actually used by this call
+    long long n_points;
+};
+
+__global__ void k_voxel_setup(const double* __restrict__ bounds, const long long* __restrict__ d_count, double voxel,
+                              long long capacity_cells, VoxelHeader* __restrict__ hdr, int* __restrict__ status) {
+    const long long n = *d_count;
+    VoxelHeader h;
+    h.n_points = n;
+    h.mbx = OCC_DADD(bounds[0], -OCC_DMUL(voxel, 0.5));
+    h.mby = OCC_DADD(bounds[1], -OCC_DMUL(voxel, 0.5));
+    if (n <= 0) { h.nx = h.ny = h.cells = 0; *hdr = h; return; }
+    h.nx = (long long)floor(OCC_DDIV(OCC_DADD(bounds[2], -h.mbx), voxel)) + 1;
+    h.ny = (long long)floor(OCC_DDIV(OCC_DADD(bounds[3], -h.mby), voxel)) + 1;
+    h.cells = h.nx * h.ny;
+    if (h.nx <= 0 || h.ny <= 0 || h.cells > capacity_cells || h.cells >= 0xffffffffll) {
+        atomicOr(status, ST_LATTICE_OVERFLOW);
+        h.cells = 0; h.n_points = 0;        // make every later kernel of this call a no-op
+    }
+    *hdr = h;
+}
+
+__global__ void __launch_bounds__(kMT)
+k_voxel_zero(const VoxelHeader* __restrict__ hdr, unsigned int* __restrict__ counts) {
+    const long long cells = hdr->cells + 1;
+    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < cells; i += (long long)gridDim.x * kMT) counts[i] = 0u;
+}
+
+__global__ void __launch_bounds__(kMT)
+k_voxel_count(const double* __restrict__ px, const double* __restrict__ py, double voxel,
+              const VoxelHeader* __restrict__ hdr, unsigned int* __restrict__ counts,
+              unsigned int* __restrict__ key, unsigned int* __restrict__ rank) {
+    const long long n = hdr->n_points;
+    const double mbx = hdr->mbx, mby = hdr->mby;
+    const long long nx = hdr->nx;
+    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
+        const long long ix = (long long)floor(OCC_DDIV(OCC_DADD(px[i], -mbx), voxel));
+        const long long iy = (long long)floor(OCC_DDIV(OCC_DADD(py[i], -mby), voxel));
+        const unsigned int k = (unsigned int)(iy * nx + ix);
+        key[i] = k;
+        rank[i] = atomicAdd(&counts[k], 1u);
+    }
+}
+
+// Large exclusive scan, three kernels.  Input counts[c]; outputs pts_off[c] (exclusive sum of
+// counts, in place) and vox_off[c] (exclusive count of non-empty voxels).  Element `cells`
+// receives the totals.
+constexpr int kScanItems = 8;
+constexpr int kScanChunk = kMT * kScanItems;
+
+__global__ void __launch_bounds__(kMT)
+k_scan_partial(const unsigned int* __restrict__ counts, const VoxelHeader* __restrict__ hdr, uint2* __restrict__ block_sums) {
+    __shared__ unsigned int s_warp[33];
+    const long long cells = hdr->cells + 1;
+    const long long nblocks = (cells + kScanChunk - 1) / kScanChunk;
+    for (long long b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const long long base = b * kScanChunk + (long long)threadIdx.x * kScanItems;
+        unsigned int s = 0, f = 0;
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+            const unsigned int c = (base + i < cells) ? counts[base + i] : 0u;
+            s += c;
+            f += c ? 1u : 0u;
+        }
+        unsigned int ts, tf;
+        block_exclusive_scan(s, s_warp, &ts);
+        block_exclusive_scan(f, s_warp, &tf);
+        if (threadIdx.x == 0) block_sums[b] = make_uint2(ts, tf);
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k_scan_top(uint2* __restrict__ block_sums, const VoxelHeader* __restrict__ hdr) {
+    __shared__ unsigned int s_warp[33];
+    __shared__ unsigned int s_c0, s_c1;
+    const long long cells = hdr->cells + 1;
+    const long long nblocks = (cells + kScanChunk - 1) / kScanChunk;
+    if (threadIdx.x == 0) { s_c0 = 0; s_c1 = 0; }
+    __syncthreads();
+    for (long long start = 0; start < nblocks; start += blockDim.x) {
+        const long long i = start + threadIdx.x;
+        const uint2 v = i < nblocks ? block_sums[i] : make_uint2(0u, 0u);
+        unsigned int t0, t1;
+        const unsigned int e0 = block_exclusive_scan(v.x, s_warp, &t0);
+        const unsigned int e1 = block_exclusive_scan(v.y, s_warp, &t1);
+        if (i < nblocks) block_sums[i] = make_uint2(s_c0 + e0, s_c1 + e1);
+        __syncthreads();
+        if (threadIdx.x == 0) { s_c0 += t0; s_c1 += t1; }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kMT)
+k_scan_apply(unsigned int* __restrict__ counts_to_ptsoff, unsigned int* __restrict__ vox_off,
+             const VoxelHeader* __restrict__ hdr, const uint2* __restrict__ block_sums) {
+    __shared__ unsigned int s_warp[33];
+    const long long cells = hdr->cells + 1;
+    const long long nblocks = (cells + kScanChunk - 1) / kScanChunk;
+    for (long long b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const long long base = b * kScanChunk + (long long)threadIdx.x * kScanItems;
+        unsigned int c[kScanItems];
+        unsigned int s = 0, f = 0;
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+            c[i] = (base + i < cells) ? counts_to_ptsoff[base + i] : 0u;
+            s += c[i];
+            f += c[i] ? 1u : 0u;
+        }
+        unsigned int ts, tf;
+        unsigned int es = block_exclusive_scan(s, s_warp, &ts);
+        unsigned int ef = block_exclusive_scan(f, s_warp, &tf);
+        const uint2 carry = block_sums[b];
+        es += carry.x;
+        ef += carry.y;
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+            if (base + i < cells) {
+                counts_to_ptsoff[base + i] = es;
+                vox_off[base + i] = ef;
+            }
+            es += c[i];
+            ef += c[i] ? 1u : 0u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kMT)
+k_voxel_fill(const VoxelHeader* __restrict__ hdr, const unsigned int* __restrict__ pts_off,
+             const unsigned int* __restrict__ key, const unsigned int* __restrict__ rank, unsigned int* __restrict__ slots) {
+    const long long n = hdr->n_points;
+    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT)
+        slots[pts_off[key[i]] + rank[i]] = (unsigned int)i;
+}
+
+// One thread per voxel (the thread of the point that drew rank 0): visit the voxel's point
+// indices in ascending order, accumulate, divide (AccumulatedPoint::GetAveragePoint).
+__global__ void __launch_bounds__(kMT)
+k_voxel_reduce(const double* __restrict__ px, const double* __restrict__ py, const VoxelHeader* __restrict__ hdr,
+               const unsigned int* __restrict__ pts_off, const unsigned int* __restrict__ vox_off,
+               const unsigned int* __restrict__ key, const unsigned int* __restrict__ rank,
+               const unsigned int* __restrict__ slots, double* __restrict__ out_x, double* __restrict__ out_y,
+               long long* __restrict__ out_count) {
+    const long long n = hdr->n_points;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = n > 0 ? (long long)vox_off[hdr->cells] : 0;
+    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
+        if (rank[i] != 0u) continue;
+        const unsigned int k = key[i];
+        const unsigned int b = pts_off[k], e = pts_off[k + 1];
+        double sx = 0.0, sy = 0.0;
+        long long last = -1;
+        for (unsigned int r = b; r < e; ++r) {          // selection by ascending index, O(cnt^2), cnt is tiny
+            unsigned int best = 0xffffffffu;
+            for (unsigned int q = b; q < e; ++q) {
+                const unsigned int idx = slots[q];
+                if ((long long)idx > last && idx < best) best = idx;
+            }
+            last = best;
+            if (r == b) { sx = px[best]; sy = py[best]; }
+            else { sx = OCC_DADD(sx, px[best]); sy = OCC_DADD(sy, py[best]); }
+        }
+        const double cnt = (double)(e - b);
+        out_x[vox_off[k]] = OCC_DDIV(sx, cnt);
+        out_y[vox_off[k]] = OCC_DDIV(sy, cnt);
+    }
+}
+
+// ---- a12: publish_global_map rasterise (:103-111) -----------------------------------------
+
+__global__ void __launch_bounds__(kMT)
+k_raster_fill(int8_t* __restrict__ grid, long long n) {
+    const long long n16 = ((reinterpret_cast<uintptr_t>(grid) & 15) == 0) ? n / 16 : 0;
+    int4* g4 = reinterpret_cast<int4*>(grid);
+    const int4 v = make_int4(-1, -1, -1, -1);
+    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n16; i += (long long)gridDim.x * kMT) g4[i] = v;
+    for (long long i = n16 * 16 + (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) grid[i] = -1;
+}
+
+__global__ void __launch_bounds__(kMT)
+k_raster_scatter(const double* __restrict__ px, const double* __restrict__ py, const long long* __restrict__ d_count,
+                 const double* __restrict__ bounds, double res, int width, int height, int8_t* __restrict__ grid) {
+    const long long n = *d_count;
+    const double min_x = bounds[0], min_y = bounds[1];
+    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
+        long long xi = (long long)OCC_DDIV(OCC_DADD(px[i], -min_x), res);     // :105  astype(int) truncates
+        long long yi = (long long)OCC_DDIV(OCC_DADD(py[i], -min_y), res);     // :106
+        xi = xi < 0 ? 0 : (xi > width - 1 ? width - 1 : xi);                    // :108
+        yi = yi < 0 ? 0 : (yi > height - 1 ? height - 1 : yi);                  // :109
+        grid[yi * width + xi] = OCCGRID_CELL_OCCUPIED;                          // :111
+    }
+}
+
+// Element-wise max of two int8 grids (values {-1, 100}: "occupied wins"), the local half of
+// the multi-GPU fuse (the cross-GPU half is ncclMax on int8).
+__global__ void __launch_bounds__(kMT)
+k_fuse_max(int8_t* __restrict__ dst, const int8_t* __restrict__ src, long long n) {
+    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
+        const int8_t a = dst[i], b = src[i];
+        dst[i] = a > b ? a : b;
+    }
+}
+
+static int grid_for(long long work_items) {
+    long long b = (work_items + kMT - 1) / kMT;
+    if (b < 1) b = 1;
+    if (b > 148 * 16) b = 148 * 16;
+    return (int)b;
+}
+
+}  // namespace occ
+
+using namespace occ;
+
+extern "C" {
+
+size_t mapmerge_extract_workspace_bytes(int64_t n_cells) {
+    const int64_t blocks = (n_cells + kChunk - 1) / kChunk;
+    return align_up((size_t)blocks * sizeof(unsigned int), 256) + 256;
+}
+
+int mapmerge_extract_transform(const int8_t* d_grid, int32_t width, int32_t height, double res, double origin_x,
+                               double origin_y, const double* T_host, double* d_px, double* d_py, int64_t capacity,
+                               int64_t* d_count, int64_t* d_last_appended, int32_t* d_status, void* d_ws, size_t ws_bytes,
+                               void* stream) {
+    if (!d_grid || !d_px || !d_py || !d_count || !d_status || !d_ws || width <= 0 || height <= 0 || !(res > 0.0)) {
+        set_last_error("mapmerge_extract_transform: bad arguments");
+        return OCCGRID_E_ARG;
+    }
+    const long long n_cells = (long long)width * height;
+    if (ws_bytes < mapmerge_extract_workspace_bytes(n_cells)) { set_last_error("mapmerge_extract_transform: workspace too small"); return OCCGRID_E_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = (int)((n_cells + kChunk - 1) / kChunk);
+    long long* ws_base = reinterpret_cast<long long*>(d_ws);
+    unsigned int* block_counts = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(d_ws) + 256);
+    Xform T;
+    T.identity = 1;
+    for (int i = 0; i < 16; ++i) T.m[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    if (T_host) {
+        for (int i = 0; i < 16; ++i) { T.m[i] = T_host[i]; if (T_host[i] != ((i % 5 == 0) ? 1.0 : 0.0)) T.identity = 0; }
+    }
+    ProfileScope ps(K_MERGE_EXTRACT, st);
+    k_extract_count<<<blocks, kMT, 0, st>>>(d_grid, n_cells, block_counts);
+    k_extract_reserve<<<1, 1024, 0, st>>>(block_counts, blocks, (long long*)d_count, capacity, ws_base, d_status,
+                                           (long long*)d_last_appended);
+    k_extract_write<<<blocks, kMT, 0, st>>>(d_grid, n_cells, width, res, origin_x, origin_y, T, block_counts, ws_base, d_px, d_py);
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
+}
+
+size_t mapmerge_bounds_workspace_bytes(void) { return (size_t)148 * 8 * 4 * sizeof(double); }
+
+int mapmerge_bounds(const double* d_px, const double* d_py, const int64_t* d_count, double* d_bounds, void* d_ws,
+                    size_t ws_bytes, void* stream) {
+    if (!d_px || !d_py || !d_count || !d_bounds || !d_ws || ws_bytes < mapmerge_bounds_workspace_bytes()) {
+        set_last_error("mapmerge_bounds: bad arguments");
+        return OCCGRID_E_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = 148 * 8;
+    ProfileScope ps(K_MERGE_BOUNDS, st);
+    k_bounds_partial<<<blocks, kMT, 0, st>>>(d_px, d_py, (const long long*)d_count, (double*)d_ws);
+    k_bounds_final<<<1, kMT, 0, st>>>((const double*)d_ws, blocks, d_bounds);
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
+}
+
+// Workspace: header | counts/pts_off u32[cells+1] | vox_off u32[cells+1] | block_sums uint2[...] |
+//            key u32[points] | rank u32[points] | slots u32[points]
+static size_t voxel_layout(int64_t cells, int64_t points, size_t off[7]) {
+    size_t o = 0;
+    off[0] = o; o += 256;
+    off[1] = o; o += align_up((size_t)(cells + 1) * 4, 256);
+    off[2] = o; o += align_up((size_t)(cells + 1) * 4, 256);
+    off[3] = o; o += align_up((size_t)((cells + 1 + kScanChunk - 1) / kScanChunk) * 8, 256);
+    off[4] = o; o += align_up((size_t)points * 4, 256);
+    off[5] = o; o += align_up((size_t)points * 4, 256);
+    off[6] = o; o += align_up((size_t)points * 4, 256);
+    return o;
+}
+
+size_t mapmerge_voxel_workspace_bytes(int64_t lattice_capacity_cells, int64_t point_capacity) {
+    size_t off[7];
+    return voxel_layout(lattice_capacity_cells, point_capacity, off);
+}
+
+int mapmerge_voxel_downsample(const double* d_px, const double* d_py, const int64_t* d_count, int64_t point_capacity,
+                              double voxel, const double* d_bounds, int64_t lattice_capacity_cells,
+                              double* d_out_px, double* d_out_py, int64_t* d_out_count, int32_t* d_status,
+                              void* d_ws, size_t ws_bytes, void* stream) {
+    if (!d_px || !d_py || !d_count || !d_bounds || !d_out_px || !d_out_py || !d_out_count || !d_status || !d_ws ||
+        !(voxel > 0.0) || lattice_capacity_cells <= 0 || point_capacity <= 0) {
+        set_last_error("mapmerge_voxel_downsample: bad arguments");
+        return OCCGRID_E_ARG;
+    }
+    size_t off[7];
+    if (ws_bytes < voxel_layout(lattice_capacity_cells, point_capacity, off)) {
+        set_last_error("mapmerge_voxel_downsample: workspace too small");
+        return OCCGRID_E_WORKSPACE;
+    }
+    char* ws = reinterpret_cast<char*>(d_ws);
+    VoxelHeader* hdr = reinterpret_cast<VoxelHeader*>(ws + off[0]);
+    unsigned int* counts = reinterpret_cast<unsigned int*>(ws + off[1]);
+    unsigned int* vox_off = reinterpret_cast<unsigned int*>(ws + off[2]);
+    uint2* block_sums = reinterpret_cast<uint2*>(ws + off[3]);
+    unsigned int* key = reinterpret_cast<unsigned int*>(ws + off[4]);
+    unsigned int* rank = reinterpret_cast<unsigned int*>(ws + off[5]);
+    unsigned int* slots = reinterpret_cast<unsigned int*>(ws + off[6]);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gp = grid_for(point_capacity);
+    const int gc = grid_for(lattice_capacity_cells / 4 + 1);
+    const int gs = grid_for((lattice_capacity_cells + 1 + kScanItems - 1) / kScanItems);
+    ProfileScope ps(K_MERGE_VOXEL, st);
+    k_voxel_setup<<<1, 1, 0, st>>>(d_bounds, (const long long*)d_count, voxel, lattice_capacity_cells, hdr, d_status);
+    k_voxel_zero<<<gc, kMT, 0, st>>>(hdr, counts);
+    k_voxel_count<<<gp, kMT, 0, st>>>(d_px, d_py, voxel, hdr, counts, key, rank);
+    k_scan_partial<<<gs, kMT, 0, st>>>(counts, hdr, block_sums);
+    k_scan_top<<<1, 1024, 0, st>>>(block_sums, hdr);
+    k_scan_apply<<<gs, kMT, 0, st>>>(counts, vox_off, hdr, block_sums);
+    k_voxel_fill<<<gp, kMT, 0, st>>>(hdr, counts, key, rank, slots);
+    k_voxel_reduce<<<gp, kMT, 0, st>>>(d_px, d_py, hdr, counts, vox_off, key, rank, slots, d_out_px, d_out_py,
+                                       (long long*)d_out_count);
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
+}
+
+int mapmerge_rasterise(const double* d_px, const double* d_py, const int64_t* d_count, double res, const double* d_bounds,
+                       int32_t width, int32_t height, int8_t* d_grid_out, void* stream) {
+    if (!d_px || !d_py || !d_count || !d_bounds || !d_grid_out || width <= 0 || height <= 0 || !(res > 0.0)) {
+        set_last_error("mapmerge_rasterise: bad arguments");
+        return OCCGRID_E_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)width * height;
+    ProfileScope ps(K_MERGE_RASTER, st);
+    k_raster_fill<<<grid_for(n / 16 + 1), kMT, 0, st>>>(d_grid_out, n);
+    k_raster_scatter<<<148 * 8, kMT, 0, st>>>(d_px, d_py, (const long long*)d_count, d_bounds, res, width, height, d_grid_out);
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
+}
+
+int mapmerge_fuse_max(int8_t* d_dst, const int8_t* d_src, int64_t n, void* stream) {
+    if (!d_dst || !d_src || n < 0) { set_last_error("mapmerge_fuse_max: bad arguments"); return OCCGRID_E_ARG; }
+    if (n == 0) return OCCGRID_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfileScope ps(K_MERGE_FUSE, st);
+    k_fuse_max<<<grid_for(n), kMT, 0, st>>>(d_dst, d_src, n);
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
+}
+
+}  // extern "C"

@@ -237,12 +237,15 @@ class OccupancyGrid:
                 raise ValueError('flat packet buffer length is not a multiple of 42')
             packets = packets.reshape(-1, PACKET_SIZE)
         if packets.device.type != 'cuda':
-            n = packets.numel()
-            if self._pinned is None or self._pinned.numel() < n:
-                self._pinned = torch.empty(max(n, 1 << 16), dtype=torch.uint8).pin_memory()
-            stage = self._pinned[:n].view(packets.shape)
-            stage.copy_(packets)
-            packets = stage.to(self.device, non_blocking=True)
+            packets = packets.contiguous()
+            if not packets.is_pinned():          # pageable input: one pass through a pinned staging buffer
+                n = packets.numel()
+                if self._pinned is None or self._pinned.numel() < n:
+                    self._pinned = torch.empty(max(n, 1 << 16), dtype=torch.uint8).pin_memory()
+                stage = self._pinned[:n].view(packets.shape)
+                stage.copy_(packets)
+                packets = stage
+            packets = packets.to(self.device, non_blocking=True)
         return packets.contiguous(), kept
 
     def update_packets(self, packets, separation=0.0, drift=None, agent_offsets=None,

@@ -1,0 +1,283 @@
+"""Drop-in surface of the reference's ``server_nodes/map_merger.py`` (ROS 2 node ``MapMerger``).
+
+Same entry points and message shapes as the reference, without rclpy / Open3D: messages are
+duck-typed (anything with ``.info.width/.height/.resolution/.origin.position.x/.y``,
+``.data`` and ``.header.frame_id`` works — a real ``nav_msgs/OccupancyGrid`` included) and the
+point cloud lives in B200 HBM as two fp64 arrays.  Per reference line:
+
+* ``map_callback(msg, agent_id)``          :35-62   (+ ``transform=`` in place of the ICP call at
+  :45-56 — ICP is outside this path, SURVEY §8 a13 — and ``fitness=`` for the gate at :54-56)
+* ``grid_to_pcd(msg)``                     :64-85   occupied cells (> 50) -> cell-corner points
+* ``publish_global_map(frame_id)``         :87-127  bbox -> int8 grid holding only -1 / 100
+* ``merge(grids, origins, res, transforms)``  NEW batched entry: the same sequence of
+  callbacks, publishing once at the end.
+
+Everything numeric runs in the hand-written sm_100a kernels behind ``mapmerge_*``
+(include/occgrid_b200.h); there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import OccGridError
+
+
+def make_grid_msg(data, width, height, resolution, origin_x, origin_y, frame_id='map'):
+    """A minimal stand-in for ``nav_msgs/OccupancyGrid`` (fields used at map_merger.py:65-71,
+    :113-125)."""
+    pos = SimpleNamespace(x=float(origin_x), y=float(origin_y), z=0.0)
+    info = SimpleNamespace(width=int(width), height=int(height), resolution=float(resolution),
+                           origin=SimpleNamespace(position=pos, orientation=SimpleNamespace(w=1.0)))
+    return SimpleNamespace(header=SimpleNamespace(frame_id=frame_id, stamp=None), info=info, data=data)
+
+
+def se2_matrix(tx, ty, theta):
+    """4x4 homogeneous matrix of a planar rigid transform (what ICP returns at :58)."""
+    c, s = math.cos(theta), math.sin(theta)
+    T = np.eye(4)
+    T[0, 0], T[0, 1], T[0, 3] = c, -s, tx
+    T[1, 0], T[1, 1], T[1, 3] = s, c, ty
+    return T
+
+
+class _Cloud:
+    """fp64 x[], y[] + device-resident count."""
+
+    def __init__(self, capacity, device):
+        self.capacity = int(capacity)
+        self.x = torch.empty(self.capacity, dtype=torch.float64, device=device)
+        self.y = torch.empty(self.capacity, dtype=torch.float64, device=device)
+        self.count = torch.zeros(1, dtype=torch.int64, device=device)
+
+
+class MapMerger:
+    """Fuses per-agent occupancy grids into one global map (reference :9-127).
+
+    agent_ids      kept for API parity (:12-15); subscriptions are the caller's business
+    device         CUDA device
+    """
+
+    def __init__(self, agent_ids=(1,), device='cuda', publisher=None):
+        if not torch.cuda.is_available():
+            raise OccGridError('no CUDA device: the map-fusion engine has no CPU fallback')
+        self.agent_ids = list(agent_ids) or [1]
+        self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        self._lib = _native.lib()
+        self.map_resolution = 0.05          # :32
+        self.map_origin = [0.0, 0.0]        # :33
+        self.publisher = publisher          # optional callable(msg), stands in for :29
+        self.published = None               # last published message
+        self._n_global = 0                  # host mirror of the global cloud size
+        self._cloud = None                  # current global cloud
+        self._spare = None                  # ping-pong partner for the voxel filter
+        self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._bounds = torch.zeros(4, dtype=torch.float64, device=self.device)
+        self._last = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._ws = {}
+
+    # ---- plumbing ------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _workspace(self, name, nbytes):
+        t = self._ws.get(name)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.device)
+            self._ws[name] = t
+        return t
+
+    def _ensure_capacity(self, need):
+        if self._cloud is not None and self._cloud.capacity >= need:
+            return
+        cap = max(int(need * 1.5), 1 << 16)
+        new, spare = _Cloud(cap, self.device), _Cloud(cap, self.device)
+        if self._cloud is not None and self._n_global:
+            n = self._n_global
+            new.x[:n].copy_(self._cloud.x[:n])
+            new.y[:n].copy_(self._cloud.y[:n])
+            new.count.copy_(self._cloud.count)
+        self._cloud, self._spare = new, spare
+
+    def _check_status(self):
+        st = int(self._status.item())
+        if st:
+            self._status.zero_()
+            raise OccGridError('map merge overflow: ' + ', '.join(
+                n for b, n in ((1, 'point capacity'), (2, 'voxel lattice capacity')) if st & b))
+
+    def _device_grid(self, msg):
+        data = msg.data
+        h, w = int(msg.info.height), int(msg.info.width)
+        if isinstance(data, torch.Tensor):
+            t = data.to(self.device, dtype=torch.int8).reshape(h, w)
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(data, dtype=np.int8).reshape(h, w))).to(self.device)
+        return t.contiguous()
+
+    def _extract(self, msg, T):
+        """grid_to_pcd (+ transform) appended to the global cloud; returns points appended."""
+        g = self._device_grid(msg)
+        h, w = g.shape
+        # worst case every cell is occupied; grow on demand instead of allocating H*W up front
+        ws = self._workspace('extract', self._lib.mapmerge_extract_workspace_bytes(h * w))
+        Tm = None
+        if T is not None:
+            Tm = np.ascontiguousarray(np.asarray(T, np.float64).reshape(4, 4))
+        for attempt in range(2):
+            rc = self._lib.mapmerge_extract_transform(
+                g.data_ptr(), w, h, float(msg.info.resolution), float(msg.info.origin.position.x),
+                float(msg.info.origin.position.y), Tm.ctypes.data if Tm is not None else None,
+                self._cloud.x.data_ptr(), self._cloud.y.data_ptr(), self._cloud.capacity,
+                self._cloud.count.data_ptr(), self._last.data_ptr(), self._status.data_ptr(),
+                ws.data_ptr(), ws.numel(), self._stream())
+            _native.check(rc, 'mapmerge_extract_transform')
+            st = int(self._status.item())
+            if st & 1 and attempt == 0:          # grow and retry once with room for every cell
+                self._status.zero_()
+                self._ensure_capacity(self._n_global + h * w)
+                continue
+            break
+        self._check_status()
+        return int(self._last.item())
+
+    def _bounds_of(self, cloud):
+        ws = self._workspace('bounds', self._lib.mapmerge_bounds_workspace_bytes())
+        rc = self._lib.mapmerge_bounds(cloud.x.data_ptr(), cloud.y.data_ptr(), cloud.count.data_ptr(),
+                                       self._bounds.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
+        _native.check(rc, 'mapmerge_bounds')
+
+    def _voxel_downsample(self):
+        """global_pcd = global_pcd.voxel_down_sample(map_resolution)  (:60)"""
+        self._bounds_of(self._cloud)
+        b = self._bounds.cpu().numpy()
+        v = self.map_resolution
+        nx = int(math.floor((b[2] - (b[0] - v * 0.5)) / v)) + 1
+        ny = int(math.floor((b[3] - (b[1] - v * 0.5)) / v)) + 1
+        cells = nx * ny
+        need = self._lib.mapmerge_voxel_workspace_bytes(cells, self._cloud.capacity)
+        ws = self._workspace('voxel', need)
+        rc = self._lib.mapmerge_voxel_downsample(
+            self._cloud.x.data_ptr(), self._cloud.y.data_ptr(), self._cloud.count.data_ptr(), self._cloud.capacity,
+            v, self._bounds.data_ptr(), cells, self._spare.x.data_ptr(), self._spare.y.data_ptr(),
+            self._spare.count.data_ptr(), self._status.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
+        _native.check(rc, 'mapmerge_voxel_downsample')
+        self._cloud, self._spare = self._spare, self._cloud
+        self._n_global = int(self._cloud.count.item())
+        self._check_status()
+
+    # ---- reference surface ---------------------------------------------------------------
+    @property
+    def global_pcd(self):
+        """Host copy of the global cloud as float64 [n, 3] (z = 0), like ``np.asarray(pcd.points)``."""
+        n = self._n_global
+        out = np.zeros((n, 3))
+        if n:
+            out[:, 0] = self._cloud.x[:n].cpu().numpy()
+            out[:, 1] = self._cloud.y[:n].cpu().numpy()
+        return out
+
+    def grid_to_pcd(self, msg):
+        """:64-85 — returns the points as float64 [k, 3] on the host (diagnostic twin of the fused
+        device path used by map_callback)."""
+        tmp = MapMerger(device=self.device)
+        tmp._ensure_capacity(1 << 16)
+        k = tmp._extract(msg, None)
+        tmp._n_global = k
+        return tmp.global_pcd
+
+    def _merge_one(self, msg, transform, fitness):
+        """:36-60 without the publish.  Returns False where the reference returns early."""
+        if transform is not None and np.asarray(transform).size == 3:
+            transform = se2_matrix(*np.asarray(transform, np.float64).tolist())
+        with torch.cuda.device(self.device):
+            first = self._n_global == 0
+            if not first and fitness < 0.6:                 # :54-56 — no state change, nothing published
+                return False
+            self._ensure_capacity(self._n_global + (1 << 16))
+            k = self._extract(msg, None if first else transform)
+            if k == 0:                                      # :37-38
+                return False
+            if first:                                       # :40-43
+                self._n_global = k
+                self.map_resolution = float(msg.info.resolution)
+                self.map_origin = [float(msg.info.origin.position.x), float(msg.info.origin.position.y)]
+            else:                                           # :58-60
+                self._n_global += k
+                self._voxel_downsample()
+        return True
+
+    def map_callback(self, msg, agent_id, transform=None, fitness=1.0):
+        """:35-62.  ``transform`` (4x4 or (tx, ty, theta)) stands in for ``reg_p2p.transformation``;
+        ``fitness`` for ``reg_p2p.fitness`` (rejected below 0.6, :54-56).  Returns the published
+        message, or None where the reference returns early."""
+        if not self._merge_one(msg, transform, fitness):
+            return None
+        return self.publish_global_map(getattr(getattr(msg, 'header', None), 'frame_id', 'map'))
+
+    def publish_global_map(self, frame_id=None, to_host=True):
+        """:87-127.  Returns (and hands to ``publisher``) a message whose ``data`` is the int8 grid
+        as a NumPy array [height, width] (``.flatten().tolist()`` gives the reference's list)."""
+        if self._n_global == 0:                             # :88-93
+            return None
+        with torch.cuda.device(self.device):
+            self._bounds_of(self._cloud)
+            min_x, min_y, max_x, max_y = self._bounds.cpu().numpy().tolist()
+            res = self.map_resolution
+            width = int(np.ceil((max_x - min_x) / res)) + 1     # :100
+            height = int(np.ceil((max_y - min_y) / res)) + 1    # :101
+            grid = torch.empty((height, width), dtype=torch.int8, device=self.device)
+            rc = self._lib.mapmerge_rasterise(self._cloud.x.data_ptr(), self._cloud.y.data_ptr(),
+                                              self._cloud.count.data_ptr(), res, self._bounds.data_ptr(),
+                                              width, height, grid.data_ptr(), self._stream())
+            _native.check(rc, 'mapmerge_rasterise')
+            data = grid.cpu().numpy() if to_host else grid
+        msg = make_grid_msg(data, width, height, res, min_x, min_y, frame_id='map_global')   # :113-123
+        self.published = msg
+        if self.publisher is not None:
+            self.publisher(msg)
+        return msg
+
+    # ---- batched entry ---------------------------------------------------------------------
+    def merge(self, grids, origins, res, transforms=None, fitness=None, to_host=True):
+        """Fuse A agent grids in order: ``grids`` int8 [A, H, W] (host or device), ``origins``
+        float64 [A, 2], ``transforms`` [A, 4, 4] or [A, 3] (tx, ty, theta) or None (identity).
+        Equal to A successive ``map_callback`` calls; publishes once at the end.  Returns
+        (int8 grid [H', W'], (origin_x, origin_y))."""
+        for a in range(len(grids)):
+            h, w = grids[a].shape
+            msg = make_grid_msg(grids[a], w, h, res, origins[a][0], origins[a][1])
+            self._merge_one(msg, None if transforms is None else transforms[a],
+                            1.0 if fitness is None else fitness[a])
+        out = self.publish_global_map(to_host=to_host)
+        if out is None:
+            return None, None
+        return out.data, (out.info.origin.position.x, out.info.origin.position.y)
+
+
+def smoke():
+    """Tiny merge on cuda:0 checked against the oracle (called from __graft_entry__.smoke)."""
+    from oracle import merge_oracle as MO
+    rng = np.random.default_rng(5)
+    m, o = MapMerger(device='cuda:0'), MO.OracleMerger()
+    for a in range(4):
+        g = np.full((256, 256), -1, np.int8)
+        g[rng.random((256, 256)) < 0.3] = 0
+        for _ in range(12):
+            x0, y0, L = int(rng.integers(0, 200)), int(rng.integers(0, 200)), int(rng.integers(10, 56))
+            if rng.random() < 0.5:
+                g[y0, x0:x0 + L] = 100
+            else:
+                g[y0:y0 + L, x0] = 100
+        T = MO.se2_matrix(*rng.uniform(-3, 3, 2), rng.uniform(-math.pi, math.pi))
+        got = m.map_callback(make_grid_msg(g.ravel(), 256, 256, 0.05, -6.4, -6.4), a + 1, transform=T)
+        want = o.map_callback(g.ravel(), 256, 256, 0.05, -6.4, -6.4, T)
+        assert np.array_equal(got.data, want[0]), f'merge step {a}: grid differs from the oracle'
+        assert (got.info.origin.position.x, got.info.origin.position.y) == want[1]
+    print(f'smoke ok: map merge, 4 agent grids, {m._n_global} fused points, grid bit-exact')

@@ -142,6 +142,59 @@ int occgrid_update_rays(const occgrid_geom* geom,
 int occgrid_scatter_probe(int kind, void* d_plane, int64_t plane_cells, int64_t n_ops,
                           uint32_t seed, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ *  Map fusion — server_nodes/map_merger.py:35-127
+ *
+ *  A point cloud is two fp64 device arrays x[], y[] (z == 0 on this path) of `capacity`
+ *  elements and a DEVICE-resident int64 count, so a merge sequence runs stream-ordered with
+ *  no host round trip.  `d_status` is a sticky device int32: bit 0 = point capacity exceeded,
+ *  bit 1 = voxel lattice capacity exceeded (the offending call becomes a no-op; the host
+ *  wrapper checks the word at its next synchronisation and raises).
+ *  The rigid transform replaces Open3D ICP (:45-56), which is outside this path.
+ * ---------------------------------------------------------------------------------------- */
+
+/* grid_to_pcd (:64-85) fused with PointCloud::Transform (:58): scan an int8 occupancy grid
+ * (row-major, height x width), keep cells with value > 50 (:72), emit the cell-corner
+ * coordinates x = col*res + origin_x, y = row*res + origin_y (:76-77) in row-major (argwhere)
+ * order, apply the 4x4 row-major transform `T_host` (HOST pointer; NULL = identity), and
+ * append to the cloud at [*d_count, ...) (= `global_pcd += local_pcd`, :59).
+ * *d_last_appended (optional) receives the number of points of this grid. */
+size_t mapmerge_extract_workspace_bytes(int64_t n_cells);
+int mapmerge_extract_transform(const int8_t* d_grid, int32_t width, int32_t height, double res,
+                               double origin_x, double origin_y, const double* T_host,
+                               double* d_px, double* d_py, int64_t capacity,
+                               int64_t* d_count, int64_t* d_last_appended, int32_t* d_status,
+                               void* d_ws, size_t ws_bytes, void* stream);
+
+/* GetMinBound/GetMaxBound of a cloud, also publish_global_map's bbox (:95-98):
+ * d_bounds = {min_x, min_y, max_x, max_y}. */
+size_t mapmerge_bounds_workspace_bytes(void);
+int mapmerge_bounds(const double* d_px, const double* d_py, const int64_t* d_count,
+                    double* d_bounds, void* d_ws, size_t ws_bytes, void* stream);
+
+/* PointCloud::VoxelDownSample(voxel) (:60): voxel_min_bound = min_bound - 0.5*voxel, index =
+ * floor((p - voxel_min_bound)/voxel), one output point per non-empty voxel = mean of its
+ * points (summed in ascending point index), emitted in ascending (iy, ix) order.
+ * `d_bounds` must hold the bounds of the input cloud; the lattice of this call must fit
+ * `lattice_capacity_cells`.  Output arrays must not alias the input. */
+size_t mapmerge_voxel_workspace_bytes(int64_t lattice_capacity_cells, int64_t point_capacity);
+int mapmerge_voxel_downsample(const double* d_px, const double* d_py, const int64_t* d_count,
+                              int64_t point_capacity, double voxel, const double* d_bounds,
+                              int64_t lattice_capacity_cells,
+                              double* d_out_px, double* d_out_py, int64_t* d_out_count,
+                              int32_t* d_status, void* d_ws, size_t ws_bytes, void* stream);
+
+/* publish_global_map's rasterisation (:103-111): fill width x height with -1, then
+ * grid[int((y-min_y)/res)][int((x-min_x)/res)] = 100 with index clipping (:108-109).
+ * width/height follow :100-101 and are computed by the caller from the bounds. */
+int mapmerge_rasterise(const double* d_px, const double* d_py, const int64_t* d_count, double res,
+                       const double* d_bounds, int32_t width, int32_t height,
+                       int8_t* d_grid_out, void* stream);
+
+/* dst = max(dst, src) element-wise on int8 grids ({-1,100}: occupied wins) — the local half
+ * of the multi-GPU fuse; the cross-GPU half is an NCCL max-reduction on int8. */
+int mapmerge_fuse_max(int8_t* d_dst, const int8_t* d_src, int64_t n, void* stream);
+
 /*
  * Measurement hook (bench.py): between _begin and _end every kernel this library launches is
  * bracketed by CUDA events on its stream.  _end synchronises those events and returns, per

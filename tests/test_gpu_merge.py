@@ -1,0 +1,107 @@
+"""GPU parity of the map-fusion path (mapmerge_* kernels through the reference-shaped
+MapMerger) against oracle/merge_oracle.py.  fp64 coordinates are compared BIT-EXACTLY (both
+sides perform the same individually rounded fp64 operations in the same order); the published
+int8 grids and origins must be identical."""
+import math
+
+import numpy as np
+import pytest
+
+from merge_util import synth_agent_grid
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip('torch')
+
+
+@pytest.fixture(scope='module')
+def MM():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from occgrid_b200 import map_merger
+    return map_merger
+
+
+def run_pair(MM, n, n_agents, seed, res=0.05, origin=(-5.0, -5.0), span=4.0, check_every=True):
+    from oracle import merge_oracle as MO
+    r = np.random.default_rng(seed)
+    m, o = MM.MapMerger(agent_ids=list(range(1, n_agents + 1))), MO.OracleMerger()
+    got = want = None
+    for a in range(n_agents):
+        g = synth_agent_grid(n, seed * 100 + a)
+        T = MO.se2_matrix(*r.uniform(-span, span, 2), r.uniform(-math.pi, math.pi))
+        got = m.map_callback(MM.make_grid_msg(g.ravel(), n, n, res, *origin), a + 1, transform=T)
+        want = o.map_callback(g.ravel(), n, n, res, origin[0], origin[1], T)
+        if check_every or a == n_agents - 1:
+            assert got is not None and want is not None
+            assert (got.info.width, got.info.height) == (want[0].shape[1], want[0].shape[0])
+            assert (got.info.origin.position.x, got.info.origin.position.y) == want[1]
+            assert np.array_equal(got.data, want[0]), f'agent {a}'
+            pc = m.global_pcd
+            assert pc.shape[0] == o.gx.shape[0]
+            assert np.array_equal(pc[:, 0], o.gx) and np.array_equal(pc[:, 1], o.gy)
+    return m, o, got, want
+
+
+def test_sequential_callbacks_match_oracle(MM):
+    m, o, got, _ = run_pair(MM, 256, 6, seed=1)
+    assert got.header.frame_id == 'map_global'
+    assert got.data.dtype == np.int8 and set(np.unique(got.data)) == {-1, 100}
+    assert m.map_resolution == 0.05 and m.map_origin == [-5.0, -5.0]
+
+
+def test_other_resolution_and_offsets(MM):
+    run_pair(MM, 300, 4, seed=2, res=0.1, origin=(12.3, -40.7), span=9.0)
+
+
+def test_first_callback_empty_and_rejected(MM):
+    from oracle import merge_oracle as MO
+    m = MM.MapMerger()
+    empty = np.full((32, 32), -1, np.int8)
+    assert m.map_callback(MM.make_grid_msg(empty.ravel(), 32, 32, 0.05, 0, 0), 1) is None
+    g = synth_agent_grid(96, 5)
+    first = m.map_callback(MM.make_grid_msg(g.ravel(), 96, 96, 0.05, -2.4, -2.4), 1)
+    o = MO.OracleMerger()
+    want = o.map_callback(g.ravel(), 96, 96, 0.05, -2.4, -2.4)
+    assert np.array_equal(first.data, want[0])          # adopted as is: no voxel filter (:40-43)
+    n = m.global_pcd.shape[0]
+    assert m.map_callback(MM.make_grid_msg(g.ravel(), 96, 96, 0.05, -2.4, -2.4), 2,
+                          transform=(1.0, 0.5, 0.2), fitness=0.59) is None       # :54-56
+    assert m.global_pcd.shape[0] == n
+    assert m.map_callback(MM.make_grid_msg(empty.ravel(), 32, 32, 0.05, 0, 0), 2) is None
+    pts = m.grid_to_pcd(MM.make_grid_msg(g.ravel(), 96, 96, 0.05, -2.4, -2.4))
+    ox, oy = MO.grid_to_points(g.ravel(), 96, 96, 0.05, -2.4, -2.4)
+    assert np.array_equal(pts[:, 0], ox) and np.array_equal(pts[:, 1], oy) and not pts[:, 2].any()
+
+
+def test_identity_transform_property(MM):
+    """Merging a grid with itself under the identity transform leaves the occupied set
+    unchanged (every voxel averages two identical points)."""
+    g = synth_agent_grid(128, 9)
+    m = MM.MapMerger()
+    a = m.map_callback(MM.make_grid_msg(g.ravel(), 128, 128, 0.5, -32.0, -32.0), 1)
+    b = m.map_callback(MM.make_grid_msg(g.ravel(), 128, 128, 0.5, -32.0, -32.0), 2, transform=np.eye(4))
+    assert np.array_equal(a.data, b.data)
+    ys, xs = np.nonzero(g > 50)
+    want = np.full_like(a.data, -1)
+    want[ys - ys.min(), xs - xs.min()] = 100
+    assert np.array_equal(a.data, want)
+
+
+def test_batched_merge_equals_callbacks(MM):
+    from oracle import merge_oracle as MO
+    r = np.random.default_rng(4)
+    grids = np.stack([synth_agent_grid(200, 40 + a) for a in range(5)])
+    origins = np.tile(np.array([[-5.0, -5.0]]), (5, 1))
+    tf = np.stack([MO.se2_matrix(*r.uniform(-3, 3, 2), r.uniform(-math.pi, math.pi)) for _ in range(5)])
+    o = MO.OracleMerger()
+    for a in range(5):
+        want = o.map_callback(grids[a].ravel(), 200, 200, 0.05, -5.0, -5.0, tf[a])
+    out, origin = MM.MapMerger().merge(grids, origins, 0.05, tf)
+    assert np.array_equal(out, want[0]) and origin == want[1]
+    out2, origin2 = MM.MapMerger().merge(torch.from_numpy(grids).cuda(), origins, 0.05, tf)
+    assert np.array_equal(out2, want[0]) and origin2 == want[1]
+
+
+def test_2048_grids(MM):
+    """BASELINE config 3 grid size (2048^2, ~1.5 % occupied) on a few agents, 50 m translations."""
+    run_pair(MM, 2048, 4, seed=7, span=50.0, origin=(-51.2, -51.2), check_every=False)

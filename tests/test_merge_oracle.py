@@ -1,0 +1,79 @@
+"""CPU checks of the merge oracle (restatement of server_nodes/map_merger.py:35-127).
+PARITY UNPINNED vs the real reference (rclpy/Open3D absent); these tests pin the
+restatement's own invariants and the verbatim NumPy lines."""
+import math
+
+import numpy as np
+
+from merge_util import synth_agent_grid
+from oracle import merge_oracle as MO
+
+
+def test_grid_to_points_is_corner_and_row_major():
+    g = np.full((3, 4), -1, np.int8)
+    g[0, 1] = 100
+    g[2, 3] = 100
+    g[1, 0] = 51
+    g[1, 1] = 50
+    x, y = MO.grid_to_points(g.ravel(), 4, 3, 0.05, -1.0, 2.0)
+    assert x.tolist() == [1 * 0.05 + -1.0, 0 * 0.05 + -1.0, 3 * 0.05 + -1.0]
+    assert y.tolist() == [0 * 0.05 + 2.0, 1 * 0.05 + 2.0, 2 * 0.05 + 2.0]
+
+
+def test_first_callback_adopts_without_downsample_and_identity_property():
+    """SURVEY §4 merge KAT: one grid -> output occupied set == input occupied set shifted to
+    its bbox, up to the reference's own int((p-min)/res) rounding collisions."""
+    g = synth_agent_grid(128, 1)
+    m = MO.OracleMerger()
+    out, origin = m.map_callback(g.ravel(), 128, 128, 0.05, -3.2, -3.2)
+    ys, xs = np.nonzero(g > 50)
+    assert origin == (xs.min() * 0.05 - 3.2, ys.min() * 0.05 - 3.2)
+    assert m.map_resolution == 0.05 and m.map_origin == [-3.2, -3.2]
+    assert set(np.unique(out)) <= {-1, 100}
+    assert 0.9 * len(xs) <= (out == 100).sum() <= len(xs)
+    # with res = 0.5 (exact in binary) there are no rounding collisions
+    m2 = MO.OracleMerger()
+    out2, origin2 = m2.map_callback(g.ravel(), 128, 128, 0.5, -32.0, -32.0)
+    want = np.full_like(out2, -1)
+    want[ys - ys.min(), xs - xs.min()] = 100
+    assert np.array_equal(out2, want)
+
+
+def test_empty_and_rejected_callbacks_return_none():
+    m = MO.OracleMerger()
+    assert m.map_callback(np.full(16, -1, np.int8), 4, 4, 0.05, 0, 0) is None
+    g = synth_agent_grid(64, 2)
+    assert m.map_callback(g.ravel(), 64, 64, 0.05, 0, 0) is not None
+    n = m.gx.size
+    assert m.map_callback(g.ravel(), 64, 64, 0.05, 0, 0, MO.se2_matrix(1, 1, 0.3), accept=False) is None
+    assert m.gx.size == n
+
+
+def test_voxel_down_sample_means_and_order():
+    px = np.array([0.0, 0.01, 0.2, 0.21, 0.22, 1.0])
+    py = np.array([0.0, 0.01, 0.0, 0.0, 0.01, 1.0])
+    x, y = MO.voxel_down_sample(px, py, 0.05)
+    # voxel origin = min - 0.025: points 0,1 share a voxel; 2,3,4 share one; 5 alone
+    assert x.shape == (3,)
+    assert x[0] == (0.0 + 0.01) / 2 and y[0] == (0.0 + 0.01) / 2
+    assert x[1] == ((0.2 + 0.21) + 0.22) / 3
+    assert (x[2], y[2]) == (1.0, 1.0)
+    # canonical order: ascending (iy, ix)
+    px = np.array([1.0, 0.0, 0.5]); py = np.array([0.0, 1.0, 0.0])
+    x, y = MO.voxel_down_sample(px, py, 0.05)
+    assert x.tolist() == [0.5, 1.0, 0.0] and y.tolist() == [0.0, 0.0, 1.0]
+
+
+def test_sequence_is_deterministic_and_only_unknown_or_occupied():
+    rng = np.random.default_rng(3)
+    outs = []
+    for rep in range(2):
+        r = np.random.default_rng(3)
+        m = MO.OracleMerger()
+        for a in range(5):
+            g = synth_agent_grid(200, 10 + a)
+            T = MO.se2_matrix(*r.uniform(-4, 4, 2), r.uniform(-math.pi, math.pi))
+            out = m.map_callback(g.ravel(), 200, 200, 0.05, -5.0, -5.0, T)
+        outs.append(out)
+    assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
+    assert set(np.unique(outs[0][0])) == {-1, 100}

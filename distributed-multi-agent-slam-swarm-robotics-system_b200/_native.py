@@ -13,7 +13,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_PATH = os.path.join(PKG_DIR, 'liboccgrid_b200.so')
-SOURCES = ['occgrid_integrate.cu', 'occgrid_tiled.cu', 'mapmerge.cu']
+SOURCES = ['occgrid_integrate.cu', 'occgrid_tiled.cu', 'occgrid_route.cu', 'mapmerge.cu']
 HEADERS = ['common.cuh', 'beam_expand.cuh', 'sincos_dd.cuh', os.path.join('..', '..', 'include', 'occgrid_b200.h')]
 
 STRATEGY = {'auto': -1, 'global_atomic': 0, 'tiled': 1}
@@ -85,6 +85,11 @@ def lib():
     L.occgrid_update_rays.argtypes = [gp, vp, vp, i64, vp, vp, sz, vp, i32, vp]
     L.occgrid_scatter_probe.restype = i32
     L.occgrid_scatter_probe.argtypes = [i32, vp, i64, i64, u32, vp]
+    L.occgrid_route_workspace_bytes.restype = sz
+    L.occgrid_route_workspace_bytes.argtypes = [i64, i32]
+    L.occgrid_route_packets.restype = i32
+    L.occgrid_route_packets.argtypes = [gp, i32, vp, vp, i64, i32, i32, vp, vp, vp, i32, vp, vp, vp, i64, vp, vp, vp,
+                                        vp, sz, vp]
     L.occgrid_profile_begin.restype = i32
     L.occgrid_profile_end.restype = i32
     L.occgrid_profile_end.argtypes = [vp, vp, i32]
@@ -115,7 +120,7 @@ def _bind_merge(L):
 
 KERNEL_NAMES = ('integrate_global', 'resolve', 'update_rays', 'tile_count', 'tile_scan', 'tile_scatter',
                 'tile_raycast', 'tile_resolve', 'merge_extract', 'merge_bounds', 'merge_voxel', 'merge_raster',
-                'merge_fuse', 'probe')
+                'merge_fuse', 'probe', 'route')
 
 
 def profile_begin():

@@ -1,0 +1,282 @@
+"""Multi-GPU layout of the hot path: one process per GPU, ``torch.distributed``.
+
+Integration — the global ``size`` x ``size`` grid is cut into ``world`` row bands, one per
+rank.  Cells are independent given a global beam order and a ray is at most
+MAX_DIST_M / res cells long (server_nodes/dual_bot_mapper.py:57), so the only exchange step is
+routing records to the band(s) their rays can reach:
+
+    local share --occgrid_route_packets--> send buffer grouped by band
+                --all_to_all_single (NCCL over NVLink)--> records for my band, canonical order
+                --occgrid_integrate_packets(window = my band)--> my rows of the map
+
+There is no collective on the grid itself: bands are disjoint.  The canonical stream order is
+"rank 0's share, then rank 1's, ..."; routing is stable and all-to-all concatenates by source
+rank, so last-writer-wins on every band equals the single-GPU result (tests run the same
+exchange on one GPU and, with the oracle as the device, on 2 gloo ranks on the CPU).
+
+Merge — the reference's fuse is a sequential chain (each callback voxel-filters the whole
+accumulated cloud, map_merger.py:58-60), so only the HBM-bound part shards: every rank extracts
+and transforms its agents' grids, the point lists are all-gathered, and the (cheap, ordered)
+voxel chain is replicated on every rank — see ``ShardedMapMerger``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _native
+from ._native import Geom, OccGridError
+
+
+class BandLayout:
+    """Row-band partition of a ``size`` x ``size`` grid (pure host logic)."""
+
+    def __init__(self, size, n_bands):
+        if n_bands < 1 or n_bands > 32 or n_bands > size:
+            raise ValueError('n_bands must be in 1..min(32, size)')
+        self.size = int(size)
+        self.n_bands = int(n_bands)
+        self.band_y0 = [(self.size * b) // self.n_bands for b in range(self.n_bands + 1)]
+
+    def window(self, b):
+        """(x0, y0, w, h) of band b."""
+        return (0, self.band_y0[b], self.size, self.band_y0[b + 1] - self.band_y0[b])
+
+    def bands_of_row_interval(self, lo, hi):
+        return [b for b in range(self.n_bands) if hi >= self.band_y0[b] and lo < self.band_y0[b + 1]]
+
+
+class CudaBandOps:
+    """Device side of one rank: routing kernel + windowed OccupancyGrid."""
+
+    def __init__(self, layout, rank, size, resolution, origin_x, origin_y, device, strategy, max_batch):
+        from .dual_bot_mapper import OccupancyGrid
+        self.layout = layout
+        self.device = torch.device(device)
+        self.grid = OccupancyGrid(size, resolution, origin_x, origin_y, device=device,
+                                  window=layout.window(rank), strategy=strategy, max_batch=max_batch)
+        self._lib = _native.lib()
+        self._geom = Geom(float(origin_x), float(origin_y), float(resolution), int(size), int(size), 0, 0, int(size), int(size))
+        self._band_y0 = np.asarray(layout.band_y0, np.int32)
+        self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._counts = torch.zeros(layout.n_bands, dtype=torch.int64, device=self.device)
+        self._ws = None
+        self._send = None
+
+    def stage(self, packets):
+        return self.grid.stage_packets(packets)[0]
+
+    def route(self, packets, agent_idx, drift, agent_table):
+        """-> (send [m, stride] grouped by band, send_agent_idx, send_drift, counts list)"""
+        n, stride = packets.shape
+        nb = self.layout.n_bands
+        cap = 2 * n + 1024
+        need = self._lib.occgrid_route_workspace_bytes(n, nb)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        if self._send is None or self._send.shape[0] < cap or self._send.shape[1] != stride:
+            self._send = torch.empty((cap, stride), dtype=torch.uint8, device=self.device)
+        s_idx = torch.empty(cap, dtype=torch.int32, device=self.device) if agent_idx is not None else None
+        s_drift = torch.empty((cap, 2), dtype=torch.float64, device=self.device) if drift is not None else None
+        rc = self._lib.occgrid_route_packets(
+            self._geom, nb, self._band_y0.ctypes.data, packets.data_ptr(), n, stride, 42 if stride >= 42 else 41,
+            agent_idx.data_ptr() if agent_idx is not None else None, drift.data_ptr() if drift is not None else None,
+            agent_table.data_ptr(), agent_table.shape[0] - 1, self._send.data_ptr(),
+            s_idx.data_ptr() if s_idx is not None else None, s_drift.data_ptr() if s_drift is not None else None,
+            cap, self._counts.data_ptr(), self._status.data_ptr(), self.grid._counters.data_ptr(),
+            self._ws.data_ptr(), self._ws.numel(), torch.cuda.current_stream(self.device).cuda_stream)
+        _native.check(rc, 'occgrid_route_packets')
+        counts = self._counts.cpu().tolist()                 # the only host sync of a step
+        if int(self._status.item()) & 1:
+            self._status.zero_()
+            raise OccGridError('route: send buffer overflow')
+        m = int(sum(counts))
+        return (self._send[:m], s_idx[:m] if s_idx is not None else None,
+                s_drift[:m] if s_drift is not None else None, counts)
+
+    def empty(self, rows, stride, dtype):
+        shape = (rows, stride) if stride else (rows,)
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def integrate(self, packets, agent_idx, drift, agent_table):
+        self.grid.update_packets(packets, agent_offsets=agent_table, agent_idx=agent_idx, drift=drift)
+
+    def band_tensor(self):
+        return self.grid.grid_tensor
+
+
+class TiledSwarmMap:
+    """A global occupancy grid spatially tiled over the ranks of a process group.  Mirrors
+    ``OccupancyGrid``'s batched entry; each rank passes ITS share of the packet stream."""
+
+    def __init__(self, size, resolution=0.05, origin_x=-5.0, origin_y=-5.0, *, group=None, device=None,
+                 strategy='auto', max_batch=1 << 16, ops=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.size, self.res, self.ox, self.oy = int(size), float(resolution), float(origin_x), float(origin_y)
+        self.layout = BandLayout(size, self.world)
+        if ops is None:
+            if not torch.cuda.is_available():
+                raise OccGridError('no CUDA device: TiledSwarmMap has no CPU fallback')
+            device = device if device is not None else torch.device('cuda', torch.cuda.current_device())
+            ops = CudaBandOps(self.layout, self.rank, size, resolution, origin_x, origin_y, device, strategy, max_batch)
+        self.ops = ops
+        self.local = getattr(ops, 'grid', None)
+
+    def _agent_table(self, separation, agent_offsets):
+        if agent_offsets is None:
+            tab = np.array([[0.0, 0.0], [0.0, 0.0], [float(separation), 0.0]], np.float64)
+        else:
+            tab = np.ascontiguousarray(agent_offsets, np.float64).reshape(-1, 2)
+        t = torch.from_numpy(tab)
+        return t.to(self.ops.device) if hasattr(self.ops, 'device') else t
+
+    def _exchange(self, send, counts, stride, dtype):
+        """all_to_all_single of row-segments; returns the rows received (concatenated by source
+        rank, i.e. in canonical stream order)."""
+        if self.world == 1:
+            return send
+        recv_counts = self._recv_counts
+        out = self.ops.empty(int(sum(recv_counts)), stride, dtype)
+        dist.all_to_all_single(out, send.contiguous(), output_split_sizes=recv_counts, input_split_sizes=counts,
+                               group=self.group)
+        return out
+
+    def update_packets(self, packets, separation=0.0, drift=None, agent_offsets=None, agent_idx=None):
+        """Integrate this rank's share of the stream into the tiled map (all ranks must call)."""
+        tab = self._agent_table(separation, agent_offsets)
+        pk = self.ops.stage(packets)
+        dev = pk.device
+        idx = torch.as_tensor(agent_idx, dtype=torch.int32).to(dev).contiguous() if agent_idx is not None else None
+        dr = torch.as_tensor(drift, dtype=torch.float64).reshape(-1, 2).to(dev).contiguous() if drift is not None else None
+        send, s_idx, s_dr, counts = self.ops.route(pk, idx, dr, tab)
+        if self.world > 1:
+            c_in = torch.tensor(counts, dtype=torch.int64, device=dev)
+            c_out = torch.empty_like(c_in)
+            dist.all_to_all_single(c_out, c_in, group=self.group)
+            self._recv_counts = c_out.cpu().tolist()
+        recv = self._exchange(send, counts, send.shape[1], torch.uint8)
+        r_idx = self._exchange(s_idx, counts, 0, torch.int32) if s_idx is not None else None
+        r_dr = self._exchange(s_dr, counts, 2, torch.float64) if s_dr is not None else None
+        self.ops.integrate(recv, r_idx, r_dr, tab)
+        return int(recv.shape[0])
+
+    def gather_grid(self):
+        """Assemble the global map on every rank (all_gather of the disjoint bands)."""
+        band = self.ops.band_tensor()
+        if self.world == 1:
+            return band.cpu().numpy()
+        bands = [self.ops.empty(self.layout.window(b)[3], self.size, torch.int8) for b in range(self.world)]
+        dist.all_gather(bands, band.contiguous(), group=self.group)
+        return torch.cat(bands, dim=0).cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------------------
+#  Merge: shard the extraction, replicate the ordered voxel chain
+# ----------------------------------------------------------------------------------------------
+
+class ShardedMapMerger:
+    """Agents are dealt round-robin to ranks; every rank extracts + transforms the occupied cells
+    of ITS agents (the HBM-bound scan, map_merger.py:71-77 + :58), the per-agent point lists are
+    all-gathered, and the order-dependent voxel chain (:59-60) is replayed identically on every
+    rank.  Result == MapMerger.merge on one GPU."""
+
+    def __init__(self, group=None, device=None):
+        from .map_merger import MapMerger
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.merger = MapMerger(device=device if device is not None else 'cuda')
+
+    def merge(self, local_grids, local_origins, res, local_transforms, n_agents_total):
+        """``local_*`` hold the agents a with a % world == rank, in increasing a."""
+        from .map_merger import MapMerger, make_grid_msg, se2_matrix
+        dev = self.merger.device
+        mine = list(range(self.rank, n_agents_total, self.world))
+        # the first NON-EMPTY grid is adopted untransformed (:40-43): find it globally first
+        nonempty = torch.zeros(n_agents_total, dtype=torch.int64, device=dev)
+        for j, a in enumerate(mine):
+            g = local_grids[j]
+            g = g if isinstance(g, torch.Tensor) else torch.from_numpy(np.asarray(g))
+            nonempty[a] = int(bool((g > 50).any()))
+        if self.world > 1:
+            dist.all_reduce(nonempty, group=self.group)
+        ne = nonempty.cpu().tolist()
+        first_agent = next((a for a in range(n_agents_total) if ne[a]), -1)
+        pts = []
+        for j, a in enumerate(mine):
+            tmp = MapMerger(device=dev)
+            tmp._ensure_capacity(1 << 16)
+            T = local_transforms[j] if (local_transforms is not None and a != first_agent) else None
+            if T is not None and np.asarray(T).size == 3:
+                T = se2_matrix(*np.asarray(T, np.float64).tolist())
+            h, w = local_grids[j].shape
+            k = tmp._extract(make_grid_msg(local_grids[j], w, h, res, local_origins[j][0], local_origins[j][1]), T)
+            pts.append(torch.stack([tmp._cloud.x[:k], tmp._cloud.y[:k]], dim=1))
+        # all-gather variable-length point lists (pad to the global max)
+        lens = torch.zeros(n_agents_total, dtype=torch.int64, device=dev)
+        for j, a in enumerate(mine):
+            lens[a] = pts[j].shape[0]
+        if self.world > 1:
+            dist.all_reduce(lens, group=self.group)
+        lens_h = lens.cpu().tolist()
+        per_rank = -(-n_agents_total // self.world)
+        mx = max(max(lens_h), 1)
+        buf = torch.zeros((per_rank, mx, 2), dtype=torch.float64, device=dev)
+        for j in range(len(mine)):
+            buf[j, :pts[j].shape[0]] = pts[j]
+        if self.world > 1:
+            allbuf = [torch.empty_like(buf) for _ in range(self.world)]
+            dist.all_gather(allbuf, buf, group=self.group)
+        else:
+            allbuf = [buf]
+        m = self.merger
+        first_origin = None
+        for a in range(n_agents_total):
+            k = lens_h[a]
+            if k == 0:
+                continue
+            p = allbuf[a % self.world][a // self.world, :k]
+            first = m._n_global == 0
+            m._ensure_capacity(m._n_global + k + 1)
+            n0 = m._n_global
+            m._cloud.x[n0:n0 + k].copy_(p[:, 0])
+            m._cloud.y[n0:n0 + k].copy_(p[:, 1])
+            m._cloud.count.fill_(n0 + k)
+            m._n_global = n0 + k
+            if first:
+                m.map_resolution = float(res)
+            else:
+                m._voxel_downsample()
+        out = m.publish_global_map()
+        return (out.data, (out.info.origin.position.x, out.info.origin.position.y)) if out is not None else (None, None)
+
+
+# ----------------------------------------------------------------------------------------------
+#  bench.py helper: weak-scaling sessions
+# ----------------------------------------------------------------------------------------------
+
+def make_rank_sessions(world, rank, device, packets_per_rank, pool, strategy):
+    """Weak scaling of BASELINE configs[1]: (4096*world)^2 map, 64*world agents, each rank ingests
+    its own `packets_per_rank` share.  Returns (TiledSwarmMap, sessions, step_fn)."""
+    from . import simulation_tools as st
+    side = 4096 * world
+    origin = (-side * 0.05 / 2.0,) * 2
+    tmap = TiledSwarmMap(side, 0.05, origin[0], origin[1], device=device, strategy=strategy,
+                         max_batch=int(packets_per_rank * 1.25))
+    sessions = []
+    for i in range(pool):
+        full = st.generate_session(n_agents=64 * world, n_packets=packets_per_rank * world, grid_size=side,
+                                   origin=origin, seed=1000 + i)
+        sl = slice(rank * packets_per_rank, (rank + 1) * packets_per_rank)
+        sessions.append({'packets': tmap.ops.stage(full['packets'][sl]),
+                         'agent_idx': torch.from_numpy(full['agent_idx'][sl].copy()).to(device),
+                         'agent_offsets': full['agent_offsets'], 'grid': full['grid']})
+
+    def step(i):
+        s = sessions[i % pool]
+        tmap.update_packets(s['packets'], agent_offsets=s['agent_offsets'], agent_idx=s['agent_idx'])
+
+    return tmap, sessions, step

@@ -214,6 +214,8 @@ class OccupancyGrid:
         if agent_offsets is None:
             # reference rule: ids {1, 2}; only agent 2 is shifted, along x (:842, :851-852)
             tab = np.array([[0.0, 0.0], [0.0, 0.0], [float(separation), 0.0]], np.float64)
+        elif isinstance(agent_offsets, torch.Tensor):
+            return agent_offsets.to(self.device, dtype=torch.float64).reshape(-1, 2).contiguous()
         else:
             tab = np.ascontiguousarray(agent_offsets, np.float64).reshape(-1, 2)
         return torch.from_numpy(tab).to(self.device)

@@ -142,6 +142,25 @@ int occgrid_update_rays(const occgrid_geom* geom,
 int occgrid_scatter_probe(int kind, void* d_plane, int64_t plane_cells, int64_t n_ops,
                           uint32_t seed, void* stream);
 
+/*
+ * Multi-GPU routing: the global grid is cut into `n_bands` row bands
+ * (band b = rows [band_y0[b], band_y0[b+1]), host array of n_bands+1 boundaries).  Every
+ * accepted record is copied, in stable order, to the segment of `d_send` of each band its rays
+ * can reach (robot row +- ceil(MAX_DIST_M/res)+2 cells); d_band_counts[b] receives the segment
+ * lengths (segments are laid out in band order).  Optional side arrays (agent_idx, drift)
+ * travel with the records.  d_status bit 0 = send buffer too small (nothing written).
+ * The caller then exchanges the segments (NCCL all-to-all) and feeds what it receives to
+ * occgrid_integrate_packets with its own window.
+ */
+size_t occgrid_route_workspace_bytes(int64_t n, int n_bands);
+int occgrid_route_packets(const occgrid_geom* geom, int n_bands, const int32_t* band_y0_host,
+                          const uint8_t* d_packets, int64_t n, int stride, int rec_len,
+                          const int32_t* d_agent_idx, const double* d_drift,
+                          const double* d_agent_off, int n_agents,
+                          uint8_t* d_send, int32_t* d_send_agent_idx, double* d_send_drift,
+                          int64_t send_capacity, int64_t* d_band_counts, int32_t* d_status,
+                          uint64_t* d_counters, void* d_ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  *  Map fusion — server_nodes/map_merger.py:35-127
  *
@@ -204,7 +223,7 @@ enum {
     OCCGRID_K_INTEGRATE_GLOBAL = 0, OCCGRID_K_RESOLVE, OCCGRID_K_UPDATE_RAYS, OCCGRID_K_TILE_COUNT,
     OCCGRID_K_TILE_SCAN, OCCGRID_K_TILE_SCATTER, OCCGRID_K_TILE_RAYCAST, OCCGRID_K_TILE_RESOLVE,
     OCCGRID_K_MERGE_EXTRACT, OCCGRID_K_MERGE_BOUNDS, OCCGRID_K_MERGE_VOXEL, OCCGRID_K_MERGE_RASTER,
-    OCCGRID_K_MERGE_FUSE, OCCGRID_K_PROBE, OCCGRID_K_N_KERNELS
+    OCCGRID_K_MERGE_FUSE, OCCGRID_K_PROBE, OCCGRID_K_ROUTE, OCCGRID_K_N_KERNELS
 };
 int occgrid_profile_begin(void);
 int occgrid_profile_end(double* ms_by_kernel, int64_t* launches_by_kernel, int n_slots);

@@ -268,12 +268,12 @@ def make_rank_sessions(world, rank, device, packets_per_rank, pool, strategy):
                          max_batch=int(packets_per_rank * 1.25))
     sessions = []
     for i in range(pool):
-        full = st.generate_session(n_agents=64 * world, n_packets=packets_per_rank * world, grid_size=side,
-                                   origin=origin, seed=1000 + i)
-        sl = slice(rank * packets_per_rank, (rank + 1) * packets_per_rank)
-        sessions.append({'packets': tmap.ops.stage(full['packets'][sl]),
-                         'agent_idx': torch.from_numpy(full['agent_idx'][sl].copy()).to(device),
-                         'agent_offsets': full['agent_offsets'], 'grid': full['grid']})
+        # this rank's share of the stream: all 64*world agents, `packets_per_rank` records
+        sh = st.generate_session(n_agents=64 * world, n_packets=packets_per_rank, grid_size=side,
+                                 origin=origin, seed=1000 + 97 * i + rank)
+        sessions.append({'packets': tmap.ops.stage(sh['packets']),
+                         'agent_idx': torch.from_numpy(sh['agent_idx']).to(device),
+                         'agent_offsets': torch.from_numpy(sh['agent_offsets']).to(device), 'grid': sh['grid']})
 
     def step(i):
         s = sessions[i % pool]

@@ -126,12 +126,13 @@ class TiledSwarmMap:
         self.local = getattr(ops, 'grid', None)
 
     def _agent_table(self, separation, agent_offsets):
-        if agent_offsets is None:
-            tab = np.array([[0.0, 0.0], [0.0, 0.0], [float(separation), 0.0]], np.float64)
+        if isinstance(agent_offsets, torch.Tensor):
+            t = agent_offsets.to(dtype=torch.float64).reshape(-1, 2).contiguous()
+        elif agent_offsets is None:
+            t = torch.tensor([[0.0, 0.0], [0.0, 0.0], [float(separation), 0.0]], dtype=torch.float64)
         else:
-            tab = np.ascontiguousarray(agent_offsets, np.float64).reshape(-1, 2)
-        t = torch.from_numpy(tab)
-        return t.to(self.ops.device) if hasattr(self.ops, 'device') else t
+            t = torch.from_numpy(np.ascontiguousarray(agent_offsets, np.float64).reshape(-1, 2))
+        return t.to(self.ops.device)
 
     def _exchange(self, send, counts, stride, dtype):
         """all_to_all_single of row-segments; returns the rows received (concatenated by source

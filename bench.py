@@ -211,6 +211,7 @@ def main():
     ap.add_argument('--strategy', default='auto')
     ap.add_argument('--packets', type=int, default=PACKETS_PER_BATCH)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--trace', action='store_true', help='print per-step wall times (debug)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -258,9 +259,18 @@ def main():
         tmap, sessions, step = make_rank_sessions(n, rank, dev, npk, POOL, args.strategy)
         grid = tmap.local
 
-    # warm-up
-    for i in range(W):
+    # warm-up (at least one pass over every batch of the pool, so that no allocation or
+    # connection set-up is left for the timed region)
+    for i in range(max(W, POOL)):
         step(i)
+    if args.trace:
+        for i in range(2 * POOL):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            step(i)
+            torch.cuda.synchronize()
+            if rank == 0:
+                print(f'trace step {i}: {(time.perf_counter() - t0) * 1e3:.3f} ms', file=sys.stderr, flush=True)
     torch.cuda.synchronize()
     grid._counters.zero_()
     if world > 1:
@@ -271,6 +281,9 @@ def main():
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
+    if world > 1:
+        dist.barrier()          # nobody enters the timed region before rank 0's sampler is up
+    torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     ev0.record()

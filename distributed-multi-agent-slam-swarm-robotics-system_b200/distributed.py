@@ -63,6 +63,8 @@ class CudaBandOps:
         self._counts = torch.zeros(layout.n_bands, dtype=torch.int64, device=self.device)
         self._ws = None
         self._send = None
+        self._send_idx = None
+        self._send_drift = None
 
     def stage(self, packets):
         return self.grid.stage_packets(packets)[0]
@@ -77,8 +79,12 @@ class CudaBandOps:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         if self._send is None or self._send.shape[0] < cap or self._send.shape[1] != stride:
             self._send = torch.empty((cap, stride), dtype=torch.uint8, device=self.device)
-        s_idx = torch.empty(cap, dtype=torch.int32, device=self.device) if agent_idx is not None else None
-        s_drift = torch.empty((cap, 2), dtype=torch.float64, device=self.device) if drift is not None else None
+        if agent_idx is not None and (self._send_idx is None or self._send_idx.shape[0] < cap):
+            self._send_idx = torch.empty(cap, dtype=torch.int32, device=self.device)
+        if drift is not None and (self._send_drift is None or self._send_drift.shape[0] < cap):
+            self._send_drift = torch.empty((cap, 2), dtype=torch.float64, device=self.device)
+        s_idx = self._send_idx if agent_idx is not None else None
+        s_drift = self._send_drift if drift is not None else None
         rc = self._lib.occgrid_route_packets(
             self._geom, nb, self._band_y0.ctypes.data, packets.data_ptr(), n, stride, 42 if stride >= 42 else 41,
             agent_idx.data_ptr() if agent_idx is not None else None, drift.data_ptr() if drift is not None else None,
@@ -124,6 +130,7 @@ class TiledSwarmMap:
             ops = CudaBandOps(self.layout, self.rank, size, resolution, origin_x, origin_y, device, strategy, max_batch)
         self.ops = ops
         self.local = getattr(ops, 'grid', None)
+        self._recv_bufs = {}
 
     def _agent_table(self, separation, agent_offsets):
         if isinstance(agent_offsets, torch.Tensor):
@@ -140,7 +147,13 @@ class TiledSwarmMap:
         if self.world == 1:
             return send
         recv_counts = self._recv_counts
-        out = self.ops.empty(int(sum(recv_counts)), stride, dtype)
+        rows = int(sum(recv_counts))
+        key = (stride, dtype)
+        buf = self._recv_bufs.get(key)
+        if buf is None or buf.shape[0] < rows:          # grown geometrically, then reused every step
+            buf = self.ops.empty(int(rows * 1.25) + 1024, stride, dtype)
+            self._recv_bufs[key] = buf
+        out = buf[:rows]
         dist.all_to_all_single(out, send.contiguous(), output_split_sizes=recv_counts, input_split_sizes=counts,
                                group=self.group)
         return out

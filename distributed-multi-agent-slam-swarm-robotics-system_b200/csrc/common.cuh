@@ -46,23 +46,26 @@ struct ProfileScope {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Block-wide accumulation of the first N uint64 counter slots: per-thread values -> warp
-// shuffle -> shared memory -> one global atomic per slot per CTA.  All threads must call.
+// shuffle -> per-warp partials in shared memory -> one global atomic per slot per CTA.
+// All threads must call.  smem_acc needs N * 32 entries.
 template <int N>
 __device__ __forceinline__ void block_add_counters(const unsigned long long (&v)[N],
-                                                   unsigned long long* smem_acc /* >= N */, uint64_t* d_counters) {
+                                                   unsigned long long* smem_acc /* >= N * 32 */, uint64_t* d_counters) {
     if (d_counters == nullptr) return;
-    if (threadIdx.x < N) smem_acc[threadIdx.x] = 0ull;
-    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         unsigned long long x = v[i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if ((threadIdx.x & 31) == 0 && x) atomicAdd(&smem_acc[i], x);
+        if (lane == 0) smem_acc[i * 32 + warp] = x;
     }
     __syncthreads();
-    if (threadIdx.x < N && smem_acc[threadIdx.x])
-        atomicAdd(reinterpret_cast<unsigned long long*>(d_counters) + threadIdx.x, smem_acc[threadIdx.x]);
+    if (threadIdx.x < N) {
+        unsigned long long t = 0;
+        for (int w = 0; w < nwarps; ++w) t += smem_acc[threadIdx.x * 32 + w];
+        if (t) atomicAdd(reinterpret_cast<unsigned long long*>(d_counters) + threadIdx.x, t);
+    }
 }
 
 }  // namespace occ

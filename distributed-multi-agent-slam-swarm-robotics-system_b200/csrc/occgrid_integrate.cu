@@ -133,7 +133,7 @@ k_integrate_global(Geom g, const uint8_t* __restrict__ pkts, long long n, int st
                    const double* __restrict__ agent_off, int n_agents,
                    unsigned int* __restrict__ stamps, uint64_t* counters) {
     __shared__ __align__(16) uint8_t s_rec[kThreads * kMaxStride];
-    __shared__ unsigned long long s_acc[OCCGRID_C_OWNED_UPDATES + 1];
+    __shared__ unsigned long long s_acc[(OCCGRID_C_OWNED_UPDATES + 1) * 32];
     const long long first = (long long)blockIdx.x * kThreads;
     const int count = (int)min((long long)kThreads, n - first);
     stage_records(pkts + (size_t)first * stride, (size_t)count * stride, s_rec);
@@ -173,7 +173,7 @@ k_integrate_global(Geom g, const uint8_t* __restrict__ pkts, long long n, int st
 __global__ void __launch_bounds__(kThreads)
 k_update_rays_global(Geom g, const double* __restrict__ rays, const uint8_t* __restrict__ hit, long long n,
                      unsigned int* __restrict__ stamps, uint64_t* counters) {
-    __shared__ unsigned long long s_acc[OCCGRID_C_OWNED_UPDATES + 1];
+    __shared__ unsigned long long s_acc[(OCCGRID_C_OWNED_UPDATES + 1) * 32];
     const long long k = (long long)blockIdx.x * kThreads + threadIdx.x;
     unsigned long long c[OCCGRID_C_OWNED_UPDATES + 1] = {};
     if (k < n) {

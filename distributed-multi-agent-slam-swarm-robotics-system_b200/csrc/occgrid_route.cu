@@ -65,7 +65,7 @@ k_route_count(RouteParams P, const uint8_t* __restrict__ pkts, long long n, int 
               unsigned int* __restrict__ hist /* [n_bands][n_blocks] */, int n_blocks, uint64_t* counters) {
     __shared__ __align__(16) uint8_t s_rec[kRT * kRouteMaxStride];
     __shared__ unsigned int s_hist[kRouteMaxBands];
-    __shared__ unsigned long long s_acc[4];
+    __shared__ unsigned long long s_acc[4 * 32];
     const long long first = (long long)blockIdx.x * kRT;
     const int count = (int)min((long long)kRT, n - first);
     if (threadIdx.x < kRouteMaxBands) s_hist[threadIdx.x] = 0;

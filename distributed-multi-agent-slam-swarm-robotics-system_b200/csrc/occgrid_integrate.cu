@@ -301,6 +301,20 @@ k_probe_global_store8(uint8_t* plane, unsigned long long cells, int iters, unsig
     }
 }
 
+template <bool kReturn>
+__global__ void __launch_bounds__(kThreads)
+k_probe_hot_add(unsigned int* plane, unsigned long long cells, int iters, unsigned int seed) {
+    unsigned int h = mix32(seed ^ (blockIdx.x * kThreads + threadIdx.x));
+    unsigned int acc = 0;
+    for (int i = 0; i < iters; ++i) {
+        h = mix32(h + 0x9e3779b9U);
+        const unsigned long long idx = (((unsigned long long)h * cells) >> 32) * 64ull;   // one hot word per 256 B
+        if (kReturn) acc += atomicAdd(&plane[idx], 1u);
+        else atomicAdd(&plane[idx], 1u);
+    }
+    if (kReturn && acc == 0x12345678u) plane[0] = acc;
+}
+
 template <bool kAtomic>
 __global__ void __launch_bounds__(kThreads)
 k_probe_smem(unsigned int* out, unsigned int cells, int iters, unsigned int seed) {
@@ -480,6 +494,12 @@ int occgrid_scatter_probe(int kind, void* d_plane, int64_t plane_cells, int64_t 
             }
             break;
         }
+        case 4:
+            k_probe_hot_add<false><<<(unsigned int)blocks, kThreads, 0, st>>>((unsigned int*)d_plane, (unsigned long long)plane_cells, iters, seed);
+            break;
+        case 5:
+            k_probe_hot_add<true><<<(unsigned int)blocks, kThreads, 0, st>>>((unsigned int*)d_plane, (unsigned long long)plane_cells, iters, seed);
+            break;
         default:
             set_last_error("probe: unknown kind %d", kind);
             return OCCGRID_E_ARG;

@@ -89,55 +89,124 @@ __device__ __forceinline__ int home_tile(const Geom& g, const TileGeom& tg, doub
     return (py >> kTileShift) * tg.tiles_x + (px >> kTileShift);
 }
 
-template <bool kScatter>
+// ---- binning passes ------------------------------------------------------------------------
+// The hot tiles of a swarm are few (two robots per room), so per-packet global atomics on the
+// tile counters serialise on a handful of L2 addresses.  Each CTA therefore bins kPkPerCta
+// packets in a shared-memory hash table first and touches every distinct tile once.
+constexpr int kPkPerCta = 2048;
+constexpr int kSub = kPkPerCta / kTT;           // packets per thread
+constexpr int kHash = 4096;                     // >= 2 * kPkPerCta would be ideal; distinct tiles <= kPkPerCta
+constexpr unsigned int kEmpty = 0xffffffffu;
+static_assert(kHash >= 2 * kPkPerCta, "hash table must stay at most half full");
+
+__device__ __forceinline__ int hash_insert(unsigned int* keys, unsigned int tile) {
+    unsigned int h = (tile * 2654435761u) >> 20;             // 12 bits
+    for (;;) {
+        const unsigned int old = atomicCAS(&keys[h], kEmpty, tile);
+        if (old == kEmpty || old == tile) return (int)h;
+        h = (h + 1) & (kHash - 1);
+    }
+}
+
 __global__ void __launch_bounds__(kTT)
-k_home_pass(Geom g, TileGeom tg, const uint8_t* __restrict__ pkts, long long n, int stride,
-            const int32_t* __restrict__ agent_idx, const double* __restrict__ drift,
-            const double* __restrict__ agent_off, int n_agents,
-            unsigned int* __restrict__ tile_count, const unsigned int* __restrict__ tile_offset,
-            unsigned int* __restrict__ tile_cursor, const TilePlanHeader* __restrict__ hdr,
-            PoseRec* __restrict__ bins, uint64_t* counters) {
+k_home_count(Geom g, TileGeom tg, const uint8_t* __restrict__ pkts, long long n, int stride,
+             const int32_t* __restrict__ agent_idx, const double* __restrict__ drift,
+             const double* __restrict__ agent_off, int n_agents,
+             unsigned int* __restrict__ tile_count, int* __restrict__ tile_ids, uint64_t* counters) {
     __shared__ __align__(16) uint8_t s_rec[kTT * kMaxStrideT];
-    __shared__ unsigned long long s_acc[(OCCGRID_C_HITS + 1) * 32];
-    if (kScatter && hdr->overflow) return;
-    const long long first = (long long)blockIdx.x * kTT;
-    const int count = (int)min((long long)kTT, n - first);
-    stage_records_t(pkts + (size_t)first * stride, (size_t)count * stride, s_rec);
-    __syncthreads();
+    __shared__ unsigned int s_keys[kHash];
+    __shared__ unsigned int s_vals[kHash];
+    for (int i = threadIdx.x; i < kHash; i += kTT) { s_keys[i] = kEmpty; s_vals[i] = 0u; }
     unsigned long long c[OCCGRID_C_HITS + 1] = {};
-    if ((int)threadIdx.x < count) {
-        const long long k = first + threadIdx.x;
-        double rx, ry, ryaw;
-        float dist[4];
-        c[OCCGRID_C_PACKETS] = 1;
-        const int st = decode_packet(s_rec + threadIdx.x * stride, k, agent_idx, drift, agent_off, n_agents, &rx, &ry, &ryaw, dist);
-        if (st == PKT_DROPPED) c[OCCGRID_C_DROPPED] = 1;
-        else if (st == PKT_BAD_POSE) c[OCCGRID_C_BAD_POSE] = 1;
-        else {
-            c[OCCGRID_C_ACCEPTED] = 1;
-            c[OCCGRID_C_BEAMS] = 4;
+    const long long cta_first = (long long)blockIdx.x * kPkPerCta;
+    for (int sub = 0; sub < kSub; ++sub) {
+        const long long first = cta_first + (long long)sub * kTT;
+        if (first >= n) break;
+        const int count = (int)min((long long)kTT, n - first);
+        __syncthreads();
+        stage_records_t(pkts + (size_t)first * stride, (size_t)count * stride, s_rec);
+        __syncthreads();
+        if ((int)threadIdx.x < count) {
+            const long long k = first + threadIdx.x;
+            double rx, ry, ryaw;
+            float dist[4];
+            c[OCCGRID_C_PACKETS] += 1;
+            int tile = -1;
+            const int st = decode_packet(s_rec + threadIdx.x * stride, k, agent_idx, drift, agent_off, n_agents, &rx, &ry, &ryaw, dist);
+            if (st == PKT_DROPPED) c[OCCGRID_C_DROPPED] += 1;
+            else if (st == PKT_BAD_POSE) c[OCCGRID_C_BAD_POSE] += 1;
+            else {
+                c[OCCGRID_C_ACCEPTED] += 1;
+                c[OCCGRID_C_BEAMS] += 4;
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const double d = (double)dist[s];
-                c[OCCGRID_C_HITS] += (OCC_MIN_DIST_M < d && d <= OCC_MAX_DIST_M) ? 1 : 0;     // :888
-            }
-            const int tile = home_tile(g, tg, rx, ry);
-            if (tile >= 0) {
-                if (!kScatter) {
-                    atomicAdd(&tile_count[tile], 1u);
-                } else {
-                    const unsigned int slot = tile_offset[tile] + atomicAdd(&tile_cursor[tile], 1u);
-                    PoseRec r;
-                    r.rx = rx; r.ry = ry; r.yaw = (float)ryaw;      // ryaw came from an fp32 field: exact
-                    r.d[0] = dist[0]; r.d[1] = dist[1]; r.d[2] = dist[2]; r.d[3] = dist[3];
-                    r.k = (unsigned int)k;
-                    r.pad[0] = r.pad[1] = 0;
-                    bins[slot] = r;
+                for (int s = 0; s < 4; ++s) {
+                    const double d = (double)dist[s];
+                    c[OCCGRID_C_HITS] += (OCC_MIN_DIST_M < d && d <= OCC_MAX_DIST_M) ? 1 : 0;     // :888
                 }
+                tile = home_tile(g, tg, rx, ry);
+                if (tile >= 0) atomicAdd(&s_vals[hash_insert(s_keys, (unsigned int)tile)], 1u);
+            }
+            tile_ids[k] = tile;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHash; i += kTT)
+        if (s_keys[i] != kEmpty) atomicAdd(&tile_count[s_keys[i]], s_vals[i]);
+    // the staging buffer is free now: reuse it for the counter reduction (48 KB static limit)
+    block_add_counters(c, reinterpret_cast<unsigned long long*>(s_rec), counters);
+}
+
+__global__ void __launch_bounds__(kTT)
+k_home_scatter(Geom g, TileGeom tg, const uint8_t* __restrict__ pkts, long long n, int stride,
+               const int32_t* __restrict__ agent_idx, const double* __restrict__ drift,
+               const double* __restrict__ agent_off, int n_agents,
+               const int* __restrict__ tile_ids, const unsigned int* __restrict__ tile_offset,
+               unsigned int* __restrict__ tile_cursor, const TilePlanHeader* __restrict__ hdr,
+               PoseRec* __restrict__ bins) {
+    __shared__ __align__(16) uint8_t s_rec[kTT * kMaxStrideT];
+    __shared__ unsigned int s_keys[kHash];
+    __shared__ unsigned int s_vals[kHash];
+    if (hdr->overflow) return;
+    for (int i = threadIdx.x; i < kHash; i += kTT) { s_keys[i] = kEmpty; s_vals[i] = 0u; }
+    __syncthreads();
+    const long long cta_first = (long long)blockIdx.x * kPkPerCta;
+    unsigned int where[kSub];          // (hash slot << 16) | rank within this CTA's share of the tile
+#pragma unroll
+    for (int sub = 0; sub < kSub; ++sub) {
+        const long long k = cta_first + (long long)sub * kTT + threadIdx.x;
+        where[sub] = kEmpty;
+        if (k < n) {
+            const int tile = tile_ids[k];
+            if (tile >= 0) {
+                const int h = hash_insert(s_keys, (unsigned int)tile);
+                where[sub] = ((unsigned int)h << 16) | atomicAdd(&s_vals[h], 1u);
             }
         }
     }
-    if (!kScatter) block_add_counters(c, s_acc, counters);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHash; i += kTT)          // one reservation per distinct tile
+        if (s_keys[i] != kEmpty) s_vals[i] = tile_offset[s_keys[i]] + atomicAdd(&tile_cursor[s_keys[i]], s_vals[i]);
+#pragma unroll
+    for (int sub = 0; sub < kSub; ++sub) {
+        const long long first = cta_first + (long long)sub * kTT;
+        if (first >= n) break;
+        const int count = (int)min((long long)kTT, n - first);
+        __syncthreads();
+        stage_records_t(pkts + (size_t)first * stride, (size_t)count * stride, s_rec);
+        __syncthreads();
+        if ((int)threadIdx.x < count && where[sub] != kEmpty) {
+            const long long k = first + threadIdx.x;
+            double rx, ry, ryaw;
+            float dist[4];
+            decode_packet(s_rec + threadIdx.x * stride, k, agent_idx, drift, agent_off, n_agents, &rx, &ry, &ryaw, dist);
+            PoseRec r;
+            r.rx = rx; r.ry = ry; r.yaw = (float)ryaw;      // ryaw came from an fp32 field: exact
+            r.d[0] = dist[0]; r.d[1] = dist[1]; r.d[2] = dist[2]; r.d[3] = dist[3];
+            r.k = (unsigned int)k;
+            r.pad[0] = r.pad[1] = 0;
+            bins[s_vals[where[sub] >> 16] + (where[sub] & 0xffffu)] = r;
+        }
+    }
 }
 
 // One CTA.  tile_count[t] -> tile_offset[t] (exclusive), cursors zeroed, work items and the
@@ -339,7 +408,7 @@ k_home_resolve(Geom g, TileGeom tg, const unsigned int* __restrict__ active, Til
 // ---- host side ----------------------------------------------------------------------------
 
 struct TiledLayout {
-    size_t off_stamps, off_count, off_offset, off_cursor, off_active, off_hdr, off_items, off_bins, total;
+    size_t off_stamps, off_count, off_offset, off_cursor, off_active, off_hdr, off_items, off_ids, off_bins, total;
     unsigned long long max_records;
     unsigned int max_items;
 };
@@ -359,6 +428,7 @@ static TiledLayout tiled_layout(const occgrid_geom* geom, int64_t max_packets) {
     L.off_active = o; o += align_up((size_t)(tg.n_tiles + 1) * 4, 256);
     L.off_hdr = o;    o += 256;
     L.off_items = o;  o += align_up((size_t)L.max_items * sizeof(uint4), 256);
+    L.off_ids = o;    o += align_up((size_t)L.max_records * sizeof(int), 256);
     L.off_bins = o;   o += align_up((size_t)L.max_records * sizeof(PoseRec), 256);
     L.total = o;
     return L;
@@ -391,9 +461,10 @@ int integrate_packets_tiled(const occgrid_geom* geom, const uint8_t* d_packets, 
     TilePlanHeader* hdr = reinterpret_cast<TilePlanHeader*>(ws + L.off_hdr);
     uint4* items = reinterpret_cast<uint4*>(ws + L.off_items);
     PoseRec* bins = reinterpret_cast<PoseRec*>(ws + L.off_bins);
+    int* tile_ids = reinterpret_cast<int*>(ws + L.off_ids);
     const Geom g = to_geom(geom);
     const TileGeom tg = tile_geom(geom);
-    const unsigned int blocks = (unsigned int)((n + kTT - 1) / kTT);
+    const unsigned int blocks = (unsigned int)((n + kPkPerCta - 1) / kPkPerCta);
     const size_t win_bytes = (size_t)tg.win_side * tg.pitch * 4;
     int sms = 148;
     {
@@ -410,8 +481,8 @@ int integrate_packets_tiled(const occgrid_geom* geom, const uint8_t* d_packets, 
         ctas_per_sm = 1;
     {
         ProfileScope ps(K_TILE_COUNT, st);
-        k_home_pass<false><<<blocks, kTT, 0, st>>>(g, tg, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents,
-                                                  tile_count, tile_offset, tile_cursor, hdr, bins, d_counters);
+        k_home_count<<<blocks, kTT, 0, st>>>(g, tg, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents,
+                                            tile_count, tile_ids, d_counters);
     }
     {
         ProfileScope ps(K_TILE_SCAN, st);
@@ -420,8 +491,8 @@ int integrate_packets_tiled(const occgrid_geom* geom, const uint8_t* d_packets, 
     }
     {
         ProfileScope ps(K_TILE_SCATTER, st);
-        k_home_pass<true><<<blocks, kTT, 0, st>>>(g, tg, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents,
-                                                 tile_count, tile_offset, tile_cursor, hdr, bins, d_counters);
+        k_home_scatter<<<blocks, kTT, 0, st>>>(g, tg, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents,
+                                              tile_ids, tile_offset, tile_cursor, hdr, bins);
     }
     {
         ProfileScope ps(K_TILE_RAYCAST, st);

@@ -137,6 +137,9 @@ int occgrid_update_rays(const occgrid_geom* geom,
  *   kind 1: plain 1-byte stores to a global plane of `plane_cells` bytes
  *   kind 2: atomicMax(u32) on a per-CTA shared-memory tile of `plane_cells` words
  *   kind 3: plain 4-byte stores to a per-CTA shared-memory tile
+ *   kind 4: atomicAdd without return (red.global.add) spread over only `plane_cells` HOT words,
+ *           one per 256 B (plane must hold plane_cells*64 words) — contended-address rate
+ *   kind 5: as 4 but using the returned value (atom.global.add)
  * Used by bench.py to put a measured ceiling beside the integrate kernels.
  */
 int occgrid_scatter_probe(int kind, void* d_plane, int64_t plane_cells, int64_t n_ops,

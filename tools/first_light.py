@@ -19,15 +19,17 @@ def timeit(fn, warm=3, it=10):
 
 out = {}
 stream = torch.cuda.current_stream().cuda_stream
-nops = 1 << 28
+nops = 1 << 26
 for name, kind, cells, dtype in [('global_atomicmax_u32_64MiB', 0, 4096*4096, torch.int32),
                                  ('global_atomicmax_u32_2GiB', 0, 8192*65536, torch.int32),
                                  ('global_atomicmax_u32_1.2MiB', 0, 307200, torch.int32),
                                  ('global_store_u8_16MiB', 1, 4096*4096, torch.uint8),
                                  ('smem_atomicmax_16KiB', 2, 4096, torch.int32),
                                  ('smem_atomicmax_64KiB', 2, 16384, torch.int32),
-                                 ('smem_store_64KiB', 3, 16384, torch.int32)]:
-    plane = torch.zeros(max(cells, 1<<20), dtype=dtype, device=dev)
+                                 ('smem_store_64KiB', 3, 16384, torch.int32),
+                                 ('hot256_red_add', 4, 256, torch.int32), ('hot256_atom_add', 5, 256, torch.int32),
+                                 ('hot4096_red_add', 4, 4096, torch.int32), ('hot16_red_add', 4, 16, torch.int32)]:
+    plane = torch.zeros(max(cells * 64, 1<<20), dtype=dtype, device=dev)
     def f():
         rc = lib.occgrid_scatter_probe(kind, plane.data_ptr(), cells, nops, 123, stream)
         assert rc == 0, _native.last_error()

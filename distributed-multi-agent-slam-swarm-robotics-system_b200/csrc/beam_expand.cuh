@@ -14,6 +14,7 @@ namespace occ {
 
 struct Geom {
     double ox, oy, res;
+    double inv_res;          // 1.0 / res, used only by the screened fast path
     int size_x, size_y;
     int win_x0, win_y0, win_w, win_h;
 };
@@ -58,21 +59,24 @@ OCC_HD int trunc_cell(double q) {
 #endif
 }
 
-// Half-width of the band around an integer quotient inside which a <=4-ulp error of
-// sin/cos could move trunc(q).  Derivation (DESIGN.md "fp64 trig parity"): the error of
-// w = rx + range*c is below 1.6e-15 + 2^-52*|w|, the subtraction and the division add one
-// rounding each, so |dq| <= 1.3 * 2^-52 * S with S = (|rx| + |o| + 2) / res.  2^-46 * S
-// leaves a 48x margin.
-OCC_HD double boundary_tolerance(double r, double o, double res) {
-    return OCC_DMUL(OCC_DDIV(fabs(r) + fabs(o) + 2.0, res), 0x1p-46);
+// Screening tolerance of the fast path.  The fast path evaluates ONE library sincos per packet
+// (the other three sensor directions are quarter turns of it) and multiplies by 1/res instead
+// of dividing; a cell index can differ from the reference's only if the approximate quotient
+// lies within `tol` of an integer, in which case the beam is re-evaluated exactly (true angle
+// yaw + ANG[s], double-double sin/cos, true division).  Error budget (DESIGN.md "fp64 parity"):
+//   |dq| <= 2^-52 * (3.5 * S + 0.65 * (|yaw| + 9) / res),  S = (|r| + |o| + 2) / res
+// (2-ulp library sincos, the rounding of yaw + ANG[s], 1/res and every rounded operation);
+// tol = 2^-47 * (S + (|yaw| + 9) / res) leaves a 9x margin on the first term, 49x on the second.
+OCC_HD double screening_tolerance(double r, double o, double yaw, double inv_res) {
+    return OCC_DMUL(OCC_DMUL(fabs(r) + fabs(o) + fabs(yaw) + 11.0, inv_res), 0x1p-47);
 }
 
-OCC_HD bool near_cell_boundary(double q, double tol) { return fabs(q - rint(q)) <= tol; }
+OCC_HD bool near_cell_boundary(double q, double tol) { return !(fabs(q - rint(q)) > tol); }   // true for NaN/inf too
 
 // Library sincos: CUDA's on the device, glibc's on the host.  FastSinCos is a hook so the
 // CPU tests can substitute a deliberately perturbed routine and exercise the slow path.
 struct LibSinCos {
-    OCC_HD void operator()(double a, double* s, double* c) const {
+    OCC_HD_MEMBER void operator()(double a, double* s, double* c) const {
 #if defined(__CUDA_ARCH__)
         sincos(a, s, c);
 #else
@@ -88,26 +92,25 @@ OCC_HD double sensor_angle(int s) {
     return s == 0 ? 0.0 : (s == 1 ? h : (s == 2 ? 0x1.921fb54442d18p+1 : -h));
 }
 
-// Endpoint of one beam (:887-891 | :898-902) and its cell (:143).
+// Endpoint cell of one beam (:887-891 | :898-902, :143).  (sn, cs) is the screened estimate of
+// sin/cos of the beam direction; the exact path recomputes everything the way the reference does.
 template <class FastSinCos>
 OCC_HD void expand_beam(const Geom& g, double rx, double ry, double ryaw, int x0, int y0, bool origin_ok,
-                        int sensor, float dist_f32, double tolx, double toly, const FastSinCos& fsc, Beam* b) {
+                        int sensor, float dist_f32, double sn, double cs, double tolx, double toly,
+                        const FastSinCos& fsc, Beam* b) {
     double dist = (double)dist_f32;
     bool hit = (OCC_MIN_DIST_M < dist) && (dist <= OCC_MAX_DIST_M);     // :888 (false for NaN)
     double range = hit ? dist : OCC_MAX_DIST_M;                          // :900 reduces to MAX for every non-hit
-    double ang = OCC_DADD(ryaw, sensor_angle(sensor));                  // :887
-    double sn, cs;
-    fsc(ang, &sn, &cs);
-    double qx = cell_quotient(OCC_DADD(rx, OCC_DMUL(range, cs)), g.ox, g.res);
-    double qy = cell_quotient(OCC_DADD(ry, OCC_DMUL(range, sn)), g.oy, g.res);
+    double qx = OCC_DMUL(OCC_DADD(OCC_DADD(rx, OCC_DMUL(range, cs)), -g.ox), g.inv_res);
+    double qy = OCC_DMUL(OCC_DADD(OCC_DADD(ry, OCC_DMUL(range, sn)), -g.oy), g.inv_res);
     int slow = 0;
     if (near_cell_boundary(qx, tolx) || near_cell_boundary(qy, toly)) {
+        double ang = OCC_DADD(ryaw, sensor_angle(sensor));              // :887
         double s2, c2;
-        if (sincos_dd(ang, &s2, &c2)) {
-            qx = cell_quotient(OCC_DADD(rx, OCC_DMUL(range, c2)), g.ox, g.res);
-            qy = cell_quotient(OCC_DADD(ry, OCC_DMUL(range, s2)), g.oy, g.res);
-            slow = 1;
-        }
+        if (!sincos_dd(ang, &s2, &c2)) fsc(ang, &s2, &c2);
+        qx = cell_quotient(OCC_DADD(rx, OCC_DMUL(range, c2)), g.ox, g.res);   // :890 | :901, :143
+        qy = cell_quotient(OCC_DADD(ry, OCC_DMUL(range, s2)), g.oy, g.res);   // :891 | :902
+        slow = 1;
     }
     b->hit = hit ? 1 : 0;
     b->slow = slow;
@@ -154,15 +157,22 @@ OCC_HD int decode_packet(const uint8_t* p, long long k, const int32_t* agent_idx
 template <class FastSinCos>
 OCC_HD void expand_packet(const Geom& g, double rx, double ry, double ryaw, const float dist[4],
                           const FastSinCos& fsc, Beam out[4]) {
-    double q0x = cell_quotient(rx, g.ox, g.res);                                            // :142
-    double q0y = cell_quotient(ry, g.oy, g.res);
+    const double tolx = screening_tolerance(rx, g.ox, ryaw, g.inv_res);
+    const double toly = screening_tolerance(ry, g.oy, ryaw, g.inv_res);
+    double q0x = OCC_DMUL(OCC_DADD(rx, -g.ox), g.inv_res);
+    double q0y = OCC_DMUL(OCC_DADD(ry, -g.oy), g.inv_res);
+    if (near_cell_boundary(q0x, tolx)) q0x = cell_quotient(rx, g.ox, g.res);               // :142
+    if (near_cell_boundary(q0y, toly)) q0y = cell_quotient(ry, g.oy, g.res);
     bool origin_ok = quotient_in_range(q0x) && quotient_in_range(q0y);
     int x0 = origin_ok ? trunc_cell(q0x) : 0;
     int y0 = origin_ok ? trunc_cell(q0y) : 0;
-    double tolx = boundary_tolerance(rx, g.ox, g.res);
-    double toly = boundary_tolerance(ry, g.oy, g.res);
-#pragma unroll
-    for (int s = 0; s < 4; ++s) expand_beam(g, rx, ry, ryaw, x0, y0, origin_ok, s, dist[s], tolx, toly, fsc, &out[s]);
+    double s0, c0;
+    fsc(ryaw, &s0, &c0);
+    // front: yaw, left: yaw + pi/2, back: yaw + pi, right: yaw - pi/2 (:61-66) as quarter turns
+    expand_beam(g, rx, ry, ryaw, x0, y0, origin_ok, 0, dist[0], s0, c0, tolx, toly, fsc, &out[0]);
+    expand_beam(g, rx, ry, ryaw, x0, y0, origin_ok, 1, dist[1], c0, -s0, tolx, toly, fsc, &out[1]);
+    expand_beam(g, rx, ry, ryaw, x0, y0, origin_ok, 2, dist[2], -s0, -c0, tolx, toly, fsc, &out[2]);
+    expand_beam(g, rx, ry, ryaw, x0, y0, origin_ok, 3, dist[3], -c0, s0, tolx, toly, fsc, &out[3]);
 }
 
 // Explicit world-space ray -> beam (OccupancyGrid.update_ray's two world_to_grid calls, :142-143).

@@ -20,7 +20,7 @@ bool cuda_ok(cudaError_t e, const char* what);
 
 inline Geom to_geom(const occgrid_geom* g) {
     Geom o;
-    o.ox = g->ox; o.oy = g->oy; o.res = g->res;
+    o.ox = g->ox; o.oy = g->oy; o.res = g->res; o.inv_res = 1.0 / g->res;
     o.size_x = g->size_x; o.size_y = g->size_y;
     o.win_x0 = g->win_x0; o.win_y0 = g->win_y0; o.win_w = g->win_w; o.win_h = g->win_h;
     return o;

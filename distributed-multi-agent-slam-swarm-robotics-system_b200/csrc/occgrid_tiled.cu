@@ -342,13 +342,15 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
         // flush: window rows are contiguous in the stamp plane -> coalesced reductions
         const int lx_lo = max(0, g.win_x0 - wx0), lx_hi = min(side, g.win_x0 + g.win_w - wx0);
         const int ly_lo = max(0, g.win_y0 - wy0), ly_hi = min(side, g.win_y0 + g.win_h - wy0);
-        const int fw = lx_hi - lx_lo;
-        if (fw > 0 && ly_hi > ly_lo) {
-            const int total = fw * (ly_hi - ly_lo);
-            for (int idx = threadIdx.x; idx < total; idx += kTT) {
-                const int ly = ly_lo + idx / fw, lx = lx_lo + idx % fw;
-                const unsigned int v = s_win[ly * pitch + lx];
-                if (v) atomicMax(&stamps[(size_t)(wy0 + ly - g.win_y0) * g.win_w + (wx0 + lx - g.win_x0)], v);
+        if (lx_hi > lx_lo) {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            for (int ly = ly_lo + warp; ly < ly_hi; ly += kTT / 32) {          // one warp per window row
+                const unsigned int* row = s_win + ly * pitch;
+                unsigned int* out = stamps + (size_t)(wy0 + ly - g.win_y0) * g.win_w + (wx0 - g.win_x0);
+                for (int lx = lx_lo + lane; lx < lx_hi; lx += 32) {
+                    const unsigned int v = row[lx];
+                    if (v) atomicMax(out + lx, v);
+                }
             }
         }
     }

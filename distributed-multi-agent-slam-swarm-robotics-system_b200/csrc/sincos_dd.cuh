@@ -5,20 +5,22 @@
 // truncates (wx - ox) / res to a cell index (:123-124).  glibc's results are correctly
 // rounded except in rare near-midpoint cases (stated bound 0.55 ULP); CUDA's sincos() is a
 // <=2 ULP routine.  A last-bit difference flips a cell index only when the quotient lies
-// within ~1e-11 of an integer, so the integrate kernel runs CUDA's sincos() first and
-// re-evaluates with this routine only the beams whose quotient is that close to a cell
-// boundary (see beam_expand.cuh).  Everything stays on the device.
+// within ~1e-11 of an integer, so the integrate kernels run a screened fast path (CUDA's
+// sincos(), see beam_expand.cuh) and re-evaluate with this routine only the beams whose
+// quotient is that close to a cell boundary.  Everything stays on the device.
 //
 // The file is plain C++ when compiled without nvcc so the CPU test-suite can check it
-// against mpmath (tests/test_sincos_dd.py builds tests/host_harness.cpp with g++).
+// against mpmath (tests/test_host_expand.py builds tests/host_harness.cpp with g++).
 #pragma once
 #include <math.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
 #define OCC_HD __host__ __device__ __forceinline__
+#define OCC_HD_MEMBER __host__ __device__ __forceinline__
 #else
 #define OCC_HD static inline
+#define OCC_HD_MEMBER inline
 #endif
 
 namespace occ {

@@ -278,24 +278,46 @@ k_tile_plan(unsigned int* __restrict__ tile_count, unsigned int* __restrict__ ti
     }
 }
 
-// Walk one beam into the shared-memory window (exact reference Bresenham, :158-179).
-// (x, y) are window-local; by construction every cell lies inside the window, the unsigned
-// compare only guards against a violated reach bound.
+// Walk one beam into the shared-memory window (exact reference Bresenham, :158-179: strict
+// `e2 > -dy` / `e2 < dx`, both may fire, sx = -1 when x0 == x1).  (x, y) are window-local.
+// Both end points inside the (convex) window => every cell is inside, so the hot loop carries
+// no bounds test and steps a running shared-memory offset instead of recomputing y*pitch+x.
 __device__ __forceinline__ void draw_beam_smem(unsigned int* __restrict__ s_win, int side, int pitch, int x, int y,
                                                int ddx, int ddy, unsigned int free_stamp, bool hit, bool skip_first) {
     const int dx = abs(ddx), dy = abs(ddy);
-    const int sx = ddx > 0 ? 1 : -1, sy = ddy > 0 ? 1 : -1;      // sx = -1 when x0 == x1 (:163)
     int err = dx - dy;
     const int n = max(dx, dy);
+    const unsigned int us = (unsigned int)side;
+    if ((unsigned int)x < us && (unsigned int)y < us && (unsigned int)(x + ddx) < us && (unsigned int)(y + ddy) < us) {
+        const int sxo = ddx > 0 ? 1 : -1;
+        const int syo = ddy > 0 ? pitch : -pitch;
+        int off = y * pitch + x;
+        int i = 0;
+        if (skip_first) {                     // the start cell is overwritten by a later beam of the packet
+            if (n == 0) return;
+            const int e2 = 2 * err;
+            if (e2 > -dy) { err -= dy; off += sxo; }
+            if (e2 < dx)  { err += dx; off += syo; }
+            i = 1;
+        }
+        for (; i < n; ++i) {
+            atomicMax(&s_win[off], free_stamp);
+            const int e2 = 2 * err;
+            if (e2 > -dy) { err -= dy; off += sxo; }
+            if (e2 < dx)  { err += dx; off += syo; }
+        }
+        if (hit) atomicMax(&s_win[off], free_stamp | 1u);
+        return;
+    }
+    // guarded path (cannot happen while the reach bound holds): per-cell window test
+    const int sx = ddx > 0 ? 1 : -1, sy = ddy > 0 ? 1 : -1;
     for (int i = 0; i < n; ++i) {
-        if (!(i == 0 && skip_first) && (unsigned int)x < (unsigned int)side && (unsigned int)y < (unsigned int)side)
-            atomicMax(&s_win[y * pitch + x], free_stamp);
+        if (!(i == 0 && skip_first) && (unsigned int)x < us && (unsigned int)y < us) atomicMax(&s_win[y * pitch + x], free_stamp);
         const int e2 = 2 * err;
         if (e2 > -dy) { err -= dy; x += sx; }
         if (e2 < dx)  { err += dx; y += sy; }
     }
-    if (hit && !(n == 0 && skip_first) && (unsigned int)x < (unsigned int)side && (unsigned int)y < (unsigned int)side)
-        atomicMax(&s_win[y * pitch + x], free_stamp | 1u);
+    if (hit && !(n == 0 && skip_first) && (unsigned int)x < us && (unsigned int)y < us) atomicMax(&s_win[y * pitch + x], free_stamp | 1u);
 }
 
 __global__ void __launch_bounds__(kTT)

@@ -13,10 +13,10 @@
 // trigonometry, one record per packet, no duplicates:
 //
 //   k_home_count    thread/packet: decode (:828-843), pose correction (:851-857), robot cell
-//                   (:142) -> count packets per home tile
+//                   (:142) -> 48-byte pose record (packet order) + packets per home tile
 //   k_tile_plan     one CTA: exclusive scan of the counts -> bin offsets, (tile, chunk) work
 //                   items of <= kChunkPk packets, list of active tiles
-//   k_home_scatter  thread/packet: same decode, write a 48-byte pose record into its bin
+//   k_home_scatter  thread/packet: write the packet's index into its tile's bin
 //   k_home_raycast  persistent CTAs pull work items: zero the (64+2R)^2 smem window, expand
 //                   each record into its 4 beams (fp64 endpoints, :887-902) and walk the exact
 //                   reference Bresenham (:158-179) with atomicMax in shared memory; then flush
@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(kTT)
 k_home_count(Geom g, TileGeom tg, const uint8_t* __restrict__ pkts, long long n, int stride,
              const int32_t* __restrict__ agent_idx, const double* __restrict__ drift,
              const double* __restrict__ agent_off, int n_agents,
-             unsigned int* __restrict__ tile_count, int* __restrict__ tile_ids, uint64_t* counters) {
+             unsigned int* __restrict__ tile_count, int* __restrict__ tile_ids, PoseRec* __restrict__ recs,
+             uint64_t* counters) {
     __shared__ __align__(16) uint8_t s_rec[kTT * kMaxStrideT];
     __shared__ unsigned int s_keys[kHash];
     __shared__ unsigned int s_vals[kHash];
@@ -144,7 +145,15 @@ k_home_count(Geom g, TileGeom tg, const uint8_t* __restrict__ pkts, long long n,
                     c[OCCGRID_C_HITS] += (OCC_MIN_DIST_M < d && d <= OCC_MAX_DIST_M) ? 1 : 0;     // :888
                 }
                 tile = home_tile(g, tg, rx, ry);
-                if (tile >= 0) atomicAdd(&s_vals[hash_insert(s_keys, (unsigned int)tile)], 1u);
+                if (tile >= 0) {
+                    atomicAdd(&s_vals[hash_insert(s_keys, (unsigned int)tile)], 1u);
+                    PoseRec r;
+                    r.rx = rx; r.ry = ry; r.yaw = (float)ryaw;      // ryaw came from an fp32 field: exact
+                    r.d[0] = dist[0]; r.d[1] = dist[1]; r.d[2] = dist[2]; r.d[3] = dist[3];
+                    r.k = (unsigned int)k;
+                    r.pad[0] = r.pad[1] = 0;
+                    recs[k] = r;                                    // packet order: coalesced 48-byte stores
+                }
             }
             tile_ids[k] = tile;
         }
@@ -157,13 +166,9 @@ k_home_count(Geom g, TileGeom tg, const uint8_t* __restrict__ pkts, long long n,
 }
 
 __global__ void __launch_bounds__(kTT)
-k_home_scatter(Geom g, TileGeom tg, const uint8_t* __restrict__ pkts, long long n, int stride,
-               const int32_t* __restrict__ agent_idx, const double* __restrict__ drift,
-               const double* __restrict__ agent_off, int n_agents,
-               const int* __restrict__ tile_ids, const unsigned int* __restrict__ tile_offset,
+k_home_scatter(long long n, const int* __restrict__ tile_ids, const unsigned int* __restrict__ tile_offset,
                unsigned int* __restrict__ tile_cursor, const TilePlanHeader* __restrict__ hdr,
-               PoseRec* __restrict__ bins) {
-    __shared__ __align__(16) uint8_t s_rec[kTT * kMaxStrideT];
+               unsigned int* __restrict__ bins) {
     __shared__ unsigned int s_keys[kHash];
     __shared__ unsigned int s_vals[kHash];
     if (hdr->overflow) return;
@@ -186,26 +191,11 @@ k_home_scatter(Geom g, TileGeom tg, const uint8_t* __restrict__ pkts, long long 
     __syncthreads();
     for (int i = threadIdx.x; i < kHash; i += kTT)          // one reservation per distinct tile
         if (s_keys[i] != kEmpty) s_vals[i] = tile_offset[s_keys[i]] + atomicAdd(&tile_cursor[s_keys[i]], s_vals[i]);
+    __syncthreads();
 #pragma unroll
     for (int sub = 0; sub < kSub; ++sub) {
-        const long long first = cta_first + (long long)sub * kTT;
-        if (first >= n) break;
-        const int count = (int)min((long long)kTT, n - first);
-        __syncthreads();
-        stage_records_t(pkts + (size_t)first * stride, (size_t)count * stride, s_rec);
-        __syncthreads();
-        if ((int)threadIdx.x < count && where[sub] != kEmpty) {
-            const long long k = first + threadIdx.x;
-            double rx, ry, ryaw;
-            float dist[4];
-            decode_packet(s_rec + threadIdx.x * stride, k, agent_idx, drift, agent_off, n_agents, &rx, &ry, &ryaw, dist);
-            PoseRec r;
-            r.rx = rx; r.ry = ry; r.yaw = (float)ryaw;      // ryaw came from an fp32 field: exact
-            r.d[0] = dist[0]; r.d[1] = dist[1]; r.d[2] = dist[2]; r.d[3] = dist[3];
-            r.k = (unsigned int)k;
-            r.pad[0] = r.pad[1] = 0;
-            bins[s_vals[where[sub] >> 16] + (where[sub] & 0xffffu)] = r;
-        }
+        const long long k = cta_first + (long long)sub * kTT + threadIdx.x;
+        if (where[sub] != kEmpty) bins[s_vals[where[sub] >> 16] + (where[sub] & 0xffffu)] = (unsigned int)k;
     }
 }
 
@@ -322,7 +312,8 @@ __device__ __forceinline__ void draw_beam_smem(unsigned int* __restrict__ s_win,
 
 __global__ void __launch_bounds__(kTT)
 k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHeader* __restrict__ hdr,
-               const PoseRec* __restrict__ bins, unsigned int* __restrict__ stamps, uint64_t* counters) {
+               const unsigned int* __restrict__ bins, const PoseRec* __restrict__ recs,
+               unsigned int* __restrict__ stamps, uint64_t* counters) {
     extern __shared__ unsigned int s_win[];
     __shared__ unsigned int s_item;
     __shared__ unsigned long long s_acc[3 * 32];
@@ -342,7 +333,7 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
         const int wx0 = g.win_x0 - tg.pad + (ttx << kTileShift) - tg.reach;
         const int wy0 = g.win_y0 - tg.pad + (tty << kTileShift) - tg.reach;
         for (unsigned int r = item.y + threadIdx.x; r < item.z; r += kTT) {
-            const PoseRec rec = bins[r];
+            const PoseRec rec = recs[bins[r]];
             const float dist[4] = {rec.d[0], rec.d[1], rec.d[2], rec.d[3]};
             Beam b[4];
             expand_packet(g, rec.rx, rec.ry, (double)rec.yaw, dist, LibSinCos(), b);
@@ -432,7 +423,7 @@ k_home_resolve(Geom g, TileGeom tg, const unsigned int* __restrict__ active, Til
 // ---- host side ----------------------------------------------------------------------------
 
 struct TiledLayout {
-    size_t off_stamps, off_count, off_offset, off_cursor, off_active, off_hdr, off_items, off_ids, off_bins, total;
+    size_t off_stamps, off_count, off_offset, off_cursor, off_active, off_hdr, off_items, off_ids, off_bins, off_recs, total;
     unsigned long long max_records;
     unsigned int max_items;
 };
@@ -453,7 +444,8 @@ static TiledLayout tiled_layout(const occgrid_geom* geom, int64_t max_packets) {
     L.off_hdr = o;    o += 256;
     L.off_items = o;  o += align_up((size_t)L.max_items * sizeof(uint4), 256);
     L.off_ids = o;    o += align_up((size_t)L.max_records * sizeof(int), 256);
-    L.off_bins = o;   o += align_up((size_t)L.max_records * sizeof(PoseRec), 256);
+    L.off_bins = o;   o += align_up((size_t)L.max_records * sizeof(unsigned int), 256);
+    L.off_recs = o;   o += align_up((size_t)L.max_records * sizeof(PoseRec), 256);
     L.total = o;
     return L;
 }
@@ -484,7 +476,8 @@ int integrate_packets_tiled(const occgrid_geom* geom, const uint8_t* d_packets, 
     unsigned int* active = reinterpret_cast<unsigned int*>(ws + L.off_active);
     TilePlanHeader* hdr = reinterpret_cast<TilePlanHeader*>(ws + L.off_hdr);
     uint4* items = reinterpret_cast<uint4*>(ws + L.off_items);
-    PoseRec* bins = reinterpret_cast<PoseRec*>(ws + L.off_bins);
+    unsigned int* bins = reinterpret_cast<unsigned int*>(ws + L.off_bins);
+    PoseRec* recs = reinterpret_cast<PoseRec*>(ws + L.off_recs);
     int* tile_ids = reinterpret_cast<int*>(ws + L.off_ids);
     const Geom g = to_geom(geom);
     const TileGeom tg = tile_geom(geom);
@@ -506,7 +499,7 @@ int integrate_packets_tiled(const occgrid_geom* geom, const uint8_t* d_packets, 
     {
         ProfileScope ps(K_TILE_COUNT, st);
         k_home_count<<<blocks, kTT, 0, st>>>(g, tg, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents,
-                                            tile_count, tile_ids, d_counters);
+                                            tile_count, tile_ids, recs, d_counters);
     }
     {
         ProfileScope ps(K_TILE_SCAN, st);
@@ -515,12 +508,11 @@ int integrate_packets_tiled(const occgrid_geom* geom, const uint8_t* d_packets, 
     }
     {
         ProfileScope ps(K_TILE_SCATTER, st);
-        k_home_scatter<<<blocks, kTT, 0, st>>>(g, tg, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents,
-                                              tile_ids, tile_offset, tile_cursor, hdr, bins);
+        k_home_scatter<<<blocks, kTT, 0, st>>>(n, tile_ids, tile_offset, tile_cursor, hdr, bins);
     }
     {
         ProfileScope ps(K_TILE_RAYCAST, st);
-        k_home_raycast<<<sms * ctas_per_sm, kTT, win_bytes, st>>>(g, tg, items, hdr, bins, stamps, d_counters);
+        k_home_raycast<<<sms * ctas_per_sm, kTT, win_bytes, st>>>(g, tg, items, hdr, bins, recs, stamps, d_counters);
     }
     {
         ProfileScope ps(K_TILE_RESOLVE, st);

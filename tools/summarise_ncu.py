@@ -5,6 +5,7 @@
 import csv, json, os, re, subprocess, sys, collections
 tag, rep = sys.argv[1], sys.argv[2]
 launches = sys.argv[3] if len(sys.argv) > 3 and sys.argv[3] != '-' else None
+traffic_kernel = sys.argv[4] if len(sys.argv) > 4 else None
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out = os.path.join(ROOT, 'profiles')
 os.makedirs(out, exist_ok=True)
@@ -38,8 +39,9 @@ def mb(d, key):
             unit = k[k.index('[') + 1:-1]
             return f * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[unit]
     return 0.0
-tr = [mb(d, 'dram__bytes_read.sum') + mb(d, 'dram__bytes_write.sum') for d in summ]
-json.dump({'kernel': summ[0]['kernel'], 'dram_bytes_per_launch': sum(tr) / len(tr), 'launches_captured': len(tr),
+sel = [d for d in summ if (traffic_kernel is None or traffic_kernel in d['kernel'])]
+tr = [mb(d, 'dram__bytes_read.sum') + mb(d, 'dram__bytes_write.sum') for d in sel]
+json.dump({'kernel': sel[0]['kernel'], 'dram_bytes_per_launch': sum(tr) / len(tr), 'launches_captured': len(tr),
            'source': f'profiles/{tag}_ncu_full_summary.json'}, open(os.path.join(out, 'ncu_traffic.json'), 'w'), indent=1)
 # stall hot spots
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout

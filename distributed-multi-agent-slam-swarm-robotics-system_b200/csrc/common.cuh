@@ -28,6 +28,17 @@ inline Geom to_geom(const occgrid_geom* g) {
 
 int validate_geom(const occgrid_geom* g);
 
+// A decoded, pose-corrected packet (struct occgrid_pose_rec in the public header): what the
+// TILED strategy bins, and what travels between GPUs after routing.
+struct __align__(16) PoseRec {       // 48 bytes
+    double rx, ry;                   // corrected pose (dual_bot_mapper.py:851-857)
+    float yaw;
+    float d[4];                      // front, left, back, right (:882-885)
+    unsigned int k;                  // index of the source record (informational)
+    unsigned int pad[2];
+};
+static_assert(sizeof(PoseRec) == 48, "PoseRec must be 48 bytes");
+
 // Optional per-kernel timing (occgrid_profile_begin/_end): when enabled, every launch of one
 // of our kernels is bracketed by cudaEventRecord on its stream, so bench.py can report the
 // dominant kernel's own duration and the exact number of launches.

@@ -170,6 +170,39 @@ k_integrate_global(Geom g, const uint8_t* __restrict__ pkts, long long n, int st
     block_add_counters(c, s_acc, counters);
 }
 
+// Decoded input (routed pose records): same as k_integrate_global minus the decode.
+__global__ void __launch_bounds__(kThreads)
+k_integrate_poses_global(Geom g, const PoseRec* __restrict__ recs, long long n,
+                         unsigned int* __restrict__ stamps, uint64_t* counters) {
+    __shared__ unsigned long long s_acc[(OCCGRID_C_OWNED_UPDATES + 1) * 32];
+    const long long k = (long long)blockIdx.x * kThreads + threadIdx.x;
+    unsigned long long c[OCCGRID_C_OWNED_UPDATES + 1] = {};
+    if (k < n) {
+        const PoseRec r = recs[k];
+        c[OCCGRID_C_PACKETS] = 1;
+        if (!(isfinite(r.rx) && isfinite(r.ry) && isfinite(r.yaw))) c[OCCGRID_C_BAD_POSE] = 1;
+        else {
+            c[OCCGRID_C_ACCEPTED] = 1;
+            const float dist[4] = {r.d[0], r.d[1], r.d[2], r.d[3]};
+            Beam b[4];
+            expand_packet(g, r.rx, r.ry, (double)r.yaw, dist, LibSinCos(), b);
+            bool later_writes_first = false;
+#pragma unroll
+            for (int s = 3; s >= 0; --s) {
+                const int cells = b[s].valid ? beam_cells(b[s]) : 0;
+                c[OCCGRID_C_BEAMS] += 1;
+                c[OCCGRID_C_HITS] += b[s].hit;
+                c[OCCGRID_C_UPDATES] += cells;
+                c[OCCGRID_C_SLOWPATH] += b[s].slow;
+                if (start_in_window(g, b[s])) c[OCCGRID_C_OWNED_UPDATES] += cells;
+                draw_beam_global(g, stamps, b[s], (unsigned int)(k * 4 + s + 1), later_writes_first);
+                later_writes_first = later_writes_first || (b[s].valid && (cells > 1 || b[s].hit));
+            }
+        }
+    }
+    block_add_counters(c, s_acc, counters);
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_update_rays_global(Geom g, const double* __restrict__ rays, const uint8_t* __restrict__ hit, long long n,
                      unsigned int* __restrict__ stamps, uint64_t* counters) {
@@ -348,6 +381,8 @@ int integrate_packets_tiled(const occgrid_geom* geom, const uint8_t* d_packets, 
                             int n_agents, int8_t* d_grid, void* d_ws, size_t ws_bytes, uint64_t* d_counters,
                             cudaStream_t st);
 bool tiled_supported(const occgrid_geom* geom);
+int integrate_poses_tiled(const occgrid_geom* geom, const void* d_poses, int64_t n, int8_t* d_grid, void* d_ws,
+                          size_t ws_bytes, uint64_t* d_counters, cudaStream_t st);
 }
 
 extern "C" {
@@ -408,6 +443,36 @@ int occgrid_integrate_packets(const occgrid_geom* geom, const uint8_t* d_packets
     }
     set_last_error("unknown strategy %d", strategy);
     return OCCGRID_E_ARG;
+}
+
+int occgrid_integrate_poses(const occgrid_geom* geom, const void* d_pose_recs, int64_t n, int8_t* d_grid,
+                            void* d_workspace, size_t workspace_bytes, uint64_t* d_counters, int strategy, void* stream) {
+    int rc = validate_geom(geom);
+    if (rc != OCCGRID_OK) return rc;
+    if (n < 0 || n > (1ll << 29) - 1) { set_last_error("n=%lld outside 0..2^29-1 records per call", (long long)n); return OCCGRID_E_ARG; }
+    if (!d_grid || !d_workspace) { set_last_error("grid/workspace is NULL"); return OCCGRID_E_ARG; }
+    if (n == 0) return OCCGRID_OK;
+    if (!d_pose_recs || (reinterpret_cast<uintptr_t>(d_pose_recs) & 15)) { set_last_error("pose records must be non-NULL and 16-byte aligned"); return OCCGRID_E_ARG; }
+    const int s = pick_strategy(geom, strategy);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s == OCCGRID_STRATEGY_TILED) {
+        if (!tiled_supported(geom)) { set_last_error("TILED strategy does not support this geometry"); return OCCGRID_E_RANGE; }
+        return integrate_poses_tiled(geom, d_pose_recs, n, d_grid, d_workspace, workspace_bytes, d_counters, st);
+    }
+    if (s != OCCGRID_STRATEGY_GLOBAL_ATOMIC) { set_last_error("unknown strategy %d", strategy); return OCCGRID_E_ARG; }
+    if (workspace_bytes < global_workspace_bytes(geom)) {
+        set_last_error("workspace %zu B < %zu B needed by GLOBAL_ATOMIC", workspace_bytes, global_workspace_bytes(geom));
+        return OCCGRID_E_WORKSPACE;
+    }
+    unsigned int* stamps = reinterpret_cast<unsigned int*>(d_workspace);
+    const long long blocks = (n + kThreads - 1) / kThreads;
+    {
+        ProfileScope ps(K_INTEGRATE_GLOBAL, st);
+        k_integrate_poses_global<<<(unsigned int)blocks, kThreads, 0, st>>>(to_geom(geom), reinterpret_cast<const PoseRec*>(d_pose_recs),
+                                                                            n, stamps, d_counters);
+    }
+    OCC_CUDA_TRY(cudaGetLastError());
+    return launch_resolve(geom, stamps, d_grid, st);
 }
 
 int occgrid_update_rays(const occgrid_geom* geom, const double* d_rays, const uint8_t* d_hit, int64_t n,

@@ -13,7 +13,9 @@
 // canonical order and no sequence numbers have to travel.
 //
 // Three kernels: per-CTA band histograms -> single-CTA scan (band-major) -> stable scatter into
-// a send buffer grouped by band.  agent_idx / drift side arrays travel with the records.
+// a send buffer grouped by band.  What travels is the DECODED record (48-byte PoseRec: pose
+// already corrected by the agent offset and the SLAM drift), so no side arrays follow it and the
+// receiver integrates with occgrid_integrate_poses.
 #include "common.cuh"
 
 namespace occ {
@@ -34,12 +36,15 @@ struct RouteParams {
 // non-finite pose, or cannot touch the grid.
 __device__ __forceinline__ unsigned int band_mask(const RouteParams& P, const uint8_t* rec, long long k,
                                                   const int32_t* agent_idx, const double* drift,
-                                                  const double* agent_off, int n_agents, int* status) {
+                                                  const double* agent_off, int n_agents, int* status, PoseRec* out) {
     double rx, ry, ryaw;
     float dist[4];
     const int st = decode_packet(rec, k, agent_idx, drift, agent_off, n_agents, &rx, &ry, &ryaw, dist);
     *status = st;
     if (st != PKT_OK) return 0u;
+    out->rx = rx; out->ry = ry; out->yaw = (float)ryaw;            // ryaw came from an fp32 field: exact
+    out->d[0] = dist[0]; out->d[1] = dist[1]; out->d[2] = dist[2]; out->d[3] = dist[3];
+    out->k = (unsigned int)k; out->pad[0] = out->pad[1] = 0;
     const double q = cell_quotient(ry, P.oy, P.res);
     if (!quotient_in_range(q)) return 0u;
     const int gy = trunc_cell(q);
@@ -73,8 +78,9 @@ k_route_count(RouteParams P, const uint8_t* __restrict__ pkts, long long n, int 
     __syncthreads();
     unsigned int m = 0;
     int st = -1;
+    PoseRec unused;
     if ((int)threadIdx.x < count)
-        m = band_mask(P, s_rec + threadIdx.x * stride, first + threadIdx.x, agent_idx, drift, agent_off, n_agents, &st);
+        m = band_mask(P, s_rec + threadIdx.x * stride, first + threadIdx.x, agent_idx, drift, agent_off, n_agents, &st, &unused);
     for (int b = 0; b < P.n_bands; ++b) {
         const unsigned int bal = __ballot_sync(0xffffffffu, (m >> b) & 1u);
         if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&s_hist[b], __popc(bal));
@@ -132,8 +138,8 @@ __global__ void __launch_bounds__(kRT)
 k_route_scatter(RouteParams P, const uint8_t* __restrict__ pkts, long long n, int stride,
                 const int32_t* __restrict__ agent_idx, const double* __restrict__ drift,
                 const double* __restrict__ agent_off, int n_agents,
-                const unsigned int* __restrict__ hist, int n_blocks, long long capacity, const int* __restrict__ status,
-                uint8_t* __restrict__ send, int32_t* __restrict__ send_agent_idx, double* __restrict__ send_drift) {
+                const unsigned int* __restrict__ hist, int n_blocks, const int* __restrict__ status,
+                PoseRec* __restrict__ send) {
     __shared__ __align__(16) uint8_t s_rec[kRT * kRouteMaxStride];
     __shared__ unsigned int s_woff[kRT / 32];
     if (*status & 1) return;                                   // send buffer too small: nothing is written
@@ -143,8 +149,9 @@ k_route_scatter(RouteParams P, const uint8_t* __restrict__ pkts, long long n, in
     __syncthreads();
     unsigned int m = 0;
     int st;
+    PoseRec rec;
     const long long k = first + threadIdx.x;
-    if ((int)threadIdx.x < count) m = band_mask(P, s_rec + threadIdx.x * stride, k, agent_idx, drift, agent_off, n_agents, &st);
+    if ((int)threadIdx.x < count) m = band_mask(P, s_rec + threadIdx.x * stride, k, agent_idx, drift, agent_off, n_agents, &st, &rec);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int b = 0; b < P.n_bands; ++b) {
         const unsigned int bit = (m >> b) & 1u;
@@ -156,11 +163,7 @@ k_route_scatter(RouteParams P, const uint8_t* __restrict__ pkts, long long n, in
         __syncthreads();
         if (bit) {
             const size_t dst = (size_t)hist[(size_t)b * n_blocks + blockIdx.x] + woff + __popc(bal & ((1u << lane) - 1u));
-            const uint8_t* src = s_rec + threadIdx.x * stride;
-            uint8_t* out = send + dst * stride;
-            for (int i = 0; i < stride; ++i) out[i] = src[i];
-            if (send_agent_idx) send_agent_idx[dst] = agent_idx[k];
-            if (send_drift) { send_drift[2 * dst] = drift[2 * k]; send_drift[2 * dst + 1] = drift[2 * k + 1]; }
+            send[dst] = rec;                                   // three 16-byte stores
         }
     }
 }
@@ -179,7 +182,7 @@ size_t occgrid_route_workspace_bytes(int64_t n, int n_bands) {
 int occgrid_route_packets(const occgrid_geom* geom, int n_bands, const int32_t* band_y0_host,
                           const uint8_t* d_packets, int64_t n, int stride, int rec_len,
                           const int32_t* d_agent_idx, const double* d_drift, const double* d_agent_off, int n_agents,
-                          uint8_t* d_send, int32_t* d_send_agent_idx, double* d_send_drift, int64_t send_capacity,
+                          void* d_send, int64_t send_capacity,
                           int64_t* d_band_counts, int32_t* d_status, uint64_t* d_counters,
                           void* d_ws, size_t ws_bytes, void* stream) {
     int rc = validate_geom(geom);
@@ -189,10 +192,7 @@ int occgrid_route_packets(const occgrid_geom* geom, int n_bands, const int32_t* 
     if (rec_len != OCCGRID_PACKET_SIZE && rec_len != OCCGRID_PACKET_SIZE_V1) { set_last_error("route: rec_len must be 42 or 41"); return OCCGRID_E_ARG; }
     if (stride < rec_len || stride > kRouteMaxStride) { set_last_error("route: bad stride %d", stride); return OCCGRID_E_ARG; }
     if (!d_send || !d_band_counts || !d_status || !d_ws || !d_agent_off || n_agents < 1) { set_last_error("route: NULL argument"); return OCCGRID_E_ARG; }
-    if ((d_agent_idx != nullptr) != (d_send_agent_idx != nullptr) || (d_drift != nullptr) != (d_send_drift != nullptr)) {
-        set_last_error("route: side arrays and their send buffers must be given together");
-        return OCCGRID_E_ARG;
-    }
+    if (reinterpret_cast<uintptr_t>(d_send) & 15) { set_last_error("route: send buffer must be 16-byte aligned"); return OCCGRID_E_ARG; }
     if (send_capacity >= (1ll << 32)) { set_last_error("route: send capacity must be < 2^32 records"); return OCCGRID_E_ARG; }
     if (ws_bytes < occgrid_route_workspace_bytes(n, n_bands)) { set_last_error("route: workspace too small"); return OCCGRID_E_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -212,7 +212,7 @@ int occgrid_route_packets(const occgrid_geom* geom, int n_bands, const int32_t* 
     k_route_count<<<blocks, kRT, 0, st>>>(P, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents, hist, blocks, d_counters);
     k_route_scan<<<1, 1024, 0, st>>>(hist, n_bands, blocks, (long long*)d_band_counts, send_capacity, d_status);
     k_route_scatter<<<blocks, kRT, 0, st>>>(P, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents, hist, blocks,
-                                            send_capacity, d_status, d_send, d_send_agent_idx, d_send_drift);
+                                            d_status, reinterpret_cast<PoseRec*>(d_send));
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
 }

@@ -36,14 +36,6 @@ constexpr int kChunkPk = 1024;       // packets per work item
 constexpr int kMaxStrideT = 64;
 constexpr int kMaxWindowBytes = 100 * 1024;   // smem window budget (two CTAs per SM at least)
 
-struct __align__(16) PoseRec {       // 48 bytes
-    double rx, ry;                   // corrected pose (:851-857)
-    float yaw;
-    float d[4];                      // front, left, back, right (:882-885)
-    unsigned int k;                  // record index in the batch = packet ordinal
-    unsigned int pad[2];
-};
-
 struct TilePlanHeader {
     unsigned int n_items, n_active, total_records, work_counter, resolve_counter, overflow, pad[2];
 };
@@ -163,6 +155,44 @@ k_home_count(Geom g, TileGeom tg, const uint8_t* __restrict__ pkts, long long n,
         if (s_keys[i] != kEmpty) atomicAdd(&tile_count[s_keys[i]], s_vals[i]);
     // the staging buffer is free now: reuse it for the counter reduction (48 KB static limit)
     block_add_counters(c, reinterpret_cast<unsigned long long*>(s_rec), counters);
+}
+
+// Same as k_home_count for input that is already decoded (routed pose records): the records
+// are binned in place.
+__global__ void __launch_bounds__(kTT)
+k_home_count_poses(Geom g, TileGeom tg, const PoseRec* __restrict__ recs, long long n,
+                   unsigned int* __restrict__ tile_count, int* __restrict__ tile_ids, uint64_t* counters) {
+    __shared__ unsigned int s_keys[kHash];
+    __shared__ unsigned int s_vals[kHash];
+    __shared__ unsigned long long s_acc[(OCCGRID_C_HITS + 1) * 32];
+    for (int i = threadIdx.x; i < kHash; i += kTT) { s_keys[i] = kEmpty; s_vals[i] = 0u; }
+    __syncthreads();
+    unsigned long long c[OCCGRID_C_HITS + 1] = {};
+    const long long cta_first = (long long)blockIdx.x * kPkPerCta;
+    for (int sub = 0; sub < kSub; ++sub) {
+        const long long k = cta_first + (long long)sub * kTT + threadIdx.x;
+        if (k >= n) break;
+        const PoseRec r = recs[k];
+        c[OCCGRID_C_PACKETS] += 1;
+        int tile = -1;
+        if (!(isfinite(r.rx) && isfinite(r.ry) && isfinite(r.yaw))) c[OCCGRID_C_BAD_POSE] += 1;
+        else {
+            c[OCCGRID_C_ACCEPTED] += 1;
+            c[OCCGRID_C_BEAMS] += 4;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const double d = (double)r.d[s];
+                c[OCCGRID_C_HITS] += (OCC_MIN_DIST_M < d && d <= OCC_MAX_DIST_M) ? 1 : 0;
+            }
+            tile = home_tile(g, tg, r.rx, r.ry);
+            if (tile >= 0) atomicAdd(&s_vals[hash_insert(s_keys, (unsigned int)tile)], 1u);
+        }
+        tile_ids[k] = tile;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHash; i += kTT)
+        if (s_keys[i] != kEmpty) atomicAdd(&tile_count[s_keys[i]], s_vals[i]);
+    block_add_counters(c, s_acc, counters);
 }
 
 __global__ void __launch_bounds__(kTT)
@@ -333,7 +363,8 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
         const int wx0 = g.win_x0 - tg.pad + (ttx << kTileShift) - tg.reach;
         const int wy0 = g.win_y0 - tg.pad + (tty << kTileShift) - tg.reach;
         for (unsigned int r = item.y + threadIdx.x; r < item.z; r += kTT) {
-            const PoseRec rec = recs[bins[r]];
+            const unsigned int k = bins[r];            // record index = packet ordinal in this batch
+            const PoseRec rec = recs[k];
             const float dist[4] = {rec.d[0], rec.d[1], rec.d[2], rec.d[3]};
             Beam b[4];
             expand_packet(g, rec.rx, rec.ry, (double)rec.yaw, dist, LibSinCos(), b);
@@ -347,7 +378,7 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
                 if (b[s].x0 >= g.win_x0 && b[s].x0 < g.win_x0 + g.win_w && b[s].y0 >= g.win_y0 && b[s].y0 < g.win_y0 + g.win_h)
                     c[2] += cells;
                 draw_beam_smem(s_win, side, pitch, b[s].x0 - wx0, b[s].y0 - wy0, b[s].x1 - b[s].x0, b[s].y1 - b[s].y0,
-                               (rec.k * 4u + (unsigned int)s + 1u) << 1, b[s].hit != 0, later_writes_first);
+                               (k * 4u + (unsigned int)s + 1u) << 1, b[s].hit != 0, later_writes_first);
                 later_writes_first = later_writes_first || (cells > 1 || b[s].hit);
             }
         }
@@ -459,10 +490,11 @@ size_t tiled_workspace_bytes(const occgrid_geom* geom, int64_t max_packets) {
     return tiled_layout(geom, max_packets < 1 ? 1 : max_packets).total;
 }
 
-int integrate_packets_tiled(const occgrid_geom* geom, const uint8_t* d_packets, int64_t n, int stride,
-                            const int32_t* d_agent_idx, const double* d_drift, const double* d_agent_off,
-                            int n_agents, int8_t* d_grid, void* d_ws, size_t ws_bytes, uint64_t* d_counters,
-                            cudaStream_t st) {
+// `d_poses` != NULL: input is n PoseRec (already decoded and corrected), `d_packets` etc. unused.
+int integrate_tiled(const occgrid_geom* geom, const uint8_t* d_packets, const PoseRec* d_poses, int64_t n, int stride,
+                    const int32_t* d_agent_idx, const double* d_drift, const double* d_agent_off,
+                    int n_agents, int8_t* d_grid, void* d_ws, size_t ws_bytes, uint64_t* d_counters,
+                    cudaStream_t st) {
     const TiledLayout L = tiled_layout(geom, n);
     if (ws_bytes < L.total) {
         set_last_error("workspace %zu B < %zu B needed by TILED for %lld records", ws_bytes, L.total, (long long)n);
@@ -477,7 +509,7 @@ int integrate_packets_tiled(const occgrid_geom* geom, const uint8_t* d_packets, 
     TilePlanHeader* hdr = reinterpret_cast<TilePlanHeader*>(ws + L.off_hdr);
     uint4* items = reinterpret_cast<uint4*>(ws + L.off_items);
     unsigned int* bins = reinterpret_cast<unsigned int*>(ws + L.off_bins);
-    PoseRec* recs = reinterpret_cast<PoseRec*>(ws + L.off_recs);
+    const PoseRec* recs = d_poses ? d_poses : reinterpret_cast<const PoseRec*>(ws + L.off_recs);
     int* tile_ids = reinterpret_cast<int*>(ws + L.off_ids);
     const Geom g = to_geom(geom);
     const TileGeom tg = tile_geom(geom);
@@ -498,8 +530,11 @@ int integrate_packets_tiled(const occgrid_geom* geom, const uint8_t* d_packets, 
         ctas_per_sm = 1;
     {
         ProfileScope ps(K_TILE_COUNT, st);
-        k_home_count<<<blocks, kTT, 0, st>>>(g, tg, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents,
-                                            tile_count, tile_ids, recs, d_counters);
+        if (d_poses)
+            k_home_count_poses<<<blocks, kTT, 0, st>>>(g, tg, d_poses, n, tile_count, tile_ids, d_counters);
+        else
+            k_home_count<<<blocks, kTT, 0, st>>>(g, tg, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents,
+                                                tile_count, tile_ids, reinterpret_cast<PoseRec*>(ws + L.off_recs), d_counters);
     }
     {
         ProfileScope ps(K_TILE_SCAN, st);
@@ -520,6 +555,20 @@ int integrate_packets_tiled(const occgrid_geom* geom, const uint8_t* d_packets, 
     }
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
+}
+
+int integrate_packets_tiled(const occgrid_geom* geom, const uint8_t* d_packets, int64_t n, int stride,
+                            const int32_t* d_agent_idx, const double* d_drift, const double* d_agent_off,
+                            int n_agents, int8_t* d_grid, void* d_ws, size_t ws_bytes, uint64_t* d_counters,
+                            cudaStream_t st) {
+    return integrate_tiled(geom, d_packets, nullptr, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents, d_grid, d_ws,
+                           ws_bytes, d_counters, st);
+}
+
+int integrate_poses_tiled(const occgrid_geom* geom, const void* d_poses, int64_t n, int8_t* d_grid, void* d_ws,
+                          size_t ws_bytes, uint64_t* d_counters, cudaStream_t st) {
+    return integrate_tiled(geom, nullptr, reinterpret_cast<const PoseRec*>(d_poses), n, 0, nullptr, nullptr, nullptr, 0,
+                           d_grid, d_ws, ws_bytes, d_counters, st);
 }
 
 }  // namespace occ

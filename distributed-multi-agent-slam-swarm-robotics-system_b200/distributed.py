@@ -5,9 +5,9 @@ rank.  Cells are independent given a global beam order and a ray is at most
 MAX_DIST_M / res cells long (server_nodes/dual_bot_mapper.py:57), so the only exchange step is
 routing records to the band(s) their rays can reach:
 
-    local share --occgrid_route_packets--> send buffer grouped by band
+    local share --occgrid_route_packets--> decoded 48-byte records grouped by band
                 --all_to_all_single (NCCL over NVLink)--> records for my band, canonical order
-                --occgrid_integrate_packets(window = my band)--> my rows of the map
+                --occgrid_integrate_poses(window = my band)--> my rows of the map
 
 There is no collective on the grid itself: bands are disjoint.  The canonical stream order is
 "rank 0's share, then rank 1's, ..."; routing is stable and all-to-all concatenates by source
@@ -63,50 +63,40 @@ class CudaBandOps:
         self._counts = torch.zeros(layout.n_bands, dtype=torch.int64, device=self.device)
         self._ws = None
         self._send = None
-        self._send_idx = None
-        self._send_drift = None
 
     def stage(self, packets):
         return self.grid.stage_packets(packets)[0]
 
     def route(self, packets, agent_idx, drift, agent_table):
-        """-> (send [m, stride] grouped by band, send_agent_idx, send_drift, counts list)"""
+        """-> (rows uint8 [m, 48] of decoded records grouped by destination band, counts list)"""
         n, stride = packets.shape
         nb = self.layout.n_bands
         cap = 2 * n + 1024
         need = self._lib.occgrid_route_workspace_bytes(n, nb)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        if self._send is None or self._send.shape[0] < cap or self._send.shape[1] != stride:
-            self._send = torch.empty((cap, stride), dtype=torch.uint8, device=self.device)
-        if agent_idx is not None and (self._send_idx is None or self._send_idx.shape[0] < cap):
-            self._send_idx = torch.empty(cap, dtype=torch.int32, device=self.device)
-        if drift is not None and (self._send_drift is None or self._send_drift.shape[0] < cap):
-            self._send_drift = torch.empty((cap, 2), dtype=torch.float64, device=self.device)
-        s_idx = self._send_idx if agent_idx is not None else None
-        s_drift = self._send_drift if drift is not None else None
+        if self._send is None or self._send.shape[0] < cap:
+            self._send = torch.empty((cap, 48), dtype=torch.uint8, device=self.device)
         rc = self._lib.occgrid_route_packets(
             self._geom, nb, self._band_y0.ctypes.data, packets.data_ptr(), n, stride, 42 if stride >= 42 else 41,
             agent_idx.data_ptr() if agent_idx is not None else None, drift.data_ptr() if drift is not None else None,
-            agent_table.data_ptr(), agent_table.shape[0] - 1, self._send.data_ptr(),
-            s_idx.data_ptr() if s_idx is not None else None, s_drift.data_ptr() if s_drift is not None else None,
-            cap, self._counts.data_ptr(), self._status.data_ptr(), self.grid._counters.data_ptr(),
+            agent_table.data_ptr(), agent_table.shape[0] - 1, self._send.data_ptr(), cap,
+            self._counts.data_ptr(), self._status.data_ptr(), None,
             self._ws.data_ptr(), self._ws.numel(), torch.cuda.current_stream(self.device).cuda_stream)
         _native.check(rc, 'occgrid_route_packets')
-        counts = self._counts.cpu().tolist()                 # the only host sync of a step
-        if int(self._status.item()) & 1:
+        host = torch.cat([self._counts, self._status.to(torch.int64)]).cpu().tolist()   # the only host sync of a step
+        counts, status = host[:nb], host[nb]
+        if status & 1:
             self._status.zero_()
             raise OccGridError('route: send buffer overflow')
-        m = int(sum(counts))
-        return (self._send[:m], s_idx[:m] if s_idx is not None else None,
-                s_drift[:m] if s_drift is not None else None, counts)
+        return self._send[:int(sum(counts))], counts
 
     def empty(self, rows, stride, dtype):
         shape = (rows, stride) if stride else (rows,)
         return torch.empty(shape, dtype=dtype, device=self.device)
 
-    def integrate(self, packets, agent_idx, drift, agent_table):
-        self.grid.update_packets(packets, agent_offsets=agent_table, agent_idx=agent_idx, drift=drift)
+    def integrate(self, rows):
+        self.grid.update_poses(rows)
 
     def band_tensor(self):
         return self.grid.grid_tensor
@@ -165,16 +155,14 @@ class TiledSwarmMap:
         dev = pk.device
         idx = torch.as_tensor(agent_idx, dtype=torch.int32).to(dev).contiguous() if agent_idx is not None else None
         dr = torch.as_tensor(drift, dtype=torch.float64).reshape(-1, 2).to(dev).contiguous() if drift is not None else None
-        send, s_idx, s_dr, counts = self.ops.route(pk, idx, dr, tab)
+        send, counts = self.ops.route(pk, idx, dr, tab)
         if self.world > 1:
             c_in = torch.tensor(counts, dtype=torch.int64, device=dev)
             c_out = torch.empty_like(c_in)
             dist.all_to_all_single(c_out, c_in, group=self.group)
             self._recv_counts = c_out.cpu().tolist()
         recv = self._exchange(send, counts, send.shape[1], torch.uint8)
-        r_idx = self._exchange(s_idx, counts, 0, torch.int32) if s_idx is not None else None
-        r_dr = self._exchange(s_dr, counts, 2, torch.float64) if s_dr is not None else None
-        self.ops.integrate(recv, r_idx, r_dr, tab)
+        self.ops.integrate(recv)
         return int(recv.shape[0])
 
     def gather_grid(self):

@@ -69,6 +69,15 @@ typedef struct occgrid_geom {
     int32_t win_w, win_h;    /* window extent in cells                                   */
 } occgrid_geom;
 
+/* A decoded, pose-corrected packet: 48 bytes, 16-byte aligned. */
+typedef struct occgrid_pose_rec {
+    double   rx, ry;      /* pose after `+ agent offset` (:851-852) and `+ drift` (:855-857) */
+    float    yaw;         /* wire field, unchanged                                            */
+    float    d[4];        /* front, left, back, right ranges in metres (:882-885)            */
+    uint32_t k;           /* index of the source record in its batch (informational)         */
+    uint32_t pad[2];
+} occgrid_pose_rec;
+
 /* Counter slots (uint64 each, device memory, accumulated with atomics; caller zeroes). */
 enum {
     OCCGRID_C_PACKETS = 0,   /* records seen                                              */
@@ -148,21 +157,28 @@ int occgrid_scatter_probe(int kind, void* d_plane, int64_t plane_cells, int64_t 
 /*
  * Multi-GPU routing: the global grid is cut into `n_bands` row bands
  * (band b = rows [band_y0[b], band_y0[b+1]), host array of n_bands+1 boundaries).  Every
- * accepted record is copied, in stable order, to the segment of `d_send` of each band its rays
- * can reach (robot row +- ceil(MAX_DIST_M/res)+2 cells); d_band_counts[b] receives the segment
- * lengths (segments are laid out in band order).  Optional side arrays (agent_idx, drift)
- * travel with the records.  d_status bit 0 = send buffer too small (nothing written).
- * The caller then exchanges the segments (NCCL all-to-all) and feeds what it receives to
- * occgrid_integrate_packets with its own window.
+ * accepted record is decoded (:828-857) and written as an occgrid_pose_rec, in stable order, to
+ * the segment of `d_send` of each band its rays can reach (robot row +- ceil(MAX_DIST_M/res)+2
+ * cells); d_band_counts[b] receives the segment lengths (segments are laid out in band order).
+ * d_status bit 0 = send buffer too small (nothing written).  The caller then exchanges the
+ * segments (NCCL all-to-all) and feeds what it receives to occgrid_integrate_poses with its own
+ * window.
  */
 size_t occgrid_route_workspace_bytes(int64_t n, int n_bands);
 int occgrid_route_packets(const occgrid_geom* geom, int n_bands, const int32_t* band_y0_host,
                           const uint8_t* d_packets, int64_t n, int stride, int rec_len,
                           const int32_t* d_agent_idx, const double* d_drift,
                           const double* d_agent_off, int n_agents,
-                          uint8_t* d_send, int32_t* d_send_agent_idx, double* d_send_drift,
+                          void* d_send /* occgrid_pose_rec[send_capacity] */,
                           int64_t send_capacity, int64_t* d_band_counts, int32_t* d_status,
                           uint64_t* d_counters, void* d_ws, size_t ws_bytes, void* stream);
+
+/* Integrate n decoded records (occgrid_pose_rec, 16-byte aligned) in index order: the second half
+ * of occgrid_integrate_packets (beam expansion :881-903 + update_ray :136-156) for input whose
+ * decode/filter/pose correction (:826-857) already happened — on another GPU, in the router. */
+int occgrid_integrate_poses(const occgrid_geom* geom, const void* d_pose_recs, int64_t n,
+                            int8_t* d_grid, void* d_workspace, size_t workspace_bytes,
+                            uint64_t* d_counters, int strategy, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  *  Map fusion — server_nodes/map_merger.py:35-127

@@ -56,22 +56,27 @@ class OracleBandOps:
             segs.append(np.nonzero(sel)[0])
             counts.append(int(sel.sum()))
         order = np.concatenate(segs) if segs else np.zeros(0, np.int64)
-        send = torch.from_numpy(pk[order])
-        s_idx = agent_idx[torch.from_numpy(order)] if agent_idx is not None else None
-        s_dr = drift[torch.from_numpy(order)] if drift is not None else None
-        return send, s_idx, s_dr, counts
+        # opaque 64-byte rows: packet (42) | agent index (4) | drift (16) | pad
+        rows = np.zeros((order.shape[0], 64), np.uint8)
+        rows[:, :42] = pk[order][:, :42]
+        rows[:, 42:46] = ids[order].astype('<i4').view(np.uint8).reshape(-1, 4)
+        d = drift.numpy()[order] if drift is not None else np.zeros((order.shape[0], 2))
+        rows[:, 46:62] = np.ascontiguousarray(d, '<f8').view(np.uint8).reshape(-1, 16)
+        self._tab = tab
+        return torch.from_numpy(rows), counts
 
     def empty(self, rows, stride, dtype):
         return torch.empty((rows, stride) if stride else (rows,), dtype=dtype)
 
-    def integrate(self, packets, agent_idx, drift, agent_table):
+    def integrate(self, rows):
         from oracle import c_oracle
-        if packets.shape[0] == 0:
+        r = rows.numpy()
+        if r.shape[0] == 0:
             return
-        c_oracle.integrate_packets(packets.numpy(), self.band, self.ox, self.oy, self.res,
-                                   agent_offsets=agent_table.numpy(),
-                                   agent_idx=agent_idx.numpy() if agent_idx is not None else None,
-                                   drift=drift.numpy() if drift is not None else None,
+        ids = np.ascontiguousarray(r[:, 42:46]).view('<i4')[:, 0]
+        d = np.ascontiguousarray(r[:, 46:62]).view('<f8').reshape(-1, 2)
+        c_oracle.integrate_packets(np.ascontiguousarray(r[:, :42]), self.band, self.ox, self.oy, self.res,
+                                   agent_offsets=self._tab, agent_idx=ids, drift=d,
                                    window=self.win, size_x=self.size, size_y=self.size)
 
     def band_tensor(self):

@@ -38,18 +38,15 @@ def test_emulated_ranks_equal_single_grid(world, strategy):
         pk = ops[r].stage(sess['packets'][sl])
         idx = torch.from_numpy(sess['agent_idx'][sl].copy()).cuda()
         dr = torch.from_numpy(drift[sl].copy()).cuda()
-        send, s_idx, s_dr, counts = ops[r].route(pk, idx, dr, tab)
+        send, counts = ops[r].route(pk, idx, dr, tab)
         offs_c = np.concatenate([[0], np.cumsum(counts)])
-        routed.append([(send[offs_c[b]:offs_c[b + 1]].clone(), s_idx[offs_c[b]:offs_c[b + 1]].clone(),
-                        s_dr[offs_c[b]:offs_c[b + 1]].clone()) for b in range(world)])
+        routed.append([send[offs_c[b]:offs_c[b + 1]].clone() for b in range(world)])
     total_rows = 0
     bands = []
     for b in range(world):
-        recv = torch.cat([routed[r][b][0] for r in range(world)])
-        r_idx = torch.cat([routed[r][b][1] for r in range(world)])
-        r_dr = torch.cat([routed[r][b][2] for r in range(world)])
+        recv = torch.cat([routed[r][b] for r in range(world)])
         total_rows += recv.shape[0]
-        ops[b].integrate(recv, r_idx, r_dr, tab)
+        ops[b].integrate(recv)
         bands.append(ops[b].band_tensor().cpu().numpy())
     got = np.concatenate(bands, axis=0)
     want = np.full((size, size), -1, np.int8)

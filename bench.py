@@ -271,6 +271,8 @@ def main():
             torch.cuda.synchronize()
             if rank == 0:
                 print(f'trace step {i}: {(time.perf_counter() - t0) * 1e3:.3f} ms', file=sys.stderr, flush=True)
+    if n > 1:
+        tmap.flush()
     torch.cuda.synchronize()
     grid._counters.zero_()
     if world > 1:
@@ -289,6 +291,8 @@ def main():
     ev0.record()
     for i in range(K):
         step(W + i)
+    if n > 1:
+        tmap.flush()            # pipeline mode: the last batch is integrated inside the timed region
     ev1.record()
     torch.cuda.synchronize()
     t_wall1 = time.time()
@@ -311,9 +315,14 @@ def main():
     # per-kernel device time (library hook: CUDA events around each launch, on its stream), from
     # a short extra loop outside the timed region; the dominant kernel feeds `roofline`
     P = 5
+    if n > 1:
+        tmap.flush()
+    torch.cuda.synchronize()
     _native.profile_begin()
     for i in range(P):
         step(i)
+    if n > 1:
+        tmap.flush()
     torch.cuda.synchronize()
     prof = _native.profile_end()
     kernels = {k: {'ms_per_launch': v[0] / v[1], 'launches_per_step': v[1] / P} for k, v in prof.items()}

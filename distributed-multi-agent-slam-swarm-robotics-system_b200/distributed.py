@@ -107,7 +107,7 @@ class TiledSwarmMap:
     ``OccupancyGrid``'s batched entry; each rank passes ITS share of the packet stream."""
 
     def __init__(self, size, resolution=0.05, origin_x=-5.0, origin_y=-5.0, *, group=None, device=None,
-                 strategy='auto', max_batch=1 << 16, ops=None):
+                 strategy='auto', max_batch=1 << 16, ops=None, pipeline=False):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -121,6 +121,11 @@ class TiledSwarmMap:
         self.ops = ops
         self.local = getattr(ops, 'grid', None)
         self._recv_bufs = {}
+        self.pipeline = bool(pipeline) and hasattr(ops, 'grid')
+        self._pending = None
+        self._step = 0
+        self._slot_free = [None, None]
+        self._side = torch.cuda.Stream(device=ops.device) if self.pipeline else None
 
     def _agent_table(self, separation, agent_offsets):
         if isinstance(agent_offsets, torch.Tensor):
@@ -131,14 +136,14 @@ class TiledSwarmMap:
             t = torch.from_numpy(np.ascontiguousarray(agent_offsets, np.float64).reshape(-1, 2))
         return t.to(self.ops.device)
 
-    def _exchange(self, send, counts, stride, dtype):
+    def _exchange(self, send, counts, stride, dtype, slot=0):
         """all_to_all_single of row-segments; returns the rows received (concatenated by source
         rank, i.e. in canonical stream order)."""
         if self.world == 1:
             return send
         recv_counts = self._recv_counts
         rows = int(sum(recv_counts))
-        key = (stride, dtype)
+        key = (stride, dtype, slot)
         buf = self._recv_bufs.get(key)
         if buf is None or buf.shape[0] < rows:          # grown geometrically, then reused every step
             buf = self.ops.empty(int(rows * 1.25) + 1024, stride, dtype)
@@ -148,8 +153,7 @@ class TiledSwarmMap:
                                group=self.group)
         return out
 
-    def update_packets(self, packets, separation=0.0, drift=None, agent_offsets=None, agent_idx=None):
-        """Integrate this rank's share of the stream into the tiled map (all ranks must call)."""
+    def _route_and_exchange(self, packets, separation, drift, agent_offsets, agent_idx, slot):
         tab = self._agent_table(separation, agent_offsets)
         pk = self.ops.stage(packets)
         dev = pk.device
@@ -161,12 +165,50 @@ class TiledSwarmMap:
             c_out = torch.empty_like(c_in)
             dist.all_to_all_single(c_out, c_in, group=self.group)
             self._recv_counts = c_out.cpu().tolist()
-        recv = self._exchange(send, counts, send.shape[1], torch.uint8)
-        self.ops.integrate(recv)
+        return self._exchange(send, counts, send.shape[1], torch.uint8, slot)
+
+    def update_packets(self, packets, separation=0.0, drift=None, agent_offsets=None, agent_idx=None):
+        """Integrate this rank's share of the stream into the tiled map (all ranks must call).
+
+        With ``pipeline=True`` the call routes and exchanges THIS batch on a side stream while
+        the PREVIOUS batch is being integrated (NVLink traffic hidden behind SM work); the map is
+        complete after ``flush()`` (``gather_grid``/``counters`` flush first).  Batch order, and
+        with it last-writer-wins, is unchanged."""
+        if not self.pipeline:
+            recv = self._route_and_exchange(packets, separation, drift, agent_offsets, agent_idx, 0)
+            self.ops.integrate(recv)
+            return int(recv.shape[0])
+        main = torch.cuda.current_stream(self.ops.device)
+        slot = self._step & 1
+        self._step += 1
+        with torch.cuda.stream(self._side):
+            if self._slot_free[slot] is not None:
+                self._side.wait_event(self._slot_free[slot])      # integrate that last read this buffer
+            recv = self._route_and_exchange(packets, separation, drift, agent_offsets, agent_idx, slot)
+            ready = torch.cuda.Event()
+            ready.record(self._side)
+        prev, self._pending = self._pending, (recv, ready, slot)
+        if prev is not None:
+            self._integrate_pending(prev, main)
         return int(recv.shape[0])
+
+    def _integrate_pending(self, pending, main):
+        recv, ready, slot = pending
+        main.wait_event(ready)
+        self.ops.integrate(recv)
+        done = torch.cuda.Event()
+        done.record(main)
+        self._slot_free[slot] = done
+
+    def flush(self):
+        """Integrate the batch still in flight (pipeline mode)."""
+        if self.pipeline and self._pending is not None:
+            pending, self._pending = self._pending, None
+            self._integrate_pending(pending, torch.cuda.current_stream(self.ops.device))
 
     def gather_grid(self):
         """Assemble the global map on every rank (all_gather of the disjoint bands)."""
+        self.flush()
         band = self.ops.band_tensor()
         if self.world == 1:
             return band.cpu().numpy()
@@ -260,14 +302,14 @@ class ShardedMapMerger:
 #  bench.py helper: weak-scaling sessions
 # ----------------------------------------------------------------------------------------------
 
-def make_rank_sessions(world, rank, device, packets_per_rank, pool, strategy):
+def make_rank_sessions(world, rank, device, packets_per_rank, pool, strategy, pipeline=True):
     """Weak scaling of BASELINE configs[1]: (4096*world)^2 map, 64*world agents, each rank ingests
     its own `packets_per_rank` share.  Returns (TiledSwarmMap, sessions, step_fn)."""
     from . import simulation_tools as st
     side = 4096 * world
     origin = (-side * 0.05 / 2.0,) * 2
     tmap = TiledSwarmMap(side, 0.05, origin[0], origin[1], device=device, strategy=strategy,
-                         max_batch=int(packets_per_rank * 1.25))
+                         max_batch=int(packets_per_rank * 1.25), pipeline=pipeline)
     sessions = []
     for i in range(pool):
         # this rank's share of the stream: all 64*world agents, `packets_per_rank` records

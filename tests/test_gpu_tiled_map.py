@@ -56,3 +56,26 @@ def test_emulated_ranks_equal_single_grid(world, strategy):
     assert n < total_rows < 1.5 * n                      # boundary rooms are duplicated, the rest is not
     owned = sum(ops[b].grid.counters()['owned_updates'] for b in range(world))
     assert owned == c['updates']                         # every beam counted exactly once across bands
+
+
+def test_pipelined_swarm_map_single_rank():
+    """pipeline=True (route/exchange of batch i+1 on a side stream while batch i integrates):
+    same map as the oracle after flush(); exercised here with world = 1."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from occgrid_b200 import simulation_tools as st
+    from occgrid_b200.distributed import TiledSwarmMap
+    from oracle import c_oracle
+    size, origin = 1024, (-25.6, -25.6)
+    sess = st.generate_session(n_agents=16, n_packets=90_000, grid_size=size, origin=origin, seed=21)
+    tmap = TiledSwarmMap(size, 0.05, origin[0], origin[1], max_batch=30_000, pipeline=True)
+    assert tmap.pipeline
+    for i in range(3):
+        sl = slice(i * 30_000, (i + 1) * 30_000)
+        tmap.update_packets(sess['packets'][sl], agent_offsets=sess['agent_offsets'], agent_idx=sess['agent_idx'][sl])
+    got = tmap.gather_grid()            # flushes
+    want = np.full((size, size), -1, np.int8)
+    c = c_oracle.integrate_packets(sess['packets'], want, origin[0], origin[1], 0.05, agent_offsets=sess['agent_offsets'],
+                                   agent_idx=sess['agent_idx'])
+    assert np.array_equal(got, want)
+    assert tmap.local.counters()['owned_updates'] == c['updates']

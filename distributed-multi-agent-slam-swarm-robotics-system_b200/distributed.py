@@ -139,9 +139,9 @@ class TiledSwarmMap:
     def _exchange(self, send, counts, stride, dtype, slot=0):
         """all_to_all_single of row-segments; returns the rows received (concatenated by source
         rank, i.e. in canonical stream order)."""
-        if self.world == 1:
+        if self.world == 1 and not self.pipeline:
             return send
-        recv_counts = self._recv_counts
+        recv_counts = self._recv_counts if self.world > 1 else [int(send.shape[0])]
         rows = int(sum(recv_counts))
         key = (stride, dtype, slot)
         buf = self._recv_bufs.get(key)
@@ -149,6 +149,9 @@ class TiledSwarmMap:
             buf = self.ops.empty(int(rows * 1.25) + 1024, stride, dtype)
             self._recv_bufs[key] = buf
         out = buf[:rows]
+        if self.world == 1:              # pipelined single rank: the send buffer is reused by the next route
+            out.copy_(send)
+            return out
         dist.all_to_all_single(out, send.contiguous(), output_split_sizes=recv_counts, input_split_sizes=counts,
                                group=self.group)
         return out

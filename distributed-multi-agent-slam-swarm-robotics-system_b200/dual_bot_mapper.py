@@ -114,6 +114,7 @@ class OccupancyGrid:
         self._ws_capacity = 0
         self._host_cache = None
         self._pinned = None
+        self._copy_stream = None
         self._ensure_workspace(int(max_batch))
 
     # ---- workspace -----------------------------------------------------------------------
@@ -260,8 +261,73 @@ class OccupancyGrid:
         agent_offsets  EXTENSION: float64 [A+1, 2] start offsets; ids 1..A accepted
         agent_idx      EXTENSION: int32 [n] agent index replacing the uint8 wire id
         """
+        host = self._as_host_records(packets)
+        if host is not None and host[0].shape[0] >= 2 * self.h2d_chunk:
+            return self._update_packets_streamed(host[0], host[1], separation, drift, agent_offsets, agent_idx, rec_len)
         with torch.cuda.device(self.device):
             pk, kept = self.stage_packets(packets)
+            self._integrate_device(pk, kept, separation, drift, agent_offsets, agent_idx, rec_len)
+
+    h2d_chunk = 1 << 19          # records per H2D chunk of the streamed path (22 MB)
+
+    def _as_host_records(self, packets):
+        """(uint8 host tensor [n, stride], kept) when `packets` lives in host memory, else None."""
+        kept = None
+        if isinstance(packets, (list, tuple)):
+            packets, kept = normalise_datagrams(packets)
+        if isinstance(packets, (bytes, bytearray, memoryview)):
+            packets = np.frombuffer(packets, np.uint8)
+        if isinstance(packets, np.ndarray):
+            packets = torch.from_numpy(np.ascontiguousarray(packets, np.uint8))
+        if not isinstance(packets, torch.Tensor) or packets.dtype != torch.uint8 or packets.device.type != 'cpu':
+            return None
+        if packets.dim() == 1:
+            if packets.numel() % PACKET_SIZE:
+                raise ValueError('flat packet buffer length is not a multiple of 42')
+            packets = packets.reshape(-1, PACKET_SIZE)
+        return packets.contiguous(), kept
+
+    def _update_packets_streamed(self, host, kept, separation, drift, agent_offsets, agent_idx, rec_len):
+        """Large host batch: copy chunk c+1 over PCIe on a side stream while chunk c integrates.
+        Chunks are applied in order, each resolving into the grid, so later records still win."""
+        n, stride = host.shape
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+                self._h2d = [torch.empty((self.h2d_chunk, 64), dtype=torch.uint8, device=self.device) for _ in range(2)]
+                self._h2d_free = [None, None]
+            if not host.is_pinned():
+                if self._pinned is None or self._pinned.numel() < host.numel():
+                    self._pinned = torch.empty(max(host.numel(), 1 << 16), dtype=torch.uint8).pin_memory()
+            d_all = torch.as_tensor(drift, dtype=torch.float64).reshape(-1, 2) if drift is not None else None
+            if d_all is not None and kept is not None and d_all.shape[0] != n:
+                d_all = d_all[torch.from_numpy(kept)]
+            a_all = torch.as_tensor(agent_idx, dtype=torch.int32).reshape(-1) if agent_idx is not None else None
+            for c, lo in enumerate(range(0, n, self.h2d_chunk)):
+                hi = min(n, lo + self.h2d_chunk)
+                slot = c & 1
+                src = host[lo:hi]
+                if not src.is_pinned():
+                    stage = self._pinned[lo * stride:hi * stride].view(hi - lo, stride)
+                    stage.copy_(src)
+                    src = stage
+                dst = self._h2d[slot].view(-1)[:(hi - lo) * stride].view(hi - lo, stride)
+                with torch.cuda.stream(self._copy_stream):
+                    if self._h2d_free[slot] is not None:
+                        self._copy_stream.wait_event(self._h2d_free[slot])
+                    dst.copy_(src, non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(self._copy_stream)
+                main.wait_event(ready)
+                self._integrate_device(dst, None, separation, None if d_all is None else d_all[lo:hi], agent_offsets,
+                                       None if a_all is None else a_all[lo:hi], rec_len)
+                done = torch.cuda.Event()
+                done.record(main)
+                self._h2d_free[slot] = done
+
+    def _integrate_device(self, pk, kept, separation, drift, agent_offsets, agent_idx, rec_len):
+        with torch.cuda.device(self.device):
             n, stride = pk.shape
             if n == 0:
                 return

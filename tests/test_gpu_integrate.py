@@ -202,6 +202,28 @@ def test_batches_later_wins(M, strategy):
     assert np.array_equal(g.grid, want)
 
 
+@pytest.mark.parametrize('pinned', [False, True])
+def test_streamed_host_batch(M, pinned):
+    """Large host buffers are copied chunk by chunk on a side stream while earlier chunks
+    integrate; result and order semantics must not change (drift and agent_idx are sliced too)."""
+    from oracle import c_oracle
+    s = synthetic(70_000, seed=13)
+    drift = np.random.default_rng(2).normal(0, 0.03, (70_000, 2))
+    g = supported(M, 'auto', max_batch=8_000, **s['grid'])
+    g.h2d_chunk = 8_000                      # 9 chunks through 2 device slots
+    pk = torch.from_numpy(s['packets'])
+    if pinned:
+        pk = pk.pin_memory()
+    g.update_packets(pk, agent_offsets=s['agent_offsets'], agent_idx=s['agent_idx'], drift=drift)
+    g.update_packets(s['packets'][:20_000], agent_offsets=s['agent_offsets'], agent_idx=s['agent_idx'][:20_000])
+    want = np.full((4096, 4096), -1, np.int8)
+    c_oracle.integrate_packets(s['packets'], want, -102.4, -102.4, 0.05, agent_offsets=s['agent_offsets'],
+                               agent_idx=s['agent_idx'], drift=drift)
+    c_oracle.integrate_packets(s['packets'][:20_000], want, -102.4, -102.4, 0.05, agent_offsets=s['agent_offsets'],
+                               agent_idx=s['agent_idx'][:20_000])
+    assert np.array_equal(g.grid, want)
+
+
 @pytest.mark.parametrize('strategy', STRATEGIES)
 def test_window_tiles_equal_crop(M, strategy):
     """Spatial tiles (multi-GPU layout run on one GPU): integrating the same stream into

@@ -115,6 +115,7 @@ class OccupancyGrid:
         self._host_cache = None
         self._pinned = None
         self._copy_stream = None
+        self._tab_cache = None
         self._ensure_workspace(int(max_batch))
 
     # ---- workspace -----------------------------------------------------------------------
@@ -219,7 +220,12 @@ class OccupancyGrid:
             return agent_offsets.to(self.device, dtype=torch.float64).reshape(-1, 2).contiguous()
         else:
             tab = np.ascontiguousarray(agent_offsets, np.float64).reshape(-1, 2)
-        return torch.from_numpy(tab).to(self.device)
+        cached = self._tab_cache
+        if cached is not None and cached[0].shape == tab.shape and np.array_equal(cached[0], tab):
+            return cached[1]                    # same table as last call: reuse the device copy
+        dev_tab = torch.from_numpy(tab).to(self.device)
+        self._tab_cache = (tab.copy(), dev_tab)
+        return dev_tab
 
     def stage_packets(self, packets):
         """Host -> device staging of a record buffer.  Accepts bytes/bytearray/memoryview,
@@ -268,7 +274,7 @@ class OccupancyGrid:
             pk, kept = self.stage_packets(packets)
             self._integrate_device(pk, kept, separation, drift, agent_offsets, agent_idx, rec_len)
 
-    h2d_chunk = 1 << 19          # records per H2D chunk of the streamed path (22 MB)
+    h2d_chunk = 1 << 20          # records per H2D chunk of the streamed path (44 MB)
 
     def _as_host_records(self, packets):
         """(uint8 host tensor [n, stride], kept) when `packets` lives in host memory, else None."""

@@ -309,22 +309,36 @@ __device__ __forceinline__ void draw_beam_smem(unsigned int* __restrict__ s_win,
     const int n = max(dx, dy);
     const unsigned int us = (unsigned int)side;
     if ((unsigned int)x < us && (unsigned int)y < us && (unsigned int)(x + ddx) < us && (unsigned int)(y + ddy) < us) {
+        // Major/minor form of the same recurrence.  With err = dx - dy the reference steps the
+        // major axis on EVERY iteration (for dx > dy: 2*err > -dy always holds; for dy > dx:
+        // 2*err < dx always holds; both step when dx == dy), and the minor axis steps iff
+        //   x-major: 2*err < dx        y-major: 2*err > -dy  <=>  2*(-err) < dy
+        // i.e. with E = |err-form| = dmaj - dmin initially:  minor iff 2*E < dmaj (strict, like
+        // the reference), then E += (minor ? dmaj : 0) - dmin.  Branch-free across octants, so
+        // lanes walking different octants do not diverge.  (Exhaustive KAT on device:
+        // tests/test_gpu_integrate.py::test_bresenham_exhaustive_on_device.)
         const int sxo = ddx > 0 ? 1 : -1;
         const int syo = ddy > 0 ? pitch : -pitch;
+        const bool xmajor = dx >= dy;
+        const int dmaj = xmajor ? dx : dy, dmin = xmajor ? dy : dx;
+        const int step_maj = xmajor ? sxo : syo;
+        const int step_both = sxo + syo;
+        const int e_minor = dmaj - dmin;         // E change when the minor axis steps too
+        int E = dmaj - dmin;
         int off = y * pitch + x;
         int i = 0;
         if (skip_first) {                     // the start cell is overwritten by a later beam of the packet
             if (n == 0) return;
-            const int e2 = 2 * err;
-            if (e2 > -dy) { err -= dy; off += sxo; }
-            if (e2 < dx)  { err += dx; off += syo; }
+            const bool minor = 2 * E < dmaj;
+            off += minor ? step_both : step_maj;
+            E += minor ? e_minor : -dmin;
             i = 1;
         }
         for (; i < n; ++i) {
             atomicMax(&s_win[off], free_stamp);
-            const int e2 = 2 * err;
-            if (e2 > -dy) { err -= dy; off += sxo; }
-            if (e2 < dx)  { err += dx; off += syo; }
+            const bool minor = 2 * E < dmaj;
+            off += minor ? step_both : step_maj;
+            E += minor ? e_minor : -dmin;
         }
         if (hit) atomicMax(&s_win[off], free_stamp | 1u);
         return;

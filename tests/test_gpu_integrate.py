@@ -147,6 +147,39 @@ def test_bresenham_exhaustive_on_device(M):
     assert np.array_equal(g.grid, want)
 
 
+@pytest.mark.parametrize('strategy', STRATEGIES)
+def test_all_line_shapes_through_packets(M, strategy):
+    """Every integer line shape a 1.2 m beam can take at 5 cm (|d| <= 24 cells, all octants and
+    all tie cases) is produced by a packet (front beam aimed from a cell centre at another cell
+    centre; the other three beams come along) and drawn through the packet path of each
+    strategy; the grid must equal the oracle's."""
+    import math
+    from oracle import c_oracle
+    res, size = 0.05, 4096
+    ox = oy = -102.4
+    pk = []
+    slot = 0
+    for dy in range(-24, 25):
+        for dx in range(-24, 25):
+            r = math.hypot(dx, dy) * res
+            if r > 1.19 or (dx == 0 and dy == 0):
+                continue
+            cx, cy = 40 + 60 * (slot % 66), 40 + 60 * (slot // 66)
+            slot += 1
+            x, y = ox + (cx + 0.5) * res, oy + (cy + 0.5) * res
+            yaw = math.atan2(dy, dx)
+            for hit in (True, False):
+                d = r if hit else 3.0
+                pk.append(struct.pack(M.PACKET_FMT, b'QSRL', 1, x, y, yaw, 0, 0, d, 0.3 + 0.01 * (slot % 50), 0.0, 1.0, 0))
+    arr, _ = normalise_datagrams(pk)
+    g = supported(M, strategy, size=size, resolution=res, origin_x=ox, origin_y=oy)
+    g.update_packets(arr)
+    want = np.full((size, size), -1, np.int8)
+    c = c_oracle.integrate_packets(arr, want, ox, oy, res)
+    assert np.array_equal(g.grid, want)
+    assert g.counters()['updates'] == c['updates'] and c['packets'] > 3000
+
+
 def synthetic(n_packets, seed=3, n_agents=64):
     from occgrid_b200 import simulation_tools as st
     return st.generate_session(n_agents=n_agents, n_packets=n_packets, seed=seed)

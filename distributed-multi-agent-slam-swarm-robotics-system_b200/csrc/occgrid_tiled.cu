@@ -112,12 +112,41 @@ k_home_count(Geom g, TileGeom tg, const uint8_t* __restrict__ pkts, long long n,
     for (int i = threadIdx.x; i < kHash; i += kTT) { s_keys[i] = kEmpty; s_vals[i] = 0u; }
     unsigned long long c[OCCGRID_C_HITS + 1] = {};
     const long long cta_first = (long long)blockIdx.x * kPkPerCta;
+    // Software-pipelined staging: the 16-byte loads of sub-batch s+1 are in flight while
+    // sub-batch s is decoded out of shared memory.
+    constexpr int kVec = (kTT * kMaxStrideT / 16 + kTT - 1) / kTT;      // uint4 per thread per sub-batch (<= 4)
+    uint4 pre[kVec];
+    auto prefetch = [&](int sub) {
+        const long long first = cta_first + (long long)sub * kTT;
+        const long long left = n - first;
+        const size_t bytes = left <= 0 ? 0 : (size_t)min((long long)kTT, left) * stride;
+        const uint4* s4 = reinterpret_cast<const uint4*>(pkts + (size_t)first * stride);
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) {
+            const size_t i = (size_t)j * kTT + threadIdx.x;
+            pre[j] = (i * 16 + 16 <= bytes) ? __ldg(s4 + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
+    };
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(pkts) & 15) == 0 && ((kTT * stride) & 15) == 0;
+    if (vec_ok) prefetch(0);
     for (int sub = 0; sub < kSub; ++sub) {
         const long long first = cta_first + (long long)sub * kTT;
         if (first >= n) break;
         const int count = (int)min((long long)kTT, n - first);
         __syncthreads();
-        stage_records_t(pkts + (size_t)first * stride, (size_t)count * stride, s_rec);
+        if (vec_ok) {
+            const size_t bytes = (size_t)count * stride;
+            uint4* d4 = reinterpret_cast<uint4*>(s_rec);
+#pragma unroll
+            for (int j = 0; j < kVec; ++j) {
+                const size_t i = (size_t)j * kTT + threadIdx.x;
+                if (i * 16 + 16 <= bytes) d4[i] = pre[j];
+            }
+            for (size_t i = (bytes / 16) * 16 + threadIdx.x; i < bytes; i += kTT) s_rec[i] = __ldg(pkts + (size_t)first * stride + i);
+            if (sub + 1 < kSub) prefetch(sub + 1);
+        } else {
+            stage_records_t(pkts + (size_t)first * stride, (size_t)count * stride, s_rec);
+        }
         __syncthreads();
         if ((int)threadIdx.x < count) {
             const long long k = first + threadIdx.x;

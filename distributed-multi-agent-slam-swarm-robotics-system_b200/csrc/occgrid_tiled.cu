@@ -461,34 +461,37 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
     }
 }
 
+constexpr int kResolveSplit = 8;      // CTAs per active window (row slices) — few tiles are active, keep all SMs busy
+
 __global__ void __launch_bounds__(kTT)
 k_home_resolve(Geom g, TileGeom tg, const unsigned int* __restrict__ active, TilePlanHeader* __restrict__ hdr,
                unsigned int* __restrict__ stamps, int8_t* __restrict__ grid) {
     __shared__ unsigned int s_item;
-    const unsigned int n_active = hdr->n_active;
+    const unsigned int n_work = hdr->n_active * kResolveSplit;
     const int side = tg.win_side;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_item = atomicAdd(&hdr->resolve_counter, 1u);
         __syncthreads();
         const unsigned int it = s_item;
-        if (it >= n_active) break;
-        const unsigned int t = active[it];
+        if (it >= n_work) break;
+        const unsigned int t = active[it / kResolveSplit];
+        const int part = (int)(it % kResolveSplit);
         const int ttx = t % tg.tiles_x, tty = t / tg.tiles_x;
         const int wx0 = -tg.pad + (ttx << kTileShift) - tg.reach;      // window-relative
         const int wy0 = -tg.pad + (tty << kTileShift) - tg.reach;
         const int lx_lo = max(0, -wx0), lx_hi = min(side, g.win_w - wx0);
         const int ly_lo = max(0, -wy0), ly_hi = min(side, g.win_h - wy0);
-        const int fw = lx_hi - lx_lo;
-        if (fw <= 0 || ly_hi <= ly_lo) continue;
-        const int total = fw * (ly_hi - ly_lo);
-        for (int idx = threadIdx.x; idx < total; idx += kTT) {
-            const int ly = ly_lo + idx / fw, lx = lx_lo + idx % fw;
-            const size_t cidx = (size_t)(wy0 + ly) * g.win_w + (wx0 + lx);
-            const unsigned int s = stamps[cidx];
-            if (s) {
-                grid[cidx] = (s & 1u) ? OCCGRID_CELL_OCCUPIED : OCCGRID_CELL_FREE;
-                stamps[cidx] = 0u;
+        if (lx_hi <= lx_lo) continue;
+        for (int ly = ly_lo + part * (kTT / 32) + warp; ly < ly_hi; ly += kResolveSplit * (kTT / 32)) {   // one warp per row
+            const size_t row = (size_t)(wy0 + ly) * g.win_w + wx0;
+            for (int lx = lx_lo + lane; lx < lx_hi; lx += 32) {
+                const unsigned int s = stamps[row + lx];
+                if (s) {
+                    grid[row + lx] = (s & 1u) ? OCCGRID_CELL_OCCUPIED : OCCGRID_CELL_FREE;
+                    stamps[row + lx] = 0u;
+                }
             }
         }
     }
@@ -594,7 +597,7 @@ int integrate_tiled(const occgrid_geom* geom, const uint8_t* d_packets, const Po
     }
     {
         ProfileScope ps(K_TILE_RESOLVE, st);
-        k_home_resolve<<<sms * 4, kTT, 0, st>>>(g, tg, active, hdr, stamps, d_grid);
+        k_home_resolve<<<sms * 8, kTT, 0, st>>>(g, tg, active, hdr, stamps, d_grid);
     }
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;

@@ -14,8 +14,8 @@
 //
 //   k_home_count    thread/packet: decode (:828-843), pose correction (:851-857), robot cell
 //                   (:142) -> 48-byte pose record (packet order) + packets per home tile
-//   k_tile_plan     one CTA: exclusive scan of the counts -> bin offsets, (tile, chunk) work
-//                   items of <= kChunkPk packets, list of active tiles
+//   k_tile_plan     one CTA over the active tiles (listed by the count pass): exclusive scan of
+//                   their counts -> bin offsets, (tile, chunk) work items of <= kChunkPk packets
 //   k_home_scatter  thread/packet: write the packet's index into its tile's bin
 //   k_home_raycast  persistent CTAs pull work items: zero the (64+2R)^2 smem window, expand
 //                   each record into its 4 beams (fp64 endpoints, :887-902) and walk the exact
@@ -37,7 +37,9 @@ constexpr int kMaxStrideT = 64;
 constexpr int kMaxWindowBytes = 100 * 1024;   // smem window budget (two CTAs per SM at least)
 
 struct TilePlanHeader {
-    unsigned int n_items, n_active, total_records, work_counter, resolve_counter, overflow, pad[2];
+    unsigned int n_items, n_active, total_records, work_counter, resolve_counter, overflow;
+    unsigned int active_count;   // tiles appended to the active list by the count pass of the current call
+    unsigned int pad;
 };
 
 struct TileGeom {
@@ -105,7 +107,7 @@ k_home_count(Geom g, TileGeom tg, const uint8_t* __restrict__ pkts, long long n,
              const int32_t* __restrict__ agent_idx, const double* __restrict__ drift,
              const double* __restrict__ agent_off, int n_agents,
              unsigned int* __restrict__ tile_count, int* __restrict__ tile_ids, PoseRec* __restrict__ recs,
-             uint64_t* counters) {
+             unsigned int* __restrict__ active, TilePlanHeader* __restrict__ hdr, uint64_t* counters) {
     __shared__ __align__(16) uint8_t s_rec[kTT * kMaxStrideT];
     __shared__ unsigned int s_keys[kHash];
     __shared__ unsigned int s_vals[kHash];
@@ -181,7 +183,8 @@ k_home_count(Geom g, TileGeom tg, const uint8_t* __restrict__ pkts, long long n,
     }
     __syncthreads();
     for (int i = threadIdx.x; i < kHash; i += kTT)
-        if (s_keys[i] != kEmpty) atomicAdd(&tile_count[s_keys[i]], s_vals[i]);
+        if (s_keys[i] != kEmpty && atomicAdd(&tile_count[s_keys[i]], s_vals[i]) == 0u)
+            active[atomicAdd(&hdr->active_count, 1u)] = s_keys[i];          // first toucher lists the tile
     // the staging buffer is free now: reuse it for the counter reduction (48 KB static limit)
     block_add_counters(c, reinterpret_cast<unsigned long long*>(s_rec), counters);
 }
@@ -190,7 +193,8 @@ k_home_count(Geom g, TileGeom tg, const uint8_t* __restrict__ pkts, long long n,
 // are binned in place.
 __global__ void __launch_bounds__(kTT)
 k_home_count_poses(Geom g, TileGeom tg, const PoseRec* __restrict__ recs, long long n,
-                   unsigned int* __restrict__ tile_count, int* __restrict__ tile_ids, uint64_t* counters) {
+                   unsigned int* __restrict__ tile_count, int* __restrict__ tile_ids,
+                   unsigned int* __restrict__ active, TilePlanHeader* __restrict__ hdr, uint64_t* counters) {
     __shared__ unsigned int s_keys[kHash];
     __shared__ unsigned int s_vals[kHash];
     __shared__ unsigned long long s_acc[(OCCGRID_C_HITS + 1) * 32];
@@ -220,7 +224,8 @@ k_home_count_poses(Geom g, TileGeom tg, const PoseRec* __restrict__ recs, long l
     }
     __syncthreads();
     for (int i = threadIdx.x; i < kHash; i += kTT)
-        if (s_keys[i] != kEmpty) atomicAdd(&tile_count[s_keys[i]], s_vals[i]);
+        if (s_keys[i] != kEmpty && atomicAdd(&tile_count[s_keys[i]], s_vals[i]) == 0u)
+            active[atomicAdd(&hdr->active_count, 1u)] = s_keys[i];          // first toucher lists the tile
     block_add_counters(c, s_acc, counters);
 }
 
@@ -258,25 +263,28 @@ k_home_scatter(long long n, const int* __restrict__ tile_ids, const unsigned int
     }
 }
 
-// One CTA.  tile_count[t] -> tile_offset[t] (exclusive), cursors zeroed, work items and the
-// active-tile list built.  tile_count is re-zeroed for the next call.
+// One CTA over the ACTIVE tiles only (listed by the count pass, in arbitrary order — nothing
+// downstream depends on the order): exclusive scan of their counts -> bin offsets, cursors
+// zeroed, (tile, chunk) work items built.  tile_count is re-zeroed for the next call.
 __global__ void __launch_bounds__(1024)
 k_tile_plan(unsigned int* __restrict__ tile_count, unsigned int* __restrict__ tile_offset,
-            unsigned int* __restrict__ tile_cursor, int n_tiles, uint4* __restrict__ items, unsigned int max_items,
-            unsigned int* __restrict__ active, unsigned long long max_records, TilePlanHeader* __restrict__ hdr,
+            unsigned int* __restrict__ tile_cursor, uint4* __restrict__ items, unsigned int max_items,
+            const unsigned int* __restrict__ active, unsigned long long max_records, TilePlanHeader* __restrict__ hdr,
             uint64_t* counters) {
-    __shared__ unsigned int s_warp[3][33];
-    __shared__ unsigned int s_carry[3];
-    if (threadIdx.x < 3) s_carry[threadIdx.x] = 0;
+    __shared__ unsigned int s_warp[2][33];
+    __shared__ unsigned int s_carry[2];
+    if (threadIdx.x < 2) s_carry[threadIdx.x] = 0;
     __syncthreads();
+    const int n_active = (int)hdr->active_count;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int start = 0; start < n_tiles; start += blockDim.x) {
-        const int t = start + threadIdx.x;
-        const unsigned int cnt = t < n_tiles ? tile_count[t] : 0u;
-        unsigned int v[3] = {cnt, (cnt + kChunkPk - 1) / kChunkPk, cnt ? 1u : 0u};
-        unsigned int ex[3];
+    for (int start = 0; start < n_active; start += blockDim.x) {
+        const int i = start + threadIdx.x;
+        const unsigned int t = i < n_active ? active[i] : 0u;
+        const unsigned int cnt = i < n_active ? tile_count[t] : 0u;
+        unsigned int v[2] = {cnt, (cnt + kChunkPk - 1) / kChunkPk};
+        unsigned int ex[2];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
+        for (int j = 0; j < 2; ++j) {
             unsigned int inc = v[j];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { unsigned int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
@@ -284,7 +292,7 @@ k_tile_plan(unsigned int* __restrict__ tile_count, unsigned int* __restrict__ ti
             ex[j] = inc - v[j];
         }
         __syncthreads();
-        if (warp < 3) {
+        if (warp < 2) {
             unsigned int w = s_warp[warp][lane], winc = w;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { unsigned int u = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += u; }
@@ -294,34 +302,31 @@ k_tile_plan(unsigned int* __restrict__ tile_count, unsigned int* __restrict__ ti
         __syncthreads();
         const unsigned int off = s_carry[0] + s_warp[0][warp] + ex[0];
         const unsigned int item0 = s_carry[1] + s_warp[1][warp] + ex[1];
-        const unsigned int act = s_carry[2] + s_warp[2][warp] + ex[2];
-        if (t < n_tiles) {
+        if (i < n_active) {
             tile_offset[t] = off;
             tile_cursor[t] = 0u;
             tile_count[t] = 0u;
-            if (cnt) {
-                active[act] = (unsigned int)t;
-                for (unsigned int j = 0; j < v[1]; ++j) {
-                    const unsigned int b = off + j * kChunkPk;
-                    const unsigned int e = min(off + cnt, b + kChunkPk);
-                    if (item0 + j < max_items) items[item0 + j] = make_uint4((unsigned int)t, b, e, 0u);
-                }
+            for (unsigned int j = 0; j < v[1]; ++j) {
+                const unsigned int b = off + j * kChunkPk;
+                const unsigned int e = min(off + cnt, b + kChunkPk);
+                if (item0 + j < max_items) items[item0 + j] = make_uint4(t, b, e, 0u);
             }
         }
         __syncthreads();
-        if (threadIdx.x < 3) s_carry[threadIdx.x] += s_warp[threadIdx.x][32];
+        if (threadIdx.x < 2) s_carry[threadIdx.x] += s_warp[threadIdx.x][32];
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         TilePlanHeader h;
         h.total_records = s_carry[0];
         h.n_items = s_carry[1];
-        h.n_active = s_carry[2];
+        h.n_active = (unsigned int)n_active;
         h.work_counter = 0;
         h.resolve_counter = 0;
+        h.active_count = 0;                  // ready for the next call's count pass
         h.overflow = (s_carry[0] > max_records || s_carry[1] > max_items) ? 1u : 0u;
         if (h.overflow) { h.n_items = 0; h.n_active = 0; }
-        h.pad[0] = h.pad[1] = 0;
+        h.pad = 0;
         *hdr = h;
         if (counters) atomicAdd(reinterpret_cast<unsigned long long*>(counters) + OCCGRID_C_RECORDS, (unsigned long long)s_carry[0]);
     }
@@ -577,15 +582,16 @@ int integrate_tiled(const occgrid_geom* geom, const uint8_t* d_packets, const Po
     {
         ProfileScope ps(K_TILE_COUNT, st);
         if (d_poses)
-            k_home_count_poses<<<blocks, kTT, 0, st>>>(g, tg, d_poses, n, tile_count, tile_ids, d_counters);
+            k_home_count_poses<<<blocks, kTT, 0, st>>>(g, tg, d_poses, n, tile_count, tile_ids, active, hdr, d_counters);
         else
             k_home_count<<<blocks, kTT, 0, st>>>(g, tg, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents,
-                                                tile_count, tile_ids, reinterpret_cast<PoseRec*>(ws + L.off_recs), d_counters);
+                                                tile_count, tile_ids, reinterpret_cast<PoseRec*>(ws + L.off_recs), active, hdr,
+                                                d_counters);
     }
     {
         ProfileScope ps(K_TILE_SCAN, st);
-        k_tile_plan<<<1, 1024, 0, st>>>(tile_count, tile_offset, tile_cursor, tg.n_tiles, items, L.max_items, active,
-                                        L.max_records, hdr, d_counters);
+        k_tile_plan<<<1, 1024, 0, st>>>(tile_count, tile_offset, tile_cursor, items, L.max_items, active, L.max_records, hdr,
+                                        d_counters);
     }
     {
         ProfileScope ps(K_TILE_SCATTER, st);

@@ -189,9 +189,9 @@ def run_reference(args):
     }))
 
 
-def workload_config(n):
-    side = GRID_PER_GPU * n
-    return {'workload': f'{AGENTS_PER_GPU * n} synthetic agents, {side}^2 grid at 5 cm, 1e7 beams/batch per GPU '
+def workload_config(n, grid_per_gpu=GRID_PER_GPU, agents_per_gpu=AGENTS_PER_GPU):
+    side = grid_per_gpu * n
+    return {'workload': f'{agents_per_gpu * n} synthetic agents, {side}^2 grid at 5 cm, 1e7 beams/batch per GPU '
                         f'(BASELINE.json configs[1]{"" if n == 1 else " scaled weakly: " + str(n) + " row bands"})',
             'packets_per_batch_per_gpu': PACKETS_PER_BATCH, 'grid': f'{side}x{side} int8',
             'l2': f'{POOL} distinct 105 MB packet batches cycled (420 MB > 126 MB L2); grid/stamp hot set is '
@@ -212,6 +212,9 @@ def main():
     ap.add_argument('--packets', type=int, default=PACKETS_PER_BATCH)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--trace', action='store_true', help='print per-step wall times (debug)')
+    ap.add_argument('--grid-per-gpu', type=int, default=GRID_PER_GPU,
+                    help='N>1: map side = this x N (8192 with --agents-per-gpu 128 at N=8 = BASELINE configs[3])')
+    ap.add_argument('--agents-per-gpu', type=int, default=AGENTS_PER_GPU)
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -256,7 +259,8 @@ def main():
 
     else:
         from occgrid_b200.distributed import TiledSwarmMap, make_rank_sessions
-        tmap, sessions, step = make_rank_sessions(n, rank, dev, npk, POOL, args.strategy)
+        tmap, sessions, step = make_rank_sessions(n, rank, dev, npk, POOL, args.strategy,
+                                                   grid_per_gpu=args.grid_per_gpu, agents_per_gpu=args.agents_per_gpu)
         grid = tmap.local
 
     # warm-up (at least one pass over every batch of the pool, so that no allocation or
@@ -345,7 +349,8 @@ def main():
     result = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': n, 'steps': K, 'warmup': W,
         'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64+u32', 'data': 'synthetic', 'config': workload_config(n),
+        'dtype': 'f64+u32', 'data': 'synthetic',
+        'config': workload_config(n, args.grid_per_gpu, args.agents_per_gpu) if n > 1 else workload_config(1),
         'beams_per_sec': 4.0 * packets_total / (ms * 1e-3),
         'strategy': args.strategy,
     }

@@ -305,18 +305,19 @@ class ShardedMapMerger:
 #  bench.py helper: weak-scaling sessions
 # ----------------------------------------------------------------------------------------------
 
-def make_rank_sessions(world, rank, device, packets_per_rank, pool, strategy, pipeline=True):
+def make_rank_sessions(world, rank, device, packets_per_rank, pool, strategy, pipeline=True,
+                       grid_per_gpu=4096, agents_per_gpu=64):
     """Weak scaling of BASELINE configs[1]: (4096*world)^2 map, 64*world agents, each rank ingests
     its own `packets_per_rank` share.  Returns (TiledSwarmMap, sessions, step_fn)."""
     from . import simulation_tools as st
-    side = 4096 * world
+    side = grid_per_gpu * world
     origin = (-side * 0.05 / 2.0,) * 2
     tmap = TiledSwarmMap(side, 0.05, origin[0], origin[1], device=device, strategy=strategy,
                          max_batch=int(packets_per_rank * 1.25), pipeline=pipeline)
     sessions = []
     for i in range(pool):
         # this rank's share of the stream: all 64*world agents, `packets_per_rank` records
-        sh = st.generate_session(n_agents=64 * world, n_packets=packets_per_rank, grid_size=side,
+        sh = st.generate_session(n_agents=agents_per_gpu * world, n_packets=packets_per_rank, grid_size=side,
                                  origin=origin, seed=1000 + 97 * i + rank)
         sessions.append({'packets': tmap.ops.stage(sh['packets']),
                          'agent_idx': torch.from_numpy(sh['agent_idx']).to(device),

@@ -10,13 +10,14 @@ torch.cuda.set_device(lr); dev = torch.device('cuda', lr)
 dist.init_process_group('nccl', device_id=dev)
 from occgrid_b200 import simulation_tools as st
 from occgrid_b200.distributed import TiledSwarmMap
-size = 2048 * world
+size = int(os.environ.get('CHECK_GRID_PER_GPU', '2048')) * world
+agents_per_gpu = int(os.environ.get('CHECK_AGENTS_PER_GPU', '32'))
 origin = (-size * 0.05 / 2,) * 2
 n_batches, per_rank = 3, 60_000
-sess = st.generate_session(n_agents=32 * world, n_packets=n_batches * per_rank * world, grid_size=size, origin=origin, seed=77)
+sess = st.generate_session(n_agents=agents_per_gpu * world, n_packets=n_batches * per_rank * world, grid_size=size, origin=origin, seed=77)
 pk, idx, offs = sess['packets'], sess['agent_idx'], sess['agent_offsets']
 ok = True
-for pipeline in (False, True):
+for pipeline in ((True,) if os.environ.get('CHECK_PIPELINE_ONLY') else (False, True)):
     tmap = TiledSwarmMap(size, 0.05, origin[0], origin[1], device=dev, max_batch=per_rank * 2, pipeline=pipeline)
     order = []
     for b in range(n_batches):

@@ -90,9 +90,9 @@ def main():
     m, out = run()
     torch.cuda.synchronize()
     prof = _native.profile_end()
-    kern = {k: {'ms_total': v[0], 'calls': v[1]} for k, v in prof.items()}
+    kern = {k: {'ms_total': v[0], 'kernels': v[1]} for k, v in prof.items()}
     hbm = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'] if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.0
-    ext_ms = prof['merge_extract'][0] / prof['merge_extract'][1]
+    ext_ms = prof['merge_extract'][0] / (prof['merge_extract'][1] / 3)
     result = {
         'metric': 'merged_grids_per_sec', 'value': A / (ms * 1e-3), 'unit': 'grids/s', 'n_gpus': 1, 'ms_per_merge': ms,
         'higher_is_better': True, 'dtype': 'f64+int8', 'data': 'synthetic',

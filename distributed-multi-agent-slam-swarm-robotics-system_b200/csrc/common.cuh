@@ -46,12 +46,14 @@ enum KernelId { K_INTEGRATE_GLOBAL = 0, K_RESOLVE, K_UPDATE_RAYS, K_TILE_COUNT, 
                 K_TILE_RAYCAST, K_TILE_RESOLVE, K_MERGE_EXTRACT, K_MERGE_BOUNDS, K_MERGE_VOXEL, K_MERGE_RASTER,
                 K_MERGE_FUSE, K_PROBE, K_ROUTE, K_N_KERNELS };
 bool profile_enabled();
-void profile_mark(int kernel_id, cudaStream_t st, bool begin);
+void profile_mark(int kernel_id, cudaStream_t st, bool begin, int n_kernels);
 
 struct ProfileScope {
-    int id; cudaStream_t st; bool on;
-    ProfileScope(int id_, cudaStream_t st_) : id(id_), st(st_), on(profile_enabled()) { if (on) profile_mark(id, st, true); }
-    ~ProfileScope() { if (on) profile_mark(id, st, false); }
+    int id; cudaStream_t st; bool on; int nk;
+    ProfileScope(int id_, cudaStream_t st_, int n_kernels = 1) : id(id_), st(st_), on(profile_enabled()), nk(n_kernels) {
+        if (on) profile_mark(id, st, true, nk);
+    }
+    ~ProfileScope() { if (on) profile_mark(id, st, false, nk); }
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

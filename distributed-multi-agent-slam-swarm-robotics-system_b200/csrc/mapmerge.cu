@@ -449,7 +449,7 @@ int mapmerge_extract_transform(const int8_t* d_grid, int32_t width, int32_t heig
     if (T_host) {
         for (int i = 0; i < 16; ++i) { T.m[i] = T_host[i]; if (T_host[i] != ((i % 5 == 0) ? 1.0 : 0.0)) T.identity = 0; }
     }
-    ProfileScope ps(K_MERGE_EXTRACT, st);
+    ProfileScope ps(K_MERGE_EXTRACT, st, 3);
     k_extract_count<<<blocks, kMT, 0, st>>>(d_grid, n_cells, block_counts);
     k_extract_reserve<<<1, 1024, 0, st>>>(block_counts, blocks, (long long*)d_count, capacity, ws_base, d_status,
                                            (long long*)d_last_appended);
@@ -468,7 +468,7 @@ int mapmerge_bounds(const double* d_px, const double* d_py, const int64_t* d_cou
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int blocks = 148 * 8;
-    ProfileScope ps(K_MERGE_BOUNDS, st);
+    ProfileScope ps(K_MERGE_BOUNDS, st, 2);
     k_bounds_partial<<<blocks, kMT, 0, st>>>(d_px, d_py, (const long long*)d_count, (double*)d_ws);
     k_bounds_final<<<1, kMT, 0, st>>>((const double*)d_ws, blocks, d_bounds);
     OCC_CUDA_TRY(cudaGetLastError());
@@ -520,7 +520,7 @@ int mapmerge_voxel_downsample(const double* d_px, const double* d_py, const int6
     const int gp = grid_for(point_capacity);
     const int gc = grid_for(lattice_capacity_cells / 4 + 1);
     const int gs = grid_for((lattice_capacity_cells + 1 + kScanItems - 1) / kScanItems);
-    ProfileScope ps(K_MERGE_VOXEL, st);
+    ProfileScope ps(K_MERGE_VOXEL, st, 8);
     k_voxel_setup<<<1, 1, 0, st>>>(d_bounds, (const long long*)d_count, voxel, lattice_capacity_cells, hdr, d_status);
     k_voxel_zero<<<gc, kMT, 0, st>>>(hdr, counts);
     k_voxel_count<<<gp, kMT, 0, st>>>(d_px, d_py, voxel, hdr, counts, key, rank);
@@ -542,7 +542,7 @@ int mapmerge_rasterise(const double* d_px, const double* d_py, const int64_t* d_
     }
     cudaStream_t st = (cudaStream_t)stream;
     const long long n = (long long)width * height;
-    ProfileScope ps(K_MERGE_RASTER, st);
+    ProfileScope ps(K_MERGE_RASTER, st, 2);
     k_raster_fill<<<grid_for(n / 16 + 1), kMT, 0, st>>>(d_grid_out, n);
     k_raster_scatter<<<148 * 8, kMT, 0, st>>>(d_px, d_py, (const long long*)d_count, d_bounds, res, width, height, d_grid_out);
     OCC_CUDA_TRY(cudaGetLastError());

@@ -42,14 +42,15 @@ struct ProfileState {
     std::mutex mu;
     bool on = false;
     std::vector<cudaEvent_t> ev[K_N_KERNELS];   // begin/end pairs
+    long long kernels[K_N_KERNELS] = {};         // kernels launched inside the scopes
 };
 static ProfileState g_prof;
 
 bool profile_enabled() { return g_prof.on; }
 
-void profile_mark(int id, cudaStream_t st, bool begin) {
-    (void)begin;
+void profile_mark(int id, cudaStream_t st, bool begin, int n_kernels) {
     std::lock_guard<std::mutex> lk(g_prof.mu);
+    if (begin) g_prof.kernels[id] += n_kernels;
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return;
     cudaEventRecord(e, st);
@@ -504,6 +505,7 @@ int occgrid_update_rays(const occgrid_geom* geom, const double* d_rays, const ui
 int occgrid_profile_begin(void) {
     std::lock_guard<std::mutex> lk(g_prof.mu);
     for (auto& v : g_prof.ev) { for (auto e : v) cudaEventDestroy(e); v.clear(); }
+    for (auto& k : g_prof.kernels) k = 0;
     g_prof.on = true;
     return OCCGRID_OK;
 }
@@ -522,7 +524,7 @@ int occgrid_profile_end(double* ms_by_kernel, int64_t* launches_by_kernel, int n
         }
         if (k < n_slots) {
             if (ms_by_kernel) ms_by_kernel[k] = ms;
-            if (launches_by_kernel) launches_by_kernel[k] = (int64_t)(v.size() / 2);
+            if (launches_by_kernel) launches_by_kernel[k] = (int64_t)g_prof.kernels[k];
         }
         for (auto e : v) cudaEventDestroy(e);
         v.clear();

@@ -208,7 +208,7 @@ int occgrid_route_packets(const occgrid_geom* geom, int n_bands, const int32_t* 
         OCC_CUDA_TRY(cudaMemsetAsync(d_band_counts, 0, sizeof(int64_t) * n_bands, st));
         return OCCGRID_OK;
     }
-    ProfileScope ps(K_ROUTE, st);
+    ProfileScope ps(K_ROUTE, st, 3);
     k_route_count<<<blocks, kRT, 0, st>>>(P, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents, hist, blocks, d_counters);
     k_route_scan<<<1, 1024, 0, st>>>(hist, n_bands, blocks, (long long*)d_band_counts, send_capacity, d_status);
     k_route_scatter<<<blocks, kRT, 0, st>>>(P, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents, hist, blocks,

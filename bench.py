@@ -215,6 +215,8 @@ def main():
     ap.add_argument('--grid-per-gpu', type=int, default=GRID_PER_GPU,
                     help='N>1: map side = this x N (8192 with --agents-per-gpu 128 at N=8 = BASELINE configs[3])')
     ap.add_argument('--agents-per-gpu', type=int, default=AGENTS_PER_GPU)
+    ap.add_argument('--exchange', default='auto', choices=['auto', 'p2p', 'nccl'],
+                    help='N>1: routed records via peer-memory stores from the routing kernel (p2p) or NCCL all-to-all')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -260,7 +262,8 @@ def main():
     else:
         from occgrid_b200.distributed import TiledSwarmMap, make_rank_sessions
         tmap, sessions, step = make_rank_sessions(n, rank, dev, npk, POOL, args.strategy,
-                                                   grid_per_gpu=args.grid_per_gpu, agents_per_gpu=args.agents_per_gpu)
+                                                   grid_per_gpu=args.grid_per_gpu, agents_per_gpu=args.agents_per_gpu,
+                                                   exchange=args.exchange)
         grid = tmap.local
 
     # warm-up (at least one pass over every batch of the pool, so that no allocation or
@@ -355,6 +358,8 @@ def main():
         'beams_per_sec': 4.0 * packets_total / (ms * 1e-3),
         'strategy': args.strategy,
     }
+    if n > 1:
+        result['exchange'] = tmap.exchange
 
     # ---- single-GPU extras: scatter roofline, e2e, cpu baseline ------------------------------
     if n == 1:

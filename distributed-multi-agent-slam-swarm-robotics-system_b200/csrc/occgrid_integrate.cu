@@ -173,7 +173,7 @@ k_integrate_global(Geom g, const uint8_t* __restrict__ pkts, long long n, int st
 
 // Decoded input (routed pose records): same as k_integrate_global minus the decode.
 __global__ void __launch_bounds__(kThreads)
-k_integrate_poses_global(Geom g, const PoseRec* __restrict__ recs, long long n,
+k_integrate_poses_global(Geom g, const PoseRec* __restrict__ recs, long long n, int ordinals_in_records,
                          unsigned int* __restrict__ stamps, uint64_t* counters) {
     __shared__ unsigned long long s_acc[(OCCGRID_C_OWNED_UPDATES + 1) * 32];
     const long long k = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -196,7 +196,8 @@ k_integrate_poses_global(Geom g, const PoseRec* __restrict__ recs, long long n,
                 c[OCCGRID_C_UPDATES] += cells;
                 c[OCCGRID_C_SLOWPATH] += b[s].slow;
                 if (start_in_window(g, b[s])) c[OCCGRID_C_OWNED_UPDATES] += cells;
-                draw_beam_global(g, stamps, b[s], (unsigned int)(k * 4 + s + 1), later_writes_first);
+                const unsigned int ord = ordinals_in_records ? r.k : (unsigned int)k;
+                draw_beam_global(g, stamps, b[s], ord * 4u + (unsigned int)s + 1u, later_writes_first);
                 later_writes_first = later_writes_first || (b[s].valid && (cells > 1 || b[s].hit));
             }
         }
@@ -382,8 +383,8 @@ int integrate_packets_tiled(const occgrid_geom* geom, const uint8_t* d_packets, 
                             int n_agents, int8_t* d_grid, void* d_ws, size_t ws_bytes, uint64_t* d_counters,
                             cudaStream_t st);
 bool tiled_supported(const occgrid_geom* geom);
-int integrate_poses_tiled(const occgrid_geom* geom, const void* d_poses, int64_t n, int8_t* d_grid, void* d_ws,
-                          size_t ws_bytes, uint64_t* d_counters, cudaStream_t st);
+int integrate_poses_tiled(const occgrid_geom* geom, const void* d_poses, int64_t n, int ordinals_in_records, int8_t* d_grid,
+                          void* d_ws, size_t ws_bytes, uint64_t* d_counters, cudaStream_t st);
 }
 
 extern "C" {
@@ -446,8 +447,9 @@ int occgrid_integrate_packets(const occgrid_geom* geom, const uint8_t* d_packets
     return OCCGRID_E_ARG;
 }
 
-int occgrid_integrate_poses(const occgrid_geom* geom, const void* d_pose_recs, int64_t n, int8_t* d_grid,
-                            void* d_workspace, size_t workspace_bytes, uint64_t* d_counters, int strategy, void* stream) {
+int occgrid_integrate_poses(const occgrid_geom* geom, const void* d_pose_recs, int64_t n, int ordinals_in_records,
+                            int8_t* d_grid, void* d_workspace, size_t workspace_bytes, uint64_t* d_counters, int strategy,
+                            void* stream) {
     int rc = validate_geom(geom);
     if (rc != OCCGRID_OK) return rc;
     if (n < 0 || n > (1ll << 29) - 1) { set_last_error("n=%lld outside 0..2^29-1 records per call", (long long)n); return OCCGRID_E_ARG; }
@@ -458,7 +460,7 @@ int occgrid_integrate_poses(const occgrid_geom* geom, const void* d_pose_recs, i
     cudaStream_t st = (cudaStream_t)stream;
     if (s == OCCGRID_STRATEGY_TILED) {
         if (!tiled_supported(geom)) { set_last_error("TILED strategy does not support this geometry"); return OCCGRID_E_RANGE; }
-        return integrate_poses_tiled(geom, d_pose_recs, n, d_grid, d_workspace, workspace_bytes, d_counters, st);
+        return integrate_poses_tiled(geom, d_pose_recs, n, ordinals_in_records, d_grid, d_workspace, workspace_bytes, d_counters, st);
     }
     if (s != OCCGRID_STRATEGY_GLOBAL_ATOMIC) { set_last_error("unknown strategy %d", strategy); return OCCGRID_E_ARG; }
     if (workspace_bytes < global_workspace_bytes(geom)) {
@@ -470,7 +472,7 @@ int occgrid_integrate_poses(const occgrid_geom* geom, const void* d_pose_recs, i
     {
         ProfileScope ps(K_INTEGRATE_GLOBAL, st);
         k_integrate_poses_global<<<(unsigned int)blocks, kThreads, 0, st>>>(to_geom(geom), reinterpret_cast<const PoseRec*>(d_pose_recs),
-                                                                            n, stamps, d_counters);
+                                                                            n, ordinals_in_records, stamps, d_counters);
     }
     OCC_CUDA_TRY(cudaGetLastError());
     return launch_resolve(geom, stamps, d_grid, st);

@@ -168,6 +168,62 @@ k_route_scatter(RouteParams P, const uint8_t* __restrict__ pkts, long long n, in
     }
 }
 
+// ---- fused route + exchange over peer memory ------------------------------------------------
+// One pass: decode, pick the destination band(s), reserve slots in the DESTINATION GPU's receive
+// buffer with one remote atomicAdd per band per CTA, and store the 48-byte records straight into
+// peer memory over NVLink (three 16-byte stores each).  No send buffer, no all-to-all, no counts
+// exchange.  Arrival order is arbitrary, so every record carries its ordinal in the canonical
+// stream (ordinal_base + index) and the receiver integrates with ordinals taken from the records.
+__global__ void __launch_bounds__(kRT)
+k_route_p2p(RouteParams P, const uint8_t* __restrict__ pkts, long long n, int stride,
+            const int32_t* __restrict__ agent_idx, const double* __restrict__ drift,
+            const double* __restrict__ agent_off, int n_agents, unsigned int ordinal_base,
+            PoseRec* const* __restrict__ peer_recv, unsigned int* const* __restrict__ peer_count,
+            unsigned int recv_capacity, int* __restrict__ status, uint64_t* counters) {
+    __shared__ __align__(16) uint8_t s_rec[kRT * kRouteMaxStride];
+    __shared__ unsigned int s_wcnt[kRouteMaxBands][kRT / 32];
+    __shared__ unsigned int s_base[kRouteMaxBands];
+    __shared__ unsigned long long s_acc[4 * 32];
+    const long long first = (long long)blockIdx.x * kRT;
+    const int count = (int)min((long long)kRT, n - first);
+    stage(pkts + (size_t)first * stride, (size_t)count * stride, s_rec);
+    __syncthreads();
+    unsigned int m = 0;
+    int st = -1;
+    PoseRec rec;
+    const long long k = first + threadIdx.x;
+    if ((int)threadIdx.x < count) m = band_mask(P, s_rec + threadIdx.x * stride, k, agent_idx, drift, agent_off, n_agents, &st, &rec);
+    rec.k = ordinal_base + (unsigned int)k;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b = 0; b < P.n_bands; ++b) {
+        const unsigned int bal = __ballot_sync(0xffffffffu, (m >> b) & 1u);
+        if (lane == 0) s_wcnt[b][warp] = __popc(bal);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < P.n_bands) {          // one remote reservation per band per CTA
+        unsigned int tot = 0;
+        for (int w = 0; w < kRT / 32; ++w) { const unsigned int c = s_wcnt[threadIdx.x][w]; s_wcnt[threadIdx.x][w] = tot; tot += c; }
+        unsigned int base = 0;
+        if (tot) {
+            base = atomicAdd(peer_count[threadIdx.x], tot);
+            if (base + tot > recv_capacity) { atomicOr(status, 1); base = 0xffffffffu; }
+        }
+        s_base[threadIdx.x] = base;
+    }
+    __syncthreads();
+    for (int b = 0; b < P.n_bands; ++b) {
+        const unsigned int bit = (m >> b) & 1u;
+        const unsigned int bal = __ballot_sync(0xffffffffu, bit);
+        if (bit && s_base[b] != 0xffffffffu) {
+            const unsigned int dst = s_base[b] + s_wcnt[b][warp] + __popc(bal & ((1u << lane) - 1u));
+            peer_recv[b][dst] = rec;
+        }
+    }
+    unsigned long long c[4] = {(unsigned long long)(st >= 0), (unsigned long long)(st == PKT_OK),
+                               (unsigned long long)(st == PKT_DROPPED), (unsigned long long)(st == PKT_BAD_POSE)};
+    block_add_counters(c, s_acc, counters);
+}
+
 }  // namespace occ
 
 using namespace occ;
@@ -213,6 +269,36 @@ int occgrid_route_packets(const occgrid_geom* geom, int n_bands, const int32_t* 
     k_route_scan<<<1, 1024, 0, st>>>(hist, n_bands, blocks, (long long*)d_band_counts, send_capacity, d_status);
     k_route_scatter<<<blocks, kRT, 0, st>>>(P, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents, hist, blocks,
                                             d_status, reinterpret_cast<PoseRec*>(d_send));
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
+}
+
+int occgrid_route_packets_p2p(const occgrid_geom* geom, int n_bands, const int32_t* band_y0_host,
+                              const uint8_t* d_packets, int64_t n, int stride, int rec_len,
+                              const int32_t* d_agent_idx, const double* d_drift, const double* d_agent_off, int n_agents,
+                              uint32_t ordinal_base, void* const* d_peer_recv, uint32_t* const* d_peer_count,
+                              int64_t recv_capacity, int32_t* d_status, uint64_t* d_counters, void* stream) {
+    int rc = validate_geom(geom);
+    if (rc != OCCGRID_OK) return rc;
+    if (n_bands < 1 || n_bands > kRouteMaxBands || !band_y0_host) { set_last_error("route_p2p: n_bands must be 1..32"); return OCCGRID_E_ARG; }
+    if (n < 0 || (uint64_t)ordinal_base + (uint64_t)n > (1ull << 29) - 1) { set_last_error("route_p2p: ordinals must stay below 2^29-1"); return OCCGRID_E_ARG; }
+    if (rec_len != OCCGRID_PACKET_SIZE && rec_len != OCCGRID_PACKET_SIZE_V1) { set_last_error("route_p2p: rec_len must be 42 or 41"); return OCCGRID_E_ARG; }
+    if (stride < rec_len || stride > kRouteMaxStride) { set_last_error("route_p2p: bad stride %d", stride); return OCCGRID_E_ARG; }
+    if (!d_peer_recv || !d_peer_count || !d_status || !d_agent_off || n_agents < 1) { set_last_error("route_p2p: NULL argument"); return OCCGRID_E_ARG; }
+    if (recv_capacity <= 0 || recv_capacity >= (1ll << 32)) { set_last_error("route_p2p: bad receive capacity"); return OCCGRID_E_ARG; }
+    if (n == 0) return OCCGRID_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    RouteParams P;
+    P.oy = geom->oy; P.res = geom->res; P.size_y = geom->size_y;
+    P.reach = (int)ceil(OCC_MAX_DIST_M / geom->res) + 2;
+    P.n_bands = n_bands;
+    for (int b = 0; b <= n_bands; ++b) P.band_y0[b] = band_y0_host[b];
+    for (int b = n_bands + 1; b <= kRouteMaxBands; ++b) P.band_y0[b] = band_y0_host[n_bands];
+    const int blocks = (int)((n + kRT - 1) / kRT);
+    ProfileScope ps(K_ROUTE, st, 1);
+    k_route_p2p<<<blocks, kRT, 0, st>>>(P, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents, ordinal_base,
+                                        reinterpret_cast<PoseRec* const*>(d_peer_recv), d_peer_count,
+                                        (unsigned int)recv_capacity, d_status, d_counters);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
 }

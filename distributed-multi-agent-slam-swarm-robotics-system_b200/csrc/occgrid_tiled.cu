@@ -390,7 +390,7 @@ __device__ __forceinline__ void draw_beam_smem(unsigned int* __restrict__ s_win,
 
 __global__ void __launch_bounds__(kTT)
 k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHeader* __restrict__ hdr,
-               const unsigned int* __restrict__ bins, const PoseRec* __restrict__ recs,
+               const unsigned int* __restrict__ bins, const PoseRec* __restrict__ recs, int ordinals_in_records,
                unsigned int* __restrict__ stamps, uint64_t* counters) {
     extern __shared__ unsigned int s_win[];
     __shared__ unsigned int s_item;
@@ -411,8 +411,9 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
         const int wx0 = g.win_x0 - tg.pad + (ttx << kTileShift) - tg.reach;
         const int wy0 = g.win_y0 - tg.pad + (tty << kTileShift) - tg.reach;
         for (unsigned int r = item.y + threadIdx.x; r < item.z; r += kTT) {
-            const unsigned int k = bins[r];            // record index = packet ordinal in this batch
-            const PoseRec rec = recs[k];
+            const unsigned int idx = bins[r];
+            const PoseRec rec = recs[idx];
+            const unsigned int k = ordinals_in_records ? rec.k : idx;   // packet ordinal in this batch
             const float dist[4] = {rec.d[0], rec.d[1], rec.d[2], rec.d[3]};
             Beam b[4];
             expand_packet(g, rec.rx, rec.ry, (double)rec.yaw, dist, LibSinCos(), b);
@@ -542,7 +543,8 @@ size_t tiled_workspace_bytes(const occgrid_geom* geom, int64_t max_packets) {
 }
 
 // `d_poses` != NULL: input is n PoseRec (already decoded and corrected), `d_packets` etc. unused.
-int integrate_tiled(const occgrid_geom* geom, const uint8_t* d_packets, const PoseRec* d_poses, int64_t n, int stride,
+int integrate_tiled(const occgrid_geom* geom, const uint8_t* d_packets, const PoseRec* d_poses, int ordinals_in_records,
+                    int64_t n, int stride,
                     const int32_t* d_agent_idx, const double* d_drift, const double* d_agent_off,
                     int n_agents, int8_t* d_grid, void* d_ws, size_t ws_bytes, uint64_t* d_counters,
                     cudaStream_t st) {
@@ -599,7 +601,8 @@ int integrate_tiled(const occgrid_geom* geom, const uint8_t* d_packets, const Po
     }
     {
         ProfileScope ps(K_TILE_RAYCAST, st);
-        k_home_raycast<<<sms * ctas_per_sm, kTT, win_bytes, st>>>(g, tg, items, hdr, bins, recs, stamps, d_counters);
+        k_home_raycast<<<sms * ctas_per_sm, kTT, win_bytes, st>>>(g, tg, items, hdr, bins, recs, ordinals_in_records, stamps,
+                                                                  d_counters);
     }
     {
         ProfileScope ps(K_TILE_RESOLVE, st);
@@ -613,13 +616,14 @@ int integrate_packets_tiled(const occgrid_geom* geom, const uint8_t* d_packets, 
                             const int32_t* d_agent_idx, const double* d_drift, const double* d_agent_off,
                             int n_agents, int8_t* d_grid, void* d_ws, size_t ws_bytes, uint64_t* d_counters,
                             cudaStream_t st) {
-    return integrate_tiled(geom, d_packets, nullptr, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents, d_grid, d_ws,
+    return integrate_tiled(geom, d_packets, nullptr, 0, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents, d_grid, d_ws,
                            ws_bytes, d_counters, st);
 }
 
-int integrate_poses_tiled(const occgrid_geom* geom, const void* d_poses, int64_t n, int8_t* d_grid, void* d_ws,
-                          size_t ws_bytes, uint64_t* d_counters, cudaStream_t st) {
-    return integrate_tiled(geom, nullptr, reinterpret_cast<const PoseRec*>(d_poses), n, 0, nullptr, nullptr, nullptr, 0,
+int integrate_poses_tiled(const occgrid_geom* geom, const void* d_poses, int64_t n, int ordinals_in_records, int8_t* d_grid,
+                          void* d_ws, size_t ws_bytes, uint64_t* d_counters, cudaStream_t st) {
+    return integrate_tiled(geom, nullptr, reinterpret_cast<const PoseRec*>(d_poses), ordinals_in_records, n, 0, nullptr, nullptr,
+                           nullptr, 0,
                            d_grid, d_ws, ws_bytes, d_counters, st);
 }
 

@@ -91,6 +91,17 @@ class CudaBandOps:
             raise OccGridError('route: send buffer overflow')
         return self._send[:int(sum(counts))], counts
 
+    def route_p2p(self, packets, agent_idx, drift, agent_table, ordinal_base, recv_ptrs, count_ptrs, capacity):
+        """Fused route + exchange: records go straight into the owners' receive buffers."""
+        n, stride = packets.shape
+        rc = self._lib.occgrid_route_packets_p2p(
+            self._geom, self.layout.n_bands, self._band_y0.ctypes.data, packets.data_ptr(), n, stride,
+            42 if stride >= 42 else 41,
+            agent_idx.data_ptr() if agent_idx is not None else None, drift.data_ptr() if drift is not None else None,
+            agent_table.data_ptr(), agent_table.shape[0] - 1, int(ordinal_base), recv_ptrs.data_ptr(), count_ptrs.data_ptr(),
+            int(capacity), self._status.data_ptr(), None, torch.cuda.current_stream(self.device).cuda_stream)
+        _native.check(rc, 'occgrid_route_packets_p2p')
+
     def empty(self, rows, stride, dtype):
         shape = (rows, stride) if stride else (rows,)
         return torch.empty(shape, dtype=dtype, device=self.device)
@@ -102,12 +113,53 @@ class CudaBandOps:
         return self.grid.grid_tensor
 
 
+class PeerExchange:
+    """Receive buffers in symmetric (peer-mapped) memory for the fused route+exchange kernel
+    ``occgrid_route_packets_p2p``: three slots per rank so that one cross-GPU barrier per step is
+    enough (passing barrier j implies every rank finished integrating batch j-2, whose slot is the
+    one batch j+1 will be written into)."""
+    SLOTS = 3
+
+    def __init__(self, device, group, capacity):
+        import torch.distributed._symmetric_memory as symm
+        self.device = device
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.capacity = int(capacity)
+        pg = group if group is not None else dist.group.WORLD
+        try:
+            symm.enable_symm_mem_for_group(pg.group_name)
+        except Exception:
+            pass
+        self.recv = symm.empty((self.SLOTS, self.capacity, 48), dtype=torch.uint8, device=device)
+        self.count = symm.empty((self.SLOTS, 64), dtype=torch.int32, device=device)      # one counter per 256 B
+        self.count.zero_()
+        self.h_recv = symm.rendezvous(self.recv, pg)
+        self.h_count = symm.rendezvous(self.count, pg)
+        self.recv_ptrs, self.count_ptrs = [], []
+        for s in range(self.SLOTS):
+            self.recv_ptrs.append(torch.tensor([int(p) + s * self.capacity * 48 for p in self.h_recv.buffer_ptrs],
+                                               dtype=torch.int64, device=device))
+            self.count_ptrs.append(torch.tensor([int(p) + s * 256 for p in self.h_count.buffer_ptrs],
+                                                dtype=torch.int64, device=device))
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)
+        self.group = group
+
+    def barrier(self):
+        """Cross-GPU barrier ordered on the current stream."""
+        try:
+            self.h_recv.barrier(channel=0)
+        except Exception:
+            dist.barrier(group=self.group)
+
+
 class TiledSwarmMap:
     """A global occupancy grid spatially tiled over the ranks of a process group.  Mirrors
     ``OccupancyGrid``'s batched entry; each rank passes ITS share of the packet stream."""
 
     def __init__(self, size, resolution=0.05, origin_x=-5.0, origin_y=-5.0, *, group=None, device=None,
-                 strategy='auto', max_batch=1 << 16, ops=None, pipeline=False):
+                 strategy='auto', max_batch=1 << 16, ops=None, pipeline=False, exchange='nccl'):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -126,6 +178,19 @@ class TiledSwarmMap:
         self._step = 0
         self._slot_free = [None, None]
         self._side = torch.cuda.Stream(device=ops.device) if self.pipeline else None
+        # exchange = 'p2p': routed records are stored straight into the owner's receive buffer over
+        # NVLink by the routing kernel (symmetric memory); 'nccl': send buffer + all_to_all_single
+        self.peer = None
+        self.exchange = 'nccl'
+        if exchange in ('p2p', 'auto') and self.world > 1 and hasattr(ops, 'grid'):
+            try:
+                self.peer = PeerExchange(ops.device, group, int(max_batch * 1.6) + 4096)
+                self.exchange = 'p2p'
+            except Exception as e:                      # no symmetric memory on this system: NCCL path
+                if exchange == 'p2p':
+                    raise
+                self.peer = None
+        self._done = {}
 
     def _agent_table(self, separation, agent_offsets):
         if isinstance(agent_offsets, torch.Tensor):
@@ -177,6 +242,8 @@ class TiledSwarmMap:
         the PREVIOUS batch is being integrated (NVLink traffic hidden behind SM work); the map is
         complete after ``flush()`` (``gather_grid``/``counters`` flush first).  Batch order, and
         with it last-writer-wins, is unchanged."""
+        if self.peer is not None:
+            return self._update_packets_p2p(packets, separation, drift, agent_offsets, agent_idx)
         if not self.pipeline:
             recv = self._route_and_exchange(packets, separation, drift, agent_offsets, agent_idx, 0)
             self.ops.integrate(recv)
@@ -195,6 +262,54 @@ class TiledSwarmMap:
             self._integrate_pending(prev, main)
         return int(recv.shape[0])
 
+    def _update_packets_p2p(self, packets, separation, drift, agent_offsets, agent_idx):
+        """Fused route+exchange over peer memory.  Side stream (or the current one when not
+        pipelined): wait for my integrate of batch j-2, route batch j into the owners' slot j%3,
+        cross-GPU barrier, read my fill counter.  Main stream: integrate my slot with the
+        ordinals carried by the records, zero its counter."""
+        px = self.peer
+        dev = self.ops.device
+        main = torch.cuda.current_stream(dev)
+        j = self._step
+        self._step += 1
+        slot = j % px.SLOTS
+        stream = self._side if self.pipeline else main
+        with torch.cuda.stream(stream):
+            if self.pipeline and (j - 2) in self._done:
+                stream.wait_event(self._done.pop(j - 2))
+            tab = self._agent_table(separation, agent_offsets)
+            pk = self.ops.stage(packets)
+            idx = torch.as_tensor(agent_idx, dtype=torch.int32).to(dev).contiguous() if agent_idx is not None else None
+            dr = torch.as_tensor(drift, dtype=torch.float64).reshape(-1, 2).to(dev).contiguous() if drift is not None else None
+            self.ops.route_p2p(pk, idx, dr, tab, self.rank * ((1 << 29) // (self.world + 1)), px.recv_ptrs[slot],
+                               px.count_ptrs[slot], px.capacity)
+            px.barrier()
+            host = torch.cat([px.count[slot, :1], self.ops._status]).cpu().tolist()      # the one host sync of a step
+            n_recv, status = int(host[0]), int(host[1])
+            if status & 1:
+                self.ops._status.zero_()
+                raise OccGridError('route_p2p: a receive buffer overflowed')
+            ready = torch.cuda.Event()
+            ready.record(stream)
+        pending = (slot, n_recv, ready, j)
+        if not self.pipeline:
+            self._integrate_p2p(pending, main)
+        else:
+            prev, self._pending = self._pending, pending
+            if prev is not None:
+                self._integrate_p2p(prev, main)
+        return n_recv
+
+    def _integrate_p2p(self, pending, main):
+        slot, n_recv, ready, j = pending
+        px = self.peer
+        main.wait_event(ready)
+        self.ops.grid.update_poses(px.recv[slot, :n_recv], ordinals_in_records=True)
+        px.count[slot].zero_()
+        done = torch.cuda.Event()
+        done.record(main)
+        self._done[j] = done
+
     def _integrate_pending(self, pending, main):
         recv, ready, slot = pending
         main.wait_event(ready)
@@ -207,7 +322,11 @@ class TiledSwarmMap:
         """Integrate the batch still in flight (pipeline mode)."""
         if self.pipeline and self._pending is not None:
             pending, self._pending = self._pending, None
-            self._integrate_pending(pending, torch.cuda.current_stream(self.ops.device))
+            main = torch.cuda.current_stream(self.ops.device)
+            if self.peer is not None:
+                self._integrate_p2p(pending, main)
+            else:
+                self._integrate_pending(pending, main)
 
     def gather_grid(self):
         """Assemble the global map on every rank (all_gather of the disjoint bands)."""
@@ -306,14 +425,14 @@ class ShardedMapMerger:
 # ----------------------------------------------------------------------------------------------
 
 def make_rank_sessions(world, rank, device, packets_per_rank, pool, strategy, pipeline=True,
-                       grid_per_gpu=4096, agents_per_gpu=64):
+                       grid_per_gpu=4096, agents_per_gpu=64, exchange='auto'):
     """Weak scaling of BASELINE configs[1]: (4096*world)^2 map, 64*world agents, each rank ingests
     its own `packets_per_rank` share.  Returns (TiledSwarmMap, sessions, step_fn)."""
     from . import simulation_tools as st
     side = grid_per_gpu * world
     origin = (-side * 0.05 / 2.0,) * 2
     tmap = TiledSwarmMap(side, 0.05, origin[0], origin[1], device=device, strategy=strategy,
-                         max_batch=int(packets_per_rank * 1.25), pipeline=pipeline)
+                         max_batch=int(packets_per_rank * 1.25), pipeline=pipeline, exchange=exchange)
     sessions = []
     for i in range(pool):
         # this rank's share of the stream: all 64*world agents, `packets_per_rank` records

@@ -357,9 +357,10 @@ class OccupancyGrid:
             _native.check(rc, 'occgrid_integrate_packets')
         self._host_cache = None
 
-    def update_poses(self, pose_recs):
-        """Integrate decoded records (uint8 cuda tensor [n, 48] of ``occgrid_pose_rec``) in index
-        order — the receiving side of the multi-GPU routing (``occgrid_route_packets``)."""
+    def update_poses(self, pose_recs, ordinals_in_records=False):
+        """Integrate decoded records (uint8 cuda tensor [n, 48] of ``occgrid_pose_rec``) — the
+        receiving side of the multi-GPU routing.  Order = index (``occgrid_route_packets`` +
+        all-to-all) or the ordinal carried in each record (``occgrid_route_packets_p2p``)."""
         with torch.cuda.device(self.device):
             if not (isinstance(pose_recs, torch.Tensor) and pose_recs.dtype == torch.uint8 and pose_recs.is_cuda
                     and pose_recs.dim() == 2 and pose_recs.shape[1] == 48):
@@ -369,7 +370,8 @@ class OccupancyGrid:
             if n == 0:
                 return
             self._ensure_workspace(n)
-            rc = self._lib.occgrid_integrate_poses(self._geom, pose_recs.data_ptr(), n, self.grid_tensor.data_ptr(),
+            rc = self._lib.occgrid_integrate_poses(self._geom, pose_recs.data_ptr(), n, 1 if ordinals_in_records else 0,
+                                                   self.grid_tensor.data_ptr(),
                                                    self._ws.data_ptr(), self._ws.numel(), self._counters.data_ptr(),
                                                    self._strategy, self._stream())
             _native.check(rc, 'occgrid_integrate_poses')

@@ -177,8 +177,24 @@ int occgrid_route_packets(const occgrid_geom* geom, int n_bands, const int32_t* 
  * of occgrid_integrate_packets (beam expansion :881-903 + update_ray :136-156) for input whose
  * decode/filter/pose correction (:826-857) already happened — on another GPU, in the router. */
 int occgrid_integrate_poses(const occgrid_geom* geom, const void* d_pose_recs, int64_t n,
+                            int ordinals_in_records /* 0: order = index; 1: order = rec.k */,
                             int8_t* d_grid, void* d_workspace, size_t workspace_bytes,
                             uint64_t* d_counters, int strategy, void* stream);
+
+/* Fused route + exchange over peer memory (NVLink): like occgrid_route_packets, but every record
+ * is stored DIRECTLY into the receive buffer of the GPU that owns its band — d_peer_recv[b] and
+ * d_peer_count[b] are device arrays of peer-mapped pointers (band b's occgrid_pose_rec buffer and
+ * its uint32 fill counter, zeroed by the owner) — with one remote atomicAdd per band per CTA.
+ * Records arrive in arbitrary order and carry rec.k = ordinal_base + index, the ordinal in the
+ * canonical stream; the owner integrates with occgrid_integrate_poses(ordinals_in_records = 1)
+ * after a cross-GPU barrier.  d_status bit 0 = a receive buffer overflowed. */
+int occgrid_route_packets_p2p(const occgrid_geom* geom, int n_bands, const int32_t* band_y0_host,
+                              const uint8_t* d_packets, int64_t n, int stride, int rec_len,
+                              const int32_t* d_agent_idx, const double* d_drift,
+                              const double* d_agent_off, int n_agents, uint32_t ordinal_base,
+                              void* const* d_peer_recv, uint32_t* const* d_peer_count,
+                              int64_t recv_capacity, int32_t* d_status, uint64_t* d_counters,
+                              void* stream);
 
 /* ------------------------------------------------------------------------------------------
  *  Map fusion — server_nodes/map_merger.py:35-127

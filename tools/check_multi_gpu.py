@@ -17,8 +17,15 @@ n_batches, per_rank = 3, 60_000
 sess = st.generate_session(n_agents=agents_per_gpu * world, n_packets=n_batches * per_rank * world, grid_size=size, origin=origin, seed=77)
 pk, idx, offs = sess['packets'], sess['agent_idx'], sess['agent_offsets']
 ok = True
-for pipeline in ((True,) if os.environ.get('CHECK_PIPELINE_ONLY') else (False, True)):
-    tmap = TiledSwarmMap(size, 0.05, origin[0], origin[1], device=dev, max_batch=per_rank * 2, pipeline=pipeline)
+modes = [(True, 'p2p')] if os.environ.get('CHECK_PIPELINE_ONLY') else [(False, 'nccl'), (True, 'nccl'), (False, 'p2p'), (True, 'p2p')]
+for pipeline, exchange in modes:
+    try:
+        tmap = TiledSwarmMap(size, 0.05, origin[0], origin[1], device=dev, max_batch=per_rank * 2, pipeline=pipeline,
+                             exchange=exchange)
+    except Exception as e:
+        if rank == 0:
+            print(f'world={world} pipeline={pipeline} exchange={exchange}: UNAVAILABLE ({type(e).__name__}: {e})', flush=True)
+        continue
     order = []
     for b in range(n_batches):
         base = b * per_rank * world
@@ -33,7 +40,7 @@ for pipeline in ((True,) if os.environ.get('CHECK_PIPELINE_ONLY') else (False, T
         c = c_oracle.integrate_packets(pk[o], want, origin[0], origin[1], 0.05, agent_offsets=offs, agent_idx=idx[o])
         same = bool(np.array_equal(got, want))
         ok &= same
-        print(f'world={world} pipeline={pipeline}: map {"bit-exact" if same else "DIFFERS"} vs oracle '
+        print(f'world={world} pipeline={pipeline} exchange={tmap.exchange}: map {"bit-exact" if same else "DIFFERS"} vs oracle '
               f'({c["beams"]} beams, {int((want != -1).sum())} known cells)', flush=True)
     dist.barrier()
 if rank == 0:

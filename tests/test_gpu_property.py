@@ -1,0 +1,90 @@
+"""Property tests (hypothesis) of the CUDA integration path against the C oracle: random grid
+geometry, window, agent offsets, drift, record stride and adversarial field values; the int8
+window must be identical.  Also sizes the path on the edge cases the domain has: empty batch,
+single packet, every packet dropped, rays entirely outside the grid."""
+import struct
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip('torch')
+hyp = pytest.importorskip('hypothesis')
+from hypothesis import given, settings, strategies as st_, HealthCheck
+
+
+def make_packets(rng, n, span, ox, oy, n_agents):
+    special = np.array([0.0, -1.0, 4.0, np.nan, np.inf, 0.05, 1.2, 1.2000001, 0.050000004, 0.01, 2.5], np.float32)
+    out = np.zeros((n, 42), np.uint8)
+    rec = out.view(np.dtype([('magic', 'S4'), ('agent', 'u1'), ('x', '<f4'), ('y', '<f4'), ('yaw', '<f4'), ('enc', '<i4'),
+                             ('v2v', '<u4'), ('d', '<f4', 4), ('lm', 'u1')]))[:, 0]
+    rec['magic'] = b'QSRL'
+    rec['magic'][rng.random(n) < 0.03] = b'QSRX'
+    rec['agent'] = rng.integers(0, n_agents + 2, n)
+    rec['x'] = rng.uniform(ox - 2, ox + span + 2, n)
+    rec['y'] = rng.uniform(oy - 2, oy + span + 2, n)
+    q = rng.random(n) < 0.3
+    rec['x'][q] = np.round(rec['x'][q] / 0.05) * 0.05
+    rec['yaw'] = np.where(rng.random(n) < 0.5, np.radians(15.0 * rng.integers(-12, 13, n)), rng.uniform(-7, 7, n))
+    d = rng.uniform(0, 1.5, (n, 4)).astype(np.float32)
+    m = rng.random((n, 4)) < 0.2
+    d[m] = special[rng.integers(0, len(special), int(m.sum()))]
+    rec['d'] = d
+    return out
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(seed=st_.integers(0, 2 ** 31 - 1), size=st_.integers(8, 700), res=st_.sampled_from([0.03, 0.05, 0.1, 0.2]),
+       strategy=st_.sampled_from(['auto', 'global_atomic', 'tiled']), stride=st_.sampled_from([42, 48, 64]),
+       windowed=st_.booleans(), use_drift=st_.booleans())
+def test_random_geometry_and_streams(seed, size, res, strategy, stride, windowed, use_drift):
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from occgrid_b200 import dual_bot_mapper as M
+    from oracle import c_oracle
+    rng = np.random.default_rng(seed)
+    ox, oy = float(rng.uniform(-50, 10)), float(rng.uniform(-50, 10))
+    n_agents = int(rng.integers(1, 6))
+    offs = np.zeros((n_agents + 1, 2))
+    offs[1:] = rng.uniform(-1, 1, (n_agents, 2))
+    n = int(rng.integers(1, 4000))
+    pk = make_packets(rng, n, size * res, ox, oy, n_agents)
+    buf = np.zeros((n, stride), np.uint8)
+    buf[:, :42] = pk
+    drift = rng.normal(0, 0.05, (n, 2)) if use_drift else None
+    window = None
+    if windowed:
+        x0, y0 = int(rng.integers(0, size)), int(rng.integers(0, size))
+        window = (x0, y0, int(rng.integers(1, size - x0 + 1)), int(rng.integers(1, size - y0 + 1)))
+    try:
+        g = M.OccupancyGrid(size, res, ox, oy, window=window, strategy=strategy, max_batch=n)
+    except M.OccGridError:
+        return          # TILED not available for this resolution
+    half = n // 2
+    g.update_packets(buf[:half], agent_offsets=offs, drift=None if drift is None else drift[:half])
+    g.update_packets(buf[half:], agent_offsets=offs, drift=None if drift is None else drift[half:])
+    full = np.full((size, size), -1, np.int8)
+    c_oracle.integrate_packets(pk, full, ox, oy, res, agent_offsets=offs, drift=drift)
+    want = full if window is None else full[window[1]:window[1] + window[3], window[0]:window[0] + window[2]]
+    assert np.array_equal(g.grid, want)
+
+
+@pytest.mark.parametrize('strategy', ['global_atomic', 'tiled'])
+def test_edge_batches(strategy):
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from occgrid_b200 import dual_bot_mapper as M
+    g = M.OccupancyGrid(strategy=strategy)
+    blank = np.full((200, 200), -1, np.int8)
+    g.update_packets(np.zeros((0, 42), np.uint8))
+    dropped = np.zeros((500, 42), np.uint8)                       # bad magic everywhere
+    g.update_packets(dropped)
+    far = [struct.pack(M.PACKET_FMT, b'QSRL', 1, 500.0, -700.0, 0.3, 0, 0, 0.5, 0.6, 0.7, 0.8, 0) for _ in range(300)]
+    g.update_packets(far)                                         # rays entirely outside the grid
+    assert np.array_equal(g.grid, blank)
+    c = g.counters()
+    assert c['dropped'] == 500 and c['accepted'] == 300 and c['packets'] == 800
+    one = struct.pack(M.PACKET_FMT, b'QSRL', 2, 0.0, 0.0, 0.0, 0, 0, 0.0, 0.0, 0.0, 0.0, 0)   # heartbeat packet
+    g.update_packets([one], separation=1.0)
+    got = g.grid
+    assert (got == 0).sum() == 4 * 24 - 3 and (got == 100).sum() == 0      # four 1.2 m free rays from one cell

@@ -94,6 +94,8 @@ def lib():
     L.occgrid_integrate_poses.argtypes = [gp, vp, i64, i32, vp, vp, sz, vp, i32, vp]
     L.occgrid_route_packets_p2p.restype = i32
     L.occgrid_route_packets_p2p.argtypes = [gp, i32, vp, vp, i64, i32, i32, vp, vp, vp, i32, u32, vp, vp, i64, vp, vp, vp]
+    L.occgrid_set_raycast_ctas_per_sm.restype = i32
+    L.occgrid_set_raycast_ctas_per_sm.argtypes = [i32]
     L.occgrid_profile_begin.restype = i32
     L.occgrid_profile_end.restype = i32
     L.occgrid_profile_end.argtypes = [vp, vp, i32]

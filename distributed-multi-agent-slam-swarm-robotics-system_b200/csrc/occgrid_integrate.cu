@@ -383,6 +383,7 @@ int integrate_packets_tiled(const occgrid_geom* geom, const uint8_t* d_packets, 
                             int n_agents, int8_t* d_grid, void* d_ws, size_t ws_bytes, uint64_t* d_counters,
                             cudaStream_t st);
 bool tiled_supported(const occgrid_geom* geom);
+void set_raycast_cta_cap(int cap);
 int integrate_poses_tiled(const occgrid_geom* geom, const void* d_poses, int64_t n, int ordinals_in_records, int8_t* d_grid,
                           void* d_ws, size_t ws_bytes, uint64_t* d_counters, cudaStream_t st);
 }
@@ -502,6 +503,11 @@ int occgrid_update_rays(const occgrid_geom* geom, const double* d_rays, const ui
     }
     OCC_CUDA_TRY(cudaGetLastError());
     return launch_resolve(geom, stamps, d_grid, st);
+}
+
+int occgrid_set_raycast_ctas_per_sm(int cap) {
+    set_raycast_cta_cap(cap);
+    return OCCGRID_OK;
 }
 
 int occgrid_profile_begin(void) {

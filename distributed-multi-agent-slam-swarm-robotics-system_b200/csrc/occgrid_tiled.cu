@@ -505,6 +505,11 @@ k_home_resolve(Geom g, TileGeom tg, const unsigned int* __restrict__ active, Til
 
 // ---- host side ----------------------------------------------------------------------------
 
+// Persistent raycast CTAs per SM (0 = as many as fit).  A multi-GPU pipeline lowers it so that
+// the routing kernel of the next batch can be co-resident (occgrid_set_raycast_ctas_per_sm).
+static int g_raycast_cta_cap = 0;
+void set_raycast_cta_cap(int cap) { g_raycast_cta_cap = cap < 0 ? 0 : cap; }
+
 struct TiledLayout {
     size_t off_stamps, off_count, off_offset, off_cursor, off_active, off_hdr, off_items, off_ids, off_bins, off_recs, total;
     unsigned long long max_records;
@@ -581,6 +586,7 @@ int integrate_tiled(const occgrid_geom* geom, const uint8_t* d_packets, const Po
     int ctas_per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_home_raycast, kTT, win_bytes) != cudaSuccess || ctas_per_sm < 1)
         ctas_per_sm = 1;
+    if (g_raycast_cta_cap > 0 && ctas_per_sm > g_raycast_cta_cap) ctas_per_sm = g_raycast_cta_cap;
     {
         ProfileScope ps(K_TILE_COUNT, st);
         if (d_poses)

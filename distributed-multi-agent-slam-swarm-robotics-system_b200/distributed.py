@@ -273,6 +273,12 @@ class TiledSwarmMap:
         j = self._step
         self._step += 1
         slot = j % px.SLOTS
+        # pipeline: put the PREVIOUS batch's integration on the main stream first, so that it runs
+        # while this batch is routed over NVLink on the side stream (the host then waits only for
+        # the router's fill counter)
+        if self.pipeline and self._pending is not None:
+            prev, self._pending = self._pending, None
+            self._integrate_p2p(prev, main)
         stream = self._side if self.pipeline else main
         with torch.cuda.stream(stream):
             if self.pipeline and (j - 2) in self._done:
@@ -295,9 +301,7 @@ class TiledSwarmMap:
         if not self.pipeline:
             self._integrate_p2p(pending, main)
         else:
-            prev, self._pending = self._pending, pending
-            if prev is not None:
-                self._integrate_p2p(prev, main)
+            self._pending = pending
         return n_recv
 
     def _integrate_p2p(self, pending, main):

@@ -249,6 +249,11 @@ int mapmerge_rasterise(const double* d_px, const double* d_py, const int64_t* d_
  * of the multi-GPU fuse; the cross-GPU half is an NCCL max-reduction on int8. */
 int mapmerge_fuse_max(int8_t* d_dst, const int8_t* d_src, int64_t n, void* stream);
 
+/* Tuning knob of the TILED strategy: cap the persistent raycast CTAs per SM (0 = as many as fit,
+ * the default).  A pipelined multi-GPU ingest lowers it to 2 so that the routing kernel of the
+ * next batch finds room on every SM and runs concurrently.  Process-wide. */
+int occgrid_set_raycast_ctas_per_sm(int cap);
+
 /*
  * Measurement hook (bench.py): between _begin and _end every kernel this library launches is
  * bracketed by CUDA events on its stream.  _end synchronises those events and returns, per

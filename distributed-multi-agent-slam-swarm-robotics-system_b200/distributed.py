@@ -127,10 +127,6 @@ class PeerExchange:
         self.rank = dist.get_rank(group)
         self.capacity = int(capacity)
         pg = group if group is not None else dist.group.WORLD
-        try:
-            symm.enable_symm_mem_for_group(pg.group_name)
-        except Exception:
-            pass
         self.recv = symm.empty((self.SLOTS, self.capacity, 48), dtype=torch.uint8, device=device)
         self.count = symm.empty((self.SLOTS, 64), dtype=torch.int32, device=device)      # one counter per 256 B
         self.count.zero_()

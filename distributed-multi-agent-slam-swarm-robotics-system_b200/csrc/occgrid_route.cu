@@ -174,6 +174,9 @@ k_route_scatter(RouteParams P, const uint8_t* __restrict__ pkts, long long n, in
 // peer memory over NVLink (three 16-byte stores each).  No send buffer, no all-to-all, no counts
 // exchange.  Arrival order is arbitrary, so every record carries its ordinal in the canonical
 // stream (ordinal_base + index) and the receiver integrates with ordinals taken from the records.
+constexpr int kRouteSub = 8;                       // sub-batches of kRT packets per CTA
+constexpr int kRoutePerCta = kRT * kRouteSub;     // 2048 packets share one remote reservation per band
+
 __global__ void __launch_bounds__(kRT)
 k_route_p2p(RouteParams P, const uint8_t* __restrict__ pkts, long long n, int stride,
             const int32_t* __restrict__ agent_idx, const double* __restrict__ drift,
@@ -181,47 +184,72 @@ k_route_p2p(RouteParams P, const uint8_t* __restrict__ pkts, long long n, int st
             PoseRec* const* __restrict__ peer_recv, unsigned int* const* __restrict__ peer_count,
             unsigned int recv_capacity, int* __restrict__ status, uint64_t* counters) {
     __shared__ __align__(16) uint8_t s_rec[kRT * kRouteMaxStride];
-    __shared__ unsigned int s_wcnt[kRouteMaxBands][kRT / 32];
+    __shared__ unsigned int s_cnt[kRouteSub][kRouteMaxBands][kRT / 32];   // per (sub-batch, band, warp) counts -> offsets
     __shared__ unsigned int s_base[kRouteMaxBands];
-    __shared__ unsigned long long s_acc[4 * 32];
-    const long long first = (long long)blockIdx.x * kRT;
-    const int count = (int)min((long long)kRT, n - first);
-    stage(pkts + (size_t)first * stride, (size_t)count * stride, s_rec);
-    __syncthreads();
-    unsigned int m = 0;
-    int st = -1;
-    PoseRec rec;
-    const long long k = first + threadIdx.x;
-    if ((int)threadIdx.x < count) m = band_mask(P, s_rec + threadIdx.x * stride, k, agent_idx, drift, agent_off, n_agents, &st, &rec);
-    rec.k = ordinal_base + (unsigned int)k;
+    const long long cta_first = (long long)blockIdx.x * kRoutePerCta;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int b = 0; b < P.n_bands; ++b) {
-        const unsigned int bal = __ballot_sync(0xffffffffu, (m >> b) & 1u);
-        if (lane == 0) s_wcnt[b][warp] = __popc(bal);
+    unsigned long long c[4] = {0, 0, 0, 0};
+    unsigned int masks[kRouteSub];
+    // pass 1: decode, band masks, per-warp counts
+#pragma unroll
+    for (int sub = 0; sub < kRouteSub; ++sub) {
+        const long long first = cta_first + (long long)sub * kRT;
+        masks[sub] = 0;
+        if (first < n) {                                           // uniform across the CTA
+            const int count = (int)min((long long)kRT, n - first);
+            __syncthreads();
+            stage(pkts + (size_t)first * stride, (size_t)count * stride, s_rec);
+            __syncthreads();
+            int st = -1;
+            PoseRec unused;
+            if ((int)threadIdx.x < count)
+                masks[sub] = band_mask(P, s_rec + threadIdx.x * stride, first + threadIdx.x, agent_idx, drift, agent_off, n_agents, &st, &unused);
+            c[0] += st >= 0; c[1] += st == PKT_OK; c[2] += st == PKT_DROPPED; c[3] += st == PKT_BAD_POSE;
+        }
+        for (int b = 0; b < P.n_bands; ++b) {
+            const unsigned int bal = __ballot_sync(0xffffffffu, (masks[sub] >> b) & 1u);
+            if (lane == 0) s_cnt[sub][b][warp] = __popc(bal);
+        }
     }
     __syncthreads();
-    if ((int)threadIdx.x < P.n_bands) {          // one remote reservation per band per CTA
+    if ((int)threadIdx.x < P.n_bands) {          // exclusive offsets within the CTA + one remote reservation per band
+        const int b = threadIdx.x;
         unsigned int tot = 0;
-        for (int w = 0; w < kRT / 32; ++w) { const unsigned int c = s_wcnt[threadIdx.x][w]; s_wcnt[threadIdx.x][w] = tot; tot += c; }
+        for (int sub = 0; sub < kRouteSub; ++sub)
+            for (int w = 0; w < kRT / 32; ++w) { const unsigned int v = s_cnt[sub][b][w]; s_cnt[sub][b][w] = tot; tot += v; }
         unsigned int base = 0;
         if (tot) {
-            base = atomicAdd(peer_count[threadIdx.x], tot);
+            base = atomicAdd(peer_count[b], tot);
             if (base + tot > recv_capacity) { atomicOr(status, 1); base = 0xffffffffu; }
         }
-        s_base[threadIdx.x] = base;
+        s_base[b] = base;
     }
     __syncthreads();
-    for (int b = 0; b < P.n_bands; ++b) {
-        const unsigned int bit = (m >> b) & 1u;
-        const unsigned int bal = __ballot_sync(0xffffffffu, bit);
-        if (bit && s_base[b] != 0xffffffffu) {
-            const unsigned int dst = s_base[b] + s_wcnt[b][warp] + __popc(bal & ((1u << lane) - 1u));
-            peer_recv[b][dst] = rec;
+    // pass 2: decode again (the records are L2-resident) and store into the owners' buffers
+#pragma unroll
+    for (int sub = 0; sub < kRouteSub; ++sub) {
+        const long long first = cta_first + (long long)sub * kRT;
+        if (first >= n) break;
+        const int count = (int)min((long long)kRT, n - first);
+        __syncthreads();
+        stage(pkts + (size_t)first * stride, (size_t)count * stride, s_rec);
+        __syncthreads();
+        const unsigned int m = masks[sub];
+        if (__ballot_sync(0xffffffffu, m != 0) == 0) continue;
+        PoseRec rec;
+        int st;
+        const long long k = first + threadIdx.x;
+        if (m) band_mask(P, s_rec + threadIdx.x * stride, k, agent_idx, drift, agent_off, n_agents, &st, &rec);
+        rec.k = ordinal_base + (unsigned int)k;
+        for (int b = 0; b < P.n_bands; ++b) {
+            const unsigned int bit = (m >> b) & 1u;
+            const unsigned int bal = __ballot_sync(0xffffffffu, bit);
+            if (bit && s_base[b] != 0xffffffffu)
+                peer_recv[b][s_base[b] + s_cnt[sub][b][warp] + __popc(bal & ((1u << lane) - 1u))] = rec;
         }
     }
-    unsigned long long c[4] = {(unsigned long long)(st >= 0), (unsigned long long)(st == PKT_OK),
-                               (unsigned long long)(st == PKT_DROPPED), (unsigned long long)(st == PKT_BAD_POSE)};
-    block_add_counters(c, s_acc, counters);
+    __syncthreads();
+    block_add_counters(c, reinterpret_cast<unsigned long long*>(s_rec), counters);
 }
 
 }  // namespace occ
@@ -294,7 +322,7 @@ int occgrid_route_packets_p2p(const occgrid_geom* geom, int n_bands, const int32
     P.n_bands = n_bands;
     for (int b = 0; b <= n_bands; ++b) P.band_y0[b] = band_y0_host[b];
     for (int b = n_bands + 1; b <= kRouteMaxBands; ++b) P.band_y0[b] = band_y0_host[n_bands];
-    const int blocks = (int)((n + kRT - 1) / kRT);
+    const int blocks = (int)((n + kRoutePerCta - 1) / kRoutePerCta);
     ProfileScope ps(K_ROUTE, st, 1);
     k_route_p2p<<<blocks, kRT, 0, st>>>(P, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents, ordinal_base,
                                         reinterpret_cast<PoseRec* const*>(d_peer_recv), d_peer_count,

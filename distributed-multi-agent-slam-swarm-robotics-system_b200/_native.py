@@ -107,6 +107,8 @@ def lib():
 def _bind_merge(L):
     """mapmerge_* entry points (include/occgrid_b200.h)."""
     vp, i64, i32, sz, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t, C.c_double
+    L.mapmerge_count_occupied.restype = C.c_int
+    L.mapmerge_count_occupied.argtypes = [vp, i64, vp, vp]
     L.mapmerge_extract_workspace_bytes.restype = sz
     L.mapmerge_extract_workspace_bytes.argtypes = [i64]
     L.mapmerge_extract_transform.restype = C.c_int

@@ -11,8 +11,9 @@
 // rounded operations, in the order the reference evaluates it.
 //
 // Determinism: Open3D's voxel filter emits voxels in hash-map order (unspecified).  We fix the
-// canonical order "ascending (iy, ix)" and sum the points of a voxel in ascending point index,
-// so results are bit-reproducible and equal to the oracle (oracle/merge_oracle.py).
+// canonical order "first appearance" (voxels in order of their smallest point index, as an
+// insertion-ordered map would give) and sum the points of a voxel in ascending point index, so
+// results are bit-reproducible and equal to the oracle (oracle/merge_oracle.py).
 #include "common.cuh"
 
 namespace occ {
@@ -83,6 +84,18 @@ k_extract_count(const int8_t* __restrict__ grid, long long n_cells, unsigned int
     unsigned int total;
     block_exclusive_scan(c, s_warp, &total);
     if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+}
+
+// Number of occupied (> 50) cells of a grid, added to *out (device int64).
+__global__ void __launch_bounds__(kMT)
+k_count_occupied(const int8_t* __restrict__ grid, long long n_cells, long long* __restrict__ out) {
+    unsigned int c = 0;
+    for (long long base = ((long long)blockIdx.x * kMT + threadIdx.x) * kCellsPerThread; base < n_cells;
+         base += (long long)gridDim.x * kMT * kCellsPerThread)
+        c += __popc(occupied_mask16(grid, base, n_cells));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(reinterpret_cast<unsigned long long*>(out), (unsigned long long)c);
 }
 
 // Single-CTA exclusive scan of the per-block counts; also reserves the output range
@@ -207,41 +220,49 @@ k_bounds_final(const double* __restrict__ partial, int n_partial, double* __rest
 }
 
 // ---- a11: VoxelDownSample -------------------------------------------------------------------
+// O(points) per call.  The dense voxel lattice is only a lookup table (two uint32 planes that are
+// all-zero between calls and cleaned by the very threads that dirtied them), never scanned:
+//   mark    every point i: key = voxel index; first[key] = max(first[key], ~i) (i.e. the SMALLEST
+//           index wins); cnt[key] += 1
+//   scan    over the POINTS (3 kernels): a point is its voxel's head iff first[key] == ~i; exclusive
+//           sums of [head] (-> output position: voxels come out in order of first appearance) and
+//           of [head ? cnt : 0] (-> slot range of the voxel)
+//   fill    every point drops its index into its voxel's slot range (cnt counts back to zero)
+//   reduce  every head visits its voxel's indices in ascending order, accumulates, divides
+//           (AccumulatedPoint::GetAveragePoint), writes the mean and clears first[key]
 
 struct VoxelHeader {          // lives at the start of the voxel workspace
     double mbx, mby;          // voxel_min_bound = min_bound - 0.5 * voxel
     long long nx, ny, cells;  // lattice extent actually used by this call
     long long n_points;
+    unsigned int total_slots, total_voxels;
 };
 
 __global__ void k_voxel_setup(const double* __restrict__ bounds, const long long* __restrict__ d_count, double voxel,
-                              long long capacity_cells, VoxelHeader* __restrict__ hdr, int* __restrict__ status) {
+                              long long capacity_cells, long long point_capacity, VoxelHeader* __restrict__ hdr,
+                              int* __restrict__ status) {
     const long long n = *d_count;
     VoxelHeader h;
     h.n_points = n;
+    h.total_slots = h.total_voxels = 0;
     h.mbx = OCC_DADD(bounds[0], -OCC_DMUL(voxel, 0.5));
     h.mby = OCC_DADD(bounds[1], -OCC_DMUL(voxel, 0.5));
-    if (n <= 0) { h.nx = h.ny = h.cells = 0; *hdr = h; return; }
+    if (n <= 0) { h.nx = h.ny = h.cells = 0; h.n_points = 0; *hdr = h; return; }
     h.nx = (long long)floor(OCC_DDIV(OCC_DADD(bounds[2], -h.mbx), voxel)) + 1;
     h.ny = (long long)floor(OCC_DDIV(OCC_DADD(bounds[3], -h.mby), voxel)) + 1;
     h.cells = h.nx * h.ny;
-    if (h.nx <= 0 || h.ny <= 0 || h.cells > capacity_cells || h.cells >= 0xffffffffll) {
-        atomicOr(status, ST_LATTICE_OVERFLOW);
+    if (h.nx <= 0 || h.ny <= 0 || h.cells > capacity_cells || h.cells >= 0xffffffffll || n > point_capacity ||
+        n >= 0xfffffff0ll) {
+        atomicOr(status, n > point_capacity ? ST_POINT_OVERFLOW : ST_LATTICE_OVERFLOW);
         h.cells = 0; h.n_points = 0;        // make every later kernel of this call a no-op
     }
     *hdr = h;
 }
 
 __global__ void __launch_bounds__(kMT)
-k_voxel_zero(const VoxelHeader* __restrict__ hdr, unsigned int* __restrict__ counts) {
-    const long long cells = hdr->cells + 1;
-    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < cells; i += (long long)gridDim.x * kMT) counts[i] = 0u;
-}
-
-__global__ void __launch_bounds__(kMT)
-k_voxel_count(const double* __restrict__ px, const double* __restrict__ py, double voxel,
-              const VoxelHeader* __restrict__ hdr, unsigned int* __restrict__ counts,
-              unsigned int* __restrict__ key, unsigned int* __restrict__ rank) {
+k_voxel_mark(const double* __restrict__ px, const double* __restrict__ py, double voxel,
+             const VoxelHeader* __restrict__ hdr, unsigned int* __restrict__ first, unsigned int* __restrict__ cnt,
+             unsigned int* __restrict__ key) {
     const long long n = hdr->n_points;
     const double mbx = hdr->mbx, mby = hdr->mby;
     const long long nx = hdr->nx;
@@ -250,29 +271,38 @@ k_voxel_count(const double* __restrict__ px, const double* __restrict__ py, doub
         const long long iy = (long long)floor(OCC_DDIV(OCC_DADD(py[i], -mby), voxel));
         const unsigned int k = (unsigned int)(iy * nx + ix);
         key[i] = k;
-        rank[i] = atomicAdd(&counts[k], 1u);
+        atomicMax(&first[k], 0xffffffffu - (unsigned int)i);
+        atomicAdd(&cnt[k], 1u);
     }
 }
 
-// Large exclusive scan, three kernels.  Input counts[c]; outputs pts_off[c] (exclusive sum of
-// counts, in place) and vox_off[c] (exclusive count of non-empty voxels).  Element `cells`
-// receives the totals.
 constexpr int kScanItems = 8;
 constexpr int kScanChunk = kMT * kScanItems;
 
+__device__ __forceinline__ void head_values(long long i, long long n, const unsigned int* __restrict__ key,
+                                            const unsigned int* __restrict__ first, const unsigned int* __restrict__ cnt,
+                                            unsigned int* is_head, unsigned int* slots) {
+    *is_head = 0; *slots = 0;
+    if (i < n) {
+        const unsigned int k = key[i];
+        if (first[k] == 0xffffffffu - (unsigned int)i) { *is_head = 1u; *slots = cnt[k]; }
+    }
+}
+
 __global__ void __launch_bounds__(kMT)
-k_scan_partial(const unsigned int* __restrict__ counts, const VoxelHeader* __restrict__ hdr, uint2* __restrict__ block_sums) {
+k_pscan_partial(const VoxelHeader* __restrict__ hdr, const unsigned int* __restrict__ key,
+                const unsigned int* __restrict__ first, const unsigned int* __restrict__ cnt, uint2* __restrict__ block_sums) {
     __shared__ unsigned int s_warp[33];
-    const long long cells = hdr->cells + 1;
-    const long long nblocks = (cells + kScanChunk - 1) / kScanChunk;
+    const long long n = hdr->n_points;
+    const long long nblocks = (n + kScanChunk - 1) / kScanChunk;
     for (long long b = blockIdx.x; b < nblocks; b += gridDim.x) {
         const long long base = b * kScanChunk + (long long)threadIdx.x * kScanItems;
         unsigned int s = 0, f = 0;
 #pragma unroll
-        for (int i = 0; i < kScanItems; ++i) {
-            const unsigned int c = (base + i < cells) ? counts[base + i] : 0u;
-            s += c;
-            f += c ? 1u : 0u;
+        for (int j = 0; j < kScanItems; ++j) {
+            unsigned int h, c;
+            head_values(base + j, n, key, first, cnt, &h, &c);
+            f += h; s += c;
         }
         unsigned int ts, tf;
         block_exclusive_scan(s, s_warp, &ts);
@@ -282,11 +312,11 @@ k_scan_partial(const unsigned int* __restrict__ counts, const VoxelHeader* __res
 }
 
 __global__ void __launch_bounds__(1024)
-k_scan_top(uint2* __restrict__ block_sums, const VoxelHeader* __restrict__ hdr) {
+k_pscan_top(uint2* __restrict__ block_sums, VoxelHeader* __restrict__ hdr) {
     __shared__ unsigned int s_warp[33];
     __shared__ unsigned int s_c0, s_c1;
-    const long long cells = hdr->cells + 1;
-    const long long nblocks = (cells + kScanChunk - 1) / kScanChunk;
+    const long long n = hdr->n_points;
+    const long long nblocks = (n + kScanChunk - 1) / kScanChunk;
     if (threadIdx.x == 0) { s_c0 = 0; s_c1 = 0; }
     __syncthreads();
     for (long long start = 0; start < nblocks; start += blockDim.x) {
@@ -300,23 +330,26 @@ k_scan_top(uint2* __restrict__ block_sums, const VoxelHeader* __restrict__ hdr) 
         if (threadIdx.x == 0) { s_c0 += t0; s_c1 += t1; }
         __syncthreads();
     }
+    if (threadIdx.x == 0) { hdr->total_slots = s_c0; hdr->total_voxels = s_c1; }
 }
 
+// Writes, for every head point i: out position vrank[i], slot offset soff[i], voxel size vcnt[i].
 __global__ void __launch_bounds__(kMT)
-k_scan_apply(unsigned int* __restrict__ counts_to_ptsoff, unsigned int* __restrict__ vox_off,
-             const VoxelHeader* __restrict__ hdr, const uint2* __restrict__ block_sums) {
+k_pscan_apply(const VoxelHeader* __restrict__ hdr, const unsigned int* __restrict__ key,
+              const unsigned int* __restrict__ first, const unsigned int* __restrict__ cnt,
+              const uint2* __restrict__ block_sums, unsigned int* __restrict__ vrank, unsigned int* __restrict__ soff,
+              unsigned int* __restrict__ vcnt) {
     __shared__ unsigned int s_warp[33];
-    const long long cells = hdr->cells + 1;
-    const long long nblocks = (cells + kScanChunk - 1) / kScanChunk;
+    const long long n = hdr->n_points;
+    const long long nblocks = (n + kScanChunk - 1) / kScanChunk;
     for (long long b = blockIdx.x; b < nblocks; b += gridDim.x) {
         const long long base = b * kScanChunk + (long long)threadIdx.x * kScanItems;
-        unsigned int c[kScanItems];
+        unsigned int h[kScanItems], c[kScanItems];
         unsigned int s = 0, f = 0;
 #pragma unroll
-        for (int i = 0; i < kScanItems; ++i) {
-            c[i] = (base + i < cells) ? counts_to_ptsoff[base + i] : 0u;
-            s += c[i];
-            f += c[i] ? 1u : 0u;
+        for (int j = 0; j < kScanItems; ++j) {
+            head_values(base + j, n, key, first, cnt, &h[j], &c[j]);
+            f += h[j]; s += c[j];
         }
         unsigned int ts, tf;
         unsigned int es = block_exclusive_scan(s, s_warp, &ts);
@@ -325,55 +358,63 @@ k_scan_apply(unsigned int* __restrict__ counts_to_ptsoff, unsigned int* __restri
         es += carry.x;
         ef += carry.y;
 #pragma unroll
-        for (int i = 0; i < kScanItems; ++i) {
-            if (base + i < cells) {
-                counts_to_ptsoff[base + i] = es;
-                vox_off[base + i] = ef;
-            }
-            es += c[i];
-            ef += c[i] ? 1u : 0u;
+        for (int j = 0; j < kScanItems; ++j) {
+            if (h[j]) { vrank[base + j] = ef; soff[base + j] = es; vcnt[base + j] = c[j]; }
+            es += c[j];
+            ef += h[j];
         }
     }
 }
 
 __global__ void __launch_bounds__(kMT)
-k_voxel_fill(const VoxelHeader* __restrict__ hdr, const unsigned int* __restrict__ pts_off,
-             const unsigned int* __restrict__ key, const unsigned int* __restrict__ rank, unsigned int* __restrict__ slots) {
+k_voxel_fill(const VoxelHeader* __restrict__ hdr, const unsigned int* __restrict__ key,
+             const unsigned int* __restrict__ first, unsigned int* __restrict__ cnt,
+             const unsigned int* __restrict__ soff, unsigned int* __restrict__ slots) {
     const long long n = hdr->n_points;
-    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT)
-        slots[pts_off[key[i]] + rank[i]] = (unsigned int)i;
+    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
+        const unsigned int k = key[i];
+        const unsigned int head = 0xffffffffu - first[k];
+        const unsigned int r = atomicSub(&cnt[k], 1u) - 1u;       // cnt[k] is back to zero when the kernel ends
+        slots[soff[head] + r] = (unsigned int)i;
+    }
 }
 
-// One thread per voxel (the thread of the point that drew rank 0): visit the voxel's point
-// indices in ascending order, accumulate, divide (AccumulatedPoint::GetAveragePoint).
 __global__ void __launch_bounds__(kMT)
 k_voxel_reduce(const double* __restrict__ px, const double* __restrict__ py, const VoxelHeader* __restrict__ hdr,
-               const unsigned int* __restrict__ pts_off, const unsigned int* __restrict__ vox_off,
-               const unsigned int* __restrict__ key, const unsigned int* __restrict__ rank,
-               const unsigned int* __restrict__ slots, double* __restrict__ out_x, double* __restrict__ out_y,
-               long long* __restrict__ out_count) {
+               const unsigned int* __restrict__ key, unsigned int* __restrict__ first,
+               const unsigned int* __restrict__ vrank, const unsigned int* __restrict__ soff,
+               const unsigned int* __restrict__ vcnt, const unsigned int* __restrict__ slots,
+               double* __restrict__ out_x, double* __restrict__ out_y, long long* __restrict__ out_count) {
     const long long n = hdr->n_points;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = n > 0 ? (long long)vox_off[hdr->cells] : 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = (long long)hdr->total_voxels;
     for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
-        if (rank[i] != 0u) continue;
         const unsigned int k = key[i];
-        const unsigned int b = pts_off[k], e = pts_off[k + 1];
-        double sx = 0.0, sy = 0.0;
-        long long last = -1;
-        for (unsigned int r = b; r < e; ++r) {          // selection by ascending index, O(cnt^2), cnt is tiny
+        if (first[k] != 0xffffffffu - (unsigned int)i) continue;
+        const unsigned int b = soff[i], e = b + vcnt[i];
+        double sx = px[i], sy = py[i];                  // the head has the smallest index of its voxel
+        long long last = i;
+        for (unsigned int r = b + 1; r < e; ++r) {      // selection by ascending index, O(cnt^2), cnt is tiny
             unsigned int best = 0xffffffffu;
             for (unsigned int q = b; q < e; ++q) {
                 const unsigned int idx = slots[q];
                 if ((long long)idx > last && idx < best) best = idx;
             }
             last = best;
-            if (r == b) { sx = px[best]; sy = py[best]; }
-            else { sx = OCC_DADD(sx, px[best]); sy = OCC_DADD(sy, py[best]); }
+            sx = OCC_DADD(sx, px[best]);
+            sy = OCC_DADD(sy, py[best]);
         }
         const double cnt = (double)(e - b);
-        out_x[vox_off[k]] = OCC_DDIV(sx, cnt);
-        out_y[vox_off[k]] = OCC_DDIV(sy, cnt);
+        out_x[vrank[i]] = OCC_DDIV(sx, cnt);
+        out_y[vrank[i]] = OCC_DDIV(sy, cnt);
     }
+}
+
+// first[] is cleared in its own pass: the reduce kernel's heads are still being looked up by
+// other threads of that kernel.
+__global__ void __launch_bounds__(kMT)
+k_voxel_clean(const VoxelHeader* __restrict__ hdr, const unsigned int* __restrict__ key, unsigned int* __restrict__ first) {
+    const long long n = hdr->n_points;
+    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) first[key[i]] = 0u;
 }
 
 // ---- a12: publish_global_map rasterise (:103-111) -----------------------------------------
@@ -423,6 +464,16 @@ static int grid_for(long long work_items) {
 using namespace occ;
 
 extern "C" {
+
+int mapmerge_count_occupied(const int8_t* d_grid, int64_t n_cells, int64_t* d_out, void* stream) {
+    if (!d_grid || !d_out || n_cells < 0) { set_last_error("mapmerge_count_occupied: bad arguments"); return OCCGRID_E_ARG; }
+    if (n_cells == 0) return OCCGRID_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfileScope ps(K_MERGE_EXTRACT, st, 1);
+    k_count_occupied<<<grid_for(n_cells / kCellsPerThread + 1), kMT, 0, st>>>(d_grid, n_cells, (long long*)d_out);
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
+}
 
 size_t mapmerge_extract_workspace_bytes(int64_t n_cells) {
     const int64_t blocks = (n_cells + kChunk - 1) / kChunk;
@@ -475,22 +526,21 @@ int mapmerge_bounds(const double* d_px, const double* d_py, const int64_t* d_cou
     return OCCGRID_OK;
 }
 
-// Workspace: header | counts/pts_off u32[cells+1] | vox_off u32[cells+1] | block_sums uint2[...] |
-//            key u32[points] | rank u32[points] | slots u32[points]
-static size_t voxel_layout(int64_t cells, int64_t points, size_t off[7]) {
+// Workspace: header | first u32[cells] | cnt u32[cells] | block_sums uint2[...] |
+//            key, vrank, soff, vcnt, slots: u32[points] each.
+// The two lattice planes must be zero on entry (zero the workspace once) and are zero again on exit.
+static size_t voxel_layout(int64_t cells, int64_t points, size_t off[9]) {
     size_t o = 0;
     off[0] = o; o += 256;
     off[1] = o; o += align_up((size_t)(cells + 1) * 4, 256);
     off[2] = o; o += align_up((size_t)(cells + 1) * 4, 256);
-    off[3] = o; o += align_up((size_t)((cells + 1 + kScanChunk - 1) / kScanChunk) * 8, 256);
-    off[4] = o; o += align_up((size_t)points * 4, 256);
-    off[5] = o; o += align_up((size_t)points * 4, 256);
-    off[6] = o; o += align_up((size_t)points * 4, 256);
+    off[3] = o; o += align_up((size_t)((points + kScanChunk - 1) / kScanChunk + 1) * 8, 256);
+    for (int j = 4; j < 9; ++j) { off[j] = o; o += align_up((size_t)points * 4, 256); }
     return o;
 }
 
 size_t mapmerge_voxel_workspace_bytes(int64_t lattice_capacity_cells, int64_t point_capacity) {
-    size_t off[7];
+    size_t off[9];
     return voxel_layout(lattice_capacity_cells, point_capacity, off);
 }
 
@@ -503,33 +553,34 @@ int mapmerge_voxel_downsample(const double* d_px, const double* d_py, const int6
         set_last_error("mapmerge_voxel_downsample: bad arguments");
         return OCCGRID_E_ARG;
     }
-    size_t off[7];
+    size_t off[9];
     if (ws_bytes < voxel_layout(lattice_capacity_cells, point_capacity, off)) {
         set_last_error("mapmerge_voxel_downsample: workspace too small");
         return OCCGRID_E_WORKSPACE;
     }
     char* ws = reinterpret_cast<char*>(d_ws);
     VoxelHeader* hdr = reinterpret_cast<VoxelHeader*>(ws + off[0]);
-    unsigned int* counts = reinterpret_cast<unsigned int*>(ws + off[1]);
-    unsigned int* vox_off = reinterpret_cast<unsigned int*>(ws + off[2]);
+    unsigned int* first = reinterpret_cast<unsigned int*>(ws + off[1]);
+    unsigned int* cnt = reinterpret_cast<unsigned int*>(ws + off[2]);
     uint2* block_sums = reinterpret_cast<uint2*>(ws + off[3]);
     unsigned int* key = reinterpret_cast<unsigned int*>(ws + off[4]);
-    unsigned int* rank = reinterpret_cast<unsigned int*>(ws + off[5]);
-    unsigned int* slots = reinterpret_cast<unsigned int*>(ws + off[6]);
+    unsigned int* vrank = reinterpret_cast<unsigned int*>(ws + off[5]);
+    unsigned int* soff = reinterpret_cast<unsigned int*>(ws + off[6]);
+    unsigned int* vcnt = reinterpret_cast<unsigned int*>(ws + off[7]);
+    unsigned int* slots = reinterpret_cast<unsigned int*>(ws + off[8]);
     cudaStream_t st = (cudaStream_t)stream;
     const int gp = grid_for(point_capacity);
-    const int gc = grid_for(lattice_capacity_cells / 4 + 1);
-    const int gs = grid_for((lattice_capacity_cells + 1 + kScanItems - 1) / kScanItems);
+    const int gs = grid_for((point_capacity + kScanItems - 1) / kScanItems);
     ProfileScope ps(K_MERGE_VOXEL, st, 8);
-    k_voxel_setup<<<1, 1, 0, st>>>(d_bounds, (const long long*)d_count, voxel, lattice_capacity_cells, hdr, d_status);
-    k_voxel_zero<<<gc, kMT, 0, st>>>(hdr, counts);
-    k_voxel_count<<<gp, kMT, 0, st>>>(d_px, d_py, voxel, hdr, counts, key, rank);
-    k_scan_partial<<<gs, kMT, 0, st>>>(counts, hdr, block_sums);
-    k_scan_top<<<1, 1024, 0, st>>>(block_sums, hdr);
-    k_scan_apply<<<gs, kMT, 0, st>>>(counts, vox_off, hdr, block_sums);
-    k_voxel_fill<<<gp, kMT, 0, st>>>(hdr, counts, key, rank, slots);
-    k_voxel_reduce<<<gp, kMT, 0, st>>>(d_px, d_py, hdr, counts, vox_off, key, rank, slots, d_out_px, d_out_py,
+    k_voxel_setup<<<1, 1, 0, st>>>(d_bounds, (const long long*)d_count, voxel, lattice_capacity_cells, point_capacity, hdr, d_status);
+    k_voxel_mark<<<gp, kMT, 0, st>>>(d_px, d_py, voxel, hdr, first, cnt, key);
+    k_pscan_partial<<<gs, kMT, 0, st>>>(hdr, key, first, cnt, block_sums);
+    k_pscan_top<<<1, 1024, 0, st>>>(block_sums, hdr);
+    k_pscan_apply<<<gs, kMT, 0, st>>>(hdr, key, first, cnt, block_sums, vrank, soff, vcnt);
+    k_voxel_fill<<<gp, kMT, 0, st>>>(hdr, key, first, cnt, soff, slots);
+    k_voxel_reduce<<<gp, kMT, 0, st>>>(d_px, d_py, hdr, key, first, vrank, soff, vcnt, slots, d_out_px, d_out_py,
                                        (long long*)d_out_count);
+    k_voxel_clean<<<gp, kMT, 0, st>>>(hdr, key, first);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
 }

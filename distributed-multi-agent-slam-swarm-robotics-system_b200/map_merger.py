@@ -81,15 +81,18 @@ class MapMerger:
         self._bounds = torch.zeros(4, dtype=torch.float64, device=self.device)
         self._last = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._ws = {}
+        self._lattice_cap = 0
+        self._voxel_points_cap = -1
 
     # ---- plumbing ------------------------------------------------------------------------
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def _workspace(self, name, nbytes):
+    def _workspace(self, name, nbytes, zero=False):
         t = self._ws.get(name)
         if t is None or t.numel() < nbytes:
-            t = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.device)
+            alloc = torch.zeros if zero else torch.empty
+            t = alloc(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.device)
             self._ws[name] = t
         return t
 
@@ -153,24 +156,34 @@ class MapMerger:
                                        self._bounds.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
         _native.check(rc, 'mapmerge_bounds')
 
-    def _voxel_downsample(self):
-        """global_pcd = global_pcd.voxel_down_sample(map_resolution)  (:60)"""
+    def _voxel_downsample(self, lattice_cells=None, sync=True):
+        """global_pcd = global_pcd.voxel_down_sample(map_resolution)  (:60).  `lattice_cells`: a
+        conservative bound on the voxel lattice known to the caller (batched merge, no host round
+        trip); otherwise the bounds are read back to size it."""
         self._bounds_of(self._cloud)
-        b = self._bounds.cpu().numpy()
         v = self.map_resolution
-        nx = int(math.floor((b[2] - (b[0] - v * 0.5)) / v)) + 1
-        ny = int(math.floor((b[3] - (b[1] - v * 0.5)) / v)) + 1
-        cells = nx * ny
-        need = self._lib.mapmerge_voxel_workspace_bytes(cells, self._cloud.capacity)
-        ws = self._workspace('voxel', need)
+        if lattice_cells is None:
+            b = self._bounds.cpu().numpy()
+            nx = int(math.floor((b[2] - (b[0] - v * 0.5)) / v)) + 1
+            ny = int(math.floor((b[3] - (b[1] - v * 0.5)) / v)) + 1
+            lattice_cells = nx * ny
+        # the lattice planes sit first in the workspace and must stay all-zero between calls, so
+        # the layout may only change together with a fresh (zeroed) allocation
+        if lattice_cells > self._lattice_cap or self._cloud.capacity != self._voxel_points_cap:
+            self._lattice_cap = max(int(lattice_cells * 1.5), self._lattice_cap)
+            self._voxel_points_cap = self._cloud.capacity
+            self._ws.pop('voxel', None)
+        need = self._lib.mapmerge_voxel_workspace_bytes(self._lattice_cap, self._cloud.capacity)
+        ws = self._workspace('voxel', need, zero=True)
         rc = self._lib.mapmerge_voxel_downsample(
             self._cloud.x.data_ptr(), self._cloud.y.data_ptr(), self._cloud.count.data_ptr(), self._cloud.capacity,
-            v, self._bounds.data_ptr(), cells, self._spare.x.data_ptr(), self._spare.y.data_ptr(),
+            v, self._bounds.data_ptr(), self._lattice_cap, self._spare.x.data_ptr(), self._spare.y.data_ptr(),
             self._spare.count.data_ptr(), self._status.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
         _native.check(rc, 'mapmerge_voxel_downsample')
         self._cloud, self._spare = self._spare, self._cloud
-        self._n_global = int(self._cloud.count.item())
-        self._check_status()
+        if sync:
+            self._n_global = int(self._cloud.count.item())
+            self._check_status()
 
     # ---- reference surface ---------------------------------------------------------------
     @property
@@ -248,17 +261,83 @@ class MapMerger:
     def merge(self, grids, origins, res, transforms=None, fitness=None, to_host=True):
         """Fuse A agent grids in order: ``grids`` int8 [A, H, W] (host or device), ``origins``
         float64 [A, 2], ``transforms`` [A, 4, 4] or [A, 3] (tx, ty, theta) or None (identity).
-        Equal to A successive ``map_callback`` calls; publishes once at the end.  Returns
-        (int8 grid [H', W'], (origin_x, origin_y))."""
-        for a in range(len(grids)):
-            h, w = grids[a].shape
-            msg = make_grid_msg(grids[a], w, h, res, origins[a][0], origins[a][1])
-            self._merge_one(msg, None if transforms is None else transforms[a],
-                            1.0 if fitness is None else fitness[a])
+        Equal to A successive ``map_callback`` calls (same sequential voxel chain, :58-60);
+        publishes once at the end.  Runs stream-ordered with two host synchronisations in total:
+        the occupied-cell counts up front (to size the cloud) and the final bounds.
+        Returns (int8 grid [H', W'], (origin_x, origin_y))."""
+        A = len(grids)
+        with torch.cuda.device(self.device):
+            dev = [self._device_grid(make_grid_msg(grids[a], grids[a].shape[1], grids[a].shape[0], res, 0, 0)) for a in range(A)]
+            counts = torch.zeros(A, dtype=torch.int64, device=self.device)
+            for a in range(A):
+                rc = self._lib.mapmerge_count_occupied(dev[a].data_ptr(), dev[a].numel(), counts[a:a + 1].data_ptr(), self._stream())
+                _native.check(rc, 'mapmerge_count_occupied')
+            n_occ = counts.cpu().tolist()                           # host sync 1
+            if self._n_global and self._cloud is not None:
+                self._bounds_of(self._cloud)
+                bb = self._bounds.cpu().numpy().tolist()
+            else:
+                bb = [math.inf, math.inf, -math.inf, -math.inf]
+            mats = []
+            first_seen = self._n_global > 0
+            for a in range(A):
+                T = None if transforms is None else transforms[a]
+                if T is not None and np.asarray(T).size == 3:
+                    T = se2_matrix(*np.asarray(T, np.float64).tolist())
+                f = 1.0 if fitness is None else fitness[a]
+                use = n_occ[a] > 0 and (not first_seen or f >= 0.6)
+                if use and not first_seen:
+                    T = None                                        # the first cloud is adopted as is (:40-43)
+                mats.append((use, T))
+                if use:
+                    h, w = dev[a].shape
+                    first_seen = True
+                    M = np.eye(4) if T is None else np.asarray(T, np.float64).reshape(4, 4)
+                    for cx in (origins[a][0], origins[a][0] + w * res):
+                        for cy in (origins[a][1], origins[a][1] + h * res):
+                            px = M[0, 0] * cx + M[0, 1] * cy + M[0, 3]
+                            py = M[1, 0] * cx + M[1, 1] * cy + M[1, 3]
+                            bb = [min(bb[0], px), min(bb[1], py), max(bb[2], px), max(bb[3], py)]
+            total = self._n_global + sum(n for n, (u, _) in zip(n_occ, mats) if u)
+            if total == 0:
+                return None, None
+            self._ensure_capacity(total + 1024)
+            first = self._n_global == 0
+            v = float(res) if first else self.map_resolution
+            cells = (int((bb[2] - bb[0]) / v) + 4) * (int((bb[3] - bb[1]) / v) + 4)
+            for a in range(A):
+                use, T = mats[a]
+                if not use:
+                    continue
+                h, w = dev[a].shape
+                msg = make_grid_msg(dev[a], w, h, res, origins[a][0], origins[a][1])
+                self._extract_async(msg, T)
+                if first:
+                    first = False
+                    self.map_resolution = float(res)
+                    self.map_origin = [float(origins[a][0]), float(origins[a][1])]
+                else:
+                    self._voxel_downsample(lattice_cells=cells, sync=False)
+            self._n_global = int(self._cloud.count.item())          # host sync 2 (with the status word)
+            self._check_status()
         out = self.publish_global_map(to_host=to_host)
         if out is None:
             return None, None
         return out.data, (out.info.origin.position.x, out.info.origin.position.y)
+
+    def _extract_async(self, msg, T):
+        """grid_to_pcd (+ transform) appended to the global cloud, no host read-back."""
+        g = self._device_grid(msg)
+        h, w = g.shape
+        ws = self._workspace('extract', self._lib.mapmerge_extract_workspace_bytes(h * w))
+        Tm = np.ascontiguousarray(np.asarray(T, np.float64).reshape(4, 4)) if T is not None else None
+        rc = self._lib.mapmerge_extract_transform(
+            g.data_ptr(), w, h, float(msg.info.resolution), float(msg.info.origin.position.x),
+            float(msg.info.origin.position.y), Tm.ctypes.data if Tm is not None else None,
+            self._cloud.x.data_ptr(), self._cloud.y.data_ptr(), self._cloud.capacity,
+            self._cloud.count.data_ptr(), self._last.data_ptr(), self._status.data_ptr(),
+            ws.data_ptr(), ws.numel(), self._stream())
+        _native.check(rc, 'mapmerge_extract_transform')
 
 
 def smoke():

@@ -213,6 +213,9 @@ int occgrid_route_packets_p2p(const occgrid_geom* geom, int n_bands, const int32
  * order, apply the 4x4 row-major transform `T_host` (HOST pointer; NULL = identity), and
  * append to the cloud at [*d_count, ...) (= `global_pcd += local_pcd`, :59).
  * *d_last_appended (optional) receives the number of points of this grid. */
+/* *d_out += number of cells with value > 50 (:72) — lets a batched merge size its cloud once. */
+int mapmerge_count_occupied(const int8_t* d_grid, int64_t n_cells, int64_t* d_out, void* stream);
+
 size_t mapmerge_extract_workspace_bytes(int64_t n_cells);
 int mapmerge_extract_transform(const int8_t* d_grid, int32_t width, int32_t height, double res,
                                double origin_x, double origin_y, const double* T_host,
@@ -228,7 +231,9 @@ int mapmerge_bounds(const double* d_px, const double* d_py, const int64_t* d_cou
 
 /* PointCloud::VoxelDownSample(voxel) (:60): voxel_min_bound = min_bound - 0.5*voxel, index =
  * floor((p - voxel_min_bound)/voxel), one output point per non-empty voxel = mean of its
- * points (summed in ascending point index), emitted in ascending (iy, ix) order.
+ * points (summed in ascending point index), emitted in order of first appearance (by smallest
+ * point index).  O(points): the lattice planes in the workspace are a lookup table that must be
+ * ZERO on entry (zero the workspace once) and is zero again on exit.
  * `d_bounds` must hold the bounds of the input cloud; the lattice of this call must fit
  * `lattice_capacity_cells`.  Output arrays must not alias the input. */
 size_t mapmerge_voxel_workspace_bytes(int64_t lattice_capacity_cells, int64_t point_capacity);

@@ -18,8 +18,9 @@ verbatim; the three Open3D calls are restated from Open3D's published algorithm
                       index = floor((p - voxel_min_bound) / v) per axis;
                       accumulate per voxel in point-index order; output = sum / count;
                       Open3D emits voxels in std::unordered_map order (unspecified) — this
-                      restatement (and the CUDA path) fixes the canonical order: ascending
-                      (iy, ix).                                              map_merger.py:60
+                      restatement (and the CUDA path) fixes the canonical order: first
+                      appearance (voxels ordered by their smallest point index, what an
+                      insertion-ordered map would produce).                  map_merger.py:60
 
 ICP (:45-56) is not restated: callers supply the rigid transform.
 """
@@ -67,7 +68,8 @@ def voxel_down_sample(px, py, voxel):
         m = counts > r
         sx[m] += px[order[starts[m] + r]]
         sy[m] += py[order[starts[m] + r]]
-    return sx / counts, sy / counts
+    appear = np.argsort(order[starts], kind='stable')  # canonical output order: first appearance
+    return (sx / counts)[appear], (sy / counts)[appear]
 
 
 def rasterise(px, py, res):

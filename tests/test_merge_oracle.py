@@ -58,10 +58,10 @@ def test_voxel_down_sample_means_and_order():
     assert x[0] == (0.0 + 0.01) / 2 and y[0] == (0.0 + 0.01) / 2
     assert x[1] == ((0.2 + 0.21) + 0.22) / 3
     assert (x[2], y[2]) == (1.0, 1.0)
-    # canonical order: ascending (iy, ix)
-    px = np.array([1.0, 0.0, 0.5]); py = np.array([0.0, 1.0, 0.0])
+    # canonical order: first appearance (voxels ordered by their smallest point index)
+    px = np.array([1.0, 0.0, 0.5, 1.01]); py = np.array([0.0, 1.0, 0.0, 0.01])
     x, y = MO.voxel_down_sample(px, py, 0.05)
-    assert x.tolist() == [0.5, 1.0, 0.0] and y.tolist() == [0.0, 0.0, 1.0]
+    assert x.tolist() == [(1.0 + 1.01) / 2, 0.0, 0.5] and y.tolist() == [(0.0 + 0.01) / 2, 1.0, 0.0]
 
 
 def test_sequence_is_deterministic_and_only_unknown_or_occupied():

@@ -224,12 +224,14 @@ k_bounds_final(const double* __restrict__ partial, int n_partial, double* __rest
 // all-zero between calls and cleaned by the very threads that dirtied them), never scanned:
 //   mark    every point i: key = voxel index; first[key] = max(first[key], ~i) (i.e. the SMALLEST
 //           index wins); cnt[key] += 1
-//   scan    over the POINTS (3 kernels): a point is its voxel's head iff first[key] == ~i; exclusive
-//           sums of [head] (-> output position: voxels come out in order of first appearance) and
-//           of [head ? cnt : 0] (-> slot range of the voxel)
-//   fill    every point drops its index into its voxel's slot range (cnt counts back to zero)
+//   gather  one lattice read per point -> head[i] (index of the first point of i's voxel) and
+//           hcnt[i] (voxel size if i is that head, else 0); the rest streams per-point arrays
+//   scan    over the POINTS (3 kernels): exclusive sums of [head] (-> output position: voxels come
+//           out in order of first appearance) and of hcnt (-> slot range of the voxel)
+//   fill    every point drops its index into its voxel's slot range; cnt counts back to zero and
+//           the thread that takes the last ticket clears first[key]
 //   reduce  every head visits its voxel's indices in ascending order, accumulates, divides
-//           (AccumulatedPoint::GetAveragePoint), writes the mean and clears first[key]
+//           (AccumulatedPoint::GetAveragePoint), writes the mean
 
 struct VoxelHeader {          // lives at the start of the voxel workspace
     double mbx, mby;          // voxel_min_bound = min_bound - 0.5 * voxel
@@ -259,10 +261,10 @@ __global__ void k_voxel_setup(const double* __restrict__ bounds, const long long
     *hdr = h;
 }
 
+// lattice[k] = {first, cnt} share one 8-byte slot (one sector per point per pass)
 __global__ void __launch_bounds__(kMT)
 k_voxel_mark(const double* __restrict__ px, const double* __restrict__ py, double voxel,
-             const VoxelHeader* __restrict__ hdr, unsigned int* __restrict__ first, unsigned int* __restrict__ cnt,
-             unsigned int* __restrict__ key) {
+             const VoxelHeader* __restrict__ hdr, uint2* __restrict__ lattice, unsigned int* __restrict__ key) {
     const long long n = hdr->n_points;
     const double mbx = hdr->mbx, mby = hdr->mby;
     const long long nx = hdr->nx;
@@ -271,27 +273,30 @@ k_voxel_mark(const double* __restrict__ px, const double* __restrict__ py, doubl
         const long long iy = (long long)floor(OCC_DDIV(OCC_DADD(py[i], -mby), voxel));
         const unsigned int k = (unsigned int)(iy * nx + ix);
         key[i] = k;
-        atomicMax(&first[k], 0xffffffffu - (unsigned int)i);
-        atomicAdd(&cnt[k], 1u);
+        atomicMax(&lattice[k].x, 0xffffffffu - (unsigned int)i);
+        atomicAdd(&lattice[k].y, 1u);
+    }
+}
+
+// One lattice read per point: head[i] = index of the first point of i's voxel; hcnt[i] = size of
+// the voxel when i is that head, else 0.  Everything downstream streams these per-point arrays.
+__global__ void __launch_bounds__(kMT)
+k_voxel_gather(const VoxelHeader* __restrict__ hdr, const uint2* __restrict__ lattice, const unsigned int* __restrict__ key,
+               unsigned int* __restrict__ head, unsigned int* __restrict__ hcnt) {
+    const long long n = hdr->n_points;
+    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
+        const uint2 v = lattice[key[i]];
+        const unsigned int h = 0xffffffffu - v.x;
+        head[i] = h;
+        hcnt[i] = (h == (unsigned int)i) ? v.y : 0u;
     }
 }
 
 constexpr int kScanItems = 8;
 constexpr int kScanChunk = kMT * kScanItems;
 
-__device__ __forceinline__ void head_values(long long i, long long n, const unsigned int* __restrict__ key,
-                                            const unsigned int* __restrict__ first, const unsigned int* __restrict__ cnt,
-                                            unsigned int* is_head, unsigned int* slots) {
-    *is_head = 0; *slots = 0;
-    if (i < n) {
-        const unsigned int k = key[i];
-        if (first[k] == 0xffffffffu - (unsigned int)i) { *is_head = 1u; *slots = cnt[k]; }
-    }
-}
-
 __global__ void __launch_bounds__(kMT)
-k_pscan_partial(const VoxelHeader* __restrict__ hdr, const unsigned int* __restrict__ key,
-                const unsigned int* __restrict__ first, const unsigned int* __restrict__ cnt, uint2* __restrict__ block_sums) {
+k_pscan_partial(const VoxelHeader* __restrict__ hdr, const unsigned int* __restrict__ hcnt, uint2* __restrict__ block_sums) {
     __shared__ unsigned int s_warp[33];
     const long long n = hdr->n_points;
     const long long nblocks = (n + kScanChunk - 1) / kScanChunk;
@@ -300,9 +305,8 @@ k_pscan_partial(const VoxelHeader* __restrict__ hdr, const unsigned int* __restr
         unsigned int s = 0, f = 0;
 #pragma unroll
         for (int j = 0; j < kScanItems; ++j) {
-            unsigned int h, c;
-            head_values(base + j, n, key, first, cnt, &h, &c);
-            f += h; s += c;
+            const unsigned int c = (base + j < n) ? hcnt[base + j] : 0u;
+            s += c; f += c ? 1u : 0u;
         }
         unsigned int ts, tf;
         block_exclusive_scan(s, s_warp, &ts);
@@ -333,23 +337,21 @@ k_pscan_top(uint2* __restrict__ block_sums, VoxelHeader* __restrict__ hdr) {
     if (threadIdx.x == 0) { hdr->total_slots = s_c0; hdr->total_voxels = s_c1; }
 }
 
-// Writes, for every head point i: out position vrank[i], slot offset soff[i], voxel size vcnt[i].
+// For every head point i: output position vrank[i] and slot offset soff[i].
 __global__ void __launch_bounds__(kMT)
-k_pscan_apply(const VoxelHeader* __restrict__ hdr, const unsigned int* __restrict__ key,
-              const unsigned int* __restrict__ first, const unsigned int* __restrict__ cnt,
-              const uint2* __restrict__ block_sums, unsigned int* __restrict__ vrank, unsigned int* __restrict__ soff,
-              unsigned int* __restrict__ vcnt) {
+k_pscan_apply(const VoxelHeader* __restrict__ hdr, const unsigned int* __restrict__ hcnt,
+              const uint2* __restrict__ block_sums, unsigned int* __restrict__ vrank, unsigned int* __restrict__ soff) {
     __shared__ unsigned int s_warp[33];
     const long long n = hdr->n_points;
     const long long nblocks = (n + kScanChunk - 1) / kScanChunk;
     for (long long b = blockIdx.x; b < nblocks; b += gridDim.x) {
         const long long base = b * kScanChunk + (long long)threadIdx.x * kScanItems;
-        unsigned int h[kScanItems], c[kScanItems];
+        unsigned int c[kScanItems];
         unsigned int s = 0, f = 0;
 #pragma unroll
         for (int j = 0; j < kScanItems; ++j) {
-            head_values(base + j, n, key, first, cnt, &h[j], &c[j]);
-            f += h[j]; s += c[j];
+            c[j] = (base + j < n) ? hcnt[base + j] : 0u;
+            s += c[j]; f += c[j] ? 1u : 0u;
         }
         unsigned int ts, tf;
         unsigned int es = block_exclusive_scan(s, s_warp, &ts);
@@ -359,62 +361,56 @@ k_pscan_apply(const VoxelHeader* __restrict__ hdr, const unsigned int* __restric
         ef += carry.y;
 #pragma unroll
         for (int j = 0; j < kScanItems; ++j) {
-            if (h[j]) { vrank[base + j] = ef; soff[base + j] = es; vcnt[base + j] = c[j]; }
+            if (c[j]) { vrank[base + j] = ef; soff[base + j] = es; }
             es += c[j];
-            ef += h[j];
+            ef += c[j] ? 1u : 0u;
         }
     }
 }
 
+// Every point drops its index into its voxel's slot range; the lattice slot is cleared by the
+// thread that takes the last ticket (cnt back to 0 -> first := 0), so the table is clean again.
 __global__ void __launch_bounds__(kMT)
-k_voxel_fill(const VoxelHeader* __restrict__ hdr, const unsigned int* __restrict__ key,
-             const unsigned int* __restrict__ first, unsigned int* __restrict__ cnt,
-             const unsigned int* __restrict__ soff, unsigned int* __restrict__ slots) {
+k_voxel_fill(const VoxelHeader* __restrict__ hdr, const unsigned int* __restrict__ key, uint2* __restrict__ lattice,
+             const unsigned int* __restrict__ head, const unsigned int* __restrict__ soff, unsigned int* __restrict__ slots) {
     const long long n = hdr->n_points;
     for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
         const unsigned int k = key[i];
-        const unsigned int head = 0xffffffffu - first[k];
-        const unsigned int r = atomicSub(&cnt[k], 1u) - 1u;       // cnt[k] is back to zero when the kernel ends
-        slots[soff[head] + r] = (unsigned int)i;
+        const unsigned int r = atomicSub(&lattice[k].y, 1u) - 1u;
+        if (r == 0u) lattice[k].x = 0u;                 // last ticket: nobody reads first[] any more
+        slots[soff[head[i]] + r] = (unsigned int)i;
     }
 }
 
 __global__ void __launch_bounds__(kMT)
 k_voxel_reduce(const double* __restrict__ px, const double* __restrict__ py, const VoxelHeader* __restrict__ hdr,
-               const unsigned int* __restrict__ key, unsigned int* __restrict__ first,
-               const unsigned int* __restrict__ vrank, const unsigned int* __restrict__ soff,
-               const unsigned int* __restrict__ vcnt, const unsigned int* __restrict__ slots,
+               const unsigned int* __restrict__ hcnt, const unsigned int* __restrict__ vrank,
+               const unsigned int* __restrict__ soff, const unsigned int* __restrict__ slots,
                double* __restrict__ out_x, double* __restrict__ out_y, long long* __restrict__ out_count) {
     const long long n = hdr->n_points;
     if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = (long long)hdr->total_voxels;
     for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
-        const unsigned int k = key[i];
-        if (first[k] != 0xffffffffu - (unsigned int)i) continue;
-        const unsigned int b = soff[i], e = b + vcnt[i];
+        const unsigned int c = hcnt[i];
+        if (c == 0u) continue;                          // not a head
         double sx = px[i], sy = py[i];                  // the head has the smallest index of its voxel
-        long long last = i;
-        for (unsigned int r = b + 1; r < e; ++r) {      // selection by ascending index, O(cnt^2), cnt is tiny
-            unsigned int best = 0xffffffffu;
-            for (unsigned int q = b; q < e; ++q) {
-                const unsigned int idx = slots[q];
-                if ((long long)idx > last && idx < best) best = idx;
+        if (c > 1u) {
+            const unsigned int b = soff[i], e = b + c;
+            long long last = i;
+            for (unsigned int r = b + 1; r < e; ++r) {  // selection by ascending index, O(cnt^2), cnt is tiny
+                unsigned int best = 0xffffffffu;
+                for (unsigned int q = b; q < e; ++q) {
+                    const unsigned int idx = slots[q];
+                    if ((long long)idx > last && idx < best) best = idx;
+                }
+                last = best;
+                sx = OCC_DADD(sx, px[best]);
+                sy = OCC_DADD(sy, py[best]);
             }
-            last = best;
-            sx = OCC_DADD(sx, px[best]);
-            sy = OCC_DADD(sy, py[best]);
         }
-        const double cnt = (double)(e - b);
+        const double cnt = (double)c;
         out_x[vrank[i]] = OCC_DDIV(sx, cnt);
         out_y[vrank[i]] = OCC_DDIV(sy, cnt);
     }
-}
-
-// first[] is cleared in its own pass: the reduce kernel's heads are still being looked up by
-// other threads of that kernel.
-__global__ void __launch_bounds__(kMT)
-k_voxel_clean(const VoxelHeader* __restrict__ hdr, const unsigned int* __restrict__ key, unsigned int* __restrict__ first) {
-    const long long n = hdr->n_points;
-    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) first[key[i]] = 0u;
 }
 
 // ---- a12: publish_global_map rasterise (:103-111) -----------------------------------------
@@ -526,16 +522,15 @@ int mapmerge_bounds(const double* d_px, const double* d_py, const int64_t* d_cou
     return OCCGRID_OK;
 }
 
-// Workspace: header | first u32[cells] | cnt u32[cells] | block_sums uint2[...] |
-//            key, vrank, soff, vcnt, slots: u32[points] each.
-// The two lattice planes must be zero on entry (zero the workspace once) and are zero again on exit.
+// Workspace: header | lattice uint2[cells] {first, cnt} | block_sums uint2[...] |
+//            key, head, hcnt, vrank, soff, slots: u32[points] each.
+// The lattice must be zero on entry (zero the workspace once) and is zero again on exit.
 static size_t voxel_layout(int64_t cells, int64_t points, size_t off[9]) {
     size_t o = 0;
     off[0] = o; o += 256;
-    off[1] = o; o += align_up((size_t)(cells + 1) * 4, 256);
-    off[2] = o; o += align_up((size_t)(cells + 1) * 4, 256);
-    off[3] = o; o += align_up((size_t)((points + kScanChunk - 1) / kScanChunk + 1) * 8, 256);
-    for (int j = 4; j < 9; ++j) { off[j] = o; o += align_up((size_t)points * 4, 256); }
+    off[1] = o; o += align_up((size_t)(cells + 1) * 8, 256);
+    off[2] = o; o += align_up((size_t)((points + kScanChunk - 1) / kScanChunk + 1) * 8, 256);
+    for (int j = 3; j < 9; ++j) { off[j] = o; o += align_up((size_t)points * 4, 256); }
     return o;
 }
 
@@ -560,27 +555,26 @@ int mapmerge_voxel_downsample(const double* d_px, const double* d_py, const int6
     }
     char* ws = reinterpret_cast<char*>(d_ws);
     VoxelHeader* hdr = reinterpret_cast<VoxelHeader*>(ws + off[0]);
-    unsigned int* first = reinterpret_cast<unsigned int*>(ws + off[1]);
-    unsigned int* cnt = reinterpret_cast<unsigned int*>(ws + off[2]);
-    uint2* block_sums = reinterpret_cast<uint2*>(ws + off[3]);
-    unsigned int* key = reinterpret_cast<unsigned int*>(ws + off[4]);
-    unsigned int* vrank = reinterpret_cast<unsigned int*>(ws + off[5]);
-    unsigned int* soff = reinterpret_cast<unsigned int*>(ws + off[6]);
-    unsigned int* vcnt = reinterpret_cast<unsigned int*>(ws + off[7]);
+    uint2* lattice = reinterpret_cast<uint2*>(ws + off[1]);
+    uint2* block_sums = reinterpret_cast<uint2*>(ws + off[2]);
+    unsigned int* key = reinterpret_cast<unsigned int*>(ws + off[3]);
+    unsigned int* head = reinterpret_cast<unsigned int*>(ws + off[4]);
+    unsigned int* hcnt = reinterpret_cast<unsigned int*>(ws + off[5]);
+    unsigned int* vrank = reinterpret_cast<unsigned int*>(ws + off[6]);
+    unsigned int* soff = reinterpret_cast<unsigned int*>(ws + off[7]);
     unsigned int* slots = reinterpret_cast<unsigned int*>(ws + off[8]);
     cudaStream_t st = (cudaStream_t)stream;
     const int gp = grid_for(point_capacity);
     const int gs = grid_for((point_capacity + kScanItems - 1) / kScanItems);
     ProfileScope ps(K_MERGE_VOXEL, st, 8);
     k_voxel_setup<<<1, 1, 0, st>>>(d_bounds, (const long long*)d_count, voxel, lattice_capacity_cells, point_capacity, hdr, d_status);
-    k_voxel_mark<<<gp, kMT, 0, st>>>(d_px, d_py, voxel, hdr, first, cnt, key);
-    k_pscan_partial<<<gs, kMT, 0, st>>>(hdr, key, first, cnt, block_sums);
+    k_voxel_mark<<<gp, kMT, 0, st>>>(d_px, d_py, voxel, hdr, lattice, key);
+    k_voxel_gather<<<gp, kMT, 0, st>>>(hdr, lattice, key, head, hcnt);
+    k_pscan_partial<<<gs, kMT, 0, st>>>(hdr, hcnt, block_sums);
     k_pscan_top<<<1, 1024, 0, st>>>(block_sums, hdr);
-    k_pscan_apply<<<gs, kMT, 0, st>>>(hdr, key, first, cnt, block_sums, vrank, soff, vcnt);
-    k_voxel_fill<<<gp, kMT, 0, st>>>(hdr, key, first, cnt, soff, slots);
-    k_voxel_reduce<<<gp, kMT, 0, st>>>(d_px, d_py, hdr, key, first, vrank, soff, vcnt, slots, d_out_px, d_out_py,
-                                       (long long*)d_out_count);
-    k_voxel_clean<<<gp, kMT, 0, st>>>(hdr, key, first);
+    k_pscan_apply<<<gs, kMT, 0, st>>>(hdr, hcnt, block_sums, vrank, soff);
+    k_voxel_fill<<<gp, kMT, 0, st>>>(hdr, key, lattice, head, soff, slots);
+    k_voxel_reduce<<<gp, kMT, 0, st>>>(d_px, d_py, hdr, hcnt, vrank, soff, slots, d_out_px, d_out_py, (long long*)d_out_count);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
 }

@@ -13,7 +13,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_PATH = os.path.join(PKG_DIR, 'liboccgrid_b200.so')
-SOURCES = ['occgrid_integrate.cu', 'occgrid_tiled.cu', 'occgrid_route.cu', 'mapmerge.cu']
+SOURCES = ['occgrid_integrate.cu', 'occgrid_tiled.cu', 'occgrid_route.cu', 'mapmerge.cu', 'frontier.cu']
 HEADERS = ['common.cuh', 'beam_expand.cuh', 'sincos_dd.cuh', os.path.join('..', '..', 'include', 'occgrid_b200.h')]
 
 STRATEGY = {'auto': -1, 'global_atomic': 0, 'tiled': 1}
@@ -94,6 +94,13 @@ def lib():
     L.occgrid_integrate_poses.argtypes = [gp, vp, i64, i32, vp, vp, sz, vp, i32, vp]
     L.occgrid_route_packets_p2p.restype = i32
     L.occgrid_route_packets_p2p.argtypes = [gp, i32, vp, vp, i64, i32, i32, vp, vp, vp, i32, u32, vp, vp, i64, vp, vp, vp]
+    L.occgrid_frontier_workspace_bytes.restype = sz
+    L.occgrid_frontier_workspace_bytes.argtypes = [i64, i64]
+    L.occgrid_frontiers.restype = i32
+    L.occgrid_frontiers.argtypes = [vp, i32, i32, vp, i64, vp, vp, vp, sz, vp]
+    L.occgrid_frontier_clusters.restype = i32
+    L.occgrid_frontier_clusters.argtypes = [vp, vp, i64, i32, i32, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp, vp,
+                                            vp, sz, vp]
     L.occgrid_set_raycast_ctas_per_sm.restype = i32
     L.occgrid_set_raycast_ctas_per_sm.argtypes = [i32]
     L.occgrid_profile_begin.restype = i32
@@ -128,7 +135,7 @@ def _bind_merge(L):
 
 KERNEL_NAMES = ('integrate_global', 'resolve', 'update_rays', 'tile_count', 'tile_scan', 'tile_scatter',
                 'tile_raycast', 'tile_resolve', 'merge_extract', 'merge_bounds', 'merge_voxel', 'merge_raster',
-                'merge_fuse', 'probe', 'route')
+                'merge_fuse', 'probe', 'route', 'frontier', 'frontier_cluster')
 
 
 def profile_begin():

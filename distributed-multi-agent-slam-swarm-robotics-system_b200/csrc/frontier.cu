@@ -1,0 +1,289 @@
+// Frontier detection and clustering on the device-resident grid.
+//
+// Reference: OccupancyGrid.get_frontiers / cluster_frontiers / cluster_centroid_world,
+// server_nodes/dual_bot_mapper.py:181-237, driven every 3 s from main() (:948-956):
+//   * a frontier cell is an interior FREE cell (1 <= x,y <= size-2, :187-190) with at least one
+//     UNKNOWN 4-neighbour (:193-196); the list is in row-major scan order;
+//   * clusters are the 4-connected components of the frontier set (:214-226), emitted in the
+//     order of their first cell in that list (:210), components smaller than
+//     FRONTIER_MIN_CLUSTER are dropped (:228-229);
+//   * a centroid is grid_to_world(mean x, mean y) (:233-237).
+// The reference's BFS also fixes the order of cells INSIDE a cluster; nothing downstream
+// depends on it (only the centroid is used, :953), so clusters here list their cells in scan
+// order.
+//
+// Kernels: stencil + ordered compaction (count / single-CTA scan / write), union-find over the
+// compact frontier list (neighbours found by index arithmetic and binary search in the sorted
+// list, union by smaller index so that a component's root IS its first cell), per-root integer
+// sums, ordered compaction of the surviving roots and fp64 centroids.
+#include "common.cuh"
+
+namespace occ {
+
+constexpr int kFT = 256;
+constexpr int kFCells = 16;                 // cells per thread
+constexpr int kFChunk = kFT * kFCells;
+
+__device__ __forceinline__ unsigned int frontier_mask16(const int8_t* __restrict__ g, int w, int h, long long base, long long n) {
+    unsigned int mask = 0;
+#pragma unroll 4
+    for (int i = 0; i < kFCells; ++i) {
+        const long long c = base + i;
+        if (c >= n) break;
+        const int y = (int)(c / w), x = (int)(c - (long long)y * w);
+        if (x < 1 || y < 1 || x > w - 2 || y > h - 2) continue;                       // :187-188
+        if (g[c] != OCCGRID_CELL_FREE) continue;                                     // :189
+        if (g[c - 1] == OCCGRID_CELL_UNKNOWN || g[c + 1] == OCCGRID_CELL_UNKNOWN ||
+            g[c - w] == OCCGRID_CELL_UNKNOWN || g[c + w] == OCCGRID_CELL_UNKNOWN)     // :193-196
+            mask |= 1u << i;
+    }
+    return mask;
+}
+
+__device__ __forceinline__ unsigned int block_scan_excl(unsigned int v, unsigned int* s_warp /* 33 */, unsigned int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned int wv = (lane < (int)(blockDim.x >> 5)) ? s_warp[lane] : 0u, winc = wv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+        s_warp[lane] = winc - wv;
+        if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    const unsigned int r = s_warp[warp] + inc - v;
+    *total = s_warp[32];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kFT)
+k_frontier_count(const int8_t* __restrict__ g, int w, int h, unsigned int* __restrict__ block_counts) {
+    __shared__ unsigned int s_warp[33];
+    const long long n = (long long)w * h;
+    const long long base = ((long long)blockIdx.x * kFT + threadIdx.x) * kFCells;
+    unsigned int total;
+    block_scan_excl(base < n ? __popc(frontier_mask16(g, w, h, base, n)) : 0u, s_warp, &total);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024)
+k_frontier_reserve(unsigned int* __restrict__ block_counts, int n_blocks, long long capacity,
+                   long long* __restrict__ d_count, int* __restrict__ status) {
+    __shared__ unsigned int s_warp[33];
+    __shared__ unsigned int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int start = 0; start < n_blocks; start += blockDim.x) {
+        const int i = start + threadIdx.x;
+        const unsigned int v = i < n_blocks ? block_counts[i] : 0u;
+        unsigned int total;
+        const unsigned int ex = block_scan_excl(v, s_warp, &total);
+        if (i < n_blocks) block_counts[i] = s_carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        long long total = s_carry;
+        if (total > capacity) { atomicOr(status, 1); total = 0; }
+        *d_count = total;
+    }
+}
+
+__global__ void __launch_bounds__(kFT)
+k_frontier_write(const int8_t* __restrict__ g, int w, int h, const unsigned int* __restrict__ block_offsets,
+                 const long long* __restrict__ d_count, int2* __restrict__ xy) {
+    __shared__ unsigned int s_warp[33];
+    if (*d_count == 0) return;
+    const long long n = (long long)w * h;
+    const long long base = ((long long)blockIdx.x * kFT + threadIdx.x) * kFCells;
+    unsigned int m = base < n ? frontier_mask16(g, w, h, base, n) : 0u;
+    unsigned int total;
+    long long dst = block_offsets[blockIdx.x] + block_scan_excl(__popc(m), s_warp, &total);
+    while (m) {
+        const int i = __ffs(m) - 1;
+        m &= m - 1;
+        const long long c = base + i;
+        const int y = (int)(c / w);
+        xy[dst++] = make_int2((int)(c - (long long)y * w), y);                      // (x, y) tuples, :197
+    }
+}
+
+// ---- union-find over the compact, row-major-sorted frontier list --------------------------
+
+__device__ __forceinline__ unsigned int uf_find(unsigned int* __restrict__ parent, unsigned int i) {
+    volatile unsigned int* vp = parent;
+    for (;;) {
+        const unsigned int p = vp[i];
+        if (p == i) return i;
+        const unsigned int gp = vp[p];
+        if (gp != p) atomicMin(&parent[i], gp);      // path halving; parents only ever decrease
+        i = p;
+    }
+}
+
+__device__ __forceinline__ void uf_union(unsigned int* __restrict__ parent, unsigned int a, unsigned int b) {
+    for (;;) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a > b) { const unsigned int t = a; a = b; b = t; }        // smaller index becomes the root
+        const unsigned int old = atomicMin(&parent[b], a);
+        if (old == b) return;
+        b = old;                                                     // somebody else re-parented b: retry
+    }
+}
+
+// index of linear cell `lin` in the sorted list, or -1
+__device__ __forceinline__ long long find_cell(const int2* __restrict__ xy, long long n, int w, long long lin) {
+    long long lo = 0, hi = n - 1;
+    while (lo <= hi) {
+        const long long mid = (lo + hi) >> 1;
+        const int2 c = xy[mid];
+        const long long v = (long long)c.y * w + c.x;
+        if (v == lin) return mid;
+        if (v < lin) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(kFT)
+k_cluster_init(const long long* __restrict__ d_count, unsigned int* __restrict__ parent, unsigned int* __restrict__ csize,
+               long long* __restrict__ sx, long long* __restrict__ sy) {
+    const long long n = *d_count;
+    for (long long i = (long long)blockIdx.x * kFT + threadIdx.x; i < n; i += (long long)gridDim.x * kFT) {
+        parent[i] = (unsigned int)i; csize[i] = 0u; sx[i] = 0; sy[i] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kFT)
+k_cluster_union(const int2* __restrict__ xy, const long long* __restrict__ d_count, int w, unsigned int* __restrict__ parent) {
+    const long long n = *d_count;
+    for (long long i = (long long)blockIdx.x * kFT + threadIdx.x; i < n; i += (long long)gridDim.x * kFT) {
+        const int2 c = xy[i];
+        if (i > 0) {                                                  // left neighbour is the previous list entry, if present
+            const int2 p = xy[i - 1];
+            if (p.y == c.y && p.x == c.x - 1) uf_union(parent, (unsigned int)i, (unsigned int)(i - 1));
+        }
+        const long long up = find_cell(xy, i, w, (long long)(c.y - 1) * w + c.x);   // upper neighbour precedes i
+        if (up >= 0) uf_union(parent, (unsigned int)i, (unsigned int)up);
+    }
+}
+
+__global__ void __launch_bounds__(kFT)
+k_cluster_stats(const int2* __restrict__ xy, const long long* __restrict__ d_count, unsigned int* __restrict__ parent,
+                int* __restrict__ label, unsigned int* __restrict__ csize, long long* __restrict__ sx, long long* __restrict__ sy) {
+    const long long n = *d_count;
+    for (long long i = (long long)blockIdx.x * kFT + threadIdx.x; i < n; i += (long long)gridDim.x * kFT) {
+        const unsigned int r = uf_find(parent, (unsigned int)i);
+        label[i] = (int)r;
+        const int2 c = xy[i];
+        atomicAdd(&csize[r], 1u);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&sx[r]), (unsigned long long)c.x);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&sy[r]), (unsigned long long)c.y);
+    }
+}
+
+// Single CTA: ordered compaction of roots with at least `min_cluster` cells; centroid = :233-237.
+__global__ void __launch_bounds__(1024)
+k_cluster_emit(const long long* __restrict__ d_count, const int* __restrict__ label, const unsigned int* __restrict__ csize,
+               const long long* __restrict__ sx, const long long* __restrict__ sy, int min_cluster, double ox, double oy,
+               double res, int* __restrict__ cluster_root, int* __restrict__ cluster_size, double* __restrict__ centroids,
+               long long* __restrict__ n_clusters) {
+    __shared__ unsigned int s_warp[33];
+    __shared__ unsigned int s_carry;
+    const long long n = *d_count;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (long long start = 0; start < n; start += blockDim.x) {
+        const long long i = start + threadIdx.x;
+        const bool keep = i < n && label[i] == (int)i && csize[i] >= (unsigned int)min_cluster;      // :228
+        unsigned int total;
+        const unsigned int pos = s_carry + block_scan_excl(keep ? 1u : 0u, s_warp, &total);
+        if (keep) {
+            const double cnt = (double)csize[i];
+            const double ax = OCC_DDIV((double)sx[i], cnt), ay = OCC_DDIV((double)sy[i], cnt);          // :235-236
+            cluster_root[pos] = (int)i;
+            cluster_size[pos] = (int)csize[i];
+            centroids[2 * pos + 0] = OCC_DADD(ox, OCC_DMUL(OCC_DADD(ax, 0.5), res));                      // grid_to_world, :129
+            centroids[2 * pos + 1] = OCC_DADD(oy, OCC_DMUL(OCC_DADD(ay, 0.5), res));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_clusters = s_carry;
+}
+
+static int fgrid(long long items) {
+    long long b = (items + kFT - 1) / kFT;
+    if (b < 1) b = 1;
+    if (b > 148 * 16) b = 148 * 16;
+    return (int)b;
+}
+
+}  // namespace occ
+
+using namespace occ;
+
+extern "C" {
+
+size_t occgrid_frontier_workspace_bytes(int64_t n_cells, int64_t max_frontiers) {
+    const int64_t blocks = (n_cells + kFChunk - 1) / kFChunk;
+    return align_up((size_t)blocks * 4, 256) + align_up((size_t)max_frontiers * 4, 256) * 2 + align_up((size_t)max_frontiers * 8, 256) * 2 + 256;
+}
+
+int occgrid_frontiers(const int8_t* d_grid, int32_t width, int32_t height, int32_t* d_xy, int64_t capacity,
+                      int64_t* d_count, int32_t* d_status, void* d_ws, size_t ws_bytes, void* stream) {
+    if (!d_grid || !d_xy || !d_count || !d_status || !d_ws || width < 3 || height < 3 || capacity <= 0) {
+        set_last_error("occgrid_frontiers: bad arguments");
+        return OCCGRID_E_ARG;
+    }
+    const long long n = (long long)width * height;
+    if (ws_bytes < occgrid_frontier_workspace_bytes(n, capacity)) { set_last_error("occgrid_frontiers: workspace too small"); return OCCGRID_E_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = (int)((n + kFChunk - 1) / kFChunk);
+    unsigned int* block_counts = reinterpret_cast<unsigned int*>(d_ws);
+    ProfileScope ps(K_FRONTIER, st, 3);
+    k_frontier_count<<<blocks, kFT, 0, st>>>(d_grid, width, height, block_counts);
+    k_frontier_reserve<<<1, 1024, 0, st>>>(block_counts, blocks, capacity, (long long*)d_count, d_status);
+    k_frontier_write<<<blocks, kFT, 0, st>>>(d_grid, width, height, block_counts, (const long long*)d_count, reinterpret_cast<int2*>(d_xy));
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
+}
+
+int occgrid_frontier_clusters(const int32_t* d_xy, const int64_t* d_count, int64_t capacity, int32_t width, int32_t min_cluster,
+                              double ox, double oy, double res, int32_t* d_label, int32_t* d_cluster_root,
+                              int32_t* d_cluster_size, double* d_centroids, int64_t* d_n_clusters,
+                              void* d_ws, size_t ws_bytes, void* stream) {
+    if (!d_xy || !d_count || !d_label || !d_cluster_root || !d_cluster_size || !d_centroids || !d_n_clusters || !d_ws ||
+        capacity <= 0 || width < 3) {
+        set_last_error("occgrid_frontier_clusters: bad arguments");
+        return OCCGRID_E_ARG;
+    }
+    const size_t a4 = align_up((size_t)capacity * 4, 256), a8 = align_up((size_t)capacity * 8, 256);
+    if (ws_bytes < 2 * a4 + 2 * a8) { set_last_error("occgrid_frontier_clusters: workspace too small"); return OCCGRID_E_WORKSPACE; }
+    char* ws = reinterpret_cast<char*>(d_ws);
+    unsigned int* parent = reinterpret_cast<unsigned int*>(ws);
+    unsigned int* csize = reinterpret_cast<unsigned int*>(ws + a4);
+    long long* sx = reinterpret_cast<long long*>(ws + 2 * a4);
+    long long* sy = reinterpret_cast<long long*>(ws + 2 * a4 + a8);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = fgrid(capacity);
+    const int2* xy = reinterpret_cast<const int2*>(d_xy);
+    ProfileScope ps(K_FRONTIER_CLUSTER, st, 4);
+    k_cluster_init<<<g, kFT, 0, st>>>((const long long*)d_count, parent, csize, sx, sy);
+    k_cluster_union<<<g, kFT, 0, st>>>(xy, (const long long*)d_count, width, parent);
+    k_cluster_stats<<<g, kFT, 0, st>>>(xy, (const long long*)d_count, parent, d_label, csize, sx, sy);
+    k_cluster_emit<<<1, 1024, 0, st>>>((const long long*)d_count, d_label, csize, sx, sy, min_cluster, ox, oy, res,
+                                       d_cluster_root, d_cluster_size, d_centroids, (long long*)d_n_clusters);
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
+}
+
+}  // extern "C"

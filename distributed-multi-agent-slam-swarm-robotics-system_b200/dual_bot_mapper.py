@@ -53,6 +53,10 @@ CELL_UNKNOWN = -1
 CELL_FREE = 0
 CELL_OCCUPIED = 100
 
+# -- frontier constants (:102-103) ---------------------------------------------
+FRONTIER_MIN_CLUSTER = 3
+FRONTIER_SEPARATION = 1.0
+
 # -- SLAM constants (:97-99) ---------------------------------------------------
 CLOSURE_RADIUS = 0.60
 MIN_POSES_BETWEEN = 30
@@ -116,6 +120,7 @@ class OccupancyGrid:
         self._pinned = None
         self._copy_stream = None
         self._tab_cache = None
+        self._fr = None
         self._ensure_workspace(int(max_batch))
 
     # ---- workspace -----------------------------------------------------------------------
@@ -376,6 +381,94 @@ class OccupancyGrid:
                                                    self._strategy, self._stream())
             _native.check(rc, 'occgrid_integrate_poses')
         self._host_cache = None
+
+    # ---- frontiers (:181-237) — SURVEY §8 row f1 -------------------------------------------
+    def _frontier_buffers(self, capacity):
+        if self.window != (0, 0, self.size, self.size):
+            raise OccGridError('frontier detection needs the whole grid (not a window of it)')
+        if self._fr is None or self._fr['cap'] < capacity:
+            n = self.size * self.size
+            nb = self._lib.occgrid_frontier_workspace_bytes(n, capacity)
+            with torch.cuda.device(self.device):
+                self._fr = {
+                    'cap': capacity,
+                    'xy': torch.empty((capacity, 2), dtype=torch.int32, device=self.device),
+                    'count': torch.zeros(1, dtype=torch.int64, device=self.device),
+                    'status': torch.zeros(1, dtype=torch.int32, device=self.device),
+                    'ws': torch.empty(nb, dtype=torch.uint8, device=self.device),
+                    'label': torch.empty(capacity, dtype=torch.int32, device=self.device),
+                    'root': torch.empty(capacity, dtype=torch.int32, device=self.device),
+                    'size': torch.empty(capacity, dtype=torch.int32, device=self.device),
+                    'cent': torch.empty((capacity, 2), dtype=torch.float64, device=self.device),
+                    'ncl': torch.zeros(1, dtype=torch.int64, device=self.device),
+                }
+        return self._fr
+
+    def _detect_frontiers(self):
+        """Runs the frontier stencil on the device; returns (buffers, count)."""
+        cap = max(1 << 16, self.size * 8)
+        while True:
+            f = self._frontier_buffers(cap)
+            with torch.cuda.device(self.device):
+                rc = self._lib.occgrid_frontiers(self.grid_tensor.data_ptr(), self.size, self.size, f['xy'].data_ptr(), f['cap'],
+                                                 f['count'].data_ptr(), f['status'].data_ptr(), f['ws'].data_ptr(), f['ws'].numel(),
+                                                 self._stream())
+                _native.check(rc, 'occgrid_frontiers')
+                host = torch.cat([f['count'], f['status'].to(torch.int64)]).cpu().tolist()
+            if host[1] & 1:                       # more frontier cells than the buffer holds: grow and redo
+                f['status'].zero_()
+                cap *= 4
+                continue
+            return f, int(host[0])
+
+    def get_frontiers(self):
+        """:181-197 — FREE interior cells with an UNKNOWN 4-neighbour, as (gx, gy) tuples in the
+        reference's row-major scan order."""
+        f, n = self._detect_frontiers()
+        xy = f['xy'][:n].cpu().numpy()
+        return [(int(x), int(y)) for x, y in xy]
+
+    def _cluster(self, min_cluster=FRONTIER_MIN_CLUSTER):
+        f, n = self._detect_frontiers()
+        with torch.cuda.device(self.device):
+            rc = self._lib.occgrid_frontier_clusters(
+                f['xy'].data_ptr(), f['count'].data_ptr(), f['cap'], self.size, int(min_cluster), self.ox, self.oy, self.res,
+                f['label'].data_ptr(), f['root'].data_ptr(), f['size'].data_ptr(), f['cent'].data_ptr(), f['ncl'].data_ptr(),
+                f['ws'].data_ptr(), f['ws'].numel(), self._stream())
+            _native.check(rc, 'occgrid_frontier_clusters')
+            k = int(f['ncl'].item())
+        return f, n, k
+
+    def cluster_frontiers(self, frontier_cells=None):
+        """:199-231 — 4-connected components of the current frontier set, in the reference's
+        cluster order (by first cell), clusters below FRONTIER_MIN_CLUSTER dropped.  Cells inside a
+        cluster are listed in scan order (the reference lists them in BFS order; only the centroid
+        is consumed downstream, :953).  ``frontier_cells`` is accepted for signature parity and
+        must be the list ``get_frontiers()`` returns for the current grid."""
+        f, n, k = self._cluster()
+        if frontier_cells is not None and len(frontier_cells) != n:
+            raise ValueError('frontier_cells does not match the current grid (use get_frontiers())')
+        if k == 0:
+            return []
+        xy = f['xy'][:n].cpu().numpy()
+        label = f['label'][:n].cpu().numpy()
+        roots = f['root'][:k].cpu().numpy()
+        order = np.argsort(label, kind='stable')
+        starts = np.searchsorted(label[order], roots, side='left')
+        sizes = f['size'][:k].cpu().numpy()
+        return [[(int(x), int(y)) for x, y in xy[order[s:s + c]]] for s, c in zip(starts, sizes)]
+
+    def cluster_centroid_world(self, cluster):
+        """:233-237"""
+        avg_x = sum(c[0] for c in cluster) / len(cluster)
+        avg_y = sum(c[1] for c in cluster) / len(cluster)
+        return self.grid_to_world(avg_x, avg_y)
+
+    def frontier_centroids(self):
+        """The periodic step of main() (:950-954) in one device pass: get_frontiers ->
+        cluster_frontiers -> [cluster_centroid_world(c) for c in clusters]."""
+        f, n, k = self._cluster()
+        return [(float(x), float(y)) for x, y in f['cent'][:k].cpu().numpy()]
 
     # ---- bookkeeping ---------------------------------------------------------------------
     def counters(self, reset=False):

@@ -254,6 +254,29 @@ int mapmerge_rasterise(const double* d_px, const double* d_py, const int64_t* d_
  * of the multi-GPU fuse; the cross-GPU half is an NCCL max-reduction on int8. */
 int mapmerge_fuse_max(int8_t* d_dst, const int8_t* d_src, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ *  Frontier detection and clustering — dual_bot_mapper.py:181-237, :948-956
+ * ---------------------------------------------------------------------------------------- */
+
+/* OccupancyGrid.get_frontiers (:181-197) on a full height x width int8 grid: interior FREE cells
+ * with an UNKNOWN 4-neighbour, written as (x, y) int32 pairs in row-major scan order.
+ * *d_count receives the number found; d_status bit 0 = more than `capacity`. */
+size_t occgrid_frontier_workspace_bytes(int64_t n_cells, int64_t max_frontiers);
+int occgrid_frontiers(const int8_t* d_grid, int32_t width, int32_t height, int32_t* d_xy,
+                      int64_t capacity, int64_t* d_count, int32_t* d_status,
+                      void* d_ws, size_t ws_bytes, void* stream);
+
+/* cluster_frontiers (:199-231) + cluster_centroid_world (:233-237) on the list produced above:
+ * 4-connected components; d_label[i] = list index of the first cell of i's component; clusters
+ * with at least `min_cluster` cells (FRONTIER_MIN_CLUSTER = 3, :102) are emitted in order of
+ * their first cell: d_cluster_root (list index), d_cluster_size, d_centroids (world x, y).
+ * Workspace: occgrid_frontier_workspace_bytes. */
+int occgrid_frontier_clusters(const int32_t* d_xy, const int64_t* d_count, int64_t capacity,
+                              int32_t width, int32_t min_cluster, double ox, double oy, double res,
+                              int32_t* d_label, int32_t* d_cluster_root, int32_t* d_cluster_size,
+                              double* d_centroids, int64_t* d_n_clusters,
+                              void* d_ws, size_t ws_bytes, void* stream);
+
 /* Tuning knob of the TILED strategy: cap the persistent raycast CTAs per SM (0 = as many as fit,
  * the default).  A pipelined multi-GPU ingest lowers it to 2 so that the routing kernel of the
  * next batch finds room on every SM and runs concurrently.  Process-wide. */
@@ -268,7 +291,8 @@ enum {
     OCCGRID_K_INTEGRATE_GLOBAL = 0, OCCGRID_K_RESOLVE, OCCGRID_K_UPDATE_RAYS, OCCGRID_K_TILE_COUNT,
     OCCGRID_K_TILE_SCAN, OCCGRID_K_TILE_SCATTER, OCCGRID_K_TILE_RAYCAST, OCCGRID_K_TILE_RESOLVE,
     OCCGRID_K_MERGE_EXTRACT, OCCGRID_K_MERGE_BOUNDS, OCCGRID_K_MERGE_VOXEL, OCCGRID_K_MERGE_RASTER,
-    OCCGRID_K_MERGE_FUSE, OCCGRID_K_PROBE, OCCGRID_K_ROUTE, OCCGRID_K_N_KERNELS
+    OCCGRID_K_MERGE_FUSE, OCCGRID_K_PROBE, OCCGRID_K_ROUTE, OCCGRID_K_FRONTIER, OCCGRID_K_FRONTIER_CLUSTER,
+    OCCGRID_K_N_KERNELS
 };
 int occgrid_profile_begin(void);
 int occgrid_profile_end(double* ms_by_kernel, int64_t* launches_by_kernel, int n_slots);

@@ -121,6 +121,73 @@ class OracleGrid:
                 g[gy, gx] = CELL_OCCUPIED
 
 
+FRONTIER_MIN_CLUSTER = 3      # dual_bot_mapper.py:102
+
+
+def get_frontiers(grid_array):
+    """OccupancyGrid.get_frontiers — dual_bot_mapper.py:181-197 (loop restated verbatim)."""
+    g = grid_array
+    size = g.shape[0]
+    frontiers = []
+    for y in range(1, size - 1):
+        for x in range(1, size - 1):
+            if g[y, x] != CELL_FREE:
+                continue
+            for dx, dy in [(-1, 0), (1, 0), (0, -1), (0, 1)]:
+                if g[y + dy, x + dx] == CELL_UNKNOWN:
+                    frontiers.append((x, y))
+                    break
+    return frontiers
+
+
+def get_frontiers_fast(grid_array):
+    """Vectorised equivalent of get_frontiers for large grids (checked against it in the tests)."""
+    g = np.asarray(grid_array)
+    free = g == CELL_FREE
+    unk = g == CELL_UNKNOWN
+    nb = np.zeros_like(free)
+    nb[1:-1, 1:-1] = unk[1:-1, :-2] | unk[1:-1, 2:] | unk[:-2, 1:-1] | unk[2:, 1:-1]
+    inner = np.zeros_like(free)
+    inner[1:-1, 1:-1] = True
+    ys, xs = np.nonzero(free & nb & inner)
+    return list(zip(xs.tolist(), ys.tolist()))
+
+
+def cluster_frontiers(frontier_cells):
+    """OccupancyGrid.cluster_frontiers — dual_bot_mapper.py:199-231 (BFS flood fill)."""
+    if not frontier_cells:
+        return []
+    cell_set = set(frontier_cells)
+    visited = set()
+    clusters = []
+    for cell in frontier_cells:
+        if cell in visited:
+            continue
+        cluster = []
+        queue = [cell]
+        while queue:
+            c = queue.pop(0)
+            if c in visited:
+                continue
+            visited.add(c)
+            cluster.append(c)
+            cx, cy = c
+            for dx, dy in [(-1, 0), (1, 0), (0, -1), (0, 1)]:
+                nbr = (cx + dx, cy + dy)
+                if nbr in cell_set and nbr not in visited:
+                    queue.append(nbr)
+        if len(cluster) >= FRONTIER_MIN_CLUSTER:
+            clusters.append(cluster)
+    return clusters
+
+
+def cluster_centroid_world(cluster, ox, oy, res):
+    """dual_bot_mapper.py:233-237 + grid_to_world :127-131."""
+    avg_x = sum(c[0] for c in cluster) / len(cluster)
+    avg_y = sum(c[1] for c in cluster) / len(cluster)
+    return ox + (avg_x + 0.5) * res, oy + (avg_y + 0.5) * res
+
+
 class OracleSLAM:
     """Restates ``PoseGraphSLAM`` — dual_bot_mapper.py:244-338 (prints dropped).
 

@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""bench_frontier.py — frontier detection + clustering on the device grid.
+
+Workload: the 4096^2 map of BASELINE configs[1] after one 1e7-beam batch; one "step" = what main()
+does every 3 s (dual_bot_mapper.py:948-954): get_frontiers -> cluster_frontiers ->
+cluster_centroid_world for every cluster.  Prints ONE JSON line: grid cells/s, device time per
+kernel family, HBM roofline of the stencil (algorithmic bytes = H*W read once), and the reference's
+own Python loop timed on a bounded crop of the same grid on one host core.
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+
+def main():
+    import torch
+    from occgrid_b200 import _native, dual_bot_mapper as M, simulation_tools as st
+    assert torch.cuda.is_available(), 'needs a CUDA device (no CPU fallback)'
+    s = st.generate_session(n_agents=64, n_packets=2_500_000, seed=42)
+    g = M.OccupancyGrid(max_batch=2_500_000, **s['grid'])
+    g.update_packets(s['packets'], agent_offsets=s['agent_offsets'])
+    for _ in range(3):
+        f, n, k = g._cluster()
+    torch.cuda.synchronize()
+    K = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        f, n, k = g._cluster()                    # includes the two small D2H reads of the real call
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    _native.profile_begin()
+    for _ in range(5):
+        g._cluster()
+    torch.cuda.synchronize()
+    prof = _native.profile_end()
+    cells = g.size * g.size
+    hbm = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'] if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.0
+    fr_ms = prof['frontier'][0] / 5
+    res = {'metric': 'frontier_grid_cells_per_sec', 'value': cells / (ms * 1e-3), 'unit': 'cells/s', 'n_gpus': 1,
+           'ms_per_step': ms, 'higher_is_better': True, 'dtype': 'int8+f64', 'data': 'synthetic',
+           'config': {'workload': '4096^2 int8 grid after one 1e7-beam batch of BASELINE configs[1]; '
+                                  'get_frontiers + cluster_frontiers + centroids', 'frontier_cells': n, 'clusters': k},
+           'kernels': {kname: {'ms_per_step': v[0] / 5, 'kernels_per_step': v[1] / 5} for kname, v in prof.items()},
+           'roofline': {'bound': 'hbm', 'kernel': 'frontier', 'achieved': cells / (fr_ms * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
+                        'frac': cells / (fr_ms * 1e-3) / 1e9 / hbm,
+                        'note': 'algorithmic bytes = H*W (the stencil kernels read the grid twice: count pass + write pass)'}}
+    # CPU baseline: the reference's Python loops (oracle restatement) on a 384^2 crop around a room
+    from oracle import occgrid_oracle as O
+    arr = g.grid
+    ys, xs = np.nonzero(arr != -1)
+    cy, cx = int(ys[0]), int(xs[0])
+    crop = np.ascontiguousarray(arr[max(0, cy - 100):max(0, cy - 100) + 384, max(0, cx - 100):max(0, cx - 100) + 384])
+    t0 = time.perf_counter()
+    fr = O.get_frontiers(crop)
+    cl = O.cluster_frontiers(fr)
+    [O.cluster_centroid_world(c, 0.0, 0.0, 0.05) for c in cl]
+    dt = time.perf_counter() - t0
+    res['cpu_baseline'] = {'value': crop.size / dt, 'unit': 'cells/s', 'cores': 1, 'kind': 'port',
+                           'sample': f'{crop.shape[0]}^2 crop of the same grid ({len(fr)} frontier cells), Python restatement of '
+                                     'dual_bot_mapper.py:181-237'}
+    print(json.dumps(res))
+
+
+if __name__ == '__main__':
+    main()

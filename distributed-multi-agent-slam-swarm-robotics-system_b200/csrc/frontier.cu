@@ -24,18 +24,43 @@ constexpr int kFT = 256;
 constexpr int kFCells = 16;                 // cells per thread
 constexpr int kFChunk = kFT * kFCells;
 
+// Frontier bits of 16 consecutive cells starting at linear index `base` (x0, y0 = its column/row).
+// Fast path: the 16 cells sit in one row and the three rows are 16-byte aligned -> three 16-byte
+// loads + two edge bytes, all tests on registers.
 __device__ __forceinline__ unsigned int frontier_mask16(const int8_t* __restrict__ g, int w, int h, long long base, long long n) {
+    const int y0 = (int)(base / w), x0 = (int)(base - (long long)y0 * w);
     unsigned int mask = 0;
-#pragma unroll 4
+    if (x0 + kFCells <= w && y0 >= 1 && y0 <= h - 2 && ((w & 15) == 0) && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
+        const int4 cur4 = __ldg(reinterpret_cast<const int4*>(g + base));
+        const int4 up4 = __ldg(reinterpret_cast<const int4*>(g + base - w));
+        const int4 dn4 = __ldg(reinterpret_cast<const int4*>(g + base + w));
+        const unsigned int cur[4] = {(unsigned)cur4.x, (unsigned)cur4.y, (unsigned)cur4.z, (unsigned)cur4.w};
+        const unsigned int up[4] = {(unsigned)up4.x, (unsigned)up4.y, (unsigned)up4.z, (unsigned)up4.w};
+        const unsigned int dn[4] = {(unsigned)dn4.x, (unsigned)dn4.y, (unsigned)dn4.z, (unsigned)dn4.w};
+        const unsigned int left = x0 > 0 ? (unsigned int)(unsigned char)g[base - 1] : 0u;
+        const unsigned int right = x0 + kFCells < w ? (unsigned int)(unsigned char)g[base + kFCells] : 0u;
+#pragma unroll
+        for (int i = 0; i < kFCells; ++i) {
+            const unsigned int c = (cur[i >> 2] >> (8 * (i & 3))) & 0xffu;
+            const unsigned int u = (up[i >> 2] >> (8 * (i & 3))) & 0xffu;
+            const unsigned int d = (dn[i >> 2] >> (8 * (i & 3))) & 0xffu;
+            const unsigned int l = i == 0 ? left : (cur[(i - 1) >> 2] >> (8 * ((i - 1) & 3))) & 0xffu;
+            const unsigned int r = i == kFCells - 1 ? right : (cur[(i + 1) >> 2] >> (8 * ((i + 1) & 3))) & 0xffu;
+            const int x = x0 + i;
+            const bool interior = x >= 1 && x <= w - 2;                                              // :187-188
+            if (interior && c == 0u && (u == 0xffu || d == 0xffu || l == 0xffu || r == 0xffu)) mask |= 1u << i;   // :189-196
+        }
+        return mask;
+    }
+    int x = x0, y = y0;
     for (int i = 0; i < kFCells; ++i) {
         const long long c = base + i;
         if (c >= n) break;
-        const int y = (int)(c / w), x = (int)(c - (long long)y * w);
-        if (x < 1 || y < 1 || x > w - 2 || y > h - 2) continue;                       // :187-188
-        if (g[c] != OCCGRID_CELL_FREE) continue;                                     // :189
-        if (g[c - 1] == OCCGRID_CELL_UNKNOWN || g[c + 1] == OCCGRID_CELL_UNKNOWN ||
-            g[c - w] == OCCGRID_CELL_UNKNOWN || g[c + w] == OCCGRID_CELL_UNKNOWN)     // :193-196
+        if (x >= 1 && y >= 1 && x <= w - 2 && y <= h - 2 && g[c] == OCCGRID_CELL_FREE &&
+            (g[c - 1] == OCCGRID_CELL_UNKNOWN || g[c + 1] == OCCGRID_CELL_UNKNOWN ||
+             g[c - w] == OCCGRID_CELL_UNKNOWN || g[c + w] == OCCGRID_CELL_UNKNOWN))
             mask |= 1u << i;
+        if (++x == w) { x = 0; ++y; }
     }
     return mask;
 }

@@ -32,7 +32,7 @@ namespace occ {
 constexpr int kTile = 64;            // home-tile side in cells
 constexpr int kTileShift = 6;
 constexpr int kTT = 256;             // threads per CTA
-constexpr int kChunkPk = 1024;       // packets per work item
+constexpr int kChunkPk = 2048;       // packets per work item
 constexpr int kMaxStrideT = 64;
 constexpr int kMaxWindowBytes = 100 * 1024;   // smem window budget (two CTAs per SM at least)
 

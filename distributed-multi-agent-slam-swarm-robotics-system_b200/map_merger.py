@@ -338,25 +338,3 @@ class MapMerger:
             self._cloud.count.data_ptr(), self._last.data_ptr(), self._status.data_ptr(),
             ws.data_ptr(), ws.numel(), self._stream())
         _native.check(rc, 'mapmerge_extract_transform')
-
-
-def smoke():
-    """Tiny merge on cuda:0 checked against the oracle (called from __graft_entry__.smoke)."""
-    from oracle import merge_oracle as MO
-    rng = np.random.default_rng(5)
-    m, o = MapMerger(device='cuda:0'), MO.OracleMerger()
-    for a in range(4):
-        g = np.full((256, 256), -1, np.int8)
-        g[rng.random((256, 256)) < 0.3] = 0
-        for _ in range(12):
-            x0, y0, L = int(rng.integers(0, 200)), int(rng.integers(0, 200)), int(rng.integers(10, 56))
-            if rng.random() < 0.5:
-                g[y0, x0:x0 + L] = 100
-            else:
-                g[y0:y0 + L, x0] = 100
-        T = MO.se2_matrix(*rng.uniform(-3, 3, 2), rng.uniform(-math.pi, math.pi))
-        got = m.map_callback(make_grid_msg(g.ravel(), 256, 256, 0.05, -6.4, -6.4), a + 1, transform=T)
-        want = o.map_callback(g.ravel(), 256, 256, 0.05, -6.4, -6.4, T)
-        assert np.array_equal(got.data, want[0]), f'merge step {a}: grid differs from the oracle'
-        assert (got.info.origin.position.x, got.info.origin.position.y) == want[1]
-    print(f'smoke ok: map merge, 4 agent grids, {m._n_global} fused points, grid bit-exact')

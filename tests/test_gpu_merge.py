@@ -105,3 +105,24 @@ def test_batched_merge_equals_callbacks(MM):
 def test_2048_grids(MM):
     """BASELINE config 3 grid size (2048^2, ~1.5 % occupied) on a few agents, 50 m translations."""
     run_pair(MM, 2048, 4, seed=7, span=50.0, origin=(-51.2, -51.2), check_every=False)
+
+
+def test_sharded_merger_single_rank_equals_merge(MM):
+    """ShardedMapMerger (agents dealt to ranks, extraction sharded, ordered voxel chain replicated)
+    with world = 1 must equal MapMerger.merge and the oracle; an empty first grid exercises the
+    'first NON-EMPTY grid is adopted untransformed' rule (map_merger.py:37-43)."""
+    from occgrid_b200.distributed import ShardedMapMerger
+    from oracle import merge_oracle as MO
+    r = np.random.default_rng(12)
+    grids = [np.full((160, 160), -1, np.int8)] + [synth_agent_grid(160, 70 + a) for a in range(4)]
+    origins = np.tile(np.array([[-4.0, -4.0]]), (5, 1))
+    tf = np.stack([MO.se2_matrix(*r.uniform(-3, 3, 2), r.uniform(-math.pi, math.pi)) for _ in range(5)])
+    o = MO.OracleMerger()
+    want = None
+    for a in range(5):
+        out = o.map_callback(grids[a].ravel(), 160, 160, 0.05, -4.0, -4.0, tf[a])
+        want = out if out is not None else want
+    got, origin = ShardedMapMerger().merge(grids, origins, 0.05, tf, 5)
+    assert np.array_equal(got, want[0]) and origin == want[1]
+    got2, origin2 = MM.MapMerger().merge(grids, origins, 0.05, tf)
+    assert np.array_equal(got2, want[0]) and origin2 == want[1]

@@ -43,6 +43,27 @@ for pipeline, exchange in modes:
         print(f'world={world} pipeline={pipeline} exchange={tmap.exchange}: map {"bit-exact" if same else "DIFFERS"} vs oracle '
               f'({c["beams"]} beams, {int((want != -1).sum())} known cells)', flush=True)
     dist.barrier()
+# map fusion: agents dealt round-robin to ranks, extraction sharded, ordered voxel chain replicated
+import math
+from occgrid_b200.distributed import ShardedMapMerger
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
+from merge_util import synth_agent_grid
+from oracle import merge_oracle as MO
+A, S = 3 * world + 1, 256
+rgen = np.random.default_rng(3)
+grids = [synth_agent_grid(S, 500 + a) for a in range(A)]
+tf = [MO.se2_matrix(*rgen.uniform(-5, 5, 2), rgen.uniform(-math.pi, math.pi)) for _ in range(A)]
+mine = list(range(rank, A, world))
+got, origin = ShardedMapMerger(device=dev).merge([grids[a] for a in mine], [(-6.4, -6.4)] * len(mine), 0.05,
+                                                 [tf[a] for a in mine], A)
+if rank == 0:
+    o = MO.OracleMerger()
+    for a in range(A):
+        want = o.map_callback(grids[a].ravel(), S, S, 0.05, -6.4, -6.4, tf[a])
+    same = bool(np.array_equal(got, want[0]) and origin == want[1])
+    ok &= same
+    print(f'world={world} sharded merge of {A} grids: {"bit-exact" if same else "DIFFERS"} vs oracle', flush=True)
+dist.barrier()
 if rank == 0:
     print('PASS' if ok else 'FAIL', flush=True)
 dist.destroy_process_group()

@@ -34,5 +34,6 @@ for b in range(2):
     ops[b].grid.update_poses(recv[b][:int(cnt[b][0])], ordinals_in_records=True)
     bands.append(ops[b].band_tensor().cpu().numpy())
 assert np.array_equal(np.concatenate(bands), want)
-MM.smoke()
+import __graft_entry__ as ge
+ge.merge_smoke()
 print('sanitize_case ok')

@@ -173,7 +173,7 @@ class TiledSwarmMap:
         self._pending = None
         self._step = 0
         self._slot_free = [None, None]
-        self._side = torch.cuda.Stream(device=ops.device) if self.pipeline else None
+        self._side = torch.cuda.Stream(device=ops.device, priority=-1) if self.pipeline else None   # router first
         # exchange = 'p2p': routed records are stored straight into the owner's receive buffer over
         # NVLink by the routing kernel (symmetric memory); 'nccl': send buffer + all_to_all_single
         self.peer = None

@@ -215,7 +215,7 @@ def main():
     ap.add_argument('--grid-per-gpu', type=int, default=GRID_PER_GPU,
                     help='N>1: map side = this x N (8192 with --agents-per-gpu 128 at N=8 = BASELINE configs[3])')
     ap.add_argument('--agents-per-gpu', type=int, default=AGENTS_PER_GPU)
-    ap.add_argument('--raycast-ctas', type=int, default=0, help='raycast launch: 0 = chip-filling grid, k = at most k CTAs/SM, -1 = one CTA per work item')
+    ap.add_argument('--raycast-ctas', type=int, default=0, help='cap persistent raycast CTAs per SM (0 = max)')
     ap.add_argument('--exchange', default='auto', choices=['auto', 'p2p', 'nccl'],
                     help='N>1: routed records via peer-memory stores from the routing kernel (p2p) or NCCL all-to-all')
     args = ap.parse_args()

@@ -393,18 +393,18 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
                const unsigned int* __restrict__ bins, const PoseRec* __restrict__ recs, int ordinals_in_records,
                unsigned int* __restrict__ stamps, uint64_t* counters) {
     extern __shared__ unsigned int s_win[];
+    __shared__ unsigned int s_item;
     __shared__ unsigned long long s_acc[3 * 32];
     const unsigned int n_items = hdr->n_items;
     const int side = tg.win_side, pitch = tg.pitch, words = side * pitch;
     unsigned long long c[3] = {0, 0, 0};     // updates, slowpath, owned updates
-    // Work items are dealt round-robin to the CTAs of the launch: with the default grid (as many
-    // CTAs as fit on the chip) every CTA loops over several items; with one CTA per item
-    // (occgrid_set_raycast_ctas_per_sm(-1)) CTAs retire quickly, which lets a concurrent
-    // higher-priority kernel (the multi-GPU router) interleave.
-    for (unsigned int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    for (;;) {
         __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(&hdr->work_counter, 1u);
         for (int i = threadIdx.x; i < words; i += kTT) s_win[i] = 0u;
         __syncthreads();
+        const unsigned int it = s_item;
+        if (it >= n_items) break;
         const uint4 item = items[it];
         const int ttx = item.x % tg.tiles_x, tty = item.x / tg.tiles_x;
         // global cell of window-local (0, 0)
@@ -508,7 +508,7 @@ k_home_resolve(Geom g, TileGeom tg, const unsigned int* __restrict__ active, Til
 // Persistent raycast CTAs per SM (0 = as many as fit).  A multi-GPU pipeline lowers it so that
 // the routing kernel of the next batch can be co-resident (occgrid_set_raycast_ctas_per_sm).
 static int g_raycast_cta_cap = 0;
-void set_raycast_cta_cap(int cap) { g_raycast_cta_cap = cap < -1 ? -1 : cap; }
+void set_raycast_cta_cap(int cap) { g_raycast_cta_cap = cap < 0 ? 0 : cap; }
 
 struct TiledLayout {
     size_t off_stamps, off_count, off_offset, off_cursor, off_active, off_hdr, off_items, off_ids, off_bins, off_recs, total;
@@ -587,12 +587,6 @@ int integrate_tiled(const occgrid_geom* geom, const uint8_t* d_packets, const Po
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_home_raycast, kTT, win_bytes) != cudaSuccess || ctas_per_sm < 1)
         ctas_per_sm = 1;
     if (g_raycast_cta_cap > 0 && ctas_per_sm > g_raycast_cta_cap) ctas_per_sm = g_raycast_cta_cap;
-    unsigned int raycast_grid = (unsigned int)(sms * ctas_per_sm);
-    if (g_raycast_cta_cap < 0) {            // one CTA per work item (host-side bound on the item count)
-        unsigned long long bound = (unsigned long long)n / kChunkPk + (unsigned long long)min((long long)tg.n_tiles, (long long)n) + 1;
-        if (bound > L.max_items) bound = L.max_items;
-        if (bound > raycast_grid) raycast_grid = (unsigned int)min(bound, 1ull << 20);
-    }
     {
         ProfileScope ps(K_TILE_COUNT, st);
         if (d_poses)
@@ -613,7 +607,7 @@ int integrate_tiled(const occgrid_geom* geom, const uint8_t* d_packets, const Po
     }
     {
         ProfileScope ps(K_TILE_RAYCAST, st);
-        k_home_raycast<<<raycast_grid, kTT, win_bytes, st>>>(g, tg, items, hdr, bins, recs, ordinals_in_records, stamps,
+        k_home_raycast<<<sms * ctas_per_sm, kTT, win_bytes, st>>>(g, tg, items, hdr, bins, recs, ordinals_in_records, stamps,
                                                                   d_counters);
     }
     {

@@ -277,10 +277,9 @@ int occgrid_frontier_clusters(const int32_t* d_xy, const int64_t* d_count, int64
                               double* d_centroids, int64_t* d_n_clusters,
                               void* d_ws, size_t ws_bytes, void* stream);
 
-/* Tuning knob of the TILED strategy's raycast launch: 0 (default) = as many CTAs as fit on the
- * chip, each looping over several work items; k > 0 = at most k CTAs per SM; -1 = one CTA per
- * work item, so CTAs retire quickly and a concurrent higher-priority kernel (the multi-GPU
- * router of the next batch) can interleave.  Process-wide. */
+/* Tuning knob of the TILED strategy: cap the persistent raycast CTAs per SM (0 = as many as fit,
+ * the default).  A pipelined multi-GPU ingest lowers it to 2 so that the routing kernel of the
+ * next batch finds room on every SM and runs concurrently.  Process-wide. */
 int occgrid_set_raycast_ctas_per_sm(int cap);
 
 /*

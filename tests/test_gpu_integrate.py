@@ -345,3 +345,28 @@ def test_full_size_config2_batch(M, strategy):
     tiles = [sha1(got[y:y + 512, x:x + 512]) for y in range(0, 4096, 512) for x in range(0, 4096, 512)]
     tiles_want = [sha1(want[y:y + 512, x:x + 512]) for y in range(0, 4096, 512) for x in range(0, 4096, 512)]
     assert hashlib.sha1(''.join(tiles).encode()).hexdigest() == hashlib.sha1(''.join(tiles_want).encode()).hexdigest()
+
+
+def test_fine_resolution_falls_back_to_global_atomics(M):
+    """At 2 cm cells a beam reaches 62 cells and the (64+2R)^2 shared-memory window no longer fits
+    the budget: 'tiled' is refused loudly, 'auto' picks the global-atomic kernels; result = oracle."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(4)
+    n = 4000
+    pk = np.zeros((n, 42), np.uint8)
+    rec = pk.view(np.dtype([('magic', 'S4'), ('agent', 'u1'), ('x', '<f4'), ('y', '<f4'), ('yaw', '<f4'), ('enc', '<i4'),
+                            ('v2v', '<u4'), ('d', '<f4', 4), ('lm', 'u1')]))[:, 0]
+    rec['magic'] = b'QSRL'
+    rec['agent'] = rng.integers(1, 3, n)
+    rec['x'] = rng.uniform(-1, 9, n)
+    rec['y'] = rng.uniform(-1, 9, n)
+    rec['yaw'] = rng.uniform(-3.2, 3.2, n)
+    rec['d'] = rng.uniform(0, 1.5, (n, 4))
+    with pytest.raises(M.OccGridError):
+        M.OccupancyGrid(size=400, resolution=0.02, origin_x=0.0, origin_y=0.0, strategy='tiled')
+    g = M.OccupancyGrid(size=400, resolution=0.02, origin_x=0.0, origin_y=0.0, strategy='auto', max_batch=n)
+    g.update_packets(pk, separation=0.25)
+    want = np.full((400, 400), -1, np.int8)
+    c = c_oracle.integrate_packets(pk, want, 0.0, 0.0, 0.02, separation=0.25)
+    assert np.array_equal(g.grid, want)
+    assert g.counters()['updates'] == c['updates']

@@ -409,7 +409,7 @@ def main():
                          'ms_per_step': e_ms / Ke,
                          'api': 'OccupancyGrid.update_packets(pinned host uint8[n,42]) + counters() read-back'}
         if not args.no_cpu:
-            result['cpu_baseline'] = cpu_baseline(s0, 1, 25_000)
+            result['cpu_baseline'] = cpu_baseline(s0, 1, 500_000)     # ~10 s of the reference's Python loop on one core
             result['cpu_baseline_c_port'] = c_port_rate(s0)
     if n > 1:
         # e2e at N GPUs: every rank hands ITS share to TiledSwarmMap.update_packets as a pinned host

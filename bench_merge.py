@@ -92,7 +92,7 @@ def main():
     prof = _native.profile_end()
     kern = {k: {'ms_total': v[0], 'kernels': v[1]} for k, v in prof.items()}
     hbm = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'] if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.0
-    ext_ms = prof['merge_extract'][0] / (prof['merge_extract'][1] / 3)
+    ext_ms = prof['merge_extract'][0] / A            # all extraction-side kernels of the merge, per grid
     result = {
         'metric': 'merged_grids_per_sec', 'value': A / (ms * 1e-3), 'unit': 'grids/s', 'n_gpus': 1, 'ms_per_merge': ms,
         'higher_is_better': True, 'dtype': 'f64+int8', 'data': 'synthetic',
@@ -103,8 +103,9 @@ def main():
         'kernels': kern,
         'roofline': {'bound': 'hbm', 'kernel': 'merge_extract', 'achieved': S * S / (ext_ms * 1e-3) / 1e9, 'peak': hbm,
                      'unit': 'GB/s', 'frac': S * S / (ext_ms * 1e-3) / 1e9 / hbm,
-                     'note': 'algorithmic bytes = H*W per agent grid (SURVEY §8d); the extraction scan is the HBM-bound '
-                             'part, the voxel chain is O(|cloud|) per callback as in the reference'},
+                     'note': 'algorithmic bytes = H*W per agent grid (SURVEY §8d) over the device time of all extraction-side '
+                             'kernels (batched count + write passes over all grids, plus the per-callback slice appends); '
+                             'the voxel chain is O(|cloud|) per callback as in the reference'},
     }
     # CPU baseline: NumPy restatement, one core, first cpu_agents grids
     from oracle import merge_oracle as MO

@@ -120,6 +120,14 @@ def _bind_merge(L):
     L.mapmerge_extract_workspace_bytes.argtypes = [i64]
     L.mapmerge_extract_transform.restype = C.c_int
     L.mapmerge_extract_transform.argtypes = [vp, i32, i32, dbl, dbl, dbl, vp, vp, vp, i64, vp, vp, vp, vp, sz, vp]
+    L.mapmerge_extract_batch_workspace_bytes.restype = sz
+    L.mapmerge_extract_batch_workspace_bytes.argtypes = [i64, i32]
+    L.mapmerge_extract_batch_count.restype = C.c_int
+    L.mapmerge_extract_batch_count.argtypes = [vp, i32, i32, i32, vp, vp, sz, vp]
+    L.mapmerge_extract_batch_write.restype = C.c_int
+    L.mapmerge_extract_batch_write.argtypes = [vp, i32, i32, i32, dbl, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, sz, vp]
+    L.mapmerge_append_slice.restype = C.c_int
+    L.mapmerge_append_slice.argtypes = [vp, vp, vp, i32, vp, vp, i64, vp, vp, vp]
     L.mapmerge_bounds_workspace_bytes.restype = sz
     L.mapmerge_bounds.restype = C.c_int
     L.mapmerge_bounds.argtypes = [vp, vp, vp, vp, vp, sz, vp]

@@ -14,6 +14,8 @@
 // canonical order "first appearance" (voxels in order of their smallest point index, as an
 // insertion-ordered map would give) and sum the points of a voxel in ascending point index, so
 // results are bit-reproducible and equal to the oracle (oracle/merge_oracle.py).
+#include <vector>
+
 #include "common.cuh"
 
 namespace occ {
@@ -160,6 +162,112 @@ k_extract_write(const int8_t* __restrict__ grid, long long n_cells, int width, d
         py[dst] = y;
         ++dst;
     }
+}
+
+// ---- batched extraction: all agent grids of a merge in one pass ----------------------------
+// grids[a] are A device pointers to H x W int8 maps; blockIdx.y = agent.  Output: every agent's
+// transformed points, agent after agent (row-major inside an agent), plus per-agent offsets —
+// the sequential voxel chain then appends slice a when its turn comes.
+struct BatchXform { double m[6]; double w[3]; int identity; int use; };   // rows 0,1 and 3 of the 4x4 (z == 0)
+
+__global__ void __launch_bounds__(kMT)
+k_batch_count(const int8_t* const* __restrict__ grids, long long n_cells, int blocks_per_grid,
+              unsigned int* __restrict__ block_counts /* [A][blocks_per_grid] */) {
+    __shared__ unsigned int s_warp[33];
+    const int a = blockIdx.y;
+    const long long base = ((long long)blockIdx.x * kMT + threadIdx.x) * kCellsPerThread;
+    unsigned int total;
+    block_exclusive_scan(base < n_cells ? __popc(occupied_mask16(grids[a], base, n_cells)) : 0u, s_warp, &total);
+    if (threadIdx.x == 0) block_counts[(size_t)a * blocks_per_grid + blockIdx.x] = total;
+}
+
+// One CTA per agent: exclusive scan of its block counts (in place) and its total.
+__global__ void __launch_bounds__(1024)
+k_batch_scan(unsigned int* __restrict__ block_counts, int blocks_per_grid, long long* __restrict__ agent_total) {
+    __shared__ unsigned int s_warp[33];
+    __shared__ unsigned int s_carry;
+    unsigned int* bc = block_counts + (size_t)blockIdx.x * blocks_per_grid;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int start = 0; start < blocks_per_grid; start += blockDim.x) {
+        const int i = start + threadIdx.x;
+        const unsigned int v = i < blocks_per_grid ? bc[i] : 0u;
+        unsigned int total;
+        const unsigned int ex = block_exclusive_scan(v, s_warp, &total);
+        if (i < blocks_per_grid) bc[i] = s_carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) agent_total[blockIdx.x] = s_carry;
+}
+
+// agent_offset[a] = sum of totals of the agents before a that take part in the merge.
+__global__ void k_batch_offsets(const long long* __restrict__ agent_total, const BatchXform* __restrict__ T, int n_agents,
+                                long long capacity, long long* __restrict__ agent_offset, int* __restrict__ status) {
+    long long acc = 0;
+    for (int a = 0; a < n_agents; ++a) {
+        agent_offset[a] = acc;
+        if (T[a].use) acc += agent_total[a];
+    }
+    agent_offset[n_agents] = acc;
+    if (acc > capacity) atomicOr(status, ST_POINT_OVERFLOW);
+}
+
+__global__ void __launch_bounds__(kMT)
+k_batch_write(const int8_t* const* __restrict__ grids, long long n_cells, int width, double res,
+              const double* __restrict__ origins /* [A][2] */, const BatchXform* __restrict__ T, int blocks_per_grid,
+              const unsigned int* __restrict__ block_offsets, const long long* __restrict__ agent_offset, long long capacity,
+              double* __restrict__ px, double* __restrict__ py) {
+    __shared__ unsigned int s_warp[33];
+    const int a = blockIdx.y;
+    const BatchXform t = T[a];
+    if (!t.use || agent_offset[gridDim.y] > capacity) return;
+    const long long base = ((long long)blockIdx.x * kMT + threadIdx.x) * kCellsPerThread;
+    const unsigned int mask = base < n_cells ? occupied_mask16(grids[a], base, n_cells) : 0u;
+    unsigned int total;
+    const unsigned int off = block_exclusive_scan(__popc(mask), s_warp, &total);
+    long long dst = agent_offset[a] + block_offsets[(size_t)a * blocks_per_grid + blockIdx.x] + off;
+    const double ox = origins[2 * a], oy = origins[2 * a + 1];
+    unsigned int m = mask;
+    while (m) {
+        const int i = __ffs(m) - 1;
+        m &= m - 1;
+        const long long c = base + i;
+        const long long row = c / width, col = c - row * width;
+        double x = OCC_DADD(OCC_DMUL((double)col, res), ox);       // :77
+        double y = OCC_DADD(OCC_DMUL((double)row, res), oy);       // :76
+        if (!t.identity) {
+            const double w = OCC_DADD(OCC_DADD(OCC_DMUL(t.w[0], x), OCC_DMUL(t.w[1], y)), t.w[2]);
+            const double tx = OCC_DADD(OCC_DADD(OCC_DMUL(t.m[0], x), OCC_DMUL(t.m[1], y)), t.m[2]);
+            const double ty = OCC_DADD(OCC_DADD(OCC_DMUL(t.m[3], x), OCC_DMUL(t.m[4], y)), t.m[5]);
+            x = OCC_DDIV(tx, w);
+            y = OCC_DDIV(ty, w);
+        }
+        px[dst] = x;
+        py[dst] = y;
+        ++dst;
+    }
+}
+
+// global_pcd += local_pcd (:59) for agent a of a batched extraction: append its slice.
+__global__ void __launch_bounds__(kMT)
+k_append_slice(const double* __restrict__ sx, const double* __restrict__ sy, const long long* __restrict__ agent_offset, int a,
+               double* __restrict__ px, double* __restrict__ py, long long capacity, long long* __restrict__ d_count,
+               int* __restrict__ status) {
+    const long long b = agent_offset[a], e = agent_offset[a + 1];
+    const long long n0 = *d_count;                  // read by every thread before the last block bumps it (see below)
+    const long long k = e - b;
+    if (n0 + k > capacity) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status, ST_POINT_OVERFLOW); return; }
+    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < k; i += (long long)gridDim.x * kMT) {
+        px[n0 + i] = sx[b + i];
+        py[n0 + i] = sy[b + i];
+    }
+}
+
+__global__ void k_bump_count(const long long* __restrict__ agent_offset, int a, long long capacity, long long* __restrict__ d_count) {
+    const long long k = agent_offset[a + 1] - agent_offset[a];
+    if (*d_count + k <= capacity) *d_count += k;
 }
 
 // ---- bounds (GetMinBound/GetMaxBound; publish_global_map :95-98) ---------------------------
@@ -501,6 +609,88 @@ int mapmerge_extract_transform(const int8_t* d_grid, int32_t width, int32_t heig
     k_extract_reserve<<<1, 1024, 0, st>>>(block_counts, blocks, (long long*)d_count, capacity, ws_base, d_status,
                                            (long long*)d_last_appended);
     k_extract_write<<<blocks, kMT, 0, st>>>(d_grid, n_cells, width, res, origin_x, origin_y, T, block_counts, ws_base, d_px, d_py);
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
+}
+
+size_t mapmerge_extract_batch_workspace_bytes(int64_t n_cells, int n_agents) {
+    const int64_t blocks = (n_cells + kChunk - 1) / kChunk;
+    return align_up((size_t)blocks * (size_t)n_agents * sizeof(unsigned int), 256);
+}
+
+// Pass 1 of a batched extraction: per-block and per-agent occupied-cell counts.
+int mapmerge_extract_batch_count(const int8_t* const* d_grids, int n_agents, int32_t width, int32_t height,
+                                 int64_t* d_agent_total, void* d_ws, size_t ws_bytes, void* stream) {
+    if (!d_grids || n_agents <= 0 || n_agents > 65535 || width <= 0 || height <= 0 || !d_agent_total || !d_ws) {
+        set_last_error("mapmerge_extract_batch_count: bad arguments");
+        return OCCGRID_E_ARG;
+    }
+    const long long n_cells = (long long)width * height;
+    if (ws_bytes < mapmerge_extract_batch_workspace_bytes(n_cells, n_agents)) { set_last_error("mapmerge_extract_batch_count: workspace too small"); return OCCGRID_E_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int bpg = (int)((n_cells + kChunk - 1) / kChunk);
+    unsigned int* block_counts = reinterpret_cast<unsigned int*>(d_ws);
+    ProfileScope ps(K_MERGE_EXTRACT, st, 2);
+    dim3 grid((unsigned)bpg, (unsigned)n_agents);
+    k_batch_count<<<grid, kMT, 0, st>>>(d_grids, n_cells, bpg, block_counts);
+    k_batch_scan<<<n_agents, 1024, 0, st>>>(block_counts, bpg, (long long*)d_agent_total);
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
+}
+
+// Pass 2: the caller has read the totals, decided which agents take part (use_host) and which
+// transform each gets (T_host; the first cloud is adopted untransformed, map_merger.py:40-43).
+int mapmerge_extract_batch_write(const int8_t* const* d_grids, int n_agents, int32_t width, int32_t height, double res,
+                                 const double* d_origins, const double* T_host /* [A][16] row-major or NULL */,
+                                 const uint8_t* use_host /* [A] or NULL */, void* d_xforms /* >= A * 96 bytes */,
+                                 double* d_px, double* d_py, int64_t capacity, const int64_t* d_agent_total,
+                                 int64_t* d_agent_offset, int32_t* d_status, void* d_ws, size_t ws_bytes, void* stream) {
+    if (!d_grids || n_agents <= 0 || n_agents > 65535 || width <= 0 || height <= 0 || !(res > 0.0) || !d_origins || !d_xforms ||
+        !d_px || !d_py || !d_agent_total || !d_agent_offset || !d_status || !d_ws) {
+        set_last_error("mapmerge_extract_batch_write: bad arguments");
+        return OCCGRID_E_ARG;
+    }
+    const long long n_cells = (long long)width * height;
+    if (ws_bytes < mapmerge_extract_batch_workspace_bytes(n_cells, n_agents)) { set_last_error("mapmerge_extract_batch_write: workspace too small"); return OCCGRID_E_WORKSPACE; }
+    static_assert(sizeof(BatchXform) <= 96, "BatchXform must fit the 96-byte slot");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<BatchXform> hx((size_t)n_agents);
+    for (int a = 0; a < n_agents; ++a) {
+        BatchXform& t = hx[a];
+        t.use = use_host ? (use_host[a] != 0) : 1;
+        t.identity = 1;
+        const double I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        const double* M = T_host ? T_host + 16 * (size_t)a : I;
+        for (int i = 0; i < 16; ++i) if (M[i] != I[i]) t.identity = 0;
+        t.m[0] = M[0]; t.m[1] = M[1]; t.m[2] = M[3];
+        t.m[3] = M[4]; t.m[4] = M[5]; t.m[5] = M[7];
+        t.w[0] = M[12]; t.w[1] = M[13]; t.w[2] = M[15];
+    }
+    OCC_CUDA_TRY(cudaMemcpyAsync(d_xforms, hx.data(), sizeof(BatchXform) * (size_t)n_agents, cudaMemcpyHostToDevice, st));
+    OCC_CUDA_TRY(cudaStreamSynchronize(st));        // hx is a local: the copy must have left it
+    const int bpg = (int)((n_cells + kChunk - 1) / kChunk);
+    unsigned int* block_counts = reinterpret_cast<unsigned int*>(d_ws);
+    const BatchXform* dT = reinterpret_cast<const BatchXform*>(d_xforms);
+    ProfileScope ps(K_MERGE_EXTRACT, st, 2);
+    dim3 grid((unsigned)bpg, (unsigned)n_agents);
+    k_batch_offsets<<<1, 1, 0, st>>>((const long long*)d_agent_total, dT, n_agents, capacity, (long long*)d_agent_offset, d_status);
+    k_batch_write<<<grid, kMT, 0, st>>>(d_grids, n_cells, width, res, d_origins, dT, bpg, block_counts, (const long long*)d_agent_offset,
+                                        capacity, d_px, d_py);
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
+}
+
+int mapmerge_append_slice(const double* d_sx, const double* d_sy, const int64_t* d_agent_offset, int agent,
+                          double* d_px, double* d_py, int64_t capacity, int64_t* d_count, int32_t* d_status, void* stream) {
+    if (!d_sx || !d_sy || !d_agent_offset || agent < 0 || !d_px || !d_py || !d_count || !d_status) {
+        set_last_error("mapmerge_append_slice: bad arguments");
+        return OCCGRID_E_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfileScope ps(K_MERGE_EXTRACT, st, 2);
+    k_append_slice<<<148, kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, agent, d_px, d_py, capacity,
+                                         (long long*)d_count, d_status);
+    k_bump_count<<<1, 1, 0, st>>>((const long long*)d_agent_offset, agent, capacity, (long long*)d_count);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
 }

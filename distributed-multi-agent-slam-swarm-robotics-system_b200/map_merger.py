@@ -268,10 +268,19 @@ class MapMerger:
         A = len(grids)
         with torch.cuda.device(self.device):
             dev = [self._device_grid(make_grid_msg(grids[a], grids[a].shape[1], grids[a].shape[0], res, 0, 0)) for a in range(A)]
+            same_shape = all(d.shape == dev[0].shape for d in dev)
             counts = torch.zeros(A, dtype=torch.int64, device=self.device)
-            for a in range(A):
-                rc = self._lib.mapmerge_count_occupied(dev[a].data_ptr(), dev[a].numel(), counts[a:a + 1].data_ptr(), self._stream())
-                _native.check(rc, 'mapmerge_count_occupied')
+            if same_shape:                       # one pass over all grids
+                h, w = dev[0].shape
+                ptrs = torch.tensor([d.data_ptr() for d in dev], dtype=torch.int64, device=self.device)
+                bws = self._workspace('extract_batch', self._lib.mapmerge_extract_batch_workspace_bytes(h * w, A))
+                rc = self._lib.mapmerge_extract_batch_count(ptrs.data_ptr(), A, w, h, counts.data_ptr(), bws.data_ptr(),
+                                                            bws.numel(), self._stream())
+                _native.check(rc, 'mapmerge_extract_batch_count')
+            else:
+                for a in range(A):
+                    rc = self._lib.mapmerge_count_occupied(dev[a].data_ptr(), dev[a].numel(), counts[a:a + 1].data_ptr(), self._stream())
+                    _native.check(rc, 'mapmerge_count_occupied')
             n_occ = counts.cpu().tolist()                           # host sync 1
             if self._n_global and self._cloud is not None:
                 self._bounds_of(self._cloud)
@@ -298,20 +307,40 @@ class MapMerger:
                             px = M[0, 0] * cx + M[0, 1] * cy + M[0, 3]
                             py = M[1, 0] * cx + M[1, 1] * cy + M[1, 3]
                             bb = [min(bb[0], px), min(bb[1], py), max(bb[2], px), max(bb[3], py)]
-            total = self._n_global + sum(n for n, (u, _) in zip(n_occ, mats) if u)
+            n_new = sum(n for n, (u, _) in zip(n_occ, mats) if u)
+            total = self._n_global + n_new
             if total == 0:
                 return None, None
             self._ensure_capacity(total + 1024)
             first = self._n_global == 0
             v = float(res) if first else self.map_resolution
             cells = (int((bb[2] - bb[0]) / v) + 4) * (int((bb[3] - bb[1]) / v) + 4)
+            if same_shape:                       # all slices extracted + transformed in one launch
+                h, w = dev[0].shape
+                stage = _Cloud(n_new + 16, self.device)
+                offs = torch.zeros(A + 1, dtype=torch.int64, device=self.device)
+                xf = torch.empty(A * 96, dtype=torch.uint8, device=self.device)
+                org = torch.from_numpy(np.ascontiguousarray(np.asarray(origins, np.float64).reshape(A, 2))).to(self.device)
+                Th = np.ascontiguousarray(np.stack([np.eye(4) if T is None else np.asarray(T, np.float64).reshape(4, 4)
+                                                    for _, T in mats]))
+                use_h = np.ascontiguousarray(np.array([1 if u else 0 for u, _ in mats], np.uint8))
+                rc = self._lib.mapmerge_extract_batch_write(
+                    ptrs.data_ptr(), A, w, h, float(res), org.data_ptr(), Th.ctypes.data, use_h.ctypes.data, xf.data_ptr(),
+                    stage.x.data_ptr(), stage.y.data_ptr(), stage.capacity, counts.data_ptr(), offs.data_ptr(),
+                    self._status.data_ptr(), bws.data_ptr(), bws.numel(), self._stream())
+                _native.check(rc, 'mapmerge_extract_batch_write')
             for a in range(A):
                 use, T = mats[a]
                 if not use:
                     continue
-                h, w = dev[a].shape
-                msg = make_grid_msg(dev[a], w, h, res, origins[a][0], origins[a][1])
-                self._extract_async(msg, T)
+                if same_shape:
+                    rc = self._lib.mapmerge_append_slice(stage.x.data_ptr(), stage.y.data_ptr(), offs.data_ptr(), a,
+                                                         self._cloud.x.data_ptr(), self._cloud.y.data_ptr(), self._cloud.capacity,
+                                                         self._cloud.count.data_ptr(), self._status.data_ptr(), self._stream())
+                    _native.check(rc, 'mapmerge_append_slice')
+                else:
+                    h, w = dev[a].shape
+                    self._extract_async(make_grid_msg(dev[a], w, h, res, origins[a][0], origins[a][1]), T)
                 if first:
                     first = False
                     self.map_resolution = float(res)

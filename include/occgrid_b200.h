@@ -223,6 +223,28 @@ int mapmerge_extract_transform(const int8_t* d_grid, int32_t width, int32_t heig
                                int64_t* d_count, int64_t* d_last_appended, int32_t* d_status,
                                void* d_ws, size_t ws_bytes, void* stream);
 
+/* Batched form of mapmerge_extract_transform for one merge() of A same-sized grids, in two
+ * passes over all grids at once (blockIdx.y = agent).  d_grids is a DEVICE array of A grid
+ * pointers.  _count: d_agent_total[a] = occupied cells of grid a (the caller reads them to size
+ * the cloud and to find the first non-empty grid, which is adopted untransformed, :40-43).
+ * _write: T_host (HOST, [A][16] row-major or NULL) and use_host (HOST, [A] or NULL: 0 = skip the
+ * agent) describe the callbacks; the transformed points land in d_px/d_py agent after agent and
+ * d_agent_offset[a] = start of agent a's slice (d_agent_offset[A] = total).  d_xforms is scratch
+ * (A * 96 bytes); the workspace must be the one _count filled.  The sequential chain appends
+ * slice a with mapmerge_append_slice when callback a's turn comes (:59). */
+size_t mapmerge_extract_batch_workspace_bytes(int64_t n_cells, int n_agents);
+int mapmerge_extract_batch_count(const int8_t* const* d_grids, int n_agents, int32_t width, int32_t height,
+                                 int64_t* d_agent_total, void* d_ws, size_t ws_bytes, void* stream);
+int mapmerge_extract_batch_write(const int8_t* const* d_grids, int n_agents, int32_t width, int32_t height,
+                                 double res, const double* d_origins, const double* T_host,
+                                 const uint8_t* use_host, void* d_xforms,
+                                 double* d_px, double* d_py, int64_t capacity,
+                                 const int64_t* d_agent_total, int64_t* d_agent_offset, int32_t* d_status,
+                                 void* d_ws, size_t ws_bytes, void* stream);
+int mapmerge_append_slice(const double* d_sx, const double* d_sy, const int64_t* d_agent_offset,
+                          int agent, double* d_px, double* d_py, int64_t capacity,
+                          int64_t* d_count, int32_t* d_status, void* stream);
+
 /* GetMinBound/GetMaxBound of a cloud, also publish_global_map's bbox (:95-98):
  * d_bounds = {min_x, min_y, max_x, max_y}. */
 size_t mapmerge_bounds_workspace_bytes(void);

@@ -127,14 +127,16 @@ def _bind_merge(L):
     L.mapmerge_extract_batch_write.restype = C.c_int
     L.mapmerge_extract_batch_write.argtypes = [vp, i32, i32, i32, dbl, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, sz, vp]
     L.mapmerge_append_slice.restype = C.c_int
-    L.mapmerge_append_slice.argtypes = [vp, vp, vp, i32, vp, vp, i64, vp, vp, vp]
+    L.mapmerge_append_slice.argtypes = [vp, vp, vp, i32, vp, vp, i64, vp, vp, vp, vp]
     L.mapmerge_bounds_workspace_bytes.restype = sz
     L.mapmerge_bounds.restype = C.c_int
     L.mapmerge_bounds.argtypes = [vp, vp, vp, vp, vp, sz, vp]
     L.mapmerge_voxel_workspace_bytes.restype = sz
     L.mapmerge_voxel_workspace_bytes.argtypes = [i64, i64]
     L.mapmerge_voxel_downsample.restype = C.c_int
-    L.mapmerge_voxel_downsample.argtypes = [vp, vp, vp, i64, dbl, vp, i64, vp, vp, vp, vp, vp, sz, vp]
+    L.mapmerge_voxel_downsample.argtypes = [vp, vp, vp, i64, dbl, vp, vp, i64, vp, vp, vp, vp, vp, sz, vp]
+    L.mapmerge_bounds_enc_reset.restype = C.c_int
+    L.mapmerge_bounds_enc_reset.argtypes = [vp, vp]
     L.mapmerge_rasterise.restype = C.c_int
     L.mapmerge_rasterise.argtypes = [vp, vp, vp, dbl, vp, i32, i32, vp, vp]
     L.mapmerge_fuse_max.restype = C.c_int

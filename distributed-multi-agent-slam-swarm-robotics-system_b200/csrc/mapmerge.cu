@@ -164,6 +164,45 @@ k_extract_write(const int8_t* __restrict__ grid, long long n_cells, int width, d
     }
 }
 
+__device__ __forceinline__ double warp_min(double v);
+__device__ __forceinline__ double warp_max(double v);
+
+// ---- bounds carried on the device between callbacks ----------------------------------------
+// doubles mapped to uint64 keys that sort like the doubles, so min/max become integer atomics;
+// benc = {min_x, min_y, max_x, max_y} of the current cloud.
+__device__ __forceinline__ unsigned long long enc_double(double d) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dec_double(unsigned long long k) {
+    const unsigned long long u = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)u);
+}
+
+// Block-level min/max of (x, y) over the calling threads' values, then 4 atomics per CTA.
+__device__ __forceinline__ void block_bounds_atomic(double mnx, double mny, double mxx, double mxy,
+                                                    unsigned long long* __restrict__ benc) {
+    __shared__ double s_b[4][kMT / 32];
+    mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_b[0][warp] = mnx; s_b[1][warp] = mny; s_b[2][warp] = mxx; s_b[3][warp] = mxy; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kMT / 32; ++w) {
+            mnx = fmin(mnx, s_b[0][w]); mny = fmin(mny, s_b[1][w]); mxx = fmax(mxx, s_b[2][w]); mxy = fmax(mxy, s_b[3][w]);
+        }
+        if (mnx <= mxx) {
+            atomicMin(&benc[0], enc_double(mnx)); atomicMin(&benc[1], enc_double(mny));
+            atomicMax(&benc[2], enc_double(mxx)); atomicMax(&benc[3], enc_double(mxy));
+        }
+    }
+}
+
+__global__ void k_benc_reset(unsigned long long* __restrict__ benc) {
+    benc[0] = benc[1] = enc_double(INFINITY);
+    benc[2] = benc[3] = enc_double(-INFINITY);
+}
+
 // ---- batched extraction: all agent grids of a merge in one pass ----------------------------
 // grids[a] are A device pointers to H x W int8 maps; blockIdx.y = agent.  Output: every agent's
 // transformed points, agent after agent (row-major inside an agent), plus per-agent offsets —
@@ -254,15 +293,19 @@ k_batch_write(const int8_t* const* __restrict__ grids, long long n_cells, int wi
 __global__ void __launch_bounds__(kMT)
 k_append_slice(const double* __restrict__ sx, const double* __restrict__ sy, const long long* __restrict__ agent_offset, int a,
                double* __restrict__ px, double* __restrict__ py, long long capacity, long long* __restrict__ d_count,
-               int* __restrict__ status) {
+               int* __restrict__ status, unsigned long long* __restrict__ benc) {
     const long long b = agent_offset[a], e = agent_offset[a + 1];
     const long long n0 = *d_count;                  // read by every thread before the last block bumps it (see below)
     const long long k = e - b;
     if (n0 + k > capacity) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status, ST_POINT_OVERFLOW); return; }
+    double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
     for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < k; i += (long long)gridDim.x * kMT) {
-        px[n0 + i] = sx[b + i];
-        py[n0 + i] = sy[b + i];
+        const double x = sx[b + i], y = sy[b + i];
+        px[n0 + i] = x;
+        py[n0 + i] = y;
+        mnx = fmin(mnx, x); mxx = fmax(mxx, x); mny = fmin(mny, y); mxy = fmax(mxy, y);
     }
+    if (benc) block_bounds_atomic(mnx, mny, mxx, mxy, benc);
 }
 
 __global__ void k_bump_count(const long long* __restrict__ agent_offset, int a, long long capacity, long long* __restrict__ d_count) {
@@ -348,10 +391,19 @@ struct VoxelHeader {          // lives at the start of the voxel workspace
     unsigned int total_slots, total_voxels;
 };
 
-__global__ void k_voxel_setup(const double* __restrict__ bounds, const long long* __restrict__ d_count, double voxel,
+__global__ void k_voxel_setup(const double* __restrict__ bounds_in, unsigned long long* __restrict__ benc,
+                              const long long* __restrict__ d_count, double voxel,
                               long long capacity_cells, long long point_capacity, VoxelHeader* __restrict__ hdr,
                               int* __restrict__ status) {
     const long long n = *d_count;
+    double bounds[4];
+    if (benc) {                              // bounds carried on the device: decode, then reset for this call's output
+        for (int j = 0; j < 4; ++j) bounds[j] = dec_double(benc[j]);
+        benc[0] = benc[1] = enc_double(INFINITY);
+        benc[2] = benc[3] = enc_double(-INFINITY);
+    } else {
+        for (int j = 0; j < 4; ++j) bounds[j] = bounds_in[j];
+    }
     VoxelHeader h;
     h.n_points = n;
     h.total_slots = h.total_voxels = 0;
@@ -368,6 +420,8 @@ __global__ void k_voxel_setup(const double* __restrict__ bounds, const long long
     }
     *hdr = h;
 }
+
+constexpr unsigned int kSingle = 0xffffffffu;   // head[] marker: the point is alone in its voxel
 
 // lattice[k] = {first, cnt} share one 8-byte slot (one sector per point per pass)
 __global__ void __launch_bounds__(kMT)
@@ -389,11 +443,18 @@ k_voxel_mark(const double* __restrict__ px, const double* __restrict__ py, doubl
 // One lattice read per point: head[i] = index of the first point of i's voxel; hcnt[i] = size of
 // the voxel when i is that head, else 0.  Everything downstream streams these per-point arrays.
 __global__ void __launch_bounds__(kMT)
-k_voxel_gather(const VoxelHeader* __restrict__ hdr, const uint2* __restrict__ lattice, const unsigned int* __restrict__ key,
+k_voxel_gather(const VoxelHeader* __restrict__ hdr, uint2* __restrict__ lattice, const unsigned int* __restrict__ key,
                unsigned int* __restrict__ head, unsigned int* __restrict__ hcnt) {
     const long long n = hdr->n_points;
     for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
-        const uint2 v = lattice[key[i]];
+        const unsigned int k = key[i];
+        const uint2 v = lattice[k];
+        if (v.y == 1u) {                       // alone in its voxel (the common case): nothing to collect,
+            head[i] = kSingle;                 // and nobody else looks at this slot -> clean it right here
+            hcnt[i] = 1u;
+            lattice[k] = make_uint2(0u, 0u);
+            continue;
+        }
         const unsigned int h = 0xffffffffu - v.x;
         head[i] = h;
         hcnt[i] = (h == (unsigned int)i) ? v.y : 0u;
@@ -483,10 +544,12 @@ k_voxel_fill(const VoxelHeader* __restrict__ hdr, const unsigned int* __restrict
              const unsigned int* __restrict__ head, const unsigned int* __restrict__ soff, unsigned int* __restrict__ slots) {
     const long long n = hdr->n_points;
     for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
+        const unsigned int h = head[i];
+        if (h == kSingle) continue;                     // already finished (and cleaned) by the gather pass
         const unsigned int k = key[i];
         const unsigned int r = atomicSub(&lattice[k].y, 1u) - 1u;
         if (r == 0u) lattice[k].x = 0u;                 // last ticket: nobody reads first[] any more
-        slots[soff[head[i]] + r] = (unsigned int)i;
+        slots[soff[h] + r] = (unsigned int)i;
     }
 }
 
@@ -494,9 +557,11 @@ __global__ void __launch_bounds__(kMT)
 k_voxel_reduce(const double* __restrict__ px, const double* __restrict__ py, const VoxelHeader* __restrict__ hdr,
                const unsigned int* __restrict__ hcnt, const unsigned int* __restrict__ vrank,
                const unsigned int* __restrict__ soff, const unsigned int* __restrict__ slots,
-               double* __restrict__ out_x, double* __restrict__ out_y, long long* __restrict__ out_count) {
+               double* __restrict__ out_x, double* __restrict__ out_y, long long* __restrict__ out_count,
+               unsigned long long* __restrict__ benc) {
     const long long n = hdr->n_points;
     if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = (long long)hdr->total_voxels;
+    double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
     for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
         const unsigned int c = hcnt[i];
         if (c == 0u) continue;                          // not a head
@@ -516,9 +581,12 @@ k_voxel_reduce(const double* __restrict__ px, const double* __restrict__ py, con
             }
         }
         const double cnt = (double)c;
-        out_x[vrank[i]] = OCC_DDIV(sx, cnt);
-        out_y[vrank[i]] = OCC_DDIV(sy, cnt);
+        const double ox_ = OCC_DDIV(sx, cnt), oy_ = OCC_DDIV(sy, cnt);
+        out_x[vrank[i]] = ox_;
+        out_y[vrank[i]] = oy_;
+        mnx = fmin(mnx, ox_); mxx = fmax(mxx, ox_); mny = fmin(mny, oy_); mxy = fmax(mxy, oy_);
     }
+    if (benc) block_bounds_atomic(mnx, mny, mxx, mxy, benc);
 }
 
 // ---- a12: publish_global_map rasterise (:103-111) -----------------------------------------
@@ -680,8 +748,16 @@ int mapmerge_extract_batch_write(const int8_t* const* d_grids, int n_agents, int
     return OCCGRID_OK;
 }
 
+int mapmerge_bounds_enc_reset(uint64_t* d_bounds_enc, void* stream) {
+    if (!d_bounds_enc) { set_last_error("mapmerge_bounds_enc_reset: NULL"); return OCCGRID_E_ARG; }
+    k_benc_reset<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)d_bounds_enc);
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
+}
+
 int mapmerge_append_slice(const double* d_sx, const double* d_sy, const int64_t* d_agent_offset, int agent,
-                          double* d_px, double* d_py, int64_t capacity, int64_t* d_count, int32_t* d_status, void* stream) {
+                          double* d_px, double* d_py, int64_t capacity, int64_t* d_count, int32_t* d_status,
+                          uint64_t* d_bounds_enc, void* stream) {
     if (!d_sx || !d_sy || !d_agent_offset || agent < 0 || !d_px || !d_py || !d_count || !d_status) {
         set_last_error("mapmerge_append_slice: bad arguments");
         return OCCGRID_E_ARG;
@@ -689,7 +765,7 @@ int mapmerge_append_slice(const double* d_sx, const double* d_sy, const int64_t*
     cudaStream_t st = (cudaStream_t)stream;
     ProfileScope ps(K_MERGE_EXTRACT, st, 2);
     k_append_slice<<<148, kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, agent, d_px, d_py, capacity,
-                                         (long long*)d_count, d_status);
+                                         (long long*)d_count, d_status, (unsigned long long*)d_bounds_enc);
     k_bump_count<<<1, 1, 0, st>>>((const long long*)d_agent_offset, agent, capacity, (long long*)d_count);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
@@ -730,10 +806,10 @@ size_t mapmerge_voxel_workspace_bytes(int64_t lattice_capacity_cells, int64_t po
 }
 
 int mapmerge_voxel_downsample(const double* d_px, const double* d_py, const int64_t* d_count, int64_t point_capacity,
-                              double voxel, const double* d_bounds, int64_t lattice_capacity_cells,
+                              double voxel, const double* d_bounds, uint64_t* d_bounds_enc, int64_t lattice_capacity_cells,
                               double* d_out_px, double* d_out_py, int64_t* d_out_count, int32_t* d_status,
                               void* d_ws, size_t ws_bytes, void* stream) {
-    if (!d_px || !d_py || !d_count || !d_bounds || !d_out_px || !d_out_py || !d_out_count || !d_status || !d_ws ||
+    if (!d_px || !d_py || !d_count || (!d_bounds && !d_bounds_enc) || !d_out_px || !d_out_py || !d_out_count || !d_status || !d_ws ||
         !(voxel > 0.0) || lattice_capacity_cells <= 0 || point_capacity <= 0) {
         set_last_error("mapmerge_voxel_downsample: bad arguments");
         return OCCGRID_E_ARG;
@@ -757,14 +833,16 @@ int mapmerge_voxel_downsample(const double* d_px, const double* d_py, const int6
     const int gp = grid_for(point_capacity);
     const int gs = grid_for((point_capacity + kScanItems - 1) / kScanItems);
     ProfileScope ps(K_MERGE_VOXEL, st, 8);
-    k_voxel_setup<<<1, 1, 0, st>>>(d_bounds, (const long long*)d_count, voxel, lattice_capacity_cells, point_capacity, hdr, d_status);
+    k_voxel_setup<<<1, 1, 0, st>>>(d_bounds, (unsigned long long*)d_bounds_enc, (const long long*)d_count, voxel,
+                                   lattice_capacity_cells, point_capacity, hdr, d_status);
     k_voxel_mark<<<gp, kMT, 0, st>>>(d_px, d_py, voxel, hdr, lattice, key);
     k_voxel_gather<<<gp, kMT, 0, st>>>(hdr, lattice, key, head, hcnt);
     k_pscan_partial<<<gs, kMT, 0, st>>>(hdr, hcnt, block_sums);
     k_pscan_top<<<1, 1024, 0, st>>>(block_sums, hdr);
     k_pscan_apply<<<gs, kMT, 0, st>>>(hdr, hcnt, block_sums, vrank, soff);
     k_voxel_fill<<<gp, kMT, 0, st>>>(hdr, key, lattice, head, soff, slots);
-    k_voxel_reduce<<<gp, kMT, 0, st>>>(d_px, d_py, hdr, hcnt, vrank, soff, slots, d_out_px, d_out_py, (long long*)d_out_count);
+    k_voxel_reduce<<<gp, kMT, 0, st>>>(d_px, d_py, hdr, hcnt, vrank, soff, slots, d_out_px, d_out_py, (long long*)d_out_count,
+                                       (unsigned long long*)d_bounds_enc);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
 }

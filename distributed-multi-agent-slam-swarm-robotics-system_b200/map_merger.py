@@ -156,11 +156,12 @@ class MapMerger:
                                        self._bounds.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
         _native.check(rc, 'mapmerge_bounds')
 
-    def _voxel_downsample(self, lattice_cells=None, sync=True):
+    def _voxel_downsample(self, lattice_cells=None, sync=True, benc=None):
         """global_pcd = global_pcd.voxel_down_sample(map_resolution)  (:60).  `lattice_cells`: a
         conservative bound on the voxel lattice known to the caller (batched merge, no host round
         trip); otherwise the bounds are read back to size it."""
-        self._bounds_of(self._cloud)
+        if benc is None:
+            self._bounds_of(self._cloud)
         v = self.map_resolution
         if lattice_cells is None:
             b = self._bounds.cpu().numpy()
@@ -177,7 +178,8 @@ class MapMerger:
         ws = self._workspace('voxel', need, zero=True)
         rc = self._lib.mapmerge_voxel_downsample(
             self._cloud.x.data_ptr(), self._cloud.y.data_ptr(), self._cloud.count.data_ptr(), self._cloud.capacity,
-            v, self._bounds.data_ptr(), self._lattice_cap, self._spare.x.data_ptr(), self._spare.y.data_ptr(),
+            v, self._bounds.data_ptr(), benc.data_ptr() if benc is not None else None, self._lattice_cap,
+            self._spare.x.data_ptr(), self._spare.y.data_ptr(),
             self._spare.count.data_ptr(), self._status.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
         _native.check(rc, 'mapmerge_voxel_downsample')
         self._cloud, self._spare = self._spare, self._cloud
@@ -329,6 +331,12 @@ class MapMerger:
                     stage.x.data_ptr(), stage.y.data_ptr(), stage.capacity, counts.data_ptr(), offs.data_ptr(),
                     self._status.data_ptr(), bws.data_ptr(), bws.numel(), self._stream())
                 _native.check(rc, 'mapmerge_extract_batch_write')
+            # bounds of the cloud live on the device for the whole chain when it starts from an empty
+            # merger and uses the batched slices (no min/max pass, no host read per callback)
+            benc = None
+            if same_shape and self._n_global == 0:
+                benc = torch.zeros(4, dtype=torch.int64, device=self.device)
+                _native.check(self._lib.mapmerge_bounds_enc_reset(benc.data_ptr(), self._stream()), 'mapmerge_bounds_enc_reset')
             for a in range(A):
                 use, T = mats[a]
                 if not use:
@@ -336,7 +344,8 @@ class MapMerger:
                 if same_shape:
                     rc = self._lib.mapmerge_append_slice(stage.x.data_ptr(), stage.y.data_ptr(), offs.data_ptr(), a,
                                                          self._cloud.x.data_ptr(), self._cloud.y.data_ptr(), self._cloud.capacity,
-                                                         self._cloud.count.data_ptr(), self._status.data_ptr(), self._stream())
+                                                         self._cloud.count.data_ptr(), self._status.data_ptr(),
+                                                         benc.data_ptr() if benc is not None else None, self._stream())
                     _native.check(rc, 'mapmerge_append_slice')
                 else:
                     h, w = dev[a].shape
@@ -346,7 +355,7 @@ class MapMerger:
                     self.map_resolution = float(res)
                     self.map_origin = [float(origins[a][0]), float(origins[a][1])]
                 else:
-                    self._voxel_downsample(lattice_cells=cells, sync=False)
+                    self._voxel_downsample(lattice_cells=cells, sync=False, benc=benc)
             self._n_global = int(self._cloud.count.item())          # host sync 2 (with the status word)
             self._check_status()
         out = self.publish_global_map(to_host=to_host)

@@ -243,7 +243,14 @@ int mapmerge_extract_batch_write(const int8_t* const* d_grids, int n_agents, int
                                  void* d_ws, size_t ws_bytes, void* stream);
 int mapmerge_append_slice(const double* d_sx, const double* d_sy, const int64_t* d_agent_offset,
                           int agent, double* d_px, double* d_py, int64_t capacity,
-                          int64_t* d_count, int32_t* d_status, void* stream);
+                          int64_t* d_count, int32_t* d_status, uint64_t* d_bounds_enc, void* stream);
+
+/* Bounds carried on the device across the callbacks of a batched merge (no min/max pass, no host
+ * read): d_bounds_enc = uint64[4], order-preserving encodings of {min_x, min_y, max_x, max_y} of
+ * the current cloud.  _reset empties it; mapmerge_append_slice widens it by the appended points;
+ * mapmerge_voxel_downsample (when given it instead of d_bounds) consumes it as the bounds of its
+ * input and leaves the bounds of its output in it. */
+int mapmerge_bounds_enc_reset(uint64_t* d_bounds_enc, void* stream);
 
 /* GetMinBound/GetMaxBound of a cloud, also publish_global_map's bbox (:95-98):
  * d_bounds = {min_x, min_y, max_x, max_y}. */
@@ -261,6 +268,7 @@ int mapmerge_bounds(const double* d_px, const double* d_py, const int64_t* d_cou
 size_t mapmerge_voxel_workspace_bytes(int64_t lattice_capacity_cells, int64_t point_capacity);
 int mapmerge_voxel_downsample(const double* d_px, const double* d_py, const int64_t* d_count,
                               int64_t point_capacity, double voxel, const double* d_bounds,
+                              uint64_t* d_bounds_enc /* NULL: use d_bounds */,
                               int64_t lattice_capacity_cells,
                               double* d_out_px, double* d_out_py, int64_t* d_out_count,
                               int32_t* d_status, void* d_ws, size_t ws_bytes, void* stream);

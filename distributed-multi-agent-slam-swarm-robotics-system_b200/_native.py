@@ -137,6 +137,16 @@ def _bind_merge(L):
     L.mapmerge_voxel_downsample.argtypes = [vp, vp, vp, i64, dbl, vp, vp, i64, vp, vp, vp, vp, vp, sz, vp]
     L.mapmerge_bounds_enc_reset.restype = C.c_int
     L.mapmerge_bounds_enc_reset.argtypes = [vp, vp]
+    L.mapmerge_chain_workspace_bytes.restype = sz
+    L.mapmerge_chain_workspace_bytes.argtypes = [vp]
+    L.mapmerge_chain_init.restype = C.c_int
+    L.mapmerge_chain_init.argtypes = [vp, sz, vp, vp, vp, vp, vp]
+    L.mapmerge_chain_probe.restype = C.c_int
+    L.mapmerge_chain_probe.argtypes = [vp, vp, vp, vp, vp, i32, i64, dbl, vp, vp, vp, vp]
+    L.mapmerge_chain_incremental.restype = C.c_int
+    L.mapmerge_chain_incremental.argtypes = [vp, vp, vp, vp, vp, i32, i64, dbl, vp, vp, i64, vp, vp, vp, sz, i64, vp]
+    L.mapmerge_chain_rebuild.restype = C.c_int
+    L.mapmerge_chain_rebuild.argtypes = [vp, vp, vp, vp, vp, i32, dbl, vp, vp, i64, vp, vp, vp, vp, vp, vp, sz, i64, vp]
     L.mapmerge_rasterise.restype = C.c_int
     L.mapmerge_rasterise.argtypes = [vp, vp, vp, dbl, vp, i32, i32, vp, vp]
     L.mapmerge_fuse_max.restype = C.c_int

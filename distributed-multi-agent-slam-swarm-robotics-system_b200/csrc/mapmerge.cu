@@ -589,6 +589,230 @@ k_voxel_reduce(const double* __restrict__ px, const double* __restrict__ py, con
     if (benc) block_bounds_atomic(mnx, mny, mxx, mxy, benc);
 }
 
+// ---- incremental voxel chain ---------------------------------------------------------------
+// The reference voxel-filters the WHOLE accumulated cloud on every callback (:58-60).  Once a
+// cloud G has been filtered under a lattice L (anchor = min_bound - voxel/2) it holds one point
+// per voxel, and filtering G u S under the SAME lattice only changes the voxels S falls into:
+// every other point is alone in its voxel and p / 1.0 == p.  So while the anchor stays bitwise
+// equal, a callback only has to
+//   - look every slice point up in a persistent voxel -> cloud-index map (LM),
+//   - run the ordinary filter on the mini cloud  [touched G points] ++ [slice]  (a touched G
+//     point is the head of its voxel, slice points follow in order: same sums, same order),
+//   - write the means back in place and append the new voxels in order of first appearance.
+// When the anchor moves (the cloud's min corner changed), or a mean lands in another voxel than
+// its points, the callback falls back to the full filter and rebuilds LM.  Results are bitwise
+// those of the full chain; the decision is taken on the device and read by the host (4 bytes).
+
+struct ChainHeader {
+    VoxelHeader v;                       // lattice + point count the voxel kernels of this callback see
+    double mbx, mby;                     // anchor LM / gkey are valid for
+    double new_mbx, new_mby;             // anchor this callback needs
+    unsigned long long gb_enc[4];        // bounds of the cloud (encoded, see enc_double)
+    unsigned long long gb2_enc[4];       // scratch for a full recompute
+    unsigned long long lb_enc[4];        // bounds of the slice of this callback
+    long long n_next;                    // cloud size after this callback
+    long long mini_count;                // output count of the mini filter (unused by the host)
+    unsigned int n_aff;                  // touched cloud points of this callback
+    int have_lattice, force_rebuild, need_rebuild, bounds_dirty;
+};
+constexpr unsigned int kTouched = 0x80000000u;
+
+__device__ __forceinline__ bool voxel_key_of(double x, double y, double mbx, double mby, double voxel, long long W,
+                                             long long H, unsigned int* key) {
+    const long long ix = (long long)floor(OCC_DDIV(OCC_DADD(x, -mbx), voxel));
+    const long long iy = (long long)floor(OCC_DDIV(OCC_DADD(y, -mby), voxel));
+    if (ix < 0 || iy < 0 || ix >= W || iy >= H) return false;
+    *key = (unsigned int)(iy * W + ix);
+    return true;
+}
+
+__global__ void k_chain_reset(ChainHeader* __restrict__ h) {
+    h->gb_enc[0] = h->gb_enc[1] = h->gb2_enc[0] = h->gb2_enc[1] = h->lb_enc[0] = h->lb_enc[1] = enc_double(INFINITY);
+    h->gb_enc[2] = h->gb_enc[3] = h->gb2_enc[2] = h->gb2_enc[3] = h->lb_enc[2] = h->lb_enc[3] = enc_double(-INFINITY);
+    h->have_lattice = h->force_rebuild = h->need_rebuild = 0;
+    h->bounds_dirty = 1;                 // the first k_chain_rebounds computes the bounds of the adopted cloud
+    h->n_aff = 0;
+}
+
+__global__ void __launch_bounds__(kMT)
+k_chain_slice_bounds(const double* __restrict__ sx, const double* __restrict__ sy, const long long* __restrict__ agent_offset,
+                     int a, ChainHeader* __restrict__ h) {
+    const long long b = agent_offset[a], e = agent_offset[a + 1];
+    double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (long long i = b + (long long)blockIdx.x * kMT + threadIdx.x; i < e; i += (long long)gridDim.x * kMT) {
+        const double x = sx[i], y = sy[i];
+        mnx = fmin(mnx, x); mxx = fmax(mxx, x); mny = fmin(mny, y); mxy = fmax(mxy, y);
+    }
+    block_bounds_atomic(mnx, mny, mxx, mxy, h->lb_enc);
+}
+
+__global__ void k_chain_setup(ChainHeader* __restrict__ h, const long long* __restrict__ d_count, double voxel, long long W,
+                              long long H, int* __restrict__ status) {
+    const double b0 = fmin(dec_double(h->gb_enc[0]), dec_double(h->lb_enc[0]));
+    const double b1 = fmin(dec_double(h->gb_enc[1]), dec_double(h->lb_enc[1]));
+    const double b2 = fmax(dec_double(h->gb_enc[2]), dec_double(h->lb_enc[2]));
+    const double b3 = fmax(dec_double(h->gb_enc[3]), dec_double(h->lb_enc[3]));
+    const double nmbx = OCC_DADD(b0, -OCC_DMUL(voxel, 0.5));
+    const double nmby = OCC_DADD(b1, -OCC_DMUL(voxel, 0.5));
+    const long long nx = (long long)floor(OCC_DDIV(OCC_DADD(b2, -nmbx), voxel)) + 1;
+    const long long ny = (long long)floor(OCC_DDIV(OCC_DADD(b3, -nmby), voxel)) + 1;
+    int need;
+    if (!(nx > 0 && ny > 0 && nx <= W && ny <= H) || *d_count <= 0) {
+        atomicOr(status, ST_LATTICE_OVERFLOW);
+        need = 2;
+    } else {
+        need = (!h->have_lattice || h->force_rebuild || nmbx != h->mbx || nmby != h->mby) ? 1 : 0;
+    }
+    h->new_mbx = nmbx; h->new_mby = nmby;
+    h->need_rebuild = need;
+    h->n_aff = 0;
+    h->v.mbx = nmbx; h->v.mby = nmby;
+    h->v.nx = W; h->v.ny = H; h->v.cells = W * H;
+    h->v.n_points = 0;
+    h->v.total_slots = h->v.total_voxels = 0;
+}
+
+// Slice points that fall into a voxel the cloud already occupies pull that cloud point into the
+// mini cloud (once: the top bit of the LM entry marks "already pulled").
+__global__ void __launch_bounds__(kMT)
+k_chain_lookup(const double* __restrict__ sx, const double* __restrict__ sy, const long long* __restrict__ agent_offset, int a,
+               double voxel, ChainHeader* __restrict__ h, unsigned int* __restrict__ LM, const double* __restrict__ gx,
+               const double* __restrict__ gy, double* __restrict__ mx, double* __restrict__ my,
+               unsigned int* __restrict__ msrc, int* __restrict__ status) {
+    const long long b = agent_offset[a], e = agent_offset[a + 1];
+    const double mbx = h->v.mbx, mby = h->v.mby;
+    const long long W = h->v.nx, H = h->v.ny;
+    for (long long i = b + (long long)blockIdx.x * kMT + threadIdx.x; i < e; i += (long long)gridDim.x * kMT) {
+        unsigned int k;
+        if (!voxel_key_of(sx[i], sy[i], mbx, mby, voxel, W, H, &k)) { atomicOr(status, ST_LATTICE_OVERFLOW); continue; }
+        if ((LM[k] & ~kTouched) == 0u) continue;
+        const unsigned int old = atomicOr(&LM[k], kTouched);
+        if (old & kTouched) continue;
+        const unsigned int g = (old & ~kTouched) - 1u;
+        const unsigned int pos = atomicAdd(&h->n_aff, 1u);
+        msrc[pos] = g;
+        mx[pos] = gx[g];
+        my[pos] = gy[g];
+    }
+}
+
+__global__ void __launch_bounds__(kMT)
+k_chain_copy_slice(const double* __restrict__ sx, const double* __restrict__ sy, const long long* __restrict__ agent_offset,
+                   int a, ChainHeader* __restrict__ h, double* __restrict__ mx, double* __restrict__ my) {
+    const long long b = agent_offset[a], n = agent_offset[a + 1] - b;
+    const long long base = (long long)h->n_aff;
+    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
+        mx[base + i] = sx[b + i];
+        my[base + i] = sy[b + i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) h->v.n_points = base + n;
+}
+
+// Means of the mini filter go back: ranks < n_aff are the touched cloud points (each the head of
+// its own voxel, in mini-cloud order), the rest are new voxels in order of first appearance.
+__global__ void __launch_bounds__(kMT)
+k_chain_writeback(ChainHeader* __restrict__ h, const double* __restrict__ ox, const double* __restrict__ oy,
+                  const unsigned int* __restrict__ msrc, double* __restrict__ gx, double* __restrict__ gy,
+                  unsigned int* __restrict__ gkey, unsigned int* __restrict__ LM, double voxel,
+                  const long long* __restrict__ d_count, long long capacity, int* __restrict__ status) {
+    const long long n_aff = (long long)h->n_aff, total = (long long)h->v.total_voxels, n_g = *d_count;
+    const double mbx = h->v.mbx, mby = h->v.mby;
+    const long long W = h->v.nx, H = h->v.ny;
+    const double g0 = dec_double(h->gb_enc[0]), g1 = dec_double(h->gb_enc[1]);
+    double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (long long r = (long long)blockIdx.x * kMT + threadIdx.x; r < total; r += (long long)gridDim.x * kMT) {
+        const double x = ox[r], y = oy[r];
+        unsigned int k = 0;
+        const bool ok = voxel_key_of(x, y, mbx, mby, voxel, W, H, &k);
+        if (r < n_aff) {
+            const unsigned int g = msrc[r];
+            // a point sitting on the min corner may move inwards: the bounds then need a full pass
+            if (gx[g] <= g0 || gy[g] <= g1) h->bounds_dirty = 1;
+            gx[g] = x; gy[g] = y;
+            const unsigned int kold = gkey[g];
+            LM[kold] = g + 1u;                              // drops the "pulled" bit
+            if (!ok || k != kold) h->force_rebuild = 1;     // the mean left its voxel: LM no longer describes the cloud
+        } else {
+            const long long idx = n_g + (r - n_aff);
+            if (idx >= capacity) { atomicOr(status, ST_POINT_OVERFLOW); continue; }
+            gx[idx] = x; gy[idx] = y;
+            if (!ok) { h->force_rebuild = 1; gkey[idx] = 0xffffffffu; continue; }
+            gkey[idx] = k;
+            if (atomicExch(&LM[k], (unsigned int)idx + 1u) != 0u) h->force_rebuild = 1;
+        }
+        mnx = fmin(mnx, x); mxx = fmax(mxx, x); mny = fmin(mny, y); mxy = fmax(mxy, y);
+    }
+    block_bounds_atomic(mnx, mny, mxx, mxy, h->gb_enc);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        long long nn = n_g + (total - n_aff);
+        h->n_next = nn > capacity ? capacity : nn;
+    }
+}
+
+// Full min/max pass, only when a callback may have moved the min corner inwards (or at start).
+__global__ void __launch_bounds__(kMT)
+k_chain_rebounds(const double* __restrict__ gx, const double* __restrict__ gy, const long long* __restrict__ n_ptr,
+                 ChainHeader* __restrict__ h) {
+    if (!h->bounds_dirty) return;
+    const long long n = *n_ptr;
+    double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
+        const double x = gx[i], y = gy[i];
+        mnx = fmin(mnx, x); mxx = fmax(mxx, x); mny = fmin(mny, y); mxy = fmax(mxy, y);
+    }
+    block_bounds_atomic(mnx, mny, mxx, mxy, h->gb2_enc);
+}
+
+// mode 0: after init/adopt, 1: after an incremental callback, 2: after a rebuild
+__global__ void k_chain_final(ChainHeader* __restrict__ h, long long* __restrict__ d_count, int mode) {
+    if (h->bounds_dirty) {
+        for (int j = 0; j < 4; ++j) h->gb_enc[j] = h->gb2_enc[j];
+        h->bounds_dirty = 0;
+    }
+    h->gb2_enc[0] = h->gb2_enc[1] = h->lb_enc[0] = h->lb_enc[1] = enc_double(INFINITY);
+    h->gb2_enc[2] = h->gb2_enc[3] = h->lb_enc[2] = h->lb_enc[3] = enc_double(-INFINITY);
+    if (mode == 1) *d_count = h->n_next;
+    if (mode == 2) { h->mbx = h->new_mbx; h->mby = h->new_mby; h->have_lattice = 1; }
+    h->need_rebuild = 0;
+    h->n_aff = 0;
+}
+
+__global__ void __launch_bounds__(kMT)
+k_chain_lm_clear(ChainHeader* __restrict__ h, unsigned int* __restrict__ LM, const unsigned int* __restrict__ gkey,
+                 const long long* __restrict__ d_count) {
+    if (!h->have_lattice) return;
+    const long long n = *d_count;
+    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
+        const unsigned int k = gkey[i];
+        if (k != 0xffffffffu) LM[k] = 0u;
+    }
+}
+
+__global__ void k_chain_rebuild_hdr(ChainHeader* __restrict__ h, const long long* __restrict__ d_count, long long point_capacity,
+                                    int* __restrict__ status) {
+    long long n = *d_count;
+    if (n > point_capacity || n >= 0x7ffffff0ll) { atomicOr(status, ST_POINT_OVERFLOW); n = 0; }
+    h->v.n_points = n;
+    h->force_rebuild = 0;
+    h->gb_enc[0] = h->gb_enc[1] = enc_double(INFINITY);     // the filter's reduce pass rebuilds them
+    h->gb_enc[2] = h->gb_enc[3] = enc_double(-INFINITY);
+}
+
+__global__ void __launch_bounds__(kMT)
+k_chain_lm_build(ChainHeader* __restrict__ h, const double* __restrict__ gx, const double* __restrict__ gy,
+                 const long long* __restrict__ d_count, double voxel, unsigned int* __restrict__ LM,
+                 unsigned int* __restrict__ gkey) {
+    const long long n = *d_count;
+    const double mbx = h->v.mbx, mby = h->v.mby;
+    const long long W = h->v.nx, H = h->v.ny;
+    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
+        unsigned int k;
+        if (!voxel_key_of(gx[i], gy[i], mbx, mby, voxel, W, H, &k)) { gkey[i] = 0xffffffffu; h->force_rebuild = 1; continue; }
+        gkey[i] = k;
+        if (atomicExch(&LM[k], (unsigned int)i + 1u) != 0u) h->force_rebuild = 1;   // a mean drifted into a neighbour's voxel
+    }
+}
+
 // ---- a12: publish_global_map rasterise (:103-111) -----------------------------------------
 
 __global__ void __launch_bounds__(kMT)
@@ -805,6 +1029,43 @@ size_t mapmerge_voxel_workspace_bytes(int64_t lattice_capacity_cells, int64_t po
     return voxel_layout(lattice_capacity_cells, point_capacity, off);
 }
 
+struct VoxelArrays {
+    VoxelHeader* hdr;
+    uint2* lattice;
+    uint2* block_sums;
+    unsigned int *key, *head, *hcnt, *vrank, *soff, *slots;
+};
+
+static VoxelArrays voxel_arrays(void* d_ws, const size_t off[9]) {
+    char* ws = reinterpret_cast<char*>(d_ws);
+    VoxelArrays a;
+    a.hdr = reinterpret_cast<VoxelHeader*>(ws + off[0]);
+    a.lattice = reinterpret_cast<uint2*>(ws + off[1]);
+    a.block_sums = reinterpret_cast<uint2*>(ws + off[2]);
+    a.key = reinterpret_cast<unsigned int*>(ws + off[3]);
+    a.head = reinterpret_cast<unsigned int*>(ws + off[4]);
+    a.hcnt = reinterpret_cast<unsigned int*>(ws + off[5]);
+    a.vrank = reinterpret_cast<unsigned int*>(ws + off[6]);
+    a.soff = reinterpret_cast<unsigned int*>(ws + off[7]);
+    a.slots = reinterpret_cast<unsigned int*>(ws + off[8]);
+    return a;
+}
+
+// mark .. reduce (7 launches) over the points `hdr` describes; `launch_points` sizes the grids.
+static void launch_voxel_core(const double* px, const double* py, const VoxelHeader* hdr_c, VoxelHeader* hdr, const VoxelArrays& a,
+                              int64_t launch_points, double voxel, double* out_px, double* out_py, long long* out_count,
+                              unsigned long long* benc, cudaStream_t st) {
+    const int gp = grid_for(launch_points);
+    const int gs = grid_for((launch_points + kScanItems - 1) / kScanItems);
+    k_voxel_mark<<<gp, kMT, 0, st>>>(px, py, voxel, hdr_c, a.lattice, a.key);
+    k_voxel_gather<<<gp, kMT, 0, st>>>(hdr_c, a.lattice, a.key, a.head, a.hcnt);
+    k_pscan_partial<<<gs, kMT, 0, st>>>(hdr_c, a.hcnt, a.block_sums);
+    k_pscan_top<<<1, 1024, 0, st>>>(a.block_sums, hdr);
+    k_pscan_apply<<<gs, kMT, 0, st>>>(hdr_c, a.hcnt, a.block_sums, a.vrank, a.soff);
+    k_voxel_fill<<<gp, kMT, 0, st>>>(hdr_c, a.key, a.lattice, a.head, a.soff, a.slots);
+    k_voxel_reduce<<<gp, kMT, 0, st>>>(px, py, hdr_c, a.hcnt, a.vrank, a.soff, a.slots, out_px, out_py, out_count, benc);
+}
+
 int mapmerge_voxel_downsample(const double* d_px, const double* d_py, const int64_t* d_count, int64_t point_capacity,
                               double voxel, const double* d_bounds, uint64_t* d_bounds_enc, int64_t lattice_capacity_cells,
                               double* d_out_px, double* d_out_py, int64_t* d_out_count, int32_t* d_status,
@@ -819,30 +1080,165 @@ int mapmerge_voxel_downsample(const double* d_px, const double* d_py, const int6
         set_last_error("mapmerge_voxel_downsample: workspace too small");
         return OCCGRID_E_WORKSPACE;
     }
-    char* ws = reinterpret_cast<char*>(d_ws);
-    VoxelHeader* hdr = reinterpret_cast<VoxelHeader*>(ws + off[0]);
-    uint2* lattice = reinterpret_cast<uint2*>(ws + off[1]);
-    uint2* block_sums = reinterpret_cast<uint2*>(ws + off[2]);
-    unsigned int* key = reinterpret_cast<unsigned int*>(ws + off[3]);
-    unsigned int* head = reinterpret_cast<unsigned int*>(ws + off[4]);
-    unsigned int* hcnt = reinterpret_cast<unsigned int*>(ws + off[5]);
-    unsigned int* vrank = reinterpret_cast<unsigned int*>(ws + off[6]);
-    unsigned int* soff = reinterpret_cast<unsigned int*>(ws + off[7]);
-    unsigned int* slots = reinterpret_cast<unsigned int*>(ws + off[8]);
+    const VoxelArrays a = voxel_arrays(d_ws, off);
     cudaStream_t st = (cudaStream_t)stream;
-    const int gp = grid_for(point_capacity);
-    const int gs = grid_for((point_capacity + kScanItems - 1) / kScanItems);
     ProfileScope ps(K_MERGE_VOXEL, st, 8);
     k_voxel_setup<<<1, 1, 0, st>>>(d_bounds, (unsigned long long*)d_bounds_enc, (const long long*)d_count, voxel,
-                                   lattice_capacity_cells, point_capacity, hdr, d_status);
-    k_voxel_mark<<<gp, kMT, 0, st>>>(d_px, d_py, voxel, hdr, lattice, key);
-    k_voxel_gather<<<gp, kMT, 0, st>>>(hdr, lattice, key, head, hcnt);
-    k_pscan_partial<<<gs, kMT, 0, st>>>(hdr, hcnt, block_sums);
-    k_pscan_top<<<1, 1024, 0, st>>>(block_sums, hdr);
-    k_pscan_apply<<<gs, kMT, 0, st>>>(hdr, hcnt, block_sums, vrank, soff);
-    k_voxel_fill<<<gp, kMT, 0, st>>>(hdr, key, lattice, head, soff, slots);
-    k_voxel_reduce<<<gp, kMT, 0, st>>>(d_px, d_py, hdr, hcnt, vrank, soff, slots, d_out_px, d_out_py, (long long*)d_out_count,
-                                       (unsigned long long*)d_bounds_enc);
+                                   lattice_capacity_cells, point_capacity, a.hdr, d_status);
+    launch_voxel_core(d_px, d_py, a.hdr, a.hdr, a, point_capacity, voxel, d_out_px, d_out_py, (long long*)d_out_count,
+                      (unsigned long long*)d_bounds_enc, st);
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
+}
+
+// ---- incremental voxel chain: entry points --------------------------------------------------
+// dims = {lattice_w, lattice_h, point_capacity, slice_capacity} (host array), the same for every
+// call on one chain workspace.
+struct ChainArrays {
+    ChainHeader* h;
+    unsigned int *LM, *gkey, *msrc;
+    double *mx, *my, *ox, *oy;
+};
+
+static size_t chain_layout(const int64_t* dims, ChainArrays* a, void* base) {
+    const size_t cells = (size_t)dims[0] * (size_t)dims[1], points = (size_t)dims[2], mini = 2 * (size_t)dims[3] + 16;
+    char* ws = reinterpret_cast<char*>(base);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return at; };
+    const size_t o_h = take(sizeof(ChainHeader)), o_lm = take((cells + 1) * 4), o_gk = take(points * 4), o_ms = take(mini * 4);
+    const size_t o_mx = take(mini * 8), o_my = take(mini * 8), o_ox = take(mini * 8), o_oy = take(mini * 8);
+    if (a) {
+        a->h = reinterpret_cast<ChainHeader*>(ws + o_h);
+        a->LM = reinterpret_cast<unsigned int*>(ws + o_lm);
+        a->gkey = reinterpret_cast<unsigned int*>(ws + o_gk);
+        a->msrc = reinterpret_cast<unsigned int*>(ws + o_ms);
+        a->mx = reinterpret_cast<double*>(ws + o_mx); a->my = reinterpret_cast<double*>(ws + o_my);
+        a->ox = reinterpret_cast<double*>(ws + o_ox); a->oy = reinterpret_cast<double*>(ws + o_oy);
+    }
+    return o;
+}
+
+static bool chain_dims_ok(const int64_t* dims) {
+    return dims && dims[0] > 0 && dims[1] > 0 && dims[2] > 0 && dims[3] > 0 && dims[0] * dims[1] < 0x7fffffffll &&
+           dims[2] < 0x7ffffff0ll;
+}
+
+size_t mapmerge_chain_workspace_bytes(const int64_t* dims) {
+    if (!chain_dims_ok(dims)) return 0;
+    return chain_layout(dims, nullptr, nullptr);
+}
+
+// The workspace must be all-zero when a chain starts.  Computes the bounds of the adopted cloud.
+int mapmerge_chain_init(void* d_chain, size_t chain_bytes, const int64_t* dims, const double* d_px, const double* d_py,
+                        int64_t* d_count, void* stream) {
+    if (!d_chain || !chain_dims_ok(dims) || !d_px || !d_py || !d_count) { set_last_error("mapmerge_chain_init: bad arguments"); return OCCGRID_E_ARG; }
+    if (chain_bytes < chain_layout(dims, nullptr, nullptr)) { set_last_error("mapmerge_chain_init: workspace too small"); return OCCGRID_E_WORKSPACE; }
+    ChainArrays c;
+    chain_layout(dims, &c, d_chain);
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfileScope ps(K_MERGE_BOUNDS, st, 3);
+    k_chain_reset<<<1, 1, 0, st>>>(c.h);
+    k_chain_rebounds<<<148 * 8, kMT, 0, st>>>(d_px, d_py, (const long long*)d_count, c.h);
+    k_chain_final<<<1, 1, 0, st>>>(c.h, (long long*)d_count, 0);
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
+}
+
+// Decides, on the device, whether slice `agent` can be merged incrementally; synchronises the
+// stream to hand the 4-byte answer to the host: 0 incremental, 1 rebuild, 2 lattice overflow.
+int mapmerge_chain_probe(void* d_chain, const int64_t* dims, const double* d_sx, const double* d_sy,
+                         const int64_t* d_agent_offset, int agent, int64_t slice_points, double voxel, const int64_t* d_count,
+                         int32_t* d_status, int32_t* rebuild_out, void* stream) {
+    if (!d_chain || !chain_dims_ok(dims) || !d_sx || !d_sy || !d_agent_offset || agent < 0 || slice_points < 0 ||
+        slice_points > dims[3] || !(voxel > 0.0) || !d_count || !d_status || !rebuild_out) {
+        set_last_error("mapmerge_chain_probe: bad arguments");
+        return OCCGRID_E_ARG;
+    }
+    ChainArrays c;
+    chain_layout(dims, &c, d_chain);
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        ProfileScope ps(K_MERGE_VOXEL, st, 2);
+        k_chain_slice_bounds<<<grid_for(slice_points), kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, agent, c.h);
+        k_chain_setup<<<1, 1, 0, st>>>(c.h, (const long long*)d_count, voxel, dims[0], dims[1], d_status);
+    }
+    OCC_CUDA_TRY(cudaGetLastError());
+    int need = 0;
+    OCC_CUDA_TRY(cudaMemcpyAsync(&need, &c.h->need_rebuild, sizeof(int), cudaMemcpyDeviceToHost, st));
+    OCC_CUDA_TRY(cudaStreamSynchronize(st));
+    *rebuild_out = need;
+    return OCCGRID_OK;
+}
+
+static int chain_voxel_ws(const int64_t* dims, int64_t lattice_capacity_cells, void* d_voxel_ws, size_t voxel_ws_bytes,
+                          VoxelArrays* a, const char* who) {
+    size_t off[9];
+    if (!d_voxel_ws || lattice_capacity_cells < dims[0] * dims[1] ||
+        voxel_ws_bytes < voxel_layout(lattice_capacity_cells, dims[2], off)) {
+        set_last_error(who);
+        return OCCGRID_E_WORKSPACE;
+    }
+    *a = voxel_arrays(d_voxel_ws, off);
+    return OCCGRID_OK;
+}
+
+// Callback with an unchanged lattice: O(|slice|) work.  The cloud is updated in place.
+int mapmerge_chain_incremental(void* d_chain, const int64_t* dims, const double* d_sx, const double* d_sy,
+                               const int64_t* d_agent_offset, int agent, int64_t slice_points, double voxel, double* d_px,
+                               double* d_py, int64_t capacity, int64_t* d_count, int32_t* d_status, void* d_voxel_ws,
+                               size_t voxel_ws_bytes, int64_t lattice_capacity_cells, void* stream) {
+    if (!d_chain || !chain_dims_ok(dims) || !d_sx || !d_sy || !d_agent_offset || agent < 0 || slice_points < 0 ||
+        slice_points > dims[3] || !(voxel > 0.0) || !d_px || !d_py || capacity > dims[2] || !d_count || !d_status) {
+        set_last_error("mapmerge_chain_incremental: bad arguments");
+        return OCCGRID_E_ARG;
+    }
+    VoxelArrays va;
+    const int rc = chain_voxel_ws(dims, lattice_capacity_cells, d_voxel_ws, voxel_ws_bytes, &va, "mapmerge_chain_incremental: voxel workspace too small");
+    if (rc) return rc;
+    ChainArrays c;
+    chain_layout(dims, &c, d_chain);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gsl = grid_for(slice_points);
+    ProfileScope ps(K_MERGE_VOXEL, st, 12);
+    k_chain_lookup<<<gsl, kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, agent, voxel, c.h, c.LM, d_px, d_py, c.mx, c.my,
+                                        c.msrc, d_status);
+    k_chain_copy_slice<<<gsl, kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, agent, c.h, c.mx, c.my);
+    launch_voxel_core(c.mx, c.my, &c.h->v, &c.h->v, va, 2 * slice_points, voxel, c.ox, c.oy, &c.h->mini_count, nullptr, st);
+    k_chain_writeback<<<grid_for(2 * slice_points), kMT, 0, st>>>(c.h, c.ox, c.oy, c.msrc, d_px, d_py, c.gkey, c.LM, voxel,
+                                                                  (const long long*)d_count, capacity, d_status);
+    k_chain_rebounds<<<148 * 8, kMT, 0, st>>>(d_px, d_py, &c.h->n_next, c.h);
+    k_chain_final<<<1, 1, 0, st>>>(c.h, (long long*)d_count, 1);
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
+}
+
+// Callback whose lattice moved (or whose map is stale): append the slice, full filter into
+// (d_out_px, d_out_py, d_out_count), rebuild the voxel -> index map for the new cloud.
+int mapmerge_chain_rebuild(void* d_chain, const int64_t* dims, const double* d_sx, const double* d_sy,
+                           const int64_t* d_agent_offset, int agent, double voxel, double* d_px, double* d_py, int64_t capacity,
+                           int64_t* d_count, double* d_out_px, double* d_out_py, int64_t* d_out_count, int32_t* d_status,
+                           void* d_voxel_ws, size_t voxel_ws_bytes, int64_t lattice_capacity_cells, void* stream) {
+    if (!d_chain || !chain_dims_ok(dims) || !d_sx || !d_sy || !d_agent_offset || agent < 0 || !(voxel > 0.0) || !d_px || !d_py ||
+        capacity > dims[2] || !d_count || !d_out_px || !d_out_py || !d_out_count || !d_status) {
+        set_last_error("mapmerge_chain_rebuild: bad arguments");
+        return OCCGRID_E_ARG;
+    }
+    VoxelArrays va;
+    const int rc = chain_voxel_ws(dims, lattice_capacity_cells, d_voxel_ws, voxel_ws_bytes, &va, "mapmerge_chain_rebuild: voxel workspace too small");
+    if (rc) return rc;
+    ChainArrays c;
+    chain_layout(dims, &c, d_chain);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gp = grid_for(capacity);
+    ProfileScope ps(K_MERGE_VOXEL, st, 13);
+    k_chain_lm_clear<<<gp, kMT, 0, st>>>(c.h, c.LM, c.gkey, (const long long*)d_count);
+    k_append_slice<<<148, kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, agent, d_px, d_py, capacity, (long long*)d_count,
+                                         d_status, nullptr);
+    k_bump_count<<<1, 1, 0, st>>>((const long long*)d_agent_offset, agent, capacity, (long long*)d_count);
+    k_chain_rebuild_hdr<<<1, 1, 0, st>>>(c.h, (const long long*)d_count, dims[2], d_status);
+    launch_voxel_core(d_px, d_py, &c.h->v, &c.h->v, va, capacity, voxel, d_out_px, d_out_py, (long long*)d_out_count, c.h->gb_enc, st);
+    k_chain_lm_build<<<gp, kMT, 0, st>>>(c.h, d_out_px, d_out_py, (const long long*)d_out_count, voxel, c.LM, c.gkey);
+    k_chain_final<<<1, 1, 0, st>>>(c.h, (long long*)d_out_count, 2);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
 }

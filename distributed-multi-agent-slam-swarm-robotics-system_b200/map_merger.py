@@ -17,6 +17,7 @@ Everything numeric runs in the hand-written sm_100a kernels behind ``mapmerge_*`
 """
 from __future__ import annotations
 
+import ctypes
 import math
 from types import SimpleNamespace
 
@@ -156,6 +157,16 @@ class MapMerger:
                                        self._bounds.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
         _native.check(rc, 'mapmerge_bounds')
 
+    def _voxel_workspace(self, lattice_cells, points):
+        """The lattice sits first in the workspace and must stay all-zero between calls, so the
+        layout may only change together with a fresh (zeroed) allocation."""
+        if lattice_cells > self._lattice_cap or points != self._voxel_points_cap:
+            self._lattice_cap = max(int(lattice_cells * 1.5), self._lattice_cap)
+            self._voxel_points_cap = points
+            self._ws.pop('voxel', None)
+        need = self._lib.mapmerge_voxel_workspace_bytes(self._lattice_cap, points)
+        return self._workspace('voxel', need, zero=True)
+
     def _voxel_downsample(self, lattice_cells=None, sync=True, benc=None):
         """global_pcd = global_pcd.voxel_down_sample(map_resolution)  (:60).  `lattice_cells`: a
         conservative bound on the voxel lattice known to the caller (batched merge, no host round
@@ -168,14 +179,7 @@ class MapMerger:
             nx = int(math.floor((b[2] - (b[0] - v * 0.5)) / v)) + 1
             ny = int(math.floor((b[3] - (b[1] - v * 0.5)) / v)) + 1
             lattice_cells = nx * ny
-        # the lattice planes sit first in the workspace and must stay all-zero between calls, so
-        # the layout may only change together with a fresh (zeroed) allocation
-        if lattice_cells > self._lattice_cap or self._cloud.capacity != self._voxel_points_cap:
-            self._lattice_cap = max(int(lattice_cells * 1.5), self._lattice_cap)
-            self._voxel_points_cap = self._cloud.capacity
-            self._ws.pop('voxel', None)
-        need = self._lib.mapmerge_voxel_workspace_bytes(self._lattice_cap, self._cloud.capacity)
-        ws = self._workspace('voxel', need, zero=True)
+        ws = self._voxel_workspace(lattice_cells, self._cloud.capacity)
         rc = self._lib.mapmerge_voxel_downsample(
             self._cloud.x.data_ptr(), self._cloud.y.data_ptr(), self._cloud.count.data_ptr(), self._cloud.capacity,
             v, self._bounds.data_ptr(), benc.data_ptr() if benc is not None else None, self._lattice_cap,
@@ -264,8 +268,11 @@ class MapMerger:
         """Fuse A agent grids in order: ``grids`` int8 [A, H, W] (host or device), ``origins``
         float64 [A, 2], ``transforms`` [A, 4, 4] or [A, 3] (tx, ty, theta) or None (identity).
         Equal to A successive ``map_callback`` calls (same sequential voxel chain, :58-60);
-        publishes once at the end.  Runs stream-ordered with two host synchronisations in total:
-        the occupied-cell counts up front (to size the cloud) and the final bounds.
+        publishes once at the end.  Equal-shaped grids are extracted in one batched launch and
+        fused by the incremental chain (``mapmerge_chain_*``: work per callback proportional to the
+        slice, not to the accumulated cloud, while the voxel lattice stands still); the host reads
+        the occupied-cell counts up front, a 4-byte incremental/rebuild decision per callback and
+        the final bounds.
         Returns (int8 grid [H', W'], (origin_x, origin_y))."""
         A = len(grids)
         with torch.cuda.device(self.device):
@@ -331,37 +338,84 @@ class MapMerger:
                     stage.x.data_ptr(), stage.y.data_ptr(), stage.capacity, counts.data_ptr(), offs.data_ptr(),
                     self._status.data_ptr(), bws.data_ptr(), bws.numel(), self._stream())
                 _native.check(rc, 'mapmerge_extract_batch_write')
-            # bounds of the cloud live on the device for the whole chain when it starts from an empty
-            # merger and uses the batched slices (no min/max pass, no host read per callback)
-            benc = None
-            if same_shape and self._n_global == 0:
-                benc = torch.zeros(4, dtype=torch.int64, device=self.device)
-                _native.check(self._lib.mapmerge_bounds_enc_reset(benc.data_ptr(), self._stream()), 'mapmerge_bounds_enc_reset')
+            chain = None
+            slice_cap = max([n for n, (u, _) in zip(n_occ, mats) if u] + [1])
+            lat_w, lat_h = int((bb[2] - bb[0]) / v) + 4, int((bb[3] - bb[1]) / v) + 4
             for a in range(A):
                 use, T = mats[a]
                 if not use:
                     continue
-                if same_shape:
-                    rc = self._lib.mapmerge_append_slice(stage.x.data_ptr(), stage.y.data_ptr(), offs.data_ptr(), a,
-                                                         self._cloud.x.data_ptr(), self._cloud.y.data_ptr(), self._cloud.capacity,
-                                                         self._cloud.count.data_ptr(), self._status.data_ptr(),
-                                                         benc.data_ptr() if benc is not None else None, self._stream())
-                    _native.check(rc, 'mapmerge_append_slice')
-                else:
+                if not same_shape:
                     h, w = dev[a].shape
                     self._extract_async(make_grid_msg(dev[a], w, h, res, origins[a][0], origins[a][1]), T)
-                if first:
+                    if first:
+                        first = False
+                        self.map_resolution = float(res)
+                        self.map_origin = [float(origins[a][0]), float(origins[a][1])]
+                    else:
+                        self._voxel_downsample(lattice_cells=cells, sync=False)
+                    continue
+                if first:                        # adopted as is (:40-43): no filter on this callback
+                    rc = self._lib.mapmerge_append_slice(stage.x.data_ptr(), stage.y.data_ptr(), offs.data_ptr(), a,
+                                                         self._cloud.x.data_ptr(), self._cloud.y.data_ptr(), self._cloud.capacity,
+                                                         self._cloud.count.data_ptr(), self._status.data_ptr(), None, self._stream())
+                    _native.check(rc, 'mapmerge_append_slice')
                     first = False
                     self.map_resolution = float(res)
                     self.map_origin = [float(origins[a][0]), float(origins[a][1])]
-                else:
-                    self._voxel_downsample(lattice_cells=cells, sync=False, benc=benc)
-            self._n_global = int(self._cloud.count.item())          # host sync 2 (with the status word)
+                    continue
+                if chain is None:
+                    chain = self._chain_begin(lat_w, lat_h, slice_cap)
+                self._chain_step(chain, stage, offs, a, n_occ[a])
+            self.chain_stats = None if chain is None else {'callbacks': chain['steps'], 'rebuilds': chain['rebuilds']}
+            self._n_global = int(self._cloud.count.item())          # host sync (with the status word)
             self._check_status()
         out = self.publish_global_map(to_host=to_host)
         if out is None:
             return None, None
         return out.data, (out.info.origin.position.x, out.info.origin.position.y)
+
+    def _chain_begin(self, lat_w, lat_h, slice_cap):
+        """State of the incremental callback chain (see mapmerge_chain_* in the header)."""
+        pcap = max(self._cloud.capacity, 2 * slice_cap + 16)
+        dims = np.array([lat_w, lat_h, pcap, slice_cap], np.int64)
+        nbytes = self._lib.mapmerge_chain_workspace_bytes(dims.ctypes.data)
+        if nbytes == 0:
+            raise OccGridError('map merge: voxel lattice %d x %d too large' % (lat_w, lat_h))
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        vws = self._voxel_workspace(lat_w * lat_h, pcap)
+        rc = self._lib.mapmerge_chain_init(ws.data_ptr(), ws.numel(), dims.ctypes.data, self._cloud.x.data_ptr(),
+                                           self._cloud.y.data_ptr(), self._cloud.count.data_ptr(), self._stream())
+        _native.check(rc, 'mapmerge_chain_init')
+        return {'ws': ws, 'dims': dims, 'vws': vws, 'need': ctypes.c_int32(0), 'rebuilds': 0, 'steps': 0}
+
+    def _chain_step(self, chain, stage, offs, a, n_slice):
+        """One callback `global += slice; global = voxel_down_sample(global)` (:58-60)."""
+        lib, ws, dims, vws, need = self._lib, chain['ws'], chain['dims'], chain['vws'], chain['need']
+        v = self.map_resolution
+        c = self._cloud
+        rc = lib.mapmerge_chain_probe(ws.data_ptr(), dims.ctypes.data, stage.x.data_ptr(), stage.y.data_ptr(), offs.data_ptr(), a,
+                                      n_slice, v, c.count.data_ptr(), self._status.data_ptr(), ctypes.byref(need), self._stream())
+        _native.check(rc, 'mapmerge_chain_probe')
+        chain['steps'] += 1
+        if need.value == 2:
+            self._check_status()
+            raise OccGridError('map merge: voxel lattice does not fit the chain workspace')
+        if need.value == 0:
+            rc = lib.mapmerge_chain_incremental(ws.data_ptr(), dims.ctypes.data, stage.x.data_ptr(), stage.y.data_ptr(),
+                                                offs.data_ptr(), a, n_slice, v, c.x.data_ptr(), c.y.data_ptr(), c.capacity,
+                                                c.count.data_ptr(), self._status.data_ptr(), vws.data_ptr(), vws.numel(),
+                                                self._lattice_cap, self._stream())
+            _native.check(rc, 'mapmerge_chain_incremental')
+            return
+        chain['rebuilds'] += 1
+        sp = self._spare
+        rc = lib.mapmerge_chain_rebuild(ws.data_ptr(), dims.ctypes.data, stage.x.data_ptr(), stage.y.data_ptr(), offs.data_ptr(), a,
+                                        v, c.x.data_ptr(), c.y.data_ptr(), c.capacity, c.count.data_ptr(), sp.x.data_ptr(),
+                                        sp.y.data_ptr(), sp.count.data_ptr(), self._status.data_ptr(), vws.data_ptr(),
+                                        vws.numel(), self._lattice_cap, self._stream())
+        _native.check(rc, 'mapmerge_chain_rebuild')
+        self._cloud, self._spare = self._spare, self._cloud
 
     def _extract_async(self, msg, T):
         """grid_to_pcd (+ transform) appended to the global cloud, no host read-back."""

@@ -102,6 +102,60 @@ def test_batched_merge_equals_callbacks(MM):
     assert np.array_equal(out2, want[0]) and origin2 == want[1]
 
 
+def _oracle_chain(grids, n, res, origin, tf):
+    from oracle import merge_oracle as MO
+    o = MO.OracleMerger()
+    want = None
+    for a in range(len(grids)):
+        out = o.map_callback(grids[a].ravel(), n, n, res, origin[0], origin[1], tf[a])
+        want = out if out is not None else want
+    return o, want
+
+
+@pytest.mark.parametrize('span,rot,seed', [(3.0, math.pi, 21), (0.4, 0.05, 22), (0.0, 0.0, 23)])
+def test_incremental_chain_is_bit_exact(MM, span, rot, seed):
+    """merge() fuses equal-shaped grids with the incremental chain: while the voxel lattice stands
+    still only the voxels a slice touches are re-averaged.  The cloud (coordinates AND order) and
+    the published grid must equal the oracle's full filter per callback; heavy overlap (small
+    span / rotation, or identical poses) makes most slice points land in occupied voxels."""
+    from oracle import merge_oracle as MO
+    r = np.random.default_rng(seed)
+    A, n = 24, 160
+    grids = np.stack([synth_agent_grid(n, seed * 50 + a) for a in range(A)])
+    origins = np.tile(np.array([[-4.0, -4.0]]), (A, 1))
+    tf = np.stack([MO.se2_matrix(*r.uniform(-span, span, 2), r.uniform(-rot, rot)) if (span or rot) else np.eye(4)
+                   for _ in range(A)])
+    o, want = _oracle_chain(grids, n, 0.05, (-4.0, -4.0), tf)
+    m = MM.MapMerger()
+    out, origin = m.merge(grids, origins, 0.05, tf)
+    assert np.array_equal(out, want[0]) and origin == want[1]
+    pc = m.global_pcd
+    assert pc.shape[0] == o.gx.shape[0]
+    assert np.array_equal(pc[:, 0], o.gx) and np.array_equal(pc[:, 1], o.gy)
+    st = m.chain_stats
+    assert st['callbacks'] == A - 1 and 1 <= st['rebuilds'] <= st['callbacks']
+    if span == 3.0:
+        assert st['rebuilds'] < st['callbacks'], st          # the incremental path did run
+
+
+def test_chain_continues_an_existing_cloud(MM):
+    """A second merge() (and callbacks in between) on the same merger continue the same cloud."""
+    from oracle import merge_oracle as MO
+    r = np.random.default_rng(31)
+    A, n = 12, 128
+    grids = np.stack([synth_agent_grid(n, 900 + a) for a in range(A)])
+    origins = np.tile(np.array([[-3.2, -3.2]]), (A, 1))
+    tf = np.stack([MO.se2_matrix(*r.uniform(-2, 2, 2), r.uniform(-math.pi, math.pi)) for _ in range(A)])
+    o, want = _oracle_chain(grids, n, 0.05, (-3.2, -3.2), tf)
+    m = MM.MapMerger()
+    m.merge(grids[:5], origins[:5], 0.05, tf[:5])
+    m.map_callback(MM.make_grid_msg(grids[5].ravel(), n, n, 0.05, -3.2, -3.2), 6, transform=tf[5])
+    out, origin = m.merge(grids[6:], origins[6:], 0.05, tf[6:])
+    assert np.array_equal(out, want[0]) and origin == want[1]
+    pc = m.global_pcd
+    assert np.array_equal(pc[:, 0], o.gx) and np.array_equal(pc[:, 1], o.gy)
+
+
 def test_2048_grids(MM):
     """BASELINE config 3 grid size (2048^2, ~1.5 % occupied) on a few agents, 50 m translations."""
     run_pair(MM, 2048, 4, seed=7, span=50.0, origin=(-51.2, -51.2), check_every=False)

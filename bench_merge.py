@@ -99,13 +99,14 @@ def main():
         'config': {'workload': f'map_merger fusion of {A} agent grids ({S}^2 each) under random SE(2) transforms '
                                '(BASELINE.json configs[2]), sequential reference semantics, one publish',
                    'occupied_fraction': occ_frac, 'fused_points': int(m._n_global),
-                   'output_grid': list(out.shape)},
+                   'output_grid': list(out.shape), 'chain': m.chain_stats},
         'kernels': kern,
         'roofline': {'bound': 'hbm', 'kernel': 'merge_extract', 'achieved': S * S / (ext_ms * 1e-3) / 1e9, 'peak': hbm,
                      'unit': 'GB/s', 'frac': S * S / (ext_ms * 1e-3) / 1e9 / hbm,
                      'note': 'algorithmic bytes = H*W per agent grid (SURVEY §8d) over the device time of all extraction-side '
                              'kernels (batched count + write passes over all grids, plus the per-callback slice appends); '
-                             'the voxel chain is O(|cloud|) per callback as in the reference'},
+                             'the voxel chain costs O(|slice|) on callbacks that leave the voxel lattice in place '
+                             '(chain_incremental) and O(|cloud|) on the others (chain_rebuild)'},
     }
     # CPU baseline: NumPy restatement, one core, first cpu_agents grids
     from oracle import merge_oracle as MO

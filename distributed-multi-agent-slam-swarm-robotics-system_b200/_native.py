@@ -155,7 +155,8 @@ def _bind_merge(L):
 
 KERNEL_NAMES = ('integrate_global', 'resolve', 'update_rays', 'tile_count', 'tile_scan', 'tile_scatter',
                 'tile_raycast', 'tile_resolve', 'merge_extract', 'merge_bounds', 'merge_voxel', 'merge_raster',
-                'merge_fuse', 'probe', 'route', 'frontier', 'frontier_cluster')
+                'merge_fuse', 'probe', 'route', 'frontier', 'frontier_cluster', 'chain_probe', 'chain_incremental',
+                'chain_rebuild')
 
 
 def profile_begin():

@@ -1158,7 +1158,7 @@ int mapmerge_chain_probe(void* d_chain, const int64_t* dims, const double* d_sx,
     chain_layout(dims, &c, d_chain);
     cudaStream_t st = (cudaStream_t)stream;
     {
-        ProfileScope ps(K_MERGE_VOXEL, st, 2);
+        ProfileScope ps(K_CHAIN_PROBE, st, 2);
         k_chain_slice_bounds<<<grid_for(slice_points), kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, agent, c.h);
         k_chain_setup<<<1, 1, 0, st>>>(c.h, (const long long*)d_count, voxel, dims[0], dims[1], d_status);
     }
@@ -1199,7 +1199,7 @@ int mapmerge_chain_incremental(void* d_chain, const int64_t* dims, const double*
     chain_layout(dims, &c, d_chain);
     cudaStream_t st = (cudaStream_t)stream;
     const int gsl = grid_for(slice_points);
-    ProfileScope ps(K_MERGE_VOXEL, st, 12);
+    ProfileScope ps(K_CHAIN_INCR, st, 12);
     k_chain_lookup<<<gsl, kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, agent, voxel, c.h, c.LM, d_px, d_py, c.mx, c.my,
                                         c.msrc, d_status);
     k_chain_copy_slice<<<gsl, kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, agent, c.h, c.mx, c.my);
@@ -1230,7 +1230,7 @@ int mapmerge_chain_rebuild(void* d_chain, const int64_t* dims, const double* d_s
     chain_layout(dims, &c, d_chain);
     cudaStream_t st = (cudaStream_t)stream;
     const int gp = grid_for(capacity);
-    ProfileScope ps(K_MERGE_VOXEL, st, 13);
+    ProfileScope ps(K_CHAIN_REBUILD, st, 13);
     k_chain_lm_clear<<<gp, kMT, 0, st>>>(c.h, c.LM, c.gkey, (const long long*)d_count);
     k_append_slice<<<148, kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, agent, d_px, d_py, capacity, (long long*)d_count,
                                          d_status, nullptr);

@@ -358,7 +358,7 @@ enum {
     OCCGRID_K_TILE_SCAN, OCCGRID_K_TILE_SCATTER, OCCGRID_K_TILE_RAYCAST, OCCGRID_K_TILE_RESOLVE,
     OCCGRID_K_MERGE_EXTRACT, OCCGRID_K_MERGE_BOUNDS, OCCGRID_K_MERGE_VOXEL, OCCGRID_K_MERGE_RASTER,
     OCCGRID_K_MERGE_FUSE, OCCGRID_K_PROBE, OCCGRID_K_ROUTE, OCCGRID_K_FRONTIER, OCCGRID_K_FRONTIER_CLUSTER,
-    OCCGRID_K_N_KERNELS
+    OCCGRID_K_CHAIN_PROBE, OCCGRID_K_CHAIN_INCR, OCCGRID_K_CHAIN_REBUILD, OCCGRID_K_N_KERNELS
 };
 int occgrid_profile_begin(void);
 int occgrid_profile_end(double* ms_by_kernel, int64_t* launches_by_kernel, int n_slots);

@@ -138,15 +138,17 @@ def _bind_merge(L):
     L.mapmerge_bounds_enc_reset.restype = C.c_int
     L.mapmerge_bounds_enc_reset.argtypes = [vp, vp]
     L.mapmerge_chain_workspace_bytes.restype = sz
-    L.mapmerge_chain_workspace_bytes.argtypes = [vp]
+    L.mapmerge_chain_workspace_bytes.argtypes = [vp, i32]
     L.mapmerge_chain_init.restype = C.c_int
-    L.mapmerge_chain_init.argtypes = [vp, sz, vp, vp, vp, vp, vp]
-    L.mapmerge_chain_probe.restype = C.c_int
-    L.mapmerge_chain_probe.argtypes = [vp, vp, vp, vp, vp, i32, i64, dbl, vp, vp, vp, vp]
-    L.mapmerge_chain_incremental.restype = C.c_int
-    L.mapmerge_chain_incremental.argtypes = [vp, vp, vp, vp, vp, i32, i64, dbl, vp, vp, i64, vp, vp, vp, sz, i64, vp]
+    L.mapmerge_chain_init.argtypes = [vp, sz, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp]
+    L.mapmerge_chain_run.restype = C.c_int
+    L.mapmerge_chain_run.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, dbl, vp, vp, i64, vp, vp, vp]
+    L.mapmerge_chain_poll.restype = C.c_int
+    L.mapmerge_chain_poll.argtypes = [vp, vp, i32, vp, vp]
+    L.mapmerge_chain_rebounds.restype = C.c_int
+    L.mapmerge_chain_rebounds.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.mapmerge_chain_rebuild.restype = C.c_int
-    L.mapmerge_chain_rebuild.argtypes = [vp, vp, vp, vp, vp, i32, dbl, vp, vp, i64, vp, vp, vp, vp, vp, vp, sz, i64, vp]
+    L.mapmerge_chain_rebuild.argtypes = [vp, vp, i32, vp, vp, vp, i32, dbl, vp, vp, i64, vp, vp, vp, vp, vp, vp, sz, i64, vp]
     L.mapmerge_rasterise.restype = C.c_int
     L.mapmerge_rasterise.argtypes = [vp, vp, vp, dbl, vp, i32, i32, vp, vp]
     L.mapmerge_fuse_max.restype = C.c_int

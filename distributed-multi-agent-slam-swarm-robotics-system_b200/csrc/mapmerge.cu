@@ -14,6 +14,7 @@
 // canonical order "first appearance" (voxels in order of their smallest point index, as an
 // insertion-ordered map would give) and sum the points of a voxel in ascending point index, so
 // results are bit-reproducible and equal to the oracle (oracle/merge_oracle.py).
+#include <cstddef>
 #include <vector>
 
 #include "common.cuh"
@@ -182,13 +183,13 @@ __device__ __forceinline__ double dec_double(unsigned long long k) {
 // Block-level min/max of (x, y) over the calling threads' values, then 4 atomics per CTA.
 __device__ __forceinline__ void block_bounds_atomic(double mnx, double mny, double mxx, double mxy,
                                                     unsigned long long* __restrict__ benc) {
-    __shared__ double s_b[4][kMT / 32];
+    __shared__ double s_b[4][32];                  // any block size up to 1024
     mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) { s_b[0][warp] = mnx; s_b[1][warp] = mny; s_b[2][warp] = mxx; s_b[3][warp] = mxy; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < kMT / 32; ++w) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
             mnx = fmin(mnx, s_b[0][w]); mny = fmin(mny, s_b[1][w]); mxx = fmax(mxx, s_b[2][w]); mxy = fmax(mxy, s_b[3][w]);
         }
         if (mnx <= mxx) {
@@ -591,31 +592,34 @@ k_voxel_reduce(const double* __restrict__ px, const double* __restrict__ py, con
 
 // ---- incremental voxel chain ---------------------------------------------------------------
 // The reference voxel-filters the WHOLE accumulated cloud on every callback (:58-60).  Once a
-// cloud G has been filtered under a lattice L (anchor = min_bound - voxel/2) it holds one point
-// per voxel, and filtering G u S under the SAME lattice only changes the voxels S falls into:
-// every other point is alone in its voxel and p / 1.0 == p.  So while the anchor stays bitwise
-// equal, a callback only has to
-//   - look every slice point up in a persistent voxel -> cloud-index map (LM),
-//   - run the ordinary filter on the mini cloud  [touched G points] ++ [slice]  (a touched G
-//     point is the head of its voxel, slice points follow in order: same sums, same order),
-//   - write the means back in place and append the new voxels in order of first appearance.
-// When the anchor moves (the cloud's min corner changed), or a mean lands in another voxel than
-// its points, the callback falls back to the full filter and rebuilds LM.  Results are bitwise
-// those of the full chain; the decision is taken on the device and read by the host (4 bytes).
+// cloud G has been filtered under a lattice (anchor = min_bound - voxel/2) it holds one point per
+// voxel, and filtering G u S under the SAME lattice only changes the voxels S falls into: every
+// other point is alone in its voxel and p / 1.0 == p.  So while the anchor stays bitwise equal a
+// callback is three small kernels over the slice:
+//   link    every slice point pushes itself on a per-voxel stack hanging off a persistent
+//           voxel -> cloud-index map LM (one atomicExch)
+//   fold    the point on top of each stack walks it, sums [the cloud point of that voxel, if any]
+//           ++ [the slice points in ascending index] and divides: an existing voxel is updated in
+//           place, a new one is parked at its first slice index
+//   append  ordered compaction of the parked means onto the end of the cloud (order of first
+//           appearance), LM and the per-point voxel keys are extended
+// When the anchor moves (the cloud's min corner changed) or a mean lands outside the voxel of its
+// points, the callback needs the full filter and a rebuilt LM.  Callbacks are enqueued without
+// host round trips: the kernels take the next slice from a device cursor and turn into no-ops
+// once a callback needs the host (header.stalled), which the host polls every few callbacks.
 
 struct ChainHeader {
-    VoxelHeader v;                       // lattice + point count the voxel kernels of this callback see
+    VoxelHeader v;                       // lattice + point count for the full filter of a rebuild
     double mbx, mby;                     // anchor LM / gkey are valid for
-    double new_mbx, new_mby;             // anchor this callback needs
-    unsigned long long gb_enc[4];        // bounds of the cloud (encoded, see enc_double)
-    unsigned long long gb2_enc[4];       // scratch for a full recompute
-    unsigned long long lb_enc[4];        // bounds of the slice of this callback
-    long long n_next;                    // cloud size after this callback
-    long long mini_count;                // output count of the mini filter (unused by the host)
-    unsigned int n_aff;                  // touched cloud points of this callback
-    int have_lattice, force_rebuild, need_rebuild, bounds_dirty;
+    unsigned long long gb_enc[4];        // bounds of the cloud (encoded, see enc_double); min corner exact
+    unsigned long long gb2_enc[4];       // scratch of a full recompute
+    int have_lattice, force_rebuild, bounds_dirty;
+    int stalled;                         // 0 running, else OCC_CHAIN_* reason the host has to deal with
+    int cursor;                          // next entry of order[]
+    unsigned int ticket;
 };
-constexpr unsigned int kTouched = 0x80000000u;
+enum { CHAIN_RUN = 0, CHAIN_REBUILD = 1, CHAIN_OVERFLOW = 2, CHAIN_REBOUND = 3 };
+constexpr int kAppendThreads = 1024;
 
 __device__ __forceinline__ bool voxel_key_of(double x, double y, double mbx, double mby, double voxel, long long W,
                                              long long H, unsigned int* key) {
@@ -626,134 +630,202 @@ __device__ __forceinline__ bool voxel_key_of(double x, double y, double mbx, dou
     return true;
 }
 
-__global__ void k_chain_reset(ChainHeader* __restrict__ h) {
-    h->gb_enc[0] = h->gb_enc[1] = h->gb2_enc[0] = h->gb2_enc[1] = h->lb_enc[0] = h->lb_enc[1] = enc_double(INFINITY);
-    h->gb_enc[2] = h->gb_enc[3] = h->gb2_enc[2] = h->gb2_enc[3] = h->lb_enc[2] = h->lb_enc[3] = enc_double(-INFINITY);
-    h->have_lattice = h->force_rebuild = h->need_rebuild = 0;
-    h->bounds_dirty = 1;                 // the first k_chain_rebounds computes the bounds of the adopted cloud
-    h->n_aff = 0;
+// What the callback for slice `agent` needs; also yields the anchor of cloud u slice.
+__device__ __forceinline__ int chain_decide(const ChainHeader* h, const unsigned long long* sb /* slice bounds */, double voxel,
+                                            long long W, long long H, double* nmbx, double* nmby) {
+    const double b0 = fmin(dec_double(h->gb_enc[0]), dec_double(sb[0]));
+    const double b1 = fmin(dec_double(h->gb_enc[1]), dec_double(sb[1]));
+    const double b2 = fmax(dec_double(h->gb_enc[2]), dec_double(sb[2]));
+    const double b3 = fmax(dec_double(h->gb_enc[3]), dec_double(sb[3]));
+    *nmbx = OCC_DADD(b0, -OCC_DMUL(voxel, 0.5));
+    *nmby = OCC_DADD(b1, -OCC_DMUL(voxel, 0.5));
+    if (h->bounds_dirty) return CHAIN_REBOUND;
+    const long long nx = (long long)floor(OCC_DDIV(OCC_DADD(b2, -*nmbx), voxel)) + 1;
+    const long long ny = (long long)floor(OCC_DDIV(OCC_DADD(b3, -*nmby), voxel)) + 1;
+    if (!(nx > 0 && ny > 0 && nx <= W && ny <= H)) return CHAIN_OVERFLOW;
+    if (!h->have_lattice || h->force_rebuild || *nmbx != h->mbx || *nmby != h->mby) return CHAIN_REBUILD;
+    return CHAIN_RUN;
 }
 
+__global__ void k_chain_reset(ChainHeader* __restrict__ h) {
+    h->gb_enc[0] = h->gb_enc[1] = h->gb2_enc[0] = h->gb2_enc[1] = enc_double(INFINITY);
+    h->gb_enc[2] = h->gb_enc[3] = h->gb2_enc[2] = h->gb2_enc[3] = enc_double(-INFINITY);
+    h->have_lattice = h->force_rebuild = 0;
+    h->bounds_dirty = 1;                 // k_chain_rebounds + _apply compute the bounds of the adopted cloud
+    h->stalled = 0;
+    h->cursor = 0;
+    h->ticket = 0;
+}
+
+// Bounds of every slice of the batch: blockIdx.y = agent, atomics into slice_benc[agent][4]
+// (pre-set to +-inf by k_chain_slice_bounds_init).
+__global__ void k_chain_slice_bounds_init(unsigned long long* __restrict__ slice_benc, int n_agents) {
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_agents; a += gridDim.x * blockDim.x) {
+        slice_benc[4 * a + 0] = slice_benc[4 * a + 1] = enc_double(INFINITY);
+        slice_benc[4 * a + 2] = slice_benc[4 * a + 3] = enc_double(-INFINITY);
+    }
+}
 __global__ void __launch_bounds__(kMT)
 k_chain_slice_bounds(const double* __restrict__ sx, const double* __restrict__ sy, const long long* __restrict__ agent_offset,
-                     int a, ChainHeader* __restrict__ h) {
+                     unsigned long long* __restrict__ slice_benc) {
+    const int a = blockIdx.y;
     const long long b = agent_offset[a], e = agent_offset[a + 1];
+    if (b + (long long)blockIdx.x * kMT >= e) return;
     double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
     for (long long i = b + (long long)blockIdx.x * kMT + threadIdx.x; i < e; i += (long long)gridDim.x * kMT) {
         const double x = sx[i], y = sy[i];
         mnx = fmin(mnx, x); mxx = fmax(mxx, x); mny = fmin(mny, y); mxy = fmax(mxy, y);
     }
-    block_bounds_atomic(mnx, mny, mxx, mxy, h->lb_enc);
+    block_bounds_atomic(mnx, mny, mxx, mxy, slice_benc + 4 * a);
 }
 
-__global__ void k_chain_setup(ChainHeader* __restrict__ h, const long long* __restrict__ d_count, double voxel, long long W,
-                              long long H, int* __restrict__ status) {
-    const double b0 = fmin(dec_double(h->gb_enc[0]), dec_double(h->lb_enc[0]));
-    const double b1 = fmin(dec_double(h->gb_enc[1]), dec_double(h->lb_enc[1]));
-    const double b2 = fmax(dec_double(h->gb_enc[2]), dec_double(h->lb_enc[2]));
-    const double b3 = fmax(dec_double(h->gb_enc[3]), dec_double(h->lb_enc[3]));
-    const double nmbx = OCC_DADD(b0, -OCC_DMUL(voxel, 0.5));
-    const double nmby = OCC_DADD(b1, -OCC_DMUL(voxel, 0.5));
-    const long long nx = (long long)floor(OCC_DDIV(OCC_DADD(b2, -nmbx), voxel)) + 1;
-    const long long ny = (long long)floor(OCC_DDIV(OCC_DADD(b3, -nmby), voxel)) + 1;
-    int need;
-    if (!(nx > 0 && ny > 0 && nx <= W && ny <= H) || *d_count <= 0) {
-        atomicOr(status, ST_LATTICE_OVERFLOW);
-        need = 2;
-    } else {
-        need = (!h->have_lattice || h->force_rebuild || nmbx != h->mbx || nmby != h->mby) ? 1 : 0;
-    }
-    h->new_mbx = nmbx; h->new_mby = nmby;
-    h->need_rebuild = need;
-    h->n_aff = 0;
-    h->v.mbx = nmbx; h->v.mby = nmby;
-    h->v.nx = W; h->v.ny = H; h->v.cells = W * H;
-    h->v.n_points = 0;
-    h->v.total_slots = h->v.total_voxels = 0;
-}
-
-// Slice points that fall into a voxel the cloud already occupies pull that cloud point into the
-// mini cloud (once: the top bit of the LM entry marks "already pulled").
+// LM[k] = {index + 1 of the cloud point in voxel k (0: none), top of this callback's stack}
 __global__ void __launch_bounds__(kMT)
-k_chain_lookup(const double* __restrict__ sx, const double* __restrict__ sy, const long long* __restrict__ agent_offset, int a,
-               double voxel, ChainHeader* __restrict__ h, unsigned int* __restrict__ LM, const double* __restrict__ gx,
-               const double* __restrict__ gy, double* __restrict__ mx, double* __restrict__ my,
-               unsigned int* __restrict__ msrc, int* __restrict__ status) {
-    const long long b = agent_offset[a], e = agent_offset[a + 1];
-    const double mbx = h->v.mbx, mby = h->v.mby;
-    const long long W = h->v.nx, H = h->v.ny;
-    for (long long i = b + (long long)blockIdx.x * kMT + threadIdx.x; i < e; i += (long long)gridDim.x * kMT) {
-        unsigned int k;
-        if (!voxel_key_of(sx[i], sy[i], mbx, mby, voxel, W, H, &k)) { atomicOr(status, ST_LATTICE_OVERFLOW); continue; }
-        if ((LM[k] & ~kTouched) == 0u) continue;
-        const unsigned int old = atomicOr(&LM[k], kTouched);
-        if (old & kTouched) continue;
-        const unsigned int g = (old & ~kTouched) - 1u;
-        const unsigned int pos = atomicAdd(&h->n_aff, 1u);
-        msrc[pos] = g;
-        mx[pos] = gx[g];
-        my[pos] = gy[g];
+k_chain_link(ChainHeader* __restrict__ h, const int* __restrict__ order, int n_order, const long long* __restrict__ agent_offset,
+             const unsigned long long* __restrict__ slice_benc, const double* __restrict__ sx, const double* __restrict__ sy,
+             double voxel, long long W, long long H, uint2* __restrict__ LM, unsigned int* __restrict__ lkey,
+             unsigned int* __restrict__ next, int* __restrict__ status) {
+    if (h->stalled) return;
+    const int cur = h->cursor;
+    if (cur >= n_order) return;
+    const int agent = order[cur];
+    double mbx, mby;
+    const int need = chain_decide(h, slice_benc + 4 * agent, voxel, W, H, &mbx, &mby);
+    if (need != CHAIN_RUN) {                       // every block reaches the same verdict; one records it
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            h->stalled = need;
+            if (need == CHAIN_OVERFLOW) atomicOr(status, ST_LATTICE_OVERFLOW);
+        }
+        return;
+    }
+    const long long b = agent_offset[agent], n = agent_offset[agent + 1] - b;
+    for (long long j = (long long)blockIdx.x * kMT + threadIdx.x; j < n; j += (long long)gridDim.x * kMT) {
+        unsigned int k = 0;
+        voxel_key_of(sx[b + j], sy[b + j], mbx, mby, voxel, W, H, &k);     // in range: the lattice covers cloud u slice
+        lkey[j] = k;
+        next[j] = atomicExch(&LM[k].y, (unsigned int)j + 1u);
     }
 }
 
 __global__ void __launch_bounds__(kMT)
-k_chain_copy_slice(const double* __restrict__ sx, const double* __restrict__ sy, const long long* __restrict__ agent_offset,
-                   int a, ChainHeader* __restrict__ h, double* __restrict__ mx, double* __restrict__ my) {
-    const long long b = agent_offset[a], n = agent_offset[a + 1] - b;
-    const long long base = (long long)h->n_aff;
-    for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
-        mx[base + i] = sx[b + i];
-        my[base + i] = sy[b + i];
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) h->v.n_points = base + n;
-}
-
-// Means of the mini filter go back: ranks < n_aff are the touched cloud points (each the head of
-// its own voxel, in mini-cloud order), the rest are new voxels in order of first appearance.
-__global__ void __launch_bounds__(kMT)
-k_chain_writeback(ChainHeader* __restrict__ h, const double* __restrict__ ox, const double* __restrict__ oy,
-                  const unsigned int* __restrict__ msrc, double* __restrict__ gx, double* __restrict__ gy,
-                  unsigned int* __restrict__ gkey, unsigned int* __restrict__ LM, double voxel,
-                  const long long* __restrict__ d_count, long long capacity, int* __restrict__ status) {
-    const long long n_aff = (long long)h->n_aff, total = (long long)h->v.total_voxels, n_g = *d_count;
-    const double mbx = h->v.mbx, mby = h->v.mby;
-    const long long W = h->v.nx, H = h->v.ny;
+k_chain_fold(ChainHeader* __restrict__ h, const int* __restrict__ order, int n_order, const long long* __restrict__ agent_offset,
+             const double* __restrict__ sx, const double* __restrict__ sy, double voxel, long long W, long long H,
+             uint2* __restrict__ LM, const unsigned int* __restrict__ lkey, const unsigned int* __restrict__ next,
+             double* __restrict__ gx, double* __restrict__ gy, double* __restrict__ resx, double* __restrict__ resy,
+             unsigned int* __restrict__ flag, unsigned int* __restrict__ blockcount) {
+    if (h->stalled) return;
+    const int cur = h->cursor;
+    if (cur >= n_order) return;
+    const int agent = order[cur];
+    const long long b = agent_offset[agent], n = agent_offset[agent + 1] - b;
+    const double mbx = h->mbx, mby = h->mby;
     const double g0 = dec_double(h->gb_enc[0]), g1 = dec_double(h->gb_enc[1]);
     double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
-    for (long long r = (long long)blockIdx.x * kMT + threadIdx.x; r < total; r += (long long)gridDim.x * kMT) {
-        const double x = ox[r], y = oy[r];
-        unsigned int k = 0;
-        const bool ok = voxel_key_of(x, y, mbx, mby, voxel, W, H, &k);
-        if (r < n_aff) {
-            const unsigned int g = msrc[r];
-            // a point sitting on the min corner may move inwards: the bounds then need a full pass
-            if (gx[g] <= g0 || gy[g] <= g1) h->bounds_dirty = 1;
-            gx[g] = x; gy[g] = y;
-            const unsigned int kold = gkey[g];
-            LM[kold] = g + 1u;                              // drops the "pulled" bit
-            if (!ok || k != kold) h->force_rebuild = 1;     // the mean left its voxel: LM no longer describes the cloud
-        } else {
-            const long long idx = n_g + (r - n_aff);
-            if (idx >= capacity) { atomicOr(status, ST_POINT_OVERFLOW); continue; }
-            gx[idx] = x; gy[idx] = y;
-            if (!ok) { h->force_rebuild = 1; gkey[idx] = 0xffffffffu; continue; }
-            gkey[idx] = k;
-            if (atomicExch(&LM[k], (unsigned int)idx + 1u) != 0u) h->force_rebuild = 1;
+    for (long long j = (long long)blockIdx.x * kMT + threadIdx.x; j < n; j += (long long)gridDim.x * kMT) {
+        const unsigned int k = lkey[j];
+        const uint2 e = LM[k];
+        if (e.y != (unsigned int)j + 1u) continue;             // not the top of its voxel's stack
+        unsigned int cnt = 0, head = (unsigned int)j;
+        for (unsigned int q = e.y; q; q = next[q - 1]) { ++cnt; head = min(head, q - 1u); }
+        double ax, ay;
+        long long last;
+        unsigned int remaining, total;
+        if (e.x) { ax = gx[e.x - 1]; ay = gy[e.x - 1]; last = -1; remaining = cnt; total = cnt + 1u; }
+        else     { ax = sx[b + head]; ay = sy[b + head]; last = head; remaining = cnt - 1u; total = cnt; }
+        for (unsigned int r = 0; r < remaining; ++r) {         // ascending slice index; stacks are tiny
+            unsigned int best = 0xffffffffu;
+            for (unsigned int q = e.y; q; q = next[q - 1]) {
+                const unsigned int idx = q - 1u;
+                if ((long long)idx > last && idx < best) best = idx;
+            }
+            last = best;
+            ax = OCC_DADD(ax, sx[b + best]);
+            ay = OCC_DADD(ay, sy[b + best]);
         }
-        mnx = fmin(mnx, x); mxx = fmax(mxx, x); mny = fmin(mny, y); mxy = fmax(mxy, y);
+        const double c = (double)total;
+        const double x = OCC_DDIV(ax, c), y = OCC_DDIV(ay, c);
+        if (e.x) {
+            const unsigned int g = e.x - 1u;
+            const double oldx = gx[g], oldy = gy[g];
+            // a point on the min corner moving inwards: the bounds need a full pass before the next decision
+            if ((oldx <= g0 && x > oldx) || (oldy <= g1 && y > oldy)) h->bounds_dirty = 1;
+            gx[g] = x; gy[g] = y;
+            unsigned int k2 = 0;
+            if (!voxel_key_of(x, y, mbx, mby, voxel, W, H, &k2) || k2 != k) h->force_rebuild = 1;   // LM no longer describes the cloud
+            mnx = fmin(mnx, x); mxx = fmax(mxx, x); mny = fmin(mny, y); mxy = fmax(mxy, y);
+        } else {
+            resx[head] = x; resy[head] = y;
+            flag[head] = 1u;
+            atomicAdd(&blockcount[head / kAppendThreads], 1u);
+        }
+        LM[k].y = 0u;
     }
     block_bounds_atomic(mnx, mny, mxx, mxy, h->gb_enc);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        long long nn = n_g + (total - n_aff);
-        h->n_next = nn > capacity ? capacity : nn;
+}
+
+__global__ void __launch_bounds__(kAppendThreads)
+k_chain_append(ChainHeader* __restrict__ h, const int* __restrict__ order, int n_order, const long long* __restrict__ agent_offset,
+               double voxel, long long W, long long H, uint2* __restrict__ LM, double* __restrict__ gx, double* __restrict__ gy,
+               unsigned int* __restrict__ gkey, const double* __restrict__ resx, const double* __restrict__ resy,
+               unsigned int* __restrict__ flag, unsigned int* __restrict__ blockcount, long long* __restrict__ d_count,
+               long long capacity, int* __restrict__ status) {
+    __shared__ unsigned int s_warp[33];
+    __shared__ unsigned int s_off;
+    if (h->stalled) return;
+    const int cur = h->cursor;
+    if (cur >= n_order) return;
+    const int agent = order[cur];
+    const long long n = agent_offset[agent + 1] - agent_offset[agent];
+    const long long n_g = *d_count;                 // rewritten only by the block that takes the last ticket
+    const double mbx = h->mbx, mby = h->mby;
+    unsigned int part = 0;
+    for (unsigned int bb = threadIdx.x; bb < blockIdx.x; bb += kAppendThreads) part += blockcount[bb];
+    unsigned int before;
+    block_exclusive_scan(part, s_warp, &before);    // total of the blocks in front of this one
+    if (threadIdx.x == 0) s_off = before;
+    __syncthreads();
+    const long long j = (long long)blockIdx.x * kAppendThreads + threadIdx.x;
+    const unsigned int f = (j < n) ? flag[j] : 0u;
+    unsigned int mine;
+    const unsigned int pos = block_exclusive_scan(f, s_warp, &mine);
+    double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    if (f) {
+        flag[j] = 0u;
+        const long long idx = n_g + s_off + pos;
+        if (idx >= capacity) {
+            atomicOr(status, ST_POINT_OVERFLOW);
+        } else {
+            const double x = resx[j], y = resy[j];
+            gx[idx] = x; gy[idx] = y;
+            unsigned int k = 0;
+            if (!voxel_key_of(x, y, mbx, mby, voxel, W, H, &k)) { gkey[idx] = 0xffffffffu; h->force_rebuild = 1; }
+            else {
+                gkey[idx] = k;
+                if (atomicExch(&LM[k].x, (unsigned int)idx + 1u) != 0u) h->force_rebuild = 1;   // mean drifted into an occupied voxel
+            }
+            mnx = x; mxx = x; mny = y; mxy = y;
+        }
+    }
+    block_bounds_atomic(mnx, mny, mxx, mxy, h->gb_enc);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&h->ticket, 1u) == gridDim.x - 1) {      // every block has read n_g and its counts
+            unsigned int total = 0;
+            const unsigned int nb = (unsigned int)((n + kAppendThreads - 1) / kAppendThreads);
+            for (unsigned int bb = 0; bb < nb; ++bb) { total += blockcount[bb]; blockcount[bb] = 0u; }
+            long long nn = n_g + total;
+            *d_count = nn > capacity ? capacity : nn;
+            h->ticket = 0u;
+            h->cursor = cur + 1;
+        }
     }
 }
 
-// Full min/max pass, only when a callback may have moved the min corner inwards (or at start).
+// Full min/max pass over the cloud (at start, and when a callback may have moved the min corner inwards).
 __global__ void __launch_bounds__(kMT)
 k_chain_rebounds(const double* __restrict__ gx, const double* __restrict__ gy, const long long* __restrict__ n_ptr,
                  ChainHeader* __restrict__ h) {
-    if (!h->bounds_dirty) return;
     const long long n = *n_ptr;
     double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
     for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
@@ -762,46 +834,51 @@ k_chain_rebounds(const double* __restrict__ gx, const double* __restrict__ gy, c
     }
     block_bounds_atomic(mnx, mny, mxx, mxy, h->gb2_enc);
 }
-
-// mode 0: after init/adopt, 1: after an incremental callback, 2: after a rebuild
-__global__ void k_chain_final(ChainHeader* __restrict__ h, long long* __restrict__ d_count, int mode) {
-    if (h->bounds_dirty) {
-        for (int j = 0; j < 4; ++j) h->gb_enc[j] = h->gb2_enc[j];
-        h->bounds_dirty = 0;
-    }
-    h->gb2_enc[0] = h->gb2_enc[1] = h->lb_enc[0] = h->lb_enc[1] = enc_double(INFINITY);
-    h->gb2_enc[2] = h->gb2_enc[3] = h->lb_enc[2] = h->lb_enc[3] = enc_double(-INFINITY);
-    if (mode == 1) *d_count = h->n_next;
-    if (mode == 2) { h->mbx = h->new_mbx; h->mby = h->new_mby; h->have_lattice = 1; }
-    h->need_rebuild = 0;
-    h->n_aff = 0;
+__global__ void k_chain_rebounds_apply(ChainHeader* __restrict__ h) {
+    h->gb_enc[0] = h->gb2_enc[0]; h->gb_enc[1] = h->gb2_enc[1];
+    // max corner: only has to cover the cloud (it sizes the lattice check); keep it monotone
+    h->gb_enc[2] = max(h->gb_enc[2], h->gb2_enc[2]); h->gb_enc[3] = max(h->gb_enc[3], h->gb2_enc[3]);
+    h->gb2_enc[0] = h->gb2_enc[1] = enc_double(INFINITY);
+    h->gb2_enc[2] = h->gb2_enc[3] = enc_double(-INFINITY);
+    h->bounds_dirty = 0;
+    if (h->stalled == CHAIN_REBOUND) h->stalled = CHAIN_RUN;
 }
 
 __global__ void __launch_bounds__(kMT)
-k_chain_lm_clear(ChainHeader* __restrict__ h, unsigned int* __restrict__ LM, const unsigned int* __restrict__ gkey,
+k_chain_lm_clear(ChainHeader* __restrict__ h, uint2* __restrict__ LM, const unsigned int* __restrict__ gkey,
                  const long long* __restrict__ d_count) {
     if (!h->have_lattice) return;
     const long long n = *d_count;
     for (long long i = (long long)blockIdx.x * kMT + threadIdx.x; i < n; i += (long long)gridDim.x * kMT) {
         const unsigned int k = gkey[i];
-        if (k != 0xffffffffu) LM[k] = 0u;
+        if (k != 0xffffffffu) LM[k] = make_uint2(0u, 0u);
     }
 }
 
-__global__ void k_chain_rebuild_hdr(ChainHeader* __restrict__ h, const long long* __restrict__ d_count, long long point_capacity,
-                                    int* __restrict__ status) {
+// After the slice has been appended: lattice of cloud u slice for the full filter.
+__global__ void k_chain_rebuild_hdr(ChainHeader* __restrict__ h, const unsigned long long* __restrict__ slice_benc, int agent,
+                                    const long long* __restrict__ d_count, double voxel, long long W, long long H,
+                                    long long point_capacity, int* __restrict__ status) {
+    double nmbx, nmby;
+    const int dirty = h->bounds_dirty;
+    h->bounds_dirty = 0;
+    int need = chain_decide(h, slice_benc + 4 * agent, voxel, W, H, &nmbx, &nmby);
+    h->bounds_dirty = dirty;
     long long n = *d_count;
     if (n > point_capacity || n >= 0x7ffffff0ll) { atomicOr(status, ST_POINT_OVERFLOW); n = 0; }
+    if (need == CHAIN_OVERFLOW) { atomicOr(status, ST_LATTICE_OVERFLOW); n = 0; }
+    h->v.mbx = nmbx; h->v.mby = nmby;
+    h->v.nx = W; h->v.ny = H; h->v.cells = W * H;
     h->v.n_points = n;
+    h->v.total_slots = h->v.total_voxels = 0;
     h->force_rebuild = 0;
-    h->gb_enc[0] = h->gb_enc[1] = enc_double(INFINITY);     // the filter's reduce pass rebuilds them
+    h->gb_enc[0] = h->gb_enc[1] = enc_double(INFINITY);     // the filter's reduce pass leaves the new cloud's bounds
     h->gb_enc[2] = h->gb_enc[3] = enc_double(-INFINITY);
 }
 
 __global__ void __launch_bounds__(kMT)
 k_chain_lm_build(ChainHeader* __restrict__ h, const double* __restrict__ gx, const double* __restrict__ gy,
-                 const long long* __restrict__ d_count, double voxel, unsigned int* __restrict__ LM,
-                 unsigned int* __restrict__ gkey) {
+                 const long long* __restrict__ d_count, double voxel, uint2* __restrict__ LM, unsigned int* __restrict__ gkey) {
     const long long n = *d_count;
     const double mbx = h->v.mbx, mby = h->v.mby;
     const long long W = h->v.nx, H = h->v.ny;
@@ -809,8 +886,16 @@ k_chain_lm_build(ChainHeader* __restrict__ h, const double* __restrict__ gx, con
         unsigned int k;
         if (!voxel_key_of(gx[i], gy[i], mbx, mby, voxel, W, H, &k)) { gkey[i] = 0xffffffffu; h->force_rebuild = 1; continue; }
         gkey[i] = k;
-        if (atomicExch(&LM[k], (unsigned int)i + 1u) != 0u) h->force_rebuild = 1;   // a mean drifted into a neighbour's voxel
+        if (atomicExch(&LM[k].x, (unsigned int)i + 1u) != 0u) h->force_rebuild = 1;   // a mean drifted into a neighbour's voxel
     }
+}
+
+__global__ void k_chain_rebuild_done(ChainHeader* __restrict__ h) {
+    h->mbx = h->v.mbx; h->mby = h->v.mby;
+    h->have_lattice = 1;
+    h->bounds_dirty = 0;
+    h->stalled = CHAIN_RUN;
+    h->cursor += 1;
 }
 
 // ---- a12: publish_global_map rasterise (:103-111) -----------------------------------------
@@ -1096,138 +1181,150 @@ int mapmerge_voxel_downsample(const double* d_px, const double* d_py, const int6
 // call on one chain workspace.
 struct ChainArrays {
     ChainHeader* h;
-    unsigned int *LM, *gkey, *msrc;
-    double *mx, *my, *ox, *oy;
+    uint2* LM;
+    unsigned int *gkey, *lkey, *next, *flag, *blockcount;
+    double *resx, *resy;
+    unsigned long long* slice_benc;
+    int* order;
 };
 
-static size_t chain_layout(const int64_t* dims, ChainArrays* a, void* base) {
-    const size_t cells = (size_t)dims[0] * (size_t)dims[1], points = (size_t)dims[2], mini = 2 * (size_t)dims[3] + 16;
+static size_t chain_layout(const int64_t* dims, int n_agents, ChainArrays* a, void* base) {
+    const size_t cells = (size_t)dims[0] * (size_t)dims[1], points = (size_t)dims[2], sl = (size_t)dims[3] + 16;
     char* ws = reinterpret_cast<char*>(base);
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return at; };
-    const size_t o_h = take(sizeof(ChainHeader)), o_lm = take((cells + 1) * 4), o_gk = take(points * 4), o_ms = take(mini * 4);
-    const size_t o_mx = take(mini * 8), o_my = take(mini * 8), o_ox = take(mini * 8), o_oy = take(mini * 8);
+    const size_t o_h = take(sizeof(ChainHeader)), o_lm = take((cells + 1) * 8), o_gk = take(points * 4);
+    const size_t o_lk = take(sl * 4), o_nx = take(sl * 4), o_fl = take(sl * 4), o_bc = take((sl / kAppendThreads + 2) * 4);
+    const size_t o_rx = take(sl * 8), o_ry = take(sl * 8), o_sb = take((size_t)n_agents * 32), o_or = take((size_t)n_agents * 4);
     if (a) {
         a->h = reinterpret_cast<ChainHeader*>(ws + o_h);
-        a->LM = reinterpret_cast<unsigned int*>(ws + o_lm);
+        a->LM = reinterpret_cast<uint2*>(ws + o_lm);
         a->gkey = reinterpret_cast<unsigned int*>(ws + o_gk);
-        a->msrc = reinterpret_cast<unsigned int*>(ws + o_ms);
-        a->mx = reinterpret_cast<double*>(ws + o_mx); a->my = reinterpret_cast<double*>(ws + o_my);
-        a->ox = reinterpret_cast<double*>(ws + o_ox); a->oy = reinterpret_cast<double*>(ws + o_oy);
+        a->lkey = reinterpret_cast<unsigned int*>(ws + o_lk);
+        a->next = reinterpret_cast<unsigned int*>(ws + o_nx);
+        a->flag = reinterpret_cast<unsigned int*>(ws + o_fl);
+        a->blockcount = reinterpret_cast<unsigned int*>(ws + o_bc);
+        a->resx = reinterpret_cast<double*>(ws + o_rx);
+        a->resy = reinterpret_cast<double*>(ws + o_ry);
+        a->slice_benc = reinterpret_cast<unsigned long long*>(ws + o_sb);
+        a->order = reinterpret_cast<int*>(ws + o_or);
     }
     return o;
 }
 
-static bool chain_dims_ok(const int64_t* dims) {
-    return dims && dims[0] > 0 && dims[1] > 0 && dims[2] > 0 && dims[3] > 0 && dims[0] * dims[1] < 0x7fffffffll &&
-           dims[2] < 0x7ffffff0ll;
+static bool chain_dims_ok(const int64_t* dims, int n_agents) {
+    return dims && n_agents > 0 && n_agents <= 65535 && dims[0] > 0 && dims[1] > 0 && dims[2] > 0 && dims[3] > 0 &&
+           dims[0] * dims[1] < 0x7fffffffll && dims[2] < 0x7ffffff0ll && dims[3] < 0x7ffffff0ll;
 }
 
-size_t mapmerge_chain_workspace_bytes(const int64_t* dims) {
-    if (!chain_dims_ok(dims)) return 0;
-    return chain_layout(dims, nullptr, nullptr);
+size_t mapmerge_chain_workspace_bytes(const int64_t* dims, int n_agents) {
+    if (!chain_dims_ok(dims, n_agents)) return 0;
+    return chain_layout(dims, n_agents, nullptr, nullptr);
 }
 
-// The workspace must be all-zero when a chain starts.  Computes the bounds of the adopted cloud.
-int mapmerge_chain_init(void* d_chain, size_t chain_bytes, const int64_t* dims, const double* d_px, const double* d_py,
-                        int64_t* d_count, void* stream) {
-    if (!d_chain || !chain_dims_ok(dims) || !d_px || !d_py || !d_count) { set_last_error("mapmerge_chain_init: bad arguments"); return OCCGRID_E_ARG; }
-    if (chain_bytes < chain_layout(dims, nullptr, nullptr)) { set_last_error("mapmerge_chain_init: workspace too small"); return OCCGRID_E_WORKSPACE; }
+int mapmerge_chain_init(void* d_chain, size_t chain_bytes, const int64_t* dims, int n_agents, const double* d_sx,
+                        const double* d_sy, const int64_t* d_agent_offset, const int32_t* order_host, int n_order,
+                        const double* d_px, const double* d_py, const int64_t* d_count, void* stream) {
+    if (!d_chain || !chain_dims_ok(dims, n_agents) || !d_sx || !d_sy || !d_agent_offset || !order_host || n_order < 0 ||
+        n_order > n_agents || !d_px || !d_py || !d_count) {
+        set_last_error("mapmerge_chain_init: bad arguments");
+        return OCCGRID_E_ARG;
+    }
+    if (chain_bytes < chain_layout(dims, n_agents, nullptr, nullptr)) { set_last_error("mapmerge_chain_init: workspace too small"); return OCCGRID_E_WORKSPACE; }
+    for (int i = 0; i < n_order; ++i)
+        if (order_host[i] < 0 || order_host[i] >= n_agents) { set_last_error("mapmerge_chain_init: order entry out of range"); return OCCGRID_E_ARG; }
     ChainArrays c;
-    chain_layout(dims, &c, d_chain);
+    chain_layout(dims, n_agents, &c, d_chain);
     cudaStream_t st = (cudaStream_t)stream;
-    ProfileScope ps(K_MERGE_BOUNDS, st, 3);
+    if (n_order) {
+        OCC_CUDA_TRY(cudaMemcpyAsync(c.order, order_host, sizeof(int) * (size_t)n_order, cudaMemcpyHostToDevice, st));
+        OCC_CUDA_TRY(cudaStreamSynchronize(st));           // order_host belongs to the caller
+    }
+    ProfileScope ps(K_CHAIN_PROBE, st, 5);
     k_chain_reset<<<1, 1, 0, st>>>(c.h);
+    k_chain_slice_bounds_init<<<(n_agents + 255) / 256, 256, 0, st>>>(c.slice_benc, n_agents);
+    dim3 grid((unsigned)grid_for(dims[3]), (unsigned)n_agents);
+    if (grid.x > 64) grid.x = 64;
+    k_chain_slice_bounds<<<grid, kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, c.slice_benc);
     k_chain_rebounds<<<148 * 8, kMT, 0, st>>>(d_px, d_py, (const long long*)d_count, c.h);
-    k_chain_final<<<1, 1, 0, st>>>(c.h, (long long*)d_count, 0);
+    k_chain_rebounds_apply<<<1, 1, 0, st>>>(c.h);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
 }
 
-// Decides, on the device, whether slice `agent` can be merged incrementally; synchronises the
-// stream to hand the 4-byte answer to the host: 0 incremental, 1 rebuild, 2 lattice overflow.
-int mapmerge_chain_probe(void* d_chain, const int64_t* dims, const double* d_sx, const double* d_sy,
-                         const int64_t* d_agent_offset, int agent, int64_t slice_points, double voxel, const int64_t* d_count,
-                         int32_t* d_status, int32_t* rebuild_out, void* stream) {
-    if (!d_chain || !chain_dims_ok(dims) || !d_sx || !d_sy || !d_agent_offset || agent < 0 || slice_points < 0 ||
-        slice_points > dims[3] || !(voxel > 0.0) || !d_count || !d_status || !rebuild_out) {
-        set_last_error("mapmerge_chain_probe: bad arguments");
+int mapmerge_chain_run(void* d_chain, const int64_t* dims, int n_agents, int n_order, int n_callbacks, const double* d_sx,
+                       const double* d_sy, const int64_t* d_agent_offset, double voxel, double* d_px, double* d_py,
+                       int64_t capacity, int64_t* d_count, int32_t* d_status, void* stream) {
+    if (!d_chain || !chain_dims_ok(dims, n_agents) || n_order < 0 || n_order > n_agents || n_callbacks < 0 || !d_sx || !d_sy ||
+        !d_agent_offset || !(voxel > 0.0) || !d_px || !d_py || capacity > dims[2] || !d_count || !d_status) {
+        set_last_error("mapmerge_chain_run: bad arguments");
         return OCCGRID_E_ARG;
     }
     ChainArrays c;
-    chain_layout(dims, &c, d_chain);
+    chain_layout(dims, n_agents, &c, d_chain);
     cudaStream_t st = (cudaStream_t)stream;
-    {
-        ProfileScope ps(K_CHAIN_PROBE, st, 2);
-        k_chain_slice_bounds<<<grid_for(slice_points), kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, agent, c.h);
-        k_chain_setup<<<1, 1, 0, st>>>(c.h, (const long long*)d_count, voxel, dims[0], dims[1], d_status);
+    const int gsl = grid_for(dims[3]);
+    const int gap = (int)((dims[3] + kAppendThreads - 1) / kAppendThreads);
+    const long long* offs = (const long long*)d_agent_offset;
+    ProfileScope ps(K_CHAIN_INCR, st, 3 * n_callbacks);
+    for (int i = 0; i < n_callbacks; ++i) {
+        k_chain_link<<<gsl, kMT, 0, st>>>(c.h, c.order, n_order, offs, c.slice_benc, d_sx, d_sy, voxel, dims[0], dims[1], c.LM,
+                                          c.lkey, c.next, d_status);
+        k_chain_fold<<<gsl, kMT, 0, st>>>(c.h, c.order, n_order, offs, d_sx, d_sy, voxel, dims[0], dims[1], c.LM, c.lkey, c.next,
+                                          d_px, d_py, c.resx, c.resy, c.flag, c.blockcount);
+        k_chain_append<<<gap, kAppendThreads, 0, st>>>(c.h, c.order, n_order, offs, voxel, dims[0], dims[1], c.LM, d_px, d_py,
+                                                       c.gkey, c.resx, c.resy, c.flag, c.blockcount, (long long*)d_count, capacity,
+                                                       d_status);
     }
     OCC_CUDA_TRY(cudaGetLastError());
-    int need = 0;
-    OCC_CUDA_TRY(cudaMemcpyAsync(&need, &c.h->need_rebuild, sizeof(int), cudaMemcpyDeviceToHost, st));
+    return OCCGRID_OK;
+}
+
+// Synchronises the stream; state_out = {cursor, stalled}.
+int mapmerge_chain_poll(void* d_chain, const int64_t* dims, int n_agents, int32_t* state_out, void* stream) {
+    if (!d_chain || !chain_dims_ok(dims, n_agents) || !state_out) { set_last_error("mapmerge_chain_poll: bad arguments"); return OCCGRID_E_ARG; }
+    ChainArrays c;
+    chain_layout(dims, n_agents, &c, d_chain);
+    cudaStream_t st = (cudaStream_t)stream;
+    int two[2] = {0, 0};
+    static_assert(offsetof(ChainHeader, cursor) == offsetof(ChainHeader, stalled) + sizeof(int), "stalled and cursor are read as one pair");
+    OCC_CUDA_TRY(cudaMemcpyAsync(two, &c.h->stalled, sizeof(two), cudaMemcpyDeviceToHost, st));
     OCC_CUDA_TRY(cudaStreamSynchronize(st));
-    *rebuild_out = need;
+    state_out[0] = two[1];
+    state_out[1] = two[0];
     return OCCGRID_OK;
 }
 
-static int chain_voxel_ws(const int64_t* dims, int64_t lattice_capacity_cells, void* d_voxel_ws, size_t voxel_ws_bytes,
-                          VoxelArrays* a, const char* who) {
-    size_t off[9];
-    if (!d_voxel_ws || lattice_capacity_cells < dims[0] * dims[1] ||
-        voxel_ws_bytes < voxel_layout(lattice_capacity_cells, dims[2], off)) {
-        set_last_error(who);
-        return OCCGRID_E_WORKSPACE;
-    }
-    *a = voxel_arrays(d_voxel_ws, off);
-    return OCCGRID_OK;
-}
-
-// Callback with an unchanged lattice: O(|slice|) work.  The cloud is updated in place.
-int mapmerge_chain_incremental(void* d_chain, const int64_t* dims, const double* d_sx, const double* d_sy,
-                               const int64_t* d_agent_offset, int agent, int64_t slice_points, double voxel, double* d_px,
-                               double* d_py, int64_t capacity, int64_t* d_count, int32_t* d_status, void* d_voxel_ws,
-                               size_t voxel_ws_bytes, int64_t lattice_capacity_cells, void* stream) {
-    if (!d_chain || !chain_dims_ok(dims) || !d_sx || !d_sy || !d_agent_offset || agent < 0 || slice_points < 0 ||
-        slice_points > dims[3] || !(voxel > 0.0) || !d_px || !d_py || capacity > dims[2] || !d_count || !d_status) {
-        set_last_error("mapmerge_chain_incremental: bad arguments");
-        return OCCGRID_E_ARG;
-    }
-    VoxelArrays va;
-    const int rc = chain_voxel_ws(dims, lattice_capacity_cells, d_voxel_ws, voxel_ws_bytes, &va, "mapmerge_chain_incremental: voxel workspace too small");
-    if (rc) return rc;
+int mapmerge_chain_rebounds(void* d_chain, const int64_t* dims, int n_agents, const double* d_px, const double* d_py,
+                            const int64_t* d_count, void* stream) {
+    if (!d_chain || !chain_dims_ok(dims, n_agents) || !d_px || !d_py || !d_count) { set_last_error("mapmerge_chain_rebounds: bad arguments"); return OCCGRID_E_ARG; }
     ChainArrays c;
-    chain_layout(dims, &c, d_chain);
+    chain_layout(dims, n_agents, &c, d_chain);
     cudaStream_t st = (cudaStream_t)stream;
-    const int gsl = grid_for(slice_points);
-    ProfileScope ps(K_CHAIN_INCR, st, 12);
-    k_chain_lookup<<<gsl, kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, agent, voxel, c.h, c.LM, d_px, d_py, c.mx, c.my,
-                                        c.msrc, d_status);
-    k_chain_copy_slice<<<gsl, kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, agent, c.h, c.mx, c.my);
-    launch_voxel_core(c.mx, c.my, &c.h->v, &c.h->v, va, 2 * slice_points, voxel, c.ox, c.oy, &c.h->mini_count, nullptr, st);
-    k_chain_writeback<<<grid_for(2 * slice_points), kMT, 0, st>>>(c.h, c.ox, c.oy, c.msrc, d_px, d_py, c.gkey, c.LM, voxel,
-                                                                  (const long long*)d_count, capacity, d_status);
-    k_chain_rebounds<<<148 * 8, kMT, 0, st>>>(d_px, d_py, &c.h->n_next, c.h);
-    k_chain_final<<<1, 1, 0, st>>>(c.h, (long long*)d_count, 1);
+    ProfileScope ps(K_CHAIN_PROBE, st, 2);
+    k_chain_rebounds<<<148 * 8, kMT, 0, st>>>(d_px, d_py, (const long long*)d_count, c.h);
+    k_chain_rebounds_apply<<<1, 1, 0, st>>>(c.h);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
 }
 
-// Callback whose lattice moved (or whose map is stale): append the slice, full filter into
-// (d_out_px, d_out_py, d_out_count), rebuild the voxel -> index map for the new cloud.
-int mapmerge_chain_rebuild(void* d_chain, const int64_t* dims, const double* d_sx, const double* d_sy,
+int mapmerge_chain_rebuild(void* d_chain, const int64_t* dims, int n_agents, const double* d_sx, const double* d_sy,
                            const int64_t* d_agent_offset, int agent, double voxel, double* d_px, double* d_py, int64_t capacity,
                            int64_t* d_count, double* d_out_px, double* d_out_py, int64_t* d_out_count, int32_t* d_status,
                            void* d_voxel_ws, size_t voxel_ws_bytes, int64_t lattice_capacity_cells, void* stream) {
-    if (!d_chain || !chain_dims_ok(dims) || !d_sx || !d_sy || !d_agent_offset || agent < 0 || !(voxel > 0.0) || !d_px || !d_py ||
-        capacity > dims[2] || !d_count || !d_out_px || !d_out_py || !d_out_count || !d_status) {
+    if (!d_chain || !chain_dims_ok(dims, n_agents) || !d_sx || !d_sy || !d_agent_offset || agent < 0 || agent >= n_agents ||
+        !(voxel > 0.0) || !d_px || !d_py || capacity > dims[2] || !d_count || !d_out_px || !d_out_py || !d_out_count || !d_status) {
         set_last_error("mapmerge_chain_rebuild: bad arguments");
         return OCCGRID_E_ARG;
     }
-    VoxelArrays va;
-    const int rc = chain_voxel_ws(dims, lattice_capacity_cells, d_voxel_ws, voxel_ws_bytes, &va, "mapmerge_chain_rebuild: voxel workspace too small");
-    if (rc) return rc;
+    size_t off[9];
+    if (!d_voxel_ws || lattice_capacity_cells < dims[0] * dims[1] || voxel_ws_bytes < voxel_layout(lattice_capacity_cells, dims[2], off)) {
+        set_last_error("mapmerge_chain_rebuild: voxel workspace too small");
+        return OCCGRID_E_WORKSPACE;
+    }
+    const VoxelArrays va = voxel_arrays(d_voxel_ws, off);
     ChainArrays c;
-    chain_layout(dims, &c, d_chain);
+    chain_layout(dims, n_agents, &c, d_chain);
     cudaStream_t st = (cudaStream_t)stream;
     const int gp = grid_for(capacity);
     ProfileScope ps(K_CHAIN_REBUILD, st, 13);
@@ -1235,10 +1332,10 @@ int mapmerge_chain_rebuild(void* d_chain, const int64_t* dims, const double* d_s
     k_append_slice<<<148, kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, agent, d_px, d_py, capacity, (long long*)d_count,
                                          d_status, nullptr);
     k_bump_count<<<1, 1, 0, st>>>((const long long*)d_agent_offset, agent, capacity, (long long*)d_count);
-    k_chain_rebuild_hdr<<<1, 1, 0, st>>>(c.h, (const long long*)d_count, dims[2], d_status);
+    k_chain_rebuild_hdr<<<1, 1, 0, st>>>(c.h, c.slice_benc, agent, (const long long*)d_count, voxel, dims[0], dims[1], dims[2], d_status);
     launch_voxel_core(d_px, d_py, &c.h->v, &c.h->v, va, capacity, voxel, d_out_px, d_out_py, (long long*)d_out_count, c.h->gb_enc, st);
     k_chain_lm_build<<<gp, kMT, 0, st>>>(c.h, d_out_px, d_out_py, (const long long*)d_out_count, voxel, c.LM, c.gkey);
-    k_chain_final<<<1, 1, 0, st>>>(c.h, (long long*)d_out_count, 2);
+    k_chain_rebuild_done<<<1, 1, 0, st>>>(c.h);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
 }

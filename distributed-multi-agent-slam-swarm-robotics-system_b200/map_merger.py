@@ -338,7 +338,7 @@ class MapMerger:
                     stage.x.data_ptr(), stage.y.data_ptr(), stage.capacity, counts.data_ptr(), offs.data_ptr(),
                     self._status.data_ptr(), bws.data_ptr(), bws.numel(), self._stream())
                 _native.check(rc, 'mapmerge_extract_batch_write')
-            chain = None
+            chain_order = []
             slice_cap = max([n for n, (u, _) in zip(n_occ, mats) if u] + [1])
             lat_w, lat_h = int((bb[2] - bb[0]) / v) + 4, int((bb[3] - bb[1]) / v) + 4
             for a in range(A):
@@ -364,10 +364,9 @@ class MapMerger:
                     self.map_resolution = float(res)
                     self.map_origin = [float(origins[a][0]), float(origins[a][1])]
                     continue
-                if chain is None:
-                    chain = self._chain_begin(lat_w, lat_h, slice_cap)
-                self._chain_step(chain, stage, offs, a, n_occ[a])
-            self.chain_stats = None if chain is None else {'callbacks': chain['steps'], 'rebuilds': chain['rebuilds']}
+                chain_order.append(a)
+            chain = self._run_chain(stage, offs, A, chain_order, lat_w, lat_h, slice_cap) if chain_order else None
+            self.chain_stats = chain
             self._n_global = int(self._cloud.count.item())          # host sync (with the status word)
             self._check_status()
         out = self.publish_global_map(to_host=to_host)
@@ -375,47 +374,62 @@ class MapMerger:
             return None, None
         return out.data, (out.info.origin.position.x, out.info.origin.position.y)
 
-    def _chain_begin(self, lat_w, lat_h, slice_cap):
-        """State of the incremental callback chain (see mapmerge_chain_* in the header)."""
-        pcap = max(self._cloud.capacity, 2 * slice_cap + 16)
+    def _run_chain(self, stage, offs, n_agents, order, lat_w, lat_h, slice_cap):
+        """The callbacks `global += slice; global = voxel_down_sample(global)` (:58-60) for the
+        slices `order` of a batched extraction, through the incremental chain (mapmerge_chain_*
+        in the header).  Callbacks are enqueued a few at a time without host round trips; the
+        host only steps in for the ones that need the full filter."""
+        lib = self._lib
+        pcap = self._cloud.capacity
         dims = np.array([lat_w, lat_h, pcap, slice_cap], np.int64)
-        nbytes = self._lib.mapmerge_chain_workspace_bytes(dims.ctypes.data)
+        nbytes = lib.mapmerge_chain_workspace_bytes(dims.ctypes.data, n_agents)
         if nbytes == 0:
             raise OccGridError('map merge: voxel lattice %d x %d too large' % (lat_w, lat_h))
         ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
         vws = self._voxel_workspace(lat_w * lat_h, pcap)
-        rc = self._lib.mapmerge_chain_init(ws.data_ptr(), ws.numel(), dims.ctypes.data, self._cloud.x.data_ptr(),
-                                           self._cloud.y.data_ptr(), self._cloud.count.data_ptr(), self._stream())
-        _native.check(rc, 'mapmerge_chain_init')
-        return {'ws': ws, 'dims': dims, 'vws': vws, 'need': ctypes.c_int32(0), 'rebuilds': 0, 'steps': 0}
-
-    def _chain_step(self, chain, stage, offs, a, n_slice):
-        """One callback `global += slice; global = voxel_down_sample(global)` (:58-60)."""
-        lib, ws, dims, vws, need = self._lib, chain['ws'], chain['dims'], chain['vws'], chain['need']
-        v = self.map_resolution
+        order_h = np.ascontiguousarray(np.asarray(order, np.int32))
         c = self._cloud
-        rc = lib.mapmerge_chain_probe(ws.data_ptr(), dims.ctypes.data, stage.x.data_ptr(), stage.y.data_ptr(), offs.data_ptr(), a,
-                                      n_slice, v, c.count.data_ptr(), self._status.data_ptr(), ctypes.byref(need), self._stream())
-        _native.check(rc, 'mapmerge_chain_probe')
-        chain['steps'] += 1
-        if need.value == 2:
-            self._check_status()
-            raise OccGridError('map merge: voxel lattice does not fit the chain workspace')
-        if need.value == 0:
-            rc = lib.mapmerge_chain_incremental(ws.data_ptr(), dims.ctypes.data, stage.x.data_ptr(), stage.y.data_ptr(),
-                                                offs.data_ptr(), a, n_slice, v, c.x.data_ptr(), c.y.data_ptr(), c.capacity,
-                                                c.count.data_ptr(), self._status.data_ptr(), vws.data_ptr(), vws.numel(),
-                                                self._lattice_cap, self._stream())
-            _native.check(rc, 'mapmerge_chain_incremental')
-            return
-        chain['rebuilds'] += 1
-        sp = self._spare
-        rc = lib.mapmerge_chain_rebuild(ws.data_ptr(), dims.ctypes.data, stage.x.data_ptr(), stage.y.data_ptr(), offs.data_ptr(), a,
-                                        v, c.x.data_ptr(), c.y.data_ptr(), c.capacity, c.count.data_ptr(), sp.x.data_ptr(),
-                                        sp.y.data_ptr(), sp.count.data_ptr(), self._status.data_ptr(), vws.data_ptr(),
-                                        vws.numel(), self._lattice_cap, self._stream())
-        _native.check(rc, 'mapmerge_chain_rebuild')
-        self._cloud, self._spare = self._spare, self._cloud
+        rc = lib.mapmerge_chain_init(ws.data_ptr(), ws.numel(), dims.ctypes.data, n_agents, stage.x.data_ptr(), stage.y.data_ptr(),
+                                     offs.data_ptr(), order_h.ctypes.data, len(order), c.x.data_ptr(), c.y.data_ptr(),
+                                     c.count.data_ptr(), self._stream())
+        _native.check(rc, 'mapmerge_chain_init')
+        v = self.map_resolution
+        state = (ctypes.c_int32 * 2)()
+        stats = {'callbacks': len(order), 'rebuilds': 0, 'rebounds': 0, 'polls': 0}
+        cursor, burst = 0, 1
+        while cursor < len(order):
+            c = self._cloud
+            k = min(burst, len(order) - cursor)
+            rc = lib.mapmerge_chain_run(ws.data_ptr(), dims.ctypes.data, n_agents, len(order), k, stage.x.data_ptr(),
+                                        stage.y.data_ptr(), offs.data_ptr(), v, c.x.data_ptr(), c.y.data_ptr(), c.capacity,
+                                        c.count.data_ptr(), self._status.data_ptr(), self._stream())
+            _native.check(rc, 'mapmerge_chain_run')
+            _native.check(lib.mapmerge_chain_poll(ws.data_ptr(), dims.ctypes.data, n_agents, state, self._stream()), 'mapmerge_chain_poll')
+            stats['polls'] += 1
+            cursor, stalled = int(state[0]), int(state[1])
+            if stalled == 0:
+                burst = min(burst * 2, 32)
+            elif stalled == 1:                   # the lattice moved: full filter + new voxel map
+                sp = self._spare
+                rc = lib.mapmerge_chain_rebuild(ws.data_ptr(), dims.ctypes.data, n_agents, stage.x.data_ptr(), stage.y.data_ptr(),
+                                                offs.data_ptr(), order[cursor], v, c.x.data_ptr(), c.y.data_ptr(), c.capacity,
+                                                c.count.data_ptr(), sp.x.data_ptr(), sp.y.data_ptr(), sp.count.data_ptr(),
+                                                self._status.data_ptr(), vws.data_ptr(), vws.numel(), self._lattice_cap,
+                                                self._stream())
+                _native.check(rc, 'mapmerge_chain_rebuild')
+                self._cloud, self._spare = self._spare, self._cloud
+                stats['rebuilds'] += 1
+                cursor += 1
+                burst = 2
+            elif stalled == 3:                   # min corner may have moved inwards: exact bounds first
+                rc = lib.mapmerge_chain_rebounds(ws.data_ptr(), dims.ctypes.data, n_agents, c.x.data_ptr(), c.y.data_ptr(),
+                                                 c.count.data_ptr(), self._stream())
+                _native.check(rc, 'mapmerge_chain_rebounds')
+                stats['rebounds'] += 1
+            else:
+                self._check_status()
+                raise OccGridError('map merge: voxel lattice does not fit the chain workspace')
+        return stats
 
     def _extract_async(self, msg, T):
         """grid_to_pcd (+ transform) appended to the global cloud, no host read-back."""

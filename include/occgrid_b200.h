@@ -274,40 +274,45 @@ int mapmerge_voxel_downsample(const double* d_px, const double* d_py, const int6
                               int32_t* d_status, void* d_ws, size_t ws_bytes, void* stream);
 
 /* Incremental form of the callback chain `global_pcd += local; global_pcd =
- * global_pcd.voxel_down_sample(v)` (map_merger.py:58-60) for the slices of a batched extraction.
+ * global_pcd.voxel_down_sample(v)` (map_merger.py:58-60) over the slices of a batched extraction.
  * A filtered cloud holds one point per voxel, so while the lattice anchor (min_bound - v/2) is
  * bitwise unchanged a callback only touches the voxels its slice falls into: the chain keeps a
- * voxel -> cloud-index map, filters [touched cloud points] ++ [slice] and writes the means back
- * in place (new voxels are appended in order of first appearance).  Results are bitwise those of
+ * voxel -> cloud-index map, re-averages the touched voxels in place and appends the new voxels in
+ * order of first appearance (three kernels over the slice).  A callback whose anchor moved, or
+ * whose means left their voxels, needs the full filter (_rebuild).  Results are bitwise those of
  * mapmerge_append_slice + mapmerge_voxel_downsample per callback.
  *   dims (host) = {lattice_w, lattice_h, point_capacity, slice_capacity}: a lattice that covers
  *   every cloud of the chain, the largest cloud, the largest slice.
- *   _init      d_chain must be all-zero; takes the bounds of the adopted cloud.
- *   _probe     synchronises the stream; *rebuild_out = 0: call _incremental, 1: call _rebuild,
- *              2: the lattice does not fit dims (status word set).
- *   _incremental  updates (d_px, d_py, d_count) in place.
- *   _rebuild   appends the slice, filters the whole cloud into (d_out_*) and rebuilds the map
- *              (the caller swaps the clouds, as after mapmerge_voxel_downsample).
- * d_voxel_ws is a mapmerge_voxel_downsample workspace with lattice capacity >= lattice_w *
- * lattice_h and point capacity dims[2] >= 2 * slice_capacity + 16. */
-size_t mapmerge_chain_workspace_bytes(const int64_t* dims);
-int mapmerge_chain_init(void* d_chain, size_t chain_bytes, const int64_t* dims, const double* d_px,
-                        const double* d_py, int64_t* d_count, void* stream);
-int mapmerge_chain_probe(void* d_chain, const int64_t* dims, const double* d_sx, const double* d_sy,
-                         const int64_t* d_agent_offset, int agent, int64_t slice_points, double voxel,
-                         const int64_t* d_count, int32_t* d_status, int32_t* rebuild_out, void* stream);
-int mapmerge_chain_incremental(void* d_chain, const int64_t* dims, const double* d_sx,
-                               const double* d_sy, const int64_t* d_agent_offset, int agent,
-                               int64_t slice_points, double voxel, double* d_px, double* d_py,
-                               int64_t capacity, int64_t* d_count, int32_t* d_status,
-                               void* d_voxel_ws, size_t voxel_ws_bytes,
-                               int64_t lattice_capacity_cells, void* stream);
-int mapmerge_chain_rebuild(void* d_chain, const int64_t* dims, const double* d_sx, const double* d_sy,
-                           const int64_t* d_agent_offset, int agent, double voxel, double* d_px,
-                           double* d_py, int64_t capacity, int64_t* d_count, double* d_out_px,
-                           double* d_out_py, int64_t* d_out_count, int32_t* d_status,
-                           void* d_voxel_ws, size_t voxel_ws_bytes, int64_t lattice_capacity_cells,
-                           void* stream);
+ *   order_host[n_order]: the agents (slice indices) to merge, in callback order.
+ *   _init      d_chain must be all-zero; takes the bounds of every slice and of the adopted cloud.
+ *   _run       enqueues n_callbacks incremental callbacks; each takes the next agent from a device
+ *              cursor; once a callback needs the host, it and all later ones are no-ops.
+ *   _poll      synchronises; state_out = {cursor, stalled}: stalled 0 = running, 1 = callback
+ *              order[cursor] needs _rebuild, 2 = lattice does not fit dims (status word set),
+ *              3 = the cloud's min corner may have moved inwards: call _rebounds, then go on.
+ *   _rebuild   appends slice `agent`, filters the whole cloud into (d_out_*), rebuilds the map and
+ *              advances the cursor (the caller swaps the clouds, as after
+ *              mapmerge_voxel_downsample).  d_voxel_ws: a mapmerge_voxel_downsample workspace with
+ *              lattice capacity >= lattice_w * lattice_h and point capacity dims[2]. */
+size_t mapmerge_chain_workspace_bytes(const int64_t* dims, int n_agents);
+int mapmerge_chain_init(void* d_chain, size_t chain_bytes, const int64_t* dims, int n_agents,
+                        const double* d_sx, const double* d_sy, const int64_t* d_agent_offset,
+                        const int32_t* order_host, int n_order, const double* d_px, const double* d_py,
+                        const int64_t* d_count, void* stream);
+int mapmerge_chain_run(void* d_chain, const int64_t* dims, int n_agents, int n_order, int n_callbacks,
+                       const double* d_sx, const double* d_sy, const int64_t* d_agent_offset,
+                       double voxel, double* d_px, double* d_py, int64_t capacity, int64_t* d_count,
+                       int32_t* d_status, void* stream);
+int mapmerge_chain_poll(void* d_chain, const int64_t* dims, int n_agents, int32_t* state_out,
+                        void* stream);
+int mapmerge_chain_rebounds(void* d_chain, const int64_t* dims, int n_agents, const double* d_px,
+                            const double* d_py, const int64_t* d_count, void* stream);
+int mapmerge_chain_rebuild(void* d_chain, const int64_t* dims, int n_agents, const double* d_sx,
+                           const double* d_sy, const int64_t* d_agent_offset, int agent, double voxel,
+                           double* d_px, double* d_py, int64_t capacity, int64_t* d_count,
+                           double* d_out_px, double* d_out_py, int64_t* d_out_count,
+                           int32_t* d_status, void* d_voxel_ws, size_t voxel_ws_bytes,
+                           int64_t lattice_capacity_cells, void* stream);
 
 /* publish_global_map's rasterisation (:103-111): fill width x height with -1, then
  * grid[int((y-min_y)/res)][int((x-min_x)/res)] = 100 with index clipping (:108-109).

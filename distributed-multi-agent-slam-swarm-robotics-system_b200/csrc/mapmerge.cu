@@ -619,7 +619,7 @@ struct ChainHeader {
     unsigned int ticket;
 };
 enum { CHAIN_RUN = 0, CHAIN_REBUILD = 1, CHAIN_OVERFLOW = 2, CHAIN_REBOUND = 3 };
-constexpr int kAppendThreads = 1024;
+constexpr int kAppendThreads = 256;
 
 __device__ __forceinline__ bool voxel_key_of(double x, double y, double mbx, double mby, double voxel, long long W,
                                              long long H, unsigned int* key) {
@@ -721,44 +721,52 @@ k_chain_fold(ChainHeader* __restrict__ h, const int* __restrict__ order, int n_o
     const double mbx = h->mbx, mby = h->mby;
     const double g0 = dec_double(h->gb_enc[0]), g1 = dec_double(h->gb_enc[1]);
     double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
-    for (long long j = (long long)blockIdx.x * kMT + threadIdx.x; j < n; j += (long long)gridDim.x * kMT) {
-        const unsigned int k = lkey[j];
-        const uint2 e = LM[k];
-        if (e.y != (unsigned int)j + 1u) continue;             // not the top of its voxel's stack
-        unsigned int cnt = 0, head = (unsigned int)j;
-        for (unsigned int q = e.y; q; q = next[q - 1]) { ++cnt; head = min(head, q - 1u); }
-        double ax, ay;
-        long long last;
-        unsigned int remaining, total;
-        if (e.x) { ax = gx[e.x - 1]; ay = gy[e.x - 1]; last = -1; remaining = cnt; total = cnt + 1u; }
-        else     { ax = sx[b + head]; ay = sy[b + head]; last = head; remaining = cnt - 1u; total = cnt; }
-        for (unsigned int r = 0; r < remaining; ++r) {         // ascending slice index; stacks are tiny
-            unsigned int best = 0xffffffffu;
-            for (unsigned int q = e.y; q; q = next[q - 1]) {
-                const unsigned int idx = q - 1u;
-                if ((long long)idx > last && idx < best) best = idx;
+    const int lane = threadIdx.x & 31;
+    for (long long j0 = (long long)blockIdx.x * kMT + (threadIdx.x & ~31); j0 < n; j0 += (long long)gridDim.x * kMT) {
+        const long long j = j0 + lane;
+        int parked = -1;                                       // append block a new voxel of this thread goes to
+        unsigned int k = 0;
+        uint2 e = make_uint2(0u, 0u);
+        if (j < n) { k = lkey[j]; e = LM[k]; }
+        if (j < n && e.y == (unsigned int)j + 1u) {            // top of its voxel's stack: this thread folds it
+            unsigned int cnt = 0, head = (unsigned int)j;
+            for (unsigned int q = e.y; q; q = next[q - 1]) { ++cnt; head = min(head, q - 1u); }
+            double ax, ay;
+            long long last;
+            unsigned int remaining, total;
+            if (e.x) { ax = gx[e.x - 1]; ay = gy[e.x - 1]; last = -1; remaining = cnt; total = cnt + 1u; }
+            else     { ax = sx[b + head]; ay = sy[b + head]; last = head; remaining = cnt - 1u; total = cnt; }
+            for (unsigned int r = 0; r < remaining; ++r) {     // ascending slice index; stacks are tiny
+                unsigned int best = 0xffffffffu;
+                for (unsigned int q = e.y; q; q = next[q - 1]) {
+                    const unsigned int idx = q - 1u;
+                    if ((long long)idx > last && idx < best) best = idx;
+                }
+                last = best;
+                ax = OCC_DADD(ax, sx[b + best]);
+                ay = OCC_DADD(ay, sy[b + best]);
             }
-            last = best;
-            ax = OCC_DADD(ax, sx[b + best]);
-            ay = OCC_DADD(ay, sy[b + best]);
+            const double c = (double)total;
+            const double x = OCC_DDIV(ax, c), y = OCC_DDIV(ay, c);
+            if (e.x) {
+                const unsigned int g = e.x - 1u;
+                const double oldx = gx[g], oldy = gy[g];
+                // a point on the min corner moving inwards: the bounds need a full pass before the next decision
+                if ((oldx <= g0 && x > oldx) || (oldy <= g1 && y > oldy)) h->bounds_dirty = 1;
+                gx[g] = x; gy[g] = y;
+                unsigned int k2 = 0;
+                if (!voxel_key_of(x, y, mbx, mby, voxel, W, H, &k2) || k2 != k) h->force_rebuild = 1;   // LM no longer describes the cloud
+                mnx = fmin(mnx, x); mxx = fmax(mxx, x); mny = fmin(mny, y); mxy = fmax(mxy, y);
+            } else {
+                resx[head] = x; resy[head] = y;
+                flag[head] = 1u;
+                parked = (int)(head / kAppendThreads);
+            }
+            LM[k].y = 0u;
         }
-        const double c = (double)total;
-        const double x = OCC_DDIV(ax, c), y = OCC_DDIV(ay, c);
-        if (e.x) {
-            const unsigned int g = e.x - 1u;
-            const double oldx = gx[g], oldy = gy[g];
-            // a point on the min corner moving inwards: the bounds need a full pass before the next decision
-            if ((oldx <= g0 && x > oldx) || (oldy <= g1 && y > oldy)) h->bounds_dirty = 1;
-            gx[g] = x; gy[g] = y;
-            unsigned int k2 = 0;
-            if (!voxel_key_of(x, y, mbx, mby, voxel, W, H, &k2) || k2 != k) h->force_rebuild = 1;   // LM no longer describes the cloud
-            mnx = fmin(mnx, x); mxx = fmax(mxx, x); mny = fmin(mny, y); mxy = fmax(mxy, y);
-        } else {
-            resx[head] = x; resy[head] = y;
-            flag[head] = 1u;
-            atomicAdd(&blockcount[head / kAppendThreads], 1u);
-        }
-        LM[k].y = 0u;
+        __syncwarp();
+        const unsigned int peers = __match_any_sync(0xffffffffu, parked);      // one atomic per distinct block per warp
+        if (parked >= 0 && lane == __ffs(peers) - 1) atomicAdd(&blockcount[parked], (unsigned int)__popc(peers));
     }
     block_bounds_atomic(mnx, mny, mxx, mxy, h->gb_enc);
 }
@@ -807,13 +815,20 @@ k_chain_append(ChainHeader* __restrict__ h, const int* __restrict__ order, int n
         }
     }
     block_bounds_atomic(mnx, mny, mxx, mxy, h->gb_enc);
+    __shared__ int s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(&h->ticket, 1u) == gridDim.x - 1) {      // every block has read n_g and its counts
-            unsigned int total = 0;
-            const unsigned int nb = (unsigned int)((n + kAppendThreads - 1) / kAppendThreads);
-            for (unsigned int bb = 0; bb < nb; ++bb) { total += blockcount[bb]; blockcount[bb] = 0u; }
+        s_last = (atomicAdd(&h->ticket, 1u) == gridDim.x - 1);     // every block has read n_g and its counts
+    }
+    __syncthreads();
+    if (s_last) {
+        const unsigned int nb = (unsigned int)((n + kAppendThreads - 1) / kAppendThreads);
+        unsigned int mine_total = 0;
+        for (unsigned int bb = threadIdx.x; bb < nb; bb += kAppendThreads) { mine_total += blockcount[bb]; blockcount[bb] = 0u; }
+        unsigned int total;
+        block_exclusive_scan(mine_total, s_warp, &total);
+        if (threadIdx.x == 0) {
             long long nn = n_g + total;
             *d_count = nn > capacity ? capacity : nn;
             h->ticket = 0u;

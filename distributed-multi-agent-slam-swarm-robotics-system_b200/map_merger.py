@@ -264,6 +264,37 @@ class MapMerger:
         return msg
 
     # ---- batched entry ---------------------------------------------------------------------
+    def _as_device_grids(self, grids):
+        """List of int8 [H, W] device tensors (no copies for tensors already in that form)."""
+        out = []
+        for g in grids:
+            if isinstance(g, torch.Tensor) and g.is_cuda and g.dtype == torch.int8 and g.dim() == 2 and g.is_contiguous() \
+                    and g.device == self.device:
+                out.append(g)
+            else:
+                out.append(self._device_grid(make_grid_msg(g, g.shape[1], g.shape[0], 0.0, 0, 0)))
+        return out
+
+    @staticmethod
+    def _as_matrices(transforms, A):
+        """[A, 4, 4] float64 from None / [A, 4, 4] / [A, 3] (tx, ty, theta) / a list mixing both."""
+        if transforms is None:
+            return np.tile(np.eye(4), (A, 1, 1))
+        try:
+            t = np.asarray(transforms, np.float64)
+        except ValueError:
+            t = None
+        if t is not None and t.shape == (A, 4, 4):
+            return np.ascontiguousarray(t)
+        out = np.tile(np.eye(4), (A, 1, 1))
+        for a in range(A):
+            T = transforms[a]
+            if T is None:
+                continue
+            T = np.asarray(T, np.float64)
+            out[a] = se2_matrix(*T.tolist()) if T.size == 3 else T.reshape(4, 4)
+        return np.ascontiguousarray(out)
+
     def merge(self, grids, origins, res, transforms=None, fitness=None, to_host=True):
         """Fuse A agent grids in order: ``grids`` int8 [A, H, W] (host or device), ``origins``
         float64 [A, 2], ``transforms`` [A, 4, 4] or [A, 3] (tx, ty, theta) or None (identity).
@@ -271,17 +302,16 @@ class MapMerger:
         publishes once at the end.  Equal-shaped grids are extracted in one batched launch and
         fused by the incremental chain (``mapmerge_chain_*``: work per callback proportional to the
         slice, not to the accumulated cloud, while the voxel lattice stands still); the host reads
-        the occupied-cell counts up front, a 4-byte incremental/rebuild decision per callback and
-        the final bounds.
+        the occupied-cell counts up front, the chain state every few callbacks and the final bounds.
         Returns (int8 grid [H', W'], (origin_x, origin_y))."""
         A = len(grids)
         with torch.cuda.device(self.device):
-            dev = [self._device_grid(make_grid_msg(grids[a], grids[a].shape[1], grids[a].shape[0], res, 0, 0)) for a in range(A)]
+            dev = self._as_device_grids(grids)
             same_shape = all(d.shape == dev[0].shape for d in dev)
             counts = torch.zeros(A, dtype=torch.int64, device=self.device)
             if same_shape:                       # one pass over all grids
                 h, w = dev[0].shape
-                ptrs = torch.tensor([d.data_ptr() for d in dev], dtype=torch.int64, device=self.device)
+                ptrs = torch.from_numpy(np.array([d.data_ptr() for d in dev], np.int64)).to(self.device)
                 bws = self._workspace('extract_batch', self._lib.mapmerge_extract_batch_workspace_bytes(h * w, A))
                 rc = self._lib.mapmerge_extract_batch_count(ptrs.data_ptr(), A, w, h, counts.data_ptr(), bws.data_ptr(),
                                                             bws.numel(), self._stream())
@@ -290,82 +320,77 @@ class MapMerger:
                 for a in range(A):
                     rc = self._lib.mapmerge_count_occupied(dev[a].data_ptr(), dev[a].numel(), counts[a:a + 1].data_ptr(), self._stream())
                     _native.check(rc, 'mapmerge_count_occupied')
-            n_occ = counts.cpu().tolist()                           # host sync 1
-            if self._n_global and self._cloud is not None:
+            # host work that does not need the counts overlaps the counting pass
+            org = np.ascontiguousarray(np.asarray(origins, np.float64).reshape(A, 2))
+            Tm = self._as_matrices(transforms, A)
+            fit = np.ones(A) if fitness is None else np.asarray(fitness, np.float64).reshape(A)
+            hw = np.array([[d.shape[0], d.shape[1]] for d in dev], np.float64)
+            n_occ = counts.cpu().numpy()                            # host sync 1
+            have_cloud = self._n_global > 0
+            use = (n_occ > 0) & (fit >= 0.6)                        # :37-38, :54-56
+            if not have_cloud:
+                nz = np.flatnonzero(n_occ > 0)
+                if nz.size == 0:
+                    return None, None
+                use[:nz[0]] = False
+                use[nz[0]] = True                                   # the first cloud is adopted as is (:40-43):
+                Tm[nz[0]] = np.eye(4)                               # no ICP, no fitness test, no transform
+            used = np.flatnonzero(use)
+            if have_cloud:
                 self._bounds_of(self._cloud)
                 bb = self._bounds.cpu().numpy().tolist()
             else:
                 bb = [math.inf, math.inf, -math.inf, -math.inf]
-            mats = []
-            first_seen = self._n_global > 0
-            for a in range(A):
-                T = None if transforms is None else transforms[a]
-                if T is not None and np.asarray(T).size == 3:
-                    T = se2_matrix(*np.asarray(T, np.float64).tolist())
-                f = 1.0 if fitness is None else fitness[a]
-                use = n_occ[a] > 0 and (not first_seen or f >= 0.6)
-                if use and not first_seen:
-                    T = None                                        # the first cloud is adopted as is (:40-43)
-                mats.append((use, T))
-                if use:
-                    h, w = dev[a].shape
-                    first_seen = True
-                    M = np.eye(4) if T is None else np.asarray(T, np.float64).reshape(4, 4)
-                    for cx in (origins[a][0], origins[a][0] + w * res):
-                        for cy in (origins[a][1], origins[a][1] + h * res):
-                            px = M[0, 0] * cx + M[0, 1] * cy + M[0, 3]
-                            py = M[1, 0] * cx + M[1, 1] * cy + M[1, 3]
-                            bb = [min(bb[0], px), min(bb[1], py), max(bb[2], px), max(bb[3], py)]
-            n_new = sum(n for n, (u, _) in zip(n_occ, mats) if u)
+            if used.size:
+                # transformed extents of the used grids bound every cloud of the chain
+                x0, y0 = org[used, 0], org[used, 1]
+                x1, y1 = x0 + hw[used, 1] * res, y0 + hw[used, 0] * res
+                M = Tm[used]
+                cx = np.stack([x0, x0, x1, x1], 1)
+                cy = np.stack([y0, y1, y0, y1], 1)
+                px = M[:, 0, 0, None] * cx + M[:, 0, 1, None] * cy + M[:, 0, 3, None]
+                py = M[:, 1, 0, None] * cx + M[:, 1, 1, None] * cy + M[:, 1, 3, None]
+                bb = [min(bb[0], float(px.min())), min(bb[1], float(py.min())), max(bb[2], float(px.max())), max(bb[3], float(py.max()))]
+            n_new = int(n_occ[used].sum())
             total = self._n_global + n_new
             if total == 0:
                 return None, None
             self._ensure_capacity(total + 1024)
-            first = self._n_global == 0
+            first = not have_cloud
             v = float(res) if first else self.map_resolution
-            cells = (int((bb[2] - bb[0]) / v) + 4) * (int((bb[3] - bb[1]) / v) + 4)
+            lat_w, lat_h = int((bb[2] - bb[0]) / v) + 4, int((bb[3] - bb[1]) / v) + 4
             if same_shape:                       # all slices extracted + transformed in one launch
                 h, w = dev[0].shape
                 stage = _Cloud(n_new + 16, self.device)
                 offs = torch.zeros(A + 1, dtype=torch.int64, device=self.device)
                 xf = torch.empty(A * 96, dtype=torch.uint8, device=self.device)
-                org = torch.from_numpy(np.ascontiguousarray(np.asarray(origins, np.float64).reshape(A, 2))).to(self.device)
-                Th = np.ascontiguousarray(np.stack([np.eye(4) if T is None else np.asarray(T, np.float64).reshape(4, 4)
-                                                    for _, T in mats]))
-                use_h = np.ascontiguousarray(np.array([1 if u else 0 for u, _ in mats], np.uint8))
+                org_d = torch.from_numpy(org).to(self.device)
+                use_h = np.ascontiguousarray(use.astype(np.uint8))
                 rc = self._lib.mapmerge_extract_batch_write(
-                    ptrs.data_ptr(), A, w, h, float(res), org.data_ptr(), Th.ctypes.data, use_h.ctypes.data, xf.data_ptr(),
+                    ptrs.data_ptr(), A, w, h, float(res), org_d.data_ptr(), Tm.ctypes.data, use_h.ctypes.data, xf.data_ptr(),
                     stage.x.data_ptr(), stage.y.data_ptr(), stage.capacity, counts.data_ptr(), offs.data_ptr(),
                     self._status.data_ptr(), bws.data_ptr(), bws.numel(), self._stream())
                 _native.check(rc, 'mapmerge_extract_batch_write')
-            chain_order = []
-            slice_cap = max([n for n, (u, _) in zip(n_occ, mats) if u] + [1])
-            lat_w, lat_h = int((bb[2] - bb[0]) / v) + 4, int((bb[3] - bb[1]) / v) + 4
-            for a in range(A):
-                use, T = mats[a]
-                if not use:
-                    continue
-                if not same_shape:
-                    h, w = dev[a].shape
-                    self._extract_async(make_grid_msg(dev[a], w, h, res, origins[a][0], origins[a][1]), T)
-                    if first:
-                        first = False
-                        self.map_resolution = float(res)
-                        self.map_origin = [float(origins[a][0]), float(origins[a][1])]
-                    else:
-                        self._voxel_downsample(lattice_cells=cells, sync=False)
-                    continue
-                if first:                        # adopted as is (:40-43): no filter on this callback
+            chain = None
+            order = used.tolist()
+            if first:                            # adopted as is (:40-43): no filter on this callback
+                a = order.pop(0)
+                if same_shape:
                     rc = self._lib.mapmerge_append_slice(stage.x.data_ptr(), stage.y.data_ptr(), offs.data_ptr(), a,
                                                          self._cloud.x.data_ptr(), self._cloud.y.data_ptr(), self._cloud.capacity,
                                                          self._cloud.count.data_ptr(), self._status.data_ptr(), None, self._stream())
                     _native.check(rc, 'mapmerge_append_slice')
-                    first = False
-                    self.map_resolution = float(res)
-                    self.map_origin = [float(origins[a][0]), float(origins[a][1])]
-                    continue
-                chain_order.append(a)
-            chain = self._run_chain(stage, offs, A, chain_order, lat_w, lat_h, slice_cap) if chain_order else None
+                else:
+                    self._extract_async(make_grid_msg(dev[a], dev[a].shape[1], dev[a].shape[0], res, org[a, 0], org[a, 1]), None)
+                self.map_resolution = float(res)
+                self.map_origin = [float(org[a, 0]), float(org[a, 1])]
+            if same_shape:
+                if order:
+                    chain = self._run_chain(stage, offs, A, order, lat_w, lat_h, int(n_occ[used].max()))
+            else:
+                for a in order:
+                    self._extract_async(make_grid_msg(dev[a], dev[a].shape[1], dev[a].shape[0], res, org[a, 0], org[a, 1]), Tm[a])
+                    self._voxel_downsample(lattice_cells=lat_w * lat_h, sync=False)
             self.chain_stats = chain
             self._n_global = int(self._cloud.count.item())          # host sync (with the status word)
             self._check_status()

@@ -63,8 +63,8 @@ def main():
     assert torch.cuda.is_available(), 'bench_merge.py needs a CUDA device (no CPU fallback)'
     dev = torch.device('cuda', 0)
     A, S, res = args.agents, args.size, 0.05
-    distinct = device_grids(torch, dev, min(A, 16), S)
-    grids = [distinct[a % len(distinct)] for a in range(A)]
+    distinct = device_grids(torch, dev, A, S)        # every agent its own map: A * S^2 bytes of input (1 GiB > L2)
+    grids = distinct
     rng = np.random.default_rng(0)
     origins = np.tile(np.array([[-S * res / 2, -S * res / 2]]), (A, 1))
     tf = [se2_matrix(*rng.uniform(-50, 50, 2), rng.uniform(-math.pi, math.pi)) for _ in range(A)]

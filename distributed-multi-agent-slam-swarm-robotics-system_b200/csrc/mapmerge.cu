@@ -22,7 +22,8 @@
 namespace occ {
 
 constexpr int kMT = 256;              // threads per CTA
-constexpr int kCellsPerThread = 16;   // one 16-byte load of int8 cells
+constexpr int kLoadCells = 16;        // one 16-byte load of int8 cells
+constexpr int kCellsPerThread = 64;   // four independent 16-byte loads in flight per thread
 constexpr int kChunk = kMT * kCellsPerThread;
 
 // Status word bits (device int32, sticky; checked by the host wrapper at its next sync).
@@ -60,6 +61,36 @@ __device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, uns
     return res;
 }
 
+// Same for 64-bit values (sums of per-agent point counts).  s_warp64 >= 33 entries.
+__device__ __forceinline__ unsigned long long block_exclusive_scan64(unsigned long long v, unsigned long long* s_warp64,
+                                                                     unsigned long long* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp64[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = (lane < (int)(blockDim.x >> 5)) ? s_warp64[lane] : 0ull;
+        unsigned long long winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        s_warp64[lane] = winc - w;
+        if (lane == 31) s_warp64[32] = winc;
+    }
+    __syncthreads();
+    const unsigned long long res = s_warp64[warp] + inc - v;
+    *total = s_warp64[32];
+    __syncthreads();
+    return res;
+}
+
 // ---- a10: occupied-cell extraction (data > 50, map_merger.py:72) --------------------------
 
 __device__ __forceinline__ unsigned int occupied_mask16(const int8_t* __restrict__ grid, long long base, long long n) {
@@ -79,11 +110,20 @@ __device__ __forceinline__ unsigned int occupied_mask16(const int8_t* __restrict
     return mask;
 }
 
+// 64 consecutive cells per thread: the four loads are independent, so a thread keeps 64 bytes in flight.
+__device__ __forceinline__ unsigned long long occupied_mask64(const int8_t* __restrict__ grid, long long base, long long n) {
+    unsigned int m[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) m[q] = occupied_mask16(grid, base + 16 * q, n);
+    return (unsigned long long)m[0] | ((unsigned long long)m[1] << 16) | ((unsigned long long)m[2] << 32) |
+           ((unsigned long long)m[3] << 48);
+}
+
 __global__ void __launch_bounds__(kMT)
 k_extract_count(const int8_t* __restrict__ grid, long long n_cells, unsigned int* __restrict__ block_counts) {
     __shared__ unsigned int s_warp[33];
     const long long base = ((long long)blockIdx.x * kMT + threadIdx.x) * kCellsPerThread;
-    unsigned int c = base < n_cells ? __popc(occupied_mask16(grid, base, n_cells)) : 0u;
+    unsigned int c = base < n_cells ? __popcll(occupied_mask64(grid, base, n_cells)) : 0u;
     unsigned int total;
     block_exclusive_scan(c, s_warp, &total);
     if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
@@ -93,8 +133,8 @@ k_extract_count(const int8_t* __restrict__ grid, long long n_cells, unsigned int
 __global__ void __launch_bounds__(kMT)
 k_count_occupied(const int8_t* __restrict__ grid, long long n_cells, long long* __restrict__ out) {
     unsigned int c = 0;
-    for (long long base = ((long long)blockIdx.x * kMT + threadIdx.x) * kCellsPerThread; base < n_cells;
-         base += (long long)gridDim.x * kMT * kCellsPerThread)
+    for (long long base = ((long long)blockIdx.x * kMT + threadIdx.x) * kLoadCells; base < n_cells;
+         base += (long long)gridDim.x * kMT * kLoadCells)
         c += __popc(occupied_mask16(grid, base, n_cells));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -140,13 +180,13 @@ k_extract_write(const int8_t* __restrict__ grid, long long n_cells, int width, d
     __shared__ unsigned int s_warp[33];
     if (ws_base[1] == 0) return;
     const long long base = ((long long)blockIdx.x * kMT + threadIdx.x) * kCellsPerThread;
-    const unsigned int mask = base < n_cells ? occupied_mask16(grid, base, n_cells) : 0u;
+    const unsigned long long mask = base < n_cells ? occupied_mask64(grid, base, n_cells) : 0ull;
     unsigned int total;
-    unsigned int off = block_exclusive_scan(__popc(mask), s_warp, &total);
+    unsigned int off = block_exclusive_scan(__popcll(mask), s_warp, &total);
     long long dst = ws_base[0] + block_offsets[blockIdx.x] + off;
-    unsigned int m = mask;
+    unsigned long long m = mask;
     while (m) {
-        const int i = __ffs(m) - 1;
+        const int i = __ffsll((long long)m) - 1;
         m &= m - 1;
         const long long c = base + i;
         const long long row = c / width, col = c - row * width;
@@ -217,7 +257,7 @@ k_batch_count(const int8_t* const* __restrict__ grids, long long n_cells, int bl
     const int a = blockIdx.y;
     const long long base = ((long long)blockIdx.x * kMT + threadIdx.x) * kCellsPerThread;
     unsigned int total;
-    block_exclusive_scan(base < n_cells ? __popc(occupied_mask16(grids[a], base, n_cells)) : 0u, s_warp, &total);
+    block_exclusive_scan(base < n_cells ? __popcll(occupied_mask64(grids[a], base, n_cells)) : 0u, s_warp, &total);
     if (threadIdx.x == 0) block_counts[(size_t)a * blocks_per_grid + blockIdx.x] = total;
 }
 
@@ -242,16 +282,28 @@ k_batch_scan(unsigned int* __restrict__ block_counts, int blocks_per_grid, long 
     if (threadIdx.x == 0) agent_total[blockIdx.x] = s_carry;
 }
 
-// agent_offset[a] = sum of totals of the agents before a that take part in the merge.
-__global__ void k_batch_offsets(const long long* __restrict__ agent_total, const BatchXform* __restrict__ T, int n_agents,
-                                long long capacity, long long* __restrict__ agent_offset, int* __restrict__ status) {
-    long long acc = 0;
-    for (int a = 0; a < n_agents; ++a) {
-        agent_offset[a] = acc;
-        if (T[a].use) acc += agent_total[a];
+// agent_offset[a] = sum of totals of the agents before a that take part in the merge (one CTA).
+__global__ void __launch_bounds__(1024)
+k_batch_offsets(const long long* __restrict__ agent_total, const BatchXform* __restrict__ T, int n_agents,
+                long long capacity, long long* __restrict__ agent_offset, int* __restrict__ status) {
+    __shared__ unsigned long long s_warp[33];
+    __shared__ long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int start = 0; start < n_agents; start += blockDim.x) {
+        const int a = start + threadIdx.x;
+        const unsigned long long v = (a < n_agents && T[a].use) ? (unsigned long long)agent_total[a] : 0ull;
+        unsigned long long total;
+        const unsigned long long ex = block_exclusive_scan64(v, s_warp, &total);
+        if (a < n_agents) agent_offset[a] = s_carry + (long long)ex;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += (long long)total;
+        __syncthreads();
     }
-    agent_offset[n_agents] = acc;
-    if (acc > capacity) atomicOr(status, ST_POINT_OVERFLOW);
+    if (threadIdx.x == 0) {
+        agent_offset[n_agents] = s_carry;
+        if (s_carry > capacity) atomicOr(status, ST_POINT_OVERFLOW);
+    }
 }
 
 __global__ void __launch_bounds__(kMT)
@@ -260,21 +312,29 @@ k_batch_write(const int8_t* const* __restrict__ grids, long long n_cells, int wi
               const unsigned int* __restrict__ block_offsets, const long long* __restrict__ agent_offset, long long capacity,
               double* __restrict__ px, double* __restrict__ py) {
     __shared__ unsigned int s_warp[33];
+    __shared__ unsigned short s_cell[kChunk];       // occupied cells of this chunk, in cell order
     const int a = blockIdx.y;
     const BatchXform t = T[a];
     if (!t.use || agent_offset[gridDim.y] > capacity) return;
-    const long long base = ((long long)blockIdx.x * kMT + threadIdx.x) * kCellsPerThread;
-    const unsigned int mask = base < n_cells ? occupied_mask16(grids[a], base, n_cells) : 0u;
+    const long long chunk_base = (long long)blockIdx.x * kChunk;
+    const long long base = chunk_base + (long long)threadIdx.x * kCellsPerThread;
+    const unsigned long long mask = base < n_cells ? occupied_mask64(grids[a], base, n_cells) : 0ull;
     unsigned int total;
-    const unsigned int off = block_exclusive_scan(__popc(mask), s_warp, &total);
-    long long dst = agent_offset[a] + block_offsets[(size_t)a * blocks_per_grid + blockIdx.x] + off;
-    const double ox = origins[2 * a], oy = origins[2 * a + 1];
-    unsigned int m = mask;
-    while (m) {
-        const int i = __ffs(m) - 1;
+    unsigned int off = block_exclusive_scan(__popcll(mask), s_warp, &total);
+    unsigned long long m = mask;
+    while (m) {                                      // compact first: walls put many cells in few threads
+        const int i = __ffsll((long long)m) - 1;
         m &= m - 1;
-        const long long c = base + i;
-        const long long row = c / width, col = c - row * width;
+        s_cell[off++] = (unsigned short)(threadIdx.x * kCellsPerThread + i);
+    }
+    __syncthreads();
+    const long long dst0 = agent_offset[a] + block_offsets[(size_t)a * blocks_per_grid + blockIdx.x];
+    const double ox = origins[2 * a], oy = origins[2 * a + 1];
+    for (unsigned int i = threadIdx.x; i < total; i += kMT) {      // then every thread converts its share, coalesced stores
+        const long long c = chunk_base + s_cell[i];
+        long long row, col;
+        if (n_cells <= 0x7fffffffll) { row = (int)c / width; col = (int)c - (int)row * width; }
+        else { row = c / width; col = c - row * width; }
         double x = OCC_DADD(OCC_DMUL((double)col, res), ox);       // :77
         double y = OCC_DADD(OCC_DMUL((double)row, res), oy);       // :76
         if (!t.identity) {
@@ -284,9 +344,8 @@ k_batch_write(const int8_t* const* __restrict__ grids, long long n_cells, int wi
             x = OCC_DDIV(tx, w);
             y = OCC_DDIV(ty, w);
         }
-        px[dst] = x;
-        py[dst] = y;
-        ++dst;
+        px[dst0 + i] = x;
+        py[dst0 + i] = y;
     }
 }
 
@@ -966,7 +1025,7 @@ int mapmerge_count_occupied(const int8_t* d_grid, int64_t n_cells, int64_t* d_ou
     if (n_cells == 0) return OCCGRID_OK;
     cudaStream_t st = (cudaStream_t)stream;
     ProfileScope ps(K_MERGE_EXTRACT, st, 1);
-    k_count_occupied<<<grid_for(n_cells / kCellsPerThread + 1), kMT, 0, st>>>(d_grid, n_cells, (long long*)d_out);
+    k_count_occupied<<<grid_for(n_cells / kLoadCells + 1), kMT, 0, st>>>(d_grid, n_cells, (long long*)d_out);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
 }
@@ -1065,7 +1124,7 @@ int mapmerge_extract_batch_write(const int8_t* const* d_grids, int n_agents, int
     const BatchXform* dT = reinterpret_cast<const BatchXform*>(d_xforms);
     ProfileScope ps(K_MERGE_EXTRACT, st, 2);
     dim3 grid((unsigned)bpg, (unsigned)n_agents);
-    k_batch_offsets<<<1, 1, 0, st>>>((const long long*)d_agent_total, dT, n_agents, capacity, (long long*)d_agent_offset, d_status);
+    k_batch_offsets<<<1, 1024, 0, st>>>((const long long*)d_agent_total, dT, n_agents, capacity, (long long*)d_agent_offset, d_status);
     k_batch_write<<<grid, kMT, 0, st>>>(d_grids, n_cells, width, res, d_origins, dT, bpg, block_counts, (const long long*)d_agent_offset,
                                         capacity, d_px, d_py);
     OCC_CUDA_TRY(cudaGetLastError());

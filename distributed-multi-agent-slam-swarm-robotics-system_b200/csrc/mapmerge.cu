@@ -678,7 +678,6 @@ struct ChainHeader {
     unsigned int ticket;
 };
 enum { CHAIN_RUN = 0, CHAIN_REBUILD = 1, CHAIN_OVERFLOW = 2, CHAIN_REBOUND = 3 };
-constexpr int kAppendThreads = 256;
 
 __device__ __forceinline__ bool voxel_key_of(double x, double y, double mbx, double mby, double voxel, long long W,
                                              long long H, unsigned int* key) {
@@ -739,160 +738,198 @@ k_chain_slice_bounds(const double* __restrict__ sx, const double* __restrict__ s
 }
 
 // LM[k] = {index + 1 of the cloud point in voxel k (0: none), top of this callback's stack}
-__global__ void __launch_bounds__(kMT)
-k_chain_link(ChainHeader* __restrict__ h, const int* __restrict__ order, int n_order, const long long* __restrict__ agent_offset,
-             const unsigned long long* __restrict__ slice_benc, const double* __restrict__ sx, const double* __restrict__ sy,
-             double voxel, long long W, long long H, uint2* __restrict__ LM, unsigned int* __restrict__ lkey,
-             unsigned int* __restrict__ next, int* __restrict__ status) {
-    if (h->stalled) return;
-    const int cur = h->cursor;
-    if (cur >= n_order) return;
-    const int agent = order[cur];
-    double mbx, mby;
-    const int need = chain_decide(h, slice_benc + 4 * agent, voxel, W, H, &mbx, &mby);
-    if (need != CHAIN_RUN) {                       // every block reaches the same verdict; one records it
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            h->stalled = need;
-            if (need == CHAIN_OVERFLOW) atomicOr(status, ST_LATTICE_OVERFLOW);
-        }
-        return;
+//
+// The three phases of a callback run inside ONE persistent kernel (cooperative launch, every CTA
+// resident) separated by grid-wide barriers, and the kernel loops over up to n_callbacks
+// callbacks: a phase is a few microseconds of latency-bound work on ~6e4 points, so kernel
+// boundaries would cost as much as the work.  Every CTA keeps its own copy of the cursor and the
+// cloud size (they evolve identically everywhere); CTA 0 publishes them for the host.
+struct ChainRun {
+    ChainHeader* h;
+    const int* order;
+    int n_order, n_callbacks;
+    const long long* agent_offset;
+    const unsigned long long* slice_benc;
+    const double* sx;
+    const double* sy;
+    double voxel;
+    long long W, H;
+    uint2* LM;
+    unsigned int *lkey, *next, *gkey, *flag, *blockcount;      // blockcount: two buffers of bc_stride entries
+    double *gx, *gy, *resx, *resy;
+    long long* d_count;
+    long long capacity;
+    int* status;
+    unsigned int* bar;                                         // {arrivals, exits}; both zero between launches
+    int bc_stride;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (*reinterpret_cast<volatile unsigned int*>(bar) < target) { }
+        __threadfence();
     }
-    const long long b = agent_offset[agent], n = agent_offset[agent + 1] - b;
+    __syncthreads();
+}
+
+__device__ __forceinline__ void chain_link(const ChainRun& p, long long b, long long n, double mbx, double mby) {
     for (long long j = (long long)blockIdx.x * kMT + threadIdx.x; j < n; j += (long long)gridDim.x * kMT) {
         unsigned int k = 0;
-        voxel_key_of(sx[b + j], sy[b + j], mbx, mby, voxel, W, H, &k);     // in range: the lattice covers cloud u slice
-        lkey[j] = k;
-        next[j] = atomicExch(&LM[k].y, (unsigned int)j + 1u);
+        voxel_key_of(p.sx[b + j], p.sy[b + j], mbx, mby, p.voxel, p.W, p.H, &k);    // in range: the lattice covers cloud u slice
+        p.lkey[j] = k;
+        p.next[j] = atomicExch(&p.LM[k].y, (unsigned int)j + 1u);
     }
 }
 
-__global__ void __launch_bounds__(kMT)
-k_chain_fold(ChainHeader* __restrict__ h, const int* __restrict__ order, int n_order, const long long* __restrict__ agent_offset,
-             const double* __restrict__ sx, const double* __restrict__ sy, double voxel, long long W, long long H,
-             uint2* __restrict__ LM, const unsigned int* __restrict__ lkey, const unsigned int* __restrict__ next,
-             double* __restrict__ gx, double* __restrict__ gy, double* __restrict__ resx, double* __restrict__ resy,
-             unsigned int* __restrict__ flag, unsigned int* __restrict__ blockcount) {
-    if (h->stalled) return;
-    const int cur = h->cursor;
-    if (cur >= n_order) return;
-    const int agent = order[cur];
-    const long long b = agent_offset[agent], n = agent_offset[agent + 1] - b;
-    const double mbx = h->mbx, mby = h->mby;
+__device__ __forceinline__ void chain_fold(const ChainRun& p, long long b, long long n, double mbx, double mby,
+                                           unsigned int* bc) {
+    ChainHeader* h = p.h;
     const double g0 = dec_double(h->gb_enc[0]), g1 = dec_double(h->gb_enc[1]);
     double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
     const int lane = threadIdx.x & 31;
     for (long long j0 = (long long)blockIdx.x * kMT + (threadIdx.x & ~31); j0 < n; j0 += (long long)gridDim.x * kMT) {
         const long long j = j0 + lane;
-        int parked = -1;                                       // append block a new voxel of this thread goes to
+        int parked = -1;                                       // append chunk a new voxel of this thread goes to
         unsigned int k = 0;
         uint2 e = make_uint2(0u, 0u);
-        if (j < n) { k = lkey[j]; e = LM[k]; }
+        if (j < n) { k = p.lkey[j]; e = p.LM[k]; }
         if (j < n && e.y == (unsigned int)j + 1u) {            // top of its voxel's stack: this thread folds it
             unsigned int cnt = 0, head = (unsigned int)j;
-            for (unsigned int q = e.y; q; q = next[q - 1]) { ++cnt; head = min(head, q - 1u); }
+            for (unsigned int q = e.y; q; q = p.next[q - 1]) { ++cnt; head = min(head, q - 1u); }
             double ax, ay;
             long long last;
             unsigned int remaining, total;
-            if (e.x) { ax = gx[e.x - 1]; ay = gy[e.x - 1]; last = -1; remaining = cnt; total = cnt + 1u; }
-            else     { ax = sx[b + head]; ay = sy[b + head]; last = head; remaining = cnt - 1u; total = cnt; }
+            if (e.x) { ax = p.gx[e.x - 1]; ay = p.gy[e.x - 1]; last = -1; remaining = cnt; total = cnt + 1u; }
+            else     { ax = p.sx[b + head]; ay = p.sy[b + head]; last = head; remaining = cnt - 1u; total = cnt; }
             for (unsigned int r = 0; r < remaining; ++r) {     // ascending slice index; stacks are tiny
                 unsigned int best = 0xffffffffu;
-                for (unsigned int q = e.y; q; q = next[q - 1]) {
+                for (unsigned int q = e.y; q; q = p.next[q - 1]) {
                     const unsigned int idx = q - 1u;
                     if ((long long)idx > last && idx < best) best = idx;
                 }
                 last = best;
-                ax = OCC_DADD(ax, sx[b + best]);
-                ay = OCC_DADD(ay, sy[b + best]);
+                ax = OCC_DADD(ax, p.sx[b + best]);
+                ay = OCC_DADD(ay, p.sy[b + best]);
             }
             const double c = (double)total;
             const double x = OCC_DDIV(ax, c), y = OCC_DDIV(ay, c);
             if (e.x) {
                 const unsigned int g = e.x - 1u;
-                const double oldx = gx[g], oldy = gy[g];
+                const double oldx = p.gx[g], oldy = p.gy[g];
                 // a point on the min corner moving inwards: the bounds need a full pass before the next decision
                 if ((oldx <= g0 && x > oldx) || (oldy <= g1 && y > oldy)) h->bounds_dirty = 1;
-                gx[g] = x; gy[g] = y;
+                p.gx[g] = x; p.gy[g] = y;
                 unsigned int k2 = 0;
-                if (!voxel_key_of(x, y, mbx, mby, voxel, W, H, &k2) || k2 != k) h->force_rebuild = 1;   // LM no longer describes the cloud
+                if (!voxel_key_of(x, y, mbx, mby, p.voxel, p.W, p.H, &k2) || k2 != k) h->force_rebuild = 1;   // LM no longer describes the cloud
                 mnx = fmin(mnx, x); mxx = fmax(mxx, x); mny = fmin(mny, y); mxy = fmax(mxy, y);
             } else {
-                resx[head] = x; resy[head] = y;
-                flag[head] = 1u;
-                parked = (int)(head / kAppendThreads);
+                p.resx[head] = x; p.resy[head] = y;
+                p.flag[head] = 1u;
+                parked = (int)(head / kMT);
             }
-            LM[k].y = 0u;
+            p.LM[k].y = 0u;
         }
         __syncwarp();
-        const unsigned int peers = __match_any_sync(0xffffffffu, parked);      // one atomic per distinct block per warp
-        if (parked >= 0 && lane == __ffs(peers) - 1) atomicAdd(&blockcount[parked], (unsigned int)__popc(peers));
+        const unsigned int peers = __match_any_sync(0xffffffffu, parked);      // one atomic per distinct chunk per warp
+        if (parked >= 0 && lane == __ffs(peers) - 1) atomicAdd(&bc[parked], (unsigned int)__popc(peers));
     }
     block_bounds_atomic(mnx, mny, mxx, mxy, h->gb_enc);
 }
 
-__global__ void __launch_bounds__(kAppendThreads)
-k_chain_append(ChainHeader* __restrict__ h, const int* __restrict__ order, int n_order, const long long* __restrict__ agent_offset,
-               double voxel, long long W, long long H, uint2* __restrict__ LM, double* __restrict__ gx, double* __restrict__ gy,
-               unsigned int* __restrict__ gkey, const double* __restrict__ resx, const double* __restrict__ resy,
-               unsigned int* __restrict__ flag, unsigned int* __restrict__ blockcount, long long* __restrict__ d_count,
-               long long capacity, int* __restrict__ status) {
-    __shared__ unsigned int s_warp[33];
-    __shared__ unsigned int s_off;
-    if (h->stalled) return;
-    const int cur = h->cursor;
-    if (cur >= n_order) return;
-    const int agent = order[cur];
-    const long long n = agent_offset[agent + 1] - agent_offset[agent];
-    const long long n_g = *d_count;                 // rewritten only by the block that takes the last ticket
-    const double mbx = h->mbx, mby = h->mby;
-    unsigned int part = 0;
-    for (unsigned int bb = threadIdx.x; bb < blockIdx.x; bb += kAppendThreads) part += blockcount[bb];
-    unsigned int before;
-    block_exclusive_scan(part, s_warp, &before);    // total of the blocks in front of this one
-    if (threadIdx.x == 0) s_off = before;
-    __syncthreads();
-    const long long j = (long long)blockIdx.x * kAppendThreads + threadIdx.x;
-    const unsigned int f = (j < n) ? flag[j] : 0u;
-    unsigned int mine;
-    const unsigned int pos = block_exclusive_scan(f, s_warp, &mine);
+// Ordered compaction of the parked means onto the end of the cloud; returns how many were appended.
+__device__ __forceinline__ unsigned int chain_append(const ChainRun& p, long long n, long long n_g, double mbx, double mby,
+                                                     const unsigned int* bc, unsigned int* s_warp) {
+    ChainHeader* h = p.h;
+    const unsigned int nb = (unsigned int)((n + kMT - 1) / kMT);
     double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
-    if (f) {
-        flag[j] = 0u;
-        const long long idx = n_g + s_off + pos;
-        if (idx >= capacity) {
-            atomicOr(status, ST_POINT_OVERFLOW);
-        } else {
-            const double x = resx[j], y = resy[j];
-            gx[idx] = x; gy[idx] = y;
-            unsigned int k = 0;
-            if (!voxel_key_of(x, y, mbx, mby, voxel, W, H, &k)) { gkey[idx] = 0xffffffffu; h->force_rebuild = 1; }
-            else {
-                gkey[idx] = k;
-                if (atomicExch(&LM[k].x, (unsigned int)idx + 1u) != 0u) h->force_rebuild = 1;   // mean drifted into an occupied voxel
+    unsigned int all = 0;
+    for (unsigned int c0 = 0; c0 < nb; c0 += gridDim.x) {          // uniform trip count: block scans inside
+        const unsigned int chunk = c0 + blockIdx.x;
+        // chunks in front of this one, and (first round only) every chunk: the appended total
+        unsigned int part = 0, whole = 0;
+        for (unsigned int q = threadIdx.x; q < nb; q += kMT) {
+            const unsigned int v = bc[q];
+            if (q < chunk) part += v;
+            whole += v;
+        }
+        unsigned int before;
+        block_exclusive_scan(part, s_warp, &before);
+        if (c0 == 0) block_exclusive_scan(whole, s_warp, &all);
+        const long long j = (long long)chunk * kMT + threadIdx.x;
+        const unsigned int f = (chunk < nb && j < n) ? p.flag[j] : 0u;
+        unsigned int mine;
+        const unsigned int pos = block_exclusive_scan(f, s_warp, &mine);
+        if (f) {
+            p.flag[j] = 0u;
+            const long long idx = n_g + before + pos;
+            if (idx >= p.capacity) {
+                atomicOr(p.status, ST_POINT_OVERFLOW);
+            } else {
+                const double x = p.resx[j], y = p.resy[j];
+                p.gx[idx] = x; p.gy[idx] = y;
+                unsigned int k = 0;
+                if (!voxel_key_of(x, y, mbx, mby, p.voxel, p.W, p.H, &k)) { p.gkey[idx] = 0xffffffffu; h->force_rebuild = 1; }
+                else {
+                    p.gkey[idx] = k;
+                    if (atomicExch(&p.LM[k].x, (unsigned int)idx + 1u) != 0u) h->force_rebuild = 1;   // mean drifted into an occupied voxel
+                }
+                mnx = fmin(mnx, x); mxx = fmax(mxx, x); mny = fmin(mny, y); mxy = fmax(mxy, y);
             }
-            mnx = x; mxx = x; mny = y; mxy = y;
         }
     }
     block_bounds_atomic(mnx, mny, mxx, mxy, h->gb_enc);
-    __shared__ int s_last;
+    return all;
+}
+
+__global__ void __launch_bounds__(kMT)
+k_chain_persistent(const ChainRun p) {
+    __shared__ unsigned int s_warp[33];
+    ChainHeader* h = p.h;
+    unsigned int target = 0;
+    int done = 0;
+    if (!h->stalled) {
+        int cur = h->cursor;
+        long long n_g = *p.d_count;
+        for (int it = 0; it < p.n_callbacks && cur < p.n_order; ++it) {
+            const int agent = p.order[cur];
+            double mbx, mby;
+            const int need = chain_decide(h, p.slice_benc + 4 * agent, p.voxel, p.W, p.H, &mbx, &mby);
+            if (need != CHAIN_RUN) {                   // every CTA reaches the same verdict; CTA 0 records it
+                if (blockIdx.x == 0 && threadIdx.x == 0) {
+                    h->stalled = need;
+                    if (need == CHAIN_OVERFLOW) atomicOr(p.status, ST_LATTICE_OVERFLOW);
+                }
+                break;
+            }
+            const long long b = p.agent_offset[agent], n = p.agent_offset[agent + 1] - b;
+            unsigned int* bc = p.blockcount + (size_t)(it & 1) * p.bc_stride;
+            unsigned int* bc_other = p.blockcount + (size_t)((it & 1) ^ 1) * p.bc_stride;
+            if (blockIdx.x == 0)                       // the previous callback's counters: nobody reads them any more
+                for (int q = threadIdx.x; q < p.bc_stride; q += kMT) bc_other[q] = 0u;
+            chain_link(p, b, n, mbx, mby);
+            grid_barrier(p.bar, target);
+            chain_fold(p, b, n, mbx, mby, bc);
+            grid_barrier(p.bar, target);
+            const unsigned int added = chain_append(p, n, n_g, mbx, mby, bc, s_warp);
+            n_g += added;
+            if (n_g > p.capacity) n_g = p.capacity;
+            cur += 1;
+            done = it + 1;
+            if (blockIdx.x == 0 && threadIdx.x == 0) { *p.d_count = n_g; h->cursor = cur; }
+            grid_barrier(p.bar, target);               // bounds / flags of this callback feed the next decision
+        }
+    }
+    // leave the counters and the barrier clean for the next launch
+    if (blockIdx.x == 0 && done)
+        for (int q = threadIdx.x; q < p.bc_stride; q += kMT) p.blockcount[(size_t)((done - 1) & 1) * p.bc_stride + q] = 0u;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        s_last = (atomicAdd(&h->ticket, 1u) == gridDim.x - 1);     // every block has read n_g and its counts
-    }
-    __syncthreads();
-    if (s_last) {
-        const unsigned int nb = (unsigned int)((n + kAppendThreads - 1) / kAppendThreads);
-        unsigned int mine_total = 0;
-        for (unsigned int bb = threadIdx.x; bb < nb; bb += kAppendThreads) { mine_total += blockcount[bb]; blockcount[bb] = 0u; }
-        unsigned int total;
-        block_exclusive_scan(mine_total, s_warp, &total);
-        if (threadIdx.x == 0) {
-            long long nn = n_g + total;
-            *d_count = nn > capacity ? capacity : nn;
-            h->ticket = 0u;
-            h->cursor = cur + 1;
-        }
+        if (atomicAdd(p.bar + 1, 1u) == gridDim.x - 1) { p.bar[0] = 0u; p.bar[1] = 0u; }
     }
 }
 
@@ -1256,8 +1293,9 @@ int mapmerge_voxel_downsample(const double* d_px, const double* d_py, const int6
 struct ChainArrays {
     ChainHeader* h;
     uint2* LM;
-    unsigned int *gkey, *lkey, *next, *flag, *blockcount;
+    unsigned int *gkey, *lkey, *next, *flag, *blockcount, *bar;
     double *resx, *resy;
+    int bc_stride;
     unsigned long long* slice_benc;
     int* order;
 };
@@ -1268,7 +1306,8 @@ static size_t chain_layout(const int64_t* dims, int n_agents, ChainArrays* a, vo
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return at; };
     const size_t o_h = take(sizeof(ChainHeader)), o_lm = take((cells + 1) * 8), o_gk = take(points * 4);
-    const size_t o_lk = take(sl * 4), o_nx = take(sl * 4), o_fl = take(sl * 4), o_bc = take((sl / kAppendThreads + 2) * 4);
+    const size_t bc_stride = sl / kMT + 2;
+    const size_t o_lk = take(sl * 4), o_nx = take(sl * 4), o_fl = take(sl * 4), o_bc = take(2 * bc_stride * 4), o_bar = take(8);
     const size_t o_rx = take(sl * 8), o_ry = take(sl * 8), o_sb = take((size_t)n_agents * 32), o_or = take((size_t)n_agents * 4);
     if (a) {
         a->h = reinterpret_cast<ChainHeader*>(ws + o_h);
@@ -1278,6 +1317,8 @@ static size_t chain_layout(const int64_t* dims, int n_agents, ChainArrays* a, vo
         a->next = reinterpret_cast<unsigned int*>(ws + o_nx);
         a->flag = reinterpret_cast<unsigned int*>(ws + o_fl);
         a->blockcount = reinterpret_cast<unsigned int*>(ws + o_bc);
+        a->bar = reinterpret_cast<unsigned int*>(ws + o_bar);
+        a->bc_stride = (int)bc_stride;
         a->resx = reinterpret_cast<double*>(ws + o_rx);
         a->resy = reinterpret_cast<double*>(ws + o_ry);
         a->slice_benc = reinterpret_cast<unsigned long long*>(ws + o_sb);
@@ -1334,23 +1375,31 @@ int mapmerge_chain_run(void* d_chain, const int64_t* dims, int n_agents, int n_o
         set_last_error("mapmerge_chain_run: bad arguments");
         return OCCGRID_E_ARG;
     }
+    if (n_callbacks == 0) return OCCGRID_OK;
     ChainArrays c;
     chain_layout(dims, n_agents, &c, d_chain);
     cudaStream_t st = (cudaStream_t)stream;
-    const int gsl = grid_for(dims[3]);
-    const int gap = (int)((dims[3] + kAppendThreads - 1) / kAppendThreads);
-    const long long* offs = (const long long*)d_agent_offset;
-    ProfileScope ps(K_CHAIN_INCR, st, 3 * n_callbacks);
-    for (int i = 0; i < n_callbacks; ++i) {
-        k_chain_link<<<gsl, kMT, 0, st>>>(c.h, c.order, n_order, offs, c.slice_benc, d_sx, d_sy, voxel, dims[0], dims[1], c.LM,
-                                          c.lkey, c.next, d_status);
-        k_chain_fold<<<gsl, kMT, 0, st>>>(c.h, c.order, n_order, offs, d_sx, d_sy, voxel, dims[0], dims[1], c.LM, c.lkey, c.next,
-                                          d_px, d_py, c.resx, c.resy, c.flag, c.blockcount);
-        k_chain_append<<<gap, kAppendThreads, 0, st>>>(c.h, c.order, n_order, offs, voxel, dims[0], dims[1], c.LM, d_px, d_py,
-                                                       c.gkey, c.resx, c.resy, c.flag, c.blockcount, (long long*)d_count, capacity,
-                                                       d_status);
+    static int resident_ctas = 0;                  // CTAs of the persistent kernel the device can hold at once
+    if (resident_ctas == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        OCC_CUDA_TRY(cudaGetDevice(&dev));
+        OCC_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        OCC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_persistent, kMT, 0));
+        if (sms <= 0 || per_sm <= 0) { set_last_error("mapmerge_chain_run: persistent kernel does not fit the device"); return OCCGRID_E_CUDA; }
+        resident_ctas = sms * per_sm;
     }
-    OCC_CUDA_TRY(cudaGetLastError());
+    int grid = grid_for(dims[3]);
+    if (grid > resident_ctas) grid = resident_ctas;
+    ChainRun r;
+    r.h = c.h; r.order = c.order; r.n_order = n_order; r.n_callbacks = n_callbacks;
+    r.agent_offset = (const long long*)d_agent_offset; r.slice_benc = c.slice_benc;
+    r.sx = d_sx; r.sy = d_sy; r.voxel = voxel; r.W = dims[0]; r.H = dims[1];
+    r.LM = c.LM; r.lkey = c.lkey; r.next = c.next; r.gkey = c.gkey; r.flag = c.flag; r.blockcount = c.blockcount;
+    r.gx = d_px; r.gy = d_py; r.resx = c.resx; r.resy = c.resy;
+    r.d_count = (long long*)d_count; r.capacity = capacity; r.status = d_status; r.bar = c.bar; r.bc_stride = c.bc_stride;
+    void* args[] = {&r};
+    ProfileScope ps(K_CHAIN_INCR, st, 1);
+    OCC_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_chain_persistent, dim3((unsigned)grid), dim3(kMT), args, 0, st));
     return OCCGRID_OK;
 }
 

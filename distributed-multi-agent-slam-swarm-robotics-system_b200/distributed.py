@@ -398,24 +398,45 @@ class ShardedMapMerger:
             dist.all_gather(allbuf, buf, group=self.group)
         else:
             allbuf = [buf]
+        # every rank now holds every slice: stage them in agent order and replay the ordered voxel
+        # chain (:59-60) with the incremental chain kernels, identically on every rank
+        from .map_merger import _Cloud
+        from . import _native
         m = self.merger
-        first_origin = None
-        for a in range(n_agents_total):
-            k = lens_h[a]
-            if k == 0:
-                continue
-            p = allbuf[a % self.world][a // self.world, :k]
-            first = m._n_global == 0
-            m._ensure_capacity(m._n_global + k + 1)
-            n0 = m._n_global
-            m._cloud.x[n0:n0 + k].copy_(p[:, 0])
-            m._cloud.y[n0:n0 + k].copy_(p[:, 1])
-            m._cloud.count.fill_(n0 + k)
-            m._n_global = n0 + k
-            if first:
-                m.map_resolution = float(res)
-            else:
-                m._voxel_downsample()
+        order = [a for a in range(n_agents_total) if lens_h[a] > 0]
+        total = sum(lens_h)
+        if total:
+            with torch.cuda.device(dev):
+                stage = _Cloud(total + 16, dev)
+                offs_h = np.zeros(n_agents_total + 1, np.int64)
+                offs_h[1:] = np.cumsum(lens_h)
+                for a in order:
+                    p = allbuf[a % self.world][a // self.world, :lens_h[a]]
+                    stage.x[offs_h[a]:offs_h[a + 1]].copy_(p[:, 0])
+                    stage.y[offs_h[a]:offs_h[a + 1]].copy_(p[:, 1])
+                offs = torch.from_numpy(offs_h).to(dev)
+                lo = torch.stack([stage.x[:total].min(), stage.y[:total].min()])
+                hi = torch.stack([stage.x[:total].max(), stage.y[:total].max()])
+                if m._n_global:
+                    n = m._n_global
+                    lo = torch.minimum(lo, torch.stack([m._cloud.x[:n].min(), m._cloud.y[:n].min()]))
+                    hi = torch.maximum(hi, torch.stack([m._cloud.x[:n].max(), m._cloud.y[:n].max()]))
+                bb = torch.cat([lo, hi]).cpu().tolist()
+                m._ensure_capacity(m._n_global + total + 1024)
+                if m._n_global == 0:                    # adopted as is (:40-43)
+                    a0 = order.pop(0)
+                    rc = m._lib.mapmerge_append_slice(stage.x.data_ptr(), stage.y.data_ptr(), offs.data_ptr(), a0,
+                                                      m._cloud.x.data_ptr(), m._cloud.y.data_ptr(), m._cloud.capacity,
+                                                      m._cloud.count.data_ptr(), m._status.data_ptr(), None, m._stream())
+                    _native.check(rc, 'mapmerge_append_slice')
+                    m.map_resolution = float(res)
+                v = m.map_resolution
+                if order:
+                    # means stay inside the hull of the points, so these bounds cover every cloud of the chain
+                    lat_w, lat_h = int((bb[2] - bb[0]) / v) + 4, int((bb[3] - bb[1]) / v) + 4
+                    m.chain_stats = m._run_chain(stage, offs, n_agents_total, order, lat_w, lat_h, max(lens_h))
+                m._n_global = int(m._cloud.count.item())
+                m._check_status()
         out = m.publish_global_map()
         return (out.data, (out.info.origin.position.x, out.info.origin.position.y)) if out is not None else (None, None)
 

@@ -156,6 +156,57 @@ def test_chain_continues_an_existing_cloud(MM):
     assert np.array_equal(pc[:, 0], o.gx) and np.array_equal(pc[:, 1], o.gy)
 
 
+def test_chain_deep_voxel_stacks(MM):
+    """Transforms that shrink the slices (scale 0.3) put ~10 slice points into one voxel: the
+    per-voxel stacks of the incremental chain get deep, sums still run in ascending index."""
+    from oracle import merge_oracle as MO
+    r = np.random.default_rng(77)
+    A, n = 10, 128
+    grids = np.stack([synth_agent_grid(n, 300 + a, occ_segments=40) for a in range(A)])
+    origins = np.tile(np.array([[-3.2, -3.2]]), (A, 1))
+    tf = []
+    for a in range(A):
+        T = MO.se2_matrix(*r.uniform(-0.5, 0.5, 2), r.uniform(-math.pi, math.pi))
+        T[:2, :2] *= 0.3
+        tf.append(T)
+    tf = np.stack(tf)
+    o, want = _oracle_chain(grids, n, 0.05, (-3.2, -3.2), tf)
+    m = MM.MapMerger()
+    out, origin = m.merge(grids, origins, 0.05, tf)
+    assert np.array_equal(out, want[0]) and origin == want[1]
+    pc = m.global_pcd
+    assert pc.shape[0] == o.gx.shape[0]
+    assert np.array_equal(pc[:, 0], o.gx) and np.array_equal(pc[:, 1], o.gy)
+
+
+def test_chain_with_rejected_and_empty_agents(MM):
+    """fitness < 0.6 (:54-56) and empty grids (:37-38) are skipped inside a batched merge."""
+    from oracle import merge_oracle as MO
+    r = np.random.default_rng(5)
+    A, n = 9, 96
+    grids = [synth_agent_grid(n, 500 + a) for a in range(A)]
+    grids[0] = np.full((n, n), -1, np.int8)          # empty first grid: the next one is adopted
+    grids[4] = np.full((n, n), -1, np.int8)
+    grids = np.stack(grids)
+    origins = np.tile(np.array([[-2.4, -2.4]]), (A, 1))
+    tf = np.stack([MO.se2_matrix(*r.uniform(-1, 1, 2), r.uniform(-math.pi, math.pi)) for _ in range(A)])
+    fit = np.ones(A)
+    fit[1] = 0.1                                      # adopted anyway: the first cloud is never registered
+    fit[3] = 0.59
+    fit[7] = 0.2
+    o = MO.OracleMerger()
+    want = None
+    for a in range(A):
+        out = o.map_callback(grids[a].ravel(), n, n, 0.05, -2.4, -2.4, tf[a], accept=fit[a] >= 0.6)
+        want = out if out is not None else want
+    m = MM.MapMerger()
+    out, origin = m.merge(grids, origins, 0.05, tf, fitness=fit)
+    assert np.array_equal(out, want[0]) and origin == want[1]
+    pc = m.global_pcd
+    assert np.array_equal(pc[:, 0], o.gx) and np.array_equal(pc[:, 1], o.gy)
+    assert m.chain_stats['callbacks'] == 4            # agents 2, 5, 6, 8
+
+
 def test_2048_grids(MM):
     """BASELINE config 3 grid size (2048^2, ~1.5 % occupied) on a few agents, 50 m translations."""
     run_pair(MM, 2048, 4, seed=7, span=50.0, origin=(-51.2, -51.2), check_every=False)

@@ -13,7 +13,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_PATH = os.path.join(PKG_DIR, 'liboccgrid_b200.so')
-SOURCES = ['occgrid_integrate.cu', 'occgrid_tiled.cu', 'occgrid_route.cu', 'mapmerge.cu', 'frontier.cu']
+SOURCES = ['occgrid_integrate.cu', 'occgrid_tiled.cu', 'occgrid_route.cu', 'mapmerge.cu', 'frontier.cu', 'icp.cu']
 HEADERS = ['common.cuh', 'beam_expand.cuh', 'sincos_dd.cuh', os.path.join('..', '..', 'include', 'occgrid_b200.h')]
 
 STRATEGY = {'auto': -1, 'global_atomic': 0, 'tiled': 1}
@@ -149,6 +149,10 @@ def _bind_merge(L):
     L.mapmerge_chain_rebounds.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.mapmerge_chain_rebuild.restype = C.c_int
     L.mapmerge_chain_rebuild.argtypes = [vp, vp, i32, vp, vp, vp, i32, dbl, vp, vp, i64, vp, vp, vp, vp, vp, vp, sz, i64, vp]
+    L.mapmerge_icp_workspace_bytes.restype = sz
+    L.mapmerge_icp_workspace_bytes.argtypes = [i64, i64, i32, i32]
+    L.mapmerge_icp_register.restype = C.c_int
+    L.mapmerge_icp_register.argtypes = [vp, vp, i64, vp, vp, i64, dbl, dbl, dbl, i32, i32, dbl, i32, dbl, dbl, vp, vp, sz, vp]
     L.mapmerge_rasterise.restype = C.c_int
     L.mapmerge_rasterise.argtypes = [vp, vp, vp, dbl, vp, i32, i32, vp, vp]
     L.mapmerge_fuse_max.restype = C.c_int
@@ -158,7 +162,7 @@ def _bind_merge(L):
 KERNEL_NAMES = ('integrate_global', 'resolve', 'update_rays', 'tile_count', 'tile_scan', 'tile_scatter',
                 'tile_raycast', 'tile_resolve', 'merge_extract', 'merge_bounds', 'merge_voxel', 'merge_raster',
                 'merge_fuse', 'probe', 'route', 'frontier', 'frontier_cluster', 'chain_probe', 'chain_incremental',
-                'chain_rebuild')
+                'chain_rebuild', 'icp')
 
 
 def profile_begin():

@@ -1,0 +1,361 @@
+// Point-to-point ICP of a local cloud against the global cloud.
+//
+// Reference call site: server_nodes/map_merger.py:45-56
+//     reg_p2p = o3d.pipelines.registration.registration_icp(local_pcd, self.global_pcd, 1.0, I,
+//                   TransformationEstimationPointToPoint(), ICPConvergenceCriteria(max_iteration=30))
+//     if reg_p2p.fitness < 0.6: reject
+// Open3D is a third-party dependency that is absent and un-pinned here (parity unpinned); this
+// follows its published algorithm (Registration.cpp / TransformationEstimation.cpp, Eigen
+// Umeyama.h), restated on the CPU in oracle/icp_oracle.py:
+//   * correspondences: the nearest target point of every source point, kept when its squared
+//     distance is < max_dist^2; fitness = #corr / #source; inlier_rmse = sqrt(sum d^2 / #corr);
+//   * update = rigid Umeyama fit of the corresponding pairs, T = update * T, source transformed
+//     by update; repeated max_iteration times or until |d fitness| and |d rmse| < 1e-6.
+// All clouds on this path are planar (z == 0), where the Umeyama rotation is the closed form
+// theta = atan2(sum cross, sum dot) of the demeaned pairs.
+//
+// Device design: the target is binned into a uniform cell list (cell = max_dist / 4: counting
+// sort, points of a cell contiguous); a source point searches rings of cells outwards and stops
+// as soon as the best distance is within the scanned square (exact nearest neighbour, ties by
+// lowest target index).  Sums are reduced in a fixed order (per-CTA partials, then one CTA), so a
+// registration is reproducible bit for bit.  The whole iteration loop is enqueued without host
+// round trips: a `done` flag on the device turns the remaining launches into no-ops.
+#include "common.cuh"
+#include "sincos_dd.cuh"
+
+namespace occ {
+
+constexpr int kIT = 256;
+
+struct IcpIndex {                 // cell list over the target cloud
+    double min_x, min_y, cell;
+    int w, h;
+    const unsigned int* start;    // [w*h + 1]
+    const double* x;              // target points sorted by cell
+    const double* y;
+    const unsigned int* idx;      // their indices in the caller's cloud
+};
+
+struct IcpState {                 // device-resident; the first 20 doubles are the public result
+    double T[16];
+    double fitness, rmse, iterations, n_corr;
+    double U[16];
+    double mean[4];               // source x, y; target x, y over the current correspondences
+    int done;
+};
+
+__device__ __forceinline__ int icp_cell_of(double v, double lo, double cell, int n) {
+    const double f = floor(OCC_DDIV(OCC_DADD(v, -lo), cell));
+    return f < 0.0 ? 0 : (f > (double)(n - 1) ? n - 1 : (int)f);
+}
+
+__global__ void __launch_bounds__(kIT)
+k_icp_count(const double* __restrict__ tx, const double* __restrict__ ty, long long n, double min_x, double min_y, double cell,
+            int w, int h, unsigned int* __restrict__ cnt) {
+    for (long long i = (long long)blockIdx.x * kIT + threadIdx.x; i < n; i += (long long)gridDim.x * kIT)
+        atomicAdd(&cnt[(size_t)icp_cell_of(ty[i], min_y, cell, h) * w + icp_cell_of(tx[i], min_x, cell, w)], 1u);
+}
+
+// One CTA: start[c] = exclusive sum of cnt; cursor[c] = start[c] (consumed by the fill pass).
+__global__ void __launch_bounds__(1024)
+k_icp_scan(const unsigned int* __restrict__ cnt, long long cells, unsigned int* __restrict__ start, unsigned int* __restrict__ cursor) {
+    constexpr int kItems = 16;
+    __shared__ unsigned int s_warp[32];
+    __shared__ unsigned int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long base = 0; base < cells; base += 1024 * kItems) {
+        const long long i0 = base + (long long)threadIdx.x * kItems;
+        unsigned int v[kItems], sum = 0;
+#pragma unroll
+        for (int j = 0; j < kItems; ++j) { v[j] = (i0 + j < cells) ? cnt[i0 + j] : 0u; sum += v[j]; }
+        unsigned int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned int wv = s_warp[lane], winc = wv;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+            s_warp[lane] = winc - wv;
+        }
+        __syncthreads();
+        unsigned int run = s_carry + s_warp[warp] + inc - sum;
+#pragma unroll
+        for (int j = 0; j < kItems; ++j) {
+            if (i0 + j < cells) { start[i0 + j] = run; cursor[i0 + j] = run; }
+            run += v[j];
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = run;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) start[cells] = s_carry;
+}
+
+__global__ void __launch_bounds__(kIT)
+k_icp_fill(const double* __restrict__ tx, const double* __restrict__ ty, long long n, double min_x, double min_y, double cell,
+           int w, int h, unsigned int* __restrict__ cursor, double* __restrict__ sx, double* __restrict__ sy,
+           unsigned int* __restrict__ sidx) {
+    for (long long i = (long long)blockIdx.x * kIT + threadIdx.x; i < n; i += (long long)gridDim.x * kIT) {
+        const double x = tx[i], y = ty[i];
+        const unsigned int p = atomicAdd(&cursor[(size_t)icp_cell_of(y, min_y, cell, h) * w + icp_cell_of(x, min_x, cell, w)], 1u);
+        sx[p] = x; sy[p] = y; sidx[p] = (unsigned int)i;
+    }
+}
+
+__global__ void k_icp_init(IcpState* __restrict__ s) {
+    for (int i = 0; i < 16; ++i) { s->T[i] = (i % 5 == 0) ? 1.0 : 0.0; s->U[i] = s->T[i]; }
+    s->fitness = s->rmse = s->iterations = s->n_corr = 0.0;
+    s->mean[0] = s->mean[1] = s->mean[2] = s->mean[3] = 0.0;
+    s->done = 0;
+}
+
+// Fixed-order block sum of N doubles per thread into out[N] (thread 0 writes).
+template <int N>
+__device__ __forceinline__ void block_sum(double (&v)[N], double* out) {
+    __shared__ double s_part[N][kIT / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[j] = OCC_DADD(v[j], __shfl_down_sync(0xffffffffu, v[j], o));
+        if (lane == 0) s_part[j][warp] = v[j];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double a = s_part[j][0];
+            for (int w = 1; w < kIT / 32; ++w) a = OCC_DADD(a, s_part[j][w]);
+            out[j] = a;
+        }
+    }
+    __syncthreads();
+}
+
+// Exact nearest neighbour of (px, py) in the cell list, squared distance < r2, ties -> lowest
+// target index.  Returns the sorted position or 0xffffffff.
+__device__ __forceinline__ unsigned int icp_nearest(const IcpIndex& ix, double px, double py, double r, double r2, double* d2_out) {
+    const double qx = floor(OCC_DDIV(OCC_DADD(px, -ix.min_x), ix.cell)), qy = floor(OCC_DDIV(OCC_DADD(py, -ix.min_y), ix.cell));
+    // distance from the query to the edge of its own (unclamped) cell, shaved for rounding
+    const double fx = px - (ix.min_x + qx * ix.cell), fy = py - (ix.min_y + qy * ix.cell);
+    double inner = fmin(fmin(fx, ix.cell - fx), fmin(fy, ix.cell - fy));
+    inner = fmax(inner - 1e-9 * ix.cell, 0.0);
+    const long long cqx = (long long)fmax(fmin(qx, 4.0e9), -4.0e9), cqy = (long long)fmax(fmin(qy, 4.0e9), -4.0e9);
+    const int rmax = (int)ceil(r / ix.cell) + 1;
+    double best = INFINITY;
+    unsigned int best_pos = 0xffffffffu, best_idx = 0xffffffffu;
+    for (int R = 0; R <= rmax; ++R) {
+        const long long y_lo = cqy - R, y_hi = cqy + R, x_lo = cqx - R, x_hi = cqx + R;
+        for (long long cy = y_lo; cy <= y_hi; ++cy) {
+            if (cy < 0 || cy >= ix.h) continue;
+            const bool edge_row = (cy == y_lo || cy == y_hi);
+            const long long step = edge_row ? 1 : (2 * (long long)R > 0 ? 2 * (long long)R : 1);
+            for (long long cx = x_lo; cx <= x_hi; cx += step) {              // full row on the ring's top/bottom, two cells otherwise
+                if (cx < 0 || cx >= ix.w) continue;
+                const size_t c = (size_t)cy * ix.w + (size_t)cx;
+                const unsigned int b = ix.start[c], e = ix.start[c + 1];
+                for (unsigned int p = b; p < e; ++p) {
+                    const double dx = OCC_DADD(ix.x[p], -px), dy = OCC_DADD(ix.y[p], -py);
+                    const double d2 = OCC_DADD(OCC_DMUL(dx, dx), OCC_DMUL(dy, dy));
+                    const unsigned int id = ix.idx[p];
+                    if (d2 < best || (d2 == best && id < best_idx)) { best = d2; best_pos = p; best_idx = id; }
+                }
+            }
+        }
+        const double margin = (double)R * ix.cell * (1.0 - 1e-12) + inner;      // everything unscanned is at least this far
+        if (margin >= r) break;
+        if (best_pos != 0xffffffffu && best <= margin * margin) break;
+    }
+    *d2_out = best;
+    return (best_pos != 0xffffffffu && best < r2) ? best_pos : 0xffffffffu;
+}
+
+// partial[b] = {count, sum d2, sum sx, sum sy, sum tx, sum ty}
+__global__ void __launch_bounds__(kIT)
+k_icp_assoc(const double* __restrict__ px, const double* __restrict__ py, long long n, const IcpIndex ix, double r, double r2,
+            const IcpState* __restrict__ st, unsigned int* __restrict__ corr, double* __restrict__ partial) {
+    if (st->done) return;
+    const long long i = (long long)blockIdx.x * kIT + threadIdx.x;
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    if (i < n) {
+        const double x = px[i], y = py[i];
+        double d2;
+        const unsigned int p = icp_nearest(ix, x, y, r, r2, &d2);
+        corr[i] = p;
+        if (p != 0xffffffffu) { v[0] = 1.0; v[1] = d2; v[2] = x; v[3] = y; v[4] = ix.x[p]; v[5] = ix.y[p]; }
+    }
+    block_sum<6>(v, partial + (size_t)blockIdx.x * 6);
+}
+
+// One CTA.  Folds the partials in a fixed order, scores the registration and decides whether the
+// loop has converged (Registration.cpp: |d fitness| < rel_f && |d rmse| < rel_r).
+__global__ void __launch_bounds__(kIT)
+k_icp_eval(const double* __restrict__ partial, int n_partial, long long n_source, IcpState* __restrict__ st, double rel_f,
+           double rel_r, int first) {
+    if (st->done) return;
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    for (int b = threadIdx.x; b < n_partial; b += kIT)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) v[j] = OCC_DADD(v[j], partial[(size_t)b * 6 + j]);
+    __shared__ double s_tot[6];
+    block_sum<6>(v, s_tot);
+    if (threadIdx.x == 0) {
+        const double cnt = s_tot[0];
+        const double fit = n_source > 0 ? cnt / (double)n_source : 0.0;
+        const double rmse = cnt > 0.0 ? sqrt(s_tot[1] / cnt) : 0.0;
+        if (!first) {
+            st->iterations += 1.0;
+            if (fabs(st->fitness - fit) < rel_f && fabs(st->rmse - rmse) < rel_r) st->done = 1;
+        }
+        st->fitness = fit; st->rmse = rmse; st->n_corr = cnt;
+        if (cnt > 0.0) { st->mean[0] = s_tot[2] / cnt; st->mean[1] = s_tot[3] / cnt; st->mean[2] = s_tot[4] / cnt; st->mean[3] = s_tot[5] / cnt; }
+    }
+}
+
+// partial2[b] = {sum(sx' tx' + sy' ty'), sum(sx' ty' - sy' tx')} over the demeaned pairs
+__global__ void __launch_bounds__(kIT)
+k_icp_cov(const double* __restrict__ px, const double* __restrict__ py, long long n, const IcpIndex ix,
+          const unsigned int* __restrict__ corr, const IcpState* __restrict__ st, double* __restrict__ partial2) {
+    if (st->done) return;
+    const long long i = (long long)blockIdx.x * kIT + threadIdx.x;
+    double v[2] = {0, 0};
+    if (i < n) {
+        const unsigned int p = corr[i];
+        if (p != 0xffffffffu) {
+            const double sx = px[i] - st->mean[0], sy = py[i] - st->mean[1];
+            const double tx = ix.x[p] - st->mean[2], ty = ix.y[p] - st->mean[3];
+            v[0] = sx * tx + sy * ty;
+            v[1] = sx * ty - sy * tx;
+        }
+    }
+    block_sum<2>(v, partial2 + (size_t)blockIdx.x * 2);
+}
+
+__global__ void __launch_bounds__(kIT)
+k_icp_solve(const double* __restrict__ partial2, int n_partial, IcpState* __restrict__ st) {
+    if (st->done) return;
+    double v[2] = {0, 0};
+    for (int b = threadIdx.x; b < n_partial; b += kIT) { v[0] = OCC_DADD(v[0], partial2[(size_t)b * 2]); v[1] = OCC_DADD(v[1], partial2[(size_t)b * 2 + 1]); }
+    __shared__ double s_tot[2];
+    block_sum<2>(v, s_tot);
+    if (threadIdx.x == 0) {
+        double U[16];
+        for (int i = 0; i < 16; ++i) U[i] = (i % 5 == 0) ? 1.0 : 0.0;
+        if (st->n_corr > 0.0) {                                  // no correspondences -> identity (TransformationEstimation.cpp)
+            const double th = atan2(s_tot[1], s_tot[0]);
+            const double c = cos(th), s = sin(th);
+            U[0] = c; U[1] = -s; U[4] = s; U[5] = c;
+            U[3] = st->mean[2] - (c * st->mean[0] - s * st->mean[1]);
+            U[7] = st->mean[3] - (s * st->mean[0] + c * st->mean[1]);
+        }
+        double Tn[16];
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                double a = 0.0;
+                for (int k = 0; k < 4; ++k) a += U[4 * i + k] * st->T[4 * k + j];
+                Tn[4 * i + j] = a;
+            }
+        for (int i = 0; i < 16; ++i) { st->T[i] = Tn[i]; st->U[i] = U[i]; }
+    }
+}
+
+__global__ void __launch_bounds__(kIT)
+k_icp_apply(double* __restrict__ px, double* __restrict__ py, long long n, const IcpState* __restrict__ st) {
+    if (st->done) return;
+    const long long i = (long long)blockIdx.x * kIT + threadIdx.x;
+    if (i >= n) return;
+    const double* U = st->U;
+    const double x = px[i], y = py[i];
+    const double w = OCC_DADD(OCC_DADD(OCC_DMUL(U[12], x), OCC_DMUL(U[13], y)), U[15]);      // PointCloud::Transform
+    px[i] = OCC_DDIV(OCC_DADD(OCC_DADD(OCC_DMUL(U[0], x), OCC_DMUL(U[1], y)), U[3]), w);
+    py[i] = OCC_DDIV(OCC_DADD(OCC_DADD(OCC_DMUL(U[4], x), OCC_DMUL(U[5], y)), U[7]), w);
+}
+
+struct IcpLayout {
+    size_t cnt, start, cursor, sx, sy, sidx, px, py, corr, partial, partial2, state, total;
+};
+
+static IcpLayout icp_layout(int64_t target_points, int64_t source_points, int64_t cells) {
+    IcpLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return at; };
+    const size_t blocks = (size_t)((source_points + kIT - 1) / kIT) + 1;
+    L.cnt = take((size_t)(cells + 1) * 4); L.start = take((size_t)(cells + 1) * 4); L.cursor = take((size_t)(cells + 1) * 4);
+    L.sx = take((size_t)target_points * 8); L.sy = take((size_t)target_points * 8); L.sidx = take((size_t)target_points * 4);
+    L.px = take((size_t)source_points * 8); L.py = take((size_t)source_points * 8); L.corr = take((size_t)source_points * 4);
+    L.partial = take(blocks * 6 * 8); L.partial2 = take(blocks * 2 * 8); L.state = take(sizeof(IcpState));
+    L.total = o;
+    return L;
+}
+
+}  // namespace occ
+
+using namespace occ;
+
+extern "C" {
+
+size_t mapmerge_icp_workspace_bytes(int64_t target_points, int64_t source_points, int32_t cells_w, int32_t cells_h) {
+    if (target_points <= 0 || source_points <= 0 || cells_w <= 0 || cells_h <= 0) return 0;
+    return icp_layout(target_points, source_points, (int64_t)cells_w * cells_h).total;
+}
+
+int mapmerge_icp_register(const double* d_sx, const double* d_sy, int64_t n_source, const double* d_tx, const double* d_ty,
+                          int64_t n_target, double min_x, double min_y, double cell, int32_t cells_w, int32_t cells_h,
+                          double max_correspondence_distance, int32_t max_iteration, double relative_fitness, double relative_rmse,
+                          double* d_result, void* d_ws, size_t ws_bytes, void* stream) {
+    if (!d_sx || !d_sy || !d_tx || !d_ty || n_source <= 0 || n_target <= 0 || n_target >= 0xffffffffll || !(cell > 0.0) ||
+        cells_w <= 0 || cells_h <= 0 || !(max_correspondence_distance > 0.0) || max_iteration < 0 || !d_result || !d_ws) {
+        set_last_error("mapmerge_icp_register: bad arguments");
+        return OCCGRID_E_ARG;
+    }
+    const int64_t cells = (int64_t)cells_w * cells_h;
+    const IcpLayout L = icp_layout(n_target, n_source, cells);
+    if (ws_bytes < L.total) { set_last_error("mapmerge_icp_register: workspace too small"); return OCCGRID_E_WORKSPACE; }
+    char* ws = reinterpret_cast<char*>(d_ws);
+    unsigned int* cnt = reinterpret_cast<unsigned int*>(ws + L.cnt);
+    unsigned int* start = reinterpret_cast<unsigned int*>(ws + L.start);
+    unsigned int* cursor = reinterpret_cast<unsigned int*>(ws + L.cursor);
+    double* sx = reinterpret_cast<double*>(ws + L.sx);
+    double* sy = reinterpret_cast<double*>(ws + L.sy);
+    unsigned int* sidx = reinterpret_cast<unsigned int*>(ws + L.sidx);
+    double* px = reinterpret_cast<double*>(ws + L.px);
+    double* py = reinterpret_cast<double*>(ws + L.py);
+    unsigned int* corr = reinterpret_cast<unsigned int*>(ws + L.corr);
+    double* partial = reinterpret_cast<double*>(ws + L.partial);
+    double* partial2 = reinterpret_cast<double*>(ws + L.partial2);
+    IcpState* state = reinterpret_cast<IcpState*>(ws + L.state);
+    cudaStream_t st = (cudaStream_t)stream;
+    long long gt = (n_target + kIT - 1) / kIT;
+    if (gt > 148 * 16) gt = 148 * 16;
+    const int gs = (int)((n_source + kIT - 1) / kIT);
+    ProfileScope ps(K_ICP, st, 6 + 5 * max_iteration);
+    OCC_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)(cells + 1) * 4, st));
+    OCC_CUDA_TRY(cudaMemcpyAsync(px, d_sx, (size_t)n_source * 8, cudaMemcpyDeviceToDevice, st));
+    OCC_CUDA_TRY(cudaMemcpyAsync(py, d_sy, (size_t)n_source * 8, cudaMemcpyDeviceToDevice, st));
+    k_icp_count<<<(int)gt, kIT, 0, st>>>(d_tx, d_ty, n_target, min_x, min_y, cell, cells_w, cells_h, cnt);
+    k_icp_scan<<<1, 1024, 0, st>>>(cnt, cells, start, cursor);
+    k_icp_fill<<<(int)gt, kIT, 0, st>>>(d_tx, d_ty, n_target, min_x, min_y, cell, cells_w, cells_h, cursor, sx, sy, sidx);
+    IcpIndex ix;
+    ix.min_x = min_x; ix.min_y = min_y; ix.cell = cell; ix.w = cells_w; ix.h = cells_h;
+    ix.start = start; ix.x = sx; ix.y = sy; ix.idx = sidx;
+    const double r = max_correspondence_distance, r2 = r * r;
+    k_icp_init<<<1, 1, 0, st>>>(state);
+    k_icp_assoc<<<gs, kIT, 0, st>>>(px, py, n_source, ix, r, r2, state, corr, partial);
+    k_icp_eval<<<1, kIT, 0, st>>>(partial, gs, n_source, state, relative_fitness, relative_rmse, 1);
+    for (int it = 0; it < max_iteration; ++it) {
+        k_icp_cov<<<gs, kIT, 0, st>>>(px, py, n_source, ix, corr, state, partial2);
+        k_icp_solve<<<1, kIT, 0, st>>>(partial2, gs, state);
+        k_icp_apply<<<gs, kIT, 0, st>>>(px, py, n_source, state);
+        k_icp_assoc<<<gs, kIT, 0, st>>>(px, py, n_source, ix, r, r2, state, corr, partial);
+        k_icp_eval<<<1, kIT, 0, st>>>(partial, gs, n_source, state, relative_fitness, relative_rmse, 0);
+    }
+    OCC_CUDA_TRY(cudaGetLastError());
+    OCC_CUDA_TRY(cudaMemcpyAsync(d_result, state, 20 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return OCCGRID_OK;
+}
+
+}  // extern "C"

@@ -61,9 +61,12 @@ class MapMerger:
 
     agent_ids      kept for API parity (:12-15); subscriptions are the caller's business
     device         CUDA device
+    registration   None: ``map_callback`` takes the rigid transform from its caller (what the
+                   reference gets from Open3D); 'icp': a callback without a transform is
+                   registered against the global cloud on the device first (:45-56)
     """
 
-    def __init__(self, agent_ids=(1,), device='cuda', publisher=None):
+    def __init__(self, agent_ids=(1,), device='cuda', publisher=None, registration=None):
         if not torch.cuda.is_available():
             raise OccGridError('no CUDA device: the map-fusion engine has no CPU fallback')
         self.agent_ids = list(agent_ids) or [1]
@@ -75,6 +78,11 @@ class MapMerger:
         self.map_origin = [0.0, 0.0]        # :33
         self.publisher = publisher          # optional callable(msg), stands in for :29
         self.published = None               # last published message
+        if registration not in (None, 'icp'):
+            raise ValueError("registration must be None (the caller supplies the transform) or 'icp'")
+        self.registration = registration    # 'icp': callbacks without a transform run registration_icp (:45-52)
+        self.last_registration = None
+        self._local = None                  # scratch cloud of the callback being registered
         self._n_global = 0                  # host mirror of the global cloud size
         self._cloud = None                  # current global cloud
         self._spare = None                  # ping-pong partner for the voxel filter
@@ -211,12 +219,61 @@ class MapMerger:
         tmp._n_global = k
         return tmp.global_pcd
 
+    def register(self, msg, threshold=1.0, max_iteration=30, relative_fitness=1e-6, relative_rmse=1e-6):
+        """``o3d.pipelines.registration.registration_icp(local_pcd, global_pcd, threshold,
+        identity, TransformationEstimationPointToPoint(), ICPConvergenceCriteria(max_iteration))``
+        (:45-52) on the device.  Returns an object with ``transformation`` (4x4), ``fitness``,
+        ``inlier_rmse`` and ``iterations``; None when the local cloud is empty."""
+        if self._n_global == 0:
+            raise OccGridError('register: the global cloud is empty')
+        with torch.cuda.device(self.device):
+            g = self._device_grid(msg)
+            h, w = g.shape
+            cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
+            _native.check(self._lib.mapmerge_count_occupied(g.data_ptr(), g.numel(), cnt.data_ptr(), self._stream()),
+                          'mapmerge_count_occupied')
+            k = int(cnt.item())
+            if k == 0:
+                return None
+            if self._local is None or self._local.capacity < k:
+                self._local = _Cloud(int(k * 1.25) + 16, self.device)
+            loc = self._local
+            loc.count.zero_()
+            ws = self._workspace('extract', self._lib.mapmerge_extract_workspace_bytes(h * w))
+            rc = self._lib.mapmerge_extract_transform(
+                g.data_ptr(), w, h, float(msg.info.resolution), float(msg.info.origin.position.x),
+                float(msg.info.origin.position.y), None, loc.x.data_ptr(), loc.y.data_ptr(), loc.capacity,
+                loc.count.data_ptr(), self._last.data_ptr(), self._status.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
+            _native.check(rc, 'mapmerge_extract_transform')
+            self._bounds_of(self._cloud)
+            bb = self._bounds.cpu().numpy().tolist()
+            cell = float(threshold) / 4.0
+            cw, ch = int((bb[2] - bb[0]) / cell) + 2, int((bb[3] - bb[1]) / cell) + 2
+            nbytes = self._lib.mapmerge_icp_workspace_bytes(self._n_global, k, cw, ch)
+            iws = self._workspace('icp', nbytes)
+            res = torch.empty(20, dtype=torch.float64, device=self.device)
+            rc = self._lib.mapmerge_icp_register(loc.x.data_ptr(), loc.y.data_ptr(), k, self._cloud.x.data_ptr(),
+                                                 self._cloud.y.data_ptr(), self._n_global, bb[0], bb[1], cell, cw, ch,
+                                                 float(threshold), int(max_iteration), float(relative_fitness),
+                                                 float(relative_rmse), res.data_ptr(), iws.data_ptr(), iws.numel(), self._stream())
+            _native.check(rc, 'mapmerge_icp_register')
+            r = res.cpu().numpy()
+            self._check_status()
+        self.last_registration = SimpleNamespace(transformation=r[:16].reshape(4, 4).copy(), fitness=float(r[16]),
+                                                 inlier_rmse=float(r[17]), iterations=int(r[18]), correspondences=int(r[19]))
+        return self.last_registration
+
     def _merge_one(self, msg, transform, fitness):
         """:36-60 without the publish.  Returns False where the reference returns early."""
         if transform is not None and np.asarray(transform).size == 3:
             transform = se2_matrix(*np.asarray(transform, np.float64).tolist())
         with torch.cuda.device(self.device):
             first = self._n_global == 0
+            if not first and transform is None and self.registration == 'icp':
+                reg = self.register(msg)                    # :45-52
+                if reg is None:                             # empty local cloud (:37-38)
+                    return False
+                transform, fitness = reg.transformation, reg.fitness
             if not first and fitness < 0.6:                 # :54-56 — no state change, nothing published
                 return False
             self._ensure_capacity(self._n_global + (1 << 16))

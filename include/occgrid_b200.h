@@ -314,6 +314,26 @@ int mapmerge_chain_rebuild(void* d_chain, const int64_t* dims, int n_agents, con
                            int32_t* d_status, void* d_voxel_ws, size_t voxel_ws_bytes,
                            int64_t lattice_capacity_cells, void* stream);
 
+/* registration_icp(local, global, max_correspondence_distance, identity,
+ * TransformationEstimationPointToPoint(), ICPConvergenceCriteria(max_iteration)) as called at
+ * map_merger.py:45-52 (Open3D, absent and un-pinned here: follows its published algorithm, see
+ * oracle/icp_oracle.py).  Source = local cloud (n_source points), target = global cloud
+ * (n_target points), both planar fp64 device arrays.  The target is binned into a uniform cell
+ * list: cells of size `cell` (use max_correspondence_distance / 4) starting at (min_x, min_y),
+ * cells_w x cells_h of them covering the target's bounds.  Exact nearest neighbours (squared
+ * distance < max^2, ties by lowest target index), rigid fit in closed form, sums reduced in a
+ * fixed order.  Runs stream-ordered without host round trips.
+ * d_result (20 doubles): [0..15] transformation row-major, [16] fitness, [17] inlier_rmse,
+ * [18] iterations run, [19] number of correspondences of the last evaluation. */
+size_t mapmerge_icp_workspace_bytes(int64_t target_points, int64_t source_points, int32_t cells_w,
+                                    int32_t cells_h);
+int mapmerge_icp_register(const double* d_sx, const double* d_sy, int64_t n_source,
+                          const double* d_tx, const double* d_ty, int64_t n_target, double min_x,
+                          double min_y, double cell, int32_t cells_w, int32_t cells_h,
+                          double max_correspondence_distance, int32_t max_iteration,
+                          double relative_fitness, double relative_rmse, double* d_result,
+                          void* d_ws, size_t ws_bytes, void* stream);
+
 /* publish_global_map's rasterisation (:103-111): fill width x height with -1, then
  * grid[int((y-min_y)/res)][int((x-min_x)/res)] = 100 with index clipping (:108-109).
  * width/height follow :100-101 and are computed by the caller from the bounds. */
@@ -363,7 +383,8 @@ enum {
     OCCGRID_K_TILE_SCAN, OCCGRID_K_TILE_SCATTER, OCCGRID_K_TILE_RAYCAST, OCCGRID_K_TILE_RESOLVE,
     OCCGRID_K_MERGE_EXTRACT, OCCGRID_K_MERGE_BOUNDS, OCCGRID_K_MERGE_VOXEL, OCCGRID_K_MERGE_RASTER,
     OCCGRID_K_MERGE_FUSE, OCCGRID_K_PROBE, OCCGRID_K_ROUTE, OCCGRID_K_FRONTIER, OCCGRID_K_FRONTIER_CLUSTER,
-    OCCGRID_K_CHAIN_PROBE, OCCGRID_K_CHAIN_INCR, OCCGRID_K_CHAIN_REBUILD, OCCGRID_K_N_KERNELS
+    OCCGRID_K_CHAIN_PROBE, OCCGRID_K_CHAIN_INCR, OCCGRID_K_CHAIN_REBUILD, OCCGRID_K_ICP,
+    OCCGRID_K_N_KERNELS
 };
 int occgrid_profile_begin(void);
 int occgrid_profile_end(double* ms_by_kernel, int64_t* launches_by_kernel, int n_slots);

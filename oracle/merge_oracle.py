@@ -22,7 +22,8 @@ verbatim; the three Open3D calls are restated from Open3D's published algorithm
                       appearance (voxels ordered by their smallest point index, what an
                       insertion-ordered map would produce).                  map_merger.py:60
 
-ICP (:45-56) is not restated: callers supply the rigid transform.
+ICP (:45-56) is restated separately in oracle/icp_oracle.py; `OracleMerger.map_callback` takes the
+rigid transform (and the fitness verdict) from its caller.
 """
 import numpy as np
 

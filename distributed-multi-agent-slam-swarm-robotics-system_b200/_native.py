@@ -13,7 +13,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_PATH = os.path.join(PKG_DIR, 'liboccgrid_b200.so')
-SOURCES = ['occgrid_integrate.cu', 'occgrid_tiled.cu', 'occgrid_route.cu', 'mapmerge.cu', 'frontier.cu', 'icp.cu']
+SOURCES = ['occgrid_integrate.cu', 'occgrid_tiled.cu', 'occgrid_route.cu', 'mapmerge.cu', 'frontier.cu', 'icp.cu', 'slam_chain.cpp']
 HEADERS = ['common.cuh', 'beam_expand.cuh', 'sincos_dd.cuh', os.path.join('..', '..', 'include', 'occgrid_b200.h')]
 
 STRATEGY = {'auto': -1, 'global_atomic': 0, 'tiled': 1}
@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
         return LIB_PATH
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     cmd = ['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-           '-Xcompiler', '-fPIC', '-shared', '-o', LIB_PATH] + srcs
+           '-Xcompiler', '-fPIC', '-Xcompiler', '-ffp-contract=off', '-shared', '-o', LIB_PATH] + srcs
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -153,6 +153,18 @@ def _bind_merge(L):
     L.mapmerge_icp_workspace_bytes.argtypes = [i64, i64, i32, i32]
     L.mapmerge_icp_register.restype = C.c_int
     L.mapmerge_icp_register.argtypes = [vp, vp, i64, vp, vp, i64, dbl, dbl, dbl, i32, i32, dbl, i32, dbl, dbl, vp, vp, sz, vp]
+    L.occgrid_slam_create.restype = vp
+    L.occgrid_slam_create.argtypes = []
+    L.occgrid_slam_destroy.restype = None
+    L.occgrid_slam_destroy.argtypes = [vp]
+    L.occgrid_slam_drift_table.restype = C.c_int
+    L.occgrid_slam_drift_table.argtypes = [vp, vp, i64, i32, i32, vp, dbl, vp]
+    L.occgrid_slam_counts.restype = C.c_int
+    L.occgrid_slam_counts.argtypes = [vp, vp, vp, vp]
+    L.occgrid_slam_closures.restype = C.c_int
+    L.occgrid_slam_closures.argtypes = [vp, i64, vp, vp, vp, vp]
+    L.occgrid_slam_correction_for_agent.restype = C.c_int
+    L.occgrid_slam_correction_for_agent.argtypes = [vp, i32, vp]
     L.mapmerge_rasterise.restype = C.c_int
     L.mapmerge_rasterise.argtypes = [vp, vp, vp, dbl, vp, i32, i32, vp, vp]
     L.mapmerge_fuse_max.restype = C.c_int

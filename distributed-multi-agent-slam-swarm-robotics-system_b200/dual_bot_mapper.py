@@ -17,6 +17,7 @@ library or a CUDA device the compute entry points raise.
 """
 from __future__ import annotations
 
+import ctypes
 import math
 import struct
 
@@ -542,11 +543,92 @@ class PoseGraphSLAM:
         return tx, ty
 
 
+class NativePoseGraphSLAM:
+    """``PoseGraphSLAM``'s loop-closure chain (:261-338) and the drift bookkeeping of the ingest
+    loop (:850-857, :908-914) run by the C library over whole batches of datagrams
+    (``occgrid_slam_*`` in the header; host code, no GPU).  State carries over from batch to
+    batch like the reference's ``slam`` / ``drift_correction`` objects.  Same closures and the same
+    fp64 corrections as ``PoseGraphSLAM``; the quadratic landmark scan is replaced by a spatial
+    hash that returns the same first match."""
+
+    def __init__(self):
+        self._lib = _native.lib()
+        self._h = self._lib.occgrid_slam_create()
+        if not self._h:
+            raise OccGridError('occgrid_slam_create failed')
+
+    def __del__(self):
+        h, self._h = getattr(self, '_h', None), None
+        if h:
+            self._lib.occgrid_slam_destroy(h)
+
+    def drift_table(self, packets, separation=0.0, sizes=None):
+        """``packets``: uint8 [n, stride >= 41] (42-byte v2 records, or v1 records padded to the
+        stride with ``sizes`` giving each datagram's length).  Returns float64 [n, 2]."""
+        pk = np.ascontiguousarray(packets, dtype=np.uint8)
+        if pk.ndim != 2:
+            raise ValueError('packets must be uint8 [n, record_bytes]')
+        n, stride = pk.shape
+        out = np.zeros((n, 2), np.float64)
+        sz = None if sizes is None else np.ascontiguousarray(sizes, dtype=np.int32)
+        if sz is not None and sz.shape != (n,):
+            raise ValueError('sizes must have one entry per record')
+        rc = self._lib.occgrid_slam_drift_table(self._h, pk.ctypes.data, n, stride, min(stride, PACKET_SIZE),
+                                                sz.ctypes.data if sz is not None else None, float(separation), out.ctypes.data)
+        _native.check(rc, 'occgrid_slam_drift_table')
+        return out
+
+    def _counts(self):
+        c = (ctypes.c_int64 * 3)()
+        _native.check(self._lib.occgrid_slam_counts(self._h, ctypes.byref(c, 0), ctypes.byref(c, 8), ctypes.byref(c, 16)),
+                      'occgrid_slam_counts')
+        return int(c[0]), int(c[1]), int(c[2])
+
+    n_nodes = property(lambda self: self._counts()[0])
+    n_landmarks = property(lambda self: self._counts()[1])
+
+    @property
+    def closures(self):
+        """[(landmark node index, closing node index, corr_dx, corr_dy)] like ``PoseGraphSLAM.closures``."""
+        n = self._counts()[2]
+        lm, nd, xy = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros((n, 2), np.float64)
+        _native.check(self._lib.occgrid_slam_closures(self._h, n, lm.ctypes.data, nd.ctypes.data, xy.ctypes.data, None),
+                      'occgrid_slam_closures')
+        return [(int(lm[i]), int(nd[i]), float(xy[i, 0]), float(xy[i, 1])) for i in range(n)]
+
+    def get_correction_for_agent(self, agent_id):
+        xy = (ctypes.c_double * 2)()
+        _native.check(self._lib.occgrid_slam_correction_for_agent(self._h, int(agent_id), xy), 'occgrid_slam_correction_for_agent')
+        return float(xy[0]), float(xy[1])
+
+
+def _pack_datagrams(datagrams):
+    """list of datagrams (any lengths) / bytes / uint8 [n, stride] -> (uint8 [n, 42], sizes or None)."""
+    if isinstance(datagrams, np.ndarray):
+        return datagrams, None
+    if isinstance(datagrams, (bytes, bytearray, memoryview)):
+        return np.frombuffer(bytes(datagrams), np.uint8).reshape(-1, PACKET_SIZE), None
+    sizes = np.fromiter((len(d) for d in datagrams), np.int32, len(datagrams))
+    if len(datagrams) and (sizes == PACKET_SIZE).all():
+        return np.frombuffer(b''.join(datagrams), np.uint8).reshape(-1, PACKET_SIZE), None
+    out = np.zeros((len(datagrams), PACKET_SIZE), np.uint8)
+    for k, d in enumerate(datagrams):
+        if len(d) in (PACKET_SIZE, PACKET_SIZE_V1):
+            out[k, :len(d)] = np.frombuffer(d, np.uint8)
+    return out, sizes
+
+
 def slam_drift_table(datagrams, separation=0.0, slam=None, timestamps=None):
     """Run the sequential part of the ingest loop (:826-857, :908-914) on the host and return
     the drift (cdx, cdy) in force for every datagram, float64 [n, 2] — the input
-    ``OccupancyGrid.update_packets(drift=...)`` needs to reproduce a SLAM-corrected session."""
-    slam = slam if slam is not None else PoseGraphSLAM()
+    ``OccupancyGrid.update_packets(drift=...)`` needs to reproduce a SLAM-corrected session.
+    Runs in the C library (``NativePoseGraphSLAM``) unless a Python ``PoseGraphSLAM`` is passed
+    in (kept for callers that want its ``nodes`` list)."""
+    if slam is None:
+        slam = NativePoseGraphSLAM()
+    if isinstance(slam, NativePoseGraphSLAM):
+        pk, sizes = _pack_datagrams(datagrams)
+        return slam.drift_table(pk, separation, sizes), slam
     drift = {1: (0.0, 0.0), 2: (0.0, 0.0)}
     out = np.zeros((len(datagrams), 2), np.float64)
     for k, data in enumerate(datagrams):

@@ -373,6 +373,30 @@ int occgrid_frontier_clusters(const int32_t* d_xy, const int64_t* d_count, int64
  * next batch finds room on every SM and runs concurrently.  Process-wide. */
 int occgrid_set_raycast_ctas_per_sm(int cap);
 
+/* ---------------------------------------------------------------------------------------------
+ * Host-side producer of the per-packet drift table (no GPU involved): the sequential half of
+ * the ingest loop, dual_bot_mapper.py:826-857 + :908-914 with PoseGraphSLAM.add_pose /
+ * _check_closure (:261-322).  For every record k of a HOST buffer, in order: drift_out[k] =
+ * (cdx, cdy) in force for that packet ((0, 0) for dropped records) — the table
+ * occgrid_integrate_packets takes as d_drift_xy.  State (pose count, landmarks, closures,
+ * per-agent drift) lives in the handle and carries over from batch to batch.
+ * rec_sizes: per-record datagram sizes (42 = v2, 41 = v1, anything else is dropped, :828-838),
+ * or NULL when every record has rec_size bytes.  Bit-identical to the reference's arithmetic.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct occgrid_slam occgrid_slam;
+occgrid_slam* occgrid_slam_create(void);
+void occgrid_slam_destroy(occgrid_slam* slam);
+int occgrid_slam_drift_table(occgrid_slam* slam, const uint8_t* packets_host, int64_t n_records,
+                             int32_t rec_stride, int32_t rec_size, const int32_t* rec_sizes,
+                             double separation, double* drift_out_xy);
+int occgrid_slam_counts(const occgrid_slam* slam, int64_t* n_nodes, int64_t* n_landmarks,
+                        int64_t* n_closures);
+/* closures in the order they were found: (landmark's node index, closing node index, correction) */
+int occgrid_slam_closures(const occgrid_slam* slam, int64_t capacity, int64_t* lm_node,
+                          int64_t* node, double* corr_xy, int32_t* agent);
+/* PoseGraphSLAM.get_correction_for_agent (:324-332) */
+int occgrid_slam_correction_for_agent(const occgrid_slam* slam, int32_t agent_id, double* out_xy);
+
 /*
  * Measurement hook (bench.py): between _begin and _end every kernel this library launches is
  * bracketed by CUDA events on its stream.  _end synchronises those events and returns, per

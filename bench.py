@@ -235,6 +235,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'        # NCCL's version banner goes to stdout; this script prints ONE JSON line
         dist.init_process_group('nccl', device_id=dev)
     n = world
     W = max(args.warmup, 3)

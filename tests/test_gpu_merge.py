@@ -207,6 +207,35 @@ def test_chain_with_rejected_and_empty_agents(MM):
     assert m.chain_stats['callbacks'] == 4            # agents 2, 5, 6, 8
 
 
+def test_chain_min_corner_moves_inwards(MM):
+    """The point on the cloud's min corner is re-averaged inwards by an incremental callback: the
+    chain has to recompute its bounds (stall reason 3) before the next decision, which then
+    re-anchors the lattice (rebuild).  Agents 1 and 3 do not see the corner, agents 2 and 4 see it
+    shifted by a fraction of a voxel."""
+    n = 96
+    g = synth_agent_grid(n, 41)
+    g[0, :] = -1
+    g[:, 0] = -1
+    inner = g.copy()
+    inner[:6, :] = -1
+    inner[:, :6] = -1
+    g[0, 0] = 100                                         # the only point on the min corner
+    grids = np.stack([g, inner, g, inner, g, inner])
+    A = len(grids)
+    origins = np.tile(np.array([[-2.4, -2.4]]), (A, 1))
+    tf = np.stack([np.eye(4) for _ in range(A)])
+    for a in range(A):
+        tf[a, 0, 3], tf[a, 1, 3] = 0.004 * a, 0.003 * a
+    o, want = _oracle_chain(grids, n, 0.05, (-2.4, -2.4), tf)
+    m = MM.MapMerger()
+    out, origin = m.merge(grids, origins, 0.05, tf)
+    assert np.array_equal(out, want[0]) and origin == want[1]
+    pc = m.global_pcd
+    assert pc.shape[0] == o.gx.shape[0]
+    assert np.array_equal(pc[:, 0], o.gx) and np.array_equal(pc[:, 1], o.gy)
+    assert m.chain_stats['rebounds'] >= 1 and m.chain_stats['rebuilds'] < m.chain_stats['callbacks'], m.chain_stats
+
+
 def test_2048_grids(MM):
     """BASELINE config 3 grid size (2048^2, ~1.5 % occupied) on a few agents, 50 m translations."""
     run_pair(MM, 2048, 4, seed=7, span=50.0, origin=(-51.2, -51.2), check_every=False)

@@ -120,3 +120,20 @@ def test_gpu_callbacks_with_icp_match_oracle_chain(MM):
     lx, ly = MO.grid_to_points(far.ravel(), n, n, res, origin[0] + 40.0, origin[1])
     got = m.map_callback(MM.make_grid_msg(far.ravel(), n, n, res, origin[0] + 40.0, origin[1]), 9)
     assert got is None and m.last_registration.fitness < 0.6
+
+
+@pytest.mark.gpu
+def test_gpu_no_overlap_is_rejected(MM):
+    """No target within 1 m of any source point: zero correspondences, identity transform, one
+    iteration (the second evaluation equals the first), and map_callback rejects the grid."""
+    n, res = 128, 0.05
+    g = synth_agent_grid(n, 4)
+    m = MM.MapMerger(registration='icp')
+    assert m.map_callback(MM.make_grid_msg(g.ravel(), n, n, res, -3.2, -3.2), 1) is not None
+    k = m.global_pcd.shape[0]
+    far = MM.make_grid_msg(g.ravel(), n, n, res, 100.0, -3.2)
+    reg = m.register(far)
+    assert reg.fitness == 0.0 and reg.inlier_rmse == 0.0 and reg.correspondences == 0 and reg.iterations == 1
+    assert np.array_equal(reg.transformation, np.eye(4))
+    assert m.map_callback(far, 2) is None and m.global_pcd.shape[0] == k
+    assert m.register(MM.make_grid_msg(np.full(n * n, -1, np.int8), n, n, res, 0.0, 0.0)) is None

@@ -252,12 +252,15 @@ struct BatchXform { double m[6]; double w[3]; int identity; int use; };   // row
 
 __global__ void __launch_bounds__(kMT)
 k_batch_count(const int8_t* const* __restrict__ grids, long long n_cells, int blocks_per_grid,
-              unsigned int* __restrict__ block_counts /* [A][blocks_per_grid] */) {
+              unsigned int* __restrict__ block_counts /* [A][blocks_per_grid] */,
+              unsigned long long* __restrict__ masks /* [A][blocks_per_grid * kMT]: the write pass reads these, not the grids */) {
     __shared__ unsigned int s_warp[33];
     const int a = blockIdx.y;
     const long long base = ((long long)blockIdx.x * kMT + threadIdx.x) * kCellsPerThread;
+    const unsigned long long mask = base < n_cells ? occupied_mask64(grids[a], base, n_cells) : 0ull;
+    masks[((size_t)a * blocks_per_grid + blockIdx.x) * kMT + threadIdx.x] = mask;
     unsigned int total;
-    block_exclusive_scan(base < n_cells ? __popcll(occupied_mask64(grids[a], base, n_cells)) : 0u, s_warp, &total);
+    block_exclusive_scan(__popcll(mask), s_warp, &total);
     if (threadIdx.x == 0) block_counts[(size_t)a * blocks_per_grid + blockIdx.x] = total;
 }
 
@@ -307,7 +310,7 @@ k_batch_offsets(const long long* __restrict__ agent_total, const BatchXform* __r
 }
 
 __global__ void __launch_bounds__(kMT)
-k_batch_write(const int8_t* const* __restrict__ grids, long long n_cells, int width, double res,
+k_batch_write(const unsigned long long* __restrict__ masks, long long n_cells, int width, double res,
               const double* __restrict__ origins /* [A][2] */, const BatchXform* __restrict__ T, int blocks_per_grid,
               const unsigned int* __restrict__ block_offsets, const long long* __restrict__ agent_offset, long long capacity,
               double* __restrict__ px, double* __restrict__ py) {
@@ -318,7 +321,7 @@ k_batch_write(const int8_t* const* __restrict__ grids, long long n_cells, int wi
     if (!t.use || agent_offset[gridDim.y] > capacity) return;
     const long long chunk_base = (long long)blockIdx.x * kChunk;
     const long long base = chunk_base + (long long)threadIdx.x * kCellsPerThread;
-    const unsigned long long mask = base < n_cells ? occupied_mask64(grids[a], base, n_cells) : 0ull;
+    const unsigned long long mask = masks[((size_t)a * blocks_per_grid + blockIdx.x) * kMT + threadIdx.x];   // 1 bit per cell, from the count pass
     unsigned int total;
     unsigned int off = block_exclusive_scan(__popcll(mask), s_warp, &total);
     unsigned long long m = mask;
@@ -1101,9 +1104,15 @@ int mapmerge_extract_transform(const int8_t* d_grid, int32_t width, int32_t heig
     return OCCGRID_OK;
 }
 
-size_t mapmerge_extract_batch_workspace_bytes(int64_t n_cells, int n_agents) {
+static size_t batch_counts_bytes(int64_t n_cells, int n_agents) {
     const int64_t blocks = (n_cells + kChunk - 1) / kChunk;
     return align_up((size_t)blocks * (size_t)n_agents * sizeof(unsigned int), 256);
+}
+
+// block counts [A][blocks] | occupancy masks [A][blocks * kMT] (one bit per cell)
+size_t mapmerge_extract_batch_workspace_bytes(int64_t n_cells, int n_agents) {
+    const int64_t blocks = (n_cells + kChunk - 1) / kChunk;
+    return batch_counts_bytes(n_cells, n_agents) + align_up((size_t)blocks * kMT * (size_t)n_agents * sizeof(unsigned long long), 256);
 }
 
 // Pass 1 of a batched extraction: per-block and per-agent occupied-cell counts.
@@ -1120,7 +1129,8 @@ int mapmerge_extract_batch_count(const int8_t* const* d_grids, int n_agents, int
     unsigned int* block_counts = reinterpret_cast<unsigned int*>(d_ws);
     ProfileScope ps(K_MERGE_EXTRACT, st, 2);
     dim3 grid((unsigned)bpg, (unsigned)n_agents);
-    k_batch_count<<<grid, kMT, 0, st>>>(d_grids, n_cells, bpg, block_counts);
+    unsigned long long* masks = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(d_ws) + batch_counts_bytes(n_cells, n_agents));
+    k_batch_count<<<grid, kMT, 0, st>>>(d_grids, n_cells, bpg, block_counts, masks);
     k_batch_scan<<<n_agents, 1024, 0, st>>>(block_counts, bpg, (long long*)d_agent_total);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
@@ -1162,7 +1172,8 @@ int mapmerge_extract_batch_write(const int8_t* const* d_grids, int n_agents, int
     ProfileScope ps(K_MERGE_EXTRACT, st, 2);
     dim3 grid((unsigned)bpg, (unsigned)n_agents);
     k_batch_offsets<<<1, 1024, 0, st>>>((const long long*)d_agent_total, dT, n_agents, capacity, (long long*)d_agent_offset, d_status);
-    k_batch_write<<<grid, kMT, 0, st>>>(d_grids, n_cells, width, res, d_origins, dT, bpg, block_counts, (const long long*)d_agent_offset,
+    const unsigned long long* masks = reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(d_ws) + batch_counts_bytes(n_cells, n_agents));
+    k_batch_write<<<grid, kMT, 0, st>>>(masks, n_cells, width, res, d_origins, dT, bpg, block_counts, (const long long*)d_agent_offset,
                                         capacity, d_px, d_py);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;

@@ -656,6 +656,63 @@ def slam_drift_table(datagrams, separation=0.0, slam=None, timestamps=None):
     return out, slam
 
 
+class IngestBatcher:
+    """Host-side batcher for the server loop (:797-919): datagrams are pushed as they arrive
+    (``data, addr = sock.recvfrom(...)``, :818), filtered by size exactly like :828-838, and a
+    ``flush()`` — once per frame in the reference's loop (:816 caps a frame at 20 datagrams; any
+    batch size works here) — runs the sequential SLAM chain over the pending records in the C
+    library and integrates them on the device in ONE call.  Equal to the reference handling the
+    same datagrams one by one: SLAM state and drift carry over between flushes, and a later batch
+    overwrites an earlier one cell by cell (last writer wins, :148-156).
+
+        batcher = IngestBatcher(occ_grid, separation=args.separation)
+        ...
+        batcher.push(data)                 # instead of unpack + 4x update_ray (:826-903)
+        ...
+        batcher.flush()                    # end of the frame's receive loop
+    """
+
+    def __init__(self, grid, separation=0.0, use_slam=True, capacity=4096):
+        self.grid = grid
+        self.separation = float(separation)
+        self.slam = NativePoseGraphSLAM() if use_slam else None
+        self.capacity = int(capacity)
+        self._buf = torch.zeros((self.capacity, PACKET_SIZE), dtype=torch.uint8).pin_memory() \
+            if torch.cuda.is_available() else torch.zeros((self.capacity, PACKET_SIZE), dtype=torch.uint8)
+        self._np = self._buf.numpy()
+        self._n = 0
+        self.dropped = 0                    # datagrams of a foreign size (:836-838)
+        self.total = 0                      # records handed to the device so far
+
+    def push(self, data):
+        n = len(data)
+        if n == PACKET_SIZE:
+            self._np[self._n] = np.frombuffer(data, np.uint8)
+        elif n == PACKET_SIZE_V1:           # v1: no landmark byte -> LM_NONE (:832-835)
+            row = self._np[self._n]
+            row[:PACKET_SIZE_V1] = np.frombuffer(data, np.uint8)
+            row[PACKET_SIZE_V1] = LM_NONE
+        else:
+            self.dropped += 1
+            return
+        self._n += 1
+        if self._n == self.capacity:
+            self.flush()
+
+    def flush(self):
+        """Integrate everything pushed since the last flush; returns the number of records."""
+        n = self._n
+        if n == 0:
+            return 0
+        pk = self._np[:n]
+        drift = self.slam.drift_table(pk, self.separation) if self.slam is not None else None
+        self.grid.update_packets(self._buf[:n], separation=self.separation, drift=drift)
+        torch.cuda.current_stream(self.grid.device).synchronize()      # the staging rows are reused by the next push
+        self._n = 0
+        self.total += n
+        return n
+
+
 def replay_session(datagrams, grid=None, separation=0.0, use_slam=True, **grid_kwargs):
     """Headless restatement of ``main()``'s ingest loop for a recorded session: host SLAM
     chain -> drift table -> one batched device integration.  Returns (grid, slam)."""

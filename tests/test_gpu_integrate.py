@@ -370,3 +370,42 @@ def test_fine_resolution_falls_back_to_global_atomics(M):
     c = c_oracle.integrate_packets(pk, want, 0.0, 0.0, 0.02, separation=0.25)
     assert np.array_equal(g.grid, want)
     assert g.counters()['updates'] == c['updates']
+
+
+@pytest.mark.parametrize('frame', [1, 20, 137])
+def test_ingest_batcher_frames_equal_one_batch(M, golden, frame):
+    """The server loop's shape (:797-919): datagrams pushed one at a time, one flush per frame
+    (the reference caps a frame at 20 datagrams, :816).  SLAM state and drift carry over between
+    frames, later frames overwrite earlier ones: the final grid is the golden one, with SLAM on."""
+    pk, _ = session_packets(time_sorted=True)
+    want = golden['session']['time_order_slam_on']
+    g = supported(M, 'auto')
+    b = M.IngestBatcher(g, separation=0.0, use_slam=True, capacity=256)
+    junk = 0
+    for k, d in enumerate(pk):
+        b.push(d)
+        if k % 50 == 7:
+            b.push(b'QSRL' + bytes(13))            # heartbeat-sized datagram: dropped by size (:836-838)
+            junk += 1
+        if (k + 1) % frame == 0:
+            b.flush()
+    b.flush()
+    assert b.total == len(pk) and b.dropped == junk and b.flush() == 0
+    assert sha1(g.grid) == want['sha1']
+    assert len(b.slam.closures) == want['closures']
+
+
+def test_ingest_batcher_v1_datagrams(M):
+    """41-byte v1 datagrams carry no landmark byte: LM_NONE (:832-835)."""
+    from oracle import occgrid_oracle as O
+    pk, _ = session_packets(time_sorted=True)
+    v1 = [d[:41] if i % 3 else d for i, d in enumerate(pk)]
+    og, os_ = O.OracleGrid(), O.OracleSLAM()
+    O.replay(v1, grid=og, separation=0.3, slam=os_)
+    g = supported(M, 'auto')
+    b = M.IngestBatcher(g, separation=0.3, use_slam=True, capacity=100)
+    for d in v1:
+        b.push(d)
+    b.flush()
+    assert np.array_equal(g.grid, og.grid)
+    assert b.slam.closures == [tuple(c) for c in os_.closures]

@@ -165,6 +165,10 @@ def _bind_merge(L):
     L.occgrid_slam_closures.argtypes = [vp, i64, vp, vp, vp, vp]
     L.occgrid_slam_correction_for_agent.restype = C.c_int
     L.occgrid_slam_correction_for_agent.argtypes = [vp, i32, vp]
+    L.occgrid_accumulate_packets.restype = C.c_int
+    L.occgrid_accumulate_packets.argtypes = [C.POINTER(Geom), vp, i64, i32, i32, vp, vp, vp, i32, vp, vp, sz, vp, i32, vp]
+    L.occgrid_counts_to_logodds.restype = C.c_int
+    L.occgrid_counts_to_logodds.argtypes = [vp, i64, dbl, dbl, dbl, dbl, vp, vp]
     L.mapmerge_rasterise.restype = C.c_int
     L.mapmerge_rasterise.argtypes = [vp, vp, vp, dbl, vp, i32, i32, vp, vp]
     L.mapmerge_fuse_max.restype = C.c_int

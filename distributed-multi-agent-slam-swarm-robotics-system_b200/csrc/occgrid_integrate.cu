@@ -115,6 +115,31 @@ __device__ __forceinline__ void draw_beam_global(const Geom& g, unsigned int* __
         atomicMax(&stamps[(size_t)(y - g.win_y0) * g.win_w + (x - g.win_x0)], free_stamp | 1u);
 }
 
+// Hit/miss COUNT mode (extension): counts = int32 [win_h][win_w][2] = {miss, hit} per cell.  Every
+// cell update_ray would have stored FREE to counts a miss, the OCCUPIED end cell of a valid hit
+// counts a hit; integer adds commute, so the planes equal np.add.at over the reference's cells.
+__device__ __forceinline__ void count_beam_global(const Geom& g, int* __restrict__ counts, const Beam& b) {
+    if (!b.valid) return;
+    const int wx1 = g.win_x0 + g.win_w, wy1 = g.win_y0 + g.win_h;
+    const int bx0 = min(b.x0, b.x1), bx1 = max(b.x0, b.x1);
+    const int by0 = min(b.y0, b.y1), by1 = max(b.y0, b.y1);
+    if (bx1 < g.win_x0 || bx0 >= wx1 || by1 < g.win_y0 || by0 >= wy1) return;
+    int x = b.x0, y = b.y0;
+    const int dx = bx1 - bx0, dy = by1 - by0;
+    const int sx = b.x0 < b.x1 ? 1 : -1, sy = b.y0 < b.y1 ? 1 : -1;
+    int err = dx - dy;
+    const int n = max(dx, dy);
+    for (int i = 0; i < n; ++i) {
+        if (x >= g.win_x0 && x < wx1 && y >= g.win_y0 && y < wy1)
+            atomicAdd(&counts[2 * ((size_t)(y - g.win_y0) * g.win_w + (x - g.win_x0))], 1);
+        const int e2 = 2 * err;
+        if (e2 > -dy) { err -= dy; x += sx; }
+        if (e2 < dx)  { err += dx; y += sy; }
+    }
+    if (b.hit && x >= g.win_x0 && x < wx1 && y >= g.win_y0 && y < wy1)
+        atomicAdd(&counts[2 * ((size_t)(y - g.win_y0) * g.win_w + (x - g.win_x0)) + 1], 1);
+}
+
 // Cooperative copy of this CTA's records into shared memory with 16-byte loads.
 __device__ __forceinline__ void stage_records(const uint8_t* __restrict__ src, size_t bytes, uint8_t* smem) {
     const size_t nvec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) ? bytes / 16 : 0;
@@ -128,6 +153,7 @@ __device__ __forceinline__ bool start_in_window(const Geom& g, const Beam& b) {
     return b.valid && b.x0 >= g.win_x0 && b.x0 < g.win_x0 + g.win_w && b.y0 >= g.win_y0 && b.y0 < g.win_y0 + g.win_h;
 }
 
+template <bool kCounts>
 __global__ void __launch_bounds__(kThreads)
 k_integrate_global(Geom g, const uint8_t* __restrict__ pkts, long long n, int stride,
                    const int32_t* __restrict__ agent_idx, const double* __restrict__ drift,
@@ -163,7 +189,8 @@ k_integrate_global(Geom g, const uint8_t* __restrict__ pkts, long long n, int st
                 c[OCCGRID_C_UPDATES] += cells;
                 c[OCCGRID_C_SLOWPATH] += b[s].slow;
                 if (start_in_window(g, b[s])) c[OCCGRID_C_OWNED_UPDATES] += cells;
-                draw_beam_global(g, stamps, b[s], (unsigned int)(k * 4 + s + 1), later_writes_first);
+                if (kCounts) count_beam_global(g, reinterpret_cast<int*>(stamps), b[s]);
+                else draw_beam_global(g, stamps, b[s], (unsigned int)(k * 4 + s + 1), later_writes_first);
                 later_writes_first = later_writes_first || (b[s].valid && (cells > 1 || b[s].hit));
             }
         }
@@ -300,11 +327,23 @@ int integrate_packets_global(const occgrid_geom* geom, const uint8_t* d_packets,
     const long long blocks = (n + kThreads - 1) / kThreads;
     {
         ProfileScope ps(K_INTEGRATE_GLOBAL, st);
-        k_integrate_global<<<(unsigned int)blocks, kThreads, 0, st>>>(g, d_packets, n, stride, d_agent_idx, d_drift,
-                                                                     d_agent_off, n_agents, stamps, d_counters);
+        k_integrate_global<false><<<(unsigned int)blocks, kThreads, 0, st>>>(g, d_packets, n, stride, d_agent_idx, d_drift,
+                                                                            d_agent_off, n_agents, stamps, d_counters);
     }
     OCC_CUDA_TRY(cudaGetLastError());
     return launch_resolve(geom, stamps, d_grid, st);
+}
+
+// L = clamp(hits * l_occ + misses * l_free, l_min, l_max), derived from the integer planes so
+// that it does not depend on the order the beams arrived in (no float atomics anywhere).
+__global__ void __launch_bounds__(kThreads)
+k_counts_to_logodds(const int32_t* __restrict__ counts, long long n_cells, double l_occ, double l_free, double l_min, double l_max,
+                    float* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n_cells; i += (long long)gridDim.x * kThreads) {
+        const int2 c = reinterpret_cast<const int2*>(counts)[i];          // {miss, hit}
+        const double l = OCC_DADD(OCC_DMUL((double)c.y, l_occ), OCC_DMUL((double)c.x, l_free));
+        out[i] = (float)fmin(fmax(l, l_min), l_max);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -383,6 +422,10 @@ int integrate_packets_tiled(const occgrid_geom* geom, const uint8_t* d_packets, 
                             int n_agents, int8_t* d_grid, void* d_ws, size_t ws_bytes, uint64_t* d_counters,
                             cudaStream_t st);
 bool tiled_supported(const occgrid_geom* geom);
+int accumulate_packets_tiled(const occgrid_geom* geom, const uint8_t* d_packets, int64_t n, int stride,
+                             const int32_t* d_agent_idx, const double* d_drift, const double* d_agent_off,
+                             int n_agents, int32_t* d_counts, void* d_ws, size_t ws_bytes, uint64_t* d_counters,
+                             cudaStream_t st);
 void set_raycast_cta_cap(int cap);
 int integrate_poses_tiled(const occgrid_geom* geom, const void* d_poses, int64_t n, int ordinals_in_records, int8_t* d_grid,
                           void* d_ws, size_t ws_bytes, uint64_t* d_counters, cudaStream_t st);
@@ -446,6 +489,54 @@ int occgrid_integrate_packets(const occgrid_geom* geom, const uint8_t* d_packets
     }
     set_last_error("unknown strategy %d", strategy);
     return OCCGRID_E_ARG;
+}
+
+int occgrid_accumulate_packets(const occgrid_geom* geom, const uint8_t* d_packets, int64_t n, int stride, int rec_len,
+                               const int32_t* d_agent_idx, const double* d_drift, const double* d_agent_off,
+                               int n_agents, int32_t* d_counts, void* d_workspace, size_t workspace_bytes,
+                               uint64_t* d_counters, int strategy, void* stream) {
+    int rc = validate_geom(geom);
+    if (rc != OCCGRID_OK) return rc;
+    if (n < 0 || n > (1ll << 29) - 1) { set_last_error("n=%lld outside 0..2^29-1 records per call", (long long)n); return OCCGRID_E_ARG; }
+    if (rec_len != OCCGRID_PACKET_SIZE && rec_len != OCCGRID_PACKET_SIZE_V1) {
+        set_last_error("rec_len must be 42 or 41, got %d", rec_len);
+        return OCCGRID_E_ARG;
+    }
+    if (stride < rec_len || stride > kMaxStride) { set_last_error("stride %d outside %d..%d", stride, rec_len, kMaxStride); return OCCGRID_E_ARG; }
+    if (n_agents < 1 || !d_agent_off) { set_last_error("need n_agents >= 1 and an agent offset table"); return OCCGRID_E_ARG; }
+    if (!d_counts || (reinterpret_cast<uintptr_t>(d_counts) & 7) || !d_workspace) { set_last_error("counts (8-byte aligned) / workspace is NULL"); return OCCGRID_E_ARG; }
+    if (n == 0) return OCCGRID_OK;
+    if (!d_packets) { set_last_error("packets is NULL"); return OCCGRID_E_ARG; }
+    const int s = pick_strategy(geom, strategy);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s == OCCGRID_STRATEGY_TILED) {
+        if (!tiled_supported(geom)) { set_last_error("TILED strategy does not support this geometry"); return OCCGRID_E_RANGE; }
+        return accumulate_packets_tiled(geom, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents, d_counts,
+                                        d_workspace, workspace_bytes, d_counters, st);
+    }
+    if (s != OCCGRID_STRATEGY_GLOBAL_ATOMIC) { set_last_error("unknown strategy %d", strategy); return OCCGRID_E_ARG; }
+    const long long blocks = (n + kThreads - 1) / kThreads;
+    {
+        ProfileScope ps(K_INTEGRATE_GLOBAL, st);
+        k_integrate_global<true><<<(unsigned int)blocks, kThreads, 0, st>>>(to_geom(geom), d_packets, n, stride, d_agent_idx, d_drift,
+                                                                           d_agent_off, n_agents, reinterpret_cast<unsigned int*>(d_counts),
+                                                                           d_counters);
+    }
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
+}
+
+int occgrid_counts_to_logodds(const int32_t* d_counts, int64_t n_cells, double l_occ, double l_free, double l_min, double l_max,
+                              float* d_logodds, void* stream) {
+    if (!d_counts || !d_logodds || n_cells < 0 || !(l_min <= l_max)) { set_last_error("occgrid_counts_to_logodds: bad arguments"); return OCCGRID_E_ARG; }
+    if (n_cells == 0) return OCCGRID_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    long long blocks = (n_cells + kThreads - 1) / kThreads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    ProfileScope ps(K_RESOLVE, st);
+    k_counts_to_logodds<<<(unsigned int)blocks, kThreads, 0, st>>>(d_counts, n_cells, l_occ, l_free, l_min, l_max, d_logodds);
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
 }
 
 int occgrid_integrate_poses(const occgrid_geom* geom, const void* d_pose_recs, int64_t n, int ordinals_in_records,

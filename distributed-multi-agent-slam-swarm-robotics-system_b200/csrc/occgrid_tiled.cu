@@ -388,6 +388,46 @@ __device__ __forceinline__ void draw_beam_smem(unsigned int* __restrict__ s_win,
     if (hit && !(n == 0 && skip_first) && (unsigned int)x < us && (unsigned int)y < us) atomicMax(&s_win[y * pitch + x], free_stamp | 1u);
 }
 
+// Hit/miss COUNT mode (extension): the same walk, but every cell update_ray (:148-156)
+// would have stored FREE to counts one miss (low half of the window word) and the OCCUPIED end
+// cell of a valid hit counts one hit (high half).  A work item holds <= 4 * kChunkPk beams and a
+// beam visits a cell once, so 16 bits per half cannot overflow.
+__device__ __forceinline__ void count_beam_smem(unsigned int* __restrict__ s_win, int side, int pitch, int x, int y,
+                                                int ddx, int ddy, bool hit) {
+    const int dx = abs(ddx), dy = abs(ddy);
+    const int n = max(dx, dy);
+    const unsigned int us = (unsigned int)side;
+    if ((unsigned int)x < us && (unsigned int)y < us && (unsigned int)(x + ddx) < us && (unsigned int)(y + ddy) < us) {
+        const int sxo = ddx > 0 ? 1 : -1;
+        const int syo = ddy > 0 ? pitch : -pitch;
+        const bool xmajor = dx >= dy;
+        const int dmaj = xmajor ? dx : dy, dmin = xmajor ? dy : dx;
+        const int step_maj = xmajor ? sxo : syo;
+        const int step_both = sxo + syo;
+        const int e_minor = dmaj - dmin;
+        int E = dmaj - dmin;
+        int off = y * pitch + x;
+        for (int i = 0; i < n; ++i) {
+            atomicAdd(&s_win[off], 1u);
+            const bool minor = 2 * E < dmaj;
+            off += minor ? step_both : step_maj;
+            E += minor ? e_minor : -dmin;
+        }
+        if (hit) atomicAdd(&s_win[off], 0x10000u);
+        return;
+    }
+    int err = dx - dy;
+    const int sx = ddx > 0 ? 1 : -1, sy = ddy > 0 ? 1 : -1;
+    for (int i = 0; i < n; ++i) {
+        if ((unsigned int)x < us && (unsigned int)y < us) atomicAdd(&s_win[y * pitch + x], 1u);
+        const int e2 = 2 * err;
+        if (e2 > -dy) { err -= dy; x += sx; }
+        if (e2 < dx)  { err += dx; y += sy; }
+    }
+    if (hit && (unsigned int)x < us && (unsigned int)y < us) atomicAdd(&s_win[y * pitch + x], 0x10000u);
+}
+
+template <bool kCounts>
 __global__ void __launch_bounds__(kTT)
 k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHeader* __restrict__ hdr,
                const unsigned int* __restrict__ bins, const PoseRec* __restrict__ recs, int ordinals_in_records,
@@ -426,8 +466,12 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
                 c[1] += b[s].slow;
                 if (b[s].x0 >= g.win_x0 && b[s].x0 < g.win_x0 + g.win_w && b[s].y0 >= g.win_y0 && b[s].y0 < g.win_y0 + g.win_h)
                     c[2] += cells;
-                draw_beam_smem(s_win, side, pitch, b[s].x0 - wx0, b[s].y0 - wy0, b[s].x1 - b[s].x0, b[s].y1 - b[s].y0,
-                               (k * 4u + (unsigned int)s + 1u) << 1, b[s].hit != 0, later_writes_first);
+                if (kCounts)
+                    count_beam_smem(s_win, side, pitch, b[s].x0 - wx0, b[s].y0 - wy0, b[s].x1 - b[s].x0, b[s].y1 - b[s].y0,
+                                    b[s].hit != 0);
+                else
+                    draw_beam_smem(s_win, side, pitch, b[s].x0 - wx0, b[s].y0 - wy0, b[s].x1 - b[s].x0, b[s].y1 - b[s].y0,
+                                   (k * 4u + (unsigned int)s + 1u) << 1, b[s].hit != 0, later_writes_first);
                 later_writes_first = later_writes_first || (cells > 1 || b[s].hit);
             }
         }
@@ -442,7 +486,12 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
                 unsigned int* out = stamps + (size_t)(wy0 + ly - g.win_y0) * g.win_w + (wx0 - g.win_x0);
                 for (int lx = lx_lo + lane; lx < lx_hi; lx += 32) {
                     const unsigned int v = row[lx];
-                    if (v) atomicMax(out + lx, v);
+                    if (!v) continue;
+                    if (kCounts)     // {miss, hit} int32 pair of the cell: one 64-bit add (the halves cannot carry into each other)
+                        atomicAdd(reinterpret_cast<unsigned long long*>(stamps) + ((size_t)(wy0 + ly - g.win_y0) * g.win_w + (wx0 - g.win_x0) + lx),
+                                  ((unsigned long long)(v >> 16) << 32) | (unsigned long long)(v & 0xffffu));
+                    else
+                        atomicMax(out + lx, v);
                 }
             }
         }
@@ -551,7 +600,7 @@ size_t tiled_workspace_bytes(const occgrid_geom* geom, int64_t max_packets) {
 int integrate_tiled(const occgrid_geom* geom, const uint8_t* d_packets, const PoseRec* d_poses, int ordinals_in_records,
                     int64_t n, int stride,
                     const int32_t* d_agent_idx, const double* d_drift, const double* d_agent_off,
-                    int n_agents, int8_t* d_grid, void* d_ws, size_t ws_bytes, uint64_t* d_counters,
+                    int n_agents, int8_t* d_grid, int32_t* d_counts, void* d_ws, size_t ws_bytes, uint64_t* d_counters,
                     cudaStream_t st) {
     const TiledLayout L = tiled_layout(geom, n);
     if (ws_bytes < L.total) {
@@ -580,11 +629,14 @@ int integrate_tiled(const occgrid_geom* geom, const uint8_t* d_packets, const Po
     }
     static thread_local size_t configured_smem = 0;
     if (win_bytes > configured_smem) {
-        OCC_CUDA_TRY(cudaFuncSetAttribute(k_home_raycast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_bytes));
+        OCC_CUDA_TRY(cudaFuncSetAttribute(k_home_raycast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_bytes));
+        OCC_CUDA_TRY(cudaFuncSetAttribute(k_home_raycast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_bytes));
         configured_smem = win_bytes;
     }
     int ctas_per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_home_raycast, kTT, win_bytes) != cudaSuccess || ctas_per_sm < 1)
+    const cudaError_t occ_rc = d_counts ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_home_raycast<true>, kTT, win_bytes)
+                                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_home_raycast<false>, kTT, win_bytes);
+    if (occ_rc != cudaSuccess || ctas_per_sm < 1)
         ctas_per_sm = 1;
     if (g_raycast_cta_cap > 0 && ctas_per_sm > g_raycast_cta_cap) ctas_per_sm = g_raycast_cta_cap;
     {
@@ -607,10 +659,14 @@ int integrate_tiled(const occgrid_geom* geom, const uint8_t* d_packets, const Po
     }
     {
         ProfileScope ps(K_TILE_RAYCAST, st);
-        k_home_raycast<<<sms * ctas_per_sm, kTT, win_bytes, st>>>(g, tg, items, hdr, bins, recs, ordinals_in_records, stamps,
-                                                                  d_counters);
+        if (d_counts)
+            k_home_raycast<true><<<sms * ctas_per_sm, kTT, win_bytes, st>>>(g, tg, items, hdr, bins, recs, ordinals_in_records,
+                                                                            reinterpret_cast<unsigned int*>(d_counts), d_counters);
+        else
+            k_home_raycast<false><<<sms * ctas_per_sm, kTT, win_bytes, st>>>(g, tg, items, hdr, bins, recs, ordinals_in_records, stamps,
+                                                                             d_counters);
     }
-    {
+    if (!d_counts) {
         ProfileScope ps(K_TILE_RESOLVE, st);
         k_home_resolve<<<sms * 8, kTT, 0, st>>>(g, tg, active, hdr, stamps, d_grid);
     }
@@ -622,7 +678,15 @@ int integrate_packets_tiled(const occgrid_geom* geom, const uint8_t* d_packets, 
                             const int32_t* d_agent_idx, const double* d_drift, const double* d_agent_off,
                             int n_agents, int8_t* d_grid, void* d_ws, size_t ws_bytes, uint64_t* d_counters,
                             cudaStream_t st) {
-    return integrate_tiled(geom, d_packets, nullptr, 0, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents, d_grid, d_ws,
+    return integrate_tiled(geom, d_packets, nullptr, 0, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents, d_grid, nullptr, d_ws,
+                           ws_bytes, d_counters, st);
+}
+
+int accumulate_packets_tiled(const occgrid_geom* geom, const uint8_t* d_packets, int64_t n, int stride,
+                             const int32_t* d_agent_idx, const double* d_drift, const double* d_agent_off,
+                             int n_agents, int32_t* d_counts, void* d_ws, size_t ws_bytes, uint64_t* d_counters,
+                             cudaStream_t st) {
+    return integrate_tiled(geom, d_packets, nullptr, 0, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents, nullptr, d_counts, d_ws,
                            ws_bytes, d_counters, st);
 }
 
@@ -630,7 +694,7 @@ int integrate_poses_tiled(const occgrid_geom* geom, const void* d_poses, int64_t
                           void* d_ws, size_t ws_bytes, uint64_t* d_counters, cudaStream_t st) {
     return integrate_tiled(geom, nullptr, reinterpret_cast<const PoseRec*>(d_poses), ordinals_in_records, n, 0, nullptr, nullptr,
                            nullptr, 0,
-                           d_grid, d_ws, ws_bytes, d_counters, st);
+                           d_grid, nullptr, d_ws, ws_bytes, d_counters, st);
 }
 
 }  // namespace occ

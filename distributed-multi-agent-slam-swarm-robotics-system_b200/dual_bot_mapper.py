@@ -356,12 +356,62 @@ class OccupancyGrid:
             if agent_idx is not None:
                 a = torch.as_tensor(agent_idx, dtype=torch.int32).reshape(n).to(self.device, non_blocking=True).contiguous()
                 a_ptr = a.data_ptr()
+            if self._accumulating:          # hit/miss count planes instead of the last-writer-wins grid
+                rc = self._lib.occgrid_accumulate_packets(
+                    self._geom, pk.data_ptr(), n, stride, rec_len, a_ptr, d_ptr, tab.data_ptr(), tab.shape[0] - 1,
+                    self.counts_tensor.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                    self._counters.data_ptr(), self._strategy, self._stream())
+                _native.check(rc, 'occgrid_accumulate_packets')
+                return
             rc = self._lib.occgrid_integrate_packets(
                 self._geom, pk.data_ptr(), n, stride, rec_len, a_ptr, d_ptr, tab.data_ptr(), tab.shape[0] - 1,
                 self.grid_tensor.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
                 self._counters.data_ptr(), self._strategy, self._stream())
             _native.check(rc, 'occgrid_integrate_packets')
         self._host_cache = None
+
+    # ---- extension: hit/miss counts and log-odds (no reference counterpart) -------------------
+    _accumulating = False
+    _counts = None
+
+    @property
+    def counts_tensor(self):
+        """int32 [h, w, 2] device tensor, ``[..., 0]`` misses, ``[..., 1]`` hits (allocated on first use)."""
+        if self._counts is None:
+            h, w = self.grid_tensor.shape
+            self._counts = torch.zeros((h, w, 2), dtype=torch.int32, device=self.device)
+        return self._counts
+
+    def accumulate_packets(self, packets, separation=0.0, drift=None, agent_offsets=None, agent_idx=None, rec_len=PACKET_SIZE):
+        """EXTENSION (north-star wording; the reference keeps no counts): same decode, pose
+        correction, beam expansion, ``_bresenham`` cells and per-cell clipping as
+        ``update_packets``, but instead of storing FREE / OCCUPIED (:148-156) every FREE store
+        counts one miss and every OCCUPIED store one hit.  Integer adds commute, so the planes
+        equal ``np.add.at`` over the reference's cells; they accumulate across calls."""
+        self._accumulating = True
+        try:
+            self.update_packets(packets, separation=separation, drift=drift, agent_offsets=agent_offsets,
+                                agent_idx=agent_idx, rec_len=rec_len)
+        finally:
+            self._accumulating = False
+
+    hit_counts = property(lambda self: self.counts_tensor[..., 1].cpu().numpy())
+    miss_counts = property(lambda self: self.counts_tensor[..., 0].cpu().numpy())
+
+    def reset_counts(self):
+        if self._counts is not None:
+            self._counts.zero_()
+
+    def log_odds(self, l_occ=0.85, l_free=-0.4, l_min=-2.0, l_max=3.5, to_host=True):
+        """float32 [h, w]: clamp(hits * l_occ + misses * l_free, l_min, l_max), evaluated from the
+        integer planes (order-independent; within 1e-5 of a float64 NumPy evaluation)."""
+        with torch.cuda.device(self.device):
+            h, w = self.grid_tensor.shape
+            out = torch.empty((h, w), dtype=torch.float32, device=self.device)
+            rc = self._lib.occgrid_counts_to_logodds(self.counts_tensor.data_ptr(), h * w, float(l_occ), float(l_free),
+                                                     float(l_min), float(l_max), out.data_ptr(), self._stream())
+            _native.check(rc, 'occgrid_counts_to_logodds')
+        return out.cpu().numpy() if to_host else out
 
     def update_poses(self, pose_recs, ordinals_in_records=False):
         """Integrate decoded records (uint8 cuda tensor [n, 48] of ``occgrid_pose_rec``) — the

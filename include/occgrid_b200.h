@@ -373,6 +373,23 @@ int occgrid_frontier_clusters(const int32_t* d_xy, const int64_t* d_count, int64
  * next batch finds room on every SM and runs concurrently.  Process-wide. */
 int occgrid_set_raycast_ctas_per_sm(int cap);
 
+/* EXTENSION beyond the reference (north-star wording "hit/miss log-odds"): instead of
+ * the last-writer-wins int8 grid, accumulate per-cell COUNTS over the same beams, cells and
+ * per-cell clipping: d_counts = int32 [win_h][win_w][2] = {misses, hits}; every cell update_ray
+ * (dual_bot_mapper.py:148-156) would have stored FREE to counts one miss, the OCCUPIED end cell of
+ * a valid hit one hit (a missed beam's end cell counts nothing, :153).  Integer adds commute: the
+ * planes are exactly np.add.at over the reference's _bresenham cells, whatever the order.
+ * Arguments as occgrid_integrate_packets; the counts accumulate across calls (zero them to reset).
+ * occgrid_counts_to_logodds: L = clamp(hits*l_occ + misses*l_free, l_min, l_max) as float32,
+ * evaluated in fp64 from the integer planes (no float atomics: order-independent). */
+int occgrid_accumulate_packets(const occgrid_geom* geom, const uint8_t* d_packets, int64_t n_records,
+                               int rec_stride, int rec_len, const int32_t* d_agent_idx,
+                               const double* d_drift_xy, const double* d_agent_offset_xy, int n_agents,
+                               int32_t* d_counts, void* d_workspace, size_t workspace_bytes,
+                               uint64_t* d_counters, int strategy, void* stream);
+int occgrid_counts_to_logodds(const int32_t* d_counts, int64_t n_cells, double l_occ, double l_free,
+                              double l_min, double l_max, float* d_logodds, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Host-side producer of the per-packet drift table (no GPU involved): the sequential half of
  * the ingest loop, dual_bot_mapper.py:826-857 + :908-914 with PoseGraphSLAM.add_pose /

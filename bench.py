@@ -410,6 +410,31 @@ def main():
                          'd2h_bytes_per_step': int(_native.N_COUNTERS * 8), 'steps': Ke,
                          'ms_per_step': e_ms / Ke,
                          'api': 'OccupancyGrid.update_packets(pinned host uint8[n,42]) + counters() read-back'}
+        # extension: hit/miss count planes (occgrid_accumulate_packets) over the same resident batches
+        counts = grid.counts_tensor
+        grid._counters.zero_()
+
+        def count_step(i):
+            pk = dpk[i % POOL]
+            rc = lib.occgrid_accumulate_packets(grid._geom, pk.data_ptr(), pk.shape[0], 42, 42, None, None,
+                                                off.data_ptr(), AGENTS_PER_GPU, counts.data_ptr(), grid._ws.data_ptr(),
+                                                grid._ws.numel(), grid._counters.data_ptr(), grid._strategy, stream)
+            if rc != 0:
+                raise RuntimeError(_native.last_error())
+
+        for i in range(POOL):
+            count_step(i)
+        torch.cuda.synchronize()
+        grid._counters.zero_()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for i in range(K):
+            count_step(i)
+        c1.record()
+        torch.cuda.synchronize()
+        c_ms = c0.elapsed_time(c1)
+        result['count_mode'] = {'value': grid.counters(reset=True)['updates'] / (c_ms * 1e-3), 'unit': UNIT, 'ms_per_step': c_ms / K,
+                                'what': 'extension: int32 hit/miss planes (atomic adds) instead of the last-writer-wins int8 grid'}
         if not args.no_cpu:
             result['cpu_baseline'] = cpu_baseline(s0, 1, 500_000)     # ~10 s of the reference's Python loop on one core
             result['cpu_baseline_c_port'] = c_port_rate(s0)

@@ -320,7 +320,6 @@ k_batch_write(const unsigned long long* __restrict__ masks, long long n_cells, i
     const BatchXform t = T[a];
     if (!t.use || agent_offset[gridDim.y] > capacity) return;
     const long long chunk_base = (long long)blockIdx.x * kChunk;
-    const long long base = chunk_base + (long long)threadIdx.x * kCellsPerThread;
     const unsigned long long mask = masks[((size_t)a * blocks_per_grid + blockIdx.x) * kMT + threadIdx.x];   // 1 bit per cell, from the count pass
     unsigned int total;
     unsigned int off = block_exclusive_scan(__popcll(mask), s_warp, &total);

@@ -230,7 +230,8 @@ int mapmerge_extract_transform(const int8_t* d_grid, int32_t width, int32_t heig
  * _write: T_host (HOST, [A][16] row-major or NULL) and use_host (HOST, [A] or NULL: 0 = skip the
  * agent) describe the callbacks; the transformed points land in d_px/d_py agent after agent and
  * d_agent_offset[a] = start of agent a's slice (d_agent_offset[A] = total).  d_xforms is scratch
- * (A * 96 bytes); the workspace must be the one _count filled.  The sequential chain appends
+ * (A * 96 bytes); the workspace must be the one _count filled, untouched: it carries the block
+ * counts and one occupancy bit per cell, so _write does not read the grids again.  The sequential chain appends
  * slice a with mapmerge_append_slice when callback a's turn comes (:59). */
 size_t mapmerge_extract_batch_workspace_bytes(int64_t n_cells, int n_agents);
 int mapmerge_extract_batch_count(const int8_t* const* d_grids, int n_agents, int32_t width, int32_t height,

@@ -216,6 +216,8 @@ def main():
                     help='N>1: map side = this x N (8192 with --agents-per-gpu 128 at N=8 = BASELINE configs[3])')
     ap.add_argument('--agents-per-gpu', type=int, default=AGENTS_PER_GPU)
     ap.add_argument('--raycast-ctas', type=int, default=0, help='cap persistent raycast CTAs per SM (0 = max)')
+    ap.add_argument('--ingest', default='uniform', choices=['uniform', 'affine'],
+                    help='N>1: which agents a rank receives (uniform = all agents, the worst case; affine = the agents of its band)')
     ap.add_argument('--exchange', default='auto', choices=['auto', 'p2p', 'nccl'],
                     help='N>1: routed records via peer-memory stores from the routing kernel (p2p) or NCCL all-to-all')
     args = ap.parse_args()
@@ -267,7 +269,7 @@ def main():
         from occgrid_b200.distributed import TiledSwarmMap, make_rank_sessions
         tmap, sessions, step = make_rank_sessions(n, rank, dev, npk, POOL, args.strategy,
                                                    grid_per_gpu=args.grid_per_gpu, agents_per_gpu=args.agents_per_gpu,
-                                                   exchange=args.exchange)
+                                                   exchange=args.exchange, ingest=args.ingest)
         grid = tmap.local
 
     # warm-up (at least one pass over every batch of the pool, so that no allocation or
@@ -364,6 +366,7 @@ def main():
     }
     if n > 1:
         result['exchange'] = tmap.exchange
+        result['ingest'] = args.ingest
 
     # ---- single-GPU extras: scatter roofline, e2e, cpu baseline ------------------------------
     if n == 1:

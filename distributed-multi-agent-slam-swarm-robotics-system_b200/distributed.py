@@ -446,9 +446,12 @@ class ShardedMapMerger:
 # ----------------------------------------------------------------------------------------------
 
 def make_rank_sessions(world, rank, device, packets_per_rank, pool, strategy, pipeline=True,
-                       grid_per_gpu=4096, agents_per_gpu=64, exchange='auto'):
+                       grid_per_gpu=4096, agents_per_gpu=64, exchange='auto', ingest='uniform'):
     """Weak scaling of BASELINE configs[1]: (4096*world)^2 map, 64*world agents, each rank ingests
-    its own `packets_per_rank` share.  Returns (TiledSwarmMap, sessions, step_fn)."""
+    its own `packets_per_rank` share.  ``ingest='uniform'`` (default, the worst case): every
+    rank's share covers ALL agents, so (world-1)/world of the records are routed to another GPU;
+    ``'affine'``: a rank receives the agents that drive inside its own band (only rays crossing a
+    band edge are routed).  Returns (TiledSwarmMap, sessions, step_fn)."""
     from . import simulation_tools as st
     side = grid_per_gpu * world
     origin = (-side * 0.05 / 2.0,) * 2
@@ -457,8 +460,15 @@ def make_rank_sessions(world, rank, device, packets_per_rank, pool, strategy, pi
     sessions = []
     for i in range(pool):
         # this rank's share of the stream: all 64*world agents, `packets_per_rank` records
-        sh = st.generate_session(n_agents=agents_per_gpu * world, n_packets=packets_per_rank, grid_size=side,
-                                 origin=origin, seed=1000 + 97 * i + rank)
+        if ingest == 'affine':
+            # this rank's own agents, their rooms on a lattice inside the band it owns
+            y0 = tmap.layout.window(rank)[1]
+            sh = st.generate_session(n_agents=agents_per_gpu, n_packets=packets_per_rank, grid_size=grid_per_gpu,
+                                     origin=(origin[0], origin[1] + y0 * 0.05),
+                                     seed=1000 + 97 * i + rank)
+        else:
+            sh = st.generate_session(n_agents=agents_per_gpu * world, n_packets=packets_per_rank, grid_size=side,
+                                     origin=origin, seed=1000 + 97 * i + rank)
         sessions.append({'packets': tmap.ops.stage(sh['packets']),
                          'agent_idx': torch.from_numpy(sh['agent_idx']).to(device),
                          'agent_offsets': torch.from_numpy(sh['agent_offsets']).to(device), 'grid': sh['grid']})

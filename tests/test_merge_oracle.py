@@ -77,3 +77,24 @@ def test_sequence_is_deterministic_and_only_unknown_or_occupied():
         outs.append(out)
     assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
     assert set(np.unique(outs[0][0])) == {-1, 100}
+
+
+def test_host_transform_normalisation_matches_oracle_matrices():
+    """MapMerger.merge accepts [A,4,4], [A,3] (tx, ty, theta), None or a mixed list; the matrices it
+    hands to the device must be the oracle's se2_matrix bit for bit (cos/sin from the same libm)."""
+    pytest = __import__('pytest')
+    pytest.importorskip('torch')
+    from occgrid_b200.map_merger import MapMerger, se2_matrix
+    from oracle import merge_oracle as MO
+    import numpy as np
+    r = np.random.default_rng(3)
+    p = r.uniform(-5, 5, (6, 3))
+    want = np.stack([MO.se2_matrix(*row) for row in p])
+    assert np.array_equal(MapMerger._as_matrices(p, 6), want)
+    assert np.array_equal(MapMerger._as_matrices(want, 6), want)
+    assert np.array_equal(MapMerger._as_matrices(None, 3), np.tile(np.eye(4), (3, 1, 1)))
+    mixed = [tuple(p[0]), want[1], None, p[3], want[4].ravel(), tuple(p[5])]
+    got = MapMerger._as_matrices(mixed, 6)
+    want[2] = np.eye(4)
+    assert np.array_equal(got, want) and got.flags['C_CONTIGUOUS'] and got.dtype == np.float64
+    assert np.array_equal(se2_matrix(*p[2]), MO.se2_matrix(*p[2]))

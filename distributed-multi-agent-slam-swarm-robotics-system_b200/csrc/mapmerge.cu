@@ -741,8 +741,9 @@ k_chain_slice_bounds(const double* __restrict__ sx, const double* __restrict__ s
 
 // LM[k] = {index + 1 of the cloud point in voxel k (0: none), top of this callback's stack}
 //
-// The three phases of a callback run inside ONE persistent kernel (cooperative launch, every CTA
-// resident) separated by grid-wide barriers, and the kernel loops over up to n_callbacks
+// The phases of a callback run inside ONE persistent kernel (cooperative launch, every CTA
+// resident) separated by grid-wide barriers (two per callback: the next slice is linked while the
+// current one is appended), and the kernel loops over up to n_callbacks
 // callbacks: a phase is a few microseconds of latency-bound work on ~6e4 points, so kernel
 // boundaries would cost as much as the work.  Every CTA keeps its own copy of the cursor and the
 // cloud size (they evolve identically everywhere); CTA 0 publishes them for the host.
@@ -896,24 +897,35 @@ k_chain_persistent(const ChainRun p) {
     if (!h->stalled) {
         int cur = h->cursor;
         long long n_g = *p.d_count;
-        for (int it = 0; it < p.n_callbacks && cur < p.n_order; ++it) {
+        const double mbx = h->mbx, mby = h->mby;       // the anchor LM is valid for: every callback that runs uses exactly it
+        double nmbx, nmby;
+        // The first callback of a launch is decided and linked on its own; after that the NEXT
+        // slice is linked speculatively (under the unchanged anchor) in the same phase that appends
+        // the current one, so a callback costs two grid barriers.  The decision follows at the
+        // barrier; a callback that may not run has its stacks unlinked again.
+        bool linked = false;
+        if (p.n_callbacks > 0 && cur < p.n_order) {
             const int agent = p.order[cur];
-            double mbx, mby;
-            const int need = chain_decide(h, p.slice_benc + 4 * agent, p.voxel, p.W, p.H, &mbx, &mby);
+            const int need = chain_decide(h, p.slice_benc + 4 * agent, p.voxel, p.W, p.H, &nmbx, &nmby);
             if (need != CHAIN_RUN) {                   // every CTA reaches the same verdict; CTA 0 records it
                 if (blockIdx.x == 0 && threadIdx.x == 0) {
                     h->stalled = need;
                     if (need == CHAIN_OVERFLOW) atomicOr(p.status, ST_LATTICE_OVERFLOW);
                 }
-                break;
+            } else {
+                const long long b = p.agent_offset[agent];
+                chain_link(p, b, p.agent_offset[agent + 1] - b, mbx, mby);
+                grid_barrier(p.bar, target);
+                linked = true;
             }
+        }
+        for (int it = 0; linked; ++it) {
+            const int agent = p.order[cur];
             const long long b = p.agent_offset[agent], n = p.agent_offset[agent + 1] - b;
             unsigned int* bc = p.blockcount + (size_t)(it & 1) * p.bc_stride;
             unsigned int* bc_other = p.blockcount + (size_t)((it & 1) ^ 1) * p.bc_stride;
-            if (blockIdx.x == 0)                       // the previous callback's counters: nobody reads them any more
+            if (blockIdx.x == 0 && it > 0)             // the previous callback's counters: its append phase is over
                 for (int q = threadIdx.x; q < p.bc_stride; q += kMT) bc_other[q] = 0u;
-            chain_link(p, b, n, mbx, mby);
-            grid_barrier(p.bar, target);
             chain_fold(p, b, n, mbx, mby, bc);
             grid_barrier(p.bar, target);
             const unsigned int added = chain_append(p, n, n_g, mbx, mby, bc, s_warp);
@@ -922,7 +934,27 @@ k_chain_persistent(const ChainRun p) {
             cur += 1;
             done = it + 1;
             if (blockIdx.x == 0 && threadIdx.x == 0) { *p.d_count = n_g; h->cursor = cur; }
+            const bool more = it + 1 < p.n_callbacks && cur < p.n_order;
+            int next_agent = 0;
+            long long nb = 0, nn = 0;
+            if (more) {                                // append touches LM[].x, flags and the cloud; link touches LM[].y, lkey, next
+                next_agent = p.order[cur];
+                nb = p.agent_offset[next_agent];
+                nn = p.agent_offset[next_agent + 1] - nb;
+                chain_link(p, nb, nn, mbx, mby);
+            }
             grid_barrier(p.bar, target);               // bounds / flags of this callback feed the next decision
+            if (!more) break;
+            const int need = chain_decide(h, p.slice_benc + 4 * next_agent, p.voxel, p.W, p.H, &nmbx, &nmby);
+            if (need != CHAIN_RUN) {
+                for (long long j = (long long)blockIdx.x * kMT + threadIdx.x; j < nn; j += (long long)gridDim.x * kMT)
+                    p.LM[p.lkey[j]].y = 0u;            // unlink: the host deals with this callback
+                if (blockIdx.x == 0 && threadIdx.x == 0) {
+                    h->stalled = need;
+                    if (need == CHAIN_OVERFLOW) atomicOr(p.status, ST_LATTICE_OVERFLOW);
+                }
+                break;
+            }
         }
     }
     // leave the counters and the barrier clean for the next launch

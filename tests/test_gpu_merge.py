@@ -7,7 +7,7 @@ import math
 import numpy as np
 import pytest
 
-from merge_util import synth_agent_grid
+from merge_util import load_merge_ref, synth_agent_grid
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip('torch')
@@ -260,3 +260,90 @@ def test_sharded_merger_single_rank_equals_merge(MM):
     assert np.array_equal(got, want[0]) and origin == want[1]
     got2, origin2 = MM.MapMerger().merge(grids, origins, 0.05, tf)
     assert np.array_equal(got2, want[0]) and origin2 == want[1]
+
+
+# ---- fixtures produced by EXECUTING the unmodified reference (oracle/make_golden_merge.py) --------
+@pytest.mark.parametrize('seq', ['A', 'B', 'C'])
+def test_callbacks_equal_reference_executed_fixture(MM, seq):
+    """tests/golden/merge_ref.npz: the reference's own map_callback / grid_to_pcd /
+    publish_global_map ran on these grids.  Every callback on the device must return early where
+    the reference did, hold the same cloud (fp64 bit for bit, same order), keep the same
+    map_resolution / map_origin and publish the same int8 grid and origin."""
+    steps = load_merge_ref()[seq]
+    m = MM.MapMerger()
+    for k, s in enumerate(steps):
+        g = s['grid']
+        h, w = g.shape
+        res, ox, oy = s['geom'].tolist()
+        msg = MM.make_grid_msg(g.ravel(), w, h, res, ox, oy)
+        pts = m.grid_to_pcd(msg)                                             # a10 (:64-85)
+        assert np.array_equal(pts, s['pcd'].reshape(-1, 3)), k
+        got = m.map_callback(msg, k + 1, transform=s['T'], fitness=float(s['fitness']))
+        assert (got is not None) == bool(s['published']), k
+        assert np.array_equal(m.global_pcd[:, :2], s['cloud']), k
+        assert [m.map_resolution] + list(m.map_origin) == s['state'].tolist(), k
+        if got is not None:                                                  # a12 (:87-127)
+            assert got.header.frame_id == 'map_global'
+            assert (got.info.height, got.info.width) == s['out'].shape and got.info.resolution == float(s['out_res'])
+            assert np.array_equal(got.data, s['out']), k
+            assert [got.info.origin.position.x, got.info.origin.position.y] == s['out_origin'].tolist(), k
+
+
+@pytest.mark.parametrize('seq', ['A', 'C'])
+def test_batched_merge_equals_reference_executed_fixture(MM, seq):
+    """The batched entry (one extraction launch + incremental chain) must end where the
+    reference's callback sequence ended."""
+    steps = load_merge_ref()[seq]
+    grids = np.stack([s['grid'] for s in steps])
+    origins = np.stack([s['geom'][1:] for s in steps])
+    tf = np.stack([s['T'] for s in steps])
+    fit = np.array([float(s['fitness']) for s in steps])
+    m = MM.MapMerger()
+    out, origin = m.merge(grids, origins, float(steps[0]['geom'][0]), tf, fitness=fit)
+    last = [s for s in steps if bool(s['published'])][-1]
+    assert np.array_equal(out, last['out']) and list(origin) == last['out_origin'].tolist()
+    assert np.array_equal(m.global_pcd[:, :2], steps[-1]['cloud'])
+
+
+def test_publish_equals_reference_on_handmade_clouds(MM):
+    """publish_global_map (:87-127) alone: ceil + 1 extents, astype(int) truncation and clipping
+    on clouds that never went through a grid."""
+    for case in load_merge_ref()['P']:
+        pts = case['points']
+        m = MM.MapMerger()
+        m._ensure_capacity(len(pts))
+        m._cloud.x[:len(pts)].copy_(torch.from_numpy(pts[:, 0].copy()))
+        m._cloud.y[:len(pts)].copy_(torch.from_numpy(pts[:, 1].copy()))
+        m._cloud.count.fill_(len(pts))
+        m._n_global = len(pts)
+        m.map_resolution = float(case['res'])
+        got = m.publish_global_map('map')
+        assert np.array_equal(got.data, case['out'])
+        assert [got.info.origin.position.x, got.info.origin.position.y] == case['out_origin'].tolist()
+
+
+def test_icp_callbacks_against_reference_driven_fixture(MM):
+    """Sequence D: the reference's map_callback called registration_icp itself (restated Open3D
+    algorithm) on partial views.  MapMerger(registration='icp') must accept the same callbacks,
+    find the same correspondence counts, and publish the same map up to the cells a <= 1e-9 m
+    difference in the estimated transform can move across a cell edge."""
+    ref = load_merge_ref()
+    steps, calls = ref['D'], ref['D_meta']['icp_calls']
+    m = MM.MapMerger(registration='icp')
+    j = 0
+    for k, s in enumerate(steps):
+        g = s['grid']
+        h, w = g.shape
+        res, ox, oy = s['geom'].tolist()
+        got = m.map_callback(MM.make_grid_msg(g.ravel(), w, h, res, ox, oy), k + 1)
+        assert (got is not None) == bool(s['published'])
+        if k:
+            reg = m.last_registration
+            assert reg.fitness == calls[j, 3] and reg.correspondences == round(calls[j, 3] * calls[j, 0])
+            j += 1
+        pc = m.global_pcd[:, :2]
+        assert pc.shape == s['cloud'].shape
+        assert np.abs(pc - s['cloud']).max() < 1e-8
+        assert got.data.shape == s['out'].shape
+        assert (got.data != s['out']).mean() < 1e-3
+        assert np.abs(np.array([got.info.origin.position.x, got.info.origin.position.y]) - s['out_origin']).max() < 1e-8

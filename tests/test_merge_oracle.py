@@ -1,11 +1,15 @@
 """CPU checks of the merge oracle (restatement of server_nodes/map_merger.py:35-127).
-PARITY UNPINNED vs the real reference (rclpy/Open3D absent); these tests pin the
-restatement's own invariants and the verbatim NumPy lines."""
+
+Pinned by execution for the reference's own code: tests/golden/merge_ref.npz was produced by
+running the UNMODIFIED map_merger.py (grid_to_pcd :64-85, map_callback :35-62,
+publish_global_map :87-127) under rclpy / nav_msgs / open3d stubs (oracle/make_golden_merge.py).
+The arithmetic inside Open3D's transform / += / voxel_down_sample / registration_icp stays a
+restatement of the published algorithm (the library is absent and un-pinned)."""
 import math
 
 import numpy as np
 
-from merge_util import synth_agent_grid
+from merge_util import load_merge_ref, synth_agent_grid
 from oracle import merge_oracle as MO
 
 
@@ -98,3 +102,58 @@ def test_host_transform_normalisation_matches_oracle_matrices():
     want[2] = np.eye(4)
     assert np.array_equal(got, want) and got.flags['C_CONTIGUOUS'] and got.dtype == np.float64
     assert np.array_equal(se2_matrix(*p[2]), MO.se2_matrix(*p[2]))
+
+
+# ---- fixtures produced by executing the unmodified reference -------------------------------------
+def _replay_restatement(steps, icp=False):
+    from oracle import icp_oracle as IO
+    m = MO.OracleMerger()
+    for k, s in enumerate(steps):
+        g = s['grid']
+        h, w = g.shape
+        res, ox, oy = s['geom'].tolist()
+        px, py = MO.grid_to_points(g.ravel(), w, h, res, ox, oy)            # a10
+        assert np.array_equal(px, s['pcd'][:, 0]) and np.array_equal(py, s['pcd'][:, 1]), k
+        assert not s['pcd'][:, 2].any()
+        T, fit = s['T'], float(s['fitness'])
+        if icp and m.gx.size and px.size:
+            T, fit, _, _ = IO.registration_icp(px, py, m.gx, m.gy, 1.0, 30)
+        out = m.map_callback(g.ravel(), w, h, res, ox, oy, T, accept=fit >= 0.6)
+        assert (out is not None) == bool(s['published']), k
+        assert np.array_equal(m.gx, s['cloud'][:, 0]) and np.array_equal(m.gy, s['cloud'][:, 1]), k
+        assert [m.map_resolution] + list(m.map_origin) == s['state'].tolist(), k
+        if out is not None:
+            assert out[0].dtype == np.int8 and np.array_equal(out[0], s['out']), k
+            assert list(out[1]) == s['out_origin'].tolist() and m.map_resolution == float(s['out_res']), k
+    return m
+
+
+def test_restatement_equals_reference_executed_sequences():
+    """a10 / a11 sequencing / a12: every callback of sequences A (reject + empty), B (other
+    geometry, rectangular, empty first, fitness exactly 0.6) and C (heavy overlap) gives the
+    point list, the cloud, the node state and the published grid the reference produced."""
+    ref = load_merge_ref()
+    assert _replay_restatement(ref['A']).gx.size == ref['A'][-1]['cloud'].shape[0] > 1000
+    _replay_restatement(ref['B'])
+    _replay_restatement(ref['C'])
+    published = [bool(s['published']) for s in ref['A']]
+    assert published == [True, True, False, True, False, True, True]         # :54-56 and :37-38
+    assert ref['A_meta']['icp_calls'][:, 3].tolist() == [1.0, 0.59, 1.0, 1.0, 1.0]
+    assert not bool(ref['B'][0]['published']) and ref['B_meta']['icp_calls'][0, 3] == 0.6
+
+
+def test_restatement_equals_reference_driven_registration():
+    """Sequence D: the reference's own map_callback called registration_icp (restated) on the
+    clouds IT built; replaying with the restated ICP must reproduce every cloud and grid."""
+    ref = load_merge_ref()
+    _replay_restatement(ref['D'], icp=True)
+    calls = ref['D_meta']['icp_calls']
+    assert calls.shape == (3, 4) and (calls[:, 2] == 1.0).all() and (calls[:, 3] >= 0.6).all()
+
+
+def test_rasterise_equals_reference_publish_on_handmade_clouds():
+    ref = load_merge_ref()
+    for case in ref['P']:
+        g, origin = MO.rasterise(case['points'][:, 0], case['points'][:, 1], float(case['res']))
+        assert np.array_equal(g, case['out']) and list(origin) == case['out_origin'].tolist()
+    assert ref['P'][1]['out'].shape == (1, 1)

@@ -55,3 +55,39 @@ def test_slam_chain_random(ref):
                 int(rng.integers(0, 6)) if rng.random() < 0.4 else 0, float(k))
         assert a.add_pose(*args) == b.add_pose(*args)
     assert [tuple(c) for c in a.closures] == b.closures and len(b.closures) > 3
+
+
+@pytest.mark.parametrize('seed', [11, 12])
+def test_map_merger_live_reference_vs_restatement(seed):
+    """The unmodified server_nodes/map_merger.py (under rclpy / nav_msgs / open3d stubs) against
+    oracle/merge_oracle.OracleMerger on fresh random sequences: same early returns, clouds,
+    published grids and origins.  The Open3D arithmetic is the restatement on both sides; the
+    sequencing (:35-62) and the NumPy lines (:64-85, :87-127) are the reference's own."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from merge_util import synth_agent_grid
+    from oracle import merge_oracle as MO
+    mod, script = ref_loader.load_map_merger()
+    script.mode = 'script'
+    script.queue.clear()
+    rng = np.random.default_rng(seed)
+    node, o = mod.MapMerger(), MO.OracleMerger()
+    for a in range(6):
+        n = int(rng.integers(40, 120))
+        g = synth_agent_grid(n, seed * 50 + a) if rng.random() > 0.15 else np.full((n, n), 0, np.int8)
+        res, ox, oy = 0.05, float(rng.uniform(-5, 5)), float(rng.uniform(-5, 5))
+        T = MO.se2_matrix(*rng.uniform(-3, 3, 2), rng.uniform(-math.pi, math.pi))
+        fit = float(rng.choice([0.3, 0.6, 0.95]))
+        if not node.global_pcd.is_empty() and (g > 50).any():
+            script.queue.append((T, fit))
+        n_pub = len(node.published)
+        node.map_callback(ref_loader.make_ref_grid_msg(mod, g.ravel(), n, n, res, ox, oy), a + 1)
+        want = o.map_callback(g.ravel(), n, n, res, ox, oy, T, accept=fit >= 0.6)
+        assert (len(node.published) > n_pub) == (want is not None)
+        pts = np.asarray(node.global_pcd.points).reshape(-1, 3)
+        assert np.array_equal(pts[:, 0], o.gx) and np.array_equal(pts[:, 1], o.gy)
+        if want is not None:
+            m = node.published[-1]
+            assert np.array_equal(np.array(m.data, np.int8).reshape(m.info.height, m.info.width), want[0])
+            assert (m.info.origin.position.x, m.info.origin.position.y) == want[1]
+    assert not script.queue

@@ -218,7 +218,7 @@ def main():
     ap.add_argument('--raycast-ctas', type=int, default=0, help='cap persistent raycast CTAs per SM (0 = max)')
     ap.add_argument('--ingest', default='uniform', choices=['uniform', 'affine'],
                     help='N>1: which agents a rank receives (uniform = all agents, the worst case; affine = the agents of its band)')
-    ap.add_argument('--exchange', default='auto', choices=['auto', 'p2p', 'nccl'],
+    ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'],
                     help='N>1: routed records via peer-memory stores from the routing kernel (p2p) or NCCL all-to-all')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -13,7 +13,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_PATH = os.path.join(PKG_DIR, 'liboccgrid_b200.so')
-SOURCES = ['occgrid_integrate.cu', 'occgrid_tiled.cu', 'occgrid_route.cu', 'mapmerge.cu', 'frontier.cu', 'icp.cu', 'slam_chain.cpp']
+SOURCES = ['occgrid_integrate.cu', 'occgrid_tiled.cu', 'occgrid_route.cu', 'occgrid_band.cu', 'mapmerge.cu', 'frontier.cu', 'icp.cu', 'slam_chain.cpp']
 HEADERS = ['common.cuh', 'beam_expand.cuh', 'sincos_dd.cuh', os.path.join('..', '..', 'include', 'occgrid_b200.h')]
 
 STRATEGY = {'auto': -1, 'global_atomic': 0, 'tiled': 1}
@@ -32,6 +32,16 @@ class Geom(C.Structure):
                 ('size_x', C.c_int32), ('size_y', C.c_int32),
                 ('win_x0', C.c_int32), ('win_y0', C.c_int32),
                 ('win_w', C.c_int32), ('win_h', C.c_int32)]
+
+
+class RouteJob(C.Structure):
+    """struct occgrid_route_job"""
+    _fields_ = [('d_packets', C.c_void_p), ('n', C.c_int64), ('stride', C.c_int32), ('rec_len', C.c_int32),
+                ('d_agent_idx', C.c_void_p), ('d_drift', C.c_void_p), ('d_agent_off', C.c_void_p), ('n_agents', C.c_int32),
+                ('ordinal_base', C.c_uint32), ('ox', C.c_double), ('oy', C.c_double), ('res', C.c_double),
+                ('size_x', C.c_int32), ('n_bands', C.c_int32), ('src_rank', C.c_int32), ('band_y0', C.c_int32 * 33),
+                ('d_peer_recs', C.c_void_p), ('seg_capacity', C.c_int64), ('d_resv', C.c_void_p), ('d_status', C.c_void_p),
+                ('d_counters', C.c_void_p)]
 
 
 def _stale():
@@ -92,8 +102,14 @@ def lib():
                                         vp, sz, vp]
     L.occgrid_integrate_poses.restype = i32
     L.occgrid_integrate_poses.argtypes = [gp, vp, i64, i32, vp, vp, sz, vp, i32, vp]
-    L.occgrid_route_packets_p2p.restype = i32
-    L.occgrid_route_packets_p2p.argtypes = [gp, i32, vp, vp, i64, i32, i32, vp, vp, vp, i32, u32, vp, vp, i64, vp, vp, vp]
+    L.occgrid_band_workspace_bytes.restype = sz
+    L.occgrid_band_workspace_bytes.argtypes = [gp, i32, i64]
+    L.occgrid_band_prepare.restype = i32
+    L.occgrid_band_prepare.argtypes = [gp, vp, i32, i64, vp, vp, sz, vp, vp]
+    L.occgrid_band_raycast_route.restype = i32
+    L.occgrid_band_raycast_route.argtypes = [gp, vp, i32, i64, i32, C.POINTER(RouteJob), vp, vp, sz, vp, vp]
+    L.occgrid_band_publish.restype = i32
+    L.occgrid_band_publish.argtypes = [i32, i32, vp, i64, vp, vp, vp, u32, i32, vp, vp]
     L.occgrid_frontier_workspace_bytes.restype = sz
     L.occgrid_frontier_workspace_bytes.argtypes = [i64, i64]
     L.occgrid_frontiers.restype = i32
@@ -178,7 +194,7 @@ def _bind_merge(L):
 KERNEL_NAMES = ('integrate_global', 'resolve', 'update_rays', 'tile_count', 'tile_scan', 'tile_scatter',
                 'tile_raycast', 'tile_resolve', 'merge_extract', 'merge_bounds', 'merge_voxel', 'merge_raster',
                 'merge_fuse', 'probe', 'route', 'frontier', 'frontier_cluster', 'chain_probe', 'chain_incremental',
-                'chain_rebuild', 'icp')
+                'chain_rebuild', 'icp', 'band_barrier', 'render')
 
 
 def profile_begin():

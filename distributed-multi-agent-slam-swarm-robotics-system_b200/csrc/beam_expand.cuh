@@ -175,6 +175,38 @@ OCC_HD void expand_packet(const Geom& g, double rx, double ry, double ryaw, cons
     expand_beam(g, rx, ry, ryaw, x0, y0, origin_ok, 3, dist[3], -c0, s0, tolx, toly, fsc, &out[3]);
 }
 
+// Per-packet part of expand_packet, for kernels that loop over the four sensors instead of
+// unrolling them: start cell (:142), screening tolerances and ONE library sincos of the yaw.
+struct PacketFrame {
+    double rx, ry, ryaw, tolx, toly, s0, c0;
+    int x0, y0;
+    bool origin_ok;
+};
+
+template <class FastSinCos>
+OCC_HD void packet_frame(const Geom& g, double rx, double ry, double ryaw, const FastSinCos& fsc, PacketFrame* F) {
+    F->rx = rx; F->ry = ry; F->ryaw = ryaw;
+    F->tolx = screening_tolerance(rx, g.ox, ryaw, g.inv_res);
+    F->toly = screening_tolerance(ry, g.oy, ryaw, g.inv_res);
+    double q0x = OCC_DMUL(OCC_DADD(rx, -g.ox), g.inv_res);
+    double q0y = OCC_DMUL(OCC_DADD(ry, -g.oy), g.inv_res);
+    if (near_cell_boundary(q0x, F->tolx)) q0x = cell_quotient(rx, g.ox, g.res);               // :142
+    if (near_cell_boundary(q0y, F->toly)) q0y = cell_quotient(ry, g.oy, g.res);
+    F->origin_ok = quotient_in_range(q0x) && quotient_in_range(q0y);
+    F->x0 = F->origin_ok ? trunc_cell(q0x) : 0;
+    F->y0 = F->origin_ok ? trunc_cell(q0y) : 0;
+    fsc(ryaw, &F->s0, &F->c0);
+}
+
+// Beam of sensor s (0 front, 1 left, 2 back, 3 right; :61-66) as a quarter turn of the frame's
+// sincos — the same values expand_packet hands to expand_beam.
+template <class FastSinCos>
+OCC_HD void expand_beam_of(const Geom& g, const PacketFrame& F, int s, float dist, const FastSinCos& fsc, Beam* out) {
+    const double sn = s == 0 ? F.s0 : (s == 1 ? F.c0 : (s == 2 ? -F.s0 : -F.c0));
+    const double cs = s == 0 ? F.c0 : (s == 1 ? -F.s0 : (s == 2 ? -F.c0 : F.s0));
+    expand_beam(g, F.rx, F.ry, F.ryaw, F.x0, F.y0, F.origin_ok, s, dist, sn, cs, F.tolx, F.toly, fsc, out);
+}
+
 // Explicit world-space ray -> beam (OccupancyGrid.update_ray's two world_to_grid calls, :142-143).
 OCC_HD void ray_to_beam(const Geom& g, double x0w, double y0w, double x1w, double y1w, int hit, Beam* b) {
     double q0x = cell_quotient(x0w, g.ox, g.res), q0y = cell_quotient(y0w, g.oy, g.res);

@@ -248,7 +248,7 @@ k_cluster_emit(const long long* __restrict__ d_count, const int* __restrict__ la
 static int fgrid(long long items) {
     long long b = (items + kFT - 1) / kFT;
     if (b < 1) b = 1;
-    if (b > 148 * 16) b = 148 * 16;
+    if (b > device_sm_count() * 16) b = device_sm_count() * 16;
     return (int)b;
 }
 

@@ -330,7 +330,7 @@ int mapmerge_icp_register(const double* d_sx, const double* d_sy, int64_t n_sour
     IcpState* state = reinterpret_cast<IcpState*>(ws + L.state);
     cudaStream_t st = (cudaStream_t)stream;
     long long gt = (n_target + kIT - 1) / kIT;
-    if (gt > 148 * 16) gt = 148 * 16;
+    if (gt > device_sm_count() * 16) gt = device_sm_count() * 16;
     const int gs = (int)((n_source + kIT - 1) / kIT);
     ProfileScope ps(K_ICP, st, 6 + 5 * max_iteration);
     OCC_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)(cells + 1) * 4, st));

@@ -27,7 +27,7 @@ constexpr int kCellsPerThread = 64;   // four independent 16-byte loads in fligh
 constexpr int kChunk = kMT * kCellsPerThread;
 
 // Status word bits (device int32, sticky; checked by the host wrapper at its next sync).
-enum { ST_POINT_OVERFLOW = 1, ST_LATTICE_OVERFLOW = 2 };
+enum { ST_POINT_OVERFLOW = 1, ST_LATTICE_OVERFLOW = 2, ST_CHAIN_ABORTED = 4 };
 
 struct Xform { double m[16]; int identity; };
 
@@ -677,9 +677,9 @@ struct ChainHeader {
     int have_lattice, force_rebuild, bounds_dirty;
     int stalled;                         // 0 running, else OCC_CHAIN_* reason the host has to deal with
     int cursor;                          // next entry of order[]
-    unsigned int ticket;
+    int aborted;                         // a grid barrier timed out (a CTA went missing): the launch gave up
 };
-enum { CHAIN_RUN = 0, CHAIN_REBUILD = 1, CHAIN_OVERFLOW = 2, CHAIN_REBOUND = 3 };
+enum { CHAIN_RUN = 0, CHAIN_REBUILD = 1, CHAIN_OVERFLOW = 2, CHAIN_REBOUND = 3, CHAIN_ABORTED = 4 };
 
 __device__ __forceinline__ bool voxel_key_of(double x, double y, double mbx, double mby, double voxel, long long W,
                                              long long H, unsigned int* key) {
@@ -714,7 +714,7 @@ __global__ void k_chain_reset(ChainHeader* __restrict__ h) {
     h->bounds_dirty = 1;                 // k_chain_rebounds + _apply compute the bounds of the adopted cloud
     h->stalled = 0;
     h->cursor = 0;
-    h->ticket = 0;
+    h->aborted = 0;
 }
 
 // Bounds of every slice of the batch: blockIdx.y = agent, atomics into slice_benc[agent][4]
@@ -763,20 +763,61 @@ struct ChainRun {
     long long* d_count;
     long long capacity;
     int* status;
-    unsigned int* bar;                                         // {arrivals, exits}; both zero between launches
+    unsigned int* bar;                                         // {arrivals, exits, release, verdict}; all zero between launches
     int bc_stride;
 };
 
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& target) {
+// Grid-wide barrier over co-resident CTAs (cooperative launch).  bar[0] counts arrivals, bar[2] is
+// the release word, bar[3] the verdict the LAST arriver computed (`last_arriver()` runs in exactly
+// one thread of the grid, after every CTA's pre-barrier writes are visible and before anybody is
+// released) — a decision every CTA must agree on is therefore single-sourced: nobody re-derives it
+// from header fields a faster CTA may already be overwriting in the next phase.
+// A CTA that waits longer than kBarrierTimeoutNs gives up (returns false, sets *abort_flag): a
+// missing CTA can then no longer hang the device.
+constexpr unsigned long long kBarrierTimeoutNs = 2000000000ull;
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <class F>
+__device__ __forceinline__ bool grid_barrier(unsigned int* bar, unsigned int& target, int* abort_flag, int* verdict, F&& last_arriver) {
+    __shared__ int s_ok, s_verdict;
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
+        int ok = 1;
         __threadfence();
-        atomicAdd(bar, 1u);
-        while (*reinterpret_cast<volatile unsigned int*>(bar) < target) { }
+        if (atomicAdd(bar, 1u) == target - 1u) {               // last arriver: decide, publish, release
+            __threadfence();
+            reinterpret_cast<volatile unsigned int*>(bar)[3] = (unsigned int)last_arriver();
+            __threadfence();
+            reinterpret_cast<volatile unsigned int*>(bar)[2] = target;
+        } else {
+            const unsigned long long t0 = global_ns();
+            unsigned int spins = 0;
+            while (reinterpret_cast<volatile unsigned int*>(bar)[2] < target) {
+                if (((++spins) & 1023u) == 0u &&
+                    (*reinterpret_cast<volatile int*>(abort_flag) || global_ns() - t0 > kBarrierTimeoutNs)) {
+                    atomicExch(abort_flag, 1);
+                    ok = 0;
+                    break;
+                }
+            }
+        }
         __threadfence();
+        s_ok = ok;
+        s_verdict = (int)reinterpret_cast<volatile unsigned int*>(bar)[3];
     }
     __syncthreads();
+    if (verdict) *verdict = s_verdict;
+    return s_ok != 0;
+}
+
+__device__ __forceinline__ bool grid_barrier(unsigned int* bar, unsigned int& target, int* abort_flag) {
+    return grid_barrier(bar, target, abort_flag, nullptr, [] { return 0; });
 }
 
 __device__ __forceinline__ void chain_link(const ChainRun& p, long long b, long long n, double mbx, double mby) {
@@ -894,20 +935,24 @@ k_chain_persistent(const ChainRun p) {
     ChainHeader* h = p.h;
     unsigned int target = 0;
     int done = 0;
+    bool alive = true;                                 // false once a barrier timed out: leave without touching shared state
     if (!h->stalled) {
         int cur = h->cursor;
         long long n_g = *p.d_count;
         const double mbx = h->mbx, mby = h->mby;       // the anchor LM is valid for: every callback that runs uses exactly it
-        double nmbx, nmby;
         // The first callback of a launch is decided and linked on its own; after that the NEXT
         // slice is linked speculatively (under the unchanged anchor) in the same phase that appends
-        // the current one, so a callback costs two grid barriers.  The decision follows at the
-        // barrier; a callback that may not run has its stacks unlinked again.
+        // the current one, so a callback costs two grid barriers.  The decision for it is taken by
+        // the last CTA to arrive at the second barrier — ONE evaluation of chain_decide on the
+        // header as the callback left it — and handed to every CTA with the release; a callback
+        // that may not run has its stacks unlinked again.
         bool linked = false;
         if (p.n_callbacks > 0 && cur < p.n_order) {
             const int agent = p.order[cur];
+            // nothing has been written since the launch began: all CTAs read the same header here
+            double nmbx, nmby;
             const int need = chain_decide(h, p.slice_benc + 4 * agent, p.voxel, p.W, p.H, &nmbx, &nmby);
-            if (need != CHAIN_RUN) {                   // every CTA reaches the same verdict; CTA 0 records it
+            if (need != CHAIN_RUN) {
                 if (blockIdx.x == 0 && threadIdx.x == 0) {
                     h->stalled = need;
                     if (need == CHAIN_OVERFLOW) atomicOr(p.status, ST_LATTICE_OVERFLOW);
@@ -915,8 +960,10 @@ k_chain_persistent(const ChainRun p) {
             } else {
                 const long long b = p.agent_offset[agent];
                 chain_link(p, b, p.agent_offset[agent + 1] - b, mbx, mby);
-                grid_barrier(p.bar, target);
-                linked = true;
+                // no CTA may start folding (which writes the flags chain_decide reads) before every
+                // CTA has taken the decision above
+                alive = grid_barrier(p.bar, target, &h->aborted);
+                linked = alive;
             }
         }
         for (int it = 0; linked; ++it) {
@@ -927,7 +974,7 @@ k_chain_persistent(const ChainRun p) {
             if (blockIdx.x == 0 && it > 0)             // the previous callback's counters: its append phase is over
                 for (int q = threadIdx.x; q < p.bc_stride; q += kMT) bc_other[q] = 0u;
             chain_fold(p, b, n, mbx, mby, bc);
-            grid_barrier(p.bar, target);
+            if (!(alive = grid_barrier(p.bar, target, &h->aborted))) break;
             const unsigned int added = chain_append(p, n, n_g, mbx, mby, bc, s_warp);
             n_g += added;
             if (n_g > p.capacity) n_g = p.capacity;
@@ -943,9 +990,14 @@ k_chain_persistent(const ChainRun p) {
                 nn = p.agent_offset[next_agent + 1] - nb;
                 chain_link(p, nb, nn, mbx, mby);
             }
-            grid_barrier(p.bar, target);               // bounds / flags of this callback feed the next decision
-            if (!more) break;
-            const int need = chain_decide(h, p.slice_benc + 4 * next_agent, p.voxel, p.W, p.H, &nmbx, &nmby);
+            // bounds / flags of this callback feed the next decision: taken once, by the last arriver
+            int need = CHAIN_RUN;
+            alive = grid_barrier(p.bar, target, &h->aborted, &need, [&] {
+                if (!more) return (int)CHAIN_RUN;
+                double ax, ay;
+                return chain_decide(h, p.slice_benc + 4 * next_agent, p.voxel, p.W, p.H, &ax, &ay);
+            });
+            if (!alive || !more) break;
             if (need != CHAIN_RUN) {
                 for (long long j = (long long)blockIdx.x * kMT + threadIdx.x; j < nn; j += (long long)gridDim.x * kMT)
                     p.LM[p.lkey[j]].y = 0u;            // unlink: the host deals with this callback
@@ -957,13 +1009,17 @@ k_chain_persistent(const ChainRun p) {
             }
         }
     }
+    if (!alive) {                                      // a barrier timed out: the state is unusable, tell the host
+        if (threadIdx.x == 0) { h->stalled = CHAIN_ABORTED; atomicOr(p.status, ST_CHAIN_ABORTED); }
+        return;
+    }
     // leave the counters and the barrier clean for the next launch
     if (blockIdx.x == 0 && done)
         for (int q = threadIdx.x; q < p.bc_stride; q += kMT) p.blockcount[(size_t)((done - 1) & 1) * p.bc_stride + q] = 0u;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(p.bar + 1, 1u) == gridDim.x - 1) { p.bar[0] = 0u; p.bar[1] = 0u; }
+        if (atomicAdd(p.bar + 1, 1u) == gridDim.x - 1) { p.bar[0] = 0u; p.bar[1] = 0u; p.bar[2] = 0u; p.bar[3] = 0u; }
     }
 }
 
@@ -1081,7 +1137,7 @@ k_fuse_max(int8_t* __restrict__ dst, const int8_t* __restrict__ src, long long n
 static int grid_for(long long work_items) {
     long long b = (work_items + kMT - 1) / kMT;
     if (b < 1) b = 1;
-    if (b > 148 * 16) b = 148 * 16;
+    if (b > device_sm_count() * 16) b = device_sm_count() * 16;
     return (int)b;
 }
 
@@ -1226,14 +1282,14 @@ int mapmerge_append_slice(const double* d_sx, const double* d_sy, const int64_t*
     }
     cudaStream_t st = (cudaStream_t)stream;
     ProfileScope ps(K_MERGE_EXTRACT, st, 2);
-    k_append_slice<<<148, kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, agent, d_px, d_py, capacity,
+    k_append_slice<<<device_sm_count(), kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, agent, d_px, d_py, capacity,
                                          (long long*)d_count, d_status, (unsigned long long*)d_bounds_enc);
     k_bump_count<<<1, 1, 0, st>>>((const long long*)d_agent_offset, agent, capacity, (long long*)d_count);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
 }
 
-size_t mapmerge_bounds_workspace_bytes(void) { return (size_t)148 * 8 * 4 * sizeof(double); }
+size_t mapmerge_bounds_workspace_bytes(void) { return (size_t)1024 * 8 * 4 * sizeof(double); }   // room for 8 CTAs on up to 1024 SMs
 
 int mapmerge_bounds(const double* d_px, const double* d_py, const int64_t* d_count, double* d_bounds, void* d_ws,
                     size_t ws_bytes, void* stream) {
@@ -1242,7 +1298,7 @@ int mapmerge_bounds(const double* d_px, const double* d_py, const int64_t* d_cou
         return OCCGRID_E_ARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const int blocks = 148 * 8;
+    const int blocks = device_sm_count() * 8;
     ProfileScope ps(K_MERGE_BOUNDS, st, 2);
     k_bounds_partial<<<blocks, kMT, 0, st>>>(d_px, d_py, (const long long*)d_count, (double*)d_ws);
     k_bounds_final<<<1, kMT, 0, st>>>((const double*)d_ws, blocks, d_bounds);
@@ -1349,7 +1405,7 @@ static size_t chain_layout(const int64_t* dims, int n_agents, ChainArrays* a, vo
     auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return at; };
     const size_t o_h = take(sizeof(ChainHeader)), o_lm = take((cells + 1) * 8), o_gk = take(points * 4);
     const size_t bc_stride = sl / kMT + 2;
-    const size_t o_lk = take(sl * 4), o_nx = take(sl * 4), o_fl = take(sl * 4), o_bc = take(2 * bc_stride * 4), o_bar = take(8);
+    const size_t o_lk = take(sl * 4), o_nx = take(sl * 4), o_fl = take(sl * 4), o_bc = take(2 * bc_stride * 4), o_bar = take(16);
     const size_t o_rx = take(sl * 8), o_ry = take(sl * 8), o_sb = take((size_t)n_agents * 32), o_or = take((size_t)n_agents * 4);
     if (a) {
         a->h = reinterpret_cast<ChainHeader*>(ws + o_h);
@@ -1403,7 +1459,7 @@ int mapmerge_chain_init(void* d_chain, size_t chain_bytes, const int64_t* dims, 
     dim3 grid((unsigned)grid_for(dims[3]), (unsigned)n_agents);
     if (grid.x > 64) grid.x = 64;
     k_chain_slice_bounds<<<grid, kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, c.slice_benc);
-    k_chain_rebounds<<<148 * 8, kMT, 0, st>>>(d_px, d_py, (const long long*)d_count, c.h);
+    k_chain_rebounds<<<device_sm_count() * 8, kMT, 0, st>>>(d_px, d_py, (const long long*)d_count, c.h);
     k_chain_rebounds_apply<<<1, 1, 0, st>>>(c.h);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
@@ -1421,14 +1477,17 @@ int mapmerge_chain_run(void* d_chain, const int64_t* dims, int n_agents, int n_o
     ChainArrays c;
     chain_layout(dims, n_agents, &c, d_chain);
     cudaStream_t st = (cudaStream_t)stream;
-    static int resident_ctas = 0;                  // CTAs of the persistent kernel the device can hold at once
+    static int resident_by_device[64] = {};        // CTAs of the persistent kernel each device can hold at once
+    int dev = 0;
+    OCC_CUDA_TRY(cudaGetDevice(&dev));
+    int resident_ctas = (dev >= 0 && dev < 64) ? resident_by_device[dev] : 0;
     if (resident_ctas == 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        OCC_CUDA_TRY(cudaGetDevice(&dev));
+        int sms = 0, per_sm = 0;
         OCC_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         OCC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_persistent, kMT, 0));
         if (sms <= 0 || per_sm <= 0) { set_last_error("mapmerge_chain_run: persistent kernel does not fit the device"); return OCCGRID_E_CUDA; }
         resident_ctas = sms * per_sm;
+        if (dev >= 0 && dev < 64) resident_by_device[dev] = resident_ctas;
     }
     int grid = grid_for(dims[3]);
     if (grid > resident_ctas) grid = resident_ctas;
@@ -1467,7 +1526,7 @@ int mapmerge_chain_rebounds(void* d_chain, const int64_t* dims, int n_agents, co
     chain_layout(dims, n_agents, &c, d_chain);
     cudaStream_t st = (cudaStream_t)stream;
     ProfileScope ps(K_CHAIN_PROBE, st, 2);
-    k_chain_rebounds<<<148 * 8, kMT, 0, st>>>(d_px, d_py, (const long long*)d_count, c.h);
+    k_chain_rebounds<<<device_sm_count() * 8, kMT, 0, st>>>(d_px, d_py, (const long long*)d_count, c.h);
     k_chain_rebounds_apply<<<1, 1, 0, st>>>(c.h);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
@@ -1494,7 +1553,7 @@ int mapmerge_chain_rebuild(void* d_chain, const int64_t* dims, int n_agents, con
     const int gp = grid_for(capacity);
     ProfileScope ps(K_CHAIN_REBUILD, st, 13);
     k_chain_lm_clear<<<gp, kMT, 0, st>>>(c.h, c.LM, c.gkey, (const long long*)d_count);
-    k_append_slice<<<148, kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, agent, d_px, d_py, capacity, (long long*)d_count,
+    k_append_slice<<<device_sm_count(), kMT, 0, st>>>(d_sx, d_sy, (const long long*)d_agent_offset, agent, d_px, d_py, capacity, (long long*)d_count,
                                          d_status, nullptr);
     k_bump_count<<<1, 1, 0, st>>>((const long long*)d_agent_offset, agent, capacity, (long long*)d_count);
     k_chain_rebuild_hdr<<<1, 1, 0, st>>>(c.h, c.slice_benc, agent, (const long long*)d_count, voxel, dims[0], dims[1], dims[2], d_status);
@@ -1515,7 +1574,7 @@ int mapmerge_rasterise(const double* d_px, const double* d_py, const int64_t* d_
     const long long n = (long long)width * height;
     ProfileScope ps(K_MERGE_RASTER, st, 2);
     k_raster_fill<<<grid_for(n / 16 + 1), kMT, 0, st>>>(d_grid_out, n);
-    k_raster_scatter<<<148 * 8, kMT, 0, st>>>(d_px, d_py, (const long long*)d_count, d_bounds, res, width, height, d_grid_out);
+    k_raster_scatter<<<device_sm_count() * 8, kMT, 0, st>>>(d_px, d_py, (const long long*)d_count, d_bounds, res, width, height, d_grid_out);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
 }

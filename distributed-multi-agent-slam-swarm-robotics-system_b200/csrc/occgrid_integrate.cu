@@ -287,15 +287,18 @@ k_resolve(unsigned int* __restrict__ stamps, int8_t* __restrict__ grid, size_t n
     }
 }
 
-static int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
+int device_sm_count() {
+    static int by_device[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (by_device[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        by_device[dev] = n;
     }
-    return n;
+    return by_device[dev];
 }
+static int sm_count() { return device_sm_count(); }
 
 static int launch_resolve(const occgrid_geom* geom, unsigned int* stamps, int8_t* grid, cudaStream_t st) {
     const size_t n_cells = (size_t)geom->win_w * geom->win_h;
@@ -532,7 +535,7 @@ int occgrid_counts_to_logodds(const int32_t* d_counts, int64_t n_cells, double l
     if (n_cells == 0) return OCCGRID_OK;
     cudaStream_t st = (cudaStream_t)stream;
     long long blocks = (n_cells + kThreads - 1) / kThreads;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
     ProfileScope ps(K_RESOLVE, st);
     k_counts_to_logodds<<<(unsigned int)blocks, kThreads, 0, st>>>(d_counts, n_cells, l_occ, l_free, l_min, l_max, d_logodds);
     OCC_CUDA_TRY(cudaGetLastError());

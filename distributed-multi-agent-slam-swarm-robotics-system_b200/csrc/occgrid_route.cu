@@ -12,6 +12,9 @@
 // concatenates by source rank) the record index on the receiving side is consistent with the
 // canonical order and no sequence numbers have to travel.
 //
+// This file is the NCCL variant (records grouped in a send buffer, exchanged with all-to-all); the
+// default path is the fused raycast + route kernel over peer memory (occgrid_band.cu).
+//
 // Three kernels: per-CTA band histograms -> single-CTA scan (band-major) -> stable scatter into
 // a send buffer grouped by band.  What travels is the DECODED record (48-byte PoseRec: pose
 // already corrected by the agent offset and the SLAM drift), so no side arrays follow it and the
@@ -44,7 +47,7 @@ __device__ __forceinline__ unsigned int band_mask(const RouteParams& P, const ui
     if (st != PKT_OK) return 0u;
     out->rx = rx; out->ry = ry; out->yaw = (float)ryaw;            // ryaw came from an fp32 field: exact
     out->d[0] = dist[0]; out->d[1] = dist[1]; out->d[2] = dist[2]; out->d[3] = dist[3];
-    out->k = (unsigned int)k; out->pad[0] = out->pad[1] = 0;
+    out->k = (unsigned int)k; out->tile = -1; out->pad = 0;
     const double q = cell_quotient(ry, P.oy, P.res);
     if (!quotient_in_range(q)) return 0u;
     const int gy = trunc_cell(q);
@@ -168,90 +171,6 @@ k_route_scatter(RouteParams P, const uint8_t* __restrict__ pkts, long long n, in
     }
 }
 
-// ---- fused route + exchange over peer memory ------------------------------------------------
-// One pass: decode, pick the destination band(s), reserve slots in the DESTINATION GPU's receive
-// buffer with one remote atomicAdd per band per CTA, and store the 48-byte records straight into
-// peer memory over NVLink (three 16-byte stores each).  No send buffer, no all-to-all, no counts
-// exchange.  Arrival order is arbitrary, so every record carries its ordinal in the canonical
-// stream (ordinal_base + index) and the receiver integrates with ordinals taken from the records.
-constexpr int kRouteSub = 8;                       // sub-batches of kRT packets per CTA
-constexpr int kRoutePerCta = kRT * kRouteSub;     // 2048 packets share one remote reservation per band
-
-__global__ void __launch_bounds__(kRT)
-k_route_p2p(RouteParams P, const uint8_t* __restrict__ pkts, long long n, int stride,
-            const int32_t* __restrict__ agent_idx, const double* __restrict__ drift,
-            const double* __restrict__ agent_off, int n_agents, unsigned int ordinal_base,
-            PoseRec* const* __restrict__ peer_recv, unsigned int* const* __restrict__ peer_count,
-            unsigned int recv_capacity, int* __restrict__ status, uint64_t* counters) {
-    __shared__ __align__(16) uint8_t s_rec[kRT * kRouteMaxStride];
-    __shared__ unsigned int s_cnt[kRouteSub][kRouteMaxBands][kRT / 32];   // per (sub-batch, band, warp) counts -> offsets
-    __shared__ unsigned int s_base[kRouteMaxBands];
-    const long long cta_first = (long long)blockIdx.x * kRoutePerCta;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long c[4] = {0, 0, 0, 0};
-    unsigned int masks[kRouteSub];
-    // pass 1: decode, band masks, per-warp counts
-#pragma unroll
-    for (int sub = 0; sub < kRouteSub; ++sub) {
-        const long long first = cta_first + (long long)sub * kRT;
-        masks[sub] = 0;
-        if (first < n) {                                           // uniform across the CTA
-            const int count = (int)min((long long)kRT, n - first);
-            __syncthreads();
-            stage(pkts + (size_t)first * stride, (size_t)count * stride, s_rec);
-            __syncthreads();
-            int st = -1;
-            PoseRec unused;
-            if ((int)threadIdx.x < count)
-                masks[sub] = band_mask(P, s_rec + threadIdx.x * stride, first + threadIdx.x, agent_idx, drift, agent_off, n_agents, &st, &unused);
-            c[0] += st >= 0; c[1] += st == PKT_OK; c[2] += st == PKT_DROPPED; c[3] += st == PKT_BAD_POSE;
-        }
-        for (int b = 0; b < P.n_bands; ++b) {
-            const unsigned int bal = __ballot_sync(0xffffffffu, (masks[sub] >> b) & 1u);
-            if (lane == 0) s_cnt[sub][b][warp] = __popc(bal);
-        }
-    }
-    __syncthreads();
-    if ((int)threadIdx.x < P.n_bands) {          // exclusive offsets within the CTA + one remote reservation per band
-        const int b = threadIdx.x;
-        unsigned int tot = 0;
-        for (int sub = 0; sub < kRouteSub; ++sub)
-            for (int w = 0; w < kRT / 32; ++w) { const unsigned int v = s_cnt[sub][b][w]; s_cnt[sub][b][w] = tot; tot += v; }
-        unsigned int base = 0;
-        if (tot) {
-            base = atomicAdd(peer_count[b], tot);
-            if (base + tot > recv_capacity) { atomicOr(status, 1); base = 0xffffffffu; }
-        }
-        s_base[b] = base;
-    }
-    __syncthreads();
-    // pass 2: decode again (the records are L2-resident) and store into the owners' buffers
-#pragma unroll
-    for (int sub = 0; sub < kRouteSub; ++sub) {
-        const long long first = cta_first + (long long)sub * kRT;
-        if (first >= n) break;
-        const int count = (int)min((long long)kRT, n - first);
-        __syncthreads();
-        stage(pkts + (size_t)first * stride, (size_t)count * stride, s_rec);
-        __syncthreads();
-        const unsigned int m = masks[sub];
-        if (__ballot_sync(0xffffffffu, m != 0) == 0) continue;
-        PoseRec rec;
-        int st;
-        const long long k = first + threadIdx.x;
-        if (m) band_mask(P, s_rec + threadIdx.x * stride, k, agent_idx, drift, agent_off, n_agents, &st, &rec);
-        rec.k = ordinal_base + (unsigned int)k;
-        for (int b = 0; b < P.n_bands; ++b) {
-            const unsigned int bit = (m >> b) & 1u;
-            const unsigned int bal = __ballot_sync(0xffffffffu, bit);
-            if (bit && s_base[b] != 0xffffffffu)
-                peer_recv[b][s_base[b] + s_cnt[sub][b][warp] + __popc(bal & ((1u << lane) - 1u))] = rec;
-        }
-    }
-    __syncthreads();
-    block_add_counters(c, reinterpret_cast<unsigned long long*>(s_rec), counters);
-}
-
 }  // namespace occ
 
 using namespace occ;
@@ -297,36 +216,6 @@ int occgrid_route_packets(const occgrid_geom* geom, int n_bands, const int32_t* 
     k_route_scan<<<1, 1024, 0, st>>>(hist, n_bands, blocks, (long long*)d_band_counts, send_capacity, d_status);
     k_route_scatter<<<blocks, kRT, 0, st>>>(P, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents, hist, blocks,
                                             d_status, reinterpret_cast<PoseRec*>(d_send));
-    OCC_CUDA_TRY(cudaGetLastError());
-    return OCCGRID_OK;
-}
-
-int occgrid_route_packets_p2p(const occgrid_geom* geom, int n_bands, const int32_t* band_y0_host,
-                              const uint8_t* d_packets, int64_t n, int stride, int rec_len,
-                              const int32_t* d_agent_idx, const double* d_drift, const double* d_agent_off, int n_agents,
-                              uint32_t ordinal_base, void* const* d_peer_recv, uint32_t* const* d_peer_count,
-                              int64_t recv_capacity, int32_t* d_status, uint64_t* d_counters, void* stream) {
-    int rc = validate_geom(geom);
-    if (rc != OCCGRID_OK) return rc;
-    if (n_bands < 1 || n_bands > kRouteMaxBands || !band_y0_host) { set_last_error("route_p2p: n_bands must be 1..32"); return OCCGRID_E_ARG; }
-    if (n < 0 || (uint64_t)ordinal_base + (uint64_t)n > (1ull << 29) - 1) { set_last_error("route_p2p: ordinals must stay below 2^29-1"); return OCCGRID_E_ARG; }
-    if (rec_len != OCCGRID_PACKET_SIZE && rec_len != OCCGRID_PACKET_SIZE_V1) { set_last_error("route_p2p: rec_len must be 42 or 41"); return OCCGRID_E_ARG; }
-    if (stride < rec_len || stride > kRouteMaxStride) { set_last_error("route_p2p: bad stride %d", stride); return OCCGRID_E_ARG; }
-    if (!d_peer_recv || !d_peer_count || !d_status || !d_agent_off || n_agents < 1) { set_last_error("route_p2p: NULL argument"); return OCCGRID_E_ARG; }
-    if (recv_capacity <= 0 || recv_capacity >= (1ll << 32)) { set_last_error("route_p2p: bad receive capacity"); return OCCGRID_E_ARG; }
-    if (n == 0) return OCCGRID_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    RouteParams P;
-    P.oy = geom->oy; P.res = geom->res; P.size_y = geom->size_y;
-    P.reach = (int)ceil(OCC_MAX_DIST_M / geom->res) + 2;
-    P.n_bands = n_bands;
-    for (int b = 0; b <= n_bands; ++b) P.band_y0[b] = band_y0_host[b];
-    for (int b = n_bands + 1; b <= kRouteMaxBands; ++b) P.band_y0[b] = band_y0_host[n_bands];
-    const int blocks = (int)((n + kRoutePerCta - 1) / kRoutePerCta);
-    ProfileScope ps(K_ROUTE, st, 1);
-    k_route_p2p<<<blocks, kRT, 0, st>>>(P, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents, ordinal_base,
-                                        reinterpret_cast<PoseRec* const*>(d_peer_recv), d_peer_count,
-                                        (unsigned int)recv_capacity, d_status, d_counters);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
 }

@@ -51,6 +51,7 @@ struct TileGeom {
 };
 
 static inline int reach_cells(double res) { return (int)ceil(OCC_MAX_DIST_M / res) + 2; }
+__device__ __forceinline__ int reach_cells_dev(double res) { return (int)ceil(OCC_MAX_DIST_M / res) + 2; }
 
 static inline TileGeom tile_geom(const occgrid_geom* g) {
     TileGeom t;
@@ -174,7 +175,7 @@ k_home_count(Geom g, TileGeom tg, const uint8_t* __restrict__ pkts, long long n,
                     r.rx = rx; r.ry = ry; r.yaw = (float)ryaw;      // ryaw came from an fp32 field: exact
                     r.d[0] = dist[0]; r.d[1] = dist[1]; r.d[2] = dist[2]; r.d[3] = dist[3];
                     r.k = (unsigned int)k;
-                    r.pad[0] = r.pad[1] = 0;
+                    r.tile = tile; r.pad = 0;
                     recs[k] = r;                                    // packet order: coalesced 48-byte stores
                 }
             }
@@ -189,43 +190,67 @@ k_home_count(Geom g, TileGeom tg, const uint8_t* __restrict__ pkts, long long n,
     block_add_counters(c, reinterpret_cast<unsigned long long*>(s_rec), counters);
 }
 
-// Same as k_home_count for input that is already decoded (routed pose records): the records
-// are binned in place.
+// Segment / validity of one 2048-address chunk of a (possibly segmented) record buffer.
+__device__ __forceinline__ int chunk_valid(const SegInfo& seg, long long chunk, long long* addr0) {
+    const long long a0 = chunk * kSegChunk;
+    *addr0 = a0;
+    const unsigned int sg = (unsigned int)(a0 / seg.seg_cap);
+    const unsigned int j0 = (unsigned int)(a0 - (long long)sg * seg.seg_cap);
+    unsigned int cnt = seg.d_counts ? seg.d_counts[sg] : seg.host_count;
+    if (cnt > seg.seg_cap) cnt = seg.seg_cap;                       // a segment that overflowed was truncated by its writer
+    return cnt > j0 ? (int)min((unsigned int)kSegChunk, cnt - j0) : 0;
+}
+
+// Same as k_home_count for input that is already decoded (routed pose records, binned in place).
+// The buffer is a set of per-source segments whose fill counts live on the device; persistent
+// CTAs stride over 2048-address chunks and skip the empty ones.  `tiles_in_records`: the router
+// already computed the home tile for THIS window (rec.tile), nothing is re-derived here.
 __global__ void __launch_bounds__(kTT)
-k_home_count_poses(Geom g, TileGeom tg, const PoseRec* __restrict__ recs, long long n,
+k_home_count_poses(Geom g, TileGeom tg, const PoseRec* __restrict__ recs, SegInfo seg, long long n_chunks, int tiles_in_records,
                    unsigned int* __restrict__ tile_count, int* __restrict__ tile_ids,
                    unsigned int* __restrict__ active, TilePlanHeader* __restrict__ hdr, uint64_t* counters) {
     __shared__ unsigned int s_keys[kHash];
     __shared__ unsigned int s_vals[kHash];
     __shared__ unsigned long long s_acc[(OCCGRID_C_HITS + 1) * 32];
-    for (int i = threadIdx.x; i < kHash; i += kTT) { s_keys[i] = kEmpty; s_vals[i] = 0u; }
-    __syncthreads();
     unsigned long long c[OCCGRID_C_HITS + 1] = {};
-    const long long cta_first = (long long)blockIdx.x * kPkPerCta;
-    for (int sub = 0; sub < kSub; ++sub) {
-        const long long k = cta_first + (long long)sub * kTT + threadIdx.x;
-        if (k >= n) break;
-        const PoseRec r = recs[k];
-        c[OCCGRID_C_PACKETS] += 1;
-        int tile = -1;
-        if (!(isfinite(r.rx) && isfinite(r.ry) && isfinite(r.yaw))) c[OCCGRID_C_BAD_POSE] += 1;
-        else {
-            c[OCCGRID_C_ACCEPTED] += 1;
-            c[OCCGRID_C_BEAMS] += 4;
+    for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        long long addr0;
+        const int valid = chunk_valid(seg, chunk, &addr0);
+        if (valid == 0) continue;                                   // uniform across the CTA
+        for (int i = threadIdx.x; i < kHash; i += kTT) { s_keys[i] = kEmpty; s_vals[i] = 0u; }
+        __syncthreads();
+        for (int sub = 0; sub < kSub; ++sub) {
+            const int j = sub * kTT + threadIdx.x;
+            if (j >= valid) break;
+            const long long k = addr0 + j;
+            int tile = -1;
+            if (tiles_in_records) {
+                tile = recs[k].tile;                                // packets / beams / hits were counted by the source rank
+            } else {
+                const PoseRec r = recs[k];
+                c[OCCGRID_C_PACKETS] += 1;
+                if (!(isfinite(r.rx) && isfinite(r.ry) && isfinite(r.yaw))) c[OCCGRID_C_BAD_POSE] += 1;
+                else {
+                    c[OCCGRID_C_ACCEPTED] += 1;
+                    c[OCCGRID_C_BEAMS] += 4;
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const double d = (double)r.d[s];
-                c[OCCGRID_C_HITS] += (OCC_MIN_DIST_M < d && d <= OCC_MAX_DIST_M) ? 1 : 0;
+                    for (int s2 = 0; s2 < 4; ++s2) {
+                        const double dd = (double)r.d[s2];
+                        c[OCCGRID_C_HITS] += (OCC_MIN_DIST_M < dd && dd <= OCC_MAX_DIST_M) ? 1 : 0;
+                    }
+                    tile = home_tile(g, tg, r.rx, r.ry);
+                }
             }
-            tile = home_tile(g, tg, r.rx, r.ry);
+            if (tile >= tg.n_tiles) tile = -1;                      // never trust a tile id that came over the wire
             if (tile >= 0) atomicAdd(&s_vals[hash_insert(s_keys, (unsigned int)tile)], 1u);
+            tile_ids[k] = tile;
         }
-        tile_ids[k] = tile;
+        __syncthreads();
+        for (int i = threadIdx.x; i < kHash; i += kTT)
+            if (s_keys[i] != kEmpty && atomicAdd(&tile_count[s_keys[i]], s_vals[i]) == 0u)
+                active[atomicAdd(&hdr->active_count, 1u)] = s_keys[i];      // first toucher lists the tile
+        __syncthreads();
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < kHash; i += kTT)
-        if (s_keys[i] != kEmpty && atomicAdd(&tile_count[s_keys[i]], s_vals[i]) == 0u)
-            active[atomicAdd(&hdr->active_count, 1u)] = s_keys[i];          // first toucher lists the tile
     block_add_counters(c, s_acc, counters);
 }
 
@@ -260,6 +285,45 @@ k_home_scatter(long long n, const int* __restrict__ tile_ids, const unsigned int
     for (int sub = 0; sub < kSub; ++sub) {
         const long long k = cta_first + (long long)sub * kTT + threadIdx.x;
         if (where[sub] != kEmpty) bins[s_vals[where[sub] >> 16] + (where[sub] & 0xffffu)] = (unsigned int)k;
+    }
+}
+
+
+// Scatter for segmented record buffers: bins hold record ADDRESSES (segment * seg_cap + index).
+__global__ void __launch_bounds__(kTT)
+k_home_scatter_segs(SegInfo seg, long long n_chunks, const int* __restrict__ tile_ids, const unsigned int* __restrict__ tile_offset,
+                    unsigned int* __restrict__ tile_cursor, const TilePlanHeader* __restrict__ hdr, unsigned int* __restrict__ bins) {
+    __shared__ unsigned int s_keys[kHash];
+    __shared__ unsigned int s_vals[kHash];
+    if (hdr->overflow) return;
+    for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        long long addr0;
+        const int valid = chunk_valid(seg, chunk, &addr0);
+        if (valid == 0) continue;
+        for (int i = threadIdx.x; i < kHash; i += kTT) { s_keys[i] = kEmpty; s_vals[i] = 0u; }
+        __syncthreads();
+        unsigned int where[kSub];
+#pragma unroll
+        for (int sub = 0; sub < kSub; ++sub) {
+            const int j = sub * kTT + threadIdx.x;
+            where[sub] = kEmpty;
+            if (j < valid) {
+                const int tile = tile_ids[addr0 + j];
+                if (tile >= 0) {
+                    const int h = hash_insert(s_keys, (unsigned int)tile);
+                    where[sub] = ((unsigned int)h << 16) | atomicAdd(&s_vals[h], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < kHash; i += kTT)
+            if (s_keys[i] != kEmpty) s_vals[i] = tile_offset[s_keys[i]] + atomicAdd(&tile_cursor[s_keys[i]], s_vals[i]);
+        __syncthreads();
+#pragma unroll
+        for (int sub = 0; sub < kSub; ++sub)
+            if (where[sub] != kEmpty)
+                bins[s_vals[where[sub] >> 16] + (where[sub] & 0xffffu)] = (unsigned int)(addr0 + sub * kTT + threadIdx.x);
+        __syncthreads();
     }
 }
 
@@ -336,7 +400,7 @@ k_tile_plan(unsigned int* __restrict__ tile_count, unsigned int* __restrict__ ti
 // `e2 > -dy` / `e2 < dx`, both may fire, sx = -1 when x0 == x1).  (x, y) are window-local.
 // Both end points inside the (convex) window => every cell is inside, so the hot loop carries
 // no bounds test and steps a running shared-memory offset instead of recomputing y*pitch+x.
-__device__ __forceinline__ void draw_beam_smem(unsigned int* __restrict__ s_win, int side, int pitch, int x, int y,
+__device__ __noinline__ void draw_beam_smem(unsigned int* __restrict__ s_win, int side, int pitch, int x, int y,
                                                int ddx, int ddy, unsigned int free_stamp, bool hit, bool skip_first) {
     const int dx = abs(ddx), dy = abs(ddy);
     int err = dx - dy;
@@ -392,7 +456,7 @@ __device__ __forceinline__ void draw_beam_smem(unsigned int* __restrict__ s_win,
 // would have stored FREE to counts one miss (low half of the window word) and the OCCUPIED end
 // cell of a valid hit counts one hit (high half).  A work item holds <= 4 * kChunkPk beams and a
 // beam visits a cell once, so 16 bits per half cannot overflow.
-__device__ __forceinline__ void count_beam_smem(unsigned int* __restrict__ s_win, int side, int pitch, int x, int y,
+__device__ __noinline__ void count_beam_smem(unsigned int* __restrict__ s_win, int side, int pitch, int x, int y,
                                                 int ddx, int ddy, bool hit) {
     const int dx = abs(ddx), dy = abs(ddy);
     const int n = max(dx, dy);
@@ -427,24 +491,249 @@ __device__ __forceinline__ void count_beam_smem(unsigned int* __restrict__ s_win
     if (hit && (unsigned int)x < us && (unsigned int)y < us) atomicAdd(&s_win[y * pitch + x], 0x10000u);
 }
 
-template <bool kCounts>
-__global__ void __launch_bounds__(kTT)
+
+
+// ---- table-driven walk -------------------------------------------------------------------------
+// The minor-axis steps of the reference's Bresenham (:158-179) depend only on (dmaj, dmin): bit i of
+// walk_mask(dmaj, dmin) says whether step i also moves the minor axis — the very recurrence of
+// draw_beam_smem (E = dmaj - dmin; minor iff 2E < dmaj; E += minor ? dmaj - dmin : -dmin), run once
+// per (dmaj, dmin) pair when the CTA starts instead of once per cell.  561 pairs for dmaj <= 32
+// (a 1.2 m ray at 5 cm is <= 26 cells); longer beams take the recurrence.  The walk itself is
+// then: one shared-memory reduction per cell on a running BYTE address, one bit test, one add.
+constexpr int kMaskMaxLen = 32;
+constexpr int kMaskEntries = (kMaskMaxLen + 1) * (kMaskMaxLen + 2) / 2;
+
+__device__ __forceinline__ unsigned int walk_mask_of(int dmaj, int dmin) {
+    unsigned int m = 0u;
+    int E = dmaj - dmin;
+    for (int i = 0; i < dmaj; ++i) {
+        const bool minor = 2 * E < dmaj;
+        m |= (minor ? 1u : 0u) << i;
+        E += minor ? (dmaj - dmin) : -dmin;
+    }
+    return m;
+}
+
+__device__ __forceinline__ void build_walk_masks(unsigned int* s_mask) {
+    for (int e = threadIdx.x; e < kMaskEntries; e += blockDim.x) {
+        int dmaj = 0;
+        while ((dmaj + 1) * (dmaj + 2) / 2 <= e) ++dmaj;
+        s_mask[e] = walk_mask_of(dmaj, e - dmaj * (dmaj + 1) / 2);
+    }
+}
+
+template <bool kAdd>
+__device__ __forceinline__ void smem_red(unsigned int addr, unsigned int v) {
+    if (kAdd) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+    else      asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// Fast path of draw_beam_smem / count_beam_smem: both end points inside the window, dmaj <= 32.
+// win = 32-bit shared-space address of the window; (x, y) window-local start cell.
+//   kAdd = false: atomicMax of `v_free` on every cell but the last, `v_free | 1` on the last if hit
+//   kAdd = true : += 1 on every cell but the last, += 0x10000 on the last if hit (count mode)
+template <bool kAdd>
+__device__ __forceinline__ void walk_beam_masked(unsigned int win, int pitch, int x, int y, int ddx, int ddy,
+                                                 unsigned int v_free, bool hit, bool skip_first, const unsigned int* s_mask) {
+    const int dx = abs(ddx), dy = abs(ddy);
+    const bool xmajor = dx >= dy;
+    const int dmaj = xmajor ? dx : dy, dmin = xmajor ? dy : dx;
+    const int sx4 = ddx > 0 ? 4 : -4;
+    const int sy4 = (ddy > 0 ? pitch : -pitch) * 4;
+    const int step_maj = xmajor ? sx4 : sy4, step_min = xmajor ? sy4 : sx4;
+    unsigned int mask = s_mask[dmaj * (dmaj + 1) / 2 + dmin];
+    unsigned int a = win + (unsigned int)(y * pitch + x) * 4u;
+    const unsigned int a_end = a + (unsigned int)((ddy * pitch + ddx) * 4);
+    int rem = dmaj;                                   // cells still to mark FREE (the end cell is not one of them)
+    if (rem > 0) {
+        if (!skip_first) smem_red<kAdd>(a, v_free);   // the start cell is overwritten by a later beam of the packet otherwise
+        a += step_maj + ((mask & 1u) ? step_min : 0);
+        mask >>= 1;
+        --rem;
+    }
+    // straight-line groups of 8 and 4 cells (no guard per cell: ptxas turns a guarded ATOMS into a
+    // branch), then at most 3 single cells
+    while (rem >= 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            smem_red<kAdd>(a, v_free);
+            a += step_maj + ((mask & (1u << j)) ? step_min : 0);
+        }
+        mask >>= 8;
+        rem -= 8;
+    }
+    if (rem >= 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            smem_red<kAdd>(a, v_free);
+            a += step_maj + ((mask & (1u << j)) ? step_min : 0);
+        }
+        mask >>= 4;
+        rem -= 4;
+    }
+    for (; rem > 0; --rem) {
+        smem_red<kAdd>(a, v_free);
+        a += step_maj + ((mask & 1u) ? step_min : 0);
+        mask >>= 1;
+    }
+    if (hit && !(dmaj == 0 && skip_first && !kAdd)) smem_red<kAdd>(a_end, kAdd ? 0x10000u : (v_free | 1u));
+}
+
+// ---- route work item (multi-GPU row bands, fused into the persistent raycast kernel) -----------
+// One item = kRouteItemPk packets of the NEXT batch, one per thread: decode (:828-843), pose
+// correction (:851-857), robot cell (:142) -> the band(s) whose rows the packet's rays can reach
+// and its home tile IN THAT BAND'S WINDOW; the 48-byte records are sorted by band in shared
+// memory (the raycast window, free between two raycast items), a slot range is reserved in this
+// rank's segment of every destination with a LOCAL atomic, and the runs are copied into the band
+// owners' receive buffers over NVLink with fully coalesced 16-byte stores.  The stores are fire and
+// forget: they drain while the CTA is already walking the next raycast item.
+struct RouteSmem {
+    unsigned int cnt[kMaxBands];        // entries per band of this item
+    unsigned int off[kMaxBands + 1];    // exclusive offsets in the sorted buffer
+    unsigned int base[kMaxBands];       // reserved first slot in my segment of band b (0xffffffff: overflow)
+};
+
+__device__ __forceinline__ void route_item(const RouteJob& J, unsigned int item, unsigned int* s_buf /* >= 24.6 KB */,
+                                           RouteSmem& S, unsigned long long (&c)[6]) {
+    const long long first = (long long)item * kRouteItemPk;
+    const int count = (int)min((long long)kRouteItemPk, J.n - first);
+    if (threadIdx.x < kMaxBands) S.cnt[threadIdx.x] = 0u;
+    stage_records_t(J.pkts + (size_t)first * J.stride, (size_t)count * J.stride, reinterpret_cast<uint8_t*>(s_buf));
+    __syncthreads();
+    PoseRec rec = {};
+    int band[2] = {-1, -1}, tile[2] = {-1, -1};
+    unsigned int rank[2] = {0u, 0u};
+    if ((int)threadIdx.x < count) {
+        const long long k = first + threadIdx.x;
+        double rx, ry, ryaw;
+        float dist[4];
+        const int st = decode_packet(reinterpret_cast<const uint8_t*>(s_buf) + threadIdx.x * J.stride, k, J.agent_idx, J.drift,
+                                     J.agent_off, J.n_agents, &rx, &ry, &ryaw, dist);
+        c[OCCGRID_C_PACKETS] += 1; c[OCCGRID_C_ACCEPTED] += st == PKT_OK; c[OCCGRID_C_DROPPED] += st == PKT_DROPPED;
+        c[OCCGRID_C_BAD_POSE] += st == PKT_BAD_POSE;
+        if (st == PKT_OK) {
+            c[OCCGRID_C_BEAMS] += 4;
+#pragma unroll
+            for (int s2 = 0; s2 < 4; ++s2) {
+                const double dd = (double)dist[s2];
+                c[OCCGRID_C_HITS] += (OCC_MIN_DIST_M < dd && dd <= OCC_MAX_DIST_M) ? 1 : 0;      // :888
+            }
+            rec.rx = rx; rec.ry = ry; rec.yaw = (float)ryaw;             // ryaw came from an fp32 field: exact
+            rec.d[0] = dist[0]; rec.d[1] = dist[1]; rec.d[2] = dist[2]; rec.d[3] = dist[3];
+            rec.k = J.ordinal_base + (unsigned int)k; rec.pad = 0u;
+            const double qx = cell_quotient(rx, J.ox, J.res), qy = cell_quotient(ry, J.oy, J.res);
+            if (quotient_in_range(qx) && quotient_in_range(qy)) {
+                const int gx = trunc_cell(qx), gy = trunc_cell(qy);
+                const int reach = reach_cells_dev(J.res);
+                const int pad = ((reach + kTile - 1) / kTile) * kTile;
+                const int tiles_x = (J.size_x + 2 * pad + kTile - 1) >> kTileShift;
+                if (gx >= -reach && gx < J.size_x + reach) {
+                    int nb = 0;
+                    for (int b = 0; b < J.n_bands && nb < 2; ++b) {
+                        const int py = gy - J.band_y0[b];
+                        if (py >= -reach && py < J.band_y0[b + 1] - J.band_y0[b] + reach) {
+                            band[nb] = b;
+                            tile[nb] = ((py + pad) >> kTileShift) * tiles_x + ((gx + pad) >> kTileShift);
+                            ++nb;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // rank of every entry inside its band's run (arrival order is free: ordinals travel in the records)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const unsigned int peers = __match_any_sync(0xffffffffu, band[e]);
+        if (band[e] >= 0) {
+            const int lane = threadIdx.x & 31;
+            const int leader = __ffs(peers) - 1;
+            unsigned int b0 = 0;
+            if (lane == leader) b0 = atomicAdd(&S.cnt[band[e]], (unsigned int)__popc(peers));
+            b0 = __shfl_sync(peers, b0, leader);
+            rank[e] = b0 + __popc(peers & ((1u << lane) - 1u));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int o = 0;
+        for (int b = 0; b < J.n_bands; ++b) { S.off[b] = o; o += S.cnt[b]; }
+        S.off[J.n_bands] = o;
+    }
+    if ((int)threadIdx.x < J.n_bands) {
+        const unsigned int n_b = S.cnt[threadIdx.x];
+        unsigned int base = 0u;
+        if (n_b) {
+            base = atomicAdd(&J.resv[threadIdx.x], n_b);                 // LOCAL counter: no NVLink round trip
+            if (base + n_b > J.seg_cap) { atomicOr(J.status, 2); base = 0xffffffffu; }
+        }
+        S.base[threadIdx.x] = base;
+    }
+    __syncthreads();                                                     // raw packets are decoded: the buffer is free
+    uint4* s16 = reinterpret_cast<uint4*>(s_buf);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        if (band[e] >= 0) {                                              // struct occgrid_pose_rec, 3 x 16 bytes
+            uint4* dst = s16 + (size_t)(S.off[band[e]] + rank[e]) * 3;
+            const unsigned long long ux = (unsigned long long)__double_as_longlong(rec.rx), uy = (unsigned long long)__double_as_longlong(rec.ry);
+            dst[0] = make_uint4((unsigned int)ux, (unsigned int)(ux >> 32), (unsigned int)uy, (unsigned int)(uy >> 32));
+            dst[1] = make_uint4(__float_as_uint(rec.yaw), __float_as_uint(rec.d[0]), __float_as_uint(rec.d[1]), __float_as_uint(rec.d[2]));
+            dst[2] = make_uint4(__float_as_uint(rec.d[3]), rec.k, (unsigned int)tile[e], 0u);
+        }
+    }
+    __syncthreads();
+    const unsigned int total16 = S.off[J.n_bands] * 3u;
+    for (unsigned int q = threadIdx.x; q < total16; q += kTT) {
+        const unsigned int e = q / 3u;
+        int b = 0;
+        while (e >= S.off[b + 1]) ++b;
+        const unsigned int base = S.base[b];
+        if (base == 0xffffffffu) continue;
+        uint4* out = reinterpret_cast<uint4*>(J.peer_recs[b] + (size_t)J.src_rank * J.seg_cap + base);
+        out[q - S.off[b] * 3u] = s16[q];                                 // consecutive lanes -> consecutive 16-byte chunks
+    }
+}
+
+template <bool kCounts, bool kRoute>
+__global__ void __launch_bounds__(kTT, 3)      // three CTAs per SM: 80 registers
 k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHeader* __restrict__ hdr,
                const unsigned int* __restrict__ bins, const PoseRec* __restrict__ recs, int ordinals_in_records,
-               unsigned int* __restrict__ stamps, uint64_t* counters) {
+               unsigned int* __restrict__ stamps, uint64_t* counters, int have_items, const RouteJob job) {
     extern __shared__ unsigned int s_win[];
     __shared__ unsigned int s_item;
-    __shared__ unsigned long long s_acc[3 * 32];
-    const unsigned int n_items = hdr->n_items;
+    __shared__ unsigned long long s_acc[6 * 32];
+    __shared__ RouteSmem s_route;
+    __shared__ unsigned int s_mask[kMaskEntries];
+    build_walk_masks(s_mask);                      // visible after the first __syncthreads of the loop below
+    const unsigned int win_addr = (unsigned int)__cvta_generic_to_shared(s_win);
+    const unsigned int n_items = have_items ? hdr->n_items : 0u;
+    // Unified queue: raycast items of THIS batch and route items of the NEXT one, interleaved in
+    // proportion, so the NVLink traffic is spread over the whole kernel and overlaps the walks.
+    const unsigned int n_route = kRoute ? job.n_route_items : 0u;
+    const unsigned int n_total = n_items + n_route;
     const int side = tg.win_side, pitch = tg.pitch, words = side * pitch;
     unsigned long long c[3] = {0, 0, 0};     // updates, slowpath, owned updates
+    unsigned long long rc[6] = {0, 0, 0, 0, 0, 0};   // routed share: packets, accepted, dropped, bad pose, beams, hits
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_item = atomicAdd(&hdr->work_counter, 1u);
-        for (int i = threadIdx.x; i < words; i += kTT) s_win[i] = 0u;
+        if (!kRoute)
+            for (int i = threadIdx.x; i < words; i += kTT) s_win[i] = 0u;
         __syncthreads();
-        const unsigned int it = s_item;
-        if (it >= n_items) break;
+        unsigned int it = s_item;
+        if (it >= n_total) break;
+        if (kRoute) {
+            // r(i) = floor(i * n_route / n_total) route items precede queue position i
+            const unsigned int r0 = (unsigned int)(((unsigned long long)it * n_route) / n_total);
+            const unsigned int r1 = (unsigned int)(((unsigned long long)(it + 1) * n_route) / n_total);
+            if (r1 > r0) {
+                route_item(job, r0, s_win, s_route, rc);
+                continue;
+            }
+            it -= r0;
+            for (int i = threadIdx.x; i < words; i += kTT) s_win[i] = 0u;
+            __syncthreads();
+        }
         const uint4 item = items[it];
         const int ttx = item.x % tg.tiles_x, tty = item.x / tg.tiles_x;
         // global cell of window-local (0, 0)
@@ -454,25 +743,36 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
             const unsigned int idx = bins[r];
             const PoseRec rec = recs[idx];
             const unsigned int k = ordinals_in_records ? rec.k : idx;   // packet ordinal in this batch
-            const float dist[4] = {rec.d[0], rec.d[1], rec.d[2], rec.d[3]};
-            Beam b[4];
-            expand_packet(g, rec.rx, rec.ry, (double)rec.yaw, dist, LibSinCos(), b);
+            PacketFrame F;
+            packet_frame(g, rec.rx, rec.ry, (double)rec.yaw, LibSinCos(), &F);
+            const bool owned = F.x0 >= g.win_x0 && F.x0 < g.win_x0 + g.win_w && F.y0 >= g.win_y0 && F.y0 < g.win_y0 + g.win_h;
+            const int lx = F.x0 - wx0, ly = F.y0 - wy0;
+            const unsigned int us = (unsigned int)side;
             bool later_writes_first = false;
-#pragma unroll
+            // ONE copy of the expansion + walk code, looped over the four sensors (last sensor first:
+            // only the last beam that writes the shared start cell has to touch it).  Unrolling it
+            // four times made the kernel 110 KB of SASS and instruction-fetch bound.
+#pragma unroll 1
             for (int s = 3; s >= 0; --s) {
-                if (!b[s].valid) continue;
-                const int cells = beam_cells(b[s]);
+                Beam b;
+                expand_beam_of(g, F, s, s == 0 ? rec.d[0] : (s == 1 ? rec.d[1] : (s == 2 ? rec.d[2] : rec.d[3])), LibSinCos(), &b);
+                if (!b.valid) continue;
+                const int cells = beam_cells(b);
                 c[0] += cells;
-                c[1] += b[s].slow;
-                if (b[s].x0 >= g.win_x0 && b[s].x0 < g.win_x0 + g.win_w && b[s].y0 >= g.win_y0 && b[s].y0 < g.win_y0 + g.win_h)
-                    c[2] += cells;
-                if (kCounts)
-                    count_beam_smem(s_win, side, pitch, b[s].x0 - wx0, b[s].y0 - wy0, b[s].x1 - b[s].x0, b[s].y1 - b[s].y0,
-                                    b[s].hit != 0);
-                else
-                    draw_beam_smem(s_win, side, pitch, b[s].x0 - wx0, b[s].y0 - wy0, b[s].x1 - b[s].x0, b[s].y1 - b[s].y0,
-                                   (k * 4u + (unsigned int)s + 1u) << 1, b[s].hit != 0, later_writes_first);
-                later_writes_first = later_writes_first || (cells > 1 || b[s].hit);
+                c[1] += b.slow;
+                if (owned) c[2] += cells;
+                const int ddx = b.x1 - b.x0, ddy = b.y1 - b.y0;
+                const bool fast = (unsigned int)lx < us && (unsigned int)ly < us && (unsigned int)(lx + ddx) < us &&
+                                  (unsigned int)(ly + ddy) < us && cells <= kMaskMaxLen + 1;
+                if (kCounts) {
+                    if (fast) walk_beam_masked<true>(win_addr, pitch, lx, ly, ddx, ddy, 1u, b.hit != 0, false, s_mask);
+                    else count_beam_smem(s_win, side, pitch, lx, ly, ddx, ddy, b.hit != 0);
+                } else {
+                    const unsigned int stamp = (k * 4u + (unsigned int)s + 1u) << 1;
+                    if (fast) walk_beam_masked<false>(win_addr, pitch, lx, ly, ddx, ddy, stamp, b.hit != 0, later_writes_first, s_mask);
+                    else draw_beam_smem(s_win, side, pitch, lx, ly, ddx, ddy, stamp, b.hit != 0, later_writes_first);
+                }
+                later_writes_first = later_writes_first || (cells > 1 || b.hit);
             }
         }
         __syncthreads();
@@ -495,6 +795,10 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
                 }
             }
         }
+    }
+    if (kRoute && job.counters) {
+        __syncthreads();
+        block_add_counters(rc, s_acc, job.counters);            // slots OCCGRID_C_PACKETS .. OCCGRID_C_HITS
     }
     if (counters) {
         __syncthreads();
@@ -565,10 +869,12 @@ struct TiledLayout {
     unsigned int max_items;
 };
 
-static TiledLayout tiled_layout(const occgrid_geom* geom, int64_t max_packets) {
+// max_records = record ADDRESSES the bins / tile-id arrays must cover; with_recs: room for the
+// decoded records of a packet batch (input that arrives decoded brings its own buffer).
+static TiledLayout tiled_layout(const occgrid_geom* geom, int64_t max_records, bool with_recs) {
     TiledLayout L;
     const TileGeom tg = tile_geom(geom);
-    L.max_records = (unsigned long long)max_packets;
+    L.max_records = (unsigned long long)max_records;
     unsigned long long items = L.max_records / kChunkPk + (unsigned long long)tg.n_tiles + 1;
     if (items > L.max_records + 1) items = L.max_records + 1;
     L.max_items = (unsigned int)items;
@@ -582,7 +888,7 @@ static TiledLayout tiled_layout(const occgrid_geom* geom, int64_t max_packets) {
     L.off_items = o;  o += align_up((size_t)L.max_items * sizeof(uint4), 256);
     L.off_ids = o;    o += align_up((size_t)L.max_records * sizeof(int), 256);
     L.off_bins = o;   o += align_up((size_t)L.max_records * sizeof(unsigned int), 256);
-    L.off_recs = o;   o += align_up((size_t)L.max_records * sizeof(PoseRec), 256);
+    L.off_recs = o;   o += with_recs ? align_up((size_t)L.max_records * sizeof(PoseRec), 256) : 0;
     L.total = o;
     return L;
 }
@@ -593,7 +899,72 @@ bool tiled_supported(const occgrid_geom* geom) {
 }
 
 size_t tiled_workspace_bytes(const occgrid_geom* geom, int64_t max_packets) {
-    return tiled_layout(geom, max_packets < 1 ? 1 : max_packets).total;
+    return tiled_layout(geom, max_packets < 1 ? 1 : max_packets, true).total;
+}
+
+size_t tiled_band_workspace_bytes(const occgrid_geom* geom, int n_segs, int64_t seg_cap) {
+    return tiled_layout(geom, (int64_t)n_segs * seg_cap, false).total;
+}
+
+struct TiledPtrs {
+    unsigned int *stamps, *tile_count, *tile_offset, *tile_cursor, *active, *bins;
+    TilePlanHeader* hdr;
+    uint4* items;
+    int* tile_ids;
+    PoseRec* recs;
+};
+
+static TiledPtrs tiled_ptrs(const TiledLayout& L, void* d_ws) {
+    char* ws = reinterpret_cast<char*>(d_ws);
+    TiledPtrs p;
+    p.stamps = reinterpret_cast<unsigned int*>(ws + L.off_stamps);
+    p.tile_count = reinterpret_cast<unsigned int*>(ws + L.off_count);
+    p.tile_offset = reinterpret_cast<unsigned int*>(ws + L.off_offset);
+    p.tile_cursor = reinterpret_cast<unsigned int*>(ws + L.off_cursor);
+    p.active = reinterpret_cast<unsigned int*>(ws + L.off_active);
+    p.hdr = reinterpret_cast<TilePlanHeader*>(ws + L.off_hdr);
+    p.items = reinterpret_cast<uint4*>(ws + L.off_items);
+    p.bins = reinterpret_cast<unsigned int*>(ws + L.off_bins);
+    p.tile_ids = reinterpret_cast<int*>(ws + L.off_ids);
+    p.recs = reinterpret_cast<PoseRec*>(ws + L.off_recs);
+    return p;
+}
+
+// Dynamic shared memory of the raycast kernel: the stamp window, or the route item's staging
+// buffer (raw packets, then <= 2 records per packet) when that is larger.
+static size_t raycast_smem(const TileGeom& tg, bool route) {
+    size_t b = (size_t)tg.win_side * tg.pitch * 4;
+    const size_t r = (size_t)kRouteItemPk * 2 * sizeof(PoseRec);
+    const size_t raw = (size_t)kRouteItemPk * kMaxStrideT;
+    if (route) b = b > r ? b : r;
+    if (route) b = b > raw ? b : raw;
+    return b;
+}
+
+template <bool kCounts, bool kRoute>
+static int launch_raycast(const Geom& g, const TileGeom& tg, const TiledPtrs& P, const PoseRec* recs, int ordinals_in_records,
+                          unsigned int* plane, uint64_t* d_counters, int have_items, const RouteJob& job, cudaStream_t st) {
+    const size_t smem = raycast_smem(tg, kRoute);
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        OCC_CUDA_TRY(cudaFuncSetAttribute(k_home_raycast<kCounts, kRoute>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int ctas_per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_home_raycast<kCounts, kRoute>, kTT, smem) != cudaSuccess || ctas_per_sm < 1)
+        ctas_per_sm = 1;
+    if (g_raycast_cta_cap > 0 && ctas_per_sm > g_raycast_cta_cap) ctas_per_sm = g_raycast_cta_cap;
+    ProfileScope ps(K_TILE_RAYCAST, st);
+    k_home_raycast<kCounts, kRoute><<<device_sm_count() * ctas_per_sm, kTT, smem, st>>>(g, tg, P.items, P.hdr, P.bins, recs,
+                                                                                        ordinals_in_records, plane, d_counters,
+                                                                                        have_items, job);
+    return OCCGRID_OK;
+}
+
+static int grid_chunks(long long n_chunks) {
+    long long b = n_chunks < 1 ? 1 : n_chunks;
+    const long long cap = (long long)device_sm_count() * 8;
+    return (int)(b < cap ? b : cap);
 }
 
 // `d_poses` != NULL: input is n PoseRec (already decoded and corrected), `d_packets` etc. unused.
@@ -602,73 +973,101 @@ int integrate_tiled(const occgrid_geom* geom, const uint8_t* d_packets, const Po
                     const int32_t* d_agent_idx, const double* d_drift, const double* d_agent_off,
                     int n_agents, int8_t* d_grid, int32_t* d_counts, void* d_ws, size_t ws_bytes, uint64_t* d_counters,
                     cudaStream_t st) {
-    const TiledLayout L = tiled_layout(geom, n);
+    const TiledLayout L = tiled_layout(geom, n, d_poses == nullptr);
     if (ws_bytes < L.total) {
         set_last_error("workspace %zu B < %zu B needed by TILED for %lld records", ws_bytes, L.total, (long long)n);
         return OCCGRID_E_WORKSPACE;
     }
-    char* ws = reinterpret_cast<char*>(d_ws);
-    unsigned int* stamps = reinterpret_cast<unsigned int*>(ws + L.off_stamps);
-    unsigned int* tile_count = reinterpret_cast<unsigned int*>(ws + L.off_count);
-    unsigned int* tile_offset = reinterpret_cast<unsigned int*>(ws + L.off_offset);
-    unsigned int* tile_cursor = reinterpret_cast<unsigned int*>(ws + L.off_cursor);
-    unsigned int* active = reinterpret_cast<unsigned int*>(ws + L.off_active);
-    TilePlanHeader* hdr = reinterpret_cast<TilePlanHeader*>(ws + L.off_hdr);
-    uint4* items = reinterpret_cast<uint4*>(ws + L.off_items);
-    unsigned int* bins = reinterpret_cast<unsigned int*>(ws + L.off_bins);
-    const PoseRec* recs = d_poses ? d_poses : reinterpret_cast<const PoseRec*>(ws + L.off_recs);
-    int* tile_ids = reinterpret_cast<int*>(ws + L.off_ids);
+    const TiledPtrs P = tiled_ptrs(L, d_ws);
+    const PoseRec* recs = d_poses ? d_poses : P.recs;
     const Geom g = to_geom(geom);
     const TileGeom tg = tile_geom(geom);
     const unsigned int blocks = (unsigned int)((n + kPkPerCta - 1) / kPkPerCta);
-    const size_t win_bytes = (size_t)tg.win_side * tg.pitch * 4;
-    int sms = 148;
-    {
-        int dev = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    static thread_local size_t configured_smem = 0;
-    if (win_bytes > configured_smem) {
-        OCC_CUDA_TRY(cudaFuncSetAttribute(k_home_raycast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_bytes));
-        OCC_CUDA_TRY(cudaFuncSetAttribute(k_home_raycast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_bytes));
-        configured_smem = win_bytes;
-    }
-    int ctas_per_sm = 1;
-    const cudaError_t occ_rc = d_counts ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_home_raycast<true>, kTT, win_bytes)
-                                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_home_raycast<false>, kTT, win_bytes);
-    if (occ_rc != cudaSuccess || ctas_per_sm < 1)
-        ctas_per_sm = 1;
-    if (g_raycast_cta_cap > 0 && ctas_per_sm > g_raycast_cta_cap) ctas_per_sm = g_raycast_cta_cap;
+    SegInfo seg;
+    seg.n_segs = 1; seg.seg_cap = (unsigned int)align_up((size_t)n, kSegChunk); seg.d_counts = nullptr; seg.host_count = (unsigned int)n;
+    const long long n_chunks = (n + kSegChunk - 1) / kSegChunk;
     {
         ProfileScope ps(K_TILE_COUNT, st);
         if (d_poses)
-            k_home_count_poses<<<blocks, kTT, 0, st>>>(g, tg, d_poses, n, tile_count, tile_ids, active, hdr, d_counters);
+            k_home_count_poses<<<grid_chunks(n_chunks), kTT, 0, st>>>(g, tg, d_poses, seg, n_chunks, 0, P.tile_count, P.tile_ids, P.active,
+                                                                      P.hdr, d_counters);
         else
             k_home_count<<<blocks, kTT, 0, st>>>(g, tg, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents,
-                                                tile_count, tile_ids, reinterpret_cast<PoseRec*>(ws + L.off_recs), active, hdr,
-                                                d_counters);
+                                                P.tile_count, P.tile_ids, P.recs, P.active, P.hdr, d_counters);
     }
     {
         ProfileScope ps(K_TILE_SCAN, st);
-        k_tile_plan<<<1, 1024, 0, st>>>(tile_count, tile_offset, tile_cursor, items, L.max_items, active, L.max_records, hdr,
+        k_tile_plan<<<1, 1024, 0, st>>>(P.tile_count, P.tile_offset, P.tile_cursor, P.items, L.max_items, P.active, L.max_records, P.hdr,
                                         d_counters);
     }
     {
         ProfileScope ps(K_TILE_SCATTER, st);
-        k_home_scatter<<<blocks, kTT, 0, st>>>(n, tile_ids, tile_offset, tile_cursor, hdr, bins);
+        k_home_scatter<<<blocks, kTT, 0, st>>>(n, P.tile_ids, P.tile_offset, P.tile_cursor, P.hdr, P.bins);
     }
-    {
-        ProfileScope ps(K_TILE_RAYCAST, st);
-        if (d_counts)
-            k_home_raycast<true><<<sms * ctas_per_sm, kTT, win_bytes, st>>>(g, tg, items, hdr, bins, recs, ordinals_in_records,
-                                                                            reinterpret_cast<unsigned int*>(d_counts), d_counters);
-        else
-            k_home_raycast<false><<<sms * ctas_per_sm, kTT, win_bytes, st>>>(g, tg, items, hdr, bins, recs, ordinals_in_records, stamps,
-                                                                             d_counters);
-    }
+    RouteJob none = {};
+    if (d_counts) launch_raycast<true, false>(g, tg, P, recs, ordinals_in_records, reinterpret_cast<unsigned int*>(d_counts), d_counters, 1, none, st);
+    else          launch_raycast<false, false>(g, tg, P, recs, ordinals_in_records, P.stamps, d_counters, 1, none, st);
     if (!d_counts) {
         ProfileScope ps(K_TILE_RESOLVE, st);
-        k_home_resolve<<<sms * 8, kTT, 0, st>>>(g, tg, active, hdr, stamps, d_grid);
+        k_home_resolve<<<device_sm_count() * 8, kTT, 0, st>>>(g, tg, P.active, P.hdr, P.stamps, d_grid);
+    }
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
+}
+
+// ---- multi-GPU band step (include/occgrid_b200.h: occgrid_band_*) ---------------------------
+// count -> plan -> scatter over the per-source segments of a receive slot.
+int tiled_prepare_poses(const occgrid_geom* geom, const PoseRec* d_recs, const SegInfo& seg, int tiles_in_records,
+                        void* d_ws, size_t ws_bytes, uint64_t* d_counters, cudaStream_t st) {
+    const int64_t max_records = (int64_t)seg.n_segs * seg.seg_cap;
+    const TiledLayout L = tiled_layout(geom, max_records, false);
+    if (ws_bytes < L.total) {
+        set_last_error("workspace %zu B < %zu B needed by the band step for %lld record addresses", ws_bytes, L.total, (long long)max_records);
+        return OCCGRID_E_WORKSPACE;
+    }
+    const TiledPtrs P = tiled_ptrs(L, d_ws);
+    const Geom g = to_geom(geom);
+    const TileGeom tg = tile_geom(geom);
+    const long long n_chunks = max_records / kSegChunk;
+    {
+        ProfileScope ps(K_TILE_COUNT, st);
+        k_home_count_poses<<<grid_chunks(n_chunks), kTT, 0, st>>>(g, tg, d_recs, seg, n_chunks, tiles_in_records, P.tile_count, P.tile_ids,
+                                                                  P.active, P.hdr, d_counters);
+    }
+    {
+        ProfileScope ps(K_TILE_SCAN, st);
+        k_tile_plan<<<1, 1024, 0, st>>>(P.tile_count, P.tile_offset, P.tile_cursor, P.items, L.max_items, P.active, L.max_records, P.hdr,
+                                        d_counters);
+    }
+    {
+        ProfileScope ps(K_TILE_SCATTER, st);
+        k_home_scatter_segs<<<grid_chunks(n_chunks), kTT, 0, st>>>(seg, n_chunks, P.tile_ids, P.tile_offset, P.tile_cursor, P.hdr, P.bins);
+    }
+    OCC_CUDA_TRY(cudaGetLastError());
+    return OCCGRID_OK;
+}
+
+// The fused kernel: raycast the prepared batch (have_items) and, in between its work items, decode
+// and push the NEXT batch to the band owners (job != NULL); then resolve.
+int tiled_raycast_route(const occgrid_geom* geom, const PoseRec* d_recs, int have_items, const RouteJob* job,
+                        int8_t* d_grid, void* d_ws, size_t ws_bytes, int64_t max_records, uint64_t* d_counters, cudaStream_t st) {
+    const TiledLayout L = tiled_layout(geom, max_records, false);
+    if (ws_bytes < L.total) { set_last_error("workspace too small for the band step"); return OCCGRID_E_WORKSPACE; }
+    const TiledPtrs P = tiled_ptrs(L, d_ws);
+    const Geom g = to_geom(geom);
+    const TileGeom tg = tile_geom(geom);
+    if (!have_items) {
+        // nothing prepared (first step of a stream): the header still has to carry a clean queue
+        OCC_CUDA_TRY(cudaMemsetAsync(P.hdr, 0, sizeof(TilePlanHeader), st));
+    }
+    if (job) launch_raycast<false, true>(g, tg, P, d_recs, 1, P.stamps, d_counters, have_items, *job, st);
+    else {
+        RouteJob none = {};
+        launch_raycast<false, false>(g, tg, P, d_recs, 1, P.stamps, d_counters, have_items, none, st);
+    }
+    if (have_items) {
+        ProfileScope ps(K_TILE_RESOLVE, st);
+        k_home_resolve<<<device_sm_count() * 8, kTT, 0, st>>>(g, tg, P.active, P.hdr, P.stamps, d_grid);
     }
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;

@@ -3,23 +3,36 @@
 Integration — the global ``size`` x ``size`` grid is cut into ``world`` row bands, one per
 rank.  Cells are independent given a global beam order and a ray is at most
 MAX_DIST_M / res cells long (server_nodes/dual_bot_mapper.py:57), so the only exchange step is
-routing records to the band(s) their rays can reach:
+routing records to the band(s) their rays can reach.  Two exchange paths, same map:
 
-    local share --occgrid_route_packets--> decoded 48-byte records grouped by band
-                --all_to_all_single (NCCL over NVLink)--> records for my band, canonical order
-                --occgrid_integrate_poses(window = my band)--> my rows of the map
+``exchange='p2p'`` (default on GPUs) — the fused band step of ``csrc/occgrid_band.cu``:
+
+    call j:  occgrid_band_prepare(slot j-1)         bin what arrived during call j-1
+             occgrid_band_raycast_route(...)        ONE persistent kernel: raycast batch j-1 and,
+                                                    between its work items, decode batch j and
+                                                    store the 48-byte records straight into the
+                                                    band owners' per-source segments over NVLink
+             occgrid_band_publish(epoch j+1)        fill counts to the owners + cross-GPU barrier
+
+  everything stream-ordered on the caller's stream, no host read-back, two receive slots in
+  ``torch.distributed._symmetric_memory`` (plumbing: it hands out the peer pointers).
+
+``exchange='nccl'`` — ``occgrid_route_packets`` (records grouped by band in a send buffer) +
+``all_to_all_single`` + ``occgrid_integrate_poses``; also the path the CPU test-suite drives on
+``gloo`` with the oracle standing in for the device.
 
 There is no collective on the grid itself: bands are disjoint.  The canonical stream order is
-"rank 0's share, then rank 1's, ..."; routing is stable and all-to-all concatenates by source
-rank, so last-writer-wins on every band equals the single-GPU result (tests run the same
-exchange on one GPU and, with the oracle as the device, on 2 gloo ranks on the CPU).
+"rank 0's share, then rank 1's, ..."; every record carries its ordinal, so last-writer-wins on
+every band equals the single-GPU result.
 
-Merge — the reference's fuse is a sequential chain (each callback voxel-filters the whole
-accumulated cloud, map_merger.py:58-60), so only the HBM-bound part shards: every rank extracts
-and transforms its agents' grids, the point lists are all-gathered, and the (cheap, ordered)
-voxel chain is replicated on every rank — see ``ShardedMapMerger``.
+Merge — ``ShardedMapMerger``: agents are sharded, every rank rasterises its agents' clouds into a
+partial global grid over the all-reduced bounds and the partial grids are fused with a max
+reduction (occupied wins, map_merger.py:103-111 is idempotent and order-free).
 """
 from __future__ import annotations
+
+import ctypes
+import logging
 
 import numpy as np
 import torch
@@ -27,6 +40,9 @@ import torch.distributed as dist
 
 from . import _native
 from ._native import Geom, OccGridError
+
+log = logging.getLogger('occgrid_b200.distributed')
+SEG_CHUNK = 2048            # kSegChunk: segment capacities are multiples of this
 
 
 class BandLayout:
@@ -48,7 +64,7 @@ class BandLayout:
 
 
 class CudaBandOps:
-    """Device side of one rank: routing kernel + windowed OccupancyGrid."""
+    """Device side of one rank: windowed OccupancyGrid + the NCCL-variant routing kernel."""
 
     def __init__(self, layout, rank, size, resolution, origin_x, origin_y, device, strategy, max_batch):
         from .dual_bot_mapper import OccupancyGrid
@@ -84,23 +100,12 @@ class CudaBandOps:
             self._counts.data_ptr(), self._status.data_ptr(), None,
             self._ws.data_ptr(), self._ws.numel(), torch.cuda.current_stream(self.device).cuda_stream)
         _native.check(rc, 'occgrid_route_packets')
-        host = torch.cat([self._counts, self._status.to(torch.int64)]).cpu().tolist()   # the only host sync of a step
+        host = torch.cat([self._counts, self._status.to(torch.int64)]).cpu().tolist()   # the NCCL variant needs the split sizes
         counts, status = host[:nb], host[nb]
         if status & 1:
             self._status.zero_()
             raise OccGridError('route: send buffer overflow')
         return self._send[:int(sum(counts))], counts
-
-    def route_p2p(self, packets, agent_idx, drift, agent_table, ordinal_base, recv_ptrs, count_ptrs, capacity):
-        """Fused route + exchange: records go straight into the owners' receive buffers."""
-        n, stride = packets.shape
-        rc = self._lib.occgrid_route_packets_p2p(
-            self._geom, self.layout.n_bands, self._band_y0.ctypes.data, packets.data_ptr(), n, stride,
-            42 if stride >= 42 else 41,
-            agent_idx.data_ptr() if agent_idx is not None else None, drift.data_ptr() if drift is not None else None,
-            agent_table.data_ptr(), agent_table.shape[0] - 1, int(ordinal_base), recv_ptrs.data_ptr(), count_ptrs.data_ptr(),
-            int(capacity), self._status.data_ptr(), None, torch.cuda.current_stream(self.device).cuda_stream)
-        _native.check(rc, 'occgrid_route_packets_p2p')
 
     def empty(self, rows, stride, dtype):
         shape = (rows, stride) if stride else (rows,)
@@ -113,80 +118,214 @@ class CudaBandOps:
         return self.grid.grid_tensor
 
 
-class PeerExchange:
-    """Receive buffers in symmetric (peer-mapped) memory for the fused route+exchange kernel
-    ``occgrid_route_packets_p2p``: three slots per rank so that one cross-GPU barrier per step is
-    enough (passing barrier j implies every rank finished integrating batch j-2, whose slot is the
-    one batch j+1 will be written into)."""
-    SLOTS = 3
+class BandBuffers:
+    """Receive side of the fused band step for ONE rank: two slots of ``world`` per-source segments
+    of ``seg_cap`` 48-byte records, the per-slot fill counts and the barrier flags.  ``symmetric``:
+    allocate in ``torch.distributed._symmetric_memory`` and rendezvous, so that every rank can
+    address every other rank's buffers over NVLink; otherwise plain device tensors (world == 1, or
+    several logical ranks on one GPU in the tests)."""
+    SLOTS = 2
+    CTL_WORDS = 64 * (SLOTS + 1)          # seg_counts[slot][64] ..., flags[64]
 
-    def __init__(self, device, group, capacity):
-        import torch.distributed._symmetric_memory as symm
-        self.device = device
-        self.world = dist.get_world_size(group)
-        self.rank = dist.get_rank(group)
-        self.capacity = int(capacity)
-        pg = group if group is not None else dist.group.WORLD
-        self.recv = symm.empty((self.SLOTS, self.capacity, 48), dtype=torch.uint8, device=device)
-        self.count = symm.empty((self.SLOTS, 64), dtype=torch.int32, device=device)      # one counter per 256 B
-        self.count.zero_()
-        self.h_recv = symm.rendezvous(self.recv, pg)
-        self.h_count = symm.rendezvous(self.count, pg)
-        self.recv_ptrs, self.count_ptrs = [], []
-        for s in range(self.SLOTS):
-            self.recv_ptrs.append(torch.tensor([int(p) + s * self.capacity * 48 for p in self.h_recv.buffer_ptrs],
-                                               dtype=torch.int64, device=device))
-            self.count_ptrs.append(torch.tensor([int(p) + s * 256 for p in self.h_count.buffer_ptrs],
-                                                dtype=torch.int64, device=device))
-        torch.cuda.synchronize(device)
-        dist.barrier(group=group)
-        self.group = group
+    def __init__(self, device, world, seg_cap, symmetric=False, group=None):
+        self.device, self.world, self.seg_cap = device, int(world), int(seg_cap)
+        rec_shape = (self.SLOTS, self.world, self.seg_cap, 48)
+        if symmetric:
+            import torch.distributed._symmetric_memory as symm
+            pg = group if group is not None else dist.group.WORLD
+            self.recv = symm.empty(rec_shape, dtype=torch.uint8, device=device)
+            self.ctl = symm.empty((self.CTL_WORDS,), dtype=torch.int32, device=device)
+            self.ctl.zero_()
+            torch.cuda.synchronize(device)
+            h_recv, h_ctl = symm.rendezvous(self.recv, pg), symm.rendezvous(self.ctl, pg)
+            self._handles = (h_recv, h_ctl)
+            self.recv_bases = [int(p) for p in h_recv.buffer_ptrs]
+            self.ctl_bases = [int(p) for p in h_ctl.buffer_ptrs]
+        else:
+            self.recv = torch.empty(rec_shape, dtype=torch.uint8, device=device)
+            self.ctl = torch.zeros((self.CTL_WORDS,), dtype=torch.int32, device=device)
+            self.recv_bases = self.ctl_bases = None         # filled by link()
 
-    def barrier(self):
-        """Cross-GPU barrier ordered on the current stream."""
-        try:
-            self.h_recv.barrier(channel=0)
-        except Exception:
-            dist.barrier(group=self.group)
+    def slot_ptr(self, slot):
+        return self.recv.data_ptr() + slot * self.world * self.seg_cap * 48
+
+    def seg_counts_ptr(self, slot):
+        return self.ctl.data_ptr() + slot * 256
+
+    def flags_ptr(self):
+        return self.ctl.data_ptr() + self.SLOTS * 256
+
+    @staticmethod
+    def link(buffers):
+        """Plain (non-symmetric) buffers of all logical ranks on one device: exchange base pointers."""
+        for b in buffers:
+            b.recv_bases = [o.recv.data_ptr() for o in buffers]
+            b.ctl_bases = [o.ctl.data_ptr() for o in buffers]
+
+    def pointer_tables(self):
+        """Device arrays of peer pointers: per slot the owners' slot bases and seg_counts, plus flags."""
+        dev = self.device
+        slot_bytes = self.world * self.seg_cap * 48
+        t = lambda v: torch.tensor(v, dtype=torch.int64, device=dev)
+        self.peer_recs = [t([p + s * slot_bytes for p in self.recv_bases]) for s in range(self.SLOTS)]
+        self.peer_seg_counts = [t([p + s * 256 for p in self.ctl_bases]) for s in range(self.SLOTS)]
+        self.peer_flags = t([p + self.SLOTS * 256 for p in self.ctl_bases])
+
+
+class BandStep:
+    """The fused band step of one rank (C ABI ``occgrid_band_*``): owns the windowed grid, the tiled
+    workspace sized for ``world`` segments, the local reservation counters and the step state."""
+
+    def __init__(self, layout, rank, size, resolution, origin_x, origin_y, device, max_batch, buffers=None,
+                 symmetric=False, group=None):
+        from .dual_bot_mapper import OccupancyGrid
+        self.layout, self.rank, self.world = layout, int(rank), layout.n_bands
+        self.device = torch.device(device)
+        self._lib = _native.lib()
+        self.size, self.res, self.ox, self.oy = int(size), float(resolution), float(origin_x), float(origin_y)
+        self.seg_cap = -(-max(int(max_batch), 1) // SEG_CHUNK) * SEG_CHUNK
+        self.ordinal_stride = (1 << 29) // (self.world + 1)
+        if self.seg_cap > self.ordinal_stride:
+            raise OccGridError(f'max_batch {max_batch} exceeds the per-rank ordinal slice {self.ordinal_stride} '
+                               f'(2^29 order stamps shared by {self.world} ranks)')
+        # the band's own grid: strategy tiled (the fused kernel IS the tiled raycast); its generic workspace stays minimal
+        self.grid = OccupancyGrid(size, resolution, origin_x, origin_y, device=device, window=layout.window(rank),
+                                  strategy='tiled', max_batch=1, lazy_workspace=True)
+        self._geom = self.grid._geom
+        with torch.cuda.device(self.device):
+            nbytes = self._lib.occgrid_band_workspace_bytes(self._geom, self.world, self.seg_cap)
+            if nbytes == 0:
+                raise OccGridError('occgrid_band_workspace_bytes: ' + _native.last_error())
+            self._ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            self._resv = torch.zeros(64, dtype=torch.int32, device=self.device)
+            self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.buf = buffers if buffers is not None else BandBuffers(self.device, self.world, self.seg_cap, symmetric, group)
+        self._job = _native.RouteJob()
+        j = self._job
+        j.ox, j.oy, j.res, j.size_x = self.ox, self.oy, self.res, self.size
+        j.n_bands, j.src_rank = self.world, self.rank
+        for b in range(33):
+            j.band_y0[b] = layout.band_y0[min(b, self.world)]
+        j.seg_capacity = self.seg_cap
+        j.d_resv, j.d_status = self._resv.data_ptr(), self._status.data_ptr()
+        j.d_counters = self.grid._counters.data_ptr()
+        self._step = 0
+        self._pending = False       # a routed batch sits in slot (_step - 1) % 2, not yet integrated
+        self._keep = None           # tensors the in-flight job points at
+
+    def finish_init(self):
+        """After every rank's buffers exist (and, for plain buffers, BandBuffers.link ran)."""
+        with torch.cuda.device(self.device):
+            self.buf.pointer_tables()
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def step(self, pk, agent_idx, drift, agent_table, wait=True):
+        """Integrate the pending batch and route `pk` (uint8 cuda [n, stride]; None = nothing more to
+        route) in ONE fused kernel, then publish + barrier."""
+        lib, b = self._lib, self.buf
+        st = self._stream()
+        prev = (self._step - 1) % b.SLOTS
+        slot = self._step % b.SLOTS
+        cptr = self.grid._counters.data_ptr()
+        with torch.cuda.device(self.device):
+            if self._pending:
+                _native.check(lib.occgrid_band_prepare(self._geom, b.slot_ptr(prev), self.world, self.seg_cap,
+                                                       b.seg_counts_ptr(prev), self._ws.data_ptr(), self._ws.numel(), cptr, st),
+                              'occgrid_band_prepare')
+            job = None
+            if pk is not None and pk.shape[0] > 0:
+                n, stride = pk.shape
+                if n > self.seg_cap:
+                    raise OccGridError(f'batch of {n} records exceeds max_batch (segment capacity {self.seg_cap})')
+                j = self._job
+                j.d_packets, j.n, j.stride, j.rec_len = pk.data_ptr(), n, stride, 42 if stride >= 42 else 41
+                j.d_agent_idx = agent_idx.data_ptr() if agent_idx is not None else None
+                j.d_drift = drift.data_ptr() if drift is not None else None
+                j.d_agent_off, j.n_agents = agent_table.data_ptr(), agent_table.shape[0] - 1
+                j.ordinal_base = self.rank * self.ordinal_stride
+                j.d_peer_recs = b.peer_recs[slot].data_ptr()
+                job = ctypes.byref(j)
+                self._keep = (pk, agent_idx, drift, agent_table)
+            _native.check(lib.occgrid_band_raycast_route(self._geom, b.slot_ptr(prev), self.world, self.seg_cap,
+                                                         1 if self._pending else 0, job, self.grid.grid_tensor.data_ptr(),
+                                                         self._ws.data_ptr(), self._ws.numel(), cptr, st),
+                          'occgrid_band_raycast_route')
+            if self._pending:
+                self.grid._host_cache = None
+            self._pending = False
+            if pk is not None:         # every rank publishes every step, even an empty share, so the barrier lines up
+                _native.check(lib.occgrid_band_publish(self.world, self.rank, self._resv.data_ptr(), self.seg_cap,
+                                                       b.peer_seg_counts[slot].data_ptr(), b.peer_flags.data_ptr(), b.flags_ptr(),
+                                                       self._step + 1, 1 if wait else 0, self._status.data_ptr(), st),
+                              'occgrid_band_publish')
+                self._pending = True
+                self._step += 1
+
+    def check_status(self):
+        st = int(self._status.item())
+        if st:
+            self._status.zero_()
+            raise OccGridError('band step: ' + ', '.join(n for bit, n in ((2, 'a receive segment overflowed (records dropped)'),
+                                                                          (4, 'the cross-GPU barrier timed out')) if st & bit))
 
 
 class TiledSwarmMap:
     """A global occupancy grid spatially tiled over the ranks of a process group.  Mirrors
-    ``OccupancyGrid``'s batched entry; each rank passes ITS share of the packet stream."""
+    ``OccupancyGrid``'s batched entry; each rank passes ITS share of the packet stream.
+
+    exchange   'p2p' (default): the fused raycast + route kernel over NVLink peer memory; the map is
+               complete after ``flush()`` (``gather_grid`` / ``counters`` flush first) because a
+               batch is integrated while the NEXT one is being routed.  'nccl': route kernel +
+               ``all_to_all_single`` + integrate, synchronous.  No silent switching: when symmetric
+               memory is unavailable 'p2p' raises.
+    ops        test seam of the 'nccl' path (tests/test_distributed_cpu.py drives the host logic on
+               gloo with the oracle as the device)."""
 
     def __init__(self, size, resolution=0.05, origin_x=-5.0, origin_y=-5.0, *, group=None, device=None,
-                 strategy='auto', max_batch=1 << 16, ops=None, pipeline=False, exchange='nccl'):
+                 strategy='auto', max_batch=1 << 16, ops=None, exchange=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.size, self.res, self.ox, self.oy = int(size), float(resolution), float(origin_x), float(origin_y)
         self.layout = BandLayout(size, self.world)
+        if exchange is None:
+            exchange = 'nccl' if ops is not None else 'p2p'
+        if exchange not in ('p2p', 'nccl'):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        self.exchange = exchange
+        self.band = None
+        self._recv_bufs = {}
+        if exchange == 'p2p':
+            if ops is not None:
+                raise ValueError("the 'ops' test seam belongs to exchange='nccl'")
+            if not torch.cuda.is_available():
+                raise OccGridError('no CUDA device: TiledSwarmMap has no CPU fallback')
+            device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+            self.band = BandStep(self.layout, self.rank, size, resolution, origin_x, origin_y, device, max_batch,
+                                 symmetric=self.world > 1, group=group)
+            if self.world == 1:
+                BandBuffers.link([self.band.buf])
+            self.band.finish_init()
+            self.local = self.band.grid
+            self.device = device
+            self._tab_cache = None
+            if self.world > 1:
+                torch.cuda.synchronize(device)
+                dist.barrier(group=group)
+            log.info('TiledSwarmMap rank %d/%d: exchange=p2p (fused raycast+route over peer memory), %d-record segments',
+                     self.rank, self.world, self.band.seg_cap)
+            return
         if ops is None:
             if not torch.cuda.is_available():
                 raise OccGridError('no CUDA device: TiledSwarmMap has no CPU fallback')
             device = device if device is not None else torch.device('cuda', torch.cuda.current_device())
             ops = CudaBandOps(self.layout, self.rank, size, resolution, origin_x, origin_y, device, strategy, max_batch)
         self.ops = ops
+        self.device = ops.device
         self.local = getattr(ops, 'grid', None)
-        self._recv_bufs = {}
-        self.pipeline = bool(pipeline) and hasattr(ops, 'grid')
-        self._pending = None
-        self._step = 0
-        self._slot_free = [None, None]
-        self._side = torch.cuda.Stream(device=ops.device, priority=-1) if self.pipeline else None   # router first
-        # exchange = 'p2p': routed records are stored straight into the owner's receive buffer over
-        # NVLink by the routing kernel (symmetric memory); 'nccl': send buffer + all_to_all_single
-        self.peer = None
-        self.exchange = 'nccl'
-        if exchange in ('p2p', 'auto') and self.world > 1 and hasattr(ops, 'grid'):
-            try:
-                self.peer = PeerExchange(ops.device, group, int(max_batch * 1.6) + 4096)
-                self.exchange = 'p2p'
-            except Exception as e:                      # no symmetric memory on this system: NCCL path
-                if exchange == 'p2p':
-                    raise
-                self.peer = None
-        self._done = {}
+        log.info('TiledSwarmMap rank %d/%d: exchange=nccl (send buffer + all_to_all_single)', self.rank, self.world)
 
     def _agent_table(self, separation, agent_offsets):
         if isinstance(agent_offsets, torch.Tensor):
@@ -195,29 +334,26 @@ class TiledSwarmMap:
             t = torch.tensor([[0.0, 0.0], [0.0, 0.0], [float(separation), 0.0]], dtype=torch.float64)
         else:
             t = torch.from_numpy(np.ascontiguousarray(agent_offsets, np.float64).reshape(-1, 2))
-        return t.to(self.ops.device)
+        return t.to(self.device)
 
-    def _exchange(self, send, counts, stride, dtype, slot=0):
+    # ---- exchange = 'nccl' -----------------------------------------------------------------
+    def _exchange(self, send, counts, stride, dtype):
         """all_to_all_single of row-segments; returns the rows received (concatenated by source
         rank, i.e. in canonical stream order)."""
-        if self.world == 1 and not self.pipeline:
+        if self.world == 1:
             return send
-        recv_counts = self._recv_counts if self.world > 1 else [int(send.shape[0])]
-        rows = int(sum(recv_counts))
-        key = (stride, dtype, slot)
+        rows = int(sum(self._recv_counts))
+        key = (stride, dtype)
         buf = self._recv_bufs.get(key)
         if buf is None or buf.shape[0] < rows:          # grown geometrically, then reused every step
             buf = self.ops.empty(int(rows * 1.25) + 1024, stride, dtype)
             self._recv_bufs[key] = buf
         out = buf[:rows]
-        if self.world == 1:              # pipelined single rank: the send buffer is reused by the next route
-            out.copy_(send)
-            return out
-        dist.all_to_all_single(out, send.contiguous(), output_split_sizes=recv_counts, input_split_sizes=counts,
+        dist.all_to_all_single(out, send.contiguous(), output_split_sizes=self._recv_counts, input_split_sizes=counts,
                                group=self.group)
         return out
 
-    def _route_and_exchange(self, packets, separation, drift, agent_offsets, agent_idx, slot):
+    def _update_packets_nccl(self, packets, separation, drift, agent_offsets, agent_idx):
         tab = self._agent_table(separation, agent_offsets)
         pk = self.ops.stage(packets)
         dev = pk.device
@@ -229,112 +365,48 @@ class TiledSwarmMap:
             c_out = torch.empty_like(c_in)
             dist.all_to_all_single(c_out, c_in, group=self.group)
             self._recv_counts = c_out.cpu().tolist()
-        return self._exchange(send, counts, send.shape[1], torch.uint8, slot)
-
-    def update_packets(self, packets, separation=0.0, drift=None, agent_offsets=None, agent_idx=None):
-        """Integrate this rank's share of the stream into the tiled map (all ranks must call).
-
-        With ``pipeline=True`` the call routes and exchanges THIS batch on a side stream while
-        the PREVIOUS batch is being integrated (NVLink traffic hidden behind SM work); the map is
-        complete after ``flush()`` (``gather_grid``/``counters`` flush first).  Batch order, and
-        with it last-writer-wins, is unchanged."""
-        if self.peer is not None:
-            return self._update_packets_p2p(packets, separation, drift, agent_offsets, agent_idx)
-        if not self.pipeline:
-            recv = self._route_and_exchange(packets, separation, drift, agent_offsets, agent_idx, 0)
-            self.ops.integrate(recv)
-            return int(recv.shape[0])
-        main = torch.cuda.current_stream(self.ops.device)
-        slot = self._step & 1
-        self._step += 1
-        with torch.cuda.stream(self._side):
-            if self._slot_free[slot] is not None:
-                self._side.wait_event(self._slot_free[slot])      # integrate that last read this buffer
-            recv = self._route_and_exchange(packets, separation, drift, agent_offsets, agent_idx, slot)
-            ready = torch.cuda.Event()
-            ready.record(self._side)
-        prev, self._pending = self._pending, (recv, ready, slot)
-        if prev is not None:
-            self._integrate_pending(prev, main)
+        recv = self._exchange(send, counts, send.shape[1], torch.uint8)
+        self.ops.integrate(recv)
         return int(recv.shape[0])
 
-    def _update_packets_p2p(self, packets, separation, drift, agent_offsets, agent_idx):
-        """Fused route+exchange over peer memory.  Side stream (or the current one when not
-        pipelined): wait for my integrate of batch j-2, route batch j into the owners' slot j%3,
-        cross-GPU barrier, read my fill counter.  Main stream: integrate my slot with the
-        ordinals carried by the records, zero its counter."""
-        px = self.peer
-        dev = self.ops.device
-        main = torch.cuda.current_stream(dev)
-        j = self._step
-        self._step += 1
-        slot = j % px.SLOTS
-        # pipeline: put the PREVIOUS batch's integration on the main stream first, so that it runs
-        # while this batch is routed over NVLink on the side stream (the host then waits only for
-        # the router's fill counter)
-        if self.pipeline and self._pending is not None:
-            prev, self._pending = self._pending, None
-            self._integrate_p2p(prev, main)
-        stream = self._side if self.pipeline else main
-        with torch.cuda.stream(stream):
-            if self.pipeline and (j - 2) in self._done:
-                stream.wait_event(self._done.pop(j - 2))
-            tab = self._agent_table(separation, agent_offsets)
-            pk = self.ops.stage(packets)
+    # ---- public entry ----------------------------------------------------------------------
+    def update_packets(self, packets, separation=0.0, drift=None, agent_offsets=None, agent_idx=None):
+        """Integrate this rank's share of the stream into the tiled map (ALL ranks must call, with
+        an empty share if they have nothing).  exchange='p2p': asynchronous — this batch is routed
+        while the previous one is integrated; ``flush()`` completes the map."""
+        if self.band is None:
+            return self._update_packets_nccl(packets, separation, drift, agent_offsets, agent_idx)
+        dev = self.device
+        with torch.cuda.device(dev):
+            if isinstance(agent_offsets, torch.Tensor) and agent_offsets.is_cuda and agent_offsets.dtype == torch.float64 \
+                    and agent_offsets.is_contiguous():
+                tab = agent_offsets.reshape(-1, 2)
+            else:
+                tab = self._agent_table(separation, agent_offsets)
+            pk = self.local.stage_packets(packets)[0]
             idx = torch.as_tensor(agent_idx, dtype=torch.int32).to(dev).contiguous() if agent_idx is not None else None
             dr = torch.as_tensor(drift, dtype=torch.float64).reshape(-1, 2).to(dev).contiguous() if drift is not None else None
-            self.ops.route_p2p(pk, idx, dr, tab, self.rank * ((1 << 29) // (self.world + 1)), px.recv_ptrs[slot],
-                               px.count_ptrs[slot], px.capacity)
-            px.barrier()
-            host = torch.cat([px.count[slot, :1], self.ops._status]).cpu().tolist()      # the one host sync of a step
-            n_recv, status = int(host[0]), int(host[1])
-            if status & 1:
-                self.ops._status.zero_()
-                raise OccGridError('route_p2p: a receive buffer overflowed')
-            ready = torch.cuda.Event()
-            ready.record(stream)
-        pending = (slot, n_recv, ready, j)
-        if not self.pipeline:
-            self._integrate_p2p(pending, main)
-        else:
-            self._pending = pending
-        return n_recv
-
-    def _integrate_p2p(self, pending, main):
-        slot, n_recv, ready, j = pending
-        px = self.peer
-        main.wait_event(ready)
-        self.ops.grid.update_poses(px.recv[slot, :n_recv], ordinals_in_records=True)
-        px.count[slot].zero_()
-        done = torch.cuda.Event()
-        done.record(main)
-        self._done[j] = done
-
-    def _integrate_pending(self, pending, main):
-        recv, ready, slot = pending
-        main.wait_event(ready)
-        self.ops.integrate(recv)
-        done = torch.cuda.Event()
-        done.record(main)
-        self._slot_free[slot] = done
+            self.band.step(pk, idx, dr, tab)
+        return int(pk.shape[0])
 
     def flush(self):
-        """Integrate the batch still in flight (pipeline mode)."""
-        if self.pipeline and self._pending is not None:
-            pending, self._pending = self._pending, None
-            main = torch.cuda.current_stream(self.ops.device)
-            if self.peer is not None:
-                self._integrate_p2p(pending, main)
-            else:
-                self._integrate_pending(pending, main)
+        """exchange='p2p': integrate the batch still in flight and surface overflow / barrier errors."""
+        if self.band is not None:
+            if self.band._pending:
+                self.band.step(None, None, None, None)
+            self.band.check_status()
+
+    def counters(self, reset=False):
+        self.flush()
+        return self.local.counters(reset=reset)
 
     def gather_grid(self):
         """Assemble the global map on every rank (all_gather of the disjoint bands)."""
         self.flush()
-        band = self.ops.band_tensor()
+        band = self.local.grid_tensor if self.band is not None else self.ops.band_tensor()
         if self.world == 1:
             return band.cpu().numpy()
-        bands = [self.ops.empty(self.layout.window(b)[3], self.size, torch.int8) for b in range(self.world)]
+        bands = [torch.empty((self.layout.window(b)[3], self.size), dtype=torch.int8, device=band.device) for b in range(self.world)]
         dist.all_gather(bands, band.contiguous(), group=self.group)
         return torch.cat(bands, dim=0).cpu().numpy()
 
@@ -445,21 +517,21 @@ class ShardedMapMerger:
 #  bench.py helper: weak-scaling sessions
 # ----------------------------------------------------------------------------------------------
 
-def make_rank_sessions(world, rank, device, packets_per_rank, pool, strategy, pipeline=True,
-                       grid_per_gpu=4096, agents_per_gpu=64, exchange='auto', ingest='uniform'):
-    """Weak scaling of BASELINE configs[1]: (4096*world)^2 map, 64*world agents, each rank ingests
-    its own `packets_per_rank` share.  ``ingest='uniform'`` (default, the worst case): every
-    rank's share covers ALL agents, so (world-1)/world of the records are routed to another GPU;
-    ``'affine'``: a rank receives the agents that drive inside its own band (only rays crossing a
-    band edge are routed).  Returns (TiledSwarmMap, sessions, step_fn)."""
+def make_rank_sessions(world, rank, device, packets_per_rank, pool, strategy='auto',
+                       grid_per_gpu=4096, agents_per_gpu=64, exchange='p2p', ingest='uniform'):
+    """Weak scaling of BASELINE configs[1] / configs[3]: (grid_per_gpu*world)^2 map cut into `world`
+    row bands, agents_per_gpu*world agents, each rank ingests its own `packets_per_rank` share.
+    ``ingest='uniform'`` (default, the worst case): every rank's share covers ALL agents, so
+    (world-1)/world of the records travel to another GPU; ``'affine'``: a rank receives the agents
+    that drive inside its own band (only rays crossing a band edge travel).
+    Returns (TiledSwarmMap, sessions, step_fn)."""
     from . import simulation_tools as st
     side = grid_per_gpu * world
     origin = (-side * 0.05 / 2.0,) * 2
     tmap = TiledSwarmMap(side, 0.05, origin[0], origin[1], device=device, strategy=strategy,
-                         max_batch=int(packets_per_rank * 1.25), pipeline=pipeline, exchange=exchange)
+                         max_batch=int(packets_per_rank), exchange=exchange)
     sessions = []
     for i in range(pool):
-        # this rank's share of the stream: all 64*world agents, `packets_per_rank` records
         if ingest == 'affine':
             # this rank's own agents, their rooms on a lattice inside the band it owns
             y0 = tmap.layout.window(rank)[1]
@@ -469,9 +541,10 @@ def make_rank_sessions(world, rank, device, packets_per_rank, pool, strategy, pi
         else:
             sh = st.generate_session(n_agents=agents_per_gpu * world, n_packets=packets_per_rank, grid_size=side,
                                      origin=origin, seed=1000 + 97 * i + rank)
-        sessions.append({'packets': tmap.ops.stage(sh['packets']),
+        sessions.append({'packets': tmap.local.stage_packets(sh['packets'])[0],
                          'agent_idx': torch.from_numpy(sh['agent_idx']).to(device),
-                         'agent_offsets': torch.from_numpy(sh['agent_offsets']).to(device), 'grid': sh['grid']})
+                         'agent_offsets': torch.from_numpy(sh['agent_offsets']).to(device), 'grid': sh['grid'],
+                         'host': sh})
 
     def step(i):
         s = sessions[i % pool]

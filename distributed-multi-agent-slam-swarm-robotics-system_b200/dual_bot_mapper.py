@@ -98,7 +98,7 @@ class OccupancyGrid:
 
     def __init__(self, size=GRID_SIZE, resolution=GRID_RESOLUTION,
                  origin_x=GRID_ORIGIN_X, origin_y=GRID_ORIGIN_Y, *,
-                 device='cuda', window=None, strategy='auto', max_batch=1 << 16):
+                 device='cuda', window=None, strategy='auto', max_batch=1 << 16, lazy_workspace=False):
         self.size = int(size)
         self.res = float(resolution)
         self.ox = float(origin_x)
@@ -119,10 +119,12 @@ class OccupancyGrid:
         self._ws_capacity = 0
         self._host_cache = None
         self._pinned = None
+        self._pinned_busy = None
         self._copy_stream = None
         self._tab_cache = None
         self._fr = None
-        self._ensure_workspace(int(max_batch))
+        if not lazy_workspace:                  # (the multi-GPU band step brings its own workspace)
+            self._ensure_workspace(int(max_batch))
 
     # ---- workspace -----------------------------------------------------------------------
     def _ensure_workspace(self, n_packets):
@@ -255,13 +257,29 @@ class OccupancyGrid:
             packets = packets.contiguous()
             if not packets.is_pinned():          # pageable input: one pass through a pinned staging buffer
                 n = packets.numel()
-                if self._pinned is None or self._pinned.numel() < n:
-                    self._pinned = torch.empty(max(n, 1 << 16), dtype=torch.uint8).pin_memory()
-                stage = self._pinned[:n].view(packets.shape)
+                stage = self._pinned_staging(n)[:n].view(packets.shape)
                 stage.copy_(packets)
-                packets = stage
-            packets = packets.to(self.device, non_blocking=True)
+                packets = stage.to(self.device, non_blocking=True)
+                self._pinned_in_flight()
+            else:
+                packets = packets.to(self.device, non_blocking=True)
         return packets.contiguous(), kept
+
+    def _pinned_staging(self, nbytes):
+        """The reusable pinned staging buffer, safe to overwrite: the H2D copy that last read it
+        (possibly still queued behind earlier kernels) has completed."""
+        if self._pinned_busy is not None:
+            self._pinned_busy.synchronize()
+            self._pinned_busy = None
+        if self._pinned is None or self._pinned.numel() < nbytes:
+            self._pinned = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8).pin_memory()
+        return self._pinned
+
+    def _pinned_in_flight(self, stream=None):
+        """Call right after enqueueing an async copy out of the staging buffer."""
+        ev = torch.cuda.Event()
+        ev.record(stream if stream is not None else torch.cuda.current_stream(self.device))
+        self._pinned_busy = ev
 
     def update_packets(self, packets, separation=0.0, drift=None, agent_offsets=None,
                        agent_idx=None, rec_len=PACKET_SIZE):
@@ -310,8 +328,7 @@ class OccupancyGrid:
                 self._h2d = [torch.empty((self.h2d_chunk, 64), dtype=torch.uint8, device=self.device) for _ in range(2)]
                 self._h2d_free = [None, None]
             if not host.is_pinned():
-                if self._pinned is None or self._pinned.numel() < host.numel():
-                    self._pinned = torch.empty(max(host.numel(), 1 << 16), dtype=torch.uint8).pin_memory()
+                self._pinned_staging(host.numel())
             d_all = torch.as_tensor(drift, dtype=torch.float64).reshape(-1, 2) if drift is not None else None
             if d_all is not None and kept is not None and d_all.shape[0] != n:
                 d_all = d_all[torch.from_numpy(kept)]
@@ -331,6 +348,8 @@ class OccupancyGrid:
                     dst.copy_(src, non_blocking=True)
                     ready = torch.cuda.Event()
                     ready.record(self._copy_stream)
+                    if not host.is_pinned():
+                        self._pinned_busy = ready         # the staging buffer is free once the last chunk has left it
                 main.wait_event(ready)
                 self._integrate_device(dst, None, separation, None if d_all is None else d_all[lo:hi], agent_offsets,
                                        None if a_all is None else a_all[lo:hi], rec_len)

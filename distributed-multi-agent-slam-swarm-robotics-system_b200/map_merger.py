@@ -122,7 +122,8 @@ class MapMerger:
         if st:
             self._status.zero_()
             raise OccGridError('map merge overflow: ' + ', '.join(
-                n for b, n in ((1, 'point capacity'), (2, 'voxel lattice capacity')) if st & b))
+                n for b, n in ((1, 'point capacity'), (2, 'voxel lattice capacity'),
+                            (4, 'chain kernel aborted (a grid barrier timed out)')) if st & b))
 
     def _device_grid(self, msg):
         data = msg.data

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OCCGRID_ABI_VERSION 1
+#define OCCGRID_ABI_VERSION 2
 
 /* Cell values — dual_bot_mapper.py:92-94 (same convention as nav_msgs/OccupancyGrid.data). */
 #define OCCGRID_CELL_UNKNOWN  (-1)
@@ -74,8 +74,9 @@ typedef struct occgrid_pose_rec {
     double   rx, ry;      /* pose after `+ agent offset` (:851-852) and `+ drift` (:855-857) */
     float    yaw;         /* wire field, unchanged                                            */
     float    d[4];        /* front, left, back, right ranges in metres (:882-885)            */
-    uint32_t k;           /* index of the source record in its batch (informational)         */
-    uint32_t pad[2];
+    uint32_t k;           /* ordinal of the source record in the canonical stream            */
+    int32_t  tile;        /* home tile in the receiver's window (set by the fused router)    */
+    uint32_t pad;
 } occgrid_pose_rec;
 
 /* Counter slots (uint64 each, device memory, accumulated with atomics; caller zeroes). */
@@ -181,20 +182,60 @@ int occgrid_integrate_poses(const occgrid_geom* geom, const void* d_pose_recs, i
                             int8_t* d_grid, void* d_workspace, size_t workspace_bytes,
                             uint64_t* d_counters, int strategy, void* stream);
 
-/* Fused route + exchange over peer memory (NVLink): like occgrid_route_packets, but every record
- * is stored DIRECTLY into the receive buffer of the GPU that owns its band — d_peer_recv[b] and
- * d_peer_count[b] are device arrays of peer-mapped pointers (band b's occgrid_pose_rec buffer and
- * its uint32 fill counter, zeroed by the owner) — with one remote atomicAdd per band per CTA.
- * Records arrive in arbitrary order and carry rec.k = ordinal_base + index, the ordinal in the
- * canonical stream; the owner integrates with occgrid_integrate_poses(ordinals_in_records = 1)
- * after a cross-GPU barrier.  d_status bit 0 = a receive buffer overflowed. */
-int occgrid_route_packets_p2p(const occgrid_geom* geom, int n_bands, const int32_t* band_y0_host,
-                              const uint8_t* d_packets, int64_t n, int stride, int rec_len,
-                              const int32_t* d_agent_idx, const double* d_drift,
-                              const double* d_agent_off, int n_agents, uint32_t ordinal_base,
-                              void* const* d_peer_recv, uint32_t* const* d_peer_count,
-                              int64_t recv_capacity, int32_t* d_status, uint64_t* d_counters,
-                              void* stream);
+/* ---- Multi-GPU row-band step: fused raycast + route over NVLink peer memory ------
+ *
+ * One GPU per row band of the global grid.  Every rank ingests ITS share of the packet stream
+ * (the reference's ingest loop, dual_bot_mapper.py:816-843, once per server socket); a record has
+ * to reach the owner of every band its rays can touch (robot row +- ceil(MAX_DIST_M/res)+2).
+ * Receive buffers live in peer-mapped memory: each rank owns, per slot (2 slots), `n_bands`
+ * per-SOURCE segments of `seg_capacity` occgrid_pose_rec (a multiple of 2048) plus uint32
+ * seg_counts[n_bands]; a source reserves slots in ITS segment with a local atomic, so no remote
+ * atomics and no counts exchange are needed.  One step on every rank, all stream-ordered:
+ *
+ *   occgrid_band_prepare(slot j-1)          bin the records that arrived during the last step
+ *   occgrid_band_raycast_route(slot j-1, job -> peers' slot j)
+ *                                           ONE persistent kernel: raycast batch j-1 and, between
+ *                                           its work items, decode batch j and store the records
+ *                                           straight into the band owners' segments (compute and
+ *                                           NVLink traffic overlap); then stamps -> int8 band
+ *   occgrid_band_publish(slot j, epoch j+1) seg_counts to the owners + cross-GPU barrier
+ *
+ * Records carry rec.k = ordinal_base + index (canonical stream = rank 0's share, then rank 1's,
+ * ...; last writer wins exactly as on one GPU) and rec.tile = home tile in the owner's window.
+ * d_status bits: 2 = a segment overflowed (records dropped), 4 = the barrier timed out. */
+typedef struct occgrid_route_job {
+    const uint8_t* d_packets;      /* this rank's share of the NEXT batch: n records, `stride` apart */
+    int64_t        n;
+    int32_t        stride, rec_len;
+    const int32_t* d_agent_idx;    /* optional, as in occgrid_integrate_packets                      */
+    const double*  d_drift;        /* optional [n][2]                                                */
+    const double*  d_agent_off;    /* [n_agents + 1][2]                                              */
+    int32_t        n_agents;
+    uint32_t       ordinal_base;   /* ordinal of record 0 in the canonical stream                    */
+    double         ox, oy, res;    /* GLOBAL grid geometry                                           */
+    int32_t        size_x;         /* global width in cells (bands are full rows)                    */
+    int32_t        n_bands, src_rank;
+    int32_t        band_y0[33];    /* band b = rows [band_y0[b], band_y0[b+1])                       */
+    void* const*   d_peer_recs;    /* DEVICE array [n_bands]: owner b's receive slot (segment 0)     */
+    int64_t        seg_capacity;
+    uint32_t*      d_resv;         /* LOCAL uint32[n_bands], zero before the batch's first item      */
+    int32_t*       d_status;
+    uint64_t*      d_counters;     /* optional: packets/accepted/dropped/bad_pose of this share      */
+} occgrid_route_job;
+
+size_t occgrid_band_workspace_bytes(const occgrid_geom* band_geom, int n_segs, int64_t seg_capacity);
+int occgrid_band_prepare(const occgrid_geom* band_geom /* window = my band */, const void* d_recv_slot, int n_segs,
+                         int64_t seg_capacity, const uint32_t* d_seg_counts, void* d_workspace,
+                         size_t workspace_bytes, uint64_t* d_counters, void* stream);
+int occgrid_band_raycast_route(const occgrid_geom* band_geom, const void* d_recv_slot, int n_segs,
+                               int64_t seg_capacity, int have_prepared /* 0: nothing to raycast yet */,
+                               const occgrid_route_job* job /* NULL: nothing to route */, int8_t* d_grid,
+                               void* d_workspace, size_t workspace_bytes, uint64_t* d_counters, void* stream);
+int occgrid_band_publish(int n_bands, int rank, uint32_t* d_resv, int64_t seg_capacity,
+                         uint32_t* const* d_peer_seg_counts /* DEVICE array: owner b's seg_counts of the slot */,
+                         uint32_t* const* d_peer_flags /* DEVICE array: owner b's uint32 flags[n_bands] */,
+                         const uint32_t* d_my_flags, uint32_t epoch, int wait /* 0: publish only */,
+                         int32_t* d_status, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  *  Map fusion — server_nodes/map_merger.py:35-127

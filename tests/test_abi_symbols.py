@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported():
 def test_host_only_entry_points():
     from occgrid_b200 import _native
     lib = _native.lib()
-    assert lib.occgrid_abi_version() == 1
+    assert lib.occgrid_abi_version() == 2
     g = _native.Geom(-5.0, -5.0, 0.05, 200, 200, 0, 0, 200, 200)
     ga = lib.occgrid_workspace_bytes(g, 1000, _native.STRATEGY['global_atomic'])
     assert ga >= 200 * 200 * 4

@@ -58,9 +58,10 @@ def test_emulated_ranks_equal_single_grid(world, strategy):
     assert owned == c['updates']                         # every beam counted exactly once across bands
 
 
-def test_pipelined_swarm_map_single_rank():
-    """pipeline=True (route/exchange of batch i+1 on a side stream while batch i integrates):
-    same map as the oracle after flush(); exercised here with world = 1."""
+def test_fused_swarm_map_single_rank():
+    """exchange='p2p' with world = 1: the fused band step end to end (route batch i+1 inside the
+    persistent raycast kernel of batch i, per-source segments, device-side fill counts, publish):
+    same map as the oracle after flush()."""
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')
     from occgrid_b200 import simulation_tools as st
@@ -68,60 +69,102 @@ def test_pipelined_swarm_map_single_rank():
     from oracle import c_oracle
     size, origin = 1024, (-25.6, -25.6)
     sess = st.generate_session(n_agents=16, n_packets=90_000, grid_size=size, origin=origin, seed=21)
-    tmap = TiledSwarmMap(size, 0.05, origin[0], origin[1], max_batch=30_000, pipeline=True)
-    assert tmap.pipeline
+    tmap = TiledSwarmMap(size, 0.05, origin[0], origin[1], max_batch=30_000, exchange='p2p')
+    assert tmap.exchange == 'p2p' and tmap.band is not None
+    drift = np.random.default_rng(2).normal(0, 0.02, (90_000, 2))
     for i in range(3):
         sl = slice(i * 30_000, (i + 1) * 30_000)
-        tmap.update_packets(sess['packets'][sl], agent_offsets=sess['agent_offsets'], agent_idx=sess['agent_idx'][sl])
+        tmap.update_packets(sess['packets'][sl], agent_offsets=sess['agent_offsets'], agent_idx=sess['agent_idx'][sl],
+                            drift=drift[sl])
     got = tmap.gather_grid()            # flushes
     want = np.full((size, size), -1, np.int8)
     c = c_oracle.integrate_packets(sess['packets'], want, origin[0], origin[1], 0.05, agent_offsets=sess['agent_offsets'],
-                                   agent_idx=sess['agent_idx'])
+                                   agent_idx=sess['agent_idx'], drift=drift)
     assert np.array_equal(got, want)
-    assert tmap.local.counters()['owned_updates'] == c['updates']
+    cn = tmap.counters()
+    assert cn['owned_updates'] == c['updates'] and cn['packets'] == 90_000 and cn['beams'] == c['beams']
+    # a second stream after a flush continues on the same map (later batches still win)
+    tmap.update_packets(sess['packets'][:30_000], agent_offsets=sess['agent_offsets'], agent_idx=sess['agent_idx'][:30_000])
+    c_oracle.integrate_packets(sess['packets'][:30_000], want, origin[0], origin[1], 0.05, agent_offsets=sess['agent_offsets'],
+                               agent_idx=sess['agent_idx'][:30_000])
+    assert np.array_equal(tmap.gather_grid(), want)
+    with pytest.raises(Exception):
+        tmap.update_packets(sess['packets'][:40_000], agent_offsets=sess['agent_offsets'], agent_idx=sess['agent_idx'][:40_000])
+
+
+def _emulated_band_steps(world, size, origin, max_batch):
+    """`world` logical ranks on ONE GPU: plain receive buffers linked by pointer (peer-mapped over
+    NVLink in production), publish without the wait (the steps are issued one rank after another on
+    one stream, so a spinning barrier would never be released)."""
+    from occgrid_b200.distributed import BandBuffers, BandLayout, BandStep
+    layout = BandLayout(size, world)
+    steps = [BandStep(layout, r, size, 0.05, origin[0], origin[1], 'cuda', max_batch) for r in range(world)]
+    BandBuffers.link([s.buf for s in steps])
+    for s in steps:
+        s.finish_init()
+    return steps
 
 
 @pytest.mark.parametrize('world', [2, 4])
-def test_p2p_route_kernel_emulated_ranks(world):
-    """occgrid_route_packets_p2p on one GPU: every logical rank stores its records straight into
-    the band owners' receive buffers (plain device buffers here; peer-mapped over NVLink in
-    production) in arbitrary arrival order; owners integrate with the ordinals carried by the
-    records.  Assembled map == untiled oracle."""
+def test_fused_band_step_emulated_ranks(world):
+    """The fused raycast + route kernel on one GPU: every logical rank stores its records straight
+    into the band owners' per-source segments in arbitrary arrival order; owners bin what arrived
+    using the tile ids and ordinals carried by the records.  Three batches (so both receive slots
+    are reused); assembled map == untiled oracle over the canonical stream."""
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')
     from occgrid_b200 import simulation_tools as st
-    from occgrid_b200.distributed import BandLayout, CudaBandOps
     from oracle import c_oracle
     size, origin = 1024, (-25.6, -25.6)
-    sess = st.generate_session(n_agents=16, n_packets=60_000, grid_size=size, origin=origin, seed=9)
+    n_batches, per_rank = 3, 20_000
+    sess = st.generate_session(n_agents=16, n_packets=n_batches * per_rank * world, grid_size=size, origin=origin, seed=9)
     n = sess['packets'].shape[0]
     offs = sess['agent_offsets'].copy()
-    offs[1:3] = (-2.0, origin[1] + size * 0.05 / world - 1.0)
+    offs[1:3] = (-2.0, origin[1] + size * 0.05 / world - 1.0)     # rooms right on band boundaries: records go to two bands
     offs[3:5] = (3.0, origin[1] + size * 0.05 / 2 + 0.2)
     drift = np.random.default_rng(1).normal(0, 0.02, (n, 2))
-    layout = BandLayout(size, world)
-    ops = [CudaBandOps(layout, r, size, 0.05, origin[0], origin[1], 'cuda', 'auto', n) for r in range(world)]
+    steps = _emulated_band_steps(world, size, origin, per_rank)
     tab = torch.from_numpy(offs).cuda()
-    cap = n + 1024
-    recv = [torch.zeros((cap, 48), dtype=torch.uint8, device='cuda') for _ in range(world)]
-    cnt = [torch.zeros(64, dtype=torch.int32, device='cuda') for _ in range(world)]
-    recv_ptrs = torch.tensor([t.data_ptr() for t in recv], dtype=torch.int64, device='cuda')
-    cnt_ptrs = torch.tensor([t.data_ptr() for t in cnt], dtype=torch.int64, device='cuda')
-    stride = (1 << 29) // (world + 1)
-    for r in reversed(range(world)):                     # issue order must not matter
-        sl = slice(r * n // world, (r + 1) * n // world)
-        ops[r].route_p2p(ops[r].stage(sess['packets'][sl]), torch.from_numpy(sess['agent_idx'][sl].copy()).cuda(),
-                         torch.from_numpy(drift[sl].copy()).cuda(), tab, r * stride, recv_ptrs, cnt_ptrs, cap)
-    torch.cuda.synchronize()
-    bands, total = [], 0
-    for b in range(world):
-        m = int(cnt[b][0].item())
-        total += m
-        ops[b].grid.update_poses(recv[b][:m], ordinals_in_records=True)
-        bands.append(ops[b].band_tensor().cpu().numpy())
+    order = []
+    for b in range(n_batches):
+        base = b * per_rank * world
+        for r in reversed(range(world)):                          # issue order must not matter
+            sl = slice(base + r * per_rank, base + (r + 1) * per_rank)
+            steps[r].step(torch.from_numpy(sess['packets'][sl]).cuda(), torch.from_numpy(sess['agent_idx'][sl].copy()).cuda(),
+                          torch.from_numpy(drift[sl].copy()).cuda(), tab, wait=False)
+        order.append(np.arange(base, base + per_rank * world))
+    for s in steps:
+        s.step(None, None, None, None)
+        s.check_status()
+    got = np.concatenate([s.grid.grid for s in steps], axis=0)
+    o = np.concatenate(order)
     want = np.full((size, size), -1, np.int8)
-    c = c_oracle.integrate_packets(sess['packets'], want, origin[0], origin[1], 0.05, agent_offsets=offs,
-                                   agent_idx=sess['agent_idx'], drift=drift)
-    assert np.array_equal(np.concatenate(bands, axis=0), want)
-    assert n < total < 1.5 * n
-    assert sum(ops[b].grid.counters()['owned_updates'] for b in range(world)) == c['updates']
+    c = c_oracle.integrate_packets(sess['packets'][o], want, origin[0], origin[1], 0.05, agent_offsets=offs,
+                                   agent_idx=sess['agent_idx'][o], drift=drift[o])
+    assert np.array_equal(got, want)
+    cn = [s.grid.counters() for s in steps]
+    assert sum(x['owned_updates'] for x in cn) == c['updates']      # every beam counted exactly once across bands
+    assert sum(x['packets'] for x in cn) == n and sum(x['beams'] for x in cn) == c['beams']
+    assert n < sum(x['records'] for x in cn) < 1.5 * n              # boundary rooms are duplicated, the rest is not
+
+
+def test_fused_band_step_reports_segment_overflow():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from occgrid_b200 import simulation_tools as st
+    from occgrid_b200.distributed import OccGridError
+    size, origin = 512, (-12.8, -12.8)
+    sess = st.generate_session(n_agents=4, n_packets=6000, grid_size=size, origin=origin, seed=4)
+    steps = _emulated_band_steps(2, size, origin, 2048)
+    tab = torch.from_numpy(sess['agent_offsets']).cuda()
+    s = steps[0]
+    s.seg_cap_saved = s.seg_cap
+    pk = torch.from_numpy(sess['packets'][:2048]).cuda()
+    idx = torch.from_numpy(sess['agent_idx'][:2048].copy()).cuda()
+    s.step(pk, idx, None, tab, wait=False)
+    s.step(pk, idx, None, tab, wait=False)          # fine: the reservation counters were reset by publish
+    s.check_status()
+    s._resv[:2].fill_(2040)                         # pretend the segments are nearly full
+    s.step(pk, idx, None, tab, wait=False)
+    with pytest.raises(OccGridError, match='overflow'):
+        s.check_status()

@@ -1,6 +1,5 @@
 """Multi-GPU parity check (run under torchrun on N GPUs): every rank integrates its share of a
-seeded session through TiledSwarmMap (CUDA routing + NCCL all-to-all + windowed integration,
-pipelined), the bands are all-gathered and rank 0 compares the assembled map with the C oracle
+seeded session through TiledSwarmMap (fused raycast + route over peer memory, and the NCCL all-to-all variant), the bands are all-gathered and rank 0 compares the assembled map with the C oracle
 run over the canonical stream (batch by batch, rank 0's share first).  Prints PASS/FAIL."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -17,15 +16,9 @@ n_batches, per_rank = 3, 60_000
 sess = st.generate_session(n_agents=agents_per_gpu * world, n_packets=n_batches * per_rank * world, grid_size=size, origin=origin, seed=77)
 pk, idx, offs = sess['packets'], sess['agent_idx'], sess['agent_offsets']
 ok = True
-modes = [(True, 'p2p')] if os.environ.get('CHECK_PIPELINE_ONLY') else [(False, 'nccl'), (True, 'nccl'), (False, 'p2p'), (True, 'p2p')]
-for pipeline, exchange in modes:
-    try:
-        tmap = TiledSwarmMap(size, 0.05, origin[0], origin[1], device=dev, max_batch=per_rank * 2, pipeline=pipeline,
-                             exchange=exchange)
-    except Exception as e:
-        if rank == 0:
-            print(f'world={world} pipeline={pipeline} exchange={exchange}: UNAVAILABLE ({type(e).__name__}: {e})', flush=True)
-        continue
+modes = ['p2p'] if os.environ.get('CHECK_P2P_ONLY') else ['nccl', 'p2p']
+for exchange in modes:
+    tmap = TiledSwarmMap(size, 0.05, origin[0], origin[1], device=dev, max_batch=per_rank, exchange=exchange)
     order = []
     for b in range(n_batches):
         base = b * per_rank * world
@@ -40,7 +33,7 @@ for pipeline, exchange in modes:
         c = c_oracle.integrate_packets(pk[o], want, origin[0], origin[1], 0.05, agent_offsets=offs, agent_idx=idx[o])
         same = bool(np.array_equal(got, want))
         ok &= same
-        print(f'world={world} pipeline={pipeline} exchange={tmap.exchange}: map {"bit-exact" if same else "DIFFERS"} vs oracle '
+        print(f'world={world} exchange={tmap.exchange}: map {"bit-exact" if same else "DIFFERS"} vs oracle '
               f'({c["beams"]} beams, {int((want != -1).sum())} known cells)', flush=True)
     dist.barrier()
 # map fusion: agents dealt round-robin to ranks, extraction sharded, ordered voxel chain replicated

@@ -17,23 +17,22 @@ for strat in ('global_atomic', 'tiled'):
 g = M.OccupancyGrid(size=64)
 g.update_rays(np.random.default_rng(0).uniform(-1, 1, (500, 4)), np.ones(500, np.uint8))
 layout = BandLayout(512, 2)
-ops = [CudaBandOps(layout, r, 512, 0.05, -12.8, -12.8, 'cuda', 'auto', 6000) for r in range(2)]
+from occgrid_b200.distributed import BandBuffers, BandStep
+steps = [BandStep(layout, r, 512, 0.05, -12.8, -12.8, 'cuda', 3000) for r in range(2)]
+BandBuffers.link([b.buf for b in steps])
+for b in steps:
+    b.finish_init()
 tab = torch.from_numpy(s['agent_offsets']).cuda()
-recv = [torch.zeros((8000, 48), dtype=torch.uint8, device='cuda') for _ in range(2)]
-cnt = [torch.zeros(64, dtype=torch.int32, device='cuda') for _ in range(2)]
-rp = torch.tensor([t.data_ptr() for t in recv], dtype=torch.int64, device='cuda')
-cp = torch.tensor([t.data_ptr() for t in cnt], dtype=torch.int64, device='cuda')
+ops = [CudaBandOps(layout, r, 512, 0.05, -12.8, -12.8, 'cuda', 'auto', 6000) for r in range(2)]
 for r in range(2):
     sl = slice(r * 3000, (r + 1) * 3000)
     pk = ops[r].stage(s['packets'][sl])
-    ops[r].route(pk, None, None, tab)
-    ops[r].route_p2p(pk, None, None, tab, r * 100000, rp, cp, 8000)
-torch.cuda.synchronize()
-bands = []
-for b in range(2):
-    ops[b].grid.update_poses(recv[b][:int(cnt[b][0])], ordinals_in_records=True)
-    bands.append(ops[b].band_tensor().cpu().numpy())
-assert np.array_equal(np.concatenate(bands), want)
+    ops[r].route(pk, None, None, tab)                     # NCCL-variant routing kernels
+    steps[r].step(pk, None, None, tab, wait=False)        # fused raycast + route (first step: route only)
+for b in steps:
+    b.step(None, None, None, None)
+    b.check_status()
+assert np.array_equal(np.concatenate([b.grid.grid for b in steps]), want)
 import __graft_entry__ as ge
 ge.merge_smoke()
 print('sanitize_case ok')

@@ -191,8 +191,13 @@ def run_reference(args):
 
 def workload_config(n, grid_per_gpu=GRID_PER_GPU, agents_per_gpu=AGENTS_PER_GPU):
     side = grid_per_gpu * n
-    return {'workload': f'{agents_per_gpu * n} synthetic agents, {side}^2 grid at 5 cm, 1e7 beams/batch per GPU '
-                        f'(BASELINE.json configs[1]{"" if n == 1 else " scaled weakly: " + str(n) + " row bands"})',
+    if n == 1:
+        what = 'BASELINE.json configs[1]'
+    elif side == 65536 and agents_per_gpu * n == 1024:
+        what = 'BASELINE.json configs[3]: 1024 agents, 65536^2 grid spatially tiled across 8 GPUs'
+    else:
+        what = f'the per-GPU band of BASELINE.json configs[3] ({grid_per_gpu} x {side} cells, {agents_per_gpu} agents per GPU) on {n} row bands'
+    return {'workload': f'{agents_per_gpu * n} synthetic agents, {side}^2 grid at 5 cm, 1e7 beams/batch per GPU ({what})',
             'packets_per_batch_per_gpu': PACKETS_PER_BATCH, 'grid': f'{side}x{side} int8',
             'l2': f'{POOL} distinct 105 MB packet batches cycled (420 MB > 126 MB L2); grid/stamp hot set is '
                   'L2-resident by nature of the workload'}
@@ -201,6 +206,46 @@ def workload_config(n, grid_per_gpu=GRID_PER_GPU, agents_per_gpu=AGENTS_PER_GPU)
 # ----------------------------------------------------------------------------------------------
 #  GPU arm
 # ----------------------------------------------------------------------------------------------
+
+def multi_gpu_parity(torch, dist, dev, world, rank, exchange):
+    """Before timing at N > 1: the same exchange path on a small seeded stream (1024 rows per GPU,
+    16 agents per GPU, 3 batches of 40k packets per rank so both receive slots are reused), map
+    all-gathered and compared on rank 0 with the C oracle over the canonical stream — the checker
+    use of oracle/ (never timed).  -> {'map': 'bit-exact' | 'DIFFERS', ...} on every rank."""
+    from occgrid_b200 import simulation_tools as st
+    from occgrid_b200.distributed import TiledSwarmMap
+    size = 1024 * world
+    origin = (-size * 0.05 / 2,) * 2
+    n_batches, per_rank = 3, 40_000
+    sess = st.generate_session(n_agents=16 * world, n_packets=n_batches * per_rank * world, grid_size=size, origin=origin, seed=77)
+    pk, idx, offs = sess['packets'], sess['agent_idx'], sess['agent_offsets']
+    tmap = TiledSwarmMap(size, 0.05, origin[0], origin[1], device=dev, max_batch=per_rank, exchange=exchange)
+    order = []
+    for b in range(n_batches):
+        base = b * per_rank * world
+        sl = slice(base + rank * per_rank, base + (rank + 1) * per_rank)
+        tmap.update_packets(pk[sl], agent_offsets=offs, agent_idx=idx[sl])
+        order.append(np.arange(base, base + per_rank * world))          # canonical: rank 0's share, rank 1's, ...
+    got = tmap.gather_grid()
+    cn = tmap.counters()
+    owned = torch.tensor([cn['owned_updates']], device=dev, dtype=torch.int64)
+    dist.all_reduce(owned)
+    flag = torch.zeros(1, device=dev, dtype=torch.int64)
+    info = {}
+    if rank == 0:
+        from oracle import c_oracle
+        o = np.concatenate(order)
+        want = np.full((size, size), -1, np.int8)
+        c = c_oracle.integrate_packets(pk[o], want, origin[0], origin[1], 0.05, agent_offsets=offs, agent_idx=idx[o])
+        same = bool(np.array_equal(got, want)) and int(owned.item()) == c['updates']
+        flag[0] = 1 if same else 0
+        info = {'beams': int(c['beams']), 'known_cells': int((want != -1).sum()), 'grid': f'{size}x{size}',
+                'checker': 'oracle/occgrid_oracle.c over the canonical stream'}
+    dist.broadcast(flag, 0)
+    del tmap
+    torch.cuda.empty_cache()
+    return dict(info, map='bit-exact' if int(flag.item()) == 1 else 'DIFFERS', exchange=exchange, ranks=world)
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -212,9 +257,11 @@ def main():
     ap.add_argument('--packets', type=int, default=PACKETS_PER_BATCH)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--trace', action='store_true', help='print per-step wall times (debug)')
-    ap.add_argument('--grid-per-gpu', type=int, default=GRID_PER_GPU,
-                    help='N>1: map side = this x N (8192 with --agents-per-gpu 128 at N=8 = BASELINE configs[3])')
-    ap.add_argument('--agents-per-gpu', type=int, default=AGENTS_PER_GPU)
+    ap.add_argument('--grid-per-gpu', type=int, default=0,
+                    help='N>1: map side = this x N.  Default 8192 (with 128 agents per GPU: N=8 is BASELINE configs[3], '
+                         '65536^2 / 1024 agents; N=2 and 4 keep the same per-GPU band)')
+    ap.add_argument('--agents-per-gpu', type=int, default=0)
+    ap.add_argument('--no-parity', action='store_true', help='N>1: skip the bit-exactness check against the oracle before timing')
     ap.add_argument('--raycast-ctas', type=int, default=0, help='cap persistent raycast CTAs per SM (0 = max)')
     ap.add_argument('--ingest', default='uniform', choices=['uniform', 'affine'],
                     help='N>1: which agents a rank receives (uniform = all agents, the worst case; affine = the agents of its band)')
@@ -241,6 +288,10 @@ def main():
             os.environ['NCCL_DEBUG'] = 'WARN'        # NCCL's version banner goes to stdout; this script prints ONE JSON line
         dist.init_process_group('nccl', device_id=dev)
     n = world
+    if args.grid_per_gpu <= 0:
+        args.grid_per_gpu = GRID_PER_GPU if n == 1 else 8192
+    if args.agents_per_gpu <= 0:
+        args.agents_per_gpu = AGENTS_PER_GPU if n == 1 else 128
     W = max(args.warmup, 3)
     K = args.steps
     npk = args.packets
@@ -267,6 +318,14 @@ def main():
 
     else:
         from occgrid_b200.distributed import TiledSwarmMap, make_rank_sessions
+        parity = None
+        if not args.no_parity:
+            parity = multi_gpu_parity(torch, dist, dev, n, rank, args.exchange)
+            if parity['map'] != 'bit-exact':
+                if rank == 0:
+                    print(json.dumps({'metric': METRIC, 'n_gpus': n, 'parity': parity, 'error': 'multi-GPU map differs from the oracle'}))
+                dist.destroy_process_group()
+                raise SystemExit(3)
         tmap, sessions, step = make_rank_sessions(n, rank, dev, npk, POOL, args.strategy,
                                                    grid_per_gpu=args.grid_per_gpu, agents_per_gpu=args.agents_per_gpu,
                                                    exchange=args.exchange, ingest=args.ingest)
@@ -367,6 +426,7 @@ def main():
     if n > 1:
         result['exchange'] = tmap.exchange
         result['ingest'] = args.ingest
+        result['parity'] = parity
 
     # ---- single-GPU extras: scatter roofline, e2e, cpu baseline ------------------------------
     if n == 1:
@@ -458,7 +518,7 @@ def main():
         for i in range(Ke):
             s = sessions[i % POOL]
             tmap.update_packets(host[i % POOL], agent_offsets=s['agent_offsets'], agent_idx=s['agent_idx'])
-            grid.counters()                                   # D2H of the step's result
+            grid.counters()                                   # D2H of the counters as they stand (the step itself is asynchronous)
         tmap.flush()
         e1.record()
         torch.cuda.synchronize()

@@ -68,7 +68,8 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // addresses [s * seg_cap, s * seg_cap + count[s]).  count[] lives on the device (written by the
 // sources before the cross-GPU barrier) — the host never reads it.
 constexpr int kSegChunk = 2048;              // seg_cap is a multiple of this: a chunk never straddles two segments
-constexpr int kRouteItemPk = 256;            // packets per route work item of the fused kernel (one per thread)
+constexpr int kRouteItemPk = 256;            // packets per route sub-batch of the fused kernel (one per thread)
+constexpr int kRouteSubsPerItem = 4;         // sub-batches per route work item (software-pipelined loads)
 constexpr int kMaxBands = 32;
 
 struct SegInfo {
@@ -84,20 +85,22 @@ struct RouteJob {
     const uint8_t* pkts; long long n; int stride;
     const int32_t* agent_idx; const double* drift; const double* agent_off; int n_agents;
     unsigned int ordinal_base;
-    double ox, oy, res;                      // global grid geometry
+    double ox, oy, res, inv_res;             // global grid geometry
     int size_x;                              // bands are full-width rows: window x0 = 0, w = size_x
+    int reach, pad, tiles_x;                 // tile geometry of a band window (the same for every band)
     int n_bands, src_rank;
     int band_y0[kMaxBands + 1];
     PoseRec* const* peer_recs;               // device array [n_bands]: band owner's receive slot (its segment 0)
+    int* const* peer_tiles;                  // device array [n_bands]: the slot's compact tile ids (same addressing)
     unsigned int seg_cap;
     unsigned int* resv;                      // LOCAL reservation counters [n_bands]; zero when the batch starts
     int* status;                             // bit 1: a segment overflowed
     uint64_t* counters;                      // optional: packets / accepted / dropped / bad_pose of the routed share
-    unsigned int n_route_items;
+    unsigned int n_route_items;              // work items of kRouteItemPk * kRouteSubs packets
 };
 
 size_t tiled_band_workspace_bytes(const occgrid_geom* geom, int n_segs, int64_t seg_cap);
-int tiled_prepare_poses(const occgrid_geom* geom, const PoseRec* d_recs, const SegInfo& seg, int tiles_in_records,
+int tiled_prepare_poses(const occgrid_geom* geom, const PoseRec* d_recs, const int* d_tiles, const SegInfo& seg, int tiles_in_records,
                         void* d_ws, size_t ws_bytes, uint64_t* d_counters, cudaStream_t st);
 int tiled_raycast_route(const occgrid_geom* geom, const PoseRec* d_recs, int have_items, const RouteJob* job,
                         int8_t* d_grid, void* d_ws, size_t ws_bytes, int64_t max_records, uint64_t* d_counters, cudaStream_t st);

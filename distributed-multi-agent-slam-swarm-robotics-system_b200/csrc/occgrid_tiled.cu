@@ -103,6 +103,44 @@ __device__ __forceinline__ int hash_insert(unsigned int* keys, unsigned int tile
     }
 }
 
+// End of a binning CTA: every distinct tile of the shared-memory hash goes to the global counters
+// with ONE atomic.  The 16 slots a thread owns are handled in two unrolled phases so that all its
+// atomics are in flight together (the first-toucher test needs their return values; waiting for
+// each one in turn made these kernels pure L2 round-trip latency).
+constexpr int kHashPerThread = kHash / kTT;
+
+__device__ __forceinline__ void flush_tile_counts(const unsigned int* s_keys, const unsigned int* s_vals,
+                                                  unsigned int* __restrict__ tile_count, unsigned int* __restrict__ active,
+                                                  TilePlanHeader* __restrict__ hdr) {
+    unsigned int key[kHashPerThread], old[kHashPerThread];
+#pragma unroll
+    for (int j = 0; j < kHashPerThread; ++j) {
+        const int i = j * kTT + threadIdx.x;
+        key[j] = s_keys[i];
+        old[j] = 1u;
+        if (key[j] != kEmpty) old[j] = atomicAdd(&tile_count[key[j]], s_vals[i]);
+    }
+#pragma unroll
+    for (int j = 0; j < kHashPerThread; ++j)
+        if (key[j] != kEmpty && old[j] == 0u) active[atomicAdd(&hdr->active_count, 1u)] = key[j];      // first toucher lists the tile
+}
+
+// Scatter side: one range reservation per distinct tile; s_vals[slot] becomes the first bin slot.
+__device__ __forceinline__ void reserve_tile_ranges(const unsigned int* s_keys, unsigned int* s_vals,
+                                                    const unsigned int* __restrict__ tile_offset, unsigned int* __restrict__ tile_cursor) {
+    unsigned int key[kHashPerThread], base[kHashPerThread], off[kHashPerThread];
+#pragma unroll
+    for (int j = 0; j < kHashPerThread; ++j) {
+        const int i = j * kTT + threadIdx.x;
+        key[j] = s_keys[i];
+        base[j] = off[j] = 0u;
+        if (key[j] != kEmpty) { off[j] = tile_offset[key[j]]; base[j] = atomicAdd(&tile_cursor[key[j]], s_vals[i]); }
+    }
+#pragma unroll
+    for (int j = 0; j < kHashPerThread; ++j)
+        if (key[j] != kEmpty) s_vals[j * kTT + threadIdx.x] = off[j] + base[j];
+}
+
 __global__ void __launch_bounds__(kTT)
 k_home_count(Geom g, TileGeom tg, const uint8_t* __restrict__ pkts, long long n, int stride,
              const int32_t* __restrict__ agent_idx, const double* __restrict__ drift,
@@ -183,9 +221,7 @@ k_home_count(Geom g, TileGeom tg, const uint8_t* __restrict__ pkts, long long n,
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kHash; i += kTT)
-        if (s_keys[i] != kEmpty && atomicAdd(&tile_count[s_keys[i]], s_vals[i]) == 0u)
-            active[atomicAdd(&hdr->active_count, 1u)] = s_keys[i];          // first toucher lists the tile
+    flush_tile_counts(s_keys, s_vals, tile_count, active, hdr);
     // the staging buffer is free now: reuse it for the counter reduction (48 KB static limit)
     block_add_counters(c, reinterpret_cast<unsigned long long*>(s_rec), counters);
 }
@@ -206,7 +242,8 @@ __device__ __forceinline__ int chunk_valid(const SegInfo& seg, long long chunk, 
 // CTAs stride over 2048-address chunks and skip the empty ones.  `tiles_in_records`: the router
 // already computed the home tile for THIS window (rec.tile), nothing is re-derived here.
 __global__ void __launch_bounds__(kTT)
-k_home_count_poses(Geom g, TileGeom tg, const PoseRec* __restrict__ recs, SegInfo seg, long long n_chunks, int tiles_in_records,
+k_home_count_poses(Geom g, TileGeom tg, const PoseRec* __restrict__ recs, const int* __restrict__ in_tiles, SegInfo seg, long long n_chunks,
+                   int tiles_in_records,
                    unsigned int* __restrict__ tile_count, int* __restrict__ tile_ids,
                    unsigned int* __restrict__ active, TilePlanHeader* __restrict__ hdr, uint64_t* counters) {
     __shared__ unsigned int s_keys[kHash];
@@ -219,14 +256,29 @@ k_home_count_poses(Geom g, TileGeom tg, const PoseRec* __restrict__ recs, SegInf
         if (valid == 0) continue;                                   // uniform across the CTA
         for (int i = threadIdx.x; i < kHash; i += kTT) { s_keys[i] = kEmpty; s_vals[i] = 0u; }
         __syncthreads();
-        for (int sub = 0; sub < kSub; ++sub) {
-            const int j = sub * kTT + threadIdx.x;
-            if (j >= valid) break;
-            const long long k = addr0 + j;
-            int tile = -1;
-            if (tiles_in_records) {
-                tile = recs[k].tile;                                // packets / beams / hits were counted by the source rank
-            } else {
+        if (tiles_in_records) {
+            int tl[kSub];
+#pragma unroll
+            for (int sub = 0; sub < kSub; ++sub) {              // all loads of the thread in flight together
+                const int j = sub * kTT + threadIdx.x;
+                tl[sub] = -1;
+                if (j < valid) tl[sub] = in_tiles ? in_tiles[addr0 + j] : recs[addr0 + j].tile;
+            }
+#pragma unroll
+            for (int sub = 0; sub < kSub; ++sub) {
+                const int j = sub * kTT + threadIdx.x;
+                if (j >= valid) continue;
+                int tile = tl[sub];                             // packets / beams / hits were counted by the source rank
+                if (tile >= tg.n_tiles) tile = -1;              // never trust a tile id that came over the wire
+                if (tile >= 0) atomicAdd(&s_vals[hash_insert(s_keys, (unsigned int)tile)], 1u);
+                tile_ids[addr0 + j] = tile;
+            }
+        } else {
+            for (int sub = 0; sub < kSub; ++sub) {
+                const int j = sub * kTT + threadIdx.x;
+                if (j >= valid) break;
+                const long long k = addr0 + j;
+                int tile = -1;
                 const PoseRec r = recs[k];
                 c[OCCGRID_C_PACKETS] += 1;
                 if (!(isfinite(r.rx) && isfinite(r.ry) && isfinite(r.yaw))) c[OCCGRID_C_BAD_POSE] += 1;
@@ -240,15 +292,12 @@ k_home_count_poses(Geom g, TileGeom tg, const PoseRec* __restrict__ recs, SegInf
                     }
                     tile = home_tile(g, tg, r.rx, r.ry);
                 }
+                if (tile >= 0) atomicAdd(&s_vals[hash_insert(s_keys, (unsigned int)tile)], 1u);
+                tile_ids[k] = tile;
             }
-            if (tile >= tg.n_tiles) tile = -1;                      // never trust a tile id that came over the wire
-            if (tile >= 0) atomicAdd(&s_vals[hash_insert(s_keys, (unsigned int)tile)], 1u);
-            tile_ids[k] = tile;
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < kHash; i += kTT)
-            if (s_keys[i] != kEmpty && atomicAdd(&tile_count[s_keys[i]], s_vals[i]) == 0u)
-                active[atomicAdd(&hdr->active_count, 1u)] = s_keys[i];      // first toucher lists the tile
+        flush_tile_counts(s_keys, s_vals, tile_count, active, hdr);
         __syncthreads();
     }
     block_add_counters(c, s_acc, counters);
@@ -265,12 +314,18 @@ k_home_scatter(long long n, const int* __restrict__ tile_ids, const unsigned int
     __syncthreads();
     const long long cta_first = (long long)blockIdx.x * kPkPerCta;
     unsigned int where[kSub];          // (hash slot << 16) | rank within this CTA's share of the tile
+    int tl[kSub];
+#pragma unroll
+    for (int sub = 0; sub < kSub; ++sub) {
+        const long long k = cta_first + (long long)sub * kTT + threadIdx.x;
+        tl[sub] = k < n ? tile_ids[k] : -1;
+    }
 #pragma unroll
     for (int sub = 0; sub < kSub; ++sub) {
         const long long k = cta_first + (long long)sub * kTT + threadIdx.x;
         where[sub] = kEmpty;
         if (k < n) {
-            const int tile = tile_ids[k];
+            const int tile = tl[sub];
             if (tile >= 0) {
                 const int h = hash_insert(s_keys, (unsigned int)tile);
                 where[sub] = ((unsigned int)h << 16) | atomicAdd(&s_vals[h], 1u);
@@ -278,8 +333,7 @@ k_home_scatter(long long n, const int* __restrict__ tile_ids, const unsigned int
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kHash; i += kTT)          // one reservation per distinct tile
-        if (s_keys[i] != kEmpty) s_vals[i] = tile_offset[s_keys[i]] + atomicAdd(&tile_cursor[s_keys[i]], s_vals[i]);
+    reserve_tile_ranges(s_keys, s_vals, tile_offset, tile_cursor);          // one reservation per distinct tile
     __syncthreads();
 #pragma unroll
     for (int sub = 0; sub < kSub; ++sub) {
@@ -303,12 +357,18 @@ k_home_scatter_segs(SegInfo seg, long long n_chunks, const int* __restrict__ til
         for (int i = threadIdx.x; i < kHash; i += kTT) { s_keys[i] = kEmpty; s_vals[i] = 0u; }
         __syncthreads();
         unsigned int where[kSub];
+        int tl[kSub];
+#pragma unroll
+        for (int sub = 0; sub < kSub; ++sub) {
+            const int j = sub * kTT + threadIdx.x;
+            tl[sub] = j < valid ? tile_ids[addr0 + j] : -1;
+        }
 #pragma unroll
         for (int sub = 0; sub < kSub; ++sub) {
             const int j = sub * kTT + threadIdx.x;
             where[sub] = kEmpty;
             if (j < valid) {
-                const int tile = tile_ids[addr0 + j];
+                const int tile = tl[sub];
                 if (tile >= 0) {
                     const int h = hash_insert(s_keys, (unsigned int)tile);
                     where[sub] = ((unsigned int)h << 16) | atomicAdd(&s_vals[h], 1u);
@@ -316,8 +376,7 @@ k_home_scatter_segs(SegInfo seg, long long n_chunks, const int* __restrict__ til
             }
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < kHash; i += kTT)
-            if (s_keys[i] != kEmpty) s_vals[i] = tile_offset[s_keys[i]] + atomicAdd(&tile_cursor[s_keys[i]], s_vals[i]);
+        reserve_tile_ranges(s_keys, s_vals, tile_offset, tile_cursor);
         __syncthreads();
 #pragma unroll
         for (int sub = 0; sub < kSub; ++sub)
@@ -593,105 +652,221 @@ struct RouteSmem {
     unsigned int base[kMaxBands];       // reserved first slot in my segment of band b (0xffffffff: overflow)
 };
 
-__device__ __forceinline__ void route_item(const RouteJob& J, unsigned int item, unsigned int* s_buf /* >= 24.6 KB */,
-                                           RouteSmem& S, unsigned long long (&c)[6]) {
-    const long long first = (long long)item * kRouteItemPk;
-    const int count = (int)min((long long)kRouteItemPk, J.n - first);
-    if (threadIdx.x < kMaxBands) S.cnt[threadIdx.x] = 0u;
-    stage_records_t(J.pkts + (size_t)first * J.stride, (size_t)count * J.stride, reinterpret_cast<uint8_t*>(s_buf));
-    __syncthreads();
-    PoseRec rec = {};
-    int band[2] = {-1, -1}, tile[2] = {-1, -1};
-    unsigned int rank[2] = {0u, 0u};
-    if ((int)threadIdx.x < count) {
-        const long long k = first + threadIdx.x;
-        double rx, ry, ryaw;
-        float dist[4];
-        const int st = decode_packet(reinterpret_cast<const uint8_t*>(s_buf) + threadIdx.x * J.stride, k, J.agent_idx, J.drift,
-                                     J.agent_off, J.n_agents, &rx, &ry, &ryaw, dist);
-        c[OCCGRID_C_PACKETS] += 1; c[OCCGRID_C_ACCEPTED] += st == PKT_OK; c[OCCGRID_C_DROPPED] += st == PKT_DROPPED;
-        c[OCCGRID_C_BAD_POSE] += st == PKT_BAD_POSE;
-        if (st == PKT_OK) {
-            c[OCCGRID_C_BEAMS] += 4;
+// 32-bit little-endian field at byte offset `byte_off` (any alignment) of a buffer staged in shared
+// memory: two aligned word loads and a funnel shift instead of four byte loads.
+__device__ __forceinline__ unsigned int lds_u32_at(const unsigned int* __restrict__ words, unsigned int byte_off) {
+    const unsigned int w = byte_off >> 2, sh = (byte_off & 3u) * 8u;
+    return __funnelshift_r(words[w], words[w + 1], sh);
+}
+
+// Same result as decode_packet (beam_expand.cuh) for a record staged in shared memory.
+__device__ __forceinline__ int decode_packet_smem(const unsigned int* __restrict__ words, unsigned int byte_off, long long k,
+                                                  const int32_t* agent_idx, const double* drift, const double* agent_off,
+                                                  int n_agents, double* rx, double* ry, float* yaw, float dist[4]) {
+    if (lds_u32_at(words, byte_off) != 0x4c525351u) return PKT_DROPPED;                      // 'QSRL' (:840)
+    const unsigned int b4 = lds_u32_at(words, byte_off + 4);                                 // agent id, x[0..2]
+    const long long agent = agent_idx ? (long long)agent_idx[k] : (long long)(b4 & 0xffu);
+    if (agent < 1 || agent > n_agents) return PKT_DROPPED;                                   // :842
+    const unsigned int b8 = lds_u32_at(words, byte_off + 8), b12 = lds_u32_at(words, byte_off + 12),
+                       b16 = lds_u32_at(words, byte_off + 16);
+    double x = (double)__uint_as_float(__funnelshift_r(b4, b8, 8));                          // bytes 5..8
+    double y = (double)__uint_as_float(__funnelshift_r(b8, b12, 8));                         // bytes 9..12
+    const float fyaw = __uint_as_float(__funnelshift_r(b12, b16, 8));                        // bytes 13..16
+    x = OCC_DADD(x, agent_off[2 * agent + 0]);                                               // :851-852
+    y = OCC_DADD(y, agent_off[2 * agent + 1]);
+    if (drift) {                                                                             // :855-857
+        const double2 dv = *reinterpret_cast<const double2*>(drift + 2 * k);
+        x = OCC_DADD(x, dv.x);
+        y = OCC_DADD(y, dv.y);
+    }
+    if (!(isfinite(x) && isfinite(y) && isfinite(fyaw))) return PKT_BAD_POSE;
+    *rx = x; *ry = y; *yaw = fyaw;
+    const unsigned int c24 = lds_u32_at(words, byte_off + 24), c28 = lds_u32_at(words, byte_off + 28),
+                       c32 = lds_u32_at(words, byte_off + 32), c36 = lds_u32_at(words, byte_off + 36),
+                       c40 = lds_u32_at(words, byte_off + 40);
+    dist[0] = __uint_as_float(__funnelshift_r(c24, c28, 8));                                 // bytes 25..28
+    dist[1] = __uint_as_float(__funnelshift_r(c28, c32, 8));
+    dist[2] = __uint_as_float(__funnelshift_r(c32, c36, 8));
+    dist[3] = __uint_as_float(__funnelshift_r(c36, c40, 8));                                 // bytes 37..40
+    return PKT_OK;
+}
+
+// Robot cell along one axis: the screened quotient (r - o) * (1 / res) decides unless it lies within
+// the tolerance of an integer, where the reference's true division (:123-124) is evaluated.
+__device__ __forceinline__ bool robot_cell(double r, double o, double res, double inv_res, int* cell) {
+    double q = OCC_DMUL(OCC_DADD(r, -o), inv_res);
+    const double tol = OCC_DMUL(OCC_DMUL(fabs(r) + fabs(o) + 11.0, inv_res), 0x1p-47);
+    if (near_cell_boundary(q, tol)) q = cell_quotient(r, o, res);
+    if (!quotient_in_range(q)) return false;
+    *cell = trunc_cell(q);
+    return true;
+}
+
+// Statistics of the routed share, packed per thread (16 bits each, folded into the 64-bit counters
+// when the kernel ends): a = packets | accepted << 16, b = dropped | hits << 16.
+struct RouteStats { unsigned int a, b; };
+
+constexpr int kRouteSubs = kRouteSubsPerItem;
+
+__device__ __forceinline__ void route_load_sub(const RouteJob& J, long long first, int count, uint4 (&pre)[3]) {
+    const size_t bytes = (size_t)count * J.stride;
+    const uint4* src = reinterpret_cast<const uint4*>(J.pkts + (size_t)first * J.stride);
 #pragma unroll
-            for (int s2 = 0; s2 < 4; ++s2) {
-                const double dd = (double)dist[s2];
-                c[OCCGRID_C_HITS] += (OCC_MIN_DIST_M < dd && dd <= OCC_MAX_DIST_M) ? 1 : 0;      // :888
+    for (int j = 0; j < 3; ++j) {                   // <= 256 * 42 B = 672 chunks of 16 bytes: three per thread
+        const size_t i = (size_t)j * kTT + threadIdx.x;
+        pre[j] = (i * 16 + 16 <= bytes) ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+__device__ __noinline__ RouteStats route_item(const RouteJob& J, unsigned int item, unsigned int* s_buf /* >= 24.6 KB */,
+                                              RouteSmem& S, RouteStats st_in) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int lt = (1u << lane) - 1u;
+    // fast staging needs a 16-byte aligned sub-batch (stride 42: 256 * 42 = 10752 = 672 * 16) and <= 48-byte records
+    const bool vec = (reinterpret_cast<uintptr_t>(J.pkts) & 15) == 0 && ((kRouteItemPk * J.stride) & 15) == 0 && J.stride <= 48;
+    uint4 pre[3];
+    long long first = (long long)item * (kRouteItemPk * kRouteSubs);
+    int count = (int)max(0ll, min((long long)kRouteItemPk, J.n - first));
+    if (vec) route_load_sub(J, first, count, pre);
+    for (int sub = 0; sub < kRouteSubs && count > 0; ++sub) {
+        __syncthreads();                                                 // the previous sub-batch's copy-out has left the buffer
+        if (threadIdx.x < kMaxBands) S.cnt[threadIdx.x] = 0u;
+        if (vec) {
+            uint4* d4 = reinterpret_cast<uint4*>(s_buf);
+            const size_t bytes = (size_t)count * J.stride;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const size_t i = (size_t)j * kTT + threadIdx.x;
+                if (i * 16 + 16 <= bytes) d4[i] = pre[j];
             }
-            rec.rx = rx; rec.ry = ry; rec.yaw = (float)ryaw;             // ryaw came from an fp32 field: exact
-            rec.d[0] = dist[0]; rec.d[1] = dist[1]; rec.d[2] = dist[2]; rec.d[3] = dist[3];
-            rec.k = J.ordinal_base + (unsigned int)k; rec.pad = 0u;
-            const double qx = cell_quotient(rx, J.ox, J.res), qy = cell_quotient(ry, J.oy, J.res);
-            if (quotient_in_range(qx) && quotient_in_range(qy)) {
-                const int gx = trunc_cell(qx), gy = trunc_cell(qy);
-                const int reach = reach_cells_dev(J.res);
-                const int pad = ((reach + kTile - 1) / kTile) * kTile;
-                const int tiles_x = (J.size_x + 2 * pad + kTile - 1) >> kTileShift;
-                if (gx >= -reach && gx < J.size_x + reach) {
-                    int nb = 0;
-                    for (int b = 0; b < J.n_bands && nb < 2; ++b) {
-                        const int py = gy - J.band_y0[b];
-                        if (py >= -reach && py < J.band_y0[b + 1] - J.band_y0[b] + reach) {
-                            band[nb] = b;
-                            tile[nb] = ((py + pad) >> kTileShift) * tiles_x + ((gx + pad) >> kTileShift);
-                            ++nb;
+            for (size_t i = (bytes / 16) * 16 + threadIdx.x; i < bytes; i += kTT)
+                reinterpret_cast<uint8_t*>(s_buf)[i] = __ldg(J.pkts + (size_t)first * J.stride + i);
+        } else {
+            stage_records_t(J.pkts + (size_t)first * J.stride, (size_t)count * J.stride, reinterpret_cast<uint8_t*>(s_buf));
+        }
+        __syncthreads();
+        // the NEXT sub-batch's loads are in flight while this one is decoded, sorted and copied out
+        const long long next_first = first + kRouteItemPk;
+        const int next_count = sub + 1 < kRouteSubs ? (int)max(0ll, min((long long)kRouteItemPk, J.n - next_first)) : 0;
+        if (vec && next_count > 0) route_load_sub(J, next_first, next_count, pre);
+
+        double rx = 0.0, ry = 0.0;
+        float yaw = 0.f, dist[4] = {0.f, 0.f, 0.f, 0.f};
+        int band0 = -1, nb = 0, tile0 = -1, tile1 = -1;      // bands are contiguous rows: the second band is band0 + 1
+        const long long k = first + threadIdx.x;
+        if ((int)threadIdx.x < count) {
+            const int st = decode_packet_smem(s_buf, threadIdx.x * (unsigned int)J.stride, k, J.agent_idx, J.drift, J.agent_off,
+                                              J.n_agents, &rx, &ry, &yaw, dist);
+            st_in.a += 1u + (st == PKT_OK ? 0x10000u : 0u);
+            st_in.b += st == PKT_DROPPED ? 1u : 0u;
+            if (st == PKT_OK) {
+                unsigned int hits = 0;
+#pragma unroll
+                for (int s2 = 0; s2 < 4; ++s2) {
+                    const double dd = (double)dist[s2];
+                    hits += (OCC_MIN_DIST_M < dd && dd <= OCC_MAX_DIST_M) ? 1u : 0u;             // :888
+                }
+                st_in.b += hits << 16;
+                int gx, gy;
+                if (robot_cell(rx, J.ox, J.res, J.inv_res, &gx) && robot_cell(ry, J.oy, J.res, J.inv_res, &gy)) {
+                    const int reach = J.reach;
+                    if (gx >= -reach && gx < J.size_x + reach) {
+                        const int tcol = (gx + J.pad) >> kTileShift;
+                        for (int b = 0; b < J.n_bands; ++b) {
+                            if (gy - reach < J.band_y0[b + 1]) {             // first band whose rows end above the reach interval
+                                const int py = gy - J.band_y0[b];
+                                if (py >= -reach) {
+                                    band0 = b; nb = 1;
+                                    tile0 = ((py + J.pad) >> kTileShift) * J.tiles_x + tcol;
+                                    if (b + 1 < J.n_bands && gy + reach >= J.band_y0[b + 1]) {
+                                        nb = 2;
+                                        tile1 = ((gy - J.band_y0[b + 1] + J.pad) >> kTileShift) * J.tiles_x + tcol;
+                                    }
+                                }
+                                break;
+                            }
                         }
                     }
                 }
             }
         }
-    }
-    // rank of every entry inside its band's run (arrival order is free: ordinals travel in the records)
+        // rank of every entry inside its band's run (arrival order is free: ordinals travel in the records)
+        unsigned int rank0 = 0u, rank1 = 0u;
+        {
+            const unsigned int p0 = __match_any_sync(0xffffffffu, band0);
+            if (band0 >= 0) {
+                const int leader = __ffs(p0) - 1;
+                unsigned int b0 = 0;
+                if (lane == leader) b0 = atomicAdd(&S.cnt[band0], (unsigned int)__popc(p0));
+                rank0 = __shfl_sync(p0, b0, leader) + __popc(p0 & lt);
+            }
+            if (__any_sync(0xffffffffu, nb == 2)) {                      // rare: only next to a band edge
+                const unsigned int p1 = __match_any_sync(0xffffffffu, nb == 2 ? band0 + 1 : -1);
+                if (nb == 2) {
+                    const int leader = __ffs(p1) - 1;
+                    unsigned int b1 = 0;
+                    if (lane == leader) b1 = atomicAdd(&S.cnt[band0 + 1], (unsigned int)__popc(p1));
+                    rank1 = __shfl_sync(p1, b1, leader) + __popc(p1 & lt);
+                }
+            }
+        }
+        __syncthreads();                                                 // counts complete; raw packets decoded: the buffer is free
+        // every warp scans the <= 32 band counts in registers (lane b holds band b)
+        const unsigned int n_b = lane < J.n_bands ? S.cnt[lane] : 0u;
+        unsigned int inc = n_b;
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-        const unsigned int peers = __match_any_sync(0xffffffffu, band[e]);
-        if (band[e] >= 0) {
-            const int lane = threadIdx.x & 31;
-            const int leader = __ffs(peers) - 1;
-            unsigned int b0 = 0;
-            if (lane == leader) b0 = atomicAdd(&S.cnt[band[e]], (unsigned int)__popc(peers));
-            b0 = __shfl_sync(peers, b0, leader);
-            rank[e] = b0 + __popc(peers & ((1u << lane) - 1u));
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        const unsigned int my_off = inc - n_b;                           // exclusive offset of band `lane` in the sorted buffer
+        if (warp == 0) {                                                 // one reservation per band and sub-batch, on a LOCAL counter
+            unsigned int base = 0u;
+            if (n_b) {
+                base = atomicAdd(&J.resv[lane], n_b);
+                if (base + n_b > J.seg_cap) { atomicOr(J.status, 2); base = 0xffffffffu; }
+            }
+            S.base[lane] = base;                                         // (its latency overlaps the record stores below)
+            S.off[lane] = my_off;
+            if (lane == 31) S.off[32] = inc;
         }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int o = 0;
-        for (int b = 0; b < J.n_bands; ++b) { S.off[b] = o; o += S.cnt[b]; }
-        S.off[J.n_bands] = o;
-    }
-    if ((int)threadIdx.x < J.n_bands) {
-        const unsigned int n_b = S.cnt[threadIdx.x];
-        unsigned int base = 0u;
-        if (n_b) {
-            base = atomicAdd(&J.resv[threadIdx.x], n_b);                 // LOCAL counter: no NVLink round trip
-            if (base + n_b > J.seg_cap) { atomicOr(J.status, 2); base = 0xffffffffu; }
+        const unsigned int o0 = __shfl_sync(0xffffffffu, my_off, band0 < 0 ? 0 : band0);
+        uint4* s16 = reinterpret_cast<uint4*>(s_buf);
+        if (band0 >= 0) {                                                // struct occgrid_pose_rec, 3 x 16 bytes
+            const unsigned long long ux = (unsigned long long)__double_as_longlong(rx), uy = (unsigned long long)__double_as_longlong(ry);
+            const uint4 w0 = make_uint4((unsigned int)ux, (unsigned int)(ux >> 32), (unsigned int)uy, (unsigned int)(uy >> 32));
+            const uint4 w1 = make_uint4(__float_as_uint(yaw), __float_as_uint(dist[0]), __float_as_uint(dist[1]), __float_as_uint(dist[2]));
+            const unsigned int ord = J.ordinal_base + (unsigned int)k;
+            uint4* dst = s16 + (size_t)(o0 + rank0) * 3;
+            dst[0] = w0; dst[1] = w1; dst[2] = make_uint4(__float_as_uint(dist[3]), ord, (unsigned int)tile0, 0u);
         }
-        S.base[threadIdx.x] = base;
-    }
-    __syncthreads();                                                     // raw packets are decoded: the buffer is free
-    uint4* s16 = reinterpret_cast<uint4*>(s_buf);
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-        if (band[e] >= 0) {                                              // struct occgrid_pose_rec, 3 x 16 bytes
-            uint4* dst = s16 + (size_t)(S.off[band[e]] + rank[e]) * 3;
-            const unsigned long long ux = (unsigned long long)__double_as_longlong(rec.rx), uy = (unsigned long long)__double_as_longlong(rec.ry);
-            dst[0] = make_uint4((unsigned int)ux, (unsigned int)(ux >> 32), (unsigned int)uy, (unsigned int)(uy >> 32));
-            dst[1] = make_uint4(__float_as_uint(rec.yaw), __float_as_uint(rec.d[0]), __float_as_uint(rec.d[1]), __float_as_uint(rec.d[2]));
-            dst[2] = make_uint4(__float_as_uint(rec.d[3]), rec.k, (unsigned int)tile[e], 0u);
+        if (__any_sync(0xffffffffu, nb == 2)) {
+            const unsigned int o1 = __shfl_sync(0xffffffffu, my_off, nb == 2 ? band0 + 1 : 0);
+            if (nb == 2) {
+                const unsigned long long ux = (unsigned long long)__double_as_longlong(rx), uy = (unsigned long long)__double_as_longlong(ry);
+                uint4* dst = s16 + (size_t)(o1 + rank1) * 3;
+                dst[0] = make_uint4((unsigned int)ux, (unsigned int)(ux >> 32), (unsigned int)uy, (unsigned int)(uy >> 32));
+                dst[1] = make_uint4(__float_as_uint(yaw), __float_as_uint(dist[0]), __float_as_uint(dist[1]), __float_as_uint(dist[2]));
+                dst[2] = make_uint4(__float_as_uint(dist[3]), J.ordinal_base + (unsigned int)k, (unsigned int)tile1, 0u);
+            }
         }
+        __syncthreads();
+        // copy-out: warp w takes bands w, w + 8, ...: one contiguous run each, consecutive lanes ->
+        // consecutive 16-byte chunks in the owner's segment
+        for (int b = warp; b < J.n_bands; b += kTT / 32) {
+            const unsigned int base = S.base[b];
+            const unsigned int n16 = (S.off[b + 1] - S.off[b]) * 3u;
+            if (n16 == 0u || base == 0xffffffffu) continue;
+            const size_t slot0 = (size_t)J.src_rank * J.seg_cap + base;
+            uint4* out = reinterpret_cast<uint4*>(J.peer_recs[b] + slot0);
+            const uint4* in = s16 + (size_t)S.off[b] * 3;
+            for (unsigned int q = lane; q < n16; q += 32) out[q] = in[q];
+            // compact copy of the tile ids (word 10 of every record): the owner bins from 4 bytes per record
+            int* tout = J.peer_tiles[b] + slot0;
+            const unsigned int* tin = s_buf + (size_t)S.off[b] * 12 + 10;
+            for (unsigned int q = lane; q < n16 / 3u; q += 32) tout[q] = (int)tin[(size_t)q * 12];
+        }
+        first = next_first;
+        count = next_count;
     }
-    __syncthreads();
-    const unsigned int total16 = S.off[J.n_bands] * 3u;
-    for (unsigned int q = threadIdx.x; q < total16; q += kTT) {
-        const unsigned int e = q / 3u;
-        int b = 0;
-        while (e >= S.off[b + 1]) ++b;
-        const unsigned int base = S.base[b];
-        if (base == 0xffffffffu) continue;
-        uint4* out = reinterpret_cast<uint4*>(J.peer_recs[b] + (size_t)J.src_rank * J.seg_cap + base);
-        out[q - S.off[b] * 3u] = s16[q];                                 // consecutive lanes -> consecutive 16-byte chunks
-    }
+    return st_in;
 }
 
 template <bool kCounts, bool kRoute>
@@ -704,7 +879,9 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
     __shared__ unsigned long long s_acc[6 * 32];
     __shared__ RouteSmem s_route;
     __shared__ unsigned int s_mask[kMaskEntries];
-    build_walk_masks(s_mask);                      // visible after the first __syncthreads of the loop below
+    __shared__ RouteJob s_job;                     // the route path reads the job from shared memory, not from a stack copy
+    if (kRoute && threadIdx.x == 0) s_job = job;
+    build_walk_masks(s_mask);                      // both visible after the first __syncthreads of the loop below
     const unsigned int win_addr = (unsigned int)__cvta_generic_to_shared(s_win);
     const unsigned int n_items = have_items ? hdr->n_items : 0u;
     // Unified queue: raycast items of THIS batch and route items of the NEXT one, interleaved in
@@ -713,7 +890,7 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
     const unsigned int n_total = n_items + n_route;
     const int side = tg.win_side, pitch = tg.pitch, words = side * pitch;
     unsigned long long c[3] = {0, 0, 0};     // updates, slowpath, owned updates
-    unsigned long long rc[6] = {0, 0, 0, 0, 0, 0};   // routed share: packets, accepted, dropped, bad pose, beams, hits
+    RouteStats rs = {0u, 0u};                // routed share, packed (see RouteStats)
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_item = atomicAdd(&hdr->work_counter, 1u);
@@ -727,7 +904,7 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
             const unsigned int r0 = (unsigned int)(((unsigned long long)it * n_route) / n_total);
             const unsigned int r1 = (unsigned int)(((unsigned long long)(it + 1) * n_route) / n_total);
             if (r1 > r0) {
-                route_item(job, r0, s_win, s_route, rc);
+                rs = route_item(s_job, r0, s_win, s_route, rs);
                 continue;
             }
             it -= r0;
@@ -798,6 +975,8 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
     }
     if (kRoute && job.counters) {
         __syncthreads();
+        const unsigned long long pk = rs.a & 0xffffu, acc = rs.a >> 16, drp = rs.b & 0xffffu, hits = rs.b >> 16;
+        const unsigned long long rc[6] = {pk, acc, drp, pk - acc - drp, 4ull * acc, hits};
         block_add_counters(rc, s_acc, job.counters);            // slots OCCGRID_C_PACKETS .. OCCGRID_C_HITS
     }
     if (counters) {
@@ -989,7 +1168,7 @@ int integrate_tiled(const occgrid_geom* geom, const uint8_t* d_packets, const Po
     {
         ProfileScope ps(K_TILE_COUNT, st);
         if (d_poses)
-            k_home_count_poses<<<grid_chunks(n_chunks), kTT, 0, st>>>(g, tg, d_poses, seg, n_chunks, 0, P.tile_count, P.tile_ids, P.active,
+            k_home_count_poses<<<grid_chunks(n_chunks), kTT, 0, st>>>(g, tg, d_poses, nullptr, seg, n_chunks, 0, P.tile_count, P.tile_ids, P.active,
                                                                       P.hdr, d_counters);
         else
             k_home_count<<<blocks, kTT, 0, st>>>(g, tg, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents,
@@ -1017,7 +1196,7 @@ int integrate_tiled(const occgrid_geom* geom, const uint8_t* d_packets, const Po
 
 // ---- multi-GPU band step (include/occgrid_b200.h: occgrid_band_*) ---------------------------
 // count -> plan -> scatter over the per-source segments of a receive slot.
-int tiled_prepare_poses(const occgrid_geom* geom, const PoseRec* d_recs, const SegInfo& seg, int tiles_in_records,
+int tiled_prepare_poses(const occgrid_geom* geom, const PoseRec* d_recs, const int* d_tiles, const SegInfo& seg, int tiles_in_records,
                         void* d_ws, size_t ws_bytes, uint64_t* d_counters, cudaStream_t st) {
     const int64_t max_records = (int64_t)seg.n_segs * seg.seg_cap;
     const TiledLayout L = tiled_layout(geom, max_records, false);
@@ -1031,7 +1210,7 @@ int tiled_prepare_poses(const occgrid_geom* geom, const PoseRec* d_recs, const S
     const long long n_chunks = max_records / kSegChunk;
     {
         ProfileScope ps(K_TILE_COUNT, st);
-        k_home_count_poses<<<grid_chunks(n_chunks), kTT, 0, st>>>(g, tg, d_recs, seg, n_chunks, tiles_in_records, P.tile_count, P.tile_ids,
+        k_home_count_poses<<<grid_chunks(n_chunks), kTT, 0, st>>>(g, tg, d_recs, d_tiles, seg, n_chunks, tiles_in_records, P.tile_count, P.tile_ids,
                                                                   P.active, P.hdr, d_counters);
     }
     {

@@ -44,6 +44,15 @@ class RouteJob(C.Structure):
                 ('d_counters', C.c_void_p)]
 
 
+class BandCtx(C.Structure):
+    """struct occgrid_band_ctx"""
+    _fields_ = [('band_geom', Geom), ('n_bands', C.c_int32), ('rank', C.c_int32), ('seg_capacity', C.c_int64),
+                ('d_recv', C.c_void_p * 2), ('d_recv_tiles', C.c_void_p * 2), ('d_seg_counts', C.c_void_p * 2),
+                ('d_peer_recs', C.c_void_p * 2), ('d_peer_tiles', C.c_void_p * 2), ('d_peer_seg_counts', C.c_void_p * 2),
+                ('d_peer_flags', C.c_void_p), ('d_my_flags', C.c_void_p), ('d_resv', C.c_void_p), ('d_status', C.c_void_p),
+                ('d_grid', C.c_void_p), ('d_workspace', C.c_void_p), ('workspace_bytes', C.c_size_t), ('d_counters', C.c_void_p)]
+
+
 def _stale():
     if not os.path.exists(LIB_PATH):
         return True
@@ -108,6 +117,8 @@ def lib():
     L.occgrid_band_prepare.argtypes = [gp, vp, vp, i32, i64, vp, vp, sz, vp, vp]
     L.occgrid_band_raycast_route.restype = i32
     L.occgrid_band_raycast_route.argtypes = [gp, vp, i32, i64, i32, C.POINTER(RouteJob), vp, vp, sz, vp, vp]
+    L.occgrid_band_step.restype = i32
+    L.occgrid_band_step.argtypes = [C.POINTER(BandCtx), i64, i32, C.POINTER(RouteJob), i32, vp]
     L.occgrid_band_publish.restype = i32
     L.occgrid_band_publish.argtypes = [i32, i32, vp, i64, vp, vp, vp, u32, i32, vp, vp]
     L.occgrid_frontier_workspace_bytes.restype = sz

@@ -157,4 +157,32 @@ int occgrid_band_publish(int n_bands, int rank, uint32_t* d_resv, int64_t seg_ca
     return OCCGRID_OK;
 }
 
+// One whole step from ONE host call (the per-step host cost decides how far ahead of the GPUs the
+// launch queue runs, and with it how much of every rank's jitter ends up inside the barrier).
+int occgrid_band_step(const occgrid_band_ctx* ctx, int64_t step_index, int have_pending, const occgrid_route_job* job,
+                      int wait, void* stream) {
+    if (!ctx) { set_last_error("band_step: NULL context"); return OCCGRID_E_ARG; }
+    const int prev = (int)((step_index + 1) & 1), slot = (int)(step_index & 1);
+    int rc;
+    if (have_pending) {
+        rc = occgrid_band_prepare(&ctx->band_geom, ctx->d_recv[prev], ctx->d_recv_tiles[prev], ctx->n_bands, ctx->seg_capacity,
+                                  ctx->d_seg_counts[prev], ctx->d_workspace, ctx->workspace_bytes, ctx->d_counters, stream);
+        if (rc != OCCGRID_OK) return rc;
+    }
+    occgrid_route_job j;
+    if (job) {
+        j = *job;
+        j.n_bands = ctx->n_bands; j.src_rank = ctx->rank; j.seg_capacity = ctx->seg_capacity;
+        j.d_peer_recs = ctx->d_peer_recs[slot]; j.d_peer_tiles = ctx->d_peer_tiles[slot];
+        j.d_resv = ctx->d_resv; j.d_status = ctx->d_status;
+    }
+    rc = occgrid_band_raycast_route(&ctx->band_geom, ctx->d_recv[prev], ctx->n_bands, ctx->seg_capacity, have_pending,
+                                    job ? &j : nullptr, ctx->d_grid, ctx->d_workspace, ctx->workspace_bytes, ctx->d_counters, stream);
+    if (rc != OCCGRID_OK) return rc;
+    if (job)
+        rc = occgrid_band_publish(ctx->n_bands, ctx->rank, ctx->d_resv, ctx->seg_capacity, ctx->d_peer_seg_counts[slot],
+                                  ctx->d_peer_flags, ctx->d_my_flags, (uint32_t)(step_index + 1), wait, ctx->d_status, stream);
+    return rc;
+}
+
 }  // extern "C"

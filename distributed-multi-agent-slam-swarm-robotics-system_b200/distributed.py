@@ -225,52 +225,51 @@ class BandStep:
         """After every rank's buffers exist (and, for plain buffers, BandBuffers.link ran)."""
         with torch.cuda.device(self.device):
             self.buf.pointer_tables()
+        b, c = self.buf, _native.BandCtx()
+        c.band_geom = self._geom
+        c.n_bands, c.rank, c.seg_capacity = self.world, self.rank, self.seg_cap
+        for s in range(b.SLOTS):
+            c.d_recv[s], c.d_recv_tiles[s], c.d_seg_counts[s] = b.slot_ptr(s), b.tiles_ptr(s), b.seg_counts_ptr(s)
+            c.d_peer_recs[s], c.d_peer_tiles[s] = b.peer_recs[s].data_ptr(), b.peer_tiles[s].data_ptr()
+            c.d_peer_seg_counts[s] = b.peer_seg_counts[s].data_ptr()
+        c.d_peer_flags, c.d_my_flags = b.peer_flags.data_ptr(), b.flags_ptr()
+        c.d_resv, c.d_status = self._resv.data_ptr(), self._status.data_ptr()
+        c.d_grid = self.grid.grid_tensor.data_ptr()
+        c.d_workspace, c.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
+        c.d_counters = self.grid._counters.data_ptr()
+        self._ctx = c
+        self._ctx_ref = ctypes.byref(c)
+        self._job_ref = ctypes.byref(self._job)
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def step(self, pk, agent_idx, drift, agent_table, wait=True):
         """Integrate the pending batch and route `pk` (uint8 cuda [n, stride]; None = nothing more to
-        route) in ONE fused kernel, then publish + barrier."""
-        lib, b = self._lib, self.buf
-        st = self._stream()
-        prev = (self._step - 1) % b.SLOTS
-        slot = self._step % b.SLOTS
-        cptr = self.grid._counters.data_ptr()
-        with torch.cuda.device(self.device):
-            if self._pending:
-                _native.check(lib.occgrid_band_prepare(self._geom, b.slot_ptr(prev), b.tiles_ptr(prev), self.world, self.seg_cap,
-                                                       b.seg_counts_ptr(prev), self._ws.data_ptr(), self._ws.numel(), cptr, st),
-                              'occgrid_band_prepare')
-            job = None
-            if pk is not None and pk.shape[0] > 0:
-                n, stride = pk.shape
-                if n > self.seg_cap:
-                    raise OccGridError(f'batch of {n} records exceeds max_batch (segment capacity {self.seg_cap})')
-                j = self._job
-                j.d_packets, j.n, j.stride, j.rec_len = pk.data_ptr(), n, stride, 42 if stride >= 42 else 41
+        route) in ONE fused kernel, then publish + barrier — one host call (occgrid_band_step)."""
+        job = None
+        if pk is not None:
+            n, stride = pk.shape
+            if n > self.seg_cap:
+                raise OccGridError(f'batch of {n} records exceeds max_batch (segment capacity {self.seg_cap})')
+            j = self._job
+            j.n, j.stride, j.rec_len = n, stride, 42 if stride >= 42 else 41
+            if n:
+                j.d_packets = pk.data_ptr()
                 j.d_agent_idx = agent_idx.data_ptr() if agent_idx is not None else None
                 j.d_drift = drift.data_ptr() if drift is not None else None
                 j.d_agent_off, j.n_agents = agent_table.data_ptr(), agent_table.shape[0] - 1
                 j.ordinal_base = self.rank * self.ordinal_stride
-                j.d_peer_recs = b.peer_recs[slot].data_ptr()
-                j.d_peer_tiles = b.peer_tiles[slot].data_ptr()
-                job = ctypes.byref(j)
                 self._keep = (pk, agent_idx, drift, agent_table)
-            _native.check(lib.occgrid_band_raycast_route(self._geom, b.slot_ptr(prev), self.world, self.seg_cap,
-                                                         1 if self._pending else 0, job, self.grid.grid_tensor.data_ptr(),
-                                                         self._ws.data_ptr(), self._ws.numel(), cptr, st),
-                          'occgrid_band_raycast_route')
-            if self._pending:
-                self.grid._host_cache = None
-            self._pending = False
-            if pk is not None:         # every rank publishes every step, even an empty share, so the barrier lines up
-                _native.check(lib.occgrid_band_publish(self.world, self.rank, self._resv.data_ptr(), self.seg_cap,
-                                                       b.peer_seg_counts[slot].data_ptr(), b.peer_flags.data_ptr(), b.flags_ptr(),
-                                                       self._step + 1, 1 if wait else 0, self._status.data_ptr(), st),
-                              'occgrid_band_publish')
-                self._pending = True
-                self._step += 1
+            job = self._job_ref
+        rc = self._lib.occgrid_band_step(self._ctx_ref, self._step, 1 if self._pending else 0, job, 1 if wait else 0, self._stream())
+        if rc:
+            _native.check(rc, 'occgrid_band_step')
+        if self._pending:
+            self.grid._host_cache = None
+        self._pending = pk is not None      # every rank publishes every step, even an empty share, so the barrier lines up
+        if pk is not None:
+            self._step += 1
 
     def check_status(self):
         st = int(self._status.item())
@@ -386,12 +385,16 @@ class TiledSwarmMap:
         if self.band is None:
             return self._update_packets_nccl(packets, separation, drift, agent_offsets, agent_idx)
         dev = self.device
+        T = torch.Tensor
+        if type(packets) is T and packets.is_cuda and packets.dtype == torch.uint8 and packets.dim() == 2 and packets.is_contiguous() \
+                and type(agent_offsets) is T and agent_offsets.is_cuda and agent_offsets.dtype == torch.float64 and agent_offsets.is_contiguous() \
+                and (agent_idx is None or (type(agent_idx) is T and agent_idx.is_cuda and agent_idx.dtype == torch.int32 and agent_idx.is_contiguous())) \
+                and (drift is None or (type(drift) is T and drift.is_cuda and drift.dtype == torch.float64 and drift.is_contiguous())):
+            # everything already lives on the device in the wire layout: no conversions, one C call
+            self.band.step(packets, agent_idx, drift, agent_offsets.view(-1, 2))
+            return int(packets.shape[0])
         with torch.cuda.device(dev):
-            if isinstance(agent_offsets, torch.Tensor) and agent_offsets.is_cuda and agent_offsets.dtype == torch.float64 \
-                    and agent_offsets.is_contiguous():
-                tab = agent_offsets.reshape(-1, 2)
-            else:
-                tab = self._agent_table(separation, agent_offsets)
+            tab = self._agent_table(separation, agent_offsets)
             pk = self.local.stage_packets(packets)[0]
             idx = torch.as_tensor(agent_idx, dtype=torch.int32).to(dev).contiguous() if agent_idx is not None else None
             dr = torch.as_tensor(drift, dtype=torch.float64).reshape(-1, 2).to(dev).contiguous() if drift is not None else None

@@ -234,6 +234,33 @@ int occgrid_band_raycast_route(const occgrid_geom* band_geom, const void* d_recv
                                int64_t seg_capacity, int have_prepared /* 0: nothing to raycast yet */,
                                const occgrid_route_job* job /* NULL: nothing to route */, int8_t* d_grid,
                                void* d_workspace, size_t workspace_bytes, uint64_t* d_counters, void* stream);
+/* Everything a rank's steps share (all DEVICE pointers; [2] = the two receive slots). */
+typedef struct occgrid_band_ctx {
+    occgrid_geom     band_geom;            /* window = my band                                        */
+    int32_t          n_bands, rank;
+    int64_t          seg_capacity;
+    void*            d_recv[2];            /* my receive slots: occgrid_pose_rec[n_bands][seg_capacity] */
+    int32_t*         d_recv_tiles[2];      /* int32[n_bands][seg_capacity]                             */
+    uint32_t*        d_seg_counts[2];      /* uint32[n_bands]                                          */
+    void* const*     d_peer_recs[2];       /* device arrays [n_bands] of the owners' slot pointers     */
+    int32_t* const*  d_peer_tiles[2];
+    uint32_t* const* d_peer_seg_counts[2];
+    uint32_t* const* d_peer_flags;
+    const uint32_t*  d_my_flags;
+    uint32_t*        d_resv;
+    int32_t*         d_status;
+    int8_t*          d_grid;
+    void*            d_workspace;
+    size_t           workspace_bytes;
+    uint64_t*        d_counters;
+} occgrid_band_ctx;
+
+/* prepare (when a batch is pending) + raycast_route + publish (when `job` != NULL; job->n may be 0)
+ * for step `step_index` (slot = step_index & 1, epoch = step_index + 1) in one host call; the job's
+ * n_bands / src_rank / seg_capacity / peer pointers / d_resv / d_status are taken from `ctx`. */
+int occgrid_band_step(const occgrid_band_ctx* ctx, int64_t step_index, int have_pending,
+                      const occgrid_route_job* job /* NULL: flush only */, int wait, void* stream);
+
 int occgrid_band_publish(int n_bands, int rank, uint32_t* d_resv, int64_t seg_capacity,
                          uint32_t* const* d_peer_seg_counts /* DEVICE array: owner b's seg_counts of the slot */,
                          uint32_t* const* d_peer_flags /* DEVICE array: owner b's uint32 flags[n_bands] */,

@@ -256,11 +256,14 @@ def main():
     ap.add_argument('--strategy', default='auto')
     ap.add_argument('--packets', type=int, default=PACKETS_PER_BATCH)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-merge', action='store_true', help='N=1: skip the merged-grids/s leg (BASELINE configs[2])')
     ap.add_argument('--trace', action='store_true', help='print per-step wall times (debug)')
     ap.add_argument('--grid-per-gpu', type=int, default=0,
                     help='N>1: map side = this x N.  Default 8192 (with 128 agents per GPU: N=8 is BASELINE configs[3], '
                          '65536^2 / 1024 agents; N=2 and 4 keep the same per-GPU band)')
     ap.add_argument('--agents-per-gpu', type=int, default=0)
+    ap.add_argument('--layout', default='bands', choices=['bands', 'lattice'],
+                    help='N>1: rooms per band equal (bands, default) or one square lattice over the map (lattice: uneven bands)')
     ap.add_argument('--no-parity', action='store_true', help='N>1: skip the bit-exactness check against the oracle before timing')
     ap.add_argument('--raycast-ctas', type=int, default=0, help='cap persistent raycast CTAs per SM (0 = max)')
     ap.add_argument('--ingest', default='uniform', choices=['uniform', 'affine'],
@@ -328,7 +331,7 @@ def main():
                 raise SystemExit(3)
         tmap, sessions, step = make_rank_sessions(n, rank, dev, npk, POOL, args.strategy,
                                                    grid_per_gpu=args.grid_per_gpu, agents_per_gpu=args.agents_per_gpu,
-                                                   exchange=args.exchange, ingest=args.ingest)
+                                                   exchange=args.exchange, ingest=args.ingest, layout=args.layout)
         grid = tmap.local
 
     # warm-up (at least one pass over every batch of the pool, so that no allocation or
@@ -408,14 +411,23 @@ def main():
     hbm_peak, peak_src = measured_peaks()
     packets_total = npk * K * n
     upd_per_step_rank = updates / K / n
-    alg_bytes = (42.0 * npk + 1.0 * upd_per_step_rank) / dom_launches
+    # algorithmic bytes, charged to the kernel that moves them: the count pass reads the 42-byte wire
+    # records; the raycast kernel reads one 48-byte pose record + one 4-byte bin index per packet and
+    # produces one 1-byte cell value per beam-cell update (SURVEY §8d's per-unit figures)
+    recs_per_step = float(counters.get('records', 0)) / max(K, 1) or float(npk)
+    bytes_by_kernel = {'tile_count': 42.0 * npk, 'tile_raycast': 52.0 * recs_per_step + 1.0 * upd_per_step_rank,
+                       'integrate_global': 42.0 * npk + 1.0 * upd_per_step_rank}
+    alg_bytes = bytes_by_kernel.get(dom, 42.0 * npk + 1.0 * upd_per_step_rank) / dom_launches
+    step_bytes = 42.0 * npk + 1.0 * upd_per_step_rank
     roof = {'bound': 'hbm', 'kernel': dom, 'achieved': alg_bytes / (dom_ms * 1e-3) / 1e9, 'peak': hbm_peak,
             'unit': 'GB/s', 'frac': alg_bytes / (dom_ms * 1e-3) / 1e9 / hbm_peak, 'traffic': ncu_traffic(),
             'ms_per_launch': dom_ms, 'share_of_step': prof[dom][0] / sum(v[0] for v in prof.values()),
             'peak_source': peak_src,
-            'note': 'algorithmic bytes = 42 B/packet + 1 B/beam-cell update per launch (SURVEY §8d); by '
-                    'construction a small fraction of HBM: the binding resource is atomic/scatter '
-                    'throughput, see scatter_roofline'}
+            'step': {'achieved': step_bytes / (ms / K * 1e-3) / 1e9, 'frac': step_bytes / (ms / K * 1e-3) / 1e9 / hbm_peak,
+                     'bytes': '42 B/packet + 1 B/beam-cell update over the whole step (SURVEY §8d)'},
+            'note': 'algorithmic bytes of the dominant kernel = 52 B per pose record (48-byte record + 4-byte bin index) + 1 B per '
+                    'beam-cell update; by construction a small fraction of HBM: the binding resource is shared-memory '
+                    'atomic throughput and instruction issue, see scatter_roofline_smem'}
 
     result = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': n, 'steps': K, 'warmup': W,
@@ -428,6 +440,7 @@ def main():
     if n > 1:
         result['exchange'] = tmap.exchange
         result['ingest'] = args.ingest
+        result['layout'] = args.layout
         result['parity'] = parity
 
     # ---- single-GPU extras: scatter roofline, e2e, cpu baseline ------------------------------
@@ -449,8 +462,28 @@ def main():
         result['scatter_roofline'] = {'bound': 'l2-atomic', 'achieved': value, 'peak': probe_rate, 'unit': UNIT,
                                       'frac': value / probe_rate,
                                       'how': 'peak = same-run microkernel: 2^28 atomicMax(u32) per launch to uniformly '
-                                             'random cells of a 4096^2 u32 plane (occgrid_scatter_probe kind 0)'}
-
+                                             'random cells of a 4096^2 u32 plane (occgrid_scatter_probe kind 0): the ceiling '
+                                             'of the GLOBAL_ATOMIC strategy; the default TILED strategy resolves the order '
+                                             'stamps in shared memory and is bounded by scatter_roofline_smem instead'}
+        # the ceiling of what the TILED strategy actually does: atomicMax on a window-sized tile in shared memory
+        win_words = 116 * 117                       # (64 + 2R) x pitch words at 5 cm (occgrid_tiled.cu: tile_geom)
+        probe_out = torch.zeros(1 << 16, dtype=torch.int32, device=dev)
+        nops_s = 148 * 3 * 256 * 4096               # three 256-thread CTAs per SM, 4096 random atomics per thread
+        for _ in range(2):
+            lib.occgrid_scatter_probe(6, probe_out.data_ptr(), win_words, nops_s, 7, stream)
+        p0.record()
+        for _ in range(5):
+            lib.occgrid_scatter_probe(6, probe_out.data_ptr(), win_words, nops_s, 9, stream)
+        p1.record()
+        torch.cuda.synchronize()
+        smem_rate = 5 * nops_s / (p0.elapsed_time(p1) * 1e-3)
+        atomics_per_update = 1.0                    # one shared-memory reduction per beam-cell update (minus skipped start cells)
+        result['scatter_roofline_smem'] = {
+            'bound': 'smem-atomic', 'achieved': value, 'peak': smem_rate, 'unit': UNIT, 'frac': value / smem_rate,
+            'frac_raycast_kernel': (updates / K) / (kernels['tile_raycast']['ms_per_launch'] * 1e-3) / smem_rate,
+            'how': 'peak = same-run microkernel: 444 CTAs x 256 threads x 4096 atomicMax(u32) to uniformly random words of a '
+                   '116x117-word tile in shared memory (occgrid_scatter_probe kind 6; the stamp window of the TILED strategy), '
+                   'nothing else in the loop; frac = whole step vs that rate, frac_raycast_kernel = the raycast kernel alone'}
         # e2e: the user's call — OccupancyGrid.update_packets(host buffer) + counters read-back
         host = [torch.from_numpy(s['packets']).pin_memory() for s in sessions]
         g2 = M.OccupancyGrid(strategy=args.strategy, max_batch=npk, device=dev, **s0['grid'])
@@ -503,6 +536,12 @@ def main():
         if not args.no_cpu:
             result['cpu_baseline'] = cpu_baseline(s0, 1, 500_000)     # ~10 s of the reference's Python loop on one core
             result['cpu_baseline_c_port'] = c_port_rate(s0)
+        if not args.no_merge:
+            # second half of BASELINE.json's metric: merged grids/s on configs[2]
+            del dpk, g2, host
+            torch.cuda.empty_cache()
+            import bench_merge
+            result['merge'] = bench_merge.run_merge_bench(torch, dev, cpu_agents=0 if args.no_cpu else 8)
     if n > 1:
         # e2e at N GPUs: every rank hands ITS share to TiledSwarmMap.update_packets as a pinned host
         # buffer (H2D + route + exchange + integrate) and reads the step's counters back

@@ -50,35 +50,26 @@ def device_grids(torch, dev, n_distinct, size, seed=0):
     return out
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--agents', type=int, default=256)
-    ap.add_argument('--size', type=int, default=2048)
-    ap.add_argument('--repeat', type=int, default=3)
-    ap.add_argument('--cpu-agents', type=int, default=8)
-    args = ap.parse_args()
-    import torch
+def run_merge_bench(torch, dev, agents=256, size=2048, repeat=3, cpu_agents=8, e2e=True):
+    """-> dict for the `merge` object of bench.py's line (and bench_merge.py's own line)."""
     from occgrid_b200 import _native
     from occgrid_b200.map_merger import MapMerger, se2_matrix
-    assert torch.cuda.is_available(), 'bench_merge.py needs a CUDA device (no CPU fallback)'
-    dev = torch.device('cuda', 0)
-    A, S, res = args.agents, args.size, 0.05
-    distinct = device_grids(torch, dev, A, S)        # every agent its own map: A * S^2 bytes of input (1 GiB > L2)
-    grids = distinct
+    A, S, res = agents, size, 0.05
+    grids = device_grids(torch, dev, A, S)           # every agent its own map: A * S^2 bytes of input (1 GiB > L2)
     rng = np.random.default_rng(0)
     origins = np.tile(np.array([[-S * res / 2, -S * res / 2]]), (A, 1))
     tf = [se2_matrix(*rng.uniform(-50, 50, 2), rng.uniform(-math.pi, math.pi)) for _ in range(A)]
-    occ_frac = float((distinct[0] > 50).float().mean().item())
+    occ_frac = float((grids[0] > 50).float().mean().item())
 
-    def run():
+    def run(src=grids):
         m = MapMerger(device=dev)
-        out, origin = m.merge(grids, origins, res, tf, to_host=False)
+        out, origin = m.merge(src, origins, res, tf, to_host=False)
         return m, out
 
     run()                               # warm-up (allocations, lattice growth)
     torch.cuda.synchronize()
     times = []
-    for _ in range(args.repeat):
+    for _ in range(repeat):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         m, out = run()
@@ -91,8 +82,11 @@ def main():
     torch.cuda.synchronize()
     prof = _native.profile_end()
     kern = {k: {'ms_total': v[0], 'kernels': v[1]} for k, v in prof.items()}
-    hbm = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'] if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.0
-    ext_ms = prof['merge_extract'][0] / A            # all extraction-side kernels of the merge, per grid
+    pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    hbm = json.load(open(pk))['hbm_gbs'] if os.path.exists(pk) else 6650.0
+    scan_ms = prof['merge_scan'][0] if 'merge_scan' in prof else prof['merge_extract'][0]
+    scan_gbs = A * S * S / (scan_ms * 1e-3) / 1e9
+    bound = hbm * 1e9 / (S * S)                      # grids/s if nothing but the H*W-byte read of every grid remained
     result = {
         'metric': 'merged_grids_per_sec', 'value': A / (ms * 1e-3), 'unit': 'grids/s', 'n_gpus': 1, 'ms_per_merge': ms,
         'higher_is_better': True, 'dtype': 'f64+int8', 'data': 'synthetic',
@@ -101,25 +95,54 @@ def main():
                    'occupied_fraction': occ_frac, 'fused_points': int(m._n_global),
                    'output_grid': list(out.shape), 'chain': m.chain_stats},
         'kernels': kern,
-        'roofline': {'bound': 'hbm', 'kernel': 'merge_extract', 'achieved': S * S / (ext_ms * 1e-3) / 1e9, 'peak': hbm,
-                     'unit': 'GB/s', 'frac': S * S / (ext_ms * 1e-3) / 1e9 / hbm,
-                     'note': 'algorithmic bytes = H*W per agent grid (SURVEY §8d) over the device time of all extraction-side '
-                             'kernels (batched count + write passes over all grids, plus the per-callback slice appends); '
-                             'the voxel chain costs O(|slice|) on callbacks that leave the voxel lattice in place '
-                             '(chain_incremental) and O(|cloud|) on the others (chain_rebuild)'},
+        'roofline': {'bound': 'hbm', 'kernel': 'merge_scan (occupied-cell scan of all grids)', 'achieved': scan_gbs, 'peak': hbm,
+                     'unit': 'GB/s', 'frac': scan_gbs / hbm, 'ms_per_launch': scan_ms,
+                     'grids_per_sec_bound': bound, 'frac_of_grids_bound': A / (ms * 1e-3) / bound,
+                     'note': 'achieved = algorithmic bytes (H*W per agent grid, SURVEY §8d) over the device time of the scan kernel '
+                             'that reads them; frac_of_grids_bound = whole merge vs the 1.55e6 grids/s HBM bound: the rest of the '
+                             'merge is the reference\'s sequential voxel chain (O(|slice|) per callback while the lattice stands '
+                             'still, O(|cloud|) when its anchor moves), latency-bound by construction'},
     }
+    if e2e:
+        host = [g.cpu().pin_memory() for g in grids]
+        run(host)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        m2 = MapMerger(device=dev)
+        out2, origin2 = m2.merge(host, origins, res, tf, to_host=True)      # D2H of the published int8 grid
+        e1.record()
+        torch.cuda.synchronize()
+        e_ms = e0.elapsed_time(e1)
+        result['e2e'] = {'value': A / (e_ms * 1e-3), 'unit': 'grids/s', 'ms_per_merge': e_ms,
+                         'h2d_bytes_per_step': int(A * S * S), 'd2h_bytes_per_step': int(out2.size),
+                         'api': 'MapMerger.merge(list of pinned host int8 grids) -> published int8 grid on the host'}
+        del host
     # CPU baseline: NumPy restatement, one core, first cpu_agents grids
-    from oracle import merge_oracle as MO
-    host = [g.cpu().numpy() for g in grids[:args.cpu_agents]]
-    o = MO.OracleMerger()
-    t0 = time.perf_counter()
-    for a in range(args.cpu_agents):
-        o.map_callback(host[a].ravel(), S, S, res, origins[a][0], origins[a][1], tf[a])
-    dt = time.perf_counter() - t0
-    result['cpu_baseline'] = {'value': args.cpu_agents / dt, 'unit': 'grids/s', 'cores': 1, 'kind': 'port',
-                              'sample': f'first {args.cpu_agents} grids of the same sequence, NumPy restatement '
-                                        '(oracle/merge_oracle.py), publish after every callback as the reference does'}
-    print(json.dumps(result))
+    if cpu_agents:
+        from oracle import merge_oracle as MO
+        hostg = [g.cpu().numpy() for g in grids[:cpu_agents]]
+        o = MO.OracleMerger()
+        t0 = time.perf_counter()
+        for a in range(cpu_agents):
+            o.map_callback(hostg[a].ravel(), S, S, res, origins[a][0], origins[a][1], tf[a])
+        dt = time.perf_counter() - t0
+        result['cpu_baseline'] = {'value': cpu_agents / dt, 'unit': 'grids/s', 'cores': 1, 'kind': 'port',
+                                  'sample': f'first {cpu_agents} grids of the same sequence, NumPy restatement '
+                                            '(oracle/merge_oracle.py), publish after every callback as the reference does'}
+    return result
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--agents', type=int, default=256)
+    ap.add_argument('--size', type=int, default=2048)
+    ap.add_argument('--repeat', type=int, default=3)
+    ap.add_argument('--cpu-agents', type=int, default=8)
+    args = ap.parse_args()
+    import torch
+    assert torch.cuda.is_available(), 'bench_merge.py needs a CUDA device (no CPU fallback)'
+    print(json.dumps(run_merge_bench(torch, torch.device('cuda', 0), args.agents, args.size, args.repeat, args.cpu_agents)))
 
 
 if __name__ == '__main__':

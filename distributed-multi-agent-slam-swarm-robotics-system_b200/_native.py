@@ -150,7 +150,7 @@ def _bind_merge(L):
     L.mapmerge_extract_batch_workspace_bytes.restype = sz
     L.mapmerge_extract_batch_workspace_bytes.argtypes = [i64, i32]
     L.mapmerge_extract_batch_count.restype = C.c_int
-    L.mapmerge_extract_batch_count.argtypes = [vp, i32, i32, i32, vp, vp, sz, vp]
+    L.mapmerge_extract_batch_count.argtypes = [vp, i32, i32, i32, vp, vp, sz, i32, vp]
     L.mapmerge_extract_batch_write.restype = C.c_int
     L.mapmerge_extract_batch_write.argtypes = [vp, i32, i32, i32, dbl, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, sz, vp]
     L.mapmerge_append_slice.restype = C.c_int
@@ -205,7 +205,7 @@ def _bind_merge(L):
 KERNEL_NAMES = ('integrate_global', 'resolve', 'update_rays', 'tile_count', 'tile_scan', 'tile_scatter',
                 'tile_raycast', 'tile_resolve', 'merge_extract', 'merge_bounds', 'merge_voxel', 'merge_raster',
                 'merge_fuse', 'probe', 'route', 'frontier', 'frontier_cluster', 'chain_probe', 'chain_incremental',
-                'chain_rebuild', 'icp', 'band_barrier', 'render')
+                'chain_rebuild', 'icp', 'band_barrier', 'render', 'merge_scan')
 
 
 def profile_begin():

@@ -264,6 +264,105 @@ k_batch_count(const int8_t* const* __restrict__ grids, long long n_cells, int bl
     if (threadIdx.x == 0) block_counts[(size_t)a * blocks_per_grid + blockIdx.x] = total;
 }
 
+// ---- bulk-copy (TMA) staged scan --------------------------------------------------------------
+// The count pass is the one pure HBM stream of the merge path: every agent grid is read once
+// (H*W bytes) and leaves one occupancy bit per cell.  Persistent CTAs own a ring of kScanStages
+// 16 KiB shared-memory stages; ONE elected thread keeps the ring full with
+// cp.async.bulk.shared::cluster.global (the TMA unit's 1-D bulk copy), each stage completing on
+// its own mbarrier (complete_tx::bytes), while the 256 threads turn the stage that has landed into
+// 64-bit occupancy masks (`data > 50`, map_merger.py:72) — no thread ever waits on a global load.
+constexpr int kScanStages = 4;
+constexpr int kScanCtasPerSm = 3;            // 3 x 4 x 16 KiB = 192 KiB of bulk loads in flight per SM
+constexpr int kScanStageBytes = kChunk;                    // 16 KiB = one chunk of the existing mask layout
+
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, unsigned int bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// 16 int8 cells (one uint4 from shared memory) -> 16 occupancy bits.
+__device__ __forceinline__ unsigned int occupied_bits16(uint4 v) {
+    const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+    unsigned int bits = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const unsigned int gt = __vcmpgts4(w[i], 0x32323232u) & 0x80808080u;     // per byte: 0x80 where (int8) > 50
+        bits |= (((gt >> 7) * 0x00204081u) >> 21 & 0xfu) << (4 * i);             // gather the four flags into 4 bits
+    }
+    return bits;
+}
+
+__global__ void __launch_bounds__(kMT)
+k_batch_count_tma(const int8_t* const* __restrict__ grids, long long n_cells, int blocks_per_grid, int n_agents,
+                  unsigned int* __restrict__ block_counts, unsigned long long* __restrict__ masks) {
+    extern __shared__ __align__(128) unsigned char s_stage[];              // kScanStages x 16 KiB
+    __shared__ __align__(8) unsigned long long s_full[kScanStages];
+    __shared__ unsigned int s_cnt[kScanStages];
+    const long long total = (long long)n_agents * blocks_per_grid;         // chunks, agent-major
+    auto chunk_of = [&](long long i) { return (long long)blockIdx.x + i * gridDim.x; };
+    auto issue = [&](long long i) {                                        // elected thread only
+        const long long c = chunk_of(i);
+        if (c >= total) return;
+        const int a = (int)(c / blocks_per_grid), blk = (int)(c - (long long)a * blocks_per_grid);
+        const long long base = (long long)blk * kChunk;
+        const unsigned int bytes = (unsigned int)min((long long)kChunk, n_cells - base);
+        const int st = (int)(i % kScanStages);
+        mbar_expect_tx(&s_full[st], bytes);
+        bulk_load(s_stage + (size_t)st * kScanStageBytes, grids[a] + base, bytes, &s_full[st]);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kScanStages; ++s) mbar_init(&s_full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (threadIdx.x < kScanStages) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int i = 0; i < kScanStages; ++i) issue(i);
+    for (long long i = 0; chunk_of(i) < total; ++i) {
+        const long long c = chunk_of(i);
+        const int st = (int)(i % kScanStages);
+        const int a = (int)(c / blocks_per_grid), blk = (int)(c - (long long)a * blocks_per_grid);
+        const long long base = (long long)blk * kChunk;
+        const int valid = (int)min((long long)kChunk, n_cells - base);     // multiple of 16 on this path
+        mbar_wait(&s_full[st], (unsigned int)((i / kScanStages) & 1));
+        const uint4* src = reinterpret_cast<const uint4*>(s_stage + (size_t)st * kScanStageBytes) + threadIdx.x * 4;
+        unsigned long long mask = 0ull;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if ((int)threadIdx.x * kCellsPerThread + 16 * q < valid)
+                mask |= (unsigned long long)occupied_bits16(src[q]) << (16 * q);
+        masks[((size_t)a * blocks_per_grid + blk) * kMT + threadIdx.x] = mask;
+        unsigned int n = __popcll(mask);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+        if ((threadIdx.x & 31) == 0 && n) atomicAdd(&s_cnt[st], n);
+        __syncthreads();                                                   // everyone has read the stage; the count is complete
+        if (threadIdx.x == 0) {
+            block_counts[(size_t)a * blocks_per_grid + blk] = s_cnt[st];
+            s_cnt[st] = 0u;
+            issue(i + kScanStages);                                        // refill the stage that was just consumed
+        }
+    }
+}
+
 // One CTA per agent: exclusive scan of its block counts (in place) and its total.
 __global__ void __launch_bounds__(1024)
 k_batch_scan(unsigned int* __restrict__ block_counts, int blocks_per_grid, long long* __restrict__ agent_total) {
@@ -691,19 +790,24 @@ __device__ __forceinline__ bool voxel_key_of(double x, double y, double mbx, dou
 }
 
 // What the callback for slice `agent` needs; also yields the anchor of cloud u slice.
+// Header fields are read with ld.global.cg: other CTAs update them during a launch (atomics and plain
+// stores land in L2) and this SM's L1 may still hold an older copy.
 __device__ __forceinline__ int chain_decide(const ChainHeader* h, const unsigned long long* sb /* slice bounds */, double voxel,
                                             long long W, long long H, double* nmbx, double* nmby) {
-    const double b0 = fmin(dec_double(h->gb_enc[0]), dec_double(sb[0]));
-    const double b1 = fmin(dec_double(h->gb_enc[1]), dec_double(sb[1]));
-    const double b2 = fmax(dec_double(h->gb_enc[2]), dec_double(sb[2]));
-    const double b3 = fmax(dec_double(h->gb_enc[3]), dec_double(sb[3]));
+    const unsigned long long g0 = __ldcg(&h->gb_enc[0]), g1 = __ldcg(&h->gb_enc[1]), g2 = __ldcg(&h->gb_enc[2]), g3 = __ldcg(&h->gb_enc[3]);
+    const int dirty = __ldcg(&h->bounds_dirty), have = __ldcg(&h->have_lattice), force = __ldcg(&h->force_rebuild);
+    const double hmbx = __ldcg(&h->mbx), hmby = __ldcg(&h->mby);
+    const double b0 = fmin(dec_double(g0), dec_double(sb[0]));
+    const double b1 = fmin(dec_double(g1), dec_double(sb[1]));
+    const double b2 = fmax(dec_double(g2), dec_double(sb[2]));
+    const double b3 = fmax(dec_double(g3), dec_double(sb[3]));
     *nmbx = OCC_DADD(b0, -OCC_DMUL(voxel, 0.5));
     *nmby = OCC_DADD(b1, -OCC_DMUL(voxel, 0.5));
-    if (h->bounds_dirty) return CHAIN_REBOUND;
+    if (dirty) return CHAIN_REBOUND;
     const long long nx = (long long)floor(OCC_DDIV(OCC_DADD(b2, -*nmbx), voxel)) + 1;
     const long long ny = (long long)floor(OCC_DDIV(OCC_DADD(b3, -*nmby), voxel)) + 1;
     if (!(nx > 0 && ny > 0 && nx <= W && ny <= H)) return CHAIN_OVERFLOW;
-    if (!h->have_lattice || h->force_rebuild || *nmbx != h->mbx || *nmby != h->mby) return CHAIN_REBUILD;
+    if (!have || force || *nmbx != hmbx || *nmby != hmby) return CHAIN_REBUILD;
     return CHAIN_RUN;
 }
 
@@ -1204,7 +1308,7 @@ size_t mapmerge_extract_batch_workspace_bytes(int64_t n_cells, int n_agents) {
 
 // Pass 1 of a batched extraction: per-block and per-agent occupied-cell counts.
 int mapmerge_extract_batch_count(const int8_t* const* d_grids, int n_agents, int32_t width, int32_t height,
-                                 int64_t* d_agent_total, void* d_ws, size_t ws_bytes, void* stream) {
+                                 int64_t* d_agent_total, void* d_ws, size_t ws_bytes, int grids_bulk_ok, void* stream) {
     if (!d_grids || n_agents <= 0 || n_agents > 65535 || width <= 0 || height <= 0 || !d_agent_total || !d_ws) {
         set_last_error("mapmerge_extract_batch_count: bad arguments");
         return OCCGRID_E_ARG;
@@ -1214,10 +1318,25 @@ int mapmerge_extract_batch_count(const int8_t* const* d_grids, int n_agents, int
     cudaStream_t st = (cudaStream_t)stream;
     const int bpg = (int)((n_cells + kChunk - 1) / kChunk);
     unsigned int* block_counts = reinterpret_cast<unsigned int*>(d_ws);
-    ProfileScope ps(K_MERGE_EXTRACT, st, 2);
+    ProfileScope ps(K_MERGE_EXTRACT, st, 1);
     dim3 grid((unsigned)bpg, (unsigned)n_agents);
     unsigned long long* masks = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(d_ws) + batch_counts_bytes(n_cells, n_agents));
-    k_batch_count<<<grid, kMT, 0, st>>>(d_grids, n_cells, bpg, block_counts, masks);
+    {
+        // the scan proper, timed on its own: the HBM-bound kernel of the merge path
+        ProfileScope scan(K_MERGE_SCAN, st, 1);
+        if (grids_bulk_ok && (n_cells % 16) == 0) {
+            const int ctas = device_sm_count() * kScanCtasPerSm;
+            const size_t smem = (size_t)kScanStages * kScanStageBytes;
+            static bool configured = false;
+            if (!configured) {
+                OCC_CUDA_TRY(cudaFuncSetAttribute(k_batch_count_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured = true;
+            }
+            k_batch_count_tma<<<ctas, kMT, smem, st>>>(d_grids, n_cells, bpg, n_agents, block_counts, masks);
+        } else {
+            k_batch_count<<<grid, kMT, 0, st>>>(d_grids, n_cells, bpg, block_counts, masks);
+        }
+    }
     k_batch_scan<<<n_agents, 1024, 0, st>>>(block_counts, bpg, (long long*)d_agent_total);
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;

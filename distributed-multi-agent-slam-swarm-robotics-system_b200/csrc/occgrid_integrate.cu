@@ -638,7 +638,7 @@ int occgrid_profile_end(double* ms_by_kernel, int64_t* launches_by_kernel, int n
 int occgrid_scatter_probe(int kind, void* d_plane, int64_t plane_cells, int64_t n_ops, uint32_t seed, void* stream) {
     if (!d_plane || plane_cells <= 0 || n_ops <= 0) { set_last_error("probe: bad arguments"); return OCCGRID_E_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
-    const int iters = 64;
+    const int iters = kind == 6 ? 4096 : 64;       // kind 6: long runs, so that the tile set-up does not dilute the rate
     long long threads = (n_ops + iters - 1) / iters;
     long long blocks = (threads + kThreads - 1) / kThreads;
     if (blocks < 1) blocks = 1;
@@ -651,10 +651,11 @@ int occgrid_scatter_probe(int kind, void* d_plane, int64_t plane_cells, int64_t 
             k_probe_global_store8<<<(unsigned int)blocks, kThreads, 0, st>>>((uint8_t*)d_plane, (unsigned long long)plane_cells, iters, seed);
             break;
         case 2:
-        case 3: {
+        case 3:
+        case 6: {
             if (plane_cells > 56 * 1024) { set_last_error("probe: smem tile limited to 56Ki words"); return OCCGRID_E_ARG; }
             const size_t smem = (size_t)plane_cells * 4;
-            if (kind == 2) {
+            if (kind != 3) {
                 OCC_CUDA_TRY(cudaFuncSetAttribute(k_probe_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 k_probe_smem<true><<<(unsigned int)blocks, kThreads, smem, st>>>((unsigned int*)d_plane, (unsigned int)plane_cells, iters, seed);
             } else {

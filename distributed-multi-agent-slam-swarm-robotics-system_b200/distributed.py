@@ -424,105 +424,185 @@ class TiledSwarmMap:
 
 
 # ----------------------------------------------------------------------------------------------
-#  Merge: shard the extraction, replicate the ordered voxel chain
+#  Merge: what shards, and what the reference's semantics keep sequential
 # ----------------------------------------------------------------------------------------------
 
-class ShardedMapMerger:
-    """Agents are dealt round-robin to ranks; every rank extracts + transforms the occupied cells
-    of ITS agents (the HBM-bound scan, map_merger.py:71-77 + :58), the per-agent point lists are
-    all-gathered, and the order-dependent voxel chain (:59-60) is replayed identically on every
-    rank.  Result == MapMerger.merge on one GPU."""
+def agent_block(n_agents_total, world, rank):
+    """Agents are dealt to ranks in contiguous blocks (rank order == agent order)."""
+    return (n_agents_total * rank) // world, (n_agents_total * (rank + 1)) // world
 
-    def __init__(self, group=None, device=None):
+
+class ShardedMapMerger:
+    """Multi-GPU ``MapMerger.merge``: rank r holds the grids of the agents of ITS block
+    (``agent_block``).  Two modes:
+
+    ``mode='exact'`` (default) — results identical to the reference.  The reference's fuse is a
+    sequential chain: callback a voxel-filters the WHOLE accumulated cloud, and a voxel's point is
+    the unweighted mean of [the cloud's point, the slice's points] (map_merger.py:58-60), which is
+    order-dependent and not associative, so the chain itself cannot be split across agents without
+    changing the map.  What shards is the HBM-bound part: every rank scans, extracts and transforms
+    its agents' grids in ONE batched launch pair (bulk-copy staged scan), the per-agent point lists
+    are all-gathered (NCCL), and the ordered chain is replayed identically on every rank
+    ("replicas only" for the chain).  == ``MapMerger.merge`` on one GPU, bit for bit.
+
+    ``mode='raster_fuse'`` — the partitioning SURVEY §8e sketches: every rank runs the chain over
+    its OWN agents only, the cloud bounds are all-reduced (min / max, map_merger.py:95-98), every
+    rank rasterises its cloud into a partial int8 grid over the GLOBAL bounds (:100-111) and the
+    partial grids are fused with ReduceScatter(max) + AllGather on int8 (values {-1, 100}: max ==
+    "occupied wins", idempotent and order-free).  Scales with the ranks, but voxels that mix points
+    of agents living on different ranks are averaged per rank instead of jointly, so a small
+    fraction of cells differs from the reference's map — NOT a parity mode; callers get the count
+    of differing cells from bench.py / tools/check_multi_gpu.py, never a silent substitution."""
+
+    def __init__(self, group=None, device=None, mode='exact'):
         from .map_merger import MapMerger
+        if mode not in ('exact', 'raster_fuse'):
+            raise ValueError("mode must be 'exact' or 'raster_fuse'")
+        self.mode = mode
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.merger = MapMerger(device=device if device is not None else 'cuda')
+        self.stats = {}
 
-    def merge(self, local_grids, local_origins, res, local_transforms, n_agents_total):
-        """``local_*`` hold the agents a with a % world == rank, in increasing a."""
-        from .map_merger import MapMerger, make_grid_msg, se2_matrix
-        dev = self.merger.device
-        mine = list(range(self.rank, n_agents_total, self.world))
-        # the first NON-EMPTY grid is adopted untransformed (:40-43): find it globally first
-        nonempty = torch.zeros(n_agents_total, dtype=torch.int64, device=dev)
-        for j, a in enumerate(mine):
-            g = local_grids[j]
-            g = g if isinstance(g, torch.Tensor) else torch.from_numpy(np.asarray(g))
-            nonempty[a] = int(bool((g > 50).any()))
+    # ---- collectives (plumbing) --------------------------------------------------------------
+    def _all_gather_vec(self, local, total_len, lo):
+        """Variable-length all-gather of a per-agent vector: everybody contributes its block at [lo, ...)."""
+        full = torch.zeros(total_len, dtype=local.dtype, device=local.device)
+        full[lo:lo + local.numel()] = local
         if self.world > 1:
-            dist.all_reduce(nonempty, group=self.group)
-        ne = nonempty.cpu().tolist()
-        first_agent = next((a for a in range(n_agents_total) if ne[a]), -1)
-        pts = []
-        for j, a in enumerate(mine):
-            tmp = MapMerger(device=dev)
-            tmp._ensure_capacity(1 << 16)
-            T = local_transforms[j] if (local_transforms is not None and a != first_agent) else None
-            if T is not None and np.asarray(T).size == 3:
-                T = se2_matrix(*np.asarray(T, np.float64).tolist())
-            h, w = local_grids[j].shape
-            k = tmp._extract(make_grid_msg(local_grids[j], w, h, res, local_origins[j][0], local_origins[j][1]), T)
-            pts.append(torch.stack([tmp._cloud.x[:k], tmp._cloud.y[:k]], dim=1))
-        # all-gather variable-length point lists (pad to the global max)
-        lens = torch.zeros(n_agents_total, dtype=torch.int64, device=dev)
-        for j, a in enumerate(mine):
-            lens[a] = pts[j].shape[0]
-        if self.world > 1:
-            dist.all_reduce(lens, group=self.group)
-        lens_h = lens.cpu().tolist()
-        per_rank = -(-n_agents_total // self.world)
-        mx = max(max(lens_h), 1)
-        buf = torch.zeros((per_rank, mx, 2), dtype=torch.float64, device=dev)
-        for j in range(len(mine)):
-            buf[j, :pts[j].shape[0]] = pts[j]
-        if self.world > 1:
-            allbuf = [torch.empty_like(buf) for _ in range(self.world)]
-            dist.all_gather(allbuf, buf, group=self.group)
-        else:
-            allbuf = [buf]
-        # every rank now holds every slice: stage them in agent order and replay the ordered voxel
-        # chain (:59-60) with the incremental chain kernels, identically on every rank
+            dist.all_reduce(full, group=self.group)
+        return full
+
+    def merge(self, local_grids, local_origins, res, local_transforms, n_agents_total, fitness=None, to_host=True):
+        """``local_*``: the agents [lo, hi) = agent_block(n_agents_total, world, rank), in order.
+        ``fitness``: None or the GLOBAL float array [n_agents_total] (gate at map_merger.py:54-56).
+        Returns (int8 grid [H', W'], (origin_x, origin_y)) on every rank."""
+        if self.mode == 'raster_fuse':
+            return self._merge_raster_fuse(local_grids, local_origins, res, local_transforms, n_agents_total, fitness, to_host)
         from .map_merger import _Cloud
-        from . import _native
         m = self.merger
-        order = [a for a in range(n_agents_total) if lens_h[a] > 0]
-        total = sum(lens_h)
-        if total:
-            with torch.cuda.device(dev):
-                stage = _Cloud(total + 16, dev)
-                offs_h = np.zeros(n_agents_total + 1, np.int64)
-                offs_h[1:] = np.cumsum(lens_h)
-                for a in order:
-                    p = allbuf[a % self.world][a // self.world, :lens_h[a]]
-                    stage.x[offs_h[a]:offs_h[a + 1]].copy_(p[:, 0])
-                    stage.y[offs_h[a]:offs_h[a + 1]].copy_(p[:, 1])
-                offs = torch.from_numpy(offs_h).to(dev)
-                lo = torch.stack([stage.x[:total].min(), stage.y[:total].min()])
-                hi = torch.stack([stage.x[:total].max(), stage.y[:total].max()])
-                if m._n_global:
-                    n = m._n_global
-                    lo = torch.minimum(lo, torch.stack([m._cloud.x[:n].min(), m._cloud.y[:n].min()]))
-                    hi = torch.maximum(hi, torch.stack([m._cloud.x[:n].max(), m._cloud.y[:n].max()]))
-                bb = torch.cat([lo, hi]).cpu().tolist()
-                m._ensure_capacity(m._n_global + total + 1024)
-                if m._n_global == 0:                    # adopted as is (:40-43)
-                    a0 = order.pop(0)
-                    rc = m._lib.mapmerge_append_slice(stage.x.data_ptr(), stage.y.data_ptr(), offs.data_ptr(), a0,
-                                                      m._cloud.x.data_ptr(), m._cloud.y.data_ptr(), m._cloud.capacity,
-                                                      m._cloud.count.data_ptr(), m._status.data_ptr(), None, m._stream())
-                    _native.check(rc, 'mapmerge_append_slice')
-                    m.map_resolution = float(res)
-                v = m.map_resolution
-                if order:
-                    # means stay inside the hull of the points, so these bounds cover every cloud of the chain
-                    lat_w, lat_h = int((bb[2] - bb[0]) / v) + 4, int((bb[3] - bb[1]) / v) + 4
-                    m.chain_stats = m._run_chain(stage, offs, n_agents_total, order, lat_w, lat_h, max(lens_h))
-                m._n_global = int(m._cloud.count.item())
-                m._check_status()
-        out = m.publish_global_map()
+        dev = m.device
+        A = int(n_agents_total)
+        lo, hi = agent_block(A, self.world, self.rank)
+        if len(local_grids) != hi - lo:
+            raise ValueError(f'rank {self.rank} must hold agents [{lo}, {hi}) of {A}')
+        with torch.cuda.device(dev):
+            dgr = m._as_device_grids(local_grids)
+            shape = dgr[0].shape if dgr else (0, 0)
+            shp = torch.tensor([shape[0], shape[1], -shape[0], -shape[1]], dtype=torch.int64, device=dev)
+            if self.world > 1:
+                dist.all_reduce(shp, op=dist.ReduceOp.MAX, group=self.group)
+            H, W = int(shp[0].item()), int(shp[1].item())
+            if not all(d.shape == (H, W) for d in dgr) or (int(shp[2].item()), int(shp[3].item())) != (-H, -W):
+                raise OccGridError('ShardedMapMerger: all agent grids must have the same shape')
+            # pass 1 (sharded): occupied cells of my agents; everybody learns every count
+            if dgr:
+                counts, ptrs, bws = m._count_occupied(dgr, True)
+            else:
+                counts, ptrs, bws = torch.zeros(0, dtype=torch.int64, device=dev), None, None
+            n_occ = self._all_gather_vec(counts, A, lo).cpu().numpy()
+            meta = np.zeros((A, 18))                 # every rank plans with the GLOBAL callback table (tiny, host-side)
+            if hi > lo:
+                meta[lo:hi, :2] = np.asarray(local_origins, np.float64).reshape(hi - lo, 2)
+                meta[lo:hi, 2:] = m._as_matrices(local_transforms, hi - lo).reshape(hi - lo, 16)
+            if self.world > 1:
+                md = torch.from_numpy(meta).to(dev)
+                dist.all_reduce(md, group=self.group)       # disjoint rows: the sum is the concatenation, bit for bit
+                meta = md.cpu().numpy()
+            org, Tm = np.ascontiguousarray(meta[:, :2]), np.ascontiguousarray(meta[:, 2:]).reshape(A, 4, 4)
+            fit = np.ones(A) if fitness is None else np.asarray(fitness, np.float64).reshape(A)
+            hw = np.tile(np.array([[H, W]], np.float64), (A, 1))
+            plan = m._plan_merge(n_occ, fit, Tm, org, hw, res)
+            if plan is None:
+                return None, None
+            use, order, first, bb, n_new = plan
+            # pass 2 (sharded): my used agents' points, transformed, in one launch
+            n_mine = int(n_occ[lo:hi][use[lo:hi]].sum())
+            if dgr:
+                lstage, loffs = m._write_slices(dgr, ptrs, bws, counts, use[lo:hi], Tm[lo:hi], org[lo:hi], res, n_mine)
+            # all-gather the slices: agent order == rank order, so the gathered stage is simply the concatenation
+            stage = _Cloud(n_new + 16, dev)
+            offs_h = np.zeros(A + 1, np.int64)
+            offs_h[1:] = np.cumsum(np.where(use, n_occ, 0))
+            per_rank = [int(offs_h[agent_block(A, self.world, r)[1]] - offs_h[agent_block(A, self.world, r)[0]]) for r in range(self.world)]
+            if self.world > 1:
+                mx = max(max(per_rank), 1)
+                send = torch.zeros((2, mx), dtype=torch.float64, device=dev)
+                if n_mine:
+                    send[0, :n_mine] = lstage.x[:n_mine]
+                    send[1, :n_mine] = lstage.y[:n_mine]
+                recv = torch.empty((self.world, 2, mx), dtype=torch.float64, device=dev)
+                dist.all_gather_into_tensor(recv, send, group=self.group)
+                for r in range(self.world):
+                    b0 = int(offs_h[agent_block(A, self.world, r)[0]])
+                    stage.x[b0:b0 + per_rank[r]] = recv[r, 0, :per_rank[r]]
+                    stage.y[b0:b0 + per_rank[r]] = recv[r, 1, :per_rank[r]]
+            elif n_mine:
+                stage.x[:n_mine] = lstage.x[:n_mine]
+                stage.y[:n_mine] = lstage.y[:n_mine]
+            offs = torch.from_numpy(offs_h).to(dev)
+            # the ordered voxel chain (:59-60), replayed identically on every rank
+            m._ensure_capacity(m._n_global + n_new + 1024)
+            v = float(res) if first else m.map_resolution
+            lat_w, lat_h = int((bb[2] - bb[0]) / v) + 4, int((bb[3] - bb[1]) / v) + 4
+            if first:                                   # adopted as is (:40-43)
+                a0 = order.pop(0)
+                rc = m._lib.mapmerge_append_slice(stage.x.data_ptr(), stage.y.data_ptr(), offs.data_ptr(), a0,
+                                                  m._cloud.x.data_ptr(), m._cloud.y.data_ptr(), m._cloud.capacity,
+                                                  m._cloud.count.data_ptr(), m._status.data_ptr(), None, m._stream())
+                _native.check(rc, 'mapmerge_append_slice')
+                m.map_resolution = float(res)
+                m.map_origin = [float(org[a0, 0]), float(org[a0, 1])]
+            m.chain_stats = m._run_chain(stage, offs, A, order, lat_w, lat_h, int(n_occ[use].max())) if order else None
+            m._n_global = int(m._cloud.count.item())
+            m._check_status()
+        out = m.publish_global_map(to_host=to_host)
         return (out.data, (out.info.origin.position.x, out.info.origin.position.y)) if out is not None else (None, None)
+
+    def _merge_raster_fuse(self, local_grids, local_origins, res, local_transforms, n_agents_total, fitness, to_host):
+        """per-rank chain -> AllReduce(min/max) of the bounds -> partial raster over the
+        global bounds -> ReduceScatter(max, int8) + AllGather."""
+        from .map_merger import make_grid_msg
+        m = self.merger
+        dev = m.device
+        A = int(n_agents_total)
+        lo, hi = agent_block(A, self.world, self.rank)
+        fit = None if fitness is None else np.asarray(fitness, np.float64).reshape(A)[lo:hi]
+        with torch.cuda.device(dev):
+            # my agents' own chain; only the rank that holds agent 0's block adopts its first cloud untransformed
+            if hi > lo:
+                m.merge(local_grids, local_origins, res, local_transforms, fitness=fit, publish=False, adopt_first=self.rank == 0)
+            big = 1.0e300
+            b = torch.tensor([big, big, big, big], dtype=torch.float64, device=dev)
+            if m._n_global:
+                m._bounds_of(m._cloud)
+                b = torch.stack([m._bounds[0], m._bounds[1], -m._bounds[2], -m._bounds[3]])
+            if self.world > 1:
+                dist.all_reduce(b, op=dist.ReduceOp.MIN, group=self.group)          # min of (min_x, min_y, -max_x, -max_y)
+            bh = b.cpu().numpy()
+            if bh[0] >= big:
+                return None, None
+            min_x, min_y, max_x, max_y = float(bh[0]), float(bh[1]), float(-bh[2]), float(-bh[3])
+            v = m.map_resolution if m._n_global else float(res)
+            width = int(np.ceil((max_x - min_x) / v)) + 1                            # :100
+            height = int(np.ceil((max_y - min_y) / v)) + 1                           # :101
+            cells = width * height
+            padded = -(-cells // (16 * self.world)) * (16 * self.world)
+            part = torch.full((padded,), -1, dtype=torch.int8, device=dev)
+            if m._n_global:
+                gb = torch.tensor([min_x, min_y, max_x, max_y], dtype=torch.float64, device=dev)
+                rc = m._lib.mapmerge_rasterise(m._cloud.x.data_ptr(), m._cloud.y.data_ptr(), m._cloud.count.data_ptr(), v,
+                                               gb.data_ptr(), width, height, part.data_ptr(), m._stream())
+                _native.check(rc, 'mapmerge_rasterise')
+            if self.world > 1:
+                shard = torch.empty(padded // self.world, dtype=torch.int8, device=dev)
+                dist.reduce_scatter_tensor(shard, part, op=dist.ReduceOp.MAX, group=self.group)   # occupied wins
+                dist.all_gather_into_tensor(part, shard, group=self.group)
+            grid = part[:cells].view(height, width)
+            data = grid.cpu().numpy() if to_host else grid
+        m.published = make_grid_msg(data, width, height, v, min_x, min_y, frame_id='map_global')
+        return data, (min_x, min_y)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -530,7 +610,7 @@ class ShardedMapMerger:
 # ----------------------------------------------------------------------------------------------
 
 def make_rank_sessions(world, rank, device, packets_per_rank, pool, strategy='auto',
-                       grid_per_gpu=4096, agents_per_gpu=64, exchange='p2p', ingest='uniform'):
+                       grid_per_gpu=4096, agents_per_gpu=64, exchange='p2p', ingest='uniform', layout='bands'):
     """Weak scaling of BASELINE configs[1] / configs[3]: (grid_per_gpu*world)^2 map cut into `world`
     row bands, agents_per_gpu*world agents, each rank ingests its own `packets_per_rank` share.
     ``ingest='uniform'`` (default, the worst case): every rank's share covers ALL agents, so
@@ -551,8 +631,10 @@ def make_rank_sessions(world, rank, device, packets_per_rank, pool, strategy='au
                                      origin=(origin[0], origin[1] + y0 * 0.05),
                                      seed=1000 + 97 * i + rank)
         else:
+            # layout='bands': the same number of rooms in every band (weak scaling: same work per GPU);
+            # 'lattice': one square lattice over the whole map, whose rows fall unevenly into the bands
             sh = st.generate_session(n_agents=agents_per_gpu * world, n_packets=packets_per_rank, grid_size=side,
-                                     origin=origin, seed=1000 + 97 * i + rank)
+                                     origin=origin, seed=1000 + 97 * i + rank, bands=world if layout == 'bands' else 1)
         sessions.append({'packets': tmap.local.stage_packets(sh['packets'])[0],
                          'agent_idx': torch.from_numpy(sh['agent_idx']).to(device),
                          'agent_offsets': torch.from_numpy(sh['agent_offsets']).to(device), 'grid': sh['grid'],

@@ -353,7 +353,7 @@ class MapMerger:
             out[a] = se2_matrix(*T.tolist()) if T.size == 3 else T.reshape(4, 4)
         return np.ascontiguousarray(out)
 
-    def merge(self, grids, origins, res, transforms=None, fitness=None, to_host=True):
+    def merge(self, grids, origins, res, transforms=None, fitness=None, to_host=True, publish=True, adopt_first=True):
         """Fuse A agent grids in order: ``grids`` int8 [A, H, W] (host or device), ``origins``
         float64 [A, 2], ``transforms`` [A, 4, 4] or [A, 3] (tx, ty, theta) or None (identity).
         Equal to A successive ``map_callback`` calls (same sequential voxel chain, :58-60);
@@ -361,76 +361,31 @@ class MapMerger:
         fused by the incremental chain (``mapmerge_chain_*``: work per callback proportional to the
         slice, not to the accumulated cloud, while the voxel lattice stands still); the host reads
         the occupied-cell counts up front, the chain state every few callbacks and the final bounds.
+        ``adopt_first=False`` (multi-GPU shards that do not hold the globally first cloud): the first
+        local cloud is transformed like every other one.  ``publish=False``: fuse only.
         Returns (int8 grid [H', W'], (origin_x, origin_y))."""
         A = len(grids)
         with torch.cuda.device(self.device):
             dev = self._as_device_grids(grids)
             same_shape = all(d.shape == dev[0].shape for d in dev)
-            counts = torch.zeros(A, dtype=torch.int64, device=self.device)
-            if same_shape:                       # one pass over all grids
-                h, w = dev[0].shape
-                ptrs = torch.from_numpy(np.array([d.data_ptr() for d in dev], np.int64)).to(self.device)
-                bws = self._workspace('extract_batch', self._lib.mapmerge_extract_batch_workspace_bytes(h * w, A))
-                rc = self._lib.mapmerge_extract_batch_count(ptrs.data_ptr(), A, w, h, counts.data_ptr(), bws.data_ptr(),
-                                                            bws.numel(), self._stream())
-                _native.check(rc, 'mapmerge_extract_batch_count')
-            else:
-                for a in range(A):
-                    rc = self._lib.mapmerge_count_occupied(dev[a].data_ptr(), dev[a].numel(), counts[a:a + 1].data_ptr(), self._stream())
-                    _native.check(rc, 'mapmerge_count_occupied')
+            counts, ptrs, bws = self._count_occupied(dev, same_shape)
             # host work that does not need the counts overlaps the counting pass
             org = np.ascontiguousarray(np.asarray(origins, np.float64).reshape(A, 2))
             Tm = self._as_matrices(transforms, A)
             fit = np.ones(A) if fitness is None else np.asarray(fitness, np.float64).reshape(A)
             hw = np.array([[d.shape[0], d.shape[1]] for d in dev], np.float64)
             n_occ = counts.cpu().numpy()                            # host sync 1
-            have_cloud = self._n_global > 0
-            use = (n_occ > 0) & (fit >= 0.6)                        # :37-38, :54-56
-            if not have_cloud:
-                nz = np.flatnonzero(n_occ > 0)
-                if nz.size == 0:
-                    return None, None
-                use[:nz[0]] = False
-                use[nz[0]] = True                                   # the first cloud is adopted as is (:40-43):
-                Tm[nz[0]] = np.eye(4)                               # no ICP, no fitness test, no transform
-            used = np.flatnonzero(use)
-            if have_cloud:
-                self._bounds_of(self._cloud)
-                bb = self._bounds.cpu().numpy().tolist()
-            else:
-                bb = [math.inf, math.inf, -math.inf, -math.inf]
-            if used.size:
-                # transformed extents of the used grids bound every cloud of the chain
-                x0, y0 = org[used, 0], org[used, 1]
-                x1, y1 = x0 + hw[used, 1] * res, y0 + hw[used, 0] * res
-                M = Tm[used]
-                cx = np.stack([x0, x0, x1, x1], 1)
-                cy = np.stack([y0, y1, y0, y1], 1)
-                px = M[:, 0, 0, None] * cx + M[:, 0, 1, None] * cy + M[:, 0, 3, None]
-                py = M[:, 1, 0, None] * cx + M[:, 1, 1, None] * cy + M[:, 1, 3, None]
-                bb = [min(bb[0], float(px.min())), min(bb[1], float(py.min())), max(bb[2], float(px.max())), max(bb[3], float(py.max()))]
-            n_new = int(n_occ[used].sum())
-            total = self._n_global + n_new
-            if total == 0:
+            plan = self._plan_merge(n_occ, fit, Tm, org, hw, res, adopt_first)
+            if plan is None:
                 return None, None
-            self._ensure_capacity(total + 1024)
-            first = not have_cloud
+            use, order, first, bb, n_new = plan
+            self._ensure_capacity(self._n_global + n_new + 1024)
             v = float(res) if first else self.map_resolution
             lat_w, lat_h = int((bb[2] - bb[0]) / v) + 4, int((bb[3] - bb[1]) / v) + 4
+            stage = offs = None
             if same_shape:                       # all slices extracted + transformed in one launch
-                h, w = dev[0].shape
-                stage = _Cloud(n_new + 16, self.device)
-                offs = torch.zeros(A + 1, dtype=torch.int64, device=self.device)
-                xf = torch.empty(A * 96, dtype=torch.uint8, device=self.device)
-                org_d = torch.from_numpy(org).to(self.device)
-                use_h = np.ascontiguousarray(use.astype(np.uint8))
-                rc = self._lib.mapmerge_extract_batch_write(
-                    ptrs.data_ptr(), A, w, h, float(res), org_d.data_ptr(), Tm.ctypes.data, use_h.ctypes.data, xf.data_ptr(),
-                    stage.x.data_ptr(), stage.y.data_ptr(), stage.capacity, counts.data_ptr(), offs.data_ptr(),
-                    self._status.data_ptr(), bws.data_ptr(), bws.numel(), self._stream())
-                _native.check(rc, 'mapmerge_extract_batch_write')
+                stage, offs = self._write_slices(dev, ptrs, bws, counts, use, Tm, org, res, n_new)
             chain = None
-            order = used.tolist()
             if first:                            # adopted as is (:40-43): no filter on this callback
                 a = order.pop(0)
                 if same_shape:
@@ -439,12 +394,13 @@ class MapMerger:
                                                          self._cloud.count.data_ptr(), self._status.data_ptr(), None, self._stream())
                     _native.check(rc, 'mapmerge_append_slice')
                 else:
-                    self._extract_async(make_grid_msg(dev[a], dev[a].shape[1], dev[a].shape[0], res, org[a, 0], org[a, 1]), None)
+                    self._extract_async(make_grid_msg(dev[a], dev[a].shape[1], dev[a].shape[0], res, org[a, 0], org[a, 1]),
+                                        None if adopt_first else Tm[a])
                 self.map_resolution = float(res)
                 self.map_origin = [float(org[a, 0]), float(org[a, 1])]
             if same_shape:
                 if order:
-                    chain = self._run_chain(stage, offs, A, order, lat_w, lat_h, int(n_occ[used].max()))
+                    chain = self._run_chain(stage, offs, A, order, lat_w, lat_h, int(n_occ[use].max()))
             else:
                 for a in order:
                     self._extract_async(make_grid_msg(dev[a], dev[a].shape[1], dev[a].shape[0], res, org[a, 0], org[a, 1]), Tm[a])
@@ -452,10 +408,86 @@ class MapMerger:
             self.chain_stats = chain
             self._n_global = int(self._cloud.count.item())          # host sync (with the status word)
             self._check_status()
+        if not publish:
+            return None, None
         out = self.publish_global_map(to_host=to_host)
         if out is None:
             return None, None
         return out.data, (out.info.origin.position.x, out.info.origin.position.y)
+
+    # ---- pieces of the batched merge (also driven by distributed.ShardedMapMerger) ---------------
+    def _count_occupied(self, dev, same_shape):
+        """Pass 1 over the grids: occupied cells per grid (device int64 [A]).  Equal-shaped grids go
+        through the batched scan (bulk-copy staged when every grid is 16-byte aligned)."""
+        A = len(dev)
+        counts = torch.zeros(A, dtype=torch.int64, device=self.device)
+        ptrs = bws = None
+        if same_shape:                           # one pass over all grids
+            h, w = dev[0].shape
+            ptrs = torch.from_numpy(np.array([d.data_ptr() for d in dev], np.int64)).to(self.device)
+            bws = self._workspace('extract_batch', self._lib.mapmerge_extract_batch_workspace_bytes(h * w, A))
+            bulk_ok = 1 if all(d.data_ptr() % 16 == 0 for d in dev) else 0       # cp.async.bulk needs 16-byte aligned sources
+            rc = self._lib.mapmerge_extract_batch_count(ptrs.data_ptr(), A, w, h, counts.data_ptr(), bws.data_ptr(),
+                                                        bws.numel(), bulk_ok, self._stream())
+            _native.check(rc, 'mapmerge_extract_batch_count')
+        else:
+            for a in range(A):
+                rc = self._lib.mapmerge_count_occupied(dev[a].data_ptr(), dev[a].numel(), counts[a:a + 1].data_ptr(), self._stream())
+                _native.check(rc, 'mapmerge_count_occupied')
+        return counts, ptrs, bws
+
+    def _plan_merge(self, n_occ, fit, Tm, org, hw, res, adopt_first=True):
+        """Host decisions of a batched merge: which agents take part (:37-38, :54-56), which cloud is
+        adopted as is (:40-43; its transform becomes the identity in `Tm`), the callback order and a
+        bound on every cloud of the chain.  -> (use, order, first, bb, n_new) or None."""
+        have_cloud = self._n_global > 0
+        use = (n_occ > 0) & (fit >= 0.6)                        # :37-38, :54-56
+        if not have_cloud:
+            nz = np.flatnonzero(n_occ > 0)
+            if nz.size == 0:
+                return None
+            use[:nz[0]] = False
+            use[nz[0]] = True                                   # the first cloud is adopted as is (:40-43):
+            if adopt_first:
+                Tm[nz[0]] = np.eye(4)                           # no ICP, no fitness test, no transform
+        used = np.flatnonzero(use)
+        if have_cloud:
+            self._bounds_of(self._cloud)
+            bb = self._bounds.cpu().numpy().tolist()
+        else:
+            bb = [math.inf, math.inf, -math.inf, -math.inf]
+        if used.size:
+            # transformed extents of the used grids bound every cloud of the chain
+            x0, y0 = org[used, 0], org[used, 1]
+            x1, y1 = x0 + hw[used, 1] * res, y0 + hw[used, 0] * res
+            M = Tm[used]
+            cx = np.stack([x0, x0, x1, x1], 1)
+            cy = np.stack([y0, y1, y0, y1], 1)
+            px = M[:, 0, 0, None] * cx + M[:, 0, 1, None] * cy + M[:, 0, 3, None]
+            py = M[:, 1, 0, None] * cx + M[:, 1, 1, None] * cy + M[:, 1, 3, None]
+            bb = [min(bb[0], float(px.min())), min(bb[1], float(py.min())), max(bb[2], float(px.max())), max(bb[3], float(py.max()))]
+        n_new = int(n_occ[used].sum())
+        if self._n_global + n_new == 0:
+            return None
+        return use, used.tolist(), not have_cloud, bb, n_new
+
+    def _write_slices(self, dev, ptrs, bws, counts, use, Tm, org, res, n_new):
+        """Pass 2: every used grid's occupied cells -> transformed points, agent after agent, in a
+        staging cloud; offs[a] = start of agent a's slice."""
+        A = len(dev)
+        h, w = dev[0].shape
+        stage = _Cloud(n_new + 16, self.device)
+        offs = torch.zeros(A + 1, dtype=torch.int64, device=self.device)
+        xf = torch.empty(A * 96, dtype=torch.uint8, device=self.device)
+        org_d = torch.from_numpy(np.ascontiguousarray(org)).to(self.device)
+        use_h = np.ascontiguousarray(use.astype(np.uint8))
+        Tm = np.ascontiguousarray(Tm)
+        rc = self._lib.mapmerge_extract_batch_write(
+            ptrs.data_ptr(), A, w, h, float(res), org_d.data_ptr(), Tm.ctypes.data, use_h.ctypes.data, xf.data_ptr(),
+            stage.x.data_ptr(), stage.y.data_ptr(), stage.capacity, counts.data_ptr(), offs.data_ptr(),
+            self._status.data_ptr(), bws.data_ptr(), bws.numel(), self._stream())
+        _native.check(rc, 'mapmerge_extract_batch_write')
+        return stage, offs
 
     def _run_chain(self, stage, offs, n_agents, order, lat_w, lat_h, slice_cap):
         """The callbacks `global += slice; global = voxel_down_sample(global)` (:58-60) for the
@@ -479,7 +511,7 @@ class MapMerger:
         v = self.map_resolution
         state = (ctypes.c_int32 * 2)()
         stats = {'callbacks': len(order), 'rebuilds': 0, 'rebounds': 0, 'polls': 0}
-        cursor, burst = 0, 1
+        cursor, burst = 0, 4
         while cursor < len(order):
             c = self._cloud
             k = min(burst, len(order) - cursor)
@@ -491,7 +523,7 @@ class MapMerger:
             stats['polls'] += 1
             cursor, stalled = int(state[0]), int(state[1])
             if stalled == 0:
-                burst = min(burst * 2, 32)
+                burst = min(burst * 2, 64)
             elif stalled == 1:                   # the lattice moved: full filter + new voxel map
                 sp = self._spare
                 rc = lib.mapmerge_chain_rebuild(ws.data_ptr(), dims.ctypes.data, n_agents, stage.x.data_ptr(), stage.y.data_ptr(),
@@ -503,7 +535,7 @@ class MapMerger:
                 self._cloud, self._spare = self._spare, self._cloud
                 stats['rebuilds'] += 1
                 cursor += 1
-                burst = 2
+                burst = 8
             elif stalled == 3:                   # min corner may have moved inwards: exact bounds first
                 rc = lib.mapmerge_chain_rebounds(ws.data_ptr(), dims.ctypes.data, n_agents, c.x.data_ptr(), c.y.data_ptr(),
                                                  c.count.data_ptr(), self._stream())

@@ -71,9 +71,28 @@ def _lap(waypoints, steps_per_meter=25, turn_steps=4):
     return np.array(px), np.array(py), np.array(pyaw)
 
 
-def room_lattice(n_rooms, grid_size, resolution, origin):
-    """Room origins on a near-square lattice inside the grid, each 6 m x 4 m room fully inside."""
+def room_lattice(n_rooms, grid_size, resolution, origin, bands=1):
+    """Room origins on a near-square lattice inside the grid, each 6 m x 4 m room fully inside.
+    ``bands`` > 1 (multi-GPU row bands): every band of grid_size / bands rows gets the same number of
+    rooms, on its own lattice inside the band and clear of the band edges — the weak-scaling premise
+    (same work per GPU) made true for the synthetic swarm."""
     span = grid_size * resolution
+    if bands > 1:
+        if n_rooms % bands:
+            raise ValueError('rooms must divide evenly into the bands')
+        per = n_rooms // bands
+        band_h = span / bands
+        rows = max(1, int(round(math.sqrt(per * band_h / span / 1.5))))
+        cols = int(math.ceil(per / rows))
+        pitch_x, pitch_y = span / cols, band_h / rows
+        if pitch_x < 8.0 or pitch_y < 6.0:
+            raise ValueError('grid too small for that many rooms')
+        out = []
+        for b in range(bands):
+            for r in range(per):
+                i, j = r % cols, r // cols
+                out.append((origin[0] + (i + 0.5) * pitch_x - 2.5, origin[1] + b * band_h + (j + 0.5) * pitch_y))
+        return np.asarray(out, np.float64)
     cols = int(math.ceil(math.sqrt(n_rooms * 1.5)))
     rows = int(math.ceil(n_rooms / cols))
     pitch_x, pitch_y = span / cols, span / rows
@@ -87,7 +106,7 @@ def room_lattice(n_rooms, grid_size, resolution, origin):
 
 
 def generate_session(n_agents=64, n_packets=2_500_000, grid_size=4096, resolution=0.05,
-                     origin=(-102.4, -102.4), seed=42, time_sorted=True):
+                     origin=(-102.4, -102.4), seed=42, time_sorted=True, bands=1):
     """Synthetic many-agent session.
 
     Returns a dict:
@@ -103,7 +122,7 @@ def generate_session(n_agents=64, n_packets=2_500_000, grid_size=4096, resolutio
         raise ValueError('agents come in BOT1/BOT2 pairs')
     rng = np.random.default_rng(seed)
     n_rooms = n_agents // 2
-    rooms = room_lattice(n_rooms, grid_size, resolution, origin)
+    rooms = room_lattice(n_rooms, grid_size, resolution, origin, bands)
     offsets = np.zeros((n_agents + 1, 2), np.float64)
     offsets[1::2] = rooms
     offsets[2::2] = rooms

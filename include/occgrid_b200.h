@@ -306,7 +306,10 @@ int mapmerge_extract_transform(const int8_t* d_grid, int32_t width, int32_t heig
  * slice a with mapmerge_append_slice when callback a's turn comes (:59). */
 size_t mapmerge_extract_batch_workspace_bytes(int64_t n_cells, int n_agents);
 int mapmerge_extract_batch_count(const int8_t* const* d_grids, int n_agents, int32_t width, int32_t height,
-                                 int64_t* d_agent_total, void* d_ws, size_t ws_bytes, void* stream);
+                                 int64_t* d_agent_total, void* d_ws, size_t ws_bytes,
+                                 int grids_bulk_ok /* 1: every grid pointer is 16-byte aligned -> the scan runs on
+                                                      cp.async.bulk + mbarrier staged shared memory (TMA) */,
+                                 void* stream);
 int mapmerge_extract_batch_write(const int8_t* const* d_grids, int n_agents, int32_t width, int32_t height,
                                  double res, const double* d_origins, const double* T_host,
                                  const uint8_t* use_host, void* d_xforms,

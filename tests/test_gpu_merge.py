@@ -242,24 +242,50 @@ def test_2048_grids(MM):
 
 
 def test_sharded_merger_single_rank_equals_merge(MM):
-    """ShardedMapMerger (agents dealt to ranks, extraction sharded, ordered voxel chain replicated)
-    with world = 1 must equal MapMerger.merge and the oracle; an empty first grid exercises the
-    'first NON-EMPTY grid is adopted untransformed' rule (map_merger.py:37-43)."""
+    """ShardedMapMerger (agent blocks per rank, batched extraction sharded, ordered voxel chain
+    replicated) with world = 1 must equal MapMerger.merge and the oracle; an empty first grid
+    exercises the 'first NON-EMPTY grid is adopted untransformed' rule (map_merger.py:37-43), and a
+    second merge on the same object continues the cloud (every agent transformed from then on)."""
     from occgrid_b200.distributed import ShardedMapMerger
     from oracle import merge_oracle as MO
     r = np.random.default_rng(12)
-    grids = [np.full((160, 160), -1, np.int8)] + [synth_agent_grid(160, 70 + a) for a in range(4)]
-    origins = np.tile(np.array([[-4.0, -4.0]]), (5, 1))
-    tf = np.stack([MO.se2_matrix(*r.uniform(-3, 3, 2), r.uniform(-math.pi, math.pi)) for _ in range(5)])
+    grids = [np.full((160, 160), -1, np.int8)] + [synth_agent_grid(160, 70 + a) for a in range(6)]
+    origins = np.tile(np.array([[-4.0, -4.0]]), (7, 1))
+    tf = np.stack([MO.se2_matrix(*r.uniform(-3, 3, 2), r.uniform(-math.pi, math.pi)) for _ in range(7)])
+    fit = np.array([1.0, 1.0, 1.0, 0.5, 1.0, 1.0, 0.59])
     o = MO.OracleMerger()
     want = None
     for a in range(5):
-        out = o.map_callback(grids[a].ravel(), 160, 160, 0.05, -4.0, -4.0, tf[a])
+        out = o.map_callback(grids[a].ravel(), 160, 160, 0.05, -4.0, -4.0, tf[a], accept=fit[a] >= 0.6)
         want = out if out is not None else want
-    got, origin = ShardedMapMerger().merge(grids, origins, 0.05, tf, 5)
+    sm = ShardedMapMerger()
+    got, origin = sm.merge(grids[:5], origins[:5], 0.05, tf[:5], 5, fitness=fit[:5])
     assert np.array_equal(got, want[0]) and origin == want[1]
-    got2, origin2 = MM.MapMerger().merge(grids, origins, 0.05, tf)
+    got2, origin2 = MM.MapMerger().merge(grids[:5], origins[:5], 0.05, tf[:5], fitness=fit[:5])
     assert np.array_equal(got2, want[0]) and origin2 == want[1]
+    for a in (5, 6):                                   # second call: the merger already holds a cloud
+        out = o.map_callback(grids[a].ravel(), 160, 160, 0.05, -4.0, -4.0, tf[a], accept=fit[a] >= 0.6)
+        want = out if out is not None else want
+    got3, origin3 = sm.merge(grids[5:], origins[5:], 0.05, tf[5:], 2, fitness=fit[5:])
+    assert np.array_equal(got3, want[0]) and origin3 == want[1]
+    pc = sm.merger.global_pcd
+    assert np.array_equal(pc[:, 0], o.gx) and np.array_equal(pc[:, 1], o.gy)
+
+
+def test_raster_fuse_mode_single_rank_equals_merge(MM):
+    """mode='raster_fuse' (per-rank chain + bounds all-reduce + max fuse of partial rasters, SURVEY
+    §8e) degenerates to the exact merge when one rank holds every agent."""
+    from occgrid_b200.distributed import ShardedMapMerger
+    from oracle import merge_oracle as MO
+    r = np.random.default_rng(13)
+    grids = [synth_agent_grid(128, 170 + a) for a in range(4)]
+    origins = np.tile(np.array([[-3.2, -3.2]]), (4, 1))
+    tf = np.stack([MO.se2_matrix(*r.uniform(-2, 2, 2), r.uniform(-math.pi, math.pi)) for _ in range(4)])
+    o = MO.OracleMerger()
+    for a in range(4):
+        want = o.map_callback(grids[a].ravel(), 128, 128, 0.05, -3.2, -3.2, tf[a])
+    got, origin = ShardedMapMerger(mode='raster_fuse').merge(grids, origins, 0.05, tf, 4)
+    assert np.array_equal(got, want[0]) and origin == want[1]
 
 
 # ---- fixtures produced by EXECUTING the unmodified reference (oracle/make_golden_merge.py) --------

@@ -36,9 +36,10 @@ for exchange in modes:
         print(f'world={world} exchange={tmap.exchange}: map {"bit-exact" if same else "DIFFERS"} vs oracle '
               f'({c["beams"]} beams, {int((want != -1).sum())} known cells)', flush=True)
     dist.barrier()
-# map fusion: agents dealt round-robin to ranks, extraction sharded, ordered voxel chain replicated
+# map fusion: agent blocks per rank, batched extraction sharded, ordered voxel chain replicated (mode 'exact');
+# and the SURVEY §8e partitioning (per-rank chains, bounds all-reduce, max fuse of partial rasters; not a parity mode)
 import math
-from occgrid_b200.distributed import ShardedMapMerger
+from occgrid_b200.distributed import ShardedMapMerger, agent_block
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
 from merge_util import synth_agent_grid
 from oracle import merge_oracle as MO
@@ -46,16 +47,21 @@ A, S = 3 * world + 1, 256
 rgen = np.random.default_rng(3)
 grids = [synth_agent_grid(S, 500 + a) for a in range(A)]
 tf = [MO.se2_matrix(*rgen.uniform(-5, 5, 2), rgen.uniform(-math.pi, math.pi)) for _ in range(A)]
-mine = list(range(rank, A, world))
-got, origin = ShardedMapMerger(device=dev).merge([grids[a] for a in mine], [(-6.4, -6.4)] * len(mine), 0.05,
-                                                 [tf[a] for a in mine], A)
+lo, hi = agent_block(A, world, rank)
+got, origin = ShardedMapMerger(device=dev).merge(grids[lo:hi], [(-6.4, -6.4)] * (hi - lo), 0.05, tf[lo:hi], A)
+fused, forigin = ShardedMapMerger(device=dev, mode='raster_fuse').merge(grids[lo:hi], [(-6.4, -6.4)] * (hi - lo), 0.05, tf[lo:hi], A)
 if rank == 0:
     o = MO.OracleMerger()
     for a in range(A):
         want = o.map_callback(grids[a].ravel(), S, S, 0.05, -6.4, -6.4, tf[a])
     same = bool(np.array_equal(got, want[0]) and origin == want[1])
     ok &= same
-    print(f'world={world} sharded merge of {A} grids: {"bit-exact" if same else "DIFFERS"} vs oracle', flush=True)
+    print(f'world={world} sharded merge of {A} grids (exact): {"bit-exact" if same else "DIFFERS"} vs oracle', flush=True)
+    if fused.shape == want[0].shape:
+        print(f'world={world} raster_fuse: {int((fused != want[0]).sum())} of {fused.size} cells differ from the reference map '
+              f'(occupied: {int((fused == 100).sum())} vs {int((want[0] == 100).sum())})', flush=True)
+    else:
+        print(f'world={world} raster_fuse: map {fused.shape} vs reference {want[0].shape}', flush=True)
 dist.barrier()
 if rank == 0:
     print('PASS' if ok else 'FAIL', flush=True)

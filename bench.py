@@ -256,7 +256,7 @@ def main():
     ap.add_argument('--strategy', default='auto')
     ap.add_argument('--packets', type=int, default=PACKETS_PER_BATCH)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
-    ap.add_argument('--no-merge', action='store_true', help='N=1: skip the merged-grids/s leg (BASELINE configs[2])')
+    ap.add_argument('--no-merge', action='store_true', help='skip the merged-grids/s leg (BASELINE configs[2])')
     ap.add_argument('--trace', action='store_true', help='print per-step wall times (debug)')
     ap.add_argument('--grid-per-gpu', type=int, default=0,
                     help='N>1: map side = this x N.  Default 8192 (with 128 agents per GPU: N=8 is BASELINE configs[3], '
@@ -572,6 +572,13 @@ def main():
                          'h2d_bytes_per_step': int(host[0].numel()) * n, 'd2h_bytes_per_step': int(_native.N_COUNTERS * 8) * n,
                          'steps': Ke, 'ms_per_step': e_ms / Ke,
                          'api': 'TiledSwarmMap.update_packets(pinned host uint8[n,42] share per rank) + counters() read-back'}
+    if n > 1 and not args.no_merge:
+        # second half of BASELINE.json's metric at N GPUs (needs the integration buffers gone first)
+        del tmap, sessions, host, step
+        grid = None
+        torch.cuda.empty_cache()
+        import bench_merge
+        result['merge'] = bench_merge.run_sharded_merge_bench(torch, dist, dev, n, rank)
     result['roofline'] = roof
     result['clocks'] = clocks
     result['kernels'] = kernels

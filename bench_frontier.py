@@ -50,7 +50,7 @@ def main():
            'kernels': {kname: {'ms_per_step': v[0] / 5, 'kernels_per_step': v[1] / 5} for kname, v in prof.items()},
            'roofline': {'bound': 'hbm', 'kernel': 'frontier', 'achieved': cells / (fr_ms * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
                         'frac': cells / (fr_ms * 1e-3) / 1e9 / hbm,
-                        'note': 'algorithmic bytes = H*W (the stencil kernels read the grid twice: count pass + write pass)'}}
+                        'note': 'algorithmic bytes = H*W: the count pass reads the grid once and keeps 16 frontier bits per thread; the write pass expands the bits (three launches: count, single-CTA scan, write)'}}
     # CPU baseline: the reference's Python loops (oracle restatement) on a 384^2 crop around a room
     from oracle import occgrid_oracle as O
     arr = g.grid

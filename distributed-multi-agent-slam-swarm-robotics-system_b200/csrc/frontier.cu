@@ -39,17 +39,20 @@ __device__ __forceinline__ unsigned int frontier_mask16(const int8_t* __restrict
         const unsigned int dn[4] = {(unsigned)dn4.x, (unsigned)dn4.y, (unsigned)dn4.z, (unsigned)dn4.w};
         const unsigned int left = x0 > 0 ? (unsigned int)(unsigned char)g[base - 1] : 0u;
         const unsigned int right = x0 + kFCells < w ? (unsigned int)(unsigned char)g[base + kFCells] : 0u;
+        // four cells per step on whole words: FREE == 0x00 and UNKNOWN == 0xff are byte-wise compares,
+        // the left / right neighbours are the word funnel-shifted by one byte
 #pragma unroll
-        for (int i = 0; i < kFCells; ++i) {
-            const unsigned int c = (cur[i >> 2] >> (8 * (i & 3))) & 0xffu;
-            const unsigned int u = (up[i >> 2] >> (8 * (i & 3))) & 0xffu;
-            const unsigned int d = (dn[i >> 2] >> (8 * (i & 3))) & 0xffu;
-            const unsigned int l = i == 0 ? left : (cur[(i - 1) >> 2] >> (8 * ((i - 1) & 3))) & 0xffu;
-            const unsigned int r = i == kFCells - 1 ? right : (cur[(i + 1) >> 2] >> (8 * ((i + 1) & 3))) & 0xffu;
-            const int x = x0 + i;
-            const bool interior = x >= 1 && x <= w - 2;                                              // :187-188
-            if (interior && c == 0u && (u == 0xffu || d == 0xffu || l == 0xffu || r == 0xffu)) mask |= 1u << i;   // :189-196
+        for (int i = 0; i < 4; ++i) {
+            const unsigned int c = cur[i];
+            const unsigned int l = (c << 8) | (i > 0 ? cur[i - 1] >> 24 : left);
+            const unsigned int r = (c >> 8) | ((i < 3 ? cur[i + 1] : right) << 24);
+            const unsigned int unk = __vcmpeq4(up[i], 0xffffffffu) | __vcmpeq4(dn[i], 0xffffffffu) |
+                                     __vcmpeq4(l, 0xffffffffu) | __vcmpeq4(r, 0xffffffffu);                       // :193-196
+            const unsigned int f = __vcmpeq4(c, 0u) & unk & 0x80808080u;                                          // :189
+            mask |= ((((f >> 7) * 0x00204081u) >> 21) & 0xfu) << (4 * i);
         }
+        if (x0 == 0) mask &= ~1u;                                                                                 // interior columns only (:187-188)
+        if (x0 + kFCells == w) mask &= ~(1u << (kFCells - 1));
         return mask;
     }
     int x = x0, y = y0;
@@ -86,13 +89,18 @@ __device__ __forceinline__ unsigned int block_scan_excl(unsigned int v, unsigned
     return r;
 }
 
+// The grid is read ONCE: the count pass keeps the 16 frontier bits of every thread's cells, the
+// write pass expands those bits into (x, y) tuples without touching the grid again.
 __global__ void __launch_bounds__(kFT)
-k_frontier_count(const int8_t* __restrict__ g, int w, int h, unsigned int* __restrict__ block_counts) {
+k_frontier_count(const int8_t* __restrict__ g, int w, int h, unsigned int* __restrict__ block_counts,
+                 unsigned short* __restrict__ masks) {
     __shared__ unsigned int s_warp[33];
     const long long n = (long long)w * h;
     const long long base = ((long long)blockIdx.x * kFT + threadIdx.x) * kFCells;
+    const unsigned int m = base < n ? frontier_mask16(g, w, h, base, n) : 0u;
+    masks[(size_t)blockIdx.x * kFT + threadIdx.x] = (unsigned short)m;
     unsigned int total;
-    block_scan_excl(base < n ? __popc(frontier_mask16(g, w, h, base, n)) : 0u, s_warp, &total);
+    block_scan_excl(__popc(m), s_warp, &total);
     if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
 }
 
@@ -121,13 +129,12 @@ k_frontier_reserve(unsigned int* __restrict__ block_counts, int n_blocks, long l
 }
 
 __global__ void __launch_bounds__(kFT)
-k_frontier_write(const int8_t* __restrict__ g, int w, int h, const unsigned int* __restrict__ block_offsets,
+k_frontier_write(const unsigned short* __restrict__ masks, int w, int h, const unsigned int* __restrict__ block_offsets,
                  const long long* __restrict__ d_count, int2* __restrict__ xy) {
     __shared__ unsigned int s_warp[33];
     if (*d_count == 0) return;
-    const long long n = (long long)w * h;
     const long long base = ((long long)blockIdx.x * kFT + threadIdx.x) * kFCells;
-    unsigned int m = base < n ? frontier_mask16(g, w, h, base, n) : 0u;
+    unsigned int m = masks[(size_t)blockIdx.x * kFT + threadIdx.x];
     unsigned int total;
     long long dst = block_offsets[blockIdx.x] + block_scan_excl(__popc(m), s_warp, &total);
     while (m) {
@@ -260,7 +267,8 @@ extern "C" {
 
 size_t occgrid_frontier_workspace_bytes(int64_t n_cells, int64_t max_frontiers) {
     const int64_t blocks = (n_cells + kFChunk - 1) / kFChunk;
-    return align_up((size_t)blocks * 4, 256) + align_up((size_t)max_frontiers * 4, 256) * 2 + align_up((size_t)max_frontiers * 8, 256) * 2 + 256;
+    return align_up((size_t)blocks * 4, 256) + align_up((size_t)blocks * kFT * 2, 256) +       // block counts | 16 frontier bits per thread
+           align_up((size_t)max_frontiers * 4, 256) * 2 + align_up((size_t)max_frontiers * 8, 256) * 2 + 256;
 }
 
 int occgrid_frontiers(const int8_t* d_grid, int32_t width, int32_t height, int32_t* d_xy, int64_t capacity,
@@ -275,9 +283,10 @@ int occgrid_frontiers(const int8_t* d_grid, int32_t width, int32_t height, int32
     const int blocks = (int)((n + kFChunk - 1) / kFChunk);
     unsigned int* block_counts = reinterpret_cast<unsigned int*>(d_ws);
     ProfileScope ps(K_FRONTIER, st, 3);
-    k_frontier_count<<<blocks, kFT, 0, st>>>(d_grid, width, height, block_counts);
+    unsigned short* masks = reinterpret_cast<unsigned short*>(reinterpret_cast<char*>(d_ws) + align_up((size_t)blocks * 4, 256));
+    k_frontier_count<<<blocks, kFT, 0, st>>>(d_grid, width, height, block_counts, masks);
     k_frontier_reserve<<<1, 1024, 0, st>>>(block_counts, blocks, capacity, (long long*)d_count, d_status);
-    k_frontier_write<<<blocks, kFT, 0, st>>>(d_grid, width, height, block_counts, (const long long*)d_count, reinterpret_cast<int2*>(d_xy));
+    k_frontier_write<<<blocks, kFT, 0, st>>>(masks, width, height, block_counts, (const long long*)d_count, reinterpret_cast<int2*>(d_xy));
     OCC_CUDA_TRY(cudaGetLastError());
     return OCCGRID_OK;
 }

@@ -57,42 +57,79 @@ k_icp_count(const double* __restrict__ tx, const double* __restrict__ ty, long l
 }
 
 // One CTA: start[c] = exclusive sum of cnt; cursor[c] = start[c] (consumed by the fill pass).
+// Exclusive scan of the per-cell counts in three launches (block sums -> scan of the block sums ->
+// rescan with the carry): every block of 16 384 cells runs on its own CTA, so the index of a
+// 640 k-cell map is built in tens of microseconds instead of one CTA looping for a millisecond.
+constexpr int kScanItemsIcp = 16;
+constexpr int kScanBlockIcp = 1024 * kScanItemsIcp;
+
+__device__ __forceinline__ unsigned int icp_block_scan(unsigned int sum, unsigned int* s_warp /* 33 */, unsigned int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned int wv = s_warp[lane], winc = wv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+        s_warp[lane] = winc - wv;
+        if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    const unsigned int ex = s_warp[warp] + inc - sum;
+    *total = s_warp[32];
+    __syncthreads();
+    return ex;
+}
+
 __global__ void __launch_bounds__(1024)
-k_icp_scan(const unsigned int* __restrict__ cnt, long long cells, unsigned int* __restrict__ start, unsigned int* __restrict__ cursor) {
-    constexpr int kItems = 16;
-    __shared__ unsigned int s_warp[32];
+k_icp_scan_sums(const unsigned int* __restrict__ cnt, long long cells, unsigned int* __restrict__ block_sums) {
+    __shared__ unsigned int s_warp[33];
+    const long long i0 = (long long)blockIdx.x * kScanBlockIcp + (long long)threadIdx.x * kScanItemsIcp;
+    unsigned int sum = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItemsIcp; ++j) sum += (i0 + j < cells) ? cnt[i0 + j] : 0u;
+    unsigned int total;
+    icp_block_scan(sum, s_warp, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024)
+k_icp_scan_top(unsigned int* __restrict__ block_sums, int n_blocks, unsigned int* __restrict__ start, long long cells) {
+    __shared__ unsigned int s_warp[33];
     __shared__ unsigned int s_carry;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (long long base = 0; base < cells; base += 1024 * kItems) {
-        const long long i0 = base + (long long)threadIdx.x * kItems;
-        unsigned int v[kItems], sum = 0;
-#pragma unroll
-        for (int j = 0; j < kItems; ++j) { v[j] = (i0 + j < cells) ? cnt[i0 + j] : 0u; sum += v[j]; }
-        unsigned int inc = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        if (lane == 31) s_warp[warp] = inc;
+    for (int base = 0; base < n_blocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned int v = i < n_blocks ? block_sums[i] : 0u;
+        unsigned int total;
+        const unsigned int ex = icp_block_scan(v, s_warp, &total);
+        if (i < n_blocks) block_sums[i] = s_carry + ex;
         __syncthreads();
-        if (warp == 0) {
-            unsigned int wv = s_warp[lane], winc = wv;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
-            s_warp[lane] = winc - wv;
-        }
-        __syncthreads();
-        unsigned int run = s_carry + s_warp[warp] + inc - sum;
-#pragma unroll
-        for (int j = 0; j < kItems; ++j) {
-            if (i0 + j < cells) { start[i0 + j] = run; cursor[i0 + j] = run; }
-            run += v[j];
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = run;
+        if (threadIdx.x == 0) s_carry += total;
         __syncthreads();
     }
     if (threadIdx.x == 0) start[cells] = s_carry;
+}
+
+__global__ void __launch_bounds__(1024)
+k_icp_scan_apply(const unsigned int* __restrict__ cnt, long long cells, const unsigned int* __restrict__ block_sums,
+                 unsigned int* __restrict__ start, unsigned int* __restrict__ cursor) {
+    __shared__ unsigned int s_warp[33];
+    const long long i0 = (long long)blockIdx.x * kScanBlockIcp + (long long)threadIdx.x * kScanItemsIcp;
+    unsigned int v[kScanItemsIcp], sum = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItemsIcp; ++j) { v[j] = (i0 + j < cells) ? cnt[i0 + j] : 0u; sum += v[j]; }
+    unsigned int total;
+    unsigned int run = block_sums[blockIdx.x] + icp_block_scan(sum, s_warp, &total);
+#pragma unroll
+    for (int j = 0; j < kScanItemsIcp; ++j) {
+        if (i0 + j < cells) { start[i0 + j] = run; cursor[i0 + j] = run; }
+        run += v[j];
+    }
 }
 
 __global__ void __launch_bounds__(kIT)
@@ -276,7 +313,7 @@ k_icp_apply(double* __restrict__ px, double* __restrict__ py, long long n, const
 }
 
 struct IcpLayout {
-    size_t cnt, start, cursor, sx, sy, sidx, px, py, corr, partial, partial2, state, total;
+    size_t cnt, start, cursor, sx, sy, sidx, px, py, corr, partial, partial2, state, block_sums, total;
 };
 
 static IcpLayout icp_layout(int64_t target_points, int64_t source_points, int64_t cells) {
@@ -288,6 +325,7 @@ static IcpLayout icp_layout(int64_t target_points, int64_t source_points, int64_
     L.sx = take((size_t)target_points * 8); L.sy = take((size_t)target_points * 8); L.sidx = take((size_t)target_points * 4);
     L.px = take((size_t)source_points * 8); L.py = take((size_t)source_points * 8); L.corr = take((size_t)source_points * 4);
     L.partial = take(blocks * 6 * 8); L.partial2 = take(blocks * 2 * 8); L.state = take(sizeof(IcpState));
+    L.block_sums = take((size_t)((cells + kScanBlockIcp - 1) / kScanBlockIcp + 1) * 4);
     L.total = o;
     return L;
 }
@@ -328,6 +366,7 @@ int mapmerge_icp_register(const double* d_sx, const double* d_sy, int64_t n_sour
     double* partial = reinterpret_cast<double*>(ws + L.partial);
     double* partial2 = reinterpret_cast<double*>(ws + L.partial2);
     IcpState* state = reinterpret_cast<IcpState*>(ws + L.state);
+    unsigned int* block_sums = reinterpret_cast<unsigned int*>(ws + L.block_sums);
     cudaStream_t st = (cudaStream_t)stream;
     long long gt = (n_target + kIT - 1) / kIT;
     if (gt > device_sm_count() * 16) gt = device_sm_count() * 16;
@@ -337,7 +376,10 @@ int mapmerge_icp_register(const double* d_sx, const double* d_sy, int64_t n_sour
     OCC_CUDA_TRY(cudaMemcpyAsync(px, d_sx, (size_t)n_source * 8, cudaMemcpyDeviceToDevice, st));
     OCC_CUDA_TRY(cudaMemcpyAsync(py, d_sy, (size_t)n_source * 8, cudaMemcpyDeviceToDevice, st));
     k_icp_count<<<(int)gt, kIT, 0, st>>>(d_tx, d_ty, n_target, min_x, min_y, cell, cells_w, cells_h, cnt);
-    k_icp_scan<<<1, 1024, 0, st>>>(cnt, cells, start, cursor);
+    const int scan_blocks = (int)((cells + kScanBlockIcp - 1) / kScanBlockIcp);
+    k_icp_scan_sums<<<scan_blocks, 1024, 0, st>>>(cnt, cells, block_sums);
+    k_icp_scan_top<<<1, 1024, 0, st>>>(block_sums, scan_blocks, start, cells);
+    k_icp_scan_apply<<<scan_blocks, 1024, 0, st>>>(cnt, cells, block_sums, start, cursor);
     k_icp_fill<<<(int)gt, kIT, 0, st>>>(d_tx, d_ty, n_target, min_x, min_y, cell, cells_w, cells_h, cursor, sx, sy, sidx);
     IcpIndex ix;
     ix.min_x = min_x; ix.min_y = min_y; ix.cell = cell; ix.w = cells_w; ix.h = cells_h;

@@ -536,6 +536,37 @@ def main():
         if not args.no_cpu:
             result['cpu_baseline'] = cpu_baseline(s0, 1, 500_000)     # ~10 s of the reference's Python loop on one core
             result['cpu_baseline_c_port'] = c_port_rate(s0)
+        # workload sensitivity: the same packets with every pose moved to a random place of the map (few
+        # packets per tile, nothing re-scanned): both strategies, a short run each
+        sens = {}
+        dsess = [st.disperse_poses(s, seed=7 + i) for i, s in enumerate(sessions[:2])]
+        dd = [grid.stage_packets(s['packets'])[0] for s in dsess]
+        for sname in ('tiled', 'global_atomic'):
+            gs_ = M.OccupancyGrid(strategy=sname, max_batch=npk, device=dev, **s0['grid'])
+
+            def sstep(i):
+                pk = dd[i % 2]
+                rc = lib.occgrid_integrate_packets(gs_._geom, pk.data_ptr(), pk.shape[0], 42, 42, None, None, off.data_ptr(),
+                                                   AGENTS_PER_GPU, gs_.grid_tensor.data_ptr(), gs_._ws.data_ptr(), gs_._ws.numel(),
+                                                   gs_._counters.data_ptr(), gs_._strategy, stream)
+                if rc != 0:
+                    raise RuntimeError(_native.last_error())
+            for i in range(3):
+                sstep(i)
+            torch.cuda.synchronize()
+            gs_._counters.zero_()
+            s0e, s1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0e.record()
+            for i in range(6):
+                sstep(i)
+            s1e.record()
+            torch.cuda.synchronize()
+            s_ms = s0e.elapsed_time(s1e)
+            sens[sname] = {'value': gs_.counters()['updates'] / (s_ms * 1e-3), 'unit': UNIT, 'ms_per_step': s_ms / 6}
+            del gs_
+        result['sensitivity'] = dict(sens, workload='dispersed poses: the configs[1] packets with every pose uniformly random over the '
+                                                      '4096^2 map (no tile or cell locality); the headline workload re-scans 32 rooms')
+        del dd
         if not args.no_merge:
             # second half of BASELINE.json's metric: merged grids/s on configs[2]
             del dpk, g2, host

@@ -13,7 +13,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_PATH = os.path.join(PKG_DIR, 'liboccgrid_b200.so')
-SOURCES = ['occgrid_integrate.cu', 'occgrid_tiled.cu', 'occgrid_route.cu', 'occgrid_band.cu', 'mapmerge.cu', 'frontier.cu', 'icp.cu', 'slam_chain.cpp']
+SOURCES = ['occgrid_integrate.cu', 'occgrid_tiled.cu', 'occgrid_route.cu', 'occgrid_band.cu', 'mapmerge.cu', 'frontier.cu', 'icp.cu', 'render.cu', 'slam_chain.cpp']
 HEADERS = ['common.cuh', 'beam_expand.cuh', 'sincos_dd.cuh', os.path.join('..', '..', 'include', 'occgrid_b200.h')]
 
 STRATEGY = {'auto': -1, 'global_atomic': 0, 'tiled': 1}
@@ -128,6 +128,9 @@ def lib():
     L.occgrid_frontier_clusters.restype = i32
     L.occgrid_frontier_clusters.argtypes = [vp, vp, i64, i32, i32, C.c_double, C.c_double, C.c_double, vp, vp, vp, vp, vp,
                                             vp, sz, vp]
+    L.occgrid_render_overlay.restype = i32
+    L.occgrid_render_overlay.argtypes = [vp, i32, i32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                         i32, i32, vp, vp, vp, vp]
     L.occgrid_set_raycast_ctas_per_sm.restype = i32
     L.occgrid_set_raycast_ctas_per_sm.argtypes = [i32]
     L.occgrid_profile_begin.restype = i32

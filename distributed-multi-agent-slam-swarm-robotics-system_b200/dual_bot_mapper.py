@@ -58,6 +58,10 @@ CELL_OCCUPIED = 100
 FRONTIER_MIN_CLUSTER = 3
 FRONTIER_SEPARATION = 1.0
 
+# -- dashboard colours (:346, :373) ---
+BG_COLOR = (22, 33, 62)
+CELL_COLOR_FREE = (30, 45, 70)
+
 # -- SLAM constants (:97-99) ---------------------------------------------------
 CLOSURE_RADIUS = 0.60
 MIN_POSES_BETWEEN = 30
@@ -539,6 +543,27 @@ class OccupancyGrid:
         cluster_frontiers -> [cluster_centroid_world(c) for c in clusters]."""
         f, n, k = self._cluster()
         return [(float(x), float(y)) for x, y in f['cent'][:k].cpu().numpy()]
+
+    # ---- overlay render (:492-527) — SURVEY §8 row f4 -----------------------------------------
+    def render_overlay(self, width=1000, height=800, scale=100.0, offset_x=None, offset_y=None,
+                       background=BG_COLOR, color=CELL_COLOR_FREE, to_host=True):
+        """Headless ``MapRenderer._draw_occupancy``: an RGB image uint8 [height, width, 3] of the
+        view the dashboard would show (``scale`` pixels per metre, ``offset_x/_y`` = screen position
+        of the world origin, defaults = the renderer's start view :395-397): ``background`` with
+        every visible cell that is neither UNKNOWN nor OCCUPIED painted ``color`` (:513-521)."""
+        if self.window != (0, 0, self.size, self.size):
+            raise OccGridError('render_overlay needs the whole grid (not a window of it)')
+        offset_x = width / 2 if offset_x is None else offset_x
+        offset_y = height / 2 if offset_y is None else offset_y
+        bg = (ctypes.c_uint8 * 3)(*[int(c) for c in background])
+        fg = (ctypes.c_uint8 * 3)(*[int(c) for c in color])
+        with torch.cuda.device(self.device):
+            out = torch.empty((int(height), int(width), 3), dtype=torch.uint8, device=self.device)
+            rc = self._lib.occgrid_render_overlay(self.grid_tensor.data_ptr(), self.size, self.size, self.ox, self.oy, self.res,
+                                                  float(scale), float(offset_x), float(offset_y), int(width), int(height),
+                                                  bg, fg, out.data_ptr(), self._stream())
+            _native.check(rc, 'occgrid_render_overlay')
+        return out.cpu().numpy() if to_host else out
 
     # ---- bookkeeping ---------------------------------------------------------------------
     def counters(self, reset=False):

@@ -211,6 +211,26 @@ def generate_session(n_agents=64, n_packets=2_500_000, grid_size=4096, resolutio
     }
 
 
+def disperse_poses(sess, seed=0):
+    """Workload-sensitivity variant of a session: the same packets (ranges, yaws, agents), but every
+    pose is moved to a uniformly random place of the WHOLE map, so that consecutive packets share
+    neither tiles nor cells (few packets per tile, no cell written twice) — the opposite of robots
+    re-scanning their rooms.  Returns a new session dict."""
+    rng = np.random.default_rng(seed)
+    g = sess['grid']
+    span = g['size'] * g['resolution']
+    rec = sess['packets'].copy().view(PACKET_DTYPE).reshape(-1)
+    n = rec.shape[0]
+    wx = rng.uniform(g['origin_x'] + 2.0, g['origin_x'] + span - 2.0, n)
+    wy = rng.uniform(g['origin_y'] + 2.0, g['origin_y'] + span - 2.0, n)
+    off = sess['agent_offsets'][sess['agent_idx']]
+    rec['x'] = np.round(wx - off[:, 0], 4).astype(np.float32)
+    rec['y'] = np.round(wy - off[:, 1], 4).astype(np.float32)
+    out = dict(sess)
+    out['packets'] = rec.view(np.uint8).reshape(-1, 42)
+    return out
+
+
 def beam_cell_updates(sess, packets=None):
     """Closed-form count of beam-cell updates of a session (SURVEY §8d unit) is produced by the
     device counters; this helper only reports the packet/beam totals."""

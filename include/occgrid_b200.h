@@ -267,6 +267,17 @@ int occgrid_band_publish(int n_bands, int rank, uint32_t* d_resv, int64_t seg_ca
                          const uint32_t* d_my_flags, uint32_t epoch, int wait /* 0: publish only */,
                          int32_t* d_status, void* stream);
 
+/* Occupancy overlay of the reference's dashboard as a headless RGB image:
+ * MapRenderer._draw_occupancy (dual_bot_mapper.py:492-527) with world_to_screen (:404-408): the
+ * `width` x `height` image (uint8 [height][width][3], device) is filled with `bg_rgb` and every
+ * visible cell of the WHOLE grid `d_grid` (size_y x size_x) that is neither UNKNOWN nor OCCUPIED is
+ * painted `fg_rgb` (CELL_COLOR_FREE) as a cell_px = max(1, int(res * scale)) square centred on its
+ * screen position (a single pixel when cell_px == 2; nothing when cell_px < 2).  `scale` = pixels
+ * per metre, `offset_x/_y` = screen position of the world origin (y flipped). */
+int occgrid_render_overlay(const int8_t* d_grid, int32_t size_x, int32_t size_y, double ox, double oy, double res,
+                           double scale, double offset_x, double offset_y, int32_t width, int32_t height,
+                           const uint8_t* bg_rgb_host, const uint8_t* fg_rgb_host, uint8_t* d_rgb, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  *  Map fusion — server_nodes/map_merger.py:35-127
  *

@@ -409,3 +409,26 @@ def test_ingest_batcher_v1_datagrams(M):
     b.flush()
     assert np.array_equal(g.grid, og.grid)
     assert b.slam.closures == [tuple(c) for c in os_.closures]
+
+
+def test_pageable_batches_back_to_back_do_not_share_the_staging_buffer():
+    """update_packets on pageable host input goes through ONE reusable pinned staging buffer and an
+    asynchronous H2D copy; the next call must not overwrite the buffer while that copy is still
+    queued behind earlier kernels (it would integrate the later batch twice)."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from occgrid_b200 import dual_bot_mapper as M, simulation_tools as st
+    from oracle import c_oracle
+    s = st.generate_session(n_agents=8, n_packets=300_000, grid_size=1024, origin=(-25.6, -25.6), seed=11)
+    g = M.OccupancyGrid(max_batch=300_000, **s['grid'])
+    big = g.stage_packets(s['packets'])[0]
+    want = np.full((1024, 1024), -1, np.int8)
+    a, b = np.ascontiguousarray(s['packets'][:1500]), np.ascontiguousarray(s['packets'][150_000:151_500])
+    for _ in range(6):                                   # keep the stream busy so the small copies queue up behind kernels
+        g._integrate_device(big, None, 0.0, None, s['agent_offsets'], None, 42)
+        c_oracle.integrate_packets(s['packets'], want, -25.6, -25.6, 0.05, agent_offsets=s['agent_offsets'])
+    g.update_packets(a, agent_offsets=s['agent_offsets'])            # pageable numpy -> staging buffer
+    g.update_packets(b, agent_offsets=s['agent_offsets'])            # reuses the same staging buffer right away
+    c_oracle.integrate_packets(a, want, -25.6, -25.6, 0.05, agent_offsets=s['agent_offsets'])
+    c_oracle.integrate_packets(b, want, -25.6, -25.6, 0.05, agent_offsets=s['agent_offsets'])
+    assert np.array_equal(g.grid, want)

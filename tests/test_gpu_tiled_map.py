@@ -168,3 +168,44 @@ def test_fused_band_step_reports_segment_overflow():
     s.step(pk, idx, None, tab, wait=False)
     with pytest.raises(OccGridError, match='overflow'):
         s.check_status()
+
+
+@pytest.mark.parametrize('name', ['mixed_a', 'mixed_b_sep', 'mixed_c_4096', 'mixed_d_edge'])
+def test_fused_band_step_on_adversarial_streams(name):
+    """The router of the fused band step has its own decode (aligned word loads + funnel shifts from
+    shared memory) and screened robot-cell evaluation: the reference-generated adversarial streams
+    (bad magic, foreign agents, NaN/inf/sentinel ranges, SLAM drift, poses on cell boundaries) must
+    give the reference's grid through it, on one band and split over two."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    import hashlib
+    import json
+    import os
+    from conftest import GOLD, load_packet_stream, normalise_datagrams
+    from occgrid_b200.distributed import BandBuffers, BandLayout, BandStep
+    want = json.load(open(os.path.join(GOLD, 'golden.json')))['packet_streams'][name]
+    pk, ref_drift = load_packet_stream(name)
+    arr, drift = normalise_datagrams(pk, ref_drift if want['slam'] else None)
+    kw = want['grid_kwargs']
+    size, res = kw.get('size', 200), kw.get('resolution', 0.05)
+    ox, oy = kw.get('origin_x', -5.0), kw.get('origin_y', -5.0)
+    tab = torch.tensor([[0.0, 0.0], [0.0, 0.0], [float(want['separation']), 0.0]], dtype=torch.float64, device='cuda')
+    import math
+    for world in (1, 2):
+        if world > 1 and size // world < 2 * (math.ceil(1.2 / res) + 2) + 1:
+            continue                                             # bands thinner than two reaches are rejected by the library
+        layout = BandLayout(size, world)
+        steps = [BandStep(layout, r, size, res, ox, oy, 'cuda', arr.shape[0]) for r in range(world)]
+        BandBuffers.link([s.buf for s in steps])
+        for s in steps:
+            s.finish_init()
+        n = arr.shape[0]
+        for r in range(world):                                   # rank r ingests the r-th part of the stream, in order
+            sl = slice(r * n // world, (r + 1) * n // world)
+            steps[r].step(torch.from_numpy(arr[sl].copy()).cuda(), None,
+                          torch.from_numpy(drift[sl].copy()).cuda() if drift is not None else None, tab, wait=False)
+        for s in steps:
+            s.step(None, None, None, None)
+            s.check_status()
+        got = np.concatenate([s.grid.grid for s in steps], axis=0)
+        assert hashlib.sha1(got.tobytes()).hexdigest() == want['sha1'], (name, world)

@@ -68,8 +68,8 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // addresses [s * seg_cap, s * seg_cap + count[s]).  count[] lives on the device (written by the
 // sources before the cross-GPU barrier) — the host never reads it.
 constexpr int kSegChunk = 2048;              // seg_cap is a multiple of this: a chunk never straddles two segments
-constexpr int kRouteItemPk = 256;            // packets per route sub-batch of the fused kernel (one per thread)
-constexpr int kRouteSubsPerItem = 4;         // sub-batches per route work item (software-pipelined loads)
+constexpr int kRouteItemPk = 512;            // packets per route sub-batch of the fused kernel (two per thread)
+constexpr int kRouteSubsPerItem = 2;         // sub-batches per route work item
 constexpr int kMaxBands = 32;
 
 struct SegInfo {

@@ -25,6 +25,8 @@
 //
 // Windows of neighbouring tiles overlap; the global atomicMax merges them, and chunks of one
 // tile likewise, so the result is independent of how work was cut.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace occ {
@@ -707,109 +709,143 @@ __device__ __forceinline__ bool robot_cell(double r, double o, double res, doubl
 struct RouteStats { unsigned int a, b; };
 
 constexpr int kRouteSubs = kRouteSubsPerItem;
+constexpr int kRoutePerThread = kRouteItemPk / kTT;      // packets per thread and sub-batch
+static_assert(kRouteItemPk % kTT == 0 && kRoutePerThread >= 1 && kRoutePerThread <= 4, "route sub-batch = 1..4 packets per thread");
 
-__device__ __forceinline__ void route_load_sub(const RouteJob& J, long long first, int count, uint4 (&pre)[3]) {
-    const size_t bytes = (size_t)count * J.stride;
-    const uint4* src = reinterpret_cast<const uint4*>(J.pkts + (size_t)first * J.stride);
+// One decoded packet on its way to (at most) two band owners.
+struct RoutePk {
+    double rx, ry;
+    float yaw, d[4];
+    int band0, nb, tile0, tile1;        // bands are contiguous rows: the second band is band0 + 1
+    unsigned int rank0, rank1;
+};
+
+__device__ __forceinline__ void route_decode(const RouteJob& J, const unsigned int* s_buf, int slot, long long k, RoutePk& P,
+                                             RouteStats& st_acc) {
+    P.band0 = -1; P.nb = 0; P.tile0 = P.tile1 = -1; P.rank0 = P.rank1 = 0u;
+    const int st = decode_packet_smem(s_buf, (unsigned int)slot * (unsigned int)J.stride, k, J.agent_idx, J.drift, J.agent_off,
+                                      J.n_agents, &P.rx, &P.ry, &P.yaw, P.d);
+    st_acc.a += 1u + (st == PKT_OK ? 0x10000u : 0u);
+    st_acc.b += st == PKT_DROPPED ? 1u : 0u;
+    if (st != PKT_OK) return;
+    unsigned int hits = 0;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {                   // <= 256 * 42 B = 672 chunks of 16 bytes: three per thread
-        const size_t i = (size_t)j * kTT + threadIdx.x;
-        pre[j] = (i * 16 + 16 <= bytes) ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u);
+    for (int s2 = 0; s2 < 4; ++s2) {
+        const double dd = (double)P.d[s2];
+        hits += (OCC_MIN_DIST_M < dd && dd <= OCC_MAX_DIST_M) ? 1u : 0u;                 // :888
+    }
+    st_acc.b += hits << 16;
+    int gx, gy;
+    if (!(robot_cell(P.rx, J.ox, J.res, J.inv_res, &gx) && robot_cell(P.ry, J.oy, J.res, J.inv_res, &gy))) return;
+    const int reach = J.reach;
+    if (gx < -reach || gx >= J.size_x + reach) return;
+    const int tcol = (gx + J.pad) >> kTileShift;
+    for (int b = 0; b < J.n_bands; ++b) {
+        if (gy - reach < J.band_y0[b + 1]) {                                 // first band whose rows end above the reach interval
+            const int py = gy - J.band_y0[b];
+            if (py >= -reach) {
+                P.band0 = b; P.nb = 1;
+                P.tile0 = ((py + J.pad) >> kTileShift) * J.tiles_x + tcol;
+                if (b + 1 < J.n_bands && gy + reach >= J.band_y0[b + 1]) {
+                    P.nb = 2;
+                    P.tile1 = ((gy - J.band_y0[b + 1] + J.pad) >> kTileShift) * J.tiles_x + tcol;
+                }
+            }
+            break;
+        }
     }
 }
 
-__device__ __noinline__ RouteStats route_item(const RouteJob& J, unsigned int item, unsigned int* s_buf /* >= 24.6 KB */,
+// rank of every entry inside its band's run (arrival order is free: ordinals travel in the records)
+__device__ __forceinline__ void route_rank(RouteSmem& S, RoutePk& P, int lane, unsigned int lt) {
+    const unsigned int p0 = __match_any_sync(0xffffffffu, P.band0);
+    if (P.band0 >= 0) {
+        const int leader = __ffs(p0) - 1;
+        unsigned int b0 = 0;
+        if (lane == leader) b0 = atomicAdd(&S.cnt[P.band0], (unsigned int)__popc(p0));
+        P.rank0 = __shfl_sync(p0, b0, leader) + __popc(p0 & lt);
+    }
+    if (__any_sync(0xffffffffu, P.nb == 2)) {                            // rare: only next to a band edge
+        const unsigned int p1 = __match_any_sync(0xffffffffu, P.nb == 2 ? P.band0 + 1 : -1);
+        if (P.nb == 2) {
+            const int leader = __ffs(p1) - 1;
+            unsigned int b1 = 0;
+            if (lane == leader) b1 = atomicAdd(&S.cnt[P.band0 + 1], (unsigned int)__popc(p1));
+            P.rank1 = __shfl_sync(p1, b1, leader) + __popc(p1 & lt);
+        }
+    }
+}
+
+__device__ __forceinline__ void route_store(const RouteJob& J, uint4* s16, const RoutePk& P, unsigned int my_off, long long k) {
+    const unsigned int o0 = __shfl_sync(0xffffffffu, my_off, P.band0 < 0 ? 0 : P.band0);
+    const unsigned long long ux = (unsigned long long)__double_as_longlong(P.rx), uy = (unsigned long long)__double_as_longlong(P.ry);
+    const uint4 w0 = make_uint4((unsigned int)ux, (unsigned int)(ux >> 32), (unsigned int)uy, (unsigned int)(uy >> 32));
+    const uint4 w1 = make_uint4(__float_as_uint(P.yaw), __float_as_uint(P.d[0]), __float_as_uint(P.d[1]), __float_as_uint(P.d[2]));
+    const unsigned int ord = J.ordinal_base + (unsigned int)k;
+    if (P.band0 >= 0) {                                                  // struct occgrid_pose_rec, 3 x 16 bytes
+        uint4* dst = s16 + (size_t)(o0 + P.rank0) * 3;
+        dst[0] = w0; dst[1] = w1; dst[2] = make_uint4(__float_as_uint(P.d[3]), ord, (unsigned int)P.tile0, 0u);
+    }
+    if (__any_sync(0xffffffffu, P.nb == 2)) {
+        const unsigned int o1 = __shfl_sync(0xffffffffu, my_off, P.nb == 2 ? P.band0 + 1 : 0);
+        if (P.nb == 2) {
+            uint4* dst = s16 + (size_t)(o1 + P.rank1) * 3;
+            dst[0] = w0; dst[1] = w1; dst[2] = make_uint4(__float_as_uint(P.d[3]), ord, (unsigned int)P.tile1, 0u);
+        }
+    }
+}
+
+__device__ __noinline__ RouteStats route_item(const RouteJob& J, unsigned int item, unsigned int* s_buf /* >= kRouteItemPk * 96 B */,
                                               RouteSmem& S, RouteStats st_in) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int lt = (1u << lane) - 1u;
-    // fast staging needs a 16-byte aligned sub-batch (stride 42: 256 * 42 = 10752 = 672 * 16) and <= 48-byte records
-    const bool vec = (reinterpret_cast<uintptr_t>(J.pkts) & 15) == 0 && ((kRouteItemPk * J.stride) & 15) == 0 && J.stride <= 48;
-    uint4 pre[3];
     long long first = (long long)item * (kRouteItemPk * kRouteSubs);
-    int count = (int)max(0ll, min((long long)kRouteItemPk, J.n - first));
-    if (vec) route_load_sub(J, first, count, pre);
-    for (int sub = 0; sub < kRouteSubs && count > 0; ++sub) {
+    for (int sub = 0; sub < kRouteSubs; ++sub, first += kRouteItemPk) {
+        const int count = (int)max(0ll, min((long long)kRouteItemPk, J.n - first));
+        if (count == 0) break;                                           // uniform across the CTA
         __syncthreads();                                                 // the previous sub-batch's copy-out has left the buffer
         if (threadIdx.x < kMaxBands) S.cnt[threadIdx.x] = 0u;
-        if (vec) {
-            uint4* d4 = reinterpret_cast<uint4*>(s_buf);
+        {   // staging with every load of the thread in flight before the first store (a load-store loop
+            // would pay one DRAM latency per iteration)
+            const uint8_t* src = J.pkts + (size_t)first * J.stride;
             const size_t bytes = (size_t)count * J.stride;
+            constexpr int kVec = kRouteItemPk * kMaxStrideT / 16 / kTT;         // <= 8 chunks of 16 bytes per thread
+            if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+                const uint4* s4 = reinterpret_cast<const uint4*>(src);
+                uint4* d4 = reinterpret_cast<uint4*>(s_buf);
+                const size_t nvec = bytes / 16;
+                uint4 v[kVec];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const size_t i = (size_t)j * kTT + threadIdx.x;
-                if (i * 16 + 16 <= bytes) d4[i] = pre[j];
+                for (int j = 0; j < kVec; ++j) {
+                    const size_t i = (size_t)j * kTT + threadIdx.x;
+                    if (i < nvec) v[j] = __ldg(s4 + i);
+                }
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) {
+                    const size_t i = (size_t)j * kTT + threadIdx.x;
+                    if (i < nvec) d4[i] = v[j];
+                }
+                for (size_t i = nvec * 16 + threadIdx.x; i < bytes; i += kTT) reinterpret_cast<uint8_t*>(s_buf)[i] = __ldg(src + i);
+            } else {
+                stage_records_t(src, bytes, reinterpret_cast<uint8_t*>(s_buf));
             }
-            for (size_t i = (bytes / 16) * 16 + threadIdx.x; i < bytes; i += kTT)
-                reinterpret_cast<uint8_t*>(s_buf)[i] = __ldg(J.pkts + (size_t)first * J.stride + i);
-        } else {
-            stage_records_t(J.pkts + (size_t)first * J.stride, (size_t)count * J.stride, reinterpret_cast<uint8_t*>(s_buf));
+        }
+        {   // pull the NEXT sub-batch towards L2 while this one is decoded, sorted and copied out
+            const long long nf = first + kRouteItemPk;
+            const long long nbytes = max(0ll, min((long long)kRouteItemPk, J.n - nf)) * J.stride;
+            const long long o = (long long)threadIdx.x * 128;
+            if (sub + 1 < kRouteSubs && o < nbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(J.pkts + (size_t)nf * J.stride + o));
         }
         __syncthreads();
-        // the NEXT sub-batch's loads are in flight while this one is decoded, sorted and copied out
-        const long long next_first = first + kRouteItemPk;
-        const int next_count = sub + 1 < kRouteSubs ? (int)max(0ll, min((long long)kRouteItemPk, J.n - next_first)) : 0;
-        if (vec && next_count > 0) route_load_sub(J, next_first, next_count, pre);
-
-        double rx = 0.0, ry = 0.0;
-        float yaw = 0.f, dist[4] = {0.f, 0.f, 0.f, 0.f};
-        int band0 = -1, nb = 0, tile0 = -1, tile1 = -1;      // bands are contiguous rows: the second band is band0 + 1
-        const long long k = first + threadIdx.x;
-        if ((int)threadIdx.x < count) {
-            const int st = decode_packet_smem(s_buf, threadIdx.x * (unsigned int)J.stride, k, J.agent_idx, J.drift, J.agent_off,
-                                              J.n_agents, &rx, &ry, &yaw, dist);
-            st_in.a += 1u + (st == PKT_OK ? 0x10000u : 0u);
-            st_in.b += st == PKT_DROPPED ? 1u : 0u;
-            if (st == PKT_OK) {
-                unsigned int hits = 0;
+        RoutePk P[kRoutePerThread];
 #pragma unroll
-                for (int s2 = 0; s2 < 4; ++s2) {
-                    const double dd = (double)dist[s2];
-                    hits += (OCC_MIN_DIST_M < dd && dd <= OCC_MAX_DIST_M) ? 1u : 0u;             // :888
-                }
-                st_in.b += hits << 16;
-                int gx, gy;
-                if (robot_cell(rx, J.ox, J.res, J.inv_res, &gx) && robot_cell(ry, J.oy, J.res, J.inv_res, &gy)) {
-                    const int reach = J.reach;
-                    if (gx >= -reach && gx < J.size_x + reach) {
-                        const int tcol = (gx + J.pad) >> kTileShift;
-                        for (int b = 0; b < J.n_bands; ++b) {
-                            if (gy - reach < J.band_y0[b + 1]) {             // first band whose rows end above the reach interval
-                                const int py = gy - J.band_y0[b];
-                                if (py >= -reach) {
-                                    band0 = b; nb = 1;
-                                    tile0 = ((py + J.pad) >> kTileShift) * J.tiles_x + tcol;
-                                    if (b + 1 < J.n_bands && gy + reach >= J.band_y0[b + 1]) {
-                                        nb = 2;
-                                        tile1 = ((gy - J.band_y0[b + 1] + J.pad) >> kTileShift) * J.tiles_x + tcol;
-                                    }
-                                }
-                                break;
-                            }
-                        }
-                    }
-                }
-            }
+        for (int u = 0; u < kRoutePerThread; ++u) {                      // decode first (the table loads of all packets overlap) ...
+            const int slot = u * kTT + threadIdx.x;
+            P[u].band0 = -1; P[u].nb = 0;
+            if (slot < count) route_decode(J, s_buf, slot, first + slot, P[u], st_in);
         }
-        // rank of every entry inside its band's run (arrival order is free: ordinals travel in the records)
-        unsigned int rank0 = 0u, rank1 = 0u;
-        {
-            const unsigned int p0 = __match_any_sync(0xffffffffu, band0);
-            if (band0 >= 0) {
-                const int leader = __ffs(p0) - 1;
-                unsigned int b0 = 0;
-                if (lane == leader) b0 = atomicAdd(&S.cnt[band0], (unsigned int)__popc(p0));
-                rank0 = __shfl_sync(p0, b0, leader) + __popc(p0 & lt);
-            }
-            if (__any_sync(0xffffffffu, nb == 2)) {                      // rare: only next to a band edge
-                const unsigned int p1 = __match_any_sync(0xffffffffu, nb == 2 ? band0 + 1 : -1);
-                if (nb == 2) {
-                    const int leader = __ffs(p1) - 1;
-                    unsigned int b1 = 0;
-                    if (lane == leader) b1 = atomicAdd(&S.cnt[band0 + 1], (unsigned int)__popc(p1));
-                    rank1 = __shfl_sync(p1, b1, leader) + __popc(p1 & lt);
-                }
-            }
-        }
+#pragma unroll
+        for (int u = 0; u < kRoutePerThread; ++u) route_rank(S, P[u], lane, lt);   // ... then the warp-level ranking
         __syncthreads();                                                 // counts complete; raw packets decoded: the buffer is free
         // every warp scans the <= 32 band counts in registers (lane b holds band b)
         const unsigned int n_b = lane < J.n_bands ? S.cnt[lane] : 0u;
@@ -827,44 +863,25 @@ __device__ __noinline__ RouteStats route_item(const RouteJob& J, unsigned int it
             S.off[lane] = my_off;
             if (lane == 31) S.off[32] = inc;
         }
-        const unsigned int o0 = __shfl_sync(0xffffffffu, my_off, band0 < 0 ? 0 : band0);
         uint4* s16 = reinterpret_cast<uint4*>(s_buf);
-        if (band0 >= 0) {                                                // struct occgrid_pose_rec, 3 x 16 bytes
-            const unsigned long long ux = (unsigned long long)__double_as_longlong(rx), uy = (unsigned long long)__double_as_longlong(ry);
-            const uint4 w0 = make_uint4((unsigned int)ux, (unsigned int)(ux >> 32), (unsigned int)uy, (unsigned int)(uy >> 32));
-            const uint4 w1 = make_uint4(__float_as_uint(yaw), __float_as_uint(dist[0]), __float_as_uint(dist[1]), __float_as_uint(dist[2]));
-            const unsigned int ord = J.ordinal_base + (unsigned int)k;
-            uint4* dst = s16 + (size_t)(o0 + rank0) * 3;
-            dst[0] = w0; dst[1] = w1; dst[2] = make_uint4(__float_as_uint(dist[3]), ord, (unsigned int)tile0, 0u);
-        }
-        if (__any_sync(0xffffffffu, nb == 2)) {
-            const unsigned int o1 = __shfl_sync(0xffffffffu, my_off, nb == 2 ? band0 + 1 : 0);
-            if (nb == 2) {
-                const unsigned long long ux = (unsigned long long)__double_as_longlong(rx), uy = (unsigned long long)__double_as_longlong(ry);
-                uint4* dst = s16 + (size_t)(o1 + rank1) * 3;
-                dst[0] = make_uint4((unsigned int)ux, (unsigned int)(ux >> 32), (unsigned int)uy, (unsigned int)(uy >> 32));
-                dst[1] = make_uint4(__float_as_uint(yaw), __float_as_uint(dist[0]), __float_as_uint(dist[1]), __float_as_uint(dist[2]));
-                dst[2] = make_uint4(__float_as_uint(dist[3]), J.ordinal_base + (unsigned int)k, (unsigned int)tile1, 0u);
-            }
-        }
+#pragma unroll
+        for (int u = 0; u < kRoutePerThread; ++u) route_store(J, s16, P[u], my_off, first + u * kTT + threadIdx.x);
         __syncthreads();
-        // copy-out: warp w takes bands w, w + 8, ...: one contiguous run each, consecutive lanes ->
-        // consecutive 16-byte chunks in the owner's segment
-        for (int b = warp; b < J.n_bands; b += kTT / 32) {
+        // copy-out: one contiguous run per band, all threads on it: consecutive threads -> consecutive
+        // 16-byte chunks in the owner's segment (full NVLink / HBM write transactions)
+        for (int b = 0; b < J.n_bands; ++b) {
             const unsigned int base = S.base[b];
-            const unsigned int n16 = (S.off[b + 1] - S.off[b]) * 3u;
-            if (n16 == 0u || base == 0xffffffffu) continue;
+            const unsigned int n_rec = S.off[b + 1] - S.off[b];
+            if (n_rec == 0u || base == 0xffffffffu) continue;                // uniform across the CTA
             const size_t slot0 = (size_t)J.src_rank * J.seg_cap + base;
             uint4* out = reinterpret_cast<uint4*>(J.peer_recs[b] + slot0);
             const uint4* in = s16 + (size_t)S.off[b] * 3;
-            for (unsigned int q = lane; q < n16; q += 32) out[q] = in[q];
+            for (unsigned int q = threadIdx.x; q < n_rec * 3u; q += kTT) out[q] = in[q];
             // compact copy of the tile ids (word 10 of every record): the owner bins from 4 bytes per record
             int* tout = J.peer_tiles[b] + slot0;
             const unsigned int* tin = s_buf + (size_t)S.off[b] * 12 + 10;
-            for (unsigned int q = lane; q < n16 / 3u; q += 32) tout[q] = (int)tin[(size_t)q * 12];
+            for (unsigned int q = threadIdx.x; q < n_rec; q += kTT) tout[q] = (int)tin[(size_t)q * 12];
         }
-        first = next_first;
-        count = next_count;
     }
     return st_in;
 }
@@ -1113,7 +1130,7 @@ static TiledPtrs tiled_ptrs(const TiledLayout& L, void* d_ws) {
 // buffer (raw packets, then <= 2 records per packet) when that is larger.
 static size_t raycast_smem(const TileGeom& tg, bool route) {
     size_t b = (size_t)tg.win_side * tg.pitch * 4;
-    const size_t r = (size_t)kRouteItemPk * 2 * sizeof(PoseRec);
+    const size_t r = (size_t)kRouteItemPk * 2 * sizeof(PoseRec);   // every packet may go to two bands
     const size_t raw = (size_t)kRouteItemPk * kMaxStrideT;
     if (route) b = b > r ? b : r;
     if (route) b = b > raw ? b : raw;
@@ -1239,7 +1256,9 @@ int tiled_raycast_route(const occgrid_geom* geom, const PoseRec* d_recs, int hav
         // nothing prepared (first step of a stream): the header still has to carry a clean queue
         OCC_CUDA_TRY(cudaMemsetAsync(P.hdr, 0, sizeof(TilePlanHeader), st));
     }
+    static const bool force_route_variant = getenv("OCC_ROUTE_VARIANT_ALWAYS") != nullptr;      // diagnostic: template overhead alone
     if (job) launch_raycast<false, true>(g, tg, P, d_recs, 1, P.stamps, d_counters, have_items, *job, st);
+    else if (force_route_variant) { RouteJob none = {}; launch_raycast<false, true>(g, tg, P, d_recs, 1, P.stamps, d_counters, have_items, none, st); }
     else {
         RouteJob none = {};
         launch_raycast<false, false>(g, tg, P, d_recs, 1, P.stamps, d_counters, have_items, none, st);

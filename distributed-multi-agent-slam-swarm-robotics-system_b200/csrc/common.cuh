@@ -68,8 +68,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // addresses [s * seg_cap, s * seg_cap + count[s]).  count[] lives on the device (written by the
 // sources before the cross-GPU barrier) — the host never reads it.
 constexpr int kSegChunk = 2048;              // seg_cap is a multiple of this: a chunk never straddles two segments
-constexpr int kRouteItemPk = 512;            // packets per route sub-batch of the fused kernel (two per thread)
-constexpr int kRouteSubsPerItem = 2;         // sub-batches per route work item
+constexpr int kRouteChunkPk = 32;            // packets per route chunk of the fused kernel (one per lane of a route warp)
 constexpr int kMaxBands = 32;
 
 struct SegInfo {
@@ -91,16 +90,15 @@ struct RouteJob {
     int n_bands, src_rank;
     int band_y0[kMaxBands + 1];
     PoseRec* const* peer_recs;               // device array [n_bands]: band owner's receive slot (its segment 0)
-    int* const* peer_tiles;                  // device array [n_bands]: the slot's compact tile ids (same addressing)
     unsigned int seg_cap;
     unsigned int* resv;                      // LOCAL reservation counters [n_bands]; zero when the batch starts
     int* status;                             // bit 1: a segment overflowed
     uint64_t* counters;                      // optional: packets / accepted / dropped / bad_pose of the routed share
-    unsigned int n_route_items;              // work items of kRouteItemPk * kRouteSubs packets
+    unsigned int n_route_items;              // chunks of kRouteChunkPk packets
 };
 
 size_t tiled_band_workspace_bytes(const occgrid_geom* geom, int n_segs, int64_t seg_cap);
-int tiled_prepare_poses(const occgrid_geom* geom, const PoseRec* d_recs, const int* d_tiles, const SegInfo& seg, int tiles_in_records,
+int tiled_prepare_poses(const occgrid_geom* geom, const PoseRec* d_recs, const SegInfo& seg, int tiles_in_records,
                         void* d_ws, size_t ws_bytes, uint64_t* d_counters, cudaStream_t st);
 int tiled_raycast_route(const occgrid_geom* geom, const PoseRec* d_recs, int have_items, const RouteJob* job,
                         int8_t* d_grid, void* d_ws, size_t ws_bytes, int64_t max_records, uint64_t* d_counters, cudaStream_t st);

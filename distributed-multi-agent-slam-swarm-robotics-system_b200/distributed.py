@@ -134,26 +134,20 @@ class BandBuffers:
             import torch.distributed._symmetric_memory as symm
             pg = group if group is not None else dist.group.WORLD
             self.recv = symm.empty(rec_shape, dtype=torch.uint8, device=device)
-            self.tiles = symm.empty(rec_shape[:3], dtype=torch.int32, device=device)
             self.ctl = symm.empty((self.CTL_WORDS,), dtype=torch.int32, device=device)
             self.ctl.zero_()
             torch.cuda.synchronize(device)
-            h_recv, h_ctl, h_tiles = symm.rendezvous(self.recv, pg), symm.rendezvous(self.ctl, pg), symm.rendezvous(self.tiles, pg)
-            self._handles = (h_recv, h_ctl, h_tiles)
+            h_recv, h_ctl = symm.rendezvous(self.recv, pg), symm.rendezvous(self.ctl, pg)
+            self._handles = (h_recv, h_ctl)
             self.recv_bases = [int(p) for p in h_recv.buffer_ptrs]
-            self.tile_bases = [int(p) for p in h_tiles.buffer_ptrs]
             self.ctl_bases = [int(p) for p in h_ctl.buffer_ptrs]
         else:
             self.recv = torch.empty(rec_shape, dtype=torch.uint8, device=device)
-            self.tiles = torch.empty(rec_shape[:3], dtype=torch.int32, device=device)
             self.ctl = torch.zeros((self.CTL_WORDS,), dtype=torch.int32, device=device)
-            self.recv_bases = self.ctl_bases = self.tile_bases = None         # filled by link()
+            self.recv_bases = self.ctl_bases = None         # filled by link()
 
     def slot_ptr(self, slot):
         return self.recv.data_ptr() + slot * self.world * self.seg_cap * 48
-
-    def tiles_ptr(self, slot):
-        return self.tiles.data_ptr() + slot * self.world * self.seg_cap * 4
 
     def seg_counts_ptr(self, slot):
         return self.ctl.data_ptr() + slot * 256
@@ -167,7 +161,6 @@ class BandBuffers:
         for b in buffers:
             b.recv_bases = [o.recv.data_ptr() for o in buffers]
             b.ctl_bases = [o.ctl.data_ptr() for o in buffers]
-            b.tile_bases = [o.tiles.data_ptr() for o in buffers]
 
     def pointer_tables(self):
         """Device arrays of peer pointers: per slot the owners' slot bases and seg_counts, plus flags."""
@@ -175,7 +168,6 @@ class BandBuffers:
         slot_bytes = self.world * self.seg_cap * 48
         t = lambda v: torch.tensor(v, dtype=torch.int64, device=dev)
         self.peer_recs = [t([p + s * slot_bytes for p in self.recv_bases]) for s in range(self.SLOTS)]
-        self.peer_tiles = [t([p + s * (slot_bytes // 12) for p in self.tile_bases]) for s in range(self.SLOTS)]
         self.peer_seg_counts = [t([p + s * 256 for p in self.ctl_bases]) for s in range(self.SLOTS)]
         self.peer_flags = t([p + self.SLOTS * 256 for p in self.ctl_bases])
 
@@ -191,9 +183,12 @@ class BandStep:
         self.device = torch.device(device)
         self._lib = _native.lib()
         self.size, self.res, self.ox, self.oy = int(size), float(resolution), float(origin_x), float(origin_y)
-        self.seg_cap = -(-max(int(max_batch), 1) // SEG_CHUNK) * SEG_CHUNK
+        self.max_batch = max(int(max_batch), 1)
+        # a route warp takes its slots from blocks of 64 it reserves; a run that does not fit what is left
+        # of a block abandons the rest (marked invalid), so a segment may need up to twice the records
+        self.seg_cap = -(-(2 * self.max_batch + (1 << 18)) // SEG_CHUNK) * SEG_CHUNK
         self.ordinal_stride = (1 << 29) // (self.world + 1)
-        if self.seg_cap > self.ordinal_stride:
+        if self.max_batch > self.ordinal_stride:
             raise OccGridError(f'max_batch {max_batch} exceeds the per-rank ordinal slice {self.ordinal_stride} '
                                f'(2^29 order stamps shared by {self.world} ranks)')
         # the band's own grid: strategy tiled (the fused kernel IS the tiled raycast); its generic workspace stays minimal
@@ -229,8 +224,8 @@ class BandStep:
         c.band_geom = self._geom
         c.n_bands, c.rank, c.seg_capacity = self.world, self.rank, self.seg_cap
         for s in range(b.SLOTS):
-            c.d_recv[s], c.d_recv_tiles[s], c.d_seg_counts[s] = b.slot_ptr(s), b.tiles_ptr(s), b.seg_counts_ptr(s)
-            c.d_peer_recs[s], c.d_peer_tiles[s] = b.peer_recs[s].data_ptr(), b.peer_tiles[s].data_ptr()
+            c.d_recv[s], c.d_seg_counts[s] = b.slot_ptr(s), b.seg_counts_ptr(s)
+            c.d_peer_recs[s] = b.peer_recs[s].data_ptr()
             c.d_peer_seg_counts[s] = b.peer_seg_counts[s].data_ptr()
         c.d_peer_flags, c.d_my_flags = b.peer_flags.data_ptr(), b.flags_ptr()
         c.d_resv, c.d_status = self._resv.data_ptr(), self._status.data_ptr()
@@ -250,8 +245,8 @@ class BandStep:
         job = None
         if pk is not None:
             n, stride = pk.shape
-            if n > self.seg_cap:
-                raise OccGridError(f'batch of {n} records exceeds max_batch (segment capacity {self.seg_cap})')
+            if n > self.max_batch:
+                raise OccGridError(f'batch of {n} records exceeds max_batch = {self.max_batch}')
             j = self._job
             j.n, j.stride, j.rec_len = n, stride, 42 if stride >= 42 else 41
             if n:

@@ -40,15 +40,15 @@ class RouteJob(C.Structure):
                 ('d_agent_idx', C.c_void_p), ('d_drift', C.c_void_p), ('d_agent_off', C.c_void_p), ('n_agents', C.c_int32),
                 ('ordinal_base', C.c_uint32), ('ox', C.c_double), ('oy', C.c_double), ('res', C.c_double),
                 ('size_x', C.c_int32), ('n_bands', C.c_int32), ('src_rank', C.c_int32), ('band_y0', C.c_int32 * 33),
-                ('d_peer_recs', C.c_void_p), ('seg_capacity', C.c_int64), ('d_resv', C.c_void_p), ('d_status', C.c_void_p),
+                ('d_peer_recs', C.c_void_p), ('d_peer_tiles', C.c_void_p), ('seg_capacity', C.c_int64), ('d_resv', C.c_void_p), ('d_status', C.c_void_p),
                 ('d_counters', C.c_void_p)]
 
 
 class BandCtx(C.Structure):
     """struct occgrid_band_ctx"""
     _fields_ = [('band_geom', Geom), ('n_bands', C.c_int32), ('rank', C.c_int32), ('seg_capacity', C.c_int64),
-                ('d_recv', C.c_void_p * 2), ('d_seg_counts', C.c_void_p * 2),
-                ('d_peer_recs', C.c_void_p * 2), ('d_peer_seg_counts', C.c_void_p * 2),
+                ('d_recv', C.c_void_p * 2), ('d_recv_tiles', C.c_void_p * 2), ('d_seg_counts', C.c_void_p * 2),
+                ('d_peer_recs', C.c_void_p * 2), ('d_peer_tiles', C.c_void_p * 2), ('d_peer_seg_counts', C.c_void_p * 2),
                 ('d_peer_flags', C.c_void_p), ('d_my_flags', C.c_void_p), ('d_resv', C.c_void_p), ('d_status', C.c_void_p),
                 ('d_grid', C.c_void_p), ('d_workspace', C.c_void_p), ('workspace_bytes', C.c_size_t), ('d_counters', C.c_void_p)]
 
@@ -114,7 +114,7 @@ def lib():
     L.occgrid_band_workspace_bytes.restype = sz
     L.occgrid_band_workspace_bytes.argtypes = [gp, i32, i64]
     L.occgrid_band_prepare.restype = i32
-    L.occgrid_band_prepare.argtypes = [gp, vp, i32, i64, vp, vp, sz, vp, vp]
+    L.occgrid_band_prepare.argtypes = [gp, vp, vp, i32, i64, vp, vp, sz, vp, vp]
     L.occgrid_band_raycast_route.restype = i32
     L.occgrid_band_raycast_route.argtypes = [gp, vp, i32, i64, i32, C.POINTER(RouteJob), vp, vp, sz, vp, vp]
     L.occgrid_band_step.restype = i32

@@ -90,6 +90,7 @@ struct RouteJob {
     int n_bands, src_rank;
     int band_y0[kMaxBands + 1];
     PoseRec* const* peer_recs;               // device array [n_bands]: band owner's receive slot (its segment 0)
+    int* const* peer_tiles;                  // device array [n_bands]: the slot's compact tile ids (same addressing; -1 = unused slot)
     unsigned int seg_cap;
     unsigned int* resv;                      // LOCAL reservation counters [n_bands]; zero when the batch starts
     int* status;                             // bit 1: a segment overflowed
@@ -98,7 +99,7 @@ struct RouteJob {
 };
 
 size_t tiled_band_workspace_bytes(const occgrid_geom* geom, int n_segs, int64_t seg_cap);
-int tiled_prepare_poses(const occgrid_geom* geom, const PoseRec* d_recs, const SegInfo& seg, int tiles_in_records,
+int tiled_prepare_poses(const occgrid_geom* geom, const PoseRec* d_recs, const int* d_tiles, const SegInfo& seg, int tiles_in_records,
                         void* d_ws, size_t ws_bytes, uint64_t* d_counters, cudaStream_t st);
 int tiled_raycast_route(const occgrid_geom* geom, const PoseRec* d_recs, int have_items, const RouteJob* job,
                         int8_t* d_grid, void* d_ws, size_t ws_bytes, int64_t max_records, uint64_t* d_counters, cudaStream_t st);

@@ -78,7 +78,7 @@ size_t occgrid_band_workspace_bytes(const occgrid_geom* band_geom, int n_segs, i
     return tiled_band_workspace_bytes(band_geom, n_segs, seg_capacity);
 }
 
-int occgrid_band_prepare(const occgrid_geom* band_geom, const void* d_recv_slot, int n_segs, int64_t seg_capacity,
+int occgrid_band_prepare(const occgrid_geom* band_geom, const void* d_recv_slot, const int32_t* d_recv_tiles, int n_segs, int64_t seg_capacity,
                          const uint32_t* d_seg_counts, void* d_workspace, size_t workspace_bytes, uint64_t* d_counters,
                          void* stream) {
     int rc = validate_geom(band_geom);
@@ -90,7 +90,7 @@ int occgrid_band_prepare(const occgrid_geom* band_geom, const void* d_recv_slot,
     if (occgrid_band_workspace_bytes(band_geom, n_segs, seg_capacity) == 0) return OCCGRID_E_ARG;
     SegInfo seg;
     seg.n_segs = n_segs; seg.seg_cap = (unsigned int)seg_capacity; seg.d_counts = d_seg_counts; seg.host_count = 0;
-    return tiled_prepare_poses(band_geom, reinterpret_cast<const PoseRec*>(d_recv_slot), seg, 1, d_workspace, workspace_bytes,
+    return tiled_prepare_poses(band_geom, reinterpret_cast<const PoseRec*>(d_recv_slot), d_recv_tiles, seg, 1, d_workspace, workspace_bytes,
                                d_counters, (cudaStream_t)stream);
 }
 
@@ -103,7 +103,7 @@ int occgrid_band_raycast_route(const occgrid_geom* band_geom, const void* d_recv
     if (occgrid_band_workspace_bytes(band_geom, n_segs, seg_capacity) == 0) return OCCGRID_E_ARG;
     RouteJob J = {};
     if (job && job->n > 0) {
-        if (!job->d_packets || !job->d_agent_off || job->n_agents < 1 || !job->d_peer_recs || !job->d_resv || !job->d_status) {
+        if (!job->d_packets || !job->d_agent_off || job->n_agents < 1 || !job->d_peer_recs || !job->d_peer_tiles || !job->d_resv || !job->d_status) {
             set_last_error("band_raycast_route: NULL pointer in the route job");
             return OCCGRID_E_ARG;
         }
@@ -131,6 +131,7 @@ int occgrid_band_raycast_route(const occgrid_geom* band_geom, const void* d_recv
         J.n_bands = job->n_bands; J.src_rank = job->src_rank;
         for (int b = 0; b <= kMaxBands; ++b) J.band_y0[b] = job->band_y0[b <= job->n_bands ? b : job->n_bands];
         J.peer_recs = reinterpret_cast<PoseRec* const*>(job->d_peer_recs);
+        J.peer_tiles = reinterpret_cast<int* const*>(job->d_peer_tiles);
         J.seg_cap = (unsigned int)seg_capacity;
         J.resv = job->d_resv; J.status = job->d_status; J.counters = job->d_counters;
         J.n_route_items = (unsigned int)((job->n + kRouteChunkPk - 1) / kRouteChunkPk);
@@ -164,7 +165,7 @@ int occgrid_band_step(const occgrid_band_ctx* ctx, int64_t step_index, int have_
     const int prev = (int)((step_index + 1) & 1), slot = (int)(step_index & 1);
     int rc;
     if (have_pending) {
-        rc = occgrid_band_prepare(&ctx->band_geom, ctx->d_recv[prev], ctx->n_bands, ctx->seg_capacity,
+        rc = occgrid_band_prepare(&ctx->band_geom, ctx->d_recv[prev], ctx->d_recv_tiles[prev], ctx->n_bands, ctx->seg_capacity,
                                   ctx->d_seg_counts[prev], ctx->d_workspace, ctx->workspace_bytes, ctx->d_counters, stream);
         if (rc != OCCGRID_OK) return rc;
     }
@@ -172,7 +173,7 @@ int occgrid_band_step(const occgrid_band_ctx* ctx, int64_t step_index, int have_
     if (job) {
         j = *job;
         j.n_bands = ctx->n_bands; j.src_rank = ctx->rank; j.seg_capacity = ctx->seg_capacity;
-        j.d_peer_recs = ctx->d_peer_recs[slot];
+        j.d_peer_recs = ctx->d_peer_recs[slot]; j.d_peer_tiles = ctx->d_peer_tiles[slot];
         j.d_resv = ctx->d_resv; j.d_status = ctx->d_status;
     }
     rc = occgrid_band_raycast_route(&ctx->band_geom, ctx->d_recv[prev], ctx->n_bands, ctx->seg_capacity, have_pending,

@@ -244,7 +244,8 @@ __device__ __forceinline__ int chunk_valid(const SegInfo& seg, long long chunk, 
 // CTAs stride over 2048-address chunks and skip the empty ones.  `tiles_in_records`: the router
 // already computed the home tile for THIS window (rec.tile), nothing is re-derived here.
 __global__ void __launch_bounds__(kTT)
-k_home_count_poses(Geom g, TileGeom tg, const PoseRec* __restrict__ recs, SegInfo seg, long long n_chunks, int tiles_in_records,
+k_home_count_poses(Geom g, TileGeom tg, const PoseRec* __restrict__ recs, const int* __restrict__ in_tiles, SegInfo seg, long long n_chunks,
+                   int tiles_in_records,
                    unsigned int* __restrict__ tile_count, int* __restrict__ tile_ids,
                    unsigned int* __restrict__ active, TilePlanHeader* __restrict__ hdr, uint64_t* counters) {
     __shared__ unsigned int s_keys[kHash];
@@ -263,7 +264,7 @@ k_home_count_poses(Geom g, TileGeom tg, const PoseRec* __restrict__ recs, SegInf
             for (int sub = 0; sub < kSub; ++sub) {              // all loads of the thread in flight together
                 const int j = sub * kTT + threadIdx.x;
                 tl[sub] = -1;
-                if (j < valid) tl[sub] = recs[addr0 + j].tile;      // -1: a slot its route warp reserved but never filled
+                if (j < valid) tl[sub] = in_tiles ? in_tiles[addr0 + j] : recs[addr0 + j].tile;   // -1: reserved by a route warp, never filled
             }
 #pragma unroll
             for (int sub = 0; sub < kSub; ++sub) {
@@ -718,7 +719,7 @@ __device__ __forceinline__ unsigned int route_take_slots(const RouteJob& J, Rout
     unsigned int base = W.blk_base[b], left = W.blk_left[b];
     if (left < n) {
         if (base != 0xffffffffu)
-            for (unsigned int i = 0; i < left; ++i) J.peer_recs[b][(size_t)J.src_rank * J.seg_cap + base + i].tile = -1;
+            for (unsigned int i = 0; i < left; ++i) J.peer_tiles[b][(size_t)J.src_rank * J.seg_cap + base + i] = -1;
         base = atomicAdd(&J.resv[b], (unsigned int)kRouteBlk);                  // LOCAL counter: no NVLink round trip
         left = kRouteBlk;
         if (base + kRouteBlk > J.seg_cap) { atomicOr(J.status, 2); atomicSub(&J.resv[b], (unsigned int)kRouteBlk); base = 0xffffffffu; left = 0; }
@@ -736,6 +737,7 @@ __device__ __forceinline__ void route_store_rec(const RouteJob& J, int b, unsign
     dst[0] = make_uint4((unsigned int)ux, (unsigned int)(ux >> 32), (unsigned int)uy, (unsigned int)(uy >> 32));
     dst[1] = make_uint4(__float_as_uint(yaw), __float_as_uint(d[0]), __float_as_uint(d[1]), __float_as_uint(d[2]));
     dst[2] = make_uint4(__float_as_uint(d[3]), ord, (unsigned int)tile, 0u);
+    J.peer_tiles[b][(size_t)J.src_rank * J.seg_cap + slot] = tile;      // compact copy: the owner bins from 4 bytes per record
 }
 
 // The whole life of a route warp.  `W` is the warp's own staging area.
@@ -846,7 +848,7 @@ __device__ __noinline__ void route_warp_loop(const RouteJob& J, unsigned int* __
     for (int b = 0; b < J.n_bands; ++b) {
         const unsigned int base = W.blk_base[b], left = W.blk_left[b];
         if (base == 0xffffffffu) continue;
-        for (unsigned int i = lane; i < left; i += 32) J.peer_recs[b][(size_t)J.src_rank * J.seg_cap + base + i].tile = -1;
+        for (unsigned int i = lane; i < left; i += 32) J.peer_tiles[b][(size_t)J.src_rank * J.seg_cap + base + i] = -1;
     }
     if (J.counters) {
         unsigned int a = st_acc.a, bb = st_acc.b;
@@ -1157,7 +1159,7 @@ int integrate_tiled(const occgrid_geom* geom, const uint8_t* d_packets, const Po
     {
         ProfileScope ps(K_TILE_COUNT, st);
         if (d_poses)
-            k_home_count_poses<<<grid_chunks(n_chunks), kTT, 0, st>>>(g, tg, d_poses, seg, n_chunks, 0, P.tile_count, P.tile_ids, P.active,
+            k_home_count_poses<<<grid_chunks(n_chunks), kTT, 0, st>>>(g, tg, d_poses, nullptr, seg, n_chunks, 0, P.tile_count, P.tile_ids, P.active,
                                                                       P.hdr, d_counters);
         else
             k_home_count<<<blocks, kTT, 0, st>>>(g, tg, d_packets, n, stride, d_agent_idx, d_drift, d_agent_off, n_agents,
@@ -1185,7 +1187,7 @@ int integrate_tiled(const occgrid_geom* geom, const uint8_t* d_packets, const Po
 
 // ---- multi-GPU band step (include/occgrid_b200.h: occgrid_band_*) ---------------------------
 // count -> plan -> scatter over the per-source segments of a receive slot.
-int tiled_prepare_poses(const occgrid_geom* geom, const PoseRec* d_recs, const SegInfo& seg, int tiles_in_records,
+int tiled_prepare_poses(const occgrid_geom* geom, const PoseRec* d_recs, const int* d_tiles, const SegInfo& seg, int tiles_in_records,
                         void* d_ws, size_t ws_bytes, uint64_t* d_counters, cudaStream_t st) {
     const int64_t max_records = (int64_t)seg.n_segs * seg.seg_cap;
     const TiledLayout L = tiled_layout(geom, max_records, false);
@@ -1199,7 +1201,7 @@ int tiled_prepare_poses(const occgrid_geom* geom, const PoseRec* d_recs, const S
     const long long n_chunks = max_records / kSegChunk;
     {
         ProfileScope ps(K_TILE_COUNT, st);
-        k_home_count_poses<<<grid_chunks(n_chunks), kTT, 0, st>>>(g, tg, d_recs, seg, n_chunks, tiles_in_records, P.tile_count, P.tile_ids,
+        k_home_count_poses<<<grid_chunks(n_chunks), kTT, 0, st>>>(g, tg, d_recs, d_tiles, seg, n_chunks, tiles_in_records, P.tile_count, P.tile_ids,
                                                                   P.active, P.hdr, d_counters);
     }
     {

@@ -134,20 +134,26 @@ class BandBuffers:
             import torch.distributed._symmetric_memory as symm
             pg = group if group is not None else dist.group.WORLD
             self.recv = symm.empty(rec_shape, dtype=torch.uint8, device=device)
+            self.tiles = symm.empty(rec_shape[:3], dtype=torch.int32, device=device)
             self.ctl = symm.empty((self.CTL_WORDS,), dtype=torch.int32, device=device)
             self.ctl.zero_()
             torch.cuda.synchronize(device)
-            h_recv, h_ctl = symm.rendezvous(self.recv, pg), symm.rendezvous(self.ctl, pg)
-            self._handles = (h_recv, h_ctl)
+            h_recv, h_ctl, h_tiles = symm.rendezvous(self.recv, pg), symm.rendezvous(self.ctl, pg), symm.rendezvous(self.tiles, pg)
+            self._handles = (h_recv, h_ctl, h_tiles)
+            self.tile_bases = [int(p) for p in h_tiles.buffer_ptrs]
             self.recv_bases = [int(p) for p in h_recv.buffer_ptrs]
             self.ctl_bases = [int(p) for p in h_ctl.buffer_ptrs]
         else:
             self.recv = torch.empty(rec_shape, dtype=torch.uint8, device=device)
+            self.tiles = torch.empty(rec_shape[:3], dtype=torch.int32, device=device)
             self.ctl = torch.zeros((self.CTL_WORDS,), dtype=torch.int32, device=device)
-            self.recv_bases = self.ctl_bases = None         # filled by link()
+            self.recv_bases = self.ctl_bases = self.tile_bases = None         # filled by link()
 
     def slot_ptr(self, slot):
         return self.recv.data_ptr() + slot * self.world * self.seg_cap * 48
+
+    def tiles_ptr(self, slot):
+        return self.tiles.data_ptr() + slot * self.world * self.seg_cap * 4
 
     def seg_counts_ptr(self, slot):
         return self.ctl.data_ptr() + slot * 256
@@ -161,6 +167,7 @@ class BandBuffers:
         for b in buffers:
             b.recv_bases = [o.recv.data_ptr() for o in buffers]
             b.ctl_bases = [o.ctl.data_ptr() for o in buffers]
+            b.tile_bases = [o.tiles.data_ptr() for o in buffers]
 
     def pointer_tables(self):
         """Device arrays of peer pointers: per slot the owners' slot bases and seg_counts, plus flags."""
@@ -168,6 +175,7 @@ class BandBuffers:
         slot_bytes = self.world * self.seg_cap * 48
         t = lambda v: torch.tensor(v, dtype=torch.int64, device=dev)
         self.peer_recs = [t([p + s * slot_bytes for p in self.recv_bases]) for s in range(self.SLOTS)]
+        self.peer_tiles = [t([p + s * (slot_bytes // 12) for p in self.tile_bases]) for s in range(self.SLOTS)]
         self.peer_seg_counts = [t([p + s * 256 for p in self.ctl_bases]) for s in range(self.SLOTS)]
         self.peer_flags = t([p + self.SLOTS * 256 for p in self.ctl_bases])
 
@@ -224,8 +232,8 @@ class BandStep:
         c.band_geom = self._geom
         c.n_bands, c.rank, c.seg_capacity = self.world, self.rank, self.seg_cap
         for s in range(b.SLOTS):
-            c.d_recv[s], c.d_seg_counts[s] = b.slot_ptr(s), b.seg_counts_ptr(s)
-            c.d_peer_recs[s] = b.peer_recs[s].data_ptr()
+            c.d_recv[s], c.d_recv_tiles[s], c.d_seg_counts[s] = b.slot_ptr(s), b.tiles_ptr(s), b.seg_counts_ptr(s)
+            c.d_peer_recs[s], c.d_peer_tiles[s] = b.peer_recs[s].data_ptr(), b.peer_tiles[s].data_ptr()
             c.d_peer_seg_counts[s] = b.peer_seg_counts[s].data_ptr()
         c.d_peer_flags, c.d_my_flags = b.peer_flags.data_ptr(), b.flags_ptr()
         c.d_resv, c.d_status = self._resv.data_ptr(), self._status.data_ptr()

@@ -188,8 +188,9 @@ int occgrid_integrate_poses(const occgrid_geom* geom, const void* d_pose_recs, i
  * (the reference's ingest loop, dual_bot_mapper.py:816-843, once per server socket); a record has
  * to reach the owner of every band its rays can touch (robot row +- ceil(MAX_DIST_M/res)+2).
  * Receive buffers live in peer-mapped memory: each rank owns, per slot (2 slots), `n_bands`
- * per-SOURCE segments of `seg_capacity` occgrid_pose_rec (a multiple of 2048) plus uint32
- * seg_counts[n_bands]; a source reserves slots in ITS segment with a local atomic, so no remote
+ * per-SOURCE segments of `seg_capacity` occgrid_pose_rec (a multiple of 2048), the same number of
+ * int32 tile ids (a compact copy of rec.tile, so that binning reads 4 bytes per record; -1 marks a
+ * slot that was reserved but never filled) plus uint32 seg_counts[n_bands]; a source reserves slots in ITS segment with a local atomic, so no remote
  * atomics and no counts exchange are needed.  One step on every rank, all stream-ordered:
  *
  *   occgrid_band_prepare(slot j-1)          bin the records that arrived during the last step
@@ -217,6 +218,7 @@ typedef struct occgrid_route_job {
     int32_t        n_bands, src_rank;
     int32_t        band_y0[33];    /* band b = rows [band_y0[b], band_y0[b+1])                       */
     void* const*   d_peer_recs;    /* DEVICE array [n_bands]: owner b's receive slot (segment 0)     */
+    int32_t* const* d_peer_tiles;  /* DEVICE array [n_bands]: owner b's tile ids of that slot        */
     int64_t        seg_capacity;
     uint32_t*      d_resv;         /* LOCAL uint32[n_bands], zero before the batch's first item      */
     int32_t*       d_status;
@@ -224,7 +226,8 @@ typedef struct occgrid_route_job {
 } occgrid_route_job;
 
 size_t occgrid_band_workspace_bytes(const occgrid_geom* band_geom, int n_segs, int64_t seg_capacity);
-int occgrid_band_prepare(const occgrid_geom* band_geom /* window = my band */, const void* d_recv_slot, int n_segs,
+int occgrid_band_prepare(const occgrid_geom* band_geom /* window = my band */, const void* d_recv_slot,
+                         const int32_t* d_recv_tiles /* int32[n_segs * seg_capacity] of the slot (-1 = unused slot), or NULL: read rec.tile */, int n_segs,
                          int64_t seg_capacity, const uint32_t* d_seg_counts, void* d_workspace,
                          size_t workspace_bytes, uint64_t* d_counters, void* stream);
 int occgrid_band_raycast_route(const occgrid_geom* band_geom, const void* d_recv_slot, int n_segs,
@@ -237,8 +240,10 @@ typedef struct occgrid_band_ctx {
     int32_t          n_bands, rank;
     int64_t          seg_capacity;
     void*            d_recv[2];            /* my receive slots: occgrid_pose_rec[n_bands][seg_capacity] */
+    int32_t*         d_recv_tiles[2];      /* int32[n_bands][seg_capacity]                             */
     uint32_t*        d_seg_counts[2];      /* uint32[n_bands]                                          */
     void* const*     d_peer_recs[2];       /* device arrays [n_bands] of the owners' slot pointers     */
+    int32_t* const*  d_peer_tiles[2];
     uint32_t* const* d_peer_seg_counts[2];
     uint32_t* const* d_peer_flags;
     const uint32_t*  d_my_flags;

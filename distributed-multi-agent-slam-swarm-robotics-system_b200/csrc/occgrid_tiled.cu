@@ -654,9 +654,12 @@ __device__ __forceinline__ void walk_beam_masked(unsigned int win, int pitch, in
 constexpr int kRouteBlk = 64;                         // >= 32: one warp-wide run always fits a fresh block
 constexpr int kRawVec = 32 * kMaxStrideT / 16 / 32;   // 16-byte pieces per lane of a 32-packet chunk (<= 4)
 
+constexpr int kRouteStageRecs = 128;                 // records a route warp accumulates (all bands together) before it must flush
+
 struct __align__(16) RouteWarpSmem {
     uint4 raw[32 * kMaxStrideT / 16 + 1];             // the chunk's wire bytes (+ slack for the funnel-shift reads)
-    unsigned int blk_base[kMaxBands], blk_left[kMaxBands];
+    uint4 stage[kRouteStageRecs * 3];                 // per band: `cap` records waiting for a coalesced flush to the owner
+    unsigned int blk_base[kMaxBands], blk_left[kMaxBands], fill[kMaxBands];
 };
 
 // 32-bit little-endian field at byte offset `byte_off` (any alignment) of a buffer staged in shared
@@ -740,6 +743,25 @@ __device__ __forceinline__ void route_store_rec(const RouteJob& J, int b, unsign
     J.peer_tiles[b][(size_t)J.src_rank * J.seg_cap + slot] = tile;      // compact copy: the owner bins from 4 bytes per record
 }
 
+// One band's staged records -> its owner: slots from the warp's block, then a coalesced copy.
+__device__ __forceinline__ void route_flush_band(const RouteJob& J, RouteWarpSmem& W, int b, int cap, int lane) {
+    const unsigned int n = W.fill[b];
+    if (n == 0u) return;                                                        // warp-uniform
+    unsigned int base = 0u;
+    if (lane == 0) base = route_take_slots(J, W, b, n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base != 0xffffffffu) {
+        const size_t slot0 = (size_t)J.src_rank * J.seg_cap + base;
+        uint4* out = reinterpret_cast<uint4*>(J.peer_recs[b] + slot0);
+        const uint4* in = W.stage + (size_t)b * cap * 3;
+        for (unsigned int q = lane; q < n * 3u; q += 32) out[q] = in[q];
+        if ((unsigned int)lane < n) J.peer_tiles[b][slot0 + lane] = (int)in[lane * 3 + 2].z;    // compact copy of rec.tile
+    }
+    __syncwarp();
+    if (lane == 0) W.fill[b] = 0u;
+    __syncwarp();
+}
+
 // The whole life of a route warp.  `W` is the warp's own staging area.
 __device__ __noinline__ void route_warp_loop(const RouteJob& J, unsigned int* __restrict__ cursor, RouteWarpSmem& W) {
     const int lane = threadIdx.x & 31;
@@ -747,7 +769,9 @@ __device__ __noinline__ void route_warp_loop(const RouteJob& J, unsigned int* __
     const unsigned int n_chunks = J.n_route_items;
     W.blk_base[lane] = 0xffffffffu;
     W.blk_left[lane] = 0u;
+    W.fill[lane] = 0u;
     __syncwarp();
+    const int cap = min(32, kRouteStageRecs / J.n_bands);                       // staging slots per band (4 at 32 bands, 16 at 8)
     const bool vec = (reinterpret_cast<uintptr_t>(J.pkts) & 15) == 0 && ((32 * J.stride) & 15) == 0;
     RouteStats st_acc = {0u, 0u};
     uint4 v[kRawVec];
@@ -824,26 +848,46 @@ __device__ __noinline__ void route_warp_loop(const RouteJob& J, unsigned int* __
         }
         __syncwarp();                                                           // everybody has read the staged bytes
         const unsigned int ord = J.ordinal_base + (unsigned int)k;
-        {   // first entries: lanes of one band form a run of consecutive slots
-            const unsigned int p0 = __match_any_sync(0xffffffffu, band0);
-            const int leader = __ffs(p0) - 1;
-            unsigned int base = 0u;
-            if (band0 >= 0 && lane == leader) base = route_take_slots(J, W, band0, (unsigned int)__popc(p0));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (band0 >= 0 && base != 0xffffffffu) route_store_rec(J, band0, base + __popc(p0 & lt), rx, ry, yaw, dist, ord, tile0);
-        }
-        __syncwarp();
-        if (__any_sync(0xffffffffu, nb == 2)) {                                 // rare: only next to a band edge
-            const unsigned int p1 = __match_any_sync(0xffffffffu, nb == 2 ? band0 + 1 : -1);
-            const int leader = __ffs(p1) - 1;
-            unsigned int base = 0u;
-            if (nb == 2 && lane == leader) base = route_take_slots(J, W, band0 + 1, (unsigned int)__popc(p1));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (nb == 2 && base != 0xffffffffu) route_store_rec(J, band0 + 1, base + __popc(p1 & lt), rx, ry, yaw, dist, ord, tile1);
-            __syncwarp();
+        // Records are not sent one by one: every band has `cap` staging slots in shared memory, and a
+        // band's slots go to its owner as ONE contiguous run (consecutive lanes -> consecutive 16-byte
+        // chunks: full NVLink / HBM write transactions) when the next packet's records would not fit.
+#pragma unroll 1
+        for (int e = 0; e < 2; ++e) {
+            const int myband = e == 0 ? band0 : (nb == 2 ? band0 + 1 : -1);
+            const int mytile = e == 0 ? tile0 : tile1;
+            unsigned int present = __reduce_or_sync(0xffffffffu, myband >= 0 ? (1u << myband) : 0u);
+            while (present) {                                                   // warp-uniform loop over the bands of this chunk
+                const int b = __ffs(present) - 1;
+                present &= present - 1;
+                const unsigned int mine = __ballot_sync(0xffffffffu, myband == b);
+                const unsigned int cnt = __popc(mine), rank = __popc(mine & lt);
+                if (cnt > (unsigned int)cap || b == J.src_rank) {               // local records (L2 merges the pieces) and runs larger
+                                                                                // than the staging slots go out directly
+                    unsigned int base = 0u;
+                    if (lane == 0) base = route_take_slots(J, W, b, cnt);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (myband == b && base != 0xffffffffu) route_store_rec(J, b, base + rank, rx, ry, yaw, dist, ord, mytile);
+                    __syncwarp();
+                    continue;
+                }
+                unsigned int fill = W.fill[b];
+                if (fill + cnt > (unsigned int)cap) { route_flush_band(J, W, b, cap, lane); fill = 0u; }
+                if (myband == b) {
+                    uint4* dst = W.stage + (size_t)(b * cap + fill + rank) * 3;
+                    const unsigned long long ux = (unsigned long long)__double_as_longlong(rx), uy = (unsigned long long)__double_as_longlong(ry);
+                    dst[0] = make_uint4((unsigned int)ux, (unsigned int)(ux >> 32), (unsigned int)uy, (unsigned int)(uy >> 32));
+                    dst[1] = make_uint4(__float_as_uint(yaw), __float_as_uint(dist[0]), __float_as_uint(dist[1]), __float_as_uint(dist[2]));
+                    dst[2] = make_uint4(__float_as_uint(dist[3]), ord, (unsigned int)mytile, 0u);
+                }
+                __syncwarp();
+                if (lane == 0) W.fill[b] = fill + cnt;
+                __syncwarp();
+            }
+            if (!__any_sync(0xffffffffu, nb == 2)) break;                       // second entries are rare: only next to a band edge
         }
         cur = nxt;
     }
+    for (int b = 0; b < J.n_bands; ++b) route_flush_band(J, W, b, cap, lane);
     // what is left of the warp's blocks was reserved but never filled: mark it invalid
     for (int b = 0; b < J.n_bands; ++b) {
         const unsigned int base = W.blk_base[b], left = W.blk_left[b];
@@ -886,13 +930,13 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
     __shared__ unsigned long long s_acc[3 * 32];
     __shared__ unsigned int s_mask[kMaskEntries];
     __shared__ RouteJob s_job;                     // the route path reads the job from shared memory, not from a stack copy
-    __shared__ RouteWarpSmem s_rw;                 // staging area of the dedicated route warp
+    __shared__ __align__(16) unsigned char s_rw_bytes[kRoute ? sizeof(RouteWarpSmem) : 16];   // staging area of the dedicated route warp
     if (kRoute && threadIdx.x == 0) s_job = job;
     build_walk_masks(s_mask);
     __syncthreads();                               // the ONLY block-wide barrier: the roles split here
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (kRoute && warp == kCW) {
-        route_warp_loop(s_job, &hdr->route_cursor, s_rw);
+        route_warp_loop(s_job, &hdr->route_cursor, *reinterpret_cast<RouteWarpSmem*>(s_rw_bytes));
         return;
     }
     const unsigned int win_addr = (unsigned int)__cvta_generic_to_shared(s_win);
@@ -988,7 +1032,8 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
         // out of raycast items: the raycast warps help with whatever is left of the next batch; their
         // staging areas live in the (now unused) stamp window
         compute_sync<kCT>();
-        route_warp_loop(s_job, &hdr->route_cursor, reinterpret_cast<RouteWarpSmem*>(s_win)[warp]);
+        if ((size_t)(warp + 1) * sizeof(RouteWarpSmem) <= (size_t)words * 4)
+            route_warp_loop(s_job, &hdr->route_cursor, reinterpret_cast<RouteWarpSmem*>(s_win)[warp]);
     }
 }
 
@@ -1106,7 +1151,7 @@ static TiledPtrs tiled_ptrs(const TiledLayout& L, void* d_ws) {
 // buffer (raw packets, then <= 2 records per packet) when that is larger.
 static size_t raycast_smem(const TileGeom& tg, bool route) {
     size_t b = (size_t)tg.win_side * tg.pitch * 4;
-    const size_t r = (size_t)(kTT / 32) * sizeof(RouteWarpSmem);      // the raycast warps' route staging areas reuse the window
+    const size_t r = 2 * sizeof(RouteWarpSmem);       // at least two raycast warps can help routing once the items run out
     if (route) b = b > r ? b : r;
     return b;
 }

@@ -68,7 +68,8 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // addresses [s * seg_cap, s * seg_cap + count[s]).  count[] lives on the device (written by the
 // sources before the cross-GPU barrier) — the host never reads it.
 constexpr int kSegChunk = 2048;              // seg_cap is a multiple of this: a chunk never straddles two segments
-constexpr int kRouteChunkPk = 32;            // packets per route chunk of the fused kernel (one per lane of a route warp)
+constexpr int kRouteItemPk = 512;            // packets per route sub-batch of the fused kernel (two per thread)
+constexpr int kRouteSubsPerItem = 2;         // sub-batches per route work item
 constexpr int kMaxBands = 32;
 
 struct SegInfo {
@@ -90,12 +91,12 @@ struct RouteJob {
     int n_bands, src_rank;
     int band_y0[kMaxBands + 1];
     PoseRec* const* peer_recs;               // device array [n_bands]: band owner's receive slot (its segment 0)
-    int* const* peer_tiles;                  // device array [n_bands]: the slot's compact tile ids (same addressing; -1 = unused slot)
+    int* const* peer_tiles;                  // device array [n_bands]: the slot's compact tile ids (same addressing)
     unsigned int seg_cap;
     unsigned int* resv;                      // LOCAL reservation counters [n_bands]; zero when the batch starts
     int* status;                             // bit 1: a segment overflowed
     uint64_t* counters;                      // optional: packets / accepted / dropped / bad_pose of the routed share
-    unsigned int n_route_items;              // chunks of kRouteChunkPk packets
+    unsigned int n_route_items;              // work items of kRouteItemPk * kRouteSubs packets
 };
 
 size_t tiled_band_workspace_bytes(const occgrid_geom* geom, int n_segs, int64_t seg_cap);

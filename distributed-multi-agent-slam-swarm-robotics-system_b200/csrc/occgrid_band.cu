@@ -134,7 +134,7 @@ int occgrid_band_raycast_route(const occgrid_geom* band_geom, const void* d_recv
         J.peer_tiles = reinterpret_cast<int* const*>(job->d_peer_tiles);
         J.seg_cap = (unsigned int)seg_capacity;
         J.resv = job->d_resv; J.status = job->d_status; J.counters = job->d_counters;
-        J.n_route_items = (unsigned int)((job->n + kRouteChunkPk - 1) / kRouteChunkPk);
+        J.n_route_items = (unsigned int)((job->n + kRouteItemPk * kRouteSubsPerItem - 1) / (kRouteItemPk * kRouteSubsPerItem));
     }
     return tiled_raycast_route(band_geom, reinterpret_cast<const PoseRec*>(d_recv_slot), have_prepared ? 1 : 0,
                                J.n_route_items ? &J : nullptr, d_grid, d_workspace, workspace_bytes,

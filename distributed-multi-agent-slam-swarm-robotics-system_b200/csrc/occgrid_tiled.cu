@@ -41,7 +41,7 @@ constexpr int kMaxWindowBytes = 100 * 1024;   // smem window budget (two CTAs pe
 struct TilePlanHeader {
     unsigned int n_items, n_active, total_records, work_counter, resolve_counter, overflow;
     unsigned int active_count;   // tiles appended to the active list by the count pass of the current call
-    unsigned int route_cursor;   // next 32-packet chunk of the batch being routed (fused multi-GPU kernel)
+    unsigned int pad;
 };
 
 struct TileGeom {
@@ -264,7 +264,7 @@ k_home_count_poses(Geom g, TileGeom tg, const PoseRec* __restrict__ recs, const 
             for (int sub = 0; sub < kSub; ++sub) {              // all loads of the thread in flight together
                 const int j = sub * kTT + threadIdx.x;
                 tl[sub] = -1;
-                if (j < valid) tl[sub] = in_tiles ? in_tiles[addr0 + j] : recs[addr0 + j].tile;   // -1: reserved by a route warp, never filled
+                if (j < valid) tl[sub] = in_tiles ? in_tiles[addr0 + j] : recs[addr0 + j].tile;
             }
 #pragma unroll
             for (int sub = 0; sub < kSub; ++sub) {
@@ -451,7 +451,7 @@ k_tile_plan(unsigned int* __restrict__ tile_count, unsigned int* __restrict__ ti
         h.active_count = 0;                  // ready for the next call's count pass
         h.overflow = (s_carry[0] > max_records || s_carry[1] > max_items) ? 1u : 0u;
         if (h.overflow) { h.n_items = 0; h.n_active = 0; }
-        h.route_cursor = 0;
+        h.pad = 0;
         *hdr = h;
         if (counters) atomicAdd(reinterpret_cast<unsigned long long*>(counters) + OCCGRID_C_RECORDS, (unsigned long long)s_carry[0]);
     }
@@ -640,26 +640,18 @@ __device__ __forceinline__ void walk_beam_masked(unsigned int win, int pitch, in
     if (hit && !(dmaj == 0 && skip_first && !kAdd)) smem_red<kAdd>(a_end, kAdd ? 0x10000u : (v_free | 1u));
 }
 
-// ---- route warps (multi-GPU row bands, fused into the persistent raycast kernel) ---------------
-// Warp specialisation: in the fused kernel ONE warp of every CTA never raycasts.  It pulls chunks of
-// 32 packets of the NEXT batch (one packet per lane) from a global cursor and, on its own, with
-// warp-level primitives only: decodes (:828-843), corrects the pose (:851-857), finds the robot cell
-// (:142), the band(s) whose rows the packet's rays can reach and the home tile IN THAT BAND'S
-// WINDOW, takes slots from blocks of kRouteBlk records it reserves in this rank's segment of the
-// owner (a LOCAL atomic per block) and stores the 48-byte record straight into the owner's receive
-// buffer over NVLink.  Its loads are software-pipelined (the next chunk is in flight while the
-// current one is decoded) and its stores are fire and forget, so the route warps live in the issue
-// slots the seven raycast warps leave idle; when a CTA runs out of raycast items, its raycast warps
-// pull route chunks too.  Slots of a block that stay unused are marked invalid (tile = -1).
-constexpr int kRouteBlk = 64;                         // >= 32: one warp-wide run always fits a fresh block
-constexpr int kRawVec = 32 * kMaxStrideT / 16 / 32;   // 16-byte pieces per lane of a 32-packet chunk (<= 4)
-
-constexpr int kRouteStageRecs = 128;                 // records a route warp accumulates (all bands together) before it must flush
-
-struct __align__(16) RouteWarpSmem {
-    uint4 raw[32 * kMaxStrideT / 16 + 1];             // the chunk's wire bytes (+ slack for the funnel-shift reads)
-    uint4 stage[kRouteStageRecs * 3];                 // per band: `cap` records waiting for a coalesced flush to the owner
-    unsigned int blk_base[kMaxBands], blk_left[kMaxBands], fill[kMaxBands];
+// ---- route work item (multi-GPU row bands, fused into the persistent raycast kernel) -----------
+// One item = kRouteItemPk packets of the NEXT batch, one per thread: decode (:828-843), pose
+// correction (:851-857), robot cell (:142) -> the band(s) whose rows the packet's rays can reach
+// and its home tile IN THAT BAND'S WINDOW; the 48-byte records are sorted by band in shared
+// memory (the raycast window, free between two raycast items), a slot range is reserved in this
+// rank's segment of every destination with a LOCAL atomic, and the runs are copied into the band
+// owners' receive buffers over NVLink with fully coalesced 16-byte stores.  The stores are fire and
+// forget: they drain while the CTA is already walking the next raycast item.
+struct RouteSmem {
+    unsigned int cnt[kMaxBands];        // entries per band of this item
+    unsigned int off[kMaxBands + 1];    // exclusive offsets in the sorted buffer
+    unsigned int base[kMaxBands];       // reserved first slot in my segment of band b (0xffffffff: overflow)
 };
 
 // 32-bit little-endian field at byte offset `byte_off` (any alignment) of a buffer staged in shared
@@ -712,210 +704,186 @@ __device__ __forceinline__ bool robot_cell(double r, double o, double res, doubl
     return true;
 }
 
-// Statistics of the routed share, packed per lane (16 bits each, folded into the 64-bit counters
-// when the warp is done): a = packets | accepted << 16, b = dropped | hits << 16.
+// Statistics of the routed share, packed per thread (16 bits each, folded into the 64-bit counters
+// when the kernel ends): a = packets | accepted << 16, b = dropped | hits << 16.
 struct RouteStats { unsigned int a, b; };
 
-// Slots for a run of `n` records of band `b` (called by ONE lane): from the warp's current block,
-// or from a fresh one (the rest of the old block is marked invalid).  -> first slot, or 0xffffffff.
-__device__ __forceinline__ unsigned int route_take_slots(const RouteJob& J, RouteWarpSmem& W, int b, unsigned int n) {
-    unsigned int base = W.blk_base[b], left = W.blk_left[b];
-    if (left < n) {
-        if (base != 0xffffffffu)
-            for (unsigned int i = 0; i < left; ++i) J.peer_tiles[b][(size_t)J.src_rank * J.seg_cap + base + i] = -1;
-        base = atomicAdd(&J.resv[b], (unsigned int)kRouteBlk);                  // LOCAL counter: no NVLink round trip
-        left = kRouteBlk;
-        if (base + kRouteBlk > J.seg_cap) { atomicOr(J.status, 2); atomicSub(&J.resv[b], (unsigned int)kRouteBlk); base = 0xffffffffu; left = 0; }
-    }
-    if (base == 0xffffffffu) { W.blk_base[b] = base; W.blk_left[b] = 0; return base; }
-    W.blk_base[b] = base + n;
-    W.blk_left[b] = left - n;
-    return base;
-}
+constexpr int kRouteSubs = kRouteSubsPerItem;
+constexpr int kRoutePerThread = kRouteItemPk / kTT;      // packets per thread and sub-batch
+static_assert(kRouteItemPk % kTT == 0 && kRoutePerThread >= 1 && kRoutePerThread <= 4, "route sub-batch = 1..4 packets per thread");
 
-__device__ __forceinline__ void route_store_rec(const RouteJob& J, int b, unsigned int slot, double rx, double ry, float yaw,
-                                                const float d[4], unsigned int ord, int tile) {
-    uint4* dst = reinterpret_cast<uint4*>(J.peer_recs[b] + (size_t)J.src_rank * J.seg_cap + slot);   // struct occgrid_pose_rec
-    const unsigned long long ux = (unsigned long long)__double_as_longlong(rx), uy = (unsigned long long)__double_as_longlong(ry);
-    dst[0] = make_uint4((unsigned int)ux, (unsigned int)(ux >> 32), (unsigned int)uy, (unsigned int)(uy >> 32));
-    dst[1] = make_uint4(__float_as_uint(yaw), __float_as_uint(d[0]), __float_as_uint(d[1]), __float_as_uint(d[2]));
-    dst[2] = make_uint4(__float_as_uint(d[3]), ord, (unsigned int)tile, 0u);
-    J.peer_tiles[b][(size_t)J.src_rank * J.seg_cap + slot] = tile;      // compact copy: the owner bins from 4 bytes per record
-}
+// One decoded packet on its way to (at most) two band owners.
+struct RoutePk {
+    double rx, ry;
+    float yaw, d[4];
+    int band0, nb, tile0, tile1;        // bands are contiguous rows: the second band is band0 + 1
+    unsigned int rank0, rank1;
+};
 
-// One band's staged records -> its owner: slots from the warp's block, then a coalesced copy.
-__device__ __forceinline__ void route_flush_band(const RouteJob& J, RouteWarpSmem& W, int b, int cap, int lane) {
-    const unsigned int n = W.fill[b];
-    if (n == 0u) return;                                                        // warp-uniform
-    unsigned int base = 0u;
-    if (lane == 0) base = route_take_slots(J, W, b, n);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base != 0xffffffffu) {
-        const size_t slot0 = (size_t)J.src_rank * J.seg_cap + base;
-        uint4* out = reinterpret_cast<uint4*>(J.peer_recs[b] + slot0);
-        const uint4* in = W.stage + (size_t)b * cap * 3;
-        for (unsigned int q = lane; q < n * 3u; q += 32) out[q] = in[q];
-        if ((unsigned int)lane < n) J.peer_tiles[b][slot0 + lane] = (int)in[lane * 3 + 2].z;    // compact copy of rec.tile
+__device__ __forceinline__ void route_decode(const RouteJob& J, const unsigned int* s_buf, int slot, long long k, RoutePk& P,
+                                             RouteStats& st_acc) {
+    P.band0 = -1; P.nb = 0; P.tile0 = P.tile1 = -1; P.rank0 = P.rank1 = 0u;
+    const int st = decode_packet_smem(s_buf, (unsigned int)slot * (unsigned int)J.stride, k, J.agent_idx, J.drift, J.agent_off,
+                                      J.n_agents, &P.rx, &P.ry, &P.yaw, P.d);
+    st_acc.a += 1u + (st == PKT_OK ? 0x10000u : 0u);
+    st_acc.b += st == PKT_DROPPED ? 1u : 0u;
+    if (st != PKT_OK) return;
+    unsigned int hits = 0;
+#pragma unroll
+    for (int s2 = 0; s2 < 4; ++s2) {
+        const double dd = (double)P.d[s2];
+        hits += (OCC_MIN_DIST_M < dd && dd <= OCC_MAX_DIST_M) ? 1u : 0u;                 // :888
     }
-    __syncwarp();
-    if (lane == 0) W.fill[b] = 0u;
-    __syncwarp();
-}
-
-// The whole life of a route warp.  `W` is the warp's own staging area.
-__device__ __noinline__ void route_warp_loop(const RouteJob& J, unsigned int* __restrict__ cursor, RouteWarpSmem& W) {
-    const int lane = threadIdx.x & 31;
-    const unsigned int lt = (1u << lane) - 1u;
-    const unsigned int n_chunks = J.n_route_items;
-    W.blk_base[lane] = 0xffffffffu;
-    W.blk_left[lane] = 0u;
-    W.fill[lane] = 0u;
-    __syncwarp();
-    const int cap = min(32, kRouteStageRecs / J.n_bands);                       // staging slots per band (4 at 32 bands, 16 at 8)
-    const bool vec = (reinterpret_cast<uintptr_t>(J.pkts) & 15) == 0 && ((32 * J.stride) & 15) == 0;
-    RouteStats st_acc = {0u, 0u};
-    uint4 v[kRawVec];
-    auto pop = [&]() {
-        unsigned int c = 0;
-        if (lane == 0) c = atomicAdd(cursor, 1u);
-        return __shfl_sync(0xffffffffu, c, 0);
-    };
-    auto load = [&](unsigned int c) {                                           // this chunk's wire bytes -> registers
-        const long long first = (long long)c * 32;
-        const size_t bytes = (size_t)min(32ll, J.n - first) * J.stride;
-        const uint4* s4 = reinterpret_cast<const uint4*>(J.pkts + (size_t)first * J.stride);
-#pragma unroll
-        for (int j = 0; j < kRawVec; ++j) {
-            const size_t i = (size_t)j * 32 + lane;
-            v[j] = (i * 16 + 16 <= bytes) ? __ldg(s4 + i) : make_uint4(0u, 0u, 0u, 0u);
-        }
-    };
-    unsigned int cur = pop();
-    if (vec && cur < n_chunks) load(cur);
-    while (cur < n_chunks) {
-        const long long first = (long long)cur * 32;
-        const int count = (int)min(32ll, J.n - first);
-        if (vec) {
-#pragma unroll
-            for (int j = 0; j < kRawVec; ++j) W.raw[j * 32 + lane] = v[j];
-            const int bytes = count * J.stride;                                 // a last, partial chunk may end off a 16-byte boundary
-            for (int i = (bytes / 16) * 16 + lane; i < bytes; i += 32)
-                reinterpret_cast<uint8_t*>(W.raw)[i] = __ldg(J.pkts + (size_t)first * J.stride + i);
-        } else {
-            const uint8_t* src = J.pkts + (size_t)first * J.stride;
-            for (int i = lane; i < count * J.stride; i += 32) reinterpret_cast<uint8_t*>(W.raw)[i] = __ldg(src + i);
-        }
-        __syncwarp();
-        const unsigned int nxt = pop();                                         // the next chunk's loads fly while this one is decoded
-        if (vec && nxt < n_chunks) load(nxt);
-        double rx = 0.0, ry = 0.0;
-        float yaw = 0.f, dist[4] = {0.f, 0.f, 0.f, 0.f};
-        int band0 = -1, nb = 0, tile0 = -1, tile1 = -1;                         // bands are contiguous rows: the second band is band0 + 1
-        const long long k = first + lane;
-        if (lane < count) {
-            const int st = decode_packet_smem(reinterpret_cast<const unsigned int*>(W.raw), (unsigned int)lane * (unsigned int)J.stride, k,
-                                              J.agent_idx, J.drift, J.agent_off, J.n_agents, &rx, &ry, &yaw, dist);
-            st_acc.a += 1u + (st == PKT_OK ? 0x10000u : 0u);
-            st_acc.b += st == PKT_DROPPED ? 1u : 0u;
-            int gx, gy;
-            if (st == PKT_OK) {
-                unsigned int hits = 0;
-#pragma unroll
-                for (int s2 = 0; s2 < 4; ++s2) {
-                    const double dd = (double)dist[s2];
-                    hits += (OCC_MIN_DIST_M < dd && dd <= OCC_MAX_DIST_M) ? 1u : 0u;             // :888
-                }
-                st_acc.b += hits << 16;
-                if (robot_cell(rx, J.ox, J.res, J.inv_res, &gx) && robot_cell(ry, J.oy, J.res, J.inv_res, &gy) &&
-                    gx >= -J.reach && gx < J.size_x + J.reach) {
-                    const int tcol = (gx + J.pad) >> kTileShift;
-                    for (int b = 0; b < J.n_bands; ++b) {
-                        if (gy - J.reach < J.band_y0[b + 1]) {                  // first band whose rows end above the reach interval
-                            const int py = gy - J.band_y0[b];
-                            if (py >= -J.reach) {
-                                band0 = b; nb = 1;
-                                tile0 = ((py + J.pad) >> kTileShift) * J.tiles_x + tcol;
-                                if (b + 1 < J.n_bands && gy + J.reach >= J.band_y0[b + 1]) {
-                                    nb = 2;
-                                    tile1 = ((gy - J.band_y0[b + 1] + J.pad) >> kTileShift) * J.tiles_x + tcol;
-                                }
-                            }
-                            break;
-                        }
-                    }
-                }
-            }
-        }
-        __syncwarp();                                                           // everybody has read the staged bytes
-        const unsigned int ord = J.ordinal_base + (unsigned int)k;
-        // Records are not sent one by one: every band has `cap` staging slots in shared memory, and a
-        // band's slots go to its owner as ONE contiguous run (consecutive lanes -> consecutive 16-byte
-        // chunks: full NVLink / HBM write transactions) when the next packet's records would not fit.
-#pragma unroll 1
-        for (int e = 0; e < 2; ++e) {
-            const int myband = e == 0 ? band0 : (nb == 2 ? band0 + 1 : -1);
-            const int mytile = e == 0 ? tile0 : tile1;
-            unsigned int present = __reduce_or_sync(0xffffffffu, myband >= 0 ? (1u << myband) : 0u);
-            while (present) {                                                   // warp-uniform loop over the bands of this chunk
-                const int b = __ffs(present) - 1;
-                present &= present - 1;
-                const unsigned int mine = __ballot_sync(0xffffffffu, myband == b);
-                const unsigned int cnt = __popc(mine), rank = __popc(mine & lt);
-                if (cnt > (unsigned int)cap || b == J.src_rank) {               // local records (L2 merges the pieces) and runs larger
-                                                                                // than the staging slots go out directly
-                    unsigned int base = 0u;
-                    if (lane == 0) base = route_take_slots(J, W, b, cnt);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (myband == b && base != 0xffffffffu) route_store_rec(J, b, base + rank, rx, ry, yaw, dist, ord, mytile);
-                    __syncwarp();
-                    continue;
-                }
-                unsigned int fill = W.fill[b];
-                if (fill + cnt > (unsigned int)cap) { route_flush_band(J, W, b, cap, lane); fill = 0u; }
-                if (myband == b) {
-                    uint4* dst = W.stage + (size_t)(b * cap + fill + rank) * 3;
-                    const unsigned long long ux = (unsigned long long)__double_as_longlong(rx), uy = (unsigned long long)__double_as_longlong(ry);
-                    dst[0] = make_uint4((unsigned int)ux, (unsigned int)(ux >> 32), (unsigned int)uy, (unsigned int)(uy >> 32));
-                    dst[1] = make_uint4(__float_as_uint(yaw), __float_as_uint(dist[0]), __float_as_uint(dist[1]), __float_as_uint(dist[2]));
-                    dst[2] = make_uint4(__float_as_uint(dist[3]), ord, (unsigned int)mytile, 0u);
-                }
-                __syncwarp();
-                if (lane == 0) W.fill[b] = fill + cnt;
-                __syncwarp();
-            }
-            if (!__any_sync(0xffffffffu, nb == 2)) break;                       // second entries are rare: only next to a band edge
-        }
-        cur = nxt;
-    }
-    for (int b = 0; b < J.n_bands; ++b) route_flush_band(J, W, b, cap, lane);
-    // what is left of the warp's blocks was reserved but never filled: mark it invalid
+    st_acc.b += hits << 16;
+    int gx, gy;
+    if (!(robot_cell(P.rx, J.ox, J.res, J.inv_res, &gx) && robot_cell(P.ry, J.oy, J.res, J.inv_res, &gy))) return;
+    const int reach = J.reach;
+    if (gx < -reach || gx >= J.size_x + reach) return;
+    const int tcol = (gx + J.pad) >> kTileShift;
     for (int b = 0; b < J.n_bands; ++b) {
-        const unsigned int base = W.blk_base[b], left = W.blk_left[b];
-        if (base == 0xffffffffu) continue;
-        for (unsigned int i = lane; i < left; i += 32) J.peer_tiles[b][(size_t)J.src_rank * J.seg_cap + base + i] = -1;
-    }
-    if (J.counters) {
-        unsigned int a = st_acc.a, bb = st_acc.b;
-        unsigned long long pk = a & 0xffffu, acc = a >> 16, drp = bb & 0xffffu, hits = bb >> 16;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            pk += __shfl_xor_sync(0xffffffffu, pk, o); acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            drp += __shfl_xor_sync(0xffffffffu, drp, o); hits += __shfl_xor_sync(0xffffffffu, hits, o);
-        }
-        if (lane == 0 && pk) {
-            unsigned long long* cc = reinterpret_cast<unsigned long long*>(J.counters);
-            atomicAdd(cc + OCCGRID_C_PACKETS, pk); atomicAdd(cc + OCCGRID_C_ACCEPTED, acc); atomicAdd(cc + OCCGRID_C_DROPPED, drp);
-            atomicAdd(cc + OCCGRID_C_BAD_POSE, pk - acc - drp); atomicAdd(cc + OCCGRID_C_BEAMS, 4ull * acc);
-            atomicAdd(cc + OCCGRID_C_HITS, hits);
+        if (gy - reach < J.band_y0[b + 1]) {                                 // first band whose rows end above the reach interval
+            const int py = gy - J.band_y0[b];
+            if (py >= -reach) {
+                P.band0 = b; P.nb = 1;
+                P.tile0 = ((py + J.pad) >> kTileShift) * J.tiles_x + tcol;
+                if (b + 1 < J.n_bands && gy + reach >= J.band_y0[b + 1]) {
+                    P.nb = 2;
+                    P.tile1 = ((gy - J.band_y0[b + 1] + J.pad) >> kTileShift) * J.tiles_x + tcol;
+                }
+            }
+            break;
         }
     }
 }
 
-// Barrier over the raycast warps only (the route warp never takes part).
-template <int kThreads>
-__device__ __forceinline__ void compute_sync() {
-    if (kThreads == kTT) __syncthreads();
-    else asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+// rank of every entry inside its band's run (arrival order is free: ordinals travel in the records)
+__device__ __forceinline__ void route_rank(RouteSmem& S, RoutePk& P, int lane, unsigned int lt) {
+    const unsigned int p0 = __match_any_sync(0xffffffffu, P.band0);
+    if (P.band0 >= 0) {
+        const int leader = __ffs(p0) - 1;
+        unsigned int b0 = 0;
+        if (lane == leader) b0 = atomicAdd(&S.cnt[P.band0], (unsigned int)__popc(p0));
+        P.rank0 = __shfl_sync(p0, b0, leader) + __popc(p0 & lt);
+    }
+    if (__any_sync(0xffffffffu, P.nb == 2)) {                            // rare: only next to a band edge
+        const unsigned int p1 = __match_any_sync(0xffffffffu, P.nb == 2 ? P.band0 + 1 : -1);
+        if (P.nb == 2) {
+            const int leader = __ffs(p1) - 1;
+            unsigned int b1 = 0;
+            if (lane == leader) b1 = atomicAdd(&S.cnt[P.band0 + 1], (unsigned int)__popc(p1));
+            P.rank1 = __shfl_sync(p1, b1, leader) + __popc(p1 & lt);
+        }
+    }
+}
+
+__device__ __forceinline__ void route_store(const RouteJob& J, uint4* s16, const RoutePk& P, unsigned int my_off, long long k) {
+    const unsigned int o0 = __shfl_sync(0xffffffffu, my_off, P.band0 < 0 ? 0 : P.band0);
+    const unsigned long long ux = (unsigned long long)__double_as_longlong(P.rx), uy = (unsigned long long)__double_as_longlong(P.ry);
+    const uint4 w0 = make_uint4((unsigned int)ux, (unsigned int)(ux >> 32), (unsigned int)uy, (unsigned int)(uy >> 32));
+    const uint4 w1 = make_uint4(__float_as_uint(P.yaw), __float_as_uint(P.d[0]), __float_as_uint(P.d[1]), __float_as_uint(P.d[2]));
+    const unsigned int ord = J.ordinal_base + (unsigned int)k;
+    if (P.band0 >= 0) {                                                  // struct occgrid_pose_rec, 3 x 16 bytes
+        uint4* dst = s16 + (size_t)(o0 + P.rank0) * 3;
+        dst[0] = w0; dst[1] = w1; dst[2] = make_uint4(__float_as_uint(P.d[3]), ord, (unsigned int)P.tile0, 0u);
+    }
+    if (__any_sync(0xffffffffu, P.nb == 2)) {
+        const unsigned int o1 = __shfl_sync(0xffffffffu, my_off, P.nb == 2 ? P.band0 + 1 : 0);
+        if (P.nb == 2) {
+            uint4* dst = s16 + (size_t)(o1 + P.rank1) * 3;
+            dst[0] = w0; dst[1] = w1; dst[2] = make_uint4(__float_as_uint(P.d[3]), ord, (unsigned int)P.tile1, 0u);
+        }
+    }
+}
+
+__device__ __noinline__ RouteStats route_item(const RouteJob& J, unsigned int item, unsigned int* s_buf /* >= kRouteItemPk * 96 B */,
+                                              RouteSmem& S, RouteStats st_in) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int lt = (1u << lane) - 1u;
+    long long first = (long long)item * (kRouteItemPk * kRouteSubs);
+    for (int sub = 0; sub < kRouteSubs; ++sub, first += kRouteItemPk) {
+        const int count = (int)max(0ll, min((long long)kRouteItemPk, J.n - first));
+        if (count == 0) break;                                           // uniform across the CTA
+        __syncthreads();                                                 // the previous sub-batch's copy-out has left the buffer
+        if (threadIdx.x < kMaxBands) S.cnt[threadIdx.x] = 0u;
+        {   // staging with every load of the thread in flight before the first store (a load-store loop
+            // would pay one DRAM latency per iteration)
+            const uint8_t* src = J.pkts + (size_t)first * J.stride;
+            const size_t bytes = (size_t)count * J.stride;
+            constexpr int kVec = kRouteItemPk * kMaxStrideT / 16 / kTT;         // <= 8 chunks of 16 bytes per thread
+            if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+                const uint4* s4 = reinterpret_cast<const uint4*>(src);
+                uint4* d4 = reinterpret_cast<uint4*>(s_buf);
+                const size_t nvec = bytes / 16;
+                uint4 v[kVec];
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) {
+                    const size_t i = (size_t)j * kTT + threadIdx.x;
+                    if (i < nvec) v[j] = __ldg(s4 + i);
+                }
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) {
+                    const size_t i = (size_t)j * kTT + threadIdx.x;
+                    if (i < nvec) d4[i] = v[j];
+                }
+                for (size_t i = nvec * 16 + threadIdx.x; i < bytes; i += kTT) reinterpret_cast<uint8_t*>(s_buf)[i] = __ldg(src + i);
+            } else {
+                stage_records_t(src, bytes, reinterpret_cast<uint8_t*>(s_buf));
+            }
+        }
+        {   // pull the NEXT sub-batch towards L2 while this one is decoded, sorted and copied out
+            const long long nf = first + kRouteItemPk;
+            const long long nbytes = max(0ll, min((long long)kRouteItemPk, J.n - nf)) * J.stride;
+            const long long o = (long long)threadIdx.x * 128;
+            if (sub + 1 < kRouteSubs && o < nbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(J.pkts + (size_t)nf * J.stride + o));
+        }
+        __syncthreads();
+        RoutePk P[kRoutePerThread];
+#pragma unroll
+        for (int u = 0; u < kRoutePerThread; ++u) {                      // decode first (the table loads of all packets overlap) ...
+            const int slot = u * kTT + threadIdx.x;
+            P[u].band0 = -1; P[u].nb = 0;
+            if (slot < count) route_decode(J, s_buf, slot, first + slot, P[u], st_in);
+        }
+#pragma unroll
+        for (int u = 0; u < kRoutePerThread; ++u) route_rank(S, P[u], lane, lt);   // ... then the warp-level ranking
+        __syncthreads();                                                 // counts complete; raw packets decoded: the buffer is free
+        // every warp scans the <= 32 band counts in registers (lane b holds band b)
+        const unsigned int n_b = lane < J.n_bands ? S.cnt[lane] : 0u;
+        unsigned int inc = n_b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        const unsigned int my_off = inc - n_b;                           // exclusive offset of band `lane` in the sorted buffer
+        if (warp == 0) {                                                 // one reservation per band and sub-batch, on a LOCAL counter
+            unsigned int base = 0u;
+            if (n_b) {
+                base = atomicAdd(&J.resv[lane], n_b);
+                if (base + n_b > J.seg_cap) { atomicOr(J.status, 2); base = 0xffffffffu; }
+            }
+            S.base[lane] = base;                                         // (its latency overlaps the record stores below)
+            S.off[lane] = my_off;
+            if (lane == 31) S.off[32] = inc;
+        }
+        uint4* s16 = reinterpret_cast<uint4*>(s_buf);
+#pragma unroll
+        for (int u = 0; u < kRoutePerThread; ++u) route_store(J, s16, P[u], my_off, first + u * kTT + threadIdx.x);
+        __syncthreads();
+        // copy-out: one contiguous run per band, all threads on it: consecutive threads -> consecutive
+        // 16-byte chunks in the owner's segment (full NVLink / HBM write transactions)
+        for (int b = 0; b < J.n_bands; ++b) {
+            const unsigned int base = S.base[b];
+            const unsigned int n_rec = S.off[b + 1] - S.off[b];
+            if (n_rec == 0u || base == 0xffffffffu) continue;                // uniform across the CTA
+            const size_t slot0 = (size_t)J.src_rank * J.seg_cap + base;
+            uint4* out = reinterpret_cast<uint4*>(J.peer_recs[b] + slot0);
+            const uint4* in = s16 + (size_t)S.off[b] * 3;
+            for (unsigned int q = threadIdx.x; q < n_rec * 3u; q += kTT) out[q] = in[q];
+            // compact copy of the tile ids (word 10 of every record): the owner bins from 4 bytes per record
+            int* tout = J.peer_tiles[b] + slot0;
+            const unsigned int* tin = s_buf + (size_t)S.off[b] * 12 + 10;
+            for (unsigned int q = threadIdx.x; q < n_rec; q += kTT) tout[q] = (int)tin[(size_t)q * 12];
+        }
+    }
+    return st_in;
 }
 
 template <bool kCounts, bool kRoute>
@@ -923,39 +891,49 @@ __global__ void __launch_bounds__(kTT, 3)      // three CTAs per SM: 80 register
 k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHeader* __restrict__ hdr,
                const unsigned int* __restrict__ bins, const PoseRec* __restrict__ recs, int ordinals_in_records,
                unsigned int* __restrict__ stamps, uint64_t* counters, int have_items, const RouteJob job) {
-    constexpr int kCW = kRoute ? kTT / 32 - 1 : kTT / 32;      // raycast warps; the last warp of a fused CTA routes
-    constexpr int kCT = kCW * 32;
     extern __shared__ unsigned int s_win[];
     __shared__ unsigned int s_item;
-    __shared__ unsigned long long s_acc[3 * 32];
+    __shared__ unsigned long long s_acc[6 * 32];
+    __shared__ RouteSmem s_route;
     __shared__ unsigned int s_mask[kMaskEntries];
     __shared__ RouteJob s_job;                     // the route path reads the job from shared memory, not from a stack copy
-    __shared__ __align__(16) unsigned char s_rw_bytes[kRoute ? sizeof(RouteWarpSmem) : 16];   // staging area of the dedicated route warp
     if (kRoute && threadIdx.x == 0) s_job = job;
-    build_walk_masks(s_mask);
-    __syncthreads();                               // the ONLY block-wide barrier: the roles split here
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (kRoute && warp == kCW) {
-        route_warp_loop(s_job, &hdr->route_cursor, *reinterpret_cast<RouteWarpSmem*>(s_rw_bytes));
-        return;
-    }
+    build_walk_masks(s_mask);                      // both visible after the first __syncthreads of the loop below
     const unsigned int win_addr = (unsigned int)__cvta_generic_to_shared(s_win);
     const unsigned int n_items = have_items ? hdr->n_items : 0u;
+    // Unified queue: raycast items of THIS batch and route items of the NEXT one, interleaved in
+    // proportion, so the NVLink traffic is spread over the whole kernel and overlaps the walks.
+    const unsigned int n_route = kRoute ? job.n_route_items : 0u;
+    const unsigned int n_total = n_items + n_route;
     const int side = tg.win_side, pitch = tg.pitch, words = side * pitch;
-    unsigned int c32[3] = {0u, 0u, 0u};      // updates, slowpath, owned updates (per thread: far below 2^32)
+    unsigned long long c[3] = {0, 0, 0};     // updates, slowpath, owned updates
+    RouteStats rs = {0u, 0u};                // routed share, packed (see RouteStats)
     for (;;) {
-        compute_sync<kCT>();
+        __syncthreads();
         if (threadIdx.x == 0) s_item = atomicAdd(&hdr->work_counter, 1u);
-        for (int i = threadIdx.x; i < words; i += kCT) s_win[i] = 0u;
-        compute_sync<kCT>();
-        const unsigned int it = s_item;
-        if (it >= n_items) break;
+        if (!kRoute)
+            for (int i = threadIdx.x; i < words; i += kTT) s_win[i] = 0u;
+        __syncthreads();
+        unsigned int it = s_item;
+        if (it >= n_total) break;
+        if (kRoute) {
+            // r(i) = floor(i * n_route / n_total) route items precede queue position i
+            const unsigned int r0 = (unsigned int)(((unsigned long long)it * n_route) / n_total);
+            const unsigned int r1 = (unsigned int)(((unsigned long long)(it + 1) * n_route) / n_total);
+            if (r1 > r0) {
+                rs = route_item(s_job, r0, s_win, s_route, rs);
+                continue;
+            }
+            it -= r0;
+            for (int i = threadIdx.x; i < words; i += kTT) s_win[i] = 0u;
+            __syncthreads();
+        }
         const uint4 item = items[it];
         const int ttx = item.x % tg.tiles_x, tty = item.x / tg.tiles_x;
         // global cell of window-local (0, 0)
         const int wx0 = g.win_x0 - tg.pad + (ttx << kTileShift) - tg.reach;
         const int wy0 = g.win_y0 - tg.pad + (tty << kTileShift) - tg.reach;
-        for (unsigned int r = item.y + threadIdx.x; r < item.z; r += kCT) {
+        for (unsigned int r = item.y + threadIdx.x; r < item.z; r += kTT) {
             const unsigned int idx = bins[r];
             const PoseRec rec = recs[idx];
             const unsigned int k = ordinals_in_records ? rec.k : idx;   // packet ordinal in this batch
@@ -974,9 +952,9 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
                 expand_beam_of(g, F, s, s == 0 ? rec.d[0] : (s == 1 ? rec.d[1] : (s == 2 ? rec.d[2] : rec.d[3])), LibSinCos(), &b);
                 if (!b.valid) continue;
                 const int cells = beam_cells(b);
-                c32[0] += (unsigned int)cells;
-                c32[1] += (unsigned int)b.slow;
-                if (owned) c32[2] += (unsigned int)cells;
+                c[0] += cells;
+                c[1] += b.slow;
+                if (owned) c[2] += cells;
                 const int ddx = b.x1 - b.x0, ddy = b.y1 - b.y0;
                 const bool fast = (unsigned int)lx < us && (unsigned int)ly < us && (unsigned int)(lx + ddx) < us &&
                                   (unsigned int)(ly + ddy) < us && cells <= kMaskMaxLen + 1;
@@ -991,12 +969,13 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
                 later_writes_first = later_writes_first || (cells > 1 || b.hit);
             }
         }
-        compute_sync<kCT>();
+        __syncthreads();
         // flush: window rows are contiguous in the stamp plane -> coalesced reductions
         const int lx_lo = max(0, g.win_x0 - wx0), lx_hi = min(side, g.win_x0 + g.win_w - wx0);
         const int ly_lo = max(0, g.win_y0 - wy0), ly_hi = min(side, g.win_y0 + g.win_h - wy0);
         if (lx_hi > lx_lo) {
-            for (int ly = ly_lo + warp; ly < ly_hi; ly += kCW) {               // one warp per window row
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            for (int ly = ly_lo + warp; ly < ly_hi; ly += kTT / 32) {          // one warp per window row
                 const unsigned int* row = s_win + ly * pitch;
                 unsigned int* out = stamps + (size_t)(wy0 + ly - g.win_y0) * g.win_w + (wx0 - g.win_x0);
                 for (int lx = lx_lo + lane; lx < lx_hi; lx += 32) {
@@ -1011,29 +990,29 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
             }
         }
     }
+    if (kRoute && job.counters) {
+        __syncthreads();
+        const unsigned long long pk = rs.a & 0xffffu, acc = rs.a >> 16, drp = rs.b & 0xffffu, hits = rs.b >> 16;
+        const unsigned long long rc[6] = {pk, acc, drp, pk - acc - drp, 4ull * acc, hits};
+        block_add_counters(rc, s_acc, job.counters);            // slots OCCGRID_C_PACKETS .. OCCGRID_C_HITS
+    }
     if (counters) {
-        compute_sync<kCT>();
+        __syncthreads();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            unsigned long long x = c32[i];
+            unsigned long long x = c[i];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
             if (lane == 0) s_acc[i * 32 + warp] = x;
         }
-        compute_sync<kCT>();
+        __syncthreads();
         if (threadIdx.x < 3) {
             unsigned long long t = 0;
-            for (int w = 0; w < kCW; ++w) t += s_acc[threadIdx.x * 32 + w];
+            for (int w = 0; w < kTT / 32; ++w) t += s_acc[threadIdx.x * 32 + w];
             const int slot = threadIdx.x == 0 ? OCCGRID_C_UPDATES : (threadIdx.x == 1 ? OCCGRID_C_SLOWPATH : OCCGRID_C_OWNED_UPDATES);
             if (t) atomicAdd(reinterpret_cast<unsigned long long*>(counters) + slot, t);
         }
-    }
-    if (kRoute) {
-        // out of raycast items: the raycast warps help with whatever is left of the next batch; their
-        // staging areas live in the (now unused) stamp window
-        compute_sync<kCT>();
-        if ((size_t)(warp + 1) * sizeof(RouteWarpSmem) <= (size_t)words * 4)
-            route_warp_loop(s_job, &hdr->route_cursor, reinterpret_cast<RouteWarpSmem*>(s_win)[warp]);
     }
 }
 
@@ -1151,8 +1130,10 @@ static TiledPtrs tiled_ptrs(const TiledLayout& L, void* d_ws) {
 // buffer (raw packets, then <= 2 records per packet) when that is larger.
 static size_t raycast_smem(const TileGeom& tg, bool route) {
     size_t b = (size_t)tg.win_side * tg.pitch * 4;
-    const size_t r = 2 * sizeof(RouteWarpSmem);       // at least two raycast warps can help routing once the items run out
+    const size_t r = (size_t)kRouteItemPk * 2 * sizeof(PoseRec);   // every packet may go to two bands
+    const size_t raw = (size_t)kRouteItemPk * kMaxStrideT;
     if (route) b = b > r ? b : r;
+    if (route) b = b > raw ? b : raw;
     return b;
 }
 

@@ -140,8 +140,8 @@ class BandBuffers:
             torch.cuda.synchronize(device)
             h_recv, h_ctl, h_tiles = symm.rendezvous(self.recv, pg), symm.rendezvous(self.ctl, pg), symm.rendezvous(self.tiles, pg)
             self._handles = (h_recv, h_ctl, h_tiles)
-            self.tile_bases = [int(p) for p in h_tiles.buffer_ptrs]
             self.recv_bases = [int(p) for p in h_recv.buffer_ptrs]
+            self.tile_bases = [int(p) for p in h_tiles.buffer_ptrs]
             self.ctl_bases = [int(p) for p in h_ctl.buffer_ptrs]
         else:
             self.recv = torch.empty(rec_shape, dtype=torch.uint8, device=device)
@@ -191,12 +191,9 @@ class BandStep:
         self.device = torch.device(device)
         self._lib = _native.lib()
         self.size, self.res, self.ox, self.oy = int(size), float(resolution), float(origin_x), float(origin_y)
-        self.max_batch = max(int(max_batch), 1)
-        # a route warp takes its slots from blocks of 64 it reserves; a run that does not fit what is left
-        # of a block abandons the rest (marked invalid), so a segment may need up to twice the records
-        self.seg_cap = -(-(2 * self.max_batch + (1 << 18)) // SEG_CHUNK) * SEG_CHUNK
+        self.seg_cap = -(-max(int(max_batch), 1) // SEG_CHUNK) * SEG_CHUNK
         self.ordinal_stride = (1 << 29) // (self.world + 1)
-        if self.max_batch > self.ordinal_stride:
+        if self.seg_cap > self.ordinal_stride:
             raise OccGridError(f'max_batch {max_batch} exceeds the per-rank ordinal slice {self.ordinal_stride} '
                                f'(2^29 order stamps shared by {self.world} ranks)')
         # the band's own grid: strategy tiled (the fused kernel IS the tiled raycast); its generic workspace stays minimal
@@ -253,8 +250,8 @@ class BandStep:
         job = None
         if pk is not None:
             n, stride = pk.shape
-            if n > self.max_batch:
-                raise OccGridError(f'batch of {n} records exceeds max_batch = {self.max_batch}')
+            if n > self.seg_cap:
+                raise OccGridError(f'batch of {n} records exceeds max_batch (segment capacity {self.seg_cap})')
             j = self._job
             j.n, j.stride, j.rec_len = n, stride, 42 if stride >= 42 else 41
             if n:

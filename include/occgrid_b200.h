@@ -189,8 +189,8 @@ int occgrid_integrate_poses(const occgrid_geom* geom, const void* d_pose_recs, i
  * to reach the owner of every band its rays can touch (robot row +- ceil(MAX_DIST_M/res)+2).
  * Receive buffers live in peer-mapped memory: each rank owns, per slot (2 slots), `n_bands`
  * per-SOURCE segments of `seg_capacity` occgrid_pose_rec (a multiple of 2048), the same number of
- * int32 tile ids (a compact copy of rec.tile, so that binning reads 4 bytes per record; -1 marks a
- * slot that was reserved but never filled) plus uint32 seg_counts[n_bands]; a source reserves slots in ITS segment with a local atomic, so no remote
+ * int32 tile ids (a compact copy of rec.tile, so that binning reads 4 bytes per record) plus uint32
+ * seg_counts[n_bands]; a source reserves slots in ITS segment with a local atomic, so no remote
  * atomics and no counts exchange are needed.  One step on every rank, all stream-ordered:
  *
  *   occgrid_band_prepare(slot j-1)          bin the records that arrived during the last step
@@ -227,7 +227,7 @@ typedef struct occgrid_route_job {
 
 size_t occgrid_band_workspace_bytes(const occgrid_geom* band_geom, int n_segs, int64_t seg_capacity);
 int occgrid_band_prepare(const occgrid_geom* band_geom /* window = my band */, const void* d_recv_slot,
-                         const int32_t* d_recv_tiles /* int32[n_segs * seg_capacity] of the slot (-1 = unused slot), or NULL: read rec.tile */, int n_segs,
+                         const int32_t* d_recv_tiles /* int32[n_segs * seg_capacity] of the slot, or NULL: read rec.tile */, int n_segs,
                          int64_t seg_capacity, const uint32_t* d_seg_counts, void* d_workspace,
                          size_t workspace_bytes, uint64_t* d_counters, void* stream);
 int occgrid_band_raycast_route(const occgrid_geom* band_geom, const void* d_recv_slot, int n_segs,

@@ -158,12 +158,13 @@ def test_fused_band_step_reports_segment_overflow():
     steps = _emulated_band_steps(2, size, origin, 2048)
     tab = torch.from_numpy(sess['agent_offsets']).cuda()
     s = steps[0]
+    s.seg_cap_saved = s.seg_cap
     pk = torch.from_numpy(sess['packets'][:2048]).cuda()
     idx = torch.from_numpy(sess['agent_idx'][:2048].copy()).cuda()
     s.step(pk, idx, None, tab, wait=False)
     s.step(pk, idx, None, tab, wait=False)          # fine: the reservation counters were reset by publish
     s.check_status()
-    s._resv[:2].fill_(s.seg_cap - 8)                # pretend the segments are nearly full
+    s._resv[:2].fill_(2040)                         # pretend the segments are nearly full
     s.step(pk, idx, None, tab, wait=False)
     with pytest.raises(OccGridError, match='overflow'):
         s.check_status()

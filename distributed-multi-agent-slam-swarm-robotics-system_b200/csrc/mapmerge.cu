@@ -196,8 +196,8 @@ k_extract_write(const int8_t* __restrict__ grid, long long n_cells, int width, d
             const double w = OCC_DADD(OCC_DADD(OCC_DMUL(T.m[12], x), OCC_DMUL(T.m[13], y)), T.m[15]);
             const double tx = OCC_DADD(OCC_DADD(OCC_DMUL(T.m[0], x), OCC_DMUL(T.m[1], y)), T.m[3]);
             const double ty = OCC_DADD(OCC_DADD(OCC_DMUL(T.m[4], x), OCC_DMUL(T.m[5], y)), T.m[7]);
-            x = OCC_DDIV(tx, w);
-            y = OCC_DDIV(ty, w);
+            if (w == 1.0) { x = tx; y = ty; }                  // v / 1.0 == v bit for bit
+            else { x = OCC_DDIV(tx, w); y = OCC_DDIV(ty, w); }
         }
         px[dst] = x;
         py[dst] = y;
@@ -442,8 +442,8 @@ k_batch_write(const unsigned long long* __restrict__ masks, long long n_cells, i
             const double w = OCC_DADD(OCC_DADD(OCC_DMUL(t.w[0], x), OCC_DMUL(t.w[1], y)), t.w[2]);
             const double tx = OCC_DADD(OCC_DADD(OCC_DMUL(t.m[0], x), OCC_DMUL(t.m[1], y)), t.m[2]);
             const double ty = OCC_DADD(OCC_DADD(OCC_DMUL(t.m[3], x), OCC_DMUL(t.m[4], y)), t.m[5]);
-            x = OCC_DDIV(tx, w);
-            y = OCC_DDIV(ty, w);
+            if (w == 1.0) { x = tx; y = ty; }                  // rigid transforms: v / 1.0 == v bit for bit, skip two fp64 divisions
+            else { x = OCC_DDIV(tx, w); y = OCC_DDIV(ty, w); }
         }
         px[dst0 + i] = x;
         py[dst0 + i] = y;

@@ -39,10 +39,11 @@ def mb(d, key):
             unit = k[k.index('[') + 1:-1]
             return f * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[unit]
     return 0.0
-sel = [d for d in summ if (traffic_kernel is None or traffic_kernel in d['kernel'])]
+sel = [d for d in summ if (traffic_kernel is not None and traffic_kernel in d['kernel'])]
 tr = [mb(d, 'dram__bytes_read.sum') + mb(d, 'dram__bytes_write.sum') for d in sel]
-json.dump({'kernel': sel[0]['kernel'], 'dram_bytes_per_launch': sum(tr) / len(tr), 'launches_captured': len(tr),
-           'source': f'profiles/{tag}_ncu_full_summary.json'}, open(os.path.join(out, 'ncu_traffic.json'), 'w'), indent=1)
+if sel:
+  json.dump({'kernel': sel[0]['kernel'], 'dram_bytes_per_launch': sum(tr) / len(tr), 'launches_captured': len(tr),
+           'source': f'profiles/{tag}_ncu_full_summary.json'}, open(os.path.join(out, 'ncu_traffic.json'), 'w'), indent=1)   # only when the traffic kernel was captured
 # stall hot spots
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout
 open('/tmp/_src.csv', 'w').write(src)

@@ -50,7 +50,8 @@ class BandCtx(C.Structure):
                 ('d_recv', C.c_void_p * 2), ('d_recv_tiles', C.c_void_p * 2), ('d_seg_counts', C.c_void_p * 2),
                 ('d_peer_recs', C.c_void_p * 2), ('d_peer_tiles', C.c_void_p * 2), ('d_peer_seg_counts', C.c_void_p * 2),
                 ('d_peer_flags', C.c_void_p), ('d_my_flags', C.c_void_p), ('d_resv', C.c_void_p), ('d_status', C.c_void_p),
-                ('d_grid', C.c_void_p), ('d_workspace', C.c_void_p), ('workspace_bytes', C.c_size_t), ('d_counters', C.c_void_p)]
+                ('d_grid', C.c_void_p), ('d_workspace', C.c_void_p), ('workspace_bytes', C.c_size_t), ('d_counters', C.c_void_p),
+                ('ev_fused', C.c_void_p), ('ev_published', C.c_void_p), ('published_pending', C.c_int32)]
 
 
 def _stale():
@@ -118,7 +119,9 @@ def lib():
     L.occgrid_band_raycast_route.restype = i32
     L.occgrid_band_raycast_route.argtypes = [gp, vp, i32, i64, i32, C.POINTER(RouteJob), vp, vp, sz, vp, vp]
     L.occgrid_band_step.restype = i32
-    L.occgrid_band_step.argtypes = [C.POINTER(BandCtx), i64, i32, C.POINTER(RouteJob), i32, vp]
+    L.occgrid_band_step.argtypes = [C.POINTER(BandCtx), i64, i32, C.POINTER(RouteJob), i32, vp, vp]
+    L.occgrid_band_join.restype = i32
+    L.occgrid_band_join.argtypes = [C.POINTER(BandCtx), vp]
     L.occgrid_band_publish.restype = i32
     L.occgrid_band_publish.argtypes = [i32, i32, vp, i64, vp, vp, vp, u32, i32, vp, vp]
     L.occgrid_frontier_workspace_bytes.restype = sz

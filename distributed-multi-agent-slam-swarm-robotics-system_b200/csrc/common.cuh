@@ -103,7 +103,8 @@ size_t tiled_band_workspace_bytes(const occgrid_geom* geom, int n_segs, int64_t 
 int tiled_prepare_poses(const occgrid_geom* geom, const PoseRec* d_recs, const int* d_tiles, const SegInfo& seg, int tiles_in_records,
                         void* d_ws, size_t ws_bytes, uint64_t* d_counters, cudaStream_t st);
 int tiled_raycast_route(const occgrid_geom* geom, const PoseRec* d_recs, int have_items, const RouteJob* job,
-                        int8_t* d_grid, void* d_ws, size_t ws_bytes, int64_t max_records, uint64_t* d_counters, cudaStream_t st);
+                        int8_t* d_grid, void* d_ws, size_t ws_bytes, int64_t max_records, uint64_t* d_counters, cudaStream_t st,
+                        cudaEvent_t after_fused = nullptr);
 
 // Block-wide accumulation of the first N uint64 counter slots: per-thread values -> warp
 // shuffle -> per-warp partials in shared memory -> one global atomic per slot per CTA.

@@ -66,6 +66,9 @@ __global__ void k_band_publish(int n_bands, int rank, unsigned int* __restrict__
 
 using namespace occ;
 
+// event occgrid_band_step wants recorded between the fused kernel and the resolve (per host thread)
+static thread_local cudaEvent_t g_after_fused = nullptr;
+
 extern "C" {
 
 size_t occgrid_band_workspace_bytes(const occgrid_geom* band_geom, int n_segs, int64_t seg_capacity) {
@@ -138,7 +141,7 @@ int occgrid_band_raycast_route(const occgrid_geom* band_geom, const void* d_recv
     }
     return tiled_raycast_route(band_geom, reinterpret_cast<const PoseRec*>(d_recv_slot), have_prepared ? 1 : 0,
                                J.n_route_items ? &J : nullptr, d_grid, d_workspace, workspace_bytes,
-                               (int64_t)n_segs * seg_capacity, d_counters, (cudaStream_t)stream);
+                               (int64_t)n_segs * seg_capacity, d_counters, (cudaStream_t)stream, g_after_fused);
 }
 
 int occgrid_band_publish(int n_bands, int rank, uint32_t* d_resv, int64_t seg_capacity, uint32_t* const* d_peer_seg_counts,
@@ -159,11 +162,24 @@ int occgrid_band_publish(int n_bands, int rank, uint32_t* d_resv, int64_t seg_ca
 
 // One whole step from ONE host call (the per-step host cost decides how far ahead of the GPUs the
 // launch queue runs, and with it how much of every rank's jitter ends up inside the barrier).
-int occgrid_band_step(const occgrid_band_ctx* ctx, int64_t step_index, int have_pending, const occgrid_route_job* job,
-                      int wait, void* stream) {
+// With a `side_stream` the publish + barrier of this step's routed batch run THERE, right after the
+// fused kernel and concurrently with the resolve pass; the next step's prepare waits for them.
+int occgrid_band_step(occgrid_band_ctx* ctx, int64_t step_index, int have_pending, const occgrid_route_job* job,
+                      int wait, void* stream, void* side_stream) {
     if (!ctx) { set_last_error("band_step: NULL context"); return OCCGRID_E_ARG; }
     const int prev = (int)((step_index + 1) & 1), slot = (int)(step_index & 1);
+    cudaStream_t st = (cudaStream_t)stream, side = (cudaStream_t)side_stream;
     int rc;
+    if (side && !ctx->ev_fused) {
+        cudaEvent_t a = nullptr, p = nullptr;
+        OCC_CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        OCC_CUDA_TRY(cudaEventCreateWithFlags(&p, cudaEventDisableTiming));
+        ctx->ev_fused = a; ctx->ev_published = p;
+    }
+    if (side && ctx->published_pending) {            // the batch about to be binned must have arrived from every rank
+        OCC_CUDA_TRY(cudaStreamWaitEvent(st, (cudaEvent_t)ctx->ev_published, 0));
+        ctx->published_pending = 0;
+    }
     if (have_pending) {
         rc = occgrid_band_prepare(&ctx->band_geom, ctx->d_recv[prev], ctx->d_recv_tiles[prev], ctx->n_bands, ctx->seg_capacity,
                                   ctx->d_seg_counts[prev], ctx->d_workspace, ctx->workspace_bytes, ctx->d_counters, stream);
@@ -176,13 +192,33 @@ int occgrid_band_step(const occgrid_band_ctx* ctx, int64_t step_index, int have_
         j.d_peer_recs = ctx->d_peer_recs[slot]; j.d_peer_tiles = ctx->d_peer_tiles[slot];
         j.d_resv = ctx->d_resv; j.d_status = ctx->d_status;
     }
+    g_after_fused = (side && job) ? (cudaEvent_t)ctx->ev_fused : nullptr;
     rc = occgrid_band_raycast_route(&ctx->band_geom, ctx->d_recv[prev], ctx->n_bands, ctx->seg_capacity, have_pending,
                                     job ? &j : nullptr, ctx->d_grid, ctx->d_workspace, ctx->workspace_bytes, ctx->d_counters, stream);
+    g_after_fused = nullptr;
     if (rc != OCCGRID_OK) return rc;
-    if (job)
+    if (!job) return OCCGRID_OK;
+    if (side) {
+        OCC_CUDA_TRY(cudaStreamWaitEvent(side, (cudaEvent_t)ctx->ev_fused, 0));
         rc = occgrid_band_publish(ctx->n_bands, ctx->rank, ctx->d_resv, ctx->seg_capacity, ctx->d_peer_seg_counts[slot],
-                                  ctx->d_peer_flags, ctx->d_my_flags, (uint32_t)(step_index + 1), wait, ctx->d_status, stream);
-    return rc;
+                                  ctx->d_peer_flags, ctx->d_my_flags, (uint32_t)(step_index + 1), wait, ctx->d_status, side_stream);
+        if (rc != OCCGRID_OK) return rc;
+        OCC_CUDA_TRY(cudaEventRecord((cudaEvent_t)ctx->ev_published, side));
+        ctx->published_pending = 1;
+        return OCCGRID_OK;
+    }
+    return occgrid_band_publish(ctx->n_bands, ctx->rank, ctx->d_resv, ctx->seg_capacity, ctx->d_peer_seg_counts[slot],
+                                ctx->d_peer_flags, ctx->d_my_flags, (uint32_t)(step_index + 1), wait, ctx->d_status, stream);
+}
+
+// Make `stream` wait for the last publish + barrier issued on the side stream (before reading the map).
+int occgrid_band_join(occgrid_band_ctx* ctx, void* stream) {
+    if (!ctx) { set_last_error("band_join: NULL context"); return OCCGRID_E_ARG; }
+    if (ctx->published_pending) {
+        OCC_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)ctx->ev_published, 0));
+        ctx->published_pending = 0;
+    }
+    return OCCGRID_OK;
 }
 
 }  // extern "C"

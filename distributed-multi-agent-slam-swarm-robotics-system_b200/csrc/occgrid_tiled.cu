@@ -1246,7 +1246,8 @@ int tiled_prepare_poses(const occgrid_geom* geom, const PoseRec* d_recs, const i
 // The fused kernel: raycast the prepared batch (have_items) and, in between its work items, decode
 // and push the NEXT batch to the band owners (job != NULL); then resolve.
 int tiled_raycast_route(const occgrid_geom* geom, const PoseRec* d_recs, int have_items, const RouteJob* job,
-                        int8_t* d_grid, void* d_ws, size_t ws_bytes, int64_t max_records, uint64_t* d_counters, cudaStream_t st) {
+                        int8_t* d_grid, void* d_ws, size_t ws_bytes, int64_t max_records, uint64_t* d_counters, cudaStream_t st,
+                        cudaEvent_t after_fused) {
     const TiledLayout L = tiled_layout(geom, max_records, false);
     if (ws_bytes < L.total) { set_last_error("workspace too small for the band step"); return OCCGRID_E_WORKSPACE; }
     const TiledPtrs P = tiled_ptrs(L, d_ws);
@@ -1263,6 +1264,7 @@ int tiled_raycast_route(const occgrid_geom* geom, const PoseRec* d_recs, int hav
         RouteJob none = {};
         launch_raycast<false, false>(g, tg, P, d_recs, 1, P.stamps, d_counters, have_items, none, st);
     }
+    if (after_fused) OCC_CUDA_TRY(cudaEventRecord(after_fused, st));      // the routed batch is out: publishing may overlap the resolve
     if (have_items) {
         ProfileScope ps(K_TILE_RESOLVE, st);
         k_home_resolve<<<device_sm_count() * 8, kTT, 0, st>>>(g, tg, P.active, P.hdr, P.stamps, d_grid);

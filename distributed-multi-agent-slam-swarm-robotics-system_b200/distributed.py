@@ -217,6 +217,8 @@ class BandStep:
         j.seg_capacity = self.seg_cap
         j.d_resv, j.d_status = self._resv.data_ptr(), self._status.data_ptr()
         j.d_counters = self.grid._counters.data_ptr()
+        with torch.cuda.device(self.device):
+            self._side = torch.cuda.Stream(device=self.device)
         self._step = 0
         self._pending = False       # a routed batch sits in slot (_step - 1) % 2, not yet integrated
         self._keep = None           # tensors the in-flight job points at
@@ -262,7 +264,9 @@ class BandStep:
                 j.ordinal_base = self.rank * self.ordinal_stride
                 self._keep = (pk, agent_idx, drift, agent_table)
             job = self._job_ref
-        rc = self._lib.occgrid_band_step(self._ctx_ref, self._step, 1 if self._pending else 0, job, 1 if wait else 0, self._stream())
+        # the real barrier (wait) runs on a side stream, overlapping the resolve pass of this step
+        side = self._side.cuda_stream if wait else None
+        rc = self._lib.occgrid_band_step(self._ctx_ref, self._step, 1 if self._pending else 0, job, 1 if wait else 0, self._stream(), side)
         if rc:
             _native.check(rc, 'occgrid_band_step')
         if self._pending:
@@ -272,6 +276,7 @@ class BandStep:
             self._step += 1
 
     def check_status(self):
+        _native.check(self._lib.occgrid_band_join(self._ctx_ref, self._stream()), 'occgrid_band_join')
         st = int(self._status.item())
         if st:
             self._status.zero_()

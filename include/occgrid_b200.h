@@ -253,13 +253,19 @@ typedef struct occgrid_band_ctx {
     void*            d_workspace;
     size_t           workspace_bytes;
     uint64_t*        d_counters;
+    void*            ev_fused;             /* library-owned (created on first use with a side stream); start as NULL */
+    void*            ev_published;
+    int32_t          published_pending;    /* start as 0 */
 } occgrid_band_ctx;
 
 /* prepare (when a batch is pending) + raycast_route + publish (when `job` != NULL; job->n may be 0)
  * for step `step_index` (slot = step_index & 1, epoch = step_index + 1) in one host call; the job's
- * n_bands / src_rank / seg_capacity / peer pointers / d_resv / d_status are taken from `ctx`. */
-int occgrid_band_step(const occgrid_band_ctx* ctx, int64_t step_index, int have_pending,
-                      const occgrid_route_job* job /* NULL: flush only */, int wait, void* stream);
+ * n_bands / src_rank / seg_capacity / peer pointers / d_resv / d_status are taken from `ctx`.
+ * `side_stream` != NULL: publish + barrier run there, right after the fused kernel and concurrently
+ * with the resolve pass on `stream`; the next step (or occgrid_band_join) waits for them. */
+int occgrid_band_step(occgrid_band_ctx* ctx, int64_t step_index, int have_pending,
+                      const occgrid_route_job* job /* NULL: flush only */, int wait, void* stream, void* side_stream);
+int occgrid_band_join(occgrid_band_ctx* ctx, void* stream);
 
 int occgrid_band_publish(int n_bands, int rank, uint32_t* d_resv, int64_t seg_capacity,
                          uint32_t* const* d_peer_seg_counts /* DEVICE array: owner b's seg_counts of the slot */,

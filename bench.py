@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '25',
                  '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -250,7 +250,8 @@ def multi_gpu_parity(torch, dist, dev, world, rank, exchange):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=500,
+                    help='timed steps (default 500: ~0.17 s on one GPU, long enough for several clock samples)')
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--strategy', default='auto')
@@ -503,7 +504,21 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         e_ms = e0.elapsed_time(e1)
+        # the same call with the consumers' read of `.grid` every step (the reference's renderer reads it every
+        # frame, :512): 16 MiB more D2H per step
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r_upd = 0
+        r0.record()
+        for i in range(Ke):
+            g2.update_packets(host[i % POOL], agent_offsets=offs_np)
+            r_upd += g2.counters(reset=True)['updates']
+            _ = g2.grid
+        r1.record()
+        torch.cuda.synchronize()
+        r_ms = r0.elapsed_time(r1)
         result['e2e'] = {'value': e_upd / (e_ms * 1e-3), 'unit': UNIT,
+                         'with_grid_readback': {'value': r_upd / (r_ms * 1e-3), 'unit': UNIT, 'ms_per_step': r_ms / Ke,
+                                                'd2h_bytes_per_step': int(_native.N_COUNTERS * 8 + g2.grid_tensor.numel())},
                          'h2d_bytes_per_step': int(host[0].numel() + offs_np.nbytes),
                          'd2h_bytes_per_step': int(_native.N_COUNTERS * 8), 'steps': Ke,
                          'ms_per_step': e_ms / Ke,

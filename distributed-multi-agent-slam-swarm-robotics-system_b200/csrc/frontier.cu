@@ -104,6 +104,10 @@ k_frontier_count(const int8_t* __restrict__ g, int w, int h, unsigned int* __res
     if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
 }
 
+// One CTA, 16 consecutive block counts per thread and round: a 65 536-block grid (16384^2) is
+// scanned in four rounds instead of sixty-four.
+constexpr int kReserveItems = 16;
+
 __global__ void __launch_bounds__(1024)
 k_frontier_reserve(unsigned int* __restrict__ block_counts, int n_blocks, long long capacity,
                    long long* __restrict__ d_count, int* __restrict__ status) {
@@ -111,12 +115,18 @@ k_frontier_reserve(unsigned int* __restrict__ block_counts, int n_blocks, long l
     __shared__ unsigned int s_carry;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
-    for (int start = 0; start < n_blocks; start += blockDim.x) {
-        const int i = start + threadIdx.x;
-        const unsigned int v = i < n_blocks ? block_counts[i] : 0u;
+    for (int start = 0; start < n_blocks; start += 1024 * kReserveItems) {
+        const int i0 = start + (int)threadIdx.x * kReserveItems;
+        unsigned int v[kReserveItems], sum = 0;
+#pragma unroll
+        for (int j = 0; j < kReserveItems; ++j) { v[j] = (i0 + j < n_blocks) ? block_counts[i0 + j] : 0u; sum += v[j]; }
         unsigned int total;
-        const unsigned int ex = block_scan_excl(v, s_warp, &total);
-        if (i < n_blocks) block_counts[i] = s_carry + ex;
+        unsigned int run = s_carry + block_scan_excl(sum, s_warp, &total);
+#pragma unroll
+        for (int j = 0; j < kReserveItems; ++j) {
+            if (i0 + j < n_blocks) block_counts[i0 + j] = run;
+            run += v[j];
+        }
         __syncthreads();
         if (threadIdx.x == 0) s_carry += total;
         __syncthreads();
@@ -222,6 +232,7 @@ k_cluster_stats(const int2* __restrict__ xy, const long long* __restrict__ d_cou
 }
 
 // Single CTA: ordered compaction of roots with at least `min_cluster` cells; centroid = :233-237.
+constexpr int kEmitItems = 8;
 __global__ void __launch_bounds__(1024)
 k_cluster_emit(const long long* __restrict__ d_count, const int* __restrict__ label, const unsigned int* __restrict__ csize,
                const long long* __restrict__ sx, const long long* __restrict__ sy, int min_cluster, double ox, double oy,
@@ -232,18 +243,26 @@ k_cluster_emit(const long long* __restrict__ d_count, const int* __restrict__ la
     const long long n = *d_count;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
-    for (long long start = 0; start < n; start += blockDim.x) {
-        const long long i = start + threadIdx.x;
-        const bool keep = i < n && label[i] == (int)i && csize[i] >= (unsigned int)min_cluster;      // :228
+    for (long long start = 0; start < n; start += 1024 * kEmitItems) {          // kEmitItems consecutive candidates per thread
+        const long long i0 = start + (long long)threadIdx.x * kEmitItems;
+        unsigned int keep = 0;
+#pragma unroll
+        for (int j = 0; j < kEmitItems; ++j) {
+            const long long i = i0 + j;
+            if (i < n && label[i] == (int)i && csize[i] >= (unsigned int)min_cluster) keep |= 1u << j;              // :228
+        }
         unsigned int total;
-        const unsigned int pos = s_carry + block_scan_excl(keep ? 1u : 0u, s_warp, &total);
-        if (keep) {
+        unsigned int pos = s_carry + block_scan_excl(__popc(keep), s_warp, &total);
+        while (keep) {
+            const long long i = i0 + (__ffs(keep) - 1);
+            keep &= keep - 1;
             const double cnt = (double)csize[i];
             const double ax = OCC_DDIV((double)sx[i], cnt), ay = OCC_DDIV((double)sy[i], cnt);          // :235-236
             cluster_root[pos] = (int)i;
             cluster_size[pos] = (int)csize[i];
             centroids[2 * pos + 0] = OCC_DADD(ox, OCC_DMUL(OCC_DADD(ax, 0.5), res));                      // grid_to_world, :129
             centroids[2 * pos + 1] = OCC_DADD(oy, OCC_DMUL(OCC_DADD(ay, 0.5), res));
+            ++pos;
         }
         __syncthreads();
         if (threadIdx.x == 0) s_carry += total;

@@ -18,8 +18,9 @@
 // sort, points of a cell contiguous); a source point searches rings of cells outwards and stops
 // as soon as the best distance is within the scanned square (exact nearest neighbour, ties by
 // lowest target index).  Sums are reduced in a fixed order (per-CTA partials, then one CTA), so a
-// registration is reproducible bit for bit.  The whole iteration loop is enqueued without host
-// round trips: a `done` flag on the device turns the remaining launches into no-ops.
+// registration is reproducible bit for bit.  The whole iteration loop is ONE persistent cooperative
+// kernel (k_icp_loop): two grid barriers per iteration, no host round trips, early exit on
+// convergence.
 #include "common.cuh"
 #include "sincos_dd.cuh"
 
@@ -143,13 +144,6 @@ k_icp_fill(const double* __restrict__ tx, const double* __restrict__ ty, long lo
     }
 }
 
-__global__ void k_icp_init(IcpState* __restrict__ s) {
-    for (int i = 0; i < 16; ++i) { s->T[i] = (i % 5 == 0) ? 1.0 : 0.0; s->U[i] = s->T[i]; }
-    s->fitness = s->rmse = s->iterations = s->n_corr = 0.0;
-    s->mean[0] = s->mean[1] = s->mean[2] = s->mean[3] = 0.0;
-    s->done = 0;
-}
-
 // Fixed-order block sum of N doubles per thread into out[N] (thread 0 writes).
 template <int N>
 __device__ __forceinline__ void block_sum(double (&v)[N], double* out) {
@@ -211,109 +205,186 @@ __device__ __forceinline__ unsigned int icp_nearest(const IcpIndex& ix, double p
     return (best_pos != 0xffffffffu && best < r2) ? best_pos : 0xffffffffu;
 }
 
-// partial[b] = {count, sum d2, sum sx, sum sy, sum tx, sum ty}
-__global__ void __launch_bounds__(kIT)
-k_icp_assoc(const double* __restrict__ px, const double* __restrict__ py, long long n, const IcpIndex ix, double r, double r2,
-            const IcpState* __restrict__ st, unsigned int* __restrict__ corr, double* __restrict__ partial) {
-    if (st->done) return;
-    const long long i = (long long)blockIdx.x * kIT + threadIdx.x;
-    double v[6] = {0, 0, 0, 0, 0, 0};
-    if (i < n) {
-        const double x = px[i], y = py[i];
-        double d2;
-        const unsigned int p = icp_nearest(ix, x, y, r, r2, &d2);
-        corr[i] = p;
-        if (p != 0xffffffffu) { v[0] = 1.0; v[1] = d2; v[2] = x; v[3] = y; v[4] = ix.x[p]; v[5] = ix.y[p]; }
-    }
-    block_sum<6>(v, partial + (size_t)blockIdx.x * 6);
+// ---- the iteration loop: ONE persistent cooperative kernel --------------------------------------
+// Every CTA carries an identical copy of the registration state in shared memory: the per-block
+// partial sums go through global memory, and after a grid barrier EVERY CTA folds them in the same
+// fixed order and takes the same decisions (score, convergence, Umeyama update), so nothing has
+// to be broadcast and an iteration costs two grid barriers instead of five launches.  Work is
+// dealt in "virtual blocks" of kIT source points, so the partials — and with them every bit of the
+// result — do not depend on how many CTAs the device holds.
+struct IcpLoop {
+    double* px; double* py; long long n;          // working copy of the source cloud
+    IcpIndex ix;
+    double r, r2, rel_f, rel_r;
+    unsigned int* corr;
+    double* partial;                               // [n_vb][6] = {count, sum d2, sum sx, sum sy, sum tx, sum ty}
+    double* partial2;                              // [n_vb][2] = {sum dot, sum cross} of the demeaned pairs
+    int n_vb, max_iteration;
+    IcpState* state;
+    unsigned int* bar;                             // [0] arrivals (monotonic), [1] abort flag
+};
+
+constexpr unsigned long long kIcpBarrierTimeoutNs = 2000000000ull;
+
+__device__ __forceinline__ unsigned long long icp_global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 
-// One CTA.  Folds the partials in a fixed order, scores the registration and decides whether the
-// loop has converged (Registration.cpp: |d fitness| < rel_f && |d rmse| < rel_r).
-__global__ void __launch_bounds__(kIT)
-k_icp_eval(const double* __restrict__ partial, int n_partial, long long n_source, IcpState* __restrict__ st, double rel_f,
-           double rel_r, int first) {
-    if (st->done) return;
+// Cooperative launch keeps every CTA resident; the time-out only turns a would-be hang (a lost
+// CTA) into an error the host can report.
+__device__ __forceinline__ bool icp_grid_barrier(unsigned int* bar, unsigned int& target) {
+    __shared__ int s_ok;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        int ok = 1;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        const unsigned long long t0 = icp_global_ns();
+        unsigned int spins = 0;
+        while (*reinterpret_cast<volatile unsigned int*>(bar) < target) {
+            if (((++spins) & 1023u) == 0u &&
+                (reinterpret_cast<volatile unsigned int*>(bar)[1] || icp_global_ns() - t0 > kIcpBarrierTimeoutNs)) {
+                atomicExch(bar + 1, 1u);
+                ok = 0;
+                break;
+            }
+        }
+        __threadfence();
+        s_ok = ok;
+    }
+    __syncthreads();
+    return s_ok != 0;
+}
+
+// Folds the association partials in a fixed order, scores the registration and decides whether
+// the loop has converged (Registration.cpp: |d fitness| < rel_f && |d rmse| < rel_r).
+__device__ __forceinline__ void icp_fold_eval(const IcpLoop& p, IcpState* L, int first) {
     double v[6] = {0, 0, 0, 0, 0, 0};
-    for (int b = threadIdx.x; b < n_partial; b += kIT)
+    for (int b = threadIdx.x; b < p.n_vb; b += kIT)
 #pragma unroll
-        for (int j = 0; j < 6; ++j) v[j] = OCC_DADD(v[j], partial[(size_t)b * 6 + j]);
+        for (int j = 0; j < 6; ++j) v[j] = OCC_DADD(v[j], __ldcg(p.partial + (size_t)b * 6 + j));
     __shared__ double s_tot[6];
     block_sum<6>(v, s_tot);
     if (threadIdx.x == 0) {
         const double cnt = s_tot[0];
-        const double fit = n_source > 0 ? cnt / (double)n_source : 0.0;
+        const double fit = p.n > 0 ? cnt / (double)p.n : 0.0;
         const double rmse = cnt > 0.0 ? sqrt(s_tot[1] / cnt) : 0.0;
         if (!first) {
-            st->iterations += 1.0;
-            if (fabs(st->fitness - fit) < rel_f && fabs(st->rmse - rmse) < rel_r) st->done = 1;
+            L->iterations += 1.0;
+            if (fabs(L->fitness - fit) < p.rel_f && fabs(L->rmse - rmse) < p.rel_r) L->done = 1;
         }
-        st->fitness = fit; st->rmse = rmse; st->n_corr = cnt;
-        if (cnt > 0.0) { st->mean[0] = s_tot[2] / cnt; st->mean[1] = s_tot[3] / cnt; st->mean[2] = s_tot[4] / cnt; st->mean[3] = s_tot[5] / cnt; }
+        L->fitness = fit; L->rmse = rmse; L->n_corr = cnt;
+        if (cnt > 0.0) { L->mean[0] = s_tot[2] / cnt; L->mean[1] = s_tot[3] / cnt; L->mean[2] = s_tot[4] / cnt; L->mean[3] = s_tot[5] / cnt; }
     }
+    __syncthreads();
 }
 
-// partial2[b] = {sum(sx' tx' + sy' ty'), sum(sx' ty' - sy' tx')} over the demeaned pairs
-__global__ void __launch_bounds__(kIT)
-k_icp_cov(const double* __restrict__ px, const double* __restrict__ py, long long n, const IcpIndex ix,
-          const unsigned int* __restrict__ corr, const IcpState* __restrict__ st, double* __restrict__ partial2) {
-    if (st->done) return;
-    const long long i = (long long)blockIdx.x * kIT + threadIdx.x;
+// Folds the covariance partials and composes the update: theta = atan2(sum cross, sum dot).
+__device__ __forceinline__ void icp_fold_solve(const IcpLoop& p, IcpState* L) {
     double v[2] = {0, 0};
-    if (i < n) {
-        const unsigned int p = corr[i];
-        if (p != 0xffffffffu) {
-            const double sx = px[i] - st->mean[0], sy = py[i] - st->mean[1];
-            const double tx = ix.x[p] - st->mean[2], ty = ix.y[p] - st->mean[3];
-            v[0] = sx * tx + sy * ty;
-            v[1] = sx * ty - sy * tx;
-        }
+    for (int b = threadIdx.x; b < p.n_vb; b += kIT) {
+        v[0] = OCC_DADD(v[0], __ldcg(p.partial2 + (size_t)b * 2));
+        v[1] = OCC_DADD(v[1], __ldcg(p.partial2 + (size_t)b * 2 + 1));
     }
-    block_sum<2>(v, partial2 + (size_t)blockIdx.x * 2);
-}
-
-__global__ void __launch_bounds__(kIT)
-k_icp_solve(const double* __restrict__ partial2, int n_partial, IcpState* __restrict__ st) {
-    if (st->done) return;
-    double v[2] = {0, 0};
-    for (int b = threadIdx.x; b < n_partial; b += kIT) { v[0] = OCC_DADD(v[0], partial2[(size_t)b * 2]); v[1] = OCC_DADD(v[1], partial2[(size_t)b * 2 + 1]); }
     __shared__ double s_tot[2];
     block_sum<2>(v, s_tot);
     if (threadIdx.x == 0) {
         double U[16];
         for (int i = 0; i < 16; ++i) U[i] = (i % 5 == 0) ? 1.0 : 0.0;
-        if (st->n_corr > 0.0) {                                  // no correspondences -> identity (TransformationEstimation.cpp)
+        if (L->n_corr > 0.0) {                                   // no correspondences -> identity (TransformationEstimation.cpp)
             const double th = atan2(s_tot[1], s_tot[0]);
-            const double c = cos(th), s = sin(th);
-            U[0] = c; U[1] = -s; U[4] = s; U[5] = c;
-            U[3] = st->mean[2] - (c * st->mean[0] - s * st->mean[1]);
-            U[7] = st->mean[3] - (s * st->mean[0] + c * st->mean[1]);
+            const double c = cos(th), sn = sin(th);
+            U[0] = c; U[1] = -sn; U[4] = sn; U[5] = c;
+            U[3] = L->mean[2] - (c * L->mean[0] - sn * L->mean[1]);
+            U[7] = L->mean[3] - (sn * L->mean[0] + c * L->mean[1]);
         }
         double Tn[16];
         for (int i = 0; i < 4; ++i)
             for (int j = 0; j < 4; ++j) {
                 double a = 0.0;
-                for (int k = 0; k < 4; ++k) a += U[4 * i + k] * st->T[4 * k + j];
+                for (int k = 0; k < 4; ++k) a += U[4 * i + k] * L->T[4 * k + j];
                 Tn[4 * i + j] = a;
             }
-        for (int i = 0; i < 16; ++i) { st->T[i] = Tn[i]; st->U[i] = U[i]; }
+        for (int i = 0; i < 16; ++i) { L->T[i] = Tn[i]; L->U[i] = U[i]; }
+    }
+    __syncthreads();
+}
+
+// (optionally) moves this CTA's source points by the update, then finds their correspondences.
+__device__ __forceinline__ void icp_assoc_phase(const IcpLoop& p, const IcpState* L, bool apply) {
+    for (int vb = blockIdx.x; vb < p.n_vb; vb += gridDim.x) {
+        const long long i = (long long)vb * kIT + threadIdx.x;
+        double v[6] = {0, 0, 0, 0, 0, 0};
+        if (i < p.n) {
+            double x = p.px[i], y = p.py[i];
+            if (apply) {                                         // PointCloud::Transform
+                const double* U = L->U;
+                const double w = OCC_DADD(OCC_DADD(OCC_DMUL(U[12], x), OCC_DMUL(U[13], y)), U[15]);
+                const double nx = OCC_DDIV(OCC_DADD(OCC_DADD(OCC_DMUL(U[0], x), OCC_DMUL(U[1], y)), U[3]), w);
+                const double ny = OCC_DDIV(OCC_DADD(OCC_DADD(OCC_DMUL(U[4], x), OCC_DMUL(U[5], y)), U[7]), w);
+                x = nx; y = ny;
+                p.px[i] = x; p.py[i] = y;
+            }
+            double d2;
+            const unsigned int q = icp_nearest(p.ix, x, y, p.r, p.r2, &d2);
+            p.corr[i] = q;
+            if (q != 0xffffffffu) { v[0] = 1.0; v[1] = d2; v[2] = x; v[3] = y; v[4] = p.ix.x[q]; v[5] = p.ix.y[q]; }
+        }
+        block_sum<6>(v, p.partial + (size_t)vb * 6);
+    }
+}
+
+__device__ __forceinline__ void icp_cov_phase(const IcpLoop& p, const IcpState* L) {
+    for (int vb = blockIdx.x; vb < p.n_vb; vb += gridDim.x) {
+        const long long i = (long long)vb * kIT + threadIdx.x;
+        double v[2] = {0, 0};
+        if (i < p.n) {
+            const unsigned int q = p.corr[i];
+            if (q != 0xffffffffu) {
+                const double sx = p.px[i] - L->mean[0], sy = p.py[i] - L->mean[1];
+                const double tx = p.ix.x[q] - L->mean[2], ty = p.ix.y[q] - L->mean[3];
+                v[0] = sx * tx + sy * ty;
+                v[1] = sx * ty - sy * tx;
+            }
+        }
+        block_sum<2>(v, p.partial2 + (size_t)vb * 2);
     }
 }
 
 __global__ void __launch_bounds__(kIT)
-k_icp_apply(double* __restrict__ px, double* __restrict__ py, long long n, const IcpState* __restrict__ st) {
-    if (st->done) return;
-    const long long i = (long long)blockIdx.x * kIT + threadIdx.x;
-    if (i >= n) return;
-    const double* U = st->U;
-    const double x = px[i], y = py[i];
-    const double w = OCC_DADD(OCC_DADD(OCC_DMUL(U[12], x), OCC_DMUL(U[13], y)), U[15]);      // PointCloud::Transform
-    px[i] = OCC_DDIV(OCC_DADD(OCC_DADD(OCC_DMUL(U[0], x), OCC_DMUL(U[1], y)), U[3]), w);
-    py[i] = OCC_DDIV(OCC_DADD(OCC_DADD(OCC_DMUL(U[4], x), OCC_DMUL(U[5], y)), U[7]), w);
+k_icp_loop(const IcpLoop p) {
+    __shared__ IcpState L;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 16; ++i) { L.T[i] = (i % 5 == 0) ? 1.0 : 0.0; L.U[i] = L.T[i]; }
+        L.fitness = L.rmse = L.iterations = L.n_corr = 0.0;
+        L.mean[0] = L.mean[1] = L.mean[2] = L.mean[3] = 0.0;
+        L.done = 0;
+    }
+    __syncthreads();
+    unsigned int target = 0;
+    bool alive = true;
+    icp_assoc_phase(p, &L, false);
+    alive = icp_grid_barrier(p.bar, target);
+    if (alive) icp_fold_eval(p, &L, 1);
+    for (int it = 0; alive && it < p.max_iteration && !L.done; ++it) {
+        icp_cov_phase(p, &L);
+        if (!(alive = icp_grid_barrier(p.bar, target))) break;
+        icp_fold_solve(p, &L);
+        icp_assoc_phase(p, &L, true);
+        if (!(alive = icp_grid_barrier(p.bar, target))) break;
+        icp_fold_eval(p, &L, 0);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (!alive) L.iterations = -1.0;                       // a barrier timed out: the host reports it
+        *p.state = L;
+    }
 }
 
 struct IcpLayout {
-    size_t cnt, start, cursor, sx, sy, sidx, px, py, corr, partial, partial2, state, block_sums, total;
+    size_t cnt, start, cursor, sx, sy, sidx, px, py, corr, partial, partial2, state, block_sums, bar, total;
 };
 
 static IcpLayout icp_layout(int64_t target_points, int64_t source_points, int64_t cells) {
@@ -326,6 +397,7 @@ static IcpLayout icp_layout(int64_t target_points, int64_t source_points, int64_
     L.px = take((size_t)source_points * 8); L.py = take((size_t)source_points * 8); L.corr = take((size_t)source_points * 4);
     L.partial = take(blocks * 6 * 8); L.partial2 = take(blocks * 2 * 8); L.state = take(sizeof(IcpState));
     L.block_sums = take((size_t)((cells + kScanBlockIcp - 1) / kScanBlockIcp + 1) * 4);
+    L.bar = take(256);
     L.total = o;
     return L;
 }
@@ -367,11 +439,12 @@ int mapmerge_icp_register(const double* d_sx, const double* d_sy, int64_t n_sour
     double* partial2 = reinterpret_cast<double*>(ws + L.partial2);
     IcpState* state = reinterpret_cast<IcpState*>(ws + L.state);
     unsigned int* block_sums = reinterpret_cast<unsigned int*>(ws + L.block_sums);
+    unsigned int* bar = reinterpret_cast<unsigned int*>(ws + L.bar);
     cudaStream_t st = (cudaStream_t)stream;
     long long gt = (n_target + kIT - 1) / kIT;
     if (gt > device_sm_count() * 16) gt = device_sm_count() * 16;
     const int gs = (int)((n_source + kIT - 1) / kIT);
-    ProfileScope ps(K_ICP, st, 6 + 5 * max_iteration);
+    ProfileScope ps(K_ICP, st, 6);
     OCC_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)(cells + 1) * 4, st));
     OCC_CUDA_TRY(cudaMemcpyAsync(px, d_sx, (size_t)n_source * 8, cudaMemcpyDeviceToDevice, st));
     OCC_CUDA_TRY(cudaMemcpyAsync(py, d_sy, (size_t)n_source * 8, cudaMemcpyDeviceToDevice, st));
@@ -385,16 +458,28 @@ int mapmerge_icp_register(const double* d_sx, const double* d_sy, int64_t n_sour
     ix.min_x = min_x; ix.min_y = min_y; ix.cell = cell; ix.w = cells_w; ix.h = cells_h;
     ix.start = start; ix.x = sx; ix.y = sy; ix.idx = sidx;
     const double r = max_correspondence_distance, r2 = r * r;
-    k_icp_init<<<1, 1, 0, st>>>(state);
-    k_icp_assoc<<<gs, kIT, 0, st>>>(px, py, n_source, ix, r, r2, state, corr, partial);
-    k_icp_eval<<<1, kIT, 0, st>>>(partial, gs, n_source, state, relative_fitness, relative_rmse, 1);
-    for (int it = 0; it < max_iteration; ++it) {
-        k_icp_cov<<<gs, kIT, 0, st>>>(px, py, n_source, ix, corr, state, partial2);
-        k_icp_solve<<<1, kIT, 0, st>>>(partial2, gs, state);
-        k_icp_apply<<<gs, kIT, 0, st>>>(px, py, n_source, state);
-        k_icp_assoc<<<gs, kIT, 0, st>>>(px, py, n_source, ix, r, r2, state, corr, partial);
-        k_icp_eval<<<1, kIT, 0, st>>>(partial, gs, n_source, state, relative_fitness, relative_rmse, 0);
+    OCC_CUDA_TRY(cudaGetLastError());
+    // the iteration loop: one cooperative launch (the grid must be co-resident for its barriers)
+    static int resident_by_device[64] = {};
+    int dev = 0;
+    OCC_CUDA_TRY(cudaGetDevice(&dev));
+    int resident = (dev >= 0 && dev < 64) ? resident_by_device[dev] : 0;
+    if (resident == 0) {
+        int sms = 0, per_sm = 0;
+        OCC_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        OCC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_loop, kIT, 0));
+        if (sms <= 0 || per_sm <= 0) { set_last_error("mapmerge_icp_register: the loop kernel does not fit the device"); return OCCGRID_E_CUDA; }
+        resident = sms * per_sm;
+        if (dev >= 0 && dev < 64) resident_by_device[dev] = resident;
     }
+    IcpLoop lp;
+    lp.px = px; lp.py = py; lp.n = n_source; lp.ix = ix; lp.r = r; lp.r2 = r2;
+    lp.rel_f = relative_fitness; lp.rel_r = relative_rmse;
+    lp.corr = corr; lp.partial = partial; lp.partial2 = partial2; lp.n_vb = gs; lp.max_iteration = max_iteration;
+    lp.state = state; lp.bar = bar;
+    OCC_CUDA_TRY(cudaMemsetAsync(bar, 0, 256, st));
+    void* args[] = {&lp};
+    OCC_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_icp_loop, dim3((unsigned)(gs < resident ? gs : resident)), dim3(kIT), args, 0, st));
     OCC_CUDA_TRY(cudaGetLastError());
     OCC_CUDA_TRY(cudaMemcpyAsync(d_result, state, 20 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     return OCCGRID_OK;

@@ -478,16 +478,20 @@ class OccupancyGrid:
                 }
         return self._fr
 
+    def _launch_frontiers(self, f):
+        with torch.cuda.device(self.device):
+            rc = self._lib.occgrid_frontiers(self.grid_tensor.data_ptr(), self.size, self.size, f['xy'].data_ptr(), f['cap'],
+                                             f['count'].data_ptr(), f['status'].data_ptr(), f['ws'].data_ptr(), f['ws'].numel(),
+                                             self._stream())
+            _native.check(rc, 'occgrid_frontiers')
+
     def _detect_frontiers(self):
         """Runs the frontier stencil on the device; returns (buffers, count)."""
         cap = max(1 << 16, self.size * 8)
         while True:
             f = self._frontier_buffers(cap)
+            self._launch_frontiers(f)
             with torch.cuda.device(self.device):
-                rc = self._lib.occgrid_frontiers(self.grid_tensor.data_ptr(), self.size, self.size, f['xy'].data_ptr(), f['cap'],
-                                                 f['count'].data_ptr(), f['status'].data_ptr(), f['ws'].data_ptr(), f['ws'].numel(),
-                                                 self._stream())
-                _native.check(rc, 'occgrid_frontiers')
                 host = torch.cat([f['count'], f['status'].to(torch.int64)]).cpu().tolist()
             if host[1] & 1:                       # more frontier cells than the buffer holds: grow and redo
                 f['status'].zero_()
@@ -503,15 +507,26 @@ class OccupancyGrid:
         return [(int(x), int(y)) for x, y in xy]
 
     def _cluster(self, min_cluster=FRONTIER_MIN_CLUSTER):
-        f, n = self._detect_frontiers()
-        with torch.cuda.device(self.device):
-            rc = self._lib.occgrid_frontier_clusters(
-                f['xy'].data_ptr(), f['count'].data_ptr(), f['cap'], self.size, int(min_cluster), self.ox, self.oy, self.res,
-                f['label'].data_ptr(), f['root'].data_ptr(), f['size'].data_ptr(), f['cent'].data_ptr(), f['ncl'].data_ptr(),
-                f['ws'].data_ptr(), f['ws'].numel(), self._stream())
-            _native.check(rc, 'occgrid_frontier_clusters')
-            k = int(f['ncl'].item())
-        return f, n, k
+        """Stencil + clustering enqueued back to back (the cluster kernels take the frontier count
+        from device memory), then ONE host read of (count, status, clusters)."""
+        cap = max(1 << 16, self.size * 8)
+        if self._fr is not None:
+            cap = max(cap, self._fr['cap'])
+        while True:
+            f = self._frontier_buffers(cap)
+            self._launch_frontiers(f)
+            with torch.cuda.device(self.device):
+                rc = self._lib.occgrid_frontier_clusters(
+                    f['xy'].data_ptr(), f['count'].data_ptr(), f['cap'], self.size, int(min_cluster), self.ox, self.oy, self.res,
+                    f['label'].data_ptr(), f['root'].data_ptr(), f['size'].data_ptr(), f['cent'].data_ptr(), f['ncl'].data_ptr(),
+                    f['ws'].data_ptr(), f['ws'].numel(), self._stream())
+                _native.check(rc, 'occgrid_frontier_clusters')
+                host = torch.cat([f['count'], f['status'].to(torch.int64), f['ncl']]).cpu().tolist()
+            if host[1] & 1:                       # the list overflowed (count was forced to 0): grow and redo
+                f['status'].zero_()
+                cap *= 4
+                continue
+            return f, int(host[0]), int(host[2])
 
     def cluster_frontiers(self, frontier_cells=None):
         """:199-231 — 4-connected components of the current frontier set, in the reference's

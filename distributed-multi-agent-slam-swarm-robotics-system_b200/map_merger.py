@@ -125,11 +125,15 @@ class MapMerger:
                 n for b, n in ((1, 'point capacity'), (2, 'voxel lattice capacity'),
                             (4, 'chain kernel aborted (a grid barrier timed out)')) if st & b))
 
-    def _device_grid(self, msg):
+    def _device_grid(self, msg, async_upload=False):
         data = msg.data
         h, w = int(msg.info.height), int(msg.info.width)
         if isinstance(data, torch.Tensor):
-            t = data.to(self.device, dtype=torch.int8).reshape(h, w)
+            # async_upload: pinned host grids upload without a sync per grid (only the batch path
+            # asks for it: it reads the occupied counts back before returning, which orders every
+            # upload before the caller can touch the source again)
+            t = data.to(self.device, dtype=torch.int8,
+                        non_blocking=bool(async_upload and not data.is_cuda and data.is_pinned())).reshape(h, w)
         else:
             t = torch.from_numpy(np.ascontiguousarray(np.asarray(data, dtype=np.int8).reshape(h, w))).to(self.device)
         return t.contiguous()
@@ -260,6 +264,8 @@ class MapMerger:
             _native.check(rc, 'mapmerge_icp_register')
             r = res.cpu().numpy()
             self._check_status()
+            if r[18] < 0:                                   # a grid barrier of the loop kernel timed out
+                raise OccGridError('register: the ICP loop kernel was aborted (grid barrier time-out)')
         self.last_registration = SimpleNamespace(transformation=r[:16].reshape(4, 4).copy(), fitness=float(r[16]),
                                                  inlier_rmse=float(r[17]), iterations=int(r[18]), correspondences=int(r[19]))
         return self.last_registration
@@ -330,7 +336,7 @@ class MapMerger:
                     and g.device == self.device:
                 out.append(g)
             else:
-                out.append(self._device_grid(make_grid_msg(g, g.shape[1], g.shape[0], 0.0, 0, 0)))
+                out.append(self._device_grid(make_grid_msg(g, g.shape[1], g.shape[0], 0.0, 0, 0), async_upload=True))
         return out
 
     @staticmethod

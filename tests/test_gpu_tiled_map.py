@@ -92,6 +92,29 @@ def test_fused_swarm_map_single_rank():
         tmap.update_packets(sess['packets'][:40_000], agent_offsets=sess['agent_offsets'], agent_idx=sess['agent_idx'][:40_000])
 
 
+def test_fused_swarm_map_full_size_config2():
+    """BASELINE config 2 at full size through the fused band step (world = 1): 2.5e6 packets in 5
+    batches of 5e5 into 4096^2, equal to the C oracle, and the update count matches."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from occgrid_b200 import simulation_tools as st
+    from occgrid_b200.distributed import TiledSwarmMap
+    from oracle import c_oracle
+    size, origin, n, b = 4096, (-102.4, -102.4), 2_500_000, 500_000
+    sess = st.generate_session(n_agents=64, n_packets=n, grid_size=size, origin=origin, seed=42)
+    tmap = TiledSwarmMap(size, 0.05, origin[0], origin[1], max_batch=b, exchange='p2p')
+    for i in range(n // b):
+        sl = slice(i * b, (i + 1) * b)
+        tmap.update_packets(sess['packets'][sl], agent_offsets=sess['agent_offsets'], agent_idx=sess['agent_idx'][sl])
+    got = tmap.gather_grid()
+    want = np.full((size, size), -1, np.int8)
+    c = c_oracle.integrate_packets(sess['packets'], want, origin[0], origin[1], 0.05, agent_offsets=sess['agent_offsets'],
+                                   agent_idx=sess['agent_idx'])
+    assert np.array_equal(got, want)
+    cn = tmap.counters()
+    assert cn['owned_updates'] == c['updates'] and cn['beams'] == c['beams'] == 4 * n
+
+
 def _emulated_band_steps(world, size, origin, max_batch):
     """`world` logical ranks on ONE GPU: plain receive buffers linked by pointer (peer-mapped over
     NVLink in production), publish without the wait (the steps are issued one rank after another on

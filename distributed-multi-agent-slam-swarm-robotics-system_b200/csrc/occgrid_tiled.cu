@@ -34,7 +34,13 @@ namespace occ {
 constexpr int kTile = 64;            // home-tile side in cells
 constexpr int kTileShift = 6;
 constexpr int kTT = 256;             // threads per CTA
-constexpr int kChunkPk = 2048;       // packets per work item
+// Packets per work item: chosen per batch by k_tile_plan so that the persistent raycast CTAs get
+// ~kItemsPerCta items each: a small batch cut into 2 048-packet items would leave most CTAs without
+// work, while many small items cost more than they balance (every item re-reads and flushes its
+// tile's hot cells).
+constexpr int kChunkPk = 2048;       // largest work item
+constexpr int kChunkMin = 256;       // smallest: one packet per thread
+constexpr int kItemsPerCta = 3;       // raycast of configs[1]: 3 -> 0.202 ms, 5 -> 0.220, 8 -> 0.235, 12 -> 0.263
 constexpr int kMaxStrideT = 64;
 constexpr int kMaxWindowBytes = 100 * 1024;   // smem window budget (two CTAs per SM at least)
 
@@ -395,18 +401,31 @@ __global__ void __launch_bounds__(1024)
 k_tile_plan(unsigned int* __restrict__ tile_count, unsigned int* __restrict__ tile_offset,
             unsigned int* __restrict__ tile_cursor, uint4* __restrict__ items, unsigned int max_items,
             const unsigned int* __restrict__ active, unsigned long long max_records, TilePlanHeader* __restrict__ hdr,
-            uint64_t* counters) {
+            uint64_t* counters, unsigned int target_items) {
     __shared__ unsigned int s_warp[2][33];
     __shared__ unsigned int s_carry[2];
+    __shared__ unsigned int s_total;
     if (threadIdx.x < 2) s_carry[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_total = 0;
     __syncthreads();
     const int n_active = (int)hdr->active_count;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // records of this batch -> packets per work item (a multiple of kChunkMin)
+    {
+        unsigned int mine = 0;
+        for (int i = threadIdx.x; i < n_active; i += blockDim.x) mine += tile_count[active[i]];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if (lane == 0 && mine) atomicAdd(&s_total, mine);
+    }
+    __syncthreads();
+    unsigned int chunk_pk = (s_total / target_items + kChunkMin) / kChunkMin * kChunkMin;
+    chunk_pk = chunk_pk > (unsigned int)kChunkPk ? (unsigned int)kChunkPk : chunk_pk;
     for (int start = 0; start < n_active; start += blockDim.x) {
         const int i = start + threadIdx.x;
         const unsigned int t = i < n_active ? active[i] : 0u;
         const unsigned int cnt = i < n_active ? tile_count[t] : 0u;
-        unsigned int v[2] = {cnt, (cnt + kChunkPk - 1) / kChunkPk};
+        unsigned int v[2] = {cnt, (cnt + chunk_pk - 1) / chunk_pk};
         unsigned int ex[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -432,8 +451,8 @@ k_tile_plan(unsigned int* __restrict__ tile_count, unsigned int* __restrict__ ti
             tile_cursor[t] = 0u;
             tile_count[t] = 0u;
             for (unsigned int j = 0; j < v[1]; ++j) {
-                const unsigned int b = off + j * kChunkPk;
-                const unsigned int e = min(off + cnt, b + kChunkPk);
+                const unsigned int b = off + j * chunk_pk;
+                const unsigned int e = min(off + cnt, b + chunk_pk);
                 if (item0 + j < max_items) items[item0 + j] = make_uint4(t, b, e, 0u);
             }
         }
@@ -590,21 +609,22 @@ __device__ __forceinline__ void smem_red(unsigned int addr, unsigned int v) {
 }
 
 // Fast path of draw_beam_smem / count_beam_smem: both end points inside the window, dmaj <= 32.
-// win = 32-bit shared-space address of the window; (x, y) window-local start cell.
+// a = 32-bit shared-space BYTE address of the start cell (computed once per packet), dmaj =
+// max(|ddx|, |ddy|), mask_tab = shared-space address of the walk-mask table.
 //   kAdd = false: atomicMax of `v_free` on every cell but the last, `v_free | 1` on the last if hit
 //   kAdd = true : += 1 on every cell but the last, += 0x10000 on the last if hit (count mode)
+// After dmaj steps the running address IS the end cell, so the hit stamp needs no address of its own.
 template <bool kAdd>
-__device__ __forceinline__ void walk_beam_masked(unsigned int win, int pitch, int x, int y, int ddx, int ddy,
-                                                 unsigned int v_free, bool hit, bool skip_first, const unsigned int* s_mask) {
+__device__ __forceinline__ void walk_beam_masked(unsigned int a, int pitch, int ddx, int ddy, int dmaj,
+                                                 unsigned int v_free, bool hit, bool skip_first, unsigned int mask_tab) {
     const int dx = abs(ddx), dy = abs(ddy);
     const bool xmajor = dx >= dy;
-    const int dmaj = xmajor ? dx : dy, dmin = xmajor ? dy : dx;
+    const int dmin = xmajor ? dy : dx;
     const int sx4 = ddx > 0 ? 4 : -4;
     const int sy4 = (ddy > 0 ? pitch : -pitch) * 4;
     const int step_maj = xmajor ? sx4 : sy4, step_min = xmajor ? sy4 : sx4;
-    unsigned int mask = s_mask[dmaj * (dmaj + 1) / 2 + dmin];
-    unsigned int a = win + (unsigned int)(y * pitch + x) * 4u;
-    const unsigned int a_end = a + (unsigned int)((ddy * pitch + ddx) * 4);
+    unsigned int mask;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(mask) : "r"(mask_tab + (unsigned int)(dmaj * (dmaj + 1) / 2 + dmin) * 4u));
     int rem = dmaj;                                   // cells still to mark FREE (the end cell is not one of them)
     if (rem > 0) {
         if (!skip_first) smem_red<kAdd>(a, v_free);   // the start cell is overwritten by a later beam of the packet otherwise
@@ -637,7 +657,16 @@ __device__ __forceinline__ void walk_beam_masked(unsigned int win, int pitch, in
         a += step_maj + ((mask & 1u) ? step_min : 0);
         mask >>= 1;
     }
-    if (hit && !(dmaj == 0 && skip_first && !kAdd)) smem_red<kAdd>(a_end, kAdd ? 0x10000u : (v_free | 1u));
+    if (hit && !(dmaj == 0 && skip_first && !kAdd)) smem_red<kAdd>(a, kAdd ? 0x10000u : (v_free | 1u));
+}
+
+// The exact re-evaluation of a beam's end cell, out of line: it runs for a few beams in a million
+// and must not sit in the instruction stream of the walk.  Re-reads the pose from the record.
+__device__ __noinline__ bool exact_end_cell_of(double ox, double oy, double res, const PoseRec* __restrict__ rec, int sensor,
+                                                double range, int* x1, int* y1) {
+    Geom g;
+    g.ox = ox; g.oy = oy; g.res = res;
+    return exact_end_cell(g, rec->rx, rec->ry, (double)rec->yaw, sensor, range, LibSinCos(), x1, y1);
 }
 
 // ---- route work item (multi-GPU row bands, fused into the persistent raycast kernel) -----------
@@ -887,46 +916,60 @@ __device__ __noinline__ RouteStats route_item(const RouteJob& J, unsigned int it
 }
 
 template <bool kCounts, bool kRoute>
-__global__ void __launch_bounds__(kTT, 3)      // three CTAs per SM: 80 registers
+#ifndef OCC_RAYCAST_CTAS
+#define OCC_RAYCAST_CTAS 3
+#endif
+__global__ void __launch_bounds__(kTT, kRoute ? 3 : OCC_RAYCAST_CTAS)
 k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHeader* __restrict__ hdr,
                const unsigned int* __restrict__ bins, const PoseRec* __restrict__ recs, int ordinals_in_records,
                unsigned int* __restrict__ stamps, uint64_t* counters, int have_items, const RouteJob job) {
-    extern __shared__ unsigned int s_win[];
-    __shared__ unsigned int s_item;
-    __shared__ unsigned long long s_acc[6 * 32];
+    extern __shared__ __align__(16) unsigned int s_win[];
+    unsigned long long* const s_acc = reinterpret_cast<unsigned long long*>(s_win);   // [6 * 32], used once the window is dead
     __shared__ RouteSmem s_route;
     __shared__ unsigned int s_mask[kMaskEntries];
     __shared__ RouteJob s_job;                     // the route path reads the job from shared memory, not from a stack copy
     if (kRoute && threadIdx.x == 0) s_job = job;
     build_walk_masks(s_mask);                      // both visible after the first __syncthreads of the loop below
     const unsigned int win_addr = (unsigned int)__cvta_generic_to_shared(s_win);
+    const unsigned int mask_tab = (unsigned int)__cvta_generic_to_shared(s_mask);
     const unsigned int n_items = have_items ? hdr->n_items : 0u;
     // Unified queue: raycast items of THIS batch and route items of the NEXT one, interleaved in
     // proportion, so the NVLink traffic is spread over the whole kernel and overlaps the walks.
     const unsigned int n_route = kRoute ? job.n_route_items : 0u;
     const unsigned int n_total = n_items + n_route;
     const int side = tg.win_side, pitch = tg.pitch, words = side * pitch;
-    unsigned long long c[3] = {0, 0, 0};     // updates, slowpath, owned updates
+    // updates, slowpath, owned updates of this thread: 32 bits are ample (a launch spreads at most
+    // 2^31 packets x 4 beams x <= 33 cells over >= 37 888 threads), widened when the kernel ends
+    unsigned int c[3] = {0u, 0u, 0u};
     RouteStats rs = {0u, 0u};                // routed share, packed (see RouteStats)
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_item = atomicAdd(&hdr->work_counter, 1u);
-        if (!kRoute)
-            for (int i = threadIdx.x; i < words; i += kTT) s_win[i] = 0u;
-        __syncthreads();
-        unsigned int it = s_item;
+    // The queue position of the NEXT item is fetched while the current one is processed (the
+    // atomic's round trip to L2 is off the critical path), and the window is zeroed by the flush
+    // itself: an item costs two CTA barriers and no separate clearing pass.
+    __shared__ unsigned int s_next[2];
+    if (threadIdx.x == 0) s_next[0] = atomicAdd(&hdr->work_counter, 1u);
+    for (int i = threadIdx.x; i < words; i += kTT) s_win[i] = 0u;
+    bool window_dirty = false;               // a route item used the window as scratch
+    __syncthreads();
+    for (int turn = 0;; turn ^= 1) {
+        unsigned int it = s_next[turn];
         if (it >= n_total) break;
+        if (threadIdx.x == 0) s_next[turn ^ 1] = atomicAdd(&hdr->work_counter, 1u);   // read after this item's barriers
         if (kRoute) {
             // r(i) = floor(i * n_route / n_total) route items precede queue position i
             const unsigned int r0 = (unsigned int)(((unsigned long long)it * n_route) / n_total);
             const unsigned int r1 = (unsigned int)(((unsigned long long)(it + 1) * n_route) / n_total);
             if (r1 > r0) {
                 rs = route_item(s_job, r0, s_win, s_route, rs);
+                window_dirty = true;
+                __syncthreads();
                 continue;
             }
             it -= r0;
-            for (int i = threadIdx.x; i < words; i += kTT) s_win[i] = 0u;
-            __syncthreads();
+            if (window_dirty) {
+                for (int i = threadIdx.x; i < words; i += kTT) s_win[i] = 0u;
+                window_dirty = false;
+                __syncthreads();
+            }
         }
         const uint4 item = items[it];
         const int ttx = item.x % tg.tiles_x, tty = item.x / tg.tiles_x;
@@ -935,52 +978,72 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
         const int wy0 = g.win_y0 - tg.pad + (tty << kTileShift) - tg.reach;
         for (unsigned int r = item.y + threadIdx.x; r < item.z; r += kTT) {
             const unsigned int idx = bins[r];
-            const PoseRec rec = recs[idx];
+            const PoseRec* __restrict__ rp = recs + idx;
+            const PoseRec rec = *rp;
             const unsigned int k = ordinals_in_records ? rec.k : idx;   // packet ordinal in this batch
-            PacketFrame F;
-            packet_frame(g, rec.rx, rec.ry, (double)rec.yaw, LibSinCos(), &F);
+            LeanFrame F;                                                 // the start cell is the one this packet was binned by
+            lean_frame(g, rec.rx, rec.ry, (double)rec.yaw, LibSinCos(), &F);
             const bool owned = F.x0 >= g.win_x0 && F.x0 < g.win_x0 + g.win_w && F.y0 >= g.win_y0 && F.y0 < g.win_y0 + g.win_h;
             const int lx = F.x0 - wx0, ly = F.y0 - wy0;
-            const unsigned int us = (unsigned int)side;
+            // how far a beam may reach from the start cell and stay on the table-driven path:
+            // inside the window on every side, and no longer than the mask table (negative = never)
+            const int margin = min(min(min(lx, ly), min(side - 1 - lx, side - 1 - ly)), kMaskMaxLen);
+            const unsigned int a0 = win_addr + (unsigned int)(ly * pitch + lx) * 4u;
+            unsigned int pc = 0;                                         // cells of this packet's beams
             bool later_writes_first = false;
             // ONE copy of the expansion + walk code, looped over the four sensors (last sensor first:
             // only the last beam that writes the shared start cell has to touch it).  Unrolling it
-            // four times made the kernel 110 KB of SASS and instruction-fetch bound.
+            // four times made the kernel 110 KB of SASS and instruction-fetch bound.  The direction
+            // of sensor 3 (yaw - pi/2, :66) is (sin, -cos); every further sensor is a quarter turn back.
+            double cs_next = F.si, sn_next = -F.ci;
 #pragma unroll 1
             for (int s = 3; s >= 0; --s) {
-                Beam b;
-                expand_beam_of(g, F, s, s == 0 ? rec.d[0] : (s == 1 ? rec.d[1] : (s == 2 ? rec.d[2] : rec.d[3])), LibSinCos(), &b);
-                if (!b.valid) continue;
-                const int cells = beam_cells(b);
-                c[0] += cells;
-                c[1] += b.slow;
-                if (owned) c[2] += cells;
-                const int ddx = b.x1 - b.x0, ddy = b.y1 - b.y0;
-                const bool fast = (unsigned int)lx < us && (unsigned int)ly < us && (unsigned int)(lx + ddx) < us &&
-                                  (unsigned int)(ly + ddy) < us && cells <= kMaskMaxLen + 1;
+                const double cs = cs_next, sn = sn_next;
+                cs_next = sn; sn_next = -cs;
+                double range;
+                const bool hit = beam_hit(s == 0 ? rec.d[0] : (s == 1 ? rec.d[1] : (s == 2 ? rec.d[2] : rec.d[3])), &range);
+                const double qx = OCC_DFMA(range, cs, F.q0x), qy = OCC_DFMA(range, sn, F.q0y);
+                int x1, y1;
+                if (near_cell_boundary(qx, F.tolx) || near_cell_boundary(qy, F.toly)) {
+                    c[1] += 1u;
+                    if (!exact_end_cell_of(g.ox, g.oy, g.res, rp, s, range, &x1, &y1)) continue;
+                } else {
+                    x1 = trunc_cell(qx);
+                    y1 = trunc_cell(qy);
+                }
+                const int ddx = x1 - F.x0, ddy = y1 - F.y0;
+                const int dmaj = max(abs(ddx), abs(ddy));                // the beam has dmaj + 1 cells
+                pc += (unsigned int)dmaj + 1u;
                 if (kCounts) {
-                    if (fast) walk_beam_masked<true>(win_addr, pitch, lx, ly, ddx, ddy, 1u, b.hit != 0, false, s_mask);
-                    else count_beam_smem(s_win, side, pitch, lx, ly, ddx, ddy, b.hit != 0);
+                    if (dmaj <= margin) walk_beam_masked<true>(a0, pitch, ddx, ddy, dmaj, 1u, hit, false, mask_tab);
+                    else count_beam_smem(s_win, side, pitch, lx, ly, ddx, ddy, hit);
                 } else {
                     const unsigned int stamp = (k * 4u + (unsigned int)s + 1u) << 1;
-                    if (fast) walk_beam_masked<false>(win_addr, pitch, lx, ly, ddx, ddy, stamp, b.hit != 0, later_writes_first, s_mask);
-                    else draw_beam_smem(s_win, side, pitch, lx, ly, ddx, ddy, stamp, b.hit != 0, later_writes_first);
+                    if (dmaj <= margin) walk_beam_masked<false>(a0, pitch, ddx, ddy, dmaj, stamp, hit, later_writes_first, mask_tab);
+                    else draw_beam_smem(s_win, side, pitch, lx, ly, ddx, ddy, stamp, hit, later_writes_first);
                 }
-                later_writes_first = later_writes_first || (cells > 1 || b.hit);
+                later_writes_first = later_writes_first || dmaj > 0 || hit;
             }
+            c[0] += pc;
+            if (owned) c[2] += pc;
         }
         __syncthreads();
-        // flush: window rows are contiguous in the stamp plane -> coalesced reductions
-        const int lx_lo = max(0, g.win_x0 - wx0), lx_hi = min(side, g.win_x0 + g.win_w - wx0);
-        const int ly_lo = max(0, g.win_y0 - wy0), ly_hi = min(side, g.win_y0 + g.win_h - wy0);
-        if (lx_hi > lx_lo) {
+        // flush + clear: window rows are contiguous in the stamp plane -> coalesced reductions.  Every
+        // touched word is zeroed on the way out (cells outside the grid window included: they are
+        // dropped, not flushed), so the next item finds a clean window.
+        {
+            const int lx_lo = max(0, g.win_x0 - wx0), lx_hi = min(side, g.win_x0 + g.win_w - wx0);
+            const int ly_lo = max(0, g.win_y0 - wy0), ly_hi = min(side, g.win_y0 + g.win_h - wy0);
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-            for (int ly = ly_lo + warp; ly < ly_hi; ly += kTT / 32) {          // one warp per window row
-                const unsigned int* row = s_win + ly * pitch;
+            for (int ly = warp; ly < side; ly += kTT / 32) {                   // one warp per window row
+                unsigned int* row = s_win + ly * pitch;
+                const bool row_in = ly >= ly_lo && ly < ly_hi;
                 unsigned int* out = stamps + (size_t)(wy0 + ly - g.win_y0) * g.win_w + (wx0 - g.win_x0);
-                for (int lx = lx_lo + lane; lx < lx_hi; lx += 32) {
+                for (int lx = lane; lx < side; lx += 32) {
                     const unsigned int v = row[lx];
                     if (!v) continue;
+                    row[lx] = 0u;
+                    if (!(row_in && lx >= lx_lo && lx < lx_hi)) continue;
                     if (kCounts)     // {miss, hit} int32 pair of the cell: one 64-bit add (the halves cannot carry into each other)
                         atomicAdd(reinterpret_cast<unsigned long long*>(stamps) + ((size_t)(wy0 + ly - g.win_y0) * g.win_w + (wx0 - g.win_x0) + lx),
                                   ((unsigned long long)(v >> 16) << 32) | (unsigned long long)(v & 0xffffu));
@@ -989,6 +1052,7 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
                 }
             }
         }
+        __syncthreads();
     }
     if (kRoute && job.counters) {
         __syncthreads();
@@ -1071,7 +1135,7 @@ static TiledLayout tiled_layout(const occgrid_geom* geom, int64_t max_records, b
     TiledLayout L;
     const TileGeom tg = tile_geom(geom);
     L.max_records = (unsigned long long)max_records;
-    unsigned long long items = L.max_records / kChunkPk + (unsigned long long)tg.n_tiles + 1;
+    unsigned long long items = L.max_records / kChunkMin + (unsigned long long)tg.n_tiles + 1;
     if (items > L.max_records + 1) items = L.max_records + 1;
     L.max_items = (unsigned int)items;
     size_t o = 0;
@@ -1157,6 +1221,16 @@ static int launch_raycast(const Geom& g, const TileGeom& tg, const TiledPtrs& P,
     return OCCGRID_OK;
 }
 
+// Work items the plan aims for: kItemsPerCta per persistent raycast CTA (three CTAs per SM).
+static unsigned int plan_target_items() {
+    static unsigned int forced = 0xffffffffu;          // OCC_PLAN_ITEMS_PER_CTA: tuning hook
+    if (forced == 0xffffffffu) {
+        const char* e = getenv("OCC_PLAN_ITEMS_PER_CTA");
+        forced = e ? (unsigned int)atoi(e) : 0u;
+    }
+    return (unsigned int)device_sm_count() * 3u * (forced ? forced : (unsigned int)kItemsPerCta);
+}
+
 static int grid_chunks(long long n_chunks) {
     long long b = n_chunks < 1 ? 1 : n_chunks;
     const long long cap = (long long)device_sm_count() * 8;
@@ -1194,7 +1268,7 @@ int integrate_tiled(const occgrid_geom* geom, const uint8_t* d_packets, const Po
     {
         ProfileScope ps(K_TILE_SCAN, st);
         k_tile_plan<<<1, 1024, 0, st>>>(P.tile_count, P.tile_offset, P.tile_cursor, P.items, L.max_items, P.active, L.max_records, P.hdr,
-                                        d_counters);
+                                        d_counters, plan_target_items());
     }
     {
         ProfileScope ps(K_TILE_SCATTER, st);
@@ -1233,7 +1307,7 @@ int tiled_prepare_poses(const occgrid_geom* geom, const PoseRec* d_recs, const i
     {
         ProfileScope ps(K_TILE_SCAN, st);
         k_tile_plan<<<1, 1024, 0, st>>>(P.tile_count, P.tile_offset, P.tile_cursor, P.items, L.max_items, P.active, L.max_records, P.hdr,
-                                        d_counters);
+                                        d_counters, plan_target_items());
     }
     {
         ProfileScope ps(K_TILE_SCATTER, st);

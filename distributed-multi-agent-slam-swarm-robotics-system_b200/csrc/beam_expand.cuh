@@ -207,91 +207,6 @@ OCC_HD void expand_beam_of(const Geom& g, const PacketFrame& F, int s, float dis
     expand_beam(g, F.rx, F.ry, F.ryaw, F.x0, F.y0, F.origin_ok, s, dist, sn, cs, F.tolx, F.toly, fsc, out);
 }
 
-// ---- lean form for packets already binned by their start cell ------------------------------------
-// The tiled kernels only ever expand packets whose start cell was computed (exactly) when they
-// were binned, so the per-beam work can be cut to the bone:
-//   * end quotient = fma(range, cos * 1/res, q0) with q0 = (r - o) * 1/res the packet's own
-//     screened start quotient: two fp64 instructions per beam instead of eight;
-//   * anything doubtful is re-evaluated exactly: a quotient within the screening tolerance of an
-//     integer, and EVERY beam of a packet whose start cell is so close to the +-2^30 cell limit
-//     that an end point could cross it (the tolerances of such a packet are set to +inf), so the
-//     hot path needs no range test.
-// Error budget of the fma form against the reference's real-number quotient (u = 2^-53,
-// S = (|r| + |o| + 2) / res, L = range / res <= S): rounding of r - o, of 1/res and of their
-// product <= 3 u S; cos * 1/res carries the 2-ulp sincos, 1/res and one rounding <= 6 u L;
-// the fma rounds once <= u S; the reference's own four roundings <= 3.5 u S  =>
-// |dq| <= 2^-52 * (6.75 S + 0.65 (|yaw| + 9) / res) (angle terms as for expand_beam), against
-// tol = 2^-47 * (S + (|yaw| + 9) / res): a 4.7x margin on the first term, 49x on the second.
-struct LeanFrame {
-    double q0x, q0y;      // screened start quotients (NOT re-evaluated: they only seed the fma)
-    double tolx, toly;    // screening tolerances; +inf = always take the exact path
-    double ci, si;        // cos(yaw) / res, sin(yaw) / res
-    int x0, y0;           // start cell (:142), exact
-};
-
-template <class FastSinCos>
-OCC_HD void lean_frame(const Geom& g, double rx, double ry, double ryaw, const FastSinCos& fsc, LeanFrame* F) {
-    double tolx = screening_tolerance(rx, g.ox, ryaw, g.inv_res);
-    double toly = screening_tolerance(ry, g.oy, ryaw, g.inv_res);
-    const double q0x = OCC_DMUL(OCC_DADD(rx, -g.ox), g.inv_res);
-    const double q0y = OCC_DMUL(OCC_DADD(ry, -g.oy), g.inv_res);
-    double ex = q0x, ey = q0y;
-    if (near_cell_boundary(q0x, tolx)) ex = cell_quotient(rx, g.ox, g.res);               // :142
-    if (near_cell_boundary(q0y, toly)) ey = cell_quotient(ry, g.oy, g.res);
-    F->x0 = trunc_cell(ex);                  // in range: the caller binned this packet by this very cell
-    F->y0 = trunc_cell(ey);
-    const double lim = OCC_CELL_LIMIT - (OCC_MAX_DIST_M * g.inv_res + 4.0);
-    if (!(fabs(q0x) < lim && fabs(q0y) < lim)) { tolx = INFINITY; toly = INFINITY; }
-    F->q0x = q0x; F->q0y = q0y; F->tolx = tolx; F->toly = toly;
-    double s0, c0;
-    fsc(ryaw, &s0, &c0);
-    F->ci = OCC_DMUL(c0, g.inv_res);
-    F->si = OCC_DMUL(s0, g.inv_res);
-}
-
-OCC_HD bool beam_hit(float dist_f32, double* range) {
-    const double dist = (double)dist_f32;
-    const bool hit = (OCC_MIN_DIST_M < dist) && (dist <= OCC_MAX_DIST_M);     // :888 (false for NaN)
-    *range = hit ? dist : OCC_MAX_DIST_M;                                      // :900 reduces to MAX for every non-hit
-    return hit;
-}
-
-// The reference's own evaluation of a beam's end cell (:887-891 | :898-902, :143): true angle,
-// double-double sin/cos, true division.  False when the cell is beyond the +-2^30 limit.
-template <class FastSinCos>
-OCC_HD bool exact_end_cell(const Geom& g, double rx, double ry, double ryaw, int sensor, double range, const FastSinCos& fsc,
-                           int* x1, int* y1) {
-    const double ang = OCC_DADD(ryaw, sensor_angle(sensor));              // :887
-    double s2, c2;
-    if (!sincos_dd(ang, &s2, &c2)) fsc(ang, &s2, &c2);
-    const double qx = cell_quotient(OCC_DADD(rx, OCC_DMUL(range, c2)), g.ox, g.res);   // :890 | :901, :143
-    const double qy = cell_quotient(OCC_DADD(ry, OCC_DMUL(range, s2)), g.oy, g.res);   // :891 | :902
-    if (!(quotient_in_range(qx) && quotient_in_range(qy))) return false;
-    *x1 = trunc_cell(qx);
-    *y1 = trunc_cell(qy);
-    return true;
-}
-
-// Sensor s of a lean frame on the host (the kernels inline the same steps around their walk):
-// (csi, sni) = direction of sensor s over res, as quarter turns of (ci, si).
-template <class FastSinCos>
-OCC_HD void lean_beam(const Geom& g, const LeanFrame& F, double rx, double ry, double ryaw, int s, float dist,
-                      const FastSinCos& fsc, Beam* b) {
-    const double sni = s == 0 ? F.si : (s == 1 ? F.ci : (s == 2 ? -F.si : -F.ci));
-    const double csi = s == 0 ? F.ci : (s == 1 ? -F.si : (s == 2 ? -F.ci : F.si));
-    double range;
-    b->hit = beam_hit(dist, &range) ? 1 : 0;
-    b->x0 = F.x0; b->y0 = F.y0; b->x1 = 0; b->y1 = 0; b->slow = 0; b->valid = 1;
-    const double qx = OCC_DFMA(range, csi, F.q0x), qy = OCC_DFMA(range, sni, F.q0y);
-    if (near_cell_boundary(qx, F.tolx) || near_cell_boundary(qy, F.toly)) {
-        b->slow = 1;
-        b->valid = exact_end_cell(g, rx, ry, ryaw, s, range, fsc, &b->x1, &b->y1) ? 1 : 0;
-    } else {
-        b->x1 = trunc_cell(qx);
-        b->y1 = trunc_cell(qy);
-    }
-}
-
 // Explicit world-space ray -> beam (OccupancyGrid.update_ray's two world_to_grid calls, :142-143).
 OCC_HD void ray_to_beam(const Geom& g, double x0w, double y0w, double x1w, double y1w, int hit, Beam* b) {
     double q0x = cell_quotient(x0w, g.ox, g.res), q0y = cell_quotient(y0w, g.oy, g.res);

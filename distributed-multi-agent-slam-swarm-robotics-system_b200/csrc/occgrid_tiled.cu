@@ -609,22 +609,21 @@ __device__ __forceinline__ void smem_red(unsigned int addr, unsigned int v) {
 }
 
 // Fast path of draw_beam_smem / count_beam_smem: both end points inside the window, dmaj <= 32.
-// a = 32-bit shared-space BYTE address of the start cell (computed once per packet), dmaj =
-// max(|ddx|, |ddy|), mask_tab = shared-space address of the walk-mask table.
+// win = 32-bit shared-space address of the window; (x, y) window-local start cell.
 //   kAdd = false: atomicMax of `v_free` on every cell but the last, `v_free | 1` on the last if hit
 //   kAdd = true : += 1 on every cell but the last, += 0x10000 on the last if hit (count mode)
-// After dmaj steps the running address IS the end cell, so the hit stamp needs no address of its own.
 template <bool kAdd>
-__device__ __forceinline__ void walk_beam_masked(unsigned int a, int pitch, int ddx, int ddy, int dmaj,
-                                                 unsigned int v_free, bool hit, bool skip_first, unsigned int mask_tab) {
+__device__ __forceinline__ void walk_beam_masked(unsigned int win, int pitch, int x, int y, int ddx, int ddy,
+                                                 unsigned int v_free, bool hit, bool skip_first, const unsigned int* s_mask) {
     const int dx = abs(ddx), dy = abs(ddy);
     const bool xmajor = dx >= dy;
-    const int dmin = xmajor ? dy : dx;
+    const int dmaj = xmajor ? dx : dy, dmin = xmajor ? dy : dx;
     const int sx4 = ddx > 0 ? 4 : -4;
     const int sy4 = (ddy > 0 ? pitch : -pitch) * 4;
     const int step_maj = xmajor ? sx4 : sy4, step_min = xmajor ? sy4 : sx4;
-    unsigned int mask;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(mask) : "r"(mask_tab + (unsigned int)(dmaj * (dmaj + 1) / 2 + dmin) * 4u));
+    unsigned int mask = s_mask[dmaj * (dmaj + 1) / 2 + dmin];
+    unsigned int a = win + (unsigned int)(y * pitch + x) * 4u;
+    const unsigned int a_end = a + (unsigned int)((ddy * pitch + ddx) * 4);
     int rem = dmaj;                                   // cells still to mark FREE (the end cell is not one of them)
     if (rem > 0) {
         if (!skip_first) smem_red<kAdd>(a, v_free);   // the start cell is overwritten by a later beam of the packet otherwise
@@ -657,16 +656,7 @@ __device__ __forceinline__ void walk_beam_masked(unsigned int a, int pitch, int 
         a += step_maj + ((mask & 1u) ? step_min : 0);
         mask >>= 1;
     }
-    if (hit && !(dmaj == 0 && skip_first && !kAdd)) smem_red<kAdd>(a, kAdd ? 0x10000u : (v_free | 1u));
-}
-
-// The exact re-evaluation of a beam's end cell, out of line: it runs for a few beams in a million
-// and must not sit in the instruction stream of the walk.  Re-reads the pose from the record.
-__device__ __noinline__ bool exact_end_cell_of(double ox, double oy, double res, const PoseRec* __restrict__ rec, int sensor,
-                                                double range, int* x1, int* y1) {
-    Geom g;
-    g.ox = ox; g.oy = oy; g.res = res;
-    return exact_end_cell(g, rec->rx, rec->ry, (double)rec->yaw, sensor, range, LibSinCos(), x1, y1);
+    if (hit && !(dmaj == 0 && skip_first && !kAdd)) smem_red<kAdd>(a_end, kAdd ? 0x10000u : (v_free | 1u));
 }
 
 // ---- route work item (multi-GPU row bands, fused into the persistent raycast kernel) -----------
@@ -931,45 +921,39 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
     if (kRoute && threadIdx.x == 0) s_job = job;
     build_walk_masks(s_mask);                      // both visible after the first __syncthreads of the loop below
     const unsigned int win_addr = (unsigned int)__cvta_generic_to_shared(s_win);
-    const unsigned int mask_tab = (unsigned int)__cvta_generic_to_shared(s_mask);
     const unsigned int n_items = have_items ? hdr->n_items : 0u;
     // Unified queue: raycast items of THIS batch and route items of the NEXT one, interleaved in
     // proportion, so the NVLink traffic is spread over the whole kernel and overlaps the walks.
     const unsigned int n_route = kRoute ? job.n_route_items : 0u;
     const unsigned int n_total = n_items + n_route;
     const int side = tg.win_side, pitch = tg.pitch, words = side * pitch;
-    // updates, slowpath, owned updates of this thread: 32 bits are ample (a launch spreads at most
-    // 2^31 packets x 4 beams x <= 33 cells over >= 37 888 threads), widened when the kernel ends
-    unsigned int c[3] = {0u, 0u, 0u};
+    unsigned long long c[3] = {0, 0, 0};     // updates, slowpath, owned updates
     RouteStats rs = {0u, 0u};                // routed share, packed (see RouteStats)
-    // The queue position of the NEXT item is fetched while the current one is processed (the
-    // atomic's round trip to L2 is off the critical path), and the window is zeroed by the flush
-    // itself: an item costs two CTA barriers and no separate clearing pass.
+    // Work queue: the position of the next item is claimed while the current one is flushed (the
+    // atomic's round trip to L2 is off the critical path), and without route items the flush
+    // itself leaves the window clean: an item costs two CTA barriers and no clearing pass.
     __shared__ unsigned int s_next[2];
     if (threadIdx.x == 0) s_next[0] = atomicAdd(&hdr->work_counter, 1u);
     for (int i = threadIdx.x; i < words; i += kTT) s_win[i] = 0u;
-    bool window_dirty = false;               // a route item used the window as scratch
     __syncthreads();
     for (int turn = 0;; turn ^= 1) {
         unsigned int it = s_next[turn];
         if (it >= n_total) break;
-        if (threadIdx.x == 0) s_next[turn ^ 1] = atomicAdd(&hdr->work_counter, 1u);   // read after this item's barriers
         if (kRoute) {
             // r(i) = floor(i * n_route / n_total) route items precede queue position i
             const unsigned int r0 = (unsigned int)(((unsigned long long)it * n_route) / n_total);
             const unsigned int r1 = (unsigned int)(((unsigned long long)(it + 1) * n_route) / n_total);
             if (r1 > r0) {
+                if (threadIdx.x == 0) s_next[turn ^ 1] = atomicAdd(&hdr->work_counter, 1u);   // a route item is short
                 rs = route_item(s_job, r0, s_win, s_route, rs);
-                window_dirty = true;
                 __syncthreads();
                 continue;
             }
             it -= r0;
-            if (window_dirty) {
-                for (int i = threadIdx.x; i < words; i += kTT) s_win[i] = 0u;
-                window_dirty = false;
-                __syncthreads();
-            }
+            // route items use the window as scratch and outnumber the raycast items: clear it here,
+            // in full, and let the flush below leave it alone
+            for (int i = threadIdx.x; i < words; i += kTT) s_win[i] = 0u;
+            __syncthreads();
         }
         const uint4 item = items[it];
         const int ttx = item.x % tg.tiles_x, tty = item.x / tg.tiles_x;
@@ -978,55 +962,45 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
         const int wy0 = g.win_y0 - tg.pad + (tty << kTileShift) - tg.reach;
         for (unsigned int r = item.y + threadIdx.x; r < item.z; r += kTT) {
             const unsigned int idx = bins[r];
-            const PoseRec* __restrict__ rp = recs + idx;
-            const PoseRec rec = *rp;
+            const PoseRec rec = recs[idx];
             const unsigned int k = ordinals_in_records ? rec.k : idx;   // packet ordinal in this batch
-            LeanFrame F;                                                 // the start cell is the one this packet was binned by
-            lean_frame(g, rec.rx, rec.ry, (double)rec.yaw, LibSinCos(), &F);
+            PacketFrame F;
+            packet_frame(g, rec.rx, rec.ry, (double)rec.yaw, LibSinCos(), &F);
             const bool owned = F.x0 >= g.win_x0 && F.x0 < g.win_x0 + g.win_w && F.y0 >= g.win_y0 && F.y0 < g.win_y0 + g.win_h;
             const int lx = F.x0 - wx0, ly = F.y0 - wy0;
-            // how far a beam may reach from the start cell and stay on the table-driven path:
-            // inside the window on every side, and no longer than the mask table (negative = never)
-            const int margin = min(min(min(lx, ly), min(side - 1 - lx, side - 1 - ly)), kMaskMaxLen);
-            const unsigned int a0 = win_addr + (unsigned int)(ly * pitch + lx) * 4u;
-            unsigned int pc = 0;                                         // cells of this packet's beams
+            const unsigned int us = (unsigned int)side;
             bool later_writes_first = false;
             // ONE copy of the expansion + walk code, looped over the four sensors (last sensor first:
             // only the last beam that writes the shared start cell has to touch it).  Unrolling it
-            // four times made the kernel 110 KB of SASS and instruction-fetch bound.  The direction
-            // of sensor 3 (yaw - pi/2, :66) is (sin, -cos); every further sensor is a quarter turn back.
-            double cs_next = F.si, sn_next = -F.ci;
+            // four times made the kernel 110 KB of SASS and instruction-fetch bound.
 #pragma unroll 1
             for (int s = 3; s >= 0; --s) {
-                const double cs = cs_next, sn = sn_next;
-                cs_next = sn; sn_next = -cs;
-                double range;
-                const bool hit = beam_hit(s == 0 ? rec.d[0] : (s == 1 ? rec.d[1] : (s == 2 ? rec.d[2] : rec.d[3])), &range);
-                const double qx = OCC_DFMA(range, cs, F.q0x), qy = OCC_DFMA(range, sn, F.q0y);
-                int x1, y1;
-                if (near_cell_boundary(qx, F.tolx) || near_cell_boundary(qy, F.toly)) {
-                    c[1] += 1u;
-                    if (!exact_end_cell_of(g.ox, g.oy, g.res, rp, s, range, &x1, &y1)) continue;
-                } else {
-                    x1 = trunc_cell(qx);
-                    y1 = trunc_cell(qy);
-                }
-                const int ddx = x1 - F.x0, ddy = y1 - F.y0;
-                const int dmaj = max(abs(ddx), abs(ddy));                // the beam has dmaj + 1 cells
-                pc += (unsigned int)dmaj + 1u;
+                Beam b;
+                expand_beam_of(g, F, s, s == 0 ? rec.d[0] : (s == 1 ? rec.d[1] : (s == 2 ? rec.d[2] : rec.d[3])), LibSinCos(), &b);
+                if (!b.valid) continue;
+                const int cells = beam_cells(b);
+                c[0] += cells;
+                c[1] += b.slow;
+                if (owned) c[2] += cells;
+                const int ddx = b.x1 - b.x0, ddy = b.y1 - b.y0;
+                const bool fast = (unsigned int)lx < us && (unsigned int)ly < us && (unsigned int)(lx + ddx) < us &&
+                                  (unsigned int)(ly + ddy) < us && cells <= kMaskMaxLen + 1;
                 if (kCounts) {
-                    if (dmaj <= margin) walk_beam_masked<true>(a0, pitch, ddx, ddy, dmaj, 1u, hit, false, mask_tab);
-                    else count_beam_smem(s_win, side, pitch, lx, ly, ddx, ddy, hit);
+                    if (fast) walk_beam_masked<true>(win_addr, pitch, lx, ly, ddx, ddy, 1u, b.hit != 0, false, s_mask);
+                    else count_beam_smem(s_win, side, pitch, lx, ly, ddx, ddy, b.hit != 0);
                 } else {
                     const unsigned int stamp = (k * 4u + (unsigned int)s + 1u) << 1;
-                    if (dmaj <= margin) walk_beam_masked<false>(a0, pitch, ddx, ddy, dmaj, stamp, hit, later_writes_first, mask_tab);
-                    else draw_beam_smem(s_win, side, pitch, lx, ly, ddx, ddy, stamp, hit, later_writes_first);
+                    if (fast) walk_beam_masked<false>(win_addr, pitch, lx, ly, ddx, ddy, stamp, b.hit != 0, later_writes_first, s_mask);
+                    else draw_beam_smem(s_win, side, pitch, lx, ly, ddx, ddy, stamp, b.hit != 0, later_writes_first);
                 }
-                later_writes_first = later_writes_first || dmaj > 0 || hit;
+                later_writes_first = later_writes_first || (cells > 1 || b.hit);
             }
-            c[0] += pc;
-            if (owned) c[2] += pc;
         }
+        // Bind the next queue position late — a raycast item is long, and an item claimed early
+        // waits for this CTA while others idle at the end of the queue — but keep the atomic's round
+        // trip off the critical path: it is issued here and consumed after the flush.
+        unsigned int next_pos = 0u;
+        if (threadIdx.x == 0) next_pos = atomicAdd(&hdr->work_counter, 1u);
         __syncthreads();
         // flush + clear: window rows are contiguous in the stamp plane -> coalesced reductions.  Every
         // touched word is zeroed on the way out (cells outside the grid window included: they are
@@ -1042,7 +1016,7 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
                 for (int lx = lane; lx < side; lx += 32) {
                     const unsigned int v = row[lx];
                     if (!v) continue;
-                    row[lx] = 0u;
+                    if (!kRoute) row[lx] = 0u;
                     if (!(row_in && lx >= lx_lo && lx < lx_hi)) continue;
                     if (kCounts)     // {miss, hit} int32 pair of the cell: one 64-bit add (the halves cannot carry into each other)
                         atomicAdd(reinterpret_cast<unsigned long long*>(stamps) + ((size_t)(wy0 + ly - g.win_y0) * g.win_w + (wx0 - g.win_x0) + lx),
@@ -1052,6 +1026,7 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
                 }
             }
         }
+        if (threadIdx.x == 0) s_next[turn ^ 1] = next_pos;
         __syncthreads();
     }
     if (kRoute && job.counters) {

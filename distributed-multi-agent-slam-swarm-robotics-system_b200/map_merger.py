@@ -517,7 +517,9 @@ class MapMerger:
         v = self.map_resolution
         state = (ctypes.c_int32 * 2)()
         stats = {'callbacks': len(order), 'rebuilds': 0, 'rebounds': 0, 'polls': 0}
-        cursor, burst = 0, 4
+        # a launch stops by itself at the first callback that needs the host, so a burst only bounds
+        # how far the launch queue runs ahead: polls (a stream sync each) are what it costs
+        cursor, burst = 0, 64
         while cursor < len(order):
             c = self._cloud
             k = min(burst, len(order) - cursor)
@@ -528,9 +530,9 @@ class MapMerger:
             _native.check(lib.mapmerge_chain_poll(ws.data_ptr(), dims.ctypes.data, n_agents, state, self._stream()), 'mapmerge_chain_poll')
             stats['polls'] += 1
             cursor, stalled = int(state[0]), int(state[1])
-            if stalled == 0:
-                burst = min(burst * 2, 64)
-            elif stalled == 1:                   # the lattice moved: full filter + new voxel map
+            if stalled == 0:                     # the burst ran through
+                continue
+            if stalled == 1:                   # the lattice moved: full filter + new voxel map
                 sp = self._spare
                 rc = lib.mapmerge_chain_rebuild(ws.data_ptr(), dims.ctypes.data, n_agents, stage.x.data_ptr(), stage.y.data_ptr(),
                                                 offs.data_ptr(), order[cursor], v, c.x.data_ptr(), c.y.data_ptr(), c.capacity,
@@ -541,7 +543,6 @@ class MapMerger:
                 self._cloud, self._spare = self._spare, self._cloud
                 stats['rebuilds'] += 1
                 cursor += 1
-                burst = 8
             elif stalled == 3:                   # min corner may have moved inwards: exact bounds first
                 rc = lib.mapmerge_chain_rebounds(ws.data_ptr(), dims.ctypes.data, n_agents, c.x.data_ptr(), c.y.data_ptr(),
                                                  c.count.data_ptr(), self._stream())

@@ -48,9 +48,7 @@ void hh_expand_packets(const uint8_t* pkts, int64_t n, int stride, const int32_t
     g.ox = ox; g.oy = oy; g.res = res; g.inv_res = 1.0 / res;
     g.size_x = g.size_y = 1 << 30;
     g.win_x0 = g.win_y0 = 0; g.win_w = g.win_h = 1 << 30;
-    // mode bit 4: the lean form the tiled kernels use (lean_frame + lean_beam) instead of expand_packet
-    const bool lean = (mode & 16) != 0;
-    PerturbedSinCos fsc{mode & 15};
+    PerturbedSinCos fsc{mode};
     for (int64_t k = 0; k < n; ++k) {
         double rx, ry, ryaw;
         float dist[4];
@@ -60,13 +58,7 @@ void hh_expand_packets(const uint8_t* pkts, int64_t n, int stride, const int32_t
         std::memset(o, 0, 28 * sizeof(int32_t));
         if (st != occ::PKT_OK) continue;
         occ::Beam b[4];
-        if (lean) {
-            occ::LeanFrame F;
-            occ::lean_frame(g, rx, ry, ryaw, fsc, &F);
-            for (int s = 0; s < 4; ++s) occ::lean_beam(g, F, rx, ry, ryaw, s, dist[s], fsc, &b[s]);
-        } else {
-            occ::expand_packet(g, rx, ry, ryaw, dist, fsc, b);
-        }
+        occ::expand_packet(g, rx, ry, ryaw, dist, fsc, b);
         for (int s = 0; s < 4; ++s) {
             o[s * 7 + 0] = b[s].x0; o[s * 7 + 1] = b[s].y0; o[s * 7 + 2] = b[s].x1; o[s * 7 + 3] = b[s].y1;
             o[s * 7 + 4] = b[s].hit; o[s * 7 + 5] = b[s].valid; o[s * 7 + 6] = b[s].slow;

@@ -40,7 +40,8 @@ constexpr int kTT = 256;             // threads per CTA
 // tile's hot cells).
 constexpr int kChunkPk = 2048;       // largest work item
 constexpr int kChunkMin = 256;       // smallest: one packet per thread
-constexpr int kItemsPerCta = 3;       // raycast of configs[1]: 3 -> 0.202 ms, 5 -> 0.220, 8 -> 0.235, 12 -> 0.263
+constexpr int kItemsPerCta = 3;       // raycast of configs[1]: 3 -> 0.202 ms, 5 -> 0.220, 8 -> 0.235, 12 -> 0.263; cutting only the
+                                      // last quarter of the queue 4x / 8x finer: 0.201 / 0.215 against 0.198
 constexpr int kMaxStrideT = 64;
 constexpr int kMaxWindowBytes = 100 * 1024;   // smem window budget (two CTAs per SM at least)
 
@@ -905,11 +906,22 @@ __device__ __noinline__ RouteStats route_item(const RouteJob& J, unsigned int it
     return st_in;
 }
 
+// Route items that precede position i of the unified work queue (see k_home_raycast): half of them
+// are interleaved with the raycast items, half close the queue.  Measured (fused kernel, bit-exact
+// throughout): all interleaved 0.343 ms at N = 2 / 0.396 at N = 8; a quarter at the end 0.323 / -;
+// half 0.315 / 0.386; all at the end 0.311 / 0.409 (the route-only phase is NVLink-bound at N = 8).
+#define OCC_ROUTE_TAIL_DIV 2
+__device__ __forceinline__ unsigned int route_items_before(unsigned int i, unsigned int n_items, unsigned int n_route) {
+    const unsigned int tail = n_items ? n_route / OCC_ROUTE_TAIL_DIV : 0u;      // route items kept for the end of the queue
+    const unsigned int n_body = n_route - tail, n_head = n_items + n_body;
+    if (i >= n_head) return n_body + (i - n_head);
+    return (unsigned int)(((unsigned long long)i * n_body) / n_head);
+}
+
+// Three CTAs per SM (80 registers): measured 0.204 ms against 0.248 (two CTAs, <= 128 registers)
+// and 0.256 (four CTAs, 64 registers with spills) on BASELINE configs[1].
 template <bool kCounts, bool kRoute>
-#ifndef OCC_RAYCAST_CTAS
-#define OCC_RAYCAST_CTAS 3
-#endif
-__global__ void __launch_bounds__(kTT, kRoute ? 3 : OCC_RAYCAST_CTAS)
+__global__ void __launch_bounds__(kTT, 3)
 k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHeader* __restrict__ hdr,
                const unsigned int* __restrict__ bins, const PoseRec* __restrict__ recs, int ordinals_in_records,
                unsigned int* __restrict__ stamps, uint64_t* counters, int have_items, const RouteJob job) {
@@ -940,9 +952,11 @@ k_home_raycast(Geom g, TileGeom tg, const uint4* __restrict__ items, TilePlanHea
         unsigned int it = s_next[turn];
         if (it >= n_total) break;
         if (kRoute) {
-            // r(i) = floor(i * n_route / n_total) route items precede queue position i
-            const unsigned int r0 = (unsigned int)(((unsigned long long)it * n_route) / n_total);
-            const unsigned int r1 = (unsigned int)(((unsigned long long)(it + 1) * n_route) / n_total);
+            // Route items precede queue position i: r(i) = floor(i * n_body / n_head) in the head of the
+            // queue (all raycast items + n_body route items, interleaved in proportion), then the
+            // remaining route items on their own: the queue ends with SHORT items, so no CTA starts
+            // a 2 048-packet raycast item while the others run dry.
+            const unsigned int r0 = route_items_before(it, n_items, n_route), r1 = route_items_before(it + 1u, n_items, n_route);
             if (r1 > r0) {
                 if (threadIdx.x == 0) s_next[turn ^ 1] = atomicAdd(&hdr->work_counter, 1u);   // a route item is short
                 rs = route_item(s_job, r0, s_win, s_route, rs);

@@ -137,3 +137,29 @@ def test_gpu_no_overlap_is_rejected(MM):
     assert np.array_equal(reg.transformation, np.eye(4))
     assert m.map_callback(far, 2) is None and m.global_pcd.shape[0] == k
     assert m.register(MM.make_grid_msg(np.full(n * n, -1, np.int8), n, n, res, 0.0, 0.0)) is None
+
+
+@pytest.mark.gpu
+def test_gpu_registration_of_a_cloud_larger_than_the_resident_grid(MM):
+    """150 k source points = ~590 virtual blocks of the loop kernel, more than the CTAs a B200 keeps
+    resident (444): the persistent grid strides over them, and the result must not depend on it —
+    same correspondences, iterations and transform as the oracle."""
+    import torch
+    n, res, origin = 1024, 0.05, (-25.6, -25.6)
+    r = np.random.default_rng(11)
+    g = np.where(r.random((n, n)) < 0.145, 100, 0).astype(np.int8)
+    lx, ly = MO.grid_to_points(g.ravel(), n, n, res, *origin)
+    assert lx.shape[0] > 444 * 256
+    T = MO.se2_matrix(0.011, -0.007, 0.0004)               # well inside the basin of a dense random cloud
+    gx, gy = MO.transform_points(lx, ly, T)
+    m = MM.MapMerger(registration='icp')
+    m._ensure_capacity(gx.shape[0] + 16)
+    m._cloud.x[:gx.shape[0]].copy_(torch.from_numpy(gx))
+    m._cloud.y[:gx.shape[0]].copy_(torch.from_numpy(gy))
+    m._cloud.count.fill_(gx.shape[0])
+    m._n_global = gx.shape[0]
+    reg = m.register(MM.make_grid_msg(g.ravel(), n, n, res, *origin), max_iteration=6)
+    Tw, fw, rw, iw = IO.registration_icp(lx, ly, gx, gy, max_iteration=6)
+    assert reg.correspondences == round(fw * lx.shape[0]) and reg.fitness == fw and reg.iterations == iw
+    assert abs(reg.inlier_rmse - rw) < 1e-9
+    assert np.allclose(reg.transformation, Tw, atol=1e-9)

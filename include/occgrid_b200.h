@@ -414,9 +414,11 @@ int mapmerge_chain_rebuild(void* d_chain, const int64_t* dims, int n_agents, con
  * list: cells of size `cell` (use max_correspondence_distance / 4) starting at (min_x, min_y),
  * cells_w x cells_h of them covering the target's bounds.  Exact nearest neighbours (squared
  * distance < max^2, ties by lowest target index), rigid fit in closed form, sums reduced in a
- * fixed order.  Runs stream-ordered without host round trips.
+ * fixed order.  Runs stream-ordered without host round trips: the iteration loop is one
+ * cooperative kernel (the device must support cooperative launch).
  * d_result (20 doubles): [0..15] transformation row-major, [16] fitness, [17] inlier_rmse,
- * [18] iterations run, [19] number of correspondences of the last evaluation. */
+ * [18] iterations run (-1: the loop kernel was aborted by a grid-barrier time-out),
+ * [19] number of correspondences of the last evaluation. */
 size_t mapmerge_icp_workspace_bytes(int64_t target_points, int64_t source_points, int32_t cells_w,
                                     int32_t cells_h);
 int mapmerge_icp_register(const double* d_sx, const double* d_sy, int64_t n_source,
